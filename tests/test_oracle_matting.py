@@ -1,0 +1,66 @@
+"""CPU: pin the Laplacian oracle.  v3 against COO triplets emitted by the reference's own
+compute_laplacian (tests/golden/v3_*.npz); v2 against v3 on the interior and against an independent
+per-window restatement, plus the invariants of SURVEY §4 (symmetric, L.1 = 0, PSD)."""
+import numpy as np
+import pytest
+
+from conftest import golden
+from oracle import matting
+
+
+@pytest.mark.parametrize("tag", ["a", "b", "c"])
+def test_v3_restatement_matches_reference_coo(tag):
+    g = golden("v3_%s.npz" % tag)
+    rows, cols, vals, shape = matting.v3_compute_laplacian(g["image"], float(g["eps"]), int(g["r"]))
+    assert np.array_equal(rows, g["rows"])          # sparsity pattern and emission order: bit-exact
+    assert np.array_equal(cols, g["cols"])
+    np.testing.assert_allclose(vals, g["vals"], rtol=0, atol=1e-9 * np.abs(g["vals"]).max())
+    H, W, _ = g["image"].shape
+    assert len(vals) == 81 * (H - 2) * (W - 2)
+    op = matting.V3Operator(g["image"], float(g["eps"]), 1)
+    np.testing.assert_allclose(op.matmul(g["x"]), g["Lx"], rtol=1e-9, atol=1e-9 * np.abs(g["Lx"]).max())
+
+
+@pytest.mark.parametrize("tag", ["a", "b", "c"])
+def test_v2_equals_v3_on_interior(tag):
+    g = golden("v3_%s.npz" % tag)
+    img = g["image"]
+    H, W, _ = img.shape
+    op2 = matting.V2Operator(img, float(g["eps"]), 1)
+    y2 = op2.matmul(g["x"]).reshape(H, W, 3)
+    y3 = g["Lx"].reshape(H, W, 3)
+    scale = np.abs(y3).max()
+    if H > 4 and W > 4:
+        assert np.abs(y2[2:-2, 2:-2] - y3[2:-2, 2:-2]).max() < 1e-9 * scale
+    assert np.abs(y2 - y3).max() > 1e-3 * scale      # the border ring differs
+
+
+@pytest.mark.parametrize("r", [1, 2])
+def test_v2_integral_image_equals_direct(r, synth):
+    H, W = 9, 11
+    img = synth.image(H, W, 5)[0].astype(np.float64)
+    x = np.random.default_rng(6).random((H * W, 3))
+    op = matting.V2Operator(img, 1e-7, r)
+    y = op.matmul(x)
+    yd = matting.v2_direct(img, x, 1e-7, r)
+    assert np.abs(y - yd).max() < 1e-9 * np.abs(yd).max()
+
+
+def test_v2_invariants(synth):
+    H, W = 7, 8
+    img = synth.image(H, W, 7)[0].astype(np.float64)
+    op = matting.V2Operator(img, 1e-5, 1)
+    L = op.matmul(np.eye(H * W))
+    assert np.abs(L - L.T).max() < 1e-10
+    assert np.abs(L @ np.ones(H * W)).max() < 1e-9
+    assert np.linalg.eigvalsh((L + L.T) / 2).min() > -1e-9
+    assert op.means.shape == (H, W, 3, 1) and op.delta_inv.shape == (H, W, 3, 3)
+    assert op.shape == (H * W, H * W)
+
+
+def test_v2_x_equals_image_is_tiny(synth):
+    """x = I (iteration 0): Lx is ~eps-small; this is the case that needs float64."""
+    img = synth.image(16, 16, 8)[0].astype(np.float64)
+    op = matting.V2Operator(img, 1e-7, 1)
+    y = op.matmul(img.reshape(-1, 3))
+    assert np.abs(y).max() < 1e-4
