@@ -1,0 +1,153 @@
+// elementwise.cu -- HBM-bound streaming kernels: Adam+clip, content MSE, mask resize, axpby.
+//
+// Replaces   style_transfer.py:321-326,342-343  (tf.optimizers.Adam.apply_gradients + clip_by_value)
+//            components/loss.py:90-92           (content MSE and its gradient)
+//            components/loss.py:112-113         (tf.image.resize of the masks)
+#include "common.cuh"
+
+namespace adpst {
+
+static inline unsigned grid_for(size_t work_items, int threads, int per_sm = 8) {
+    const size_t want = (work_items + threads - 1) / threads;
+    const size_t cap = size_t(num_sms()) * per_sm;
+    return unsigned(want < cap ? (want ? want : 1) : cap);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Adam (TF/Keras flavour) + clip to [0,1].  28 B per element: read g,m,v,x; write m,v,x.
+// state[0] = completed steps t, state[1] = CTA ticket.  The last CTA to finish bumps t, so the launch
+// can sit inside a CUDA graph and be replayed.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void adam_one(float& x, float g, float& m, float& v, float b1, float b2, float alpha,
+                                         float eps) {
+    m = b1 * m + (1.0f - b1) * g;
+    v = b2 * v + (1.0f - b2) * g * g;
+    const float nx = x - alpha * m / (sqrtf(v) + eps);
+    x = fminf(fmaxf(nx, 0.0f), 1.0f);
+}
+
+__global__ void __launch_bounds__(256)
+adam_clip_kernel(float* __restrict__ x, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
+                 size_t n, int32_t* __restrict__ state, float lr, float b1, float b2, float eps) {
+    const int t = state[0] + 1;
+    const float alpha = float(double(lr) * sqrt(1.0 - pow(double(b2), double(t))) / (1.0 - pow(double(b1), double(t))));
+    const size_t n4 = n / 4;
+    const size_t stride = size_t(gridDim.x) * blockDim.x;
+    float4* x4 = reinterpret_cast<float4*>(x);
+    const float4* g4 = reinterpret_cast<const float4*>(g);
+    float4* m4 = reinterpret_cast<float4*>(m);
+    float4* v4 = reinterpret_cast<float4*>(v);
+    for (size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n4; i += stride) {
+        float4 xx = x4[i], mm = m4[i], vv = v4[i];
+        const float4 gg = __ldg(g4 + i);
+        adam_one(xx.x, gg.x, mm.x, vv.x, b1, b2, alpha, eps);
+        adam_one(xx.y, gg.y, mm.y, vv.y, b1, b2, alpha, eps);
+        adam_one(xx.z, gg.z, mm.z, vv.z, b1, b2, alpha, eps);
+        adam_one(xx.w, gg.w, mm.w, vv.w, b1, b2, alpha, eps);
+        x4[i] = xx; m4[i] = mm; v4[i] = vv;
+    }
+    if (blockIdx.x == 0) {
+        for (size_t i = n4 * 4 + threadIdx.x; i < n; i += blockDim.x) adam_one(x[i], g[i], m[i], v[i], b1, b2, alpha, eps);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        const int ticket = atomicAdd(&state[1], 1);
+        if (ticket == int(gridDim.x) - 1) { state[1] = 0; state[0] = t; }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// content layer: loss += scale * mean((t-o)^2); dOut (=|+=) scale * 2 (o-t) / n
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+content_kernel(const float* __restrict__ tgt, const float* __restrict__ out, size_t n, double scale,
+               double* __restrict__ loss, float* __restrict__ dOut, int accumulate) {
+    __shared__ double red[32];
+    const float gs = float(2.0 * scale / double(n));
+    double acc = 0.0;
+    const size_t stride = size_t(gridDim.x) * blockDim.x;
+    for (size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const float d = out[i] - tgt[i];
+        acc += double(d) * double(d);
+        if (dOut) dOut[i] = accumulate ? dOut[i] + gs * d : gs * d;
+    }
+    acc = block_sum<double>(acc, red);
+    if (threadIdx.x == 0 && loss) atomicAdd(loss, acc * scale / double(n));
+}
+
+// ---------------------------------------------------------------------------------------------
+// bilinear resize, half-pixel centres, no antialias (tf.image.resize default == F.interpolate(bilinear,
+// align_corners=False)).  Single channel.  Runs once per mask at set-up, not in the loop.
+// ---------------------------------------------------------------------------------------------
+__global__ void resize_bilinear_kernel(const float* __restrict__ src, int Hs, int Ws, float* __restrict__ dst, int Hd,
+                                       int Wd) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x, i = blockIdx.y * blockDim.y + threadIdx.y;
+    if (i >= Hd || j >= Wd) return;
+    const double sy = fmax((i + 0.5) * (double(Hs) / Hd) - 0.5, 0.0);
+    const double sx = fmax((j + 0.5) * (double(Ws) / Wd) - 0.5, 0.0);
+    const int y0 = min(int(sy), Hs - 1), x0 = min(int(sx), Ws - 1);
+    const int y1 = min(y0 + 1, Hs - 1), x1 = min(x0 + 1, Ws - 1);
+    const double ly = sy - y0, lx = sx - x0;
+    const double v00 = src[size_t(y0) * Ws + x0], v01 = src[size_t(y0) * Ws + x1];
+    const double v10 = src[size_t(y1) * Ws + x0], v11 = src[size_t(y1) * Ws + x1];
+    const double top = v00 + (v01 - v00) * lx, bot = v10 + (v11 - v10) * lx;
+    dst[size_t(i) * Wd + j] = float(top + (bot - top) * ly);
+}
+
+__global__ void __launch_bounds__(256)
+axpby_kernel(float* __restrict__ out, const float* __restrict__ a, float alpha, const float* __restrict__ b, float beta,
+             size_t n) {
+    const size_t stride = size_t(gridDim.x) * blockDim.x;
+    for (size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride)
+        out[i] = alpha * a[i] + (b ? beta * b[i] : 0.0f);
+}
+
+}  // namespace adpst
+
+extern "C" {
+
+int adpst_adam_clip_step(float* x_dev, const float* grad_dev, float* m_dev, float* v_dev, size_t n, int32_t* state_dev,
+                         float lr, float beta1, float beta2, float epsilon, adpst_stream_t stream) {
+    using namespace adpst;
+    ADPST_REQUIRE(x_dev && grad_dev && m_dev && v_dev && state_dev, "adam_clip_step: NULL argument");
+    ADPST_REQUIRE((reinterpret_cast<uintptr_t>(x_dev) | reinterpret_cast<uintptr_t>(grad_dev) |
+                   reinterpret_cast<uintptr_t>(m_dev) | reinterpret_cast<uintptr_t>(v_dev)) % 16 == 0,
+                  "adam_clip_step: buffers must be 16-byte aligned");
+    if (n == 0) return ADPST_OK;
+    adam_clip_kernel<<<grid_for(n / 4 + 1, 256), 256, 0, as_stream(stream)>>>(x_dev, grad_dev, m_dev, v_dev, n, state_dev,
+                                                                              lr, beta1, beta2, epsilon);
+    ADPST_LAUNCH_CHECK();
+    return ADPST_OK;
+}
+
+int adpst_content_layer(const float* target_dev, const float* output_dev, size_t n, double scale, double* loss_dev,
+                        float* dOut_dev, int accumulate, adpst_stream_t stream) {
+    using namespace adpst;
+    ADPST_REQUIRE(target_dev && output_dev && n > 0, "content_layer: NULL or empty input");
+    content_kernel<<<grid_for(n, 256), 256, 0, as_stream(stream)>>>(target_dev, output_dev, n, scale, loss_dev, dOut_dev,
+                                                                    accumulate);
+    ADPST_LAUNCH_CHECK();
+    return ADPST_OK;
+}
+
+int adpst_resize_bilinear(const float* src_dev, int Hs, int Ws, float* dst_dev, int Hd, int Wd, adpst_stream_t stream) {
+    using namespace adpst;
+    ADPST_REQUIRE(src_dev && dst_dev && Hs > 0 && Ws > 0 && Hd > 0 && Wd > 0, "resize_bilinear: bad argument");
+    dim3 block(32, 8), grid((Wd + 31) / 32, (Hd + 7) / 8);
+    resize_bilinear_kernel<<<grid, block, 0, as_stream(stream)>>>(src_dev, Hs, Ws, dst_dev, Hd, Wd);
+    ADPST_LAUNCH_CHECK();
+    return ADPST_OK;
+}
+
+int adpst_axpby(float* out_dev, const float* a_dev, float alpha, const float* b_dev, float beta, size_t n,
+                adpst_stream_t stream) {
+    using namespace adpst;
+    ADPST_REQUIRE(out_dev && a_dev, "axpby: NULL argument");
+    if (n == 0) return ADPST_OK;
+    axpby_kernel<<<grid_for(n, 256), 256, 0, as_stream(stream)>>>(out_dev, a_dev, alpha, b_dev, beta, n);
+    ADPST_LAUNCH_CHECK();
+    return ADPST_OK;
+}
+
+}  // extern "C"

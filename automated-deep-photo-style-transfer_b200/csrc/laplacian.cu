@@ -1,0 +1,519 @@
+// laplacian.cu -- matrix-free matting Laplacian for sm_100a.
+//
+// Replaces   components/matting_v2.py:11-52,147-251   (He et al. "large kernel" operator, symmetric padding)
+//            components/matting_v3.py:27-102          (Levin et al. explicit COO, interior windows only)
+//            components/loss.py:157-161               (x^T L x)
+//
+// One stencil serves both variants.  For every window k (centre pixel k, (2r+1)^2 pixels)
+//     M_k = sum I I^T - s s^T / n + eps * Id        (= n * (Sigma_k + eps/n Id))
+//     a_k = M_k^-1 (sum I x^T - s t^T / n),   b_k = (t - a_k^T s) / n          s = sum I, t = sum x
+// and for every pixel i      y_i = cnt_i * x_i - sum_{k in w_i} (a_k^T I_i + b_k).
+//   v2: windows are centred on every pixel of the symmetric-padded image; the coefficient fields are
+//       symmetric-padded again (matting_v2.py:164-165).  Both pads together equal ONE symmetric pad of
+//       width 2r of I and x, because a_k, b_k are invariant under reflection of the window.  cnt_i = n.
+//   v3: only windows that lie fully inside the image exist (matting_v3.py:77); cnt_i = number of such windows
+//       that contain i.
+// Window statistics are recomputed from I every call (36 B/px of traffic instead of 72+).
+#include <type_traits>
+
+#include "common.cuh"
+
+namespace adpst {
+
+// ---------------------------------------------------------------------------------------------
+// per-window algebra
+// ---------------------------------------------------------------------------------------------
+// Inverse of the symmetric 3x3  [m0 m1 m2; m1 m3 m4; m2 m4 m5]  (same packing for the result).
+template <typename T>
+__device__ __forceinline__ void sym3_inverse(const T m[6], T inv[6]) {
+    const T c00 = m[3] * m[5] - m[4] * m[4];
+    const T c01 = m[2] * m[4] - m[1] * m[5];
+    const T c02 = m[1] * m[4] - m[2] * m[3];
+    const T c11 = m[0] * m[5] - m[2] * m[2];
+    const T c12 = m[1] * m[2] - m[0] * m[4];
+    const T c22 = m[0] * m[3] - m[1] * m[1];
+    const T det = m[0] * c00 + m[1] * c01 + m[2] * c02;
+    const T id = T(1) / det;
+    inv[0] = c00 * id; inv[1] = c01 * id; inv[2] = c02 * id;
+    inv[3] = c11 * id; inv[4] = c12 * id; inv[5] = c22 * id;
+}
+
+// Window moments from a (2R+1)^2 patch in shared memory.  `pI`, `px` point at the patch's top-left pixel,
+// `pitch` is the row pitch in elements (3 per pixel).
+// Output: mu[3], pbar[3] (means), M[6] (sum of centred I I^T, + eps on the diagonal), Rc[3][3] (sum of centred
+// I x^T; Rc[j][c], j = image channel, c = x channel).  float64 uses raw moments (products of float32-exact
+// inputs are exact in float64); float32 centres first, which is what keeps it usable.
+template <typename TIO, typename TC, int R>
+__device__ __forceinline__ void window_moments(const TIO* __restrict__ pI, const TIO* __restrict__ px, int pitch,
+                                               TC eps, TC mu[3], TC pbar[3], TC M[6], TC Rc[9]) {
+    constexpr int D = 2 * R + 1;
+    constexpr TC inv_n = TC(1) / TC(D * D);
+    TC s[3] = {0, 0, 0}, t[3] = {0, 0, 0};
+#pragma unroll
+    for (int i = 0; i < 6; ++i) M[i] = 0;
+#pragma unroll
+    for (int i = 0; i < 9; ++i) Rc[i] = 0;
+    if constexpr (std::is_same<TC, double>::value) {
+#pragma unroll
+        for (int dy = 0; dy < D; ++dy) {
+#pragma unroll
+            for (int dx = 0; dx < D; ++dx) {
+                const TIO* qi = pI + dy * pitch + dx * 3;
+                const TIO* qx = px + dy * pitch + dx * 3;
+                const TC i0 = qi[0], i1 = qi[1], i2 = qi[2];
+                const TC x0 = qx[0], x1 = qx[1], x2 = qx[2];
+                s[0] += i0; s[1] += i1; s[2] += i2;
+                t[0] += x0; t[1] += x1; t[2] += x2;
+                M[0] += i0 * i0; M[1] += i0 * i1; M[2] += i0 * i2;
+                M[3] += i1 * i1; M[4] += i1 * i2; M[5] += i2 * i2;
+                Rc[0] += i0 * x0; Rc[1] += i0 * x1; Rc[2] += i0 * x2;
+                Rc[3] += i1 * x0; Rc[4] += i1 * x1; Rc[5] += i1 * x2;
+                Rc[6] += i2 * x0; Rc[7] += i2 * x1; Rc[8] += i2 * x2;
+            }
+        }
+#pragma unroll
+        for (int c = 0; c < 3; ++c) { mu[c] = s[c] * inv_n; pbar[c] = t[c] * inv_n; }
+        M[0] -= s[0] * mu[0]; M[1] -= s[0] * mu[1]; M[2] -= s[0] * mu[2];
+        M[3] -= s[1] * mu[1]; M[4] -= s[1] * mu[2]; M[5] -= s[2] * mu[2];
+#pragma unroll
+        for (int j = 0; j < 3; ++j)
+#pragma unroll
+            for (int c = 0; c < 3; ++c) Rc[j * 3 + c] -= s[j] * pbar[c];
+    } else {
+#pragma unroll
+        for (int dy = 0; dy < D; ++dy) {
+#pragma unroll
+            for (int dx = 0; dx < D; ++dx) {
+                const TIO* qi = pI + dy * pitch + dx * 3;
+                const TIO* qx = px + dy * pitch + dx * 3;
+                s[0] += TC(qi[0]); s[1] += TC(qi[1]); s[2] += TC(qi[2]);
+                t[0] += TC(qx[0]); t[1] += TC(qx[1]); t[2] += TC(qx[2]);
+            }
+        }
+#pragma unroll
+        for (int c = 0; c < 3; ++c) { mu[c] = s[c] * inv_n; pbar[c] = t[c] * inv_n; }
+#pragma unroll
+        for (int dy = 0; dy < D; ++dy) {
+#pragma unroll
+            for (int dx = 0; dx < D; ++dx) {
+                const TIO* qi = pI + dy * pitch + dx * 3;
+                const TIO* qx = px + dy * pitch + dx * 3;
+                const TC i0 = TC(qi[0]) - mu[0], i1 = TC(qi[1]) - mu[1], i2 = TC(qi[2]) - mu[2];
+                const TC x0 = TC(qx[0]) - pbar[0], x1 = TC(qx[1]) - pbar[1], x2 = TC(qx[2]) - pbar[2];
+                M[0] += i0 * i0; M[1] += i0 * i1; M[2] += i0 * i2;
+                M[3] += i1 * i1; M[4] += i1 * i2; M[5] += i2 * i2;
+                Rc[0] += i0 * x0; Rc[1] += i0 * x1; Rc[2] += i0 * x2;
+                Rc[3] += i1 * x0; Rc[4] += i1 * x1; Rc[5] += i1 * x2;
+                Rc[6] += i2 * x0; Rc[7] += i2 * x1; Rc[8] += i2 * x2;
+            }
+        }
+    }
+    M[0] += eps; M[3] += eps; M[5] += eps;
+}
+
+// ---------------------------------------------------------------------------------------------
+// fused matvec:  y = y_scale * L x,   partial[block] = sum_tile x . (L x)
+// ---------------------------------------------------------------------------------------------
+template <int R> struct LapTile {
+    static constexpr int TH = 16, TW = 32;                   // output pixels per CTA
+    static constexpr int WH = TH + 2 * R, WW = TW + 2 * R;   // windows whose coefficients the tile needs
+    static constexpr int IH = TH + 4 * R, IW = TW + 4 * R;   // input pixels those windows read
+    static constexpr int NWIN = WH * WW;
+    static constexpr int THREADS = 256;
+    template <typename TIO, typename TC> static constexpr size_t smem_bytes() {
+        return size_t(12) * NWIN * sizeof(TC) + size_t(2) * IH * IW * 3 * sizeof(TIO) + 32 * sizeof(double);
+    }
+};
+
+template <typename TIO, typename TC, int R>
+__global__ void __launch_bounds__(LapTile<R>::THREADS)
+lap_matvec_kernel(const TIO* __restrict__ img, const TIO* __restrict__ x, TIO* __restrict__ y,
+                  double* __restrict__ partial, int H, int W, int mode, TC eps, TC y_scale) {
+    using T = LapTile<R>;
+    constexpr int D = 2 * R + 1;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    TC* sC = reinterpret_cast<TC*>(smem_raw);                                  // [12][NWIN]
+    double* sRed = reinterpret_cast<double*>(sC + 12 * T::NWIN);               // [32]
+    TIO* sI = reinterpret_cast<TIO*>(sRed + 32);                               // [IH][IW*3]
+    TIO* sX = sI + T::IH * T::IW * 3;
+
+    const int x0 = blockIdx.x * T::TW, y0 = blockIdx.y * T::TH;
+    const bool v2 = (mode == ADPST_LAP_V2);
+
+    // phase 0: stage I and x with a 2R halo (v2: symmetric reflection; v3: zeros outside, never used)
+    for (int i = threadIdx.x; i < T::IH * T::IW; i += T::THREADS) {
+        const int row = i / T::IW, col = i - row * T::IW;
+        int gy = y0 - 2 * R + row, gx = x0 - 2 * R + col;
+        bool ok = true;
+        if (v2) { gy = reflect_symmetric(gy, H); gx = reflect_symmetric(gx, W); }
+        else ok = (gy >= 0 && gy < H && gx >= 0 && gx < W);
+        TIO i0 = 0, i1 = 0, i2 = 0, p0 = 0, p1 = 0, p2 = 0;
+        if (ok) {
+            const size_t g = (size_t(gy) * W + gx) * 3;
+            i0 = img[g]; i1 = img[g + 1]; i2 = img[g + 2];
+            p0 = x[g];   p1 = x[g + 1];   p2 = x[g + 2];
+        }
+        sI[i * 3] = i0; sI[i * 3 + 1] = i1; sI[i * 3 + 2] = i2;
+        sX[i * 3] = p0; sX[i * 3 + 1] = p1; sX[i * 3 + 2] = p2;
+    }
+    __syncthreads();
+
+    // phase 1: coefficients (a_k: 9, b_k: 3) of every window the tile touches
+    for (int w = threadIdx.x; w < T::NWIN; w += T::THREADS) {
+        const int wy = w / T::WW, wx = w - wy * T::WW;
+        const int cy = y0 - R + wy, cx = x0 - R + wx;                          // window centre, image coords
+        const bool valid = v2 || (cy >= R && cy < H - R && cx >= R && cx < W - R);
+        TC a[9], b[3];
+        if (valid) {
+            TC mu[3], pbar[3], M[6], Rc[9], Mi[6];
+            const int off = (wy * T::IW + wx) * 3;
+            window_moments<TIO, TC, R>(sI + off, sX + off, T::IW * 3, eps, mu, pbar, M, Rc);
+            sym3_inverse(M, Mi);
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                a[0 * 3 + c] = Mi[0] * Rc[c] + Mi[1] * Rc[3 + c] + Mi[2] * Rc[6 + c];
+                a[1 * 3 + c] = Mi[1] * Rc[c] + Mi[3] * Rc[3 + c] + Mi[4] * Rc[6 + c];
+                a[2 * 3 + c] = Mi[2] * Rc[c] + Mi[4] * Rc[3 + c] + Mi[5] * Rc[6 + c];
+                b[c] = pbar[c] - (a[c] * mu[0] + a[3 + c] * mu[1] + a[6 + c] * mu[2]);
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < 9; ++i) a[i] = 0;
+            b[0] = b[1] = b[2] = 0;
+        }
+#pragma unroll
+        for (int i = 0; i < 9; ++i) sC[i * T::NWIN + w] = a[i];
+#pragma unroll
+        for (int c = 0; c < 3; ++c) sC[(9 + c) * T::NWIN + w] = b[c];
+    }
+    __syncthreads();
+
+    // phase 2: gather the (2R+1)^2 windows that contain each output pixel
+    double acc = 0.0;
+    for (int o = threadIdx.x; o < T::TH * T::TW; o += T::THREADS) {
+        const int oy = o / T::TW, ox = o - oy * T::TW;
+        const int gy = y0 + oy, gx = x0 + ox;
+        if (gy >= H || gx >= W) continue;
+        TC A[9], B[3];
+#pragma unroll
+        for (int i = 0; i < 9; ++i) A[i] = 0;
+        B[0] = B[1] = B[2] = 0;
+#pragma unroll
+        for (int dy = 0; dy < D; ++dy) {
+#pragma unroll
+            for (int dx = 0; dx < D; ++dx) {
+                const int w = (oy + dy) * T::WW + ox + dx;
+#pragma unroll
+                for (int i = 0; i < 9; ++i) A[i] += sC[i * T::NWIN + w];
+#pragma unroll
+                for (int c = 0; c < 3; ++c) B[c] += sC[(9 + c) * T::NWIN + w];
+            }
+        }
+        TC cnt = TC(D * D);
+        if (!v2) {
+            const int ylo = max(gy - R, R), yhi = min(gy + R, H - R - 1);
+            const int xlo = max(gx - R, R), xhi = min(gx + R, W - R - 1);
+            cnt = TC(max(yhi - ylo + 1, 0) * max(xhi - xlo + 1, 0));
+        }
+        const int pi = ((oy + 2 * R) * T::IW + ox + 2 * R) * 3;
+        const TC i0 = sI[pi], i1 = sI[pi + 1], i2 = sI[pi + 2];
+        const size_t g = (size_t(gy) * W + gx) * 3;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            const TC xc = sX[pi + c];
+            const TC yc = cnt * xc - (A[c] * i0 + A[3 + c] * i1 + A[6 + c] * i2 + B[c]);
+            acc += double(xc) * double(yc);
+            if (y != nullptr) y[g + c] = TIO(y_scale * yc);
+        }
+    }
+    if (partial != nullptr) {
+        const double tot = block_sum<double>(acc, sRed);
+        if (threadIdx.x == 0) partial[blockIdx.y * gridDim.x + blockIdx.x] = tot;
+    }
+}
+
+__global__ void sum_partials_kernel(const double* __restrict__ partial, int n, double* __restrict__ out) {
+    __shared__ double red[32];
+    double a = 0.0;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) a += partial[i];   // fixed order: deterministic
+    a = block_sum<double>(a, red);
+    if (threadIdx.x == 0) *out = a;
+}
+
+// ---------------------------------------------------------------------------------------------
+// v2 coefficient fields (matting_v2.py:49-52): means = s/n, delta_inv = (Sigma + eps/n Id)^-1 = n M^-1
+// ---------------------------------------------------------------------------------------------
+template <typename TIO, typename TC, int R>
+__global__ void lap_coeff_kernel(const TIO* __restrict__ img, TIO* __restrict__ means, TIO* __restrict__ dinv,
+                                 int H, int W, TC eps) {
+    constexpr int D = 2 * R + 1;
+    const int gx = blockIdx.x * blockDim.x + threadIdx.x, gy = blockIdx.y * blockDim.y + threadIdx.y;
+    if (gx >= W || gy >= H) return;
+    TC s[3] = {0, 0, 0}, Q[6] = {0, 0, 0, 0, 0, 0};
+    TC v[D * D][3];
+#pragma unroll
+    for (int dy = 0; dy < D; ++dy) {
+        const int yy = reflect_symmetric(gy - R + dy, H);
+#pragma unroll
+        for (int dx = 0; dx < D; ++dx) {
+            const int xx = reflect_symmetric(gx - R + dx, W);
+            const size_t g = (size_t(yy) * W + xx) * 3;
+#pragma unroll
+            for (int c = 0; c < 3; ++c) { v[dy * D + dx][c] = TC(img[g + c]); s[c] += v[dy * D + dx][c]; }
+        }
+    }
+    constexpr TC inv_n = TC(1) / TC(D * D);
+    const TC mu[3] = {s[0] * inv_n, s[1] * inv_n, s[2] * inv_n};
+#pragma unroll
+    for (int k = 0; k < D * D; ++k) {
+        const TC a = v[k][0] - mu[0], b = v[k][1] - mu[1], c = v[k][2] - mu[2];
+        Q[0] += a * a; Q[1] += a * b; Q[2] += a * c; Q[3] += b * b; Q[4] += b * c; Q[5] += c * c;
+    }
+    Q[0] += eps; Q[3] += eps; Q[5] += eps;
+    TC Mi[6];
+    sym3_inverse(Q, Mi);
+    const TC n = TC(D * D);
+    const size_t p = size_t(gy) * W + gx;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) means[p * 3 + c] = TIO(mu[c]);
+    TIO* o = dinv + p * 9;
+    o[0] = TIO(n * Mi[0]); o[1] = TIO(n * Mi[1]); o[2] = TIO(n * Mi[2]);
+    o[3] = TIO(n * Mi[1]); o[4] = TIO(n * Mi[3]); o[5] = TIO(n * Mi[4]);
+    o[6] = TIO(n * Mi[2]); o[7] = TIO(n * Mi[4]); o[8] = TIO(n * Mi[5]);
+}
+
+// ---------------------------------------------------------------------------------------------
+// v3 COO export (matting_v3.py:87-100): window-major, then (a, b) row-major; duplicates kept.
+//   vals[a][b] = delta_ab - (1/n) (1 + (I_a - mu)^T (Sigma + eps/n Id)^-1 (I_b - mu))
+// ---------------------------------------------------------------------------------------------
+template <typename TIO, typename TC, int R>
+__global__ void __launch_bounds__(256)
+lap_export_coo_kernel(const TIO* __restrict__ img, int64_t* __restrict__ rows, int64_t* __restrict__ cols,
+                      TIO* __restrict__ vals, int H, int W, TC eps) {
+    constexpr int D = 2 * R + 1, N = D * D, WPB = (R == 3 ? 8 : 32);  // windows per block
+    __shared__ TC sD[WPB][N][3];                                  // centred pixels
+    __shared__ TC sXv[WPB][N][3];                                 // (Sigma + eps/n)^-1 d_a
+    const int cw = W - 2 * R, ch = H - 2 * R;
+    const long long nwin = (long long)cw * ch;
+    const long long w0 = (long long)blockIdx.x * WPB;
+    static_assert(sizeof(TC) * WPB * N * 3 * 2 <= 48 * 1024, "static shared memory budget");
+    if (threadIdx.x < WPB && w0 + threadIdx.x < nwin) {
+        const long long k = w0 + threadIdx.x;
+        const int wy = int(k / cw), wx = int(k - (long long)wy * cw);
+        TC s[3] = {0, 0, 0};
+        TC v[N][3];
+#pragma unroll
+        for (int a = 0; a < N; ++a) {
+            const size_t g = (size_t(wy + a / D) * W + wx + a % D) * 3;
+#pragma unroll
+            for (int c = 0; c < 3; ++c) { v[a][c] = TC(img[g + c]); s[c] += v[a][c]; }
+        }
+        constexpr TC inv_n = TC(1) / TC(N);
+        TC Q[6] = {0, 0, 0, 0, 0, 0};
+#pragma unroll
+        for (int a = 0; a < N; ++a) {
+#pragma unroll
+            for (int c = 0; c < 3; ++c) v[a][c] -= s[c] * inv_n;
+            Q[0] += v[a][0] * v[a][0]; Q[1] += v[a][0] * v[a][1]; Q[2] += v[a][0] * v[a][2];
+            Q[3] += v[a][1] * v[a][1]; Q[4] += v[a][1] * v[a][2]; Q[5] += v[a][2] * v[a][2];
+        }
+        Q[0] += eps; Q[3] += eps; Q[5] += eps;
+        TC Mi[6];
+        sym3_inverse(Q, Mi);                                      // (Sigma + eps/n)^-1 = n * Mi
+#pragma unroll
+        for (int a = 0; a < N; ++a) {
+            const TC d0 = v[a][0], d1 = v[a][1], d2 = v[a][2];
+            sD[threadIdx.x][a][0] = d0; sD[threadIdx.x][a][1] = d1; sD[threadIdx.x][a][2] = d2;
+            sXv[threadIdx.x][a][0] = TC(N) * (Mi[0] * d0 + Mi[1] * d1 + Mi[2] * d2);
+            sXv[threadIdx.x][a][1] = TC(N) * (Mi[1] * d0 + Mi[3] * d1 + Mi[4] * d2);
+            sXv[threadIdx.x][a][2] = TC(N) * (Mi[2] * d0 + Mi[4] * d1 + Mi[5] * d2);
+        }
+    }
+    __syncthreads();
+    const int nloc = int(min((long long)WPB, nwin - w0));
+    constexpr TC inv_n = TC(1) / TC(N);
+    for (int e = threadIdx.x; e < nloc * N * N; e += blockDim.x) {
+        const int lw = e / (N * N), ab = e - lw * N * N, a = ab / N, b = ab - a * N;
+        const long long k = w0 + lw;
+        const int wy = int(k / cw), wx = int(k - (long long)wy * cw);
+        const TC q = sXv[lw][a][0] * sD[lw][b][0] + sXv[lw][a][1] * sD[lw][b][1] + sXv[lw][a][2] * sD[lw][b][2];
+        const TC val = (a == b ? TC(1) : TC(0)) - inv_n * (TC(1) + q);
+        const size_t o = size_t(k) * N * N + ab;
+        rows[o] = int64_t(wy + a / D) * W + wx + a % D;
+        cols[o] = int64_t(wy + b / D) * W + wx + b % D;
+        vals[o] = TIO(val);
+    }
+}
+
+}  // namespace adpst
+
+// ---------------------------------------------------------------------------------------------
+// C-ABI
+// ---------------------------------------------------------------------------------------------
+struct adpst_laplacian {
+    int mode, H, W, R, io_dtype, compute_dtype;
+    double eps;
+    void* image = nullptr;       // (H,W,3) io_dtype, owned
+    double* partials = nullptr;  // one per CTA, owned
+    int npartials = 0;
+};
+
+namespace adpst {
+
+template <typename TIO, typename TC, int R>
+static int launch_matvec(adpst_laplacian* h, const void* x, void* y, double y_scale, double* xLx, cudaStream_t st) {
+    using T = LapTile<R>;
+    auto kern = lap_matvec_kernel<TIO, TC, R>;
+    const size_t smem = T::template smem_bytes<TIO, TC>();
+    static bool configured = false;            // per instantiation
+    if (!configured) {
+        ADPST_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+        configured = true;
+    }
+    dim3 grid((h->W + T::TW - 1) / T::TW, (h->H + T::TH - 1) / T::TH);
+    kern<<<grid, T::THREADS, smem, st>>>(static_cast<const TIO*>(h->image), static_cast<const TIO*>(x),
+                                          static_cast<TIO*>(y), xLx ? h->partials : nullptr, h->H, h->W, h->mode,
+                                          TC(h->eps), TC(y_scale));
+    ADPST_LAUNCH_CHECK();
+    if (xLx) {
+        sum_partials_kernel<<<1, 256, 0, st>>>(h->partials, int(grid.x * grid.y), xLx);
+        ADPST_LAUNCH_CHECK();
+    }
+    return ADPST_OK;
+}
+
+template <typename TIO, typename TC, int R>
+static int launch_coeffs(adpst_laplacian* h, void* means, void* dinv, cudaStream_t st) {
+    dim3 block(32, 8), grid((h->W + 31) / 32, (h->H + 7) / 8);
+    lap_coeff_kernel<TIO, TC, R><<<grid, block, 0, st>>>(static_cast<const TIO*>(h->image), static_cast<TIO*>(means),
+                                                         static_cast<TIO*>(dinv), h->H, h->W, TC(h->eps));
+    ADPST_LAUNCH_CHECK();
+    return ADPST_OK;
+}
+
+template <typename TIO, typename TC, int R>
+static int launch_export(adpst_laplacian* h, int64_t* rows, int64_t* cols, void* vals, cudaStream_t st) {
+    const long long nwin = (long long)(h->W - 2 * R) * (h->H - 2 * R);
+    if (nwin <= 0) return ADPST_OK;
+    constexpr int WPB = (R == 3 ? 8 : 32);
+    const unsigned blocks = unsigned((nwin + WPB - 1) / WPB);
+    lap_export_coo_kernel<TIO, TC, R><<<blocks, 256, 0, st>>>(static_cast<const TIO*>(h->image), rows, cols,
+                                                              static_cast<TIO*>(vals), h->H, h->W, TC(h->eps));
+    ADPST_LAUNCH_CHECK();
+    return ADPST_OK;
+}
+
+// dispatch over (io dtype, compute dtype, radius)
+#define ADPST_LAP_DISPATCH(FN, h, ...)                                                              \
+    do {                                                                                            \
+        const int key = (h)->io_dtype * 2 + (h)->compute_dtype;                                     \
+        switch ((h)->R) {                                                                           \
+            case 1:                                                                                 \
+                if (key == 0) return FN<float, float, 1>(h, __VA_ARGS__);                           \
+                if (key == 1) return FN<float, double, 1>(h, __VA_ARGS__);                          \
+                if (key == 3) return FN<double, double, 1>(h, __VA_ARGS__);                         \
+                break;                                                                              \
+            case 2:                                                                                 \
+                if (key == 0) return FN<float, float, 2>(h, __VA_ARGS__);                           \
+                if (key == 1) return FN<float, double, 2>(h, __VA_ARGS__);                          \
+                if (key == 3) return FN<double, double, 2>(h, __VA_ARGS__);                         \
+                break;                                                                              \
+            case 3:                                                                                 \
+                if (key == 0) return FN<float, float, 3>(h, __VA_ARGS__);                           \
+                if (key == 1) return FN<float, double, 3>(h, __VA_ARGS__);                          \
+                if (key == 3) return FN<double, double, 3>(h, __VA_ARGS__);                         \
+                break;                                                                              \
+        }                                                                                           \
+        return fail(ADPST_ERR_UNSUPPORTED, "laplacian: unsupported (io=%d, compute=%d, radius=%d)", \
+                    (h)->io_dtype, (h)->compute_dtype, (h)->R);                                     \
+    } while (0)
+
+static int dispatch_matvec(adpst_laplacian* h, const void* x, void* y, double ys, double* xLx, cudaStream_t st) {
+    ADPST_LAP_DISPATCH(launch_matvec, h, x, y, ys, xLx, st);
+}
+static int dispatch_coeffs(adpst_laplacian* h, void* means, void* dinv, cudaStream_t st) {
+    ADPST_LAP_DISPATCH(launch_coeffs, h, means, dinv, st);
+}
+static int dispatch_export(adpst_laplacian* h, int64_t* rows, int64_t* cols, void* vals, cudaStream_t st) {
+    ADPST_LAP_DISPATCH(launch_export, h, rows, cols, vals, st);
+}
+
+}  // namespace adpst
+
+extern "C" {
+
+int adpst_laplacian_create(int mode, int H, int W, int radius, double epsilon, const void* image_dev, int io_dtype,
+                           int compute_dtype, adpst_stream_t stream, adpst_laplacian** out) {
+    using namespace adpst;
+    ADPST_REQUIRE(out != nullptr, "laplacian_create: out is NULL");
+    *out = nullptr;
+    ADPST_REQUIRE(mode == ADPST_LAP_V2 || mode == ADPST_LAP_V3, "laplacian_create: mode must be V2 or V3");
+    ADPST_REQUIRE(H >= 1 && W >= 1, "laplacian_create: empty image (%d x %d)", H, W);
+    ADPST_REQUIRE(image_dev != nullptr, "laplacian_create: image is NULL");
+    ADPST_REQUIRE(epsilon > 0.0, "laplacian_create: epsilon must be > 0");
+    ADPST_REQUIRE(io_dtype == ADPST_F32 || io_dtype == ADPST_F64, "laplacian_create: bad io_dtype");
+    ADPST_REQUIRE(compute_dtype == ADPST_F32 || compute_dtype == ADPST_F64, "laplacian_create: bad compute_dtype");
+    if (radius < 1 || radius > 3)
+        return fail(ADPST_ERR_UNSUPPORTED, "laplacian_create: window_radius %d not supported (1..3)", radius);
+    if (io_dtype == ADPST_F64 && compute_dtype == ADPST_F32)
+        return fail(ADPST_ERR_UNSUPPORTED, "laplacian_create: float64 I/O with float32 arithmetic is not provided");
+    auto* h = new adpst_laplacian();
+    h->mode = mode; h->H = H; h->W = W; h->R = radius; h->io_dtype = io_dtype; h->compute_dtype = compute_dtype;
+    h->eps = epsilon;
+    const size_t bytes = size_t(H) * W * 3 * (io_dtype == ADPST_F64 ? 8 : 4);
+    cudaError_t e = cudaMalloc(&h->image, bytes);
+    if (e == cudaSuccess) {
+        h->npartials = ((W + 31) / 32) * ((H + 15) / 16);
+        e = cudaMalloc(reinterpret_cast<void**>(&h->partials), sizeof(double) * h->npartials);
+    }
+    if (e == cudaSuccess) e = cudaMemcpyAsync(h->image, image_dev, bytes, cudaMemcpyDeviceToDevice, as_stream(stream));
+    if (e != cudaSuccess) {
+        adpst_laplacian_destroy(h);
+        return fail(ADPST_ERR_CUDA, "laplacian_create: %s", cudaGetErrorString(e));
+    }
+    *out = h;
+    return ADPST_OK;
+}
+
+void adpst_laplacian_destroy(adpst_laplacian* h) {
+    if (!h) return;
+    if (h->image) cudaFree(h->image);
+    if (h->partials) cudaFree(h->partials);
+    delete h;
+}
+
+int adpst_laplacian_matvec(adpst_laplacian* h, const void* x_dev, void* y_dev, double y_scale, double* xLx_dev,
+                           adpst_stream_t stream) {
+    using namespace adpst;
+    ADPST_REQUIRE(h != nullptr && x_dev != nullptr, "laplacian_matvec: NULL handle or x");
+    ADPST_REQUIRE(y_dev != nullptr || xLx_dev != nullptr, "laplacian_matvec: nothing to compute (y and xLx NULL)");
+    return dispatch_matvec(h, x_dev, y_dev, y_scale, xLx_dev, as_stream(stream));
+}
+
+int adpst_laplacian_coefficients(adpst_laplacian* h, void* means_dev, void* delta_inv_dev, adpst_stream_t stream) {
+    using namespace adpst;
+    ADPST_REQUIRE(h != nullptr && means_dev != nullptr && delta_inv_dev != nullptr, "laplacian_coefficients: NULL argument");
+    if (h->mode != ADPST_LAP_V2)
+        return fail(ADPST_ERR_UNSUPPORTED, "laplacian_coefficients: only the v2 operator has means/delta_inv fields");
+    return dispatch_coeffs(h, means_dev, delta_inv_dev, as_stream(stream));
+}
+
+int64_t adpst_laplacian_nnz(const adpst_laplacian* h) {
+    if (!h) return -1;
+    const int64_t d = 2 * h->R + 1, ch = h->H - 2 * h->R, cw = h->W - 2 * h->R;
+    if (ch <= 0 || cw <= 0) return 0;
+    return d * d * d * d * ch * cw;
+}
+
+int adpst_laplacian_export_coo(adpst_laplacian* h, int64_t* rows_dev, int64_t* cols_dev, void* vals_dev,
+                               adpst_stream_t stream) {
+    using namespace adpst;
+    ADPST_REQUIRE(h != nullptr, "laplacian_export_coo: NULL handle");
+    if (h->mode != ADPST_LAP_V3)
+        return fail(ADPST_ERR_UNSUPPORTED, "laplacian_export_coo: only the v3 operator has an explicit matrix");
+    if (adpst_laplacian_nnz(h) == 0) return ADPST_OK;
+    ADPST_REQUIRE(rows_dev && cols_dev && vals_dev, "laplacian_export_coo: NULL output");
+    return dispatch_export(h, rows_dev, cols_dev, vals_dev, as_stream(stream));
+}
+
+}  // extern "C"

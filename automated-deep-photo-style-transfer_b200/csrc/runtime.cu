@@ -1,0 +1,43 @@
+// runtime.cu -- error reporting and device queries shared by every entry point.
+#include <stdarg.h>
+
+#include "common.cuh"
+
+namespace adpst {
+
+static thread_local std::string g_last_error;
+
+void set_error(const std::string& msg) { g_last_error = msg; }
+
+int fail(int code, const char* fmt, ...) {
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    g_last_error = buf;
+    return code;
+}
+
+int num_sms() {
+    static int cached = 0;
+    if (cached == 0) {
+        int dev = 0, n = 0;
+        if (cudaGetDevice(&dev) == cudaSuccess &&
+            cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0)
+            cached = n;
+        else
+            return 148;
+    }
+    return cached;
+}
+
+}  // namespace adpst
+
+extern "C" {
+
+int adpst_version(void) { return 100; }
+
+const char* adpst_last_error(void) { return adpst::g_last_error.c_str(); }
+
+}  // extern "C"

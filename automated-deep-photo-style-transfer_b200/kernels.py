@@ -1,0 +1,95 @@
+"""Thin, typed Python wrappers over the C-ABI entry points that are not tied to a handle.
+Every function launches hand-written CUDA from libadpst.so on torch's current stream; none has a fallback."""
+import ctypes
+
+import torch
+
+from . import _lib
+
+
+def _f32(t, name):
+    if t.dtype != torch.float32 or not t.is_cuda or not t.is_contiguous():
+        raise TypeError("%s must be a contiguous float32 CUDA tensor" % name)
+    return t
+
+
+class AdamState:
+    """Adam slots for one image variable (style_transfer.py:321-326): m, v and the device-side step counter."""
+
+    def __init__(self, like):
+        self.m = torch.zeros_like(like)
+        self.v = torch.zeros_like(like)
+        self.state = torch.zeros(2, dtype=torch.int32, device=like.device)     # {t, ticket}
+
+    @property
+    def step(self):
+        return int(self.state[0])
+
+
+def adam_clip_step(x, grad, st, lr=0.1, beta1=0.9, beta2=0.999, epsilon=1e-8):
+    """In place: TF-flavour Adam update of x followed by clip to [0,1] (style_transfer.py:342-343)."""
+    _f32(x, "x"); _f32(grad, "grad")
+    if grad.numel() != x.numel():
+        raise ValueError("grad and x differ in size")
+    _lib.check(_lib.lib().adpst_adam_clip_step(_lib.ptr(x), _lib.ptr(grad), _lib.ptr(st.m), _lib.ptr(st.v), x.numel(),
+                                               _lib.ptr(st.state), lr, beta1, beta2, epsilon, _lib.stream_ptr()))
+    return x
+
+
+def resize_bilinear(mask_hw, size):
+    """tf.image.resize(mask, size) for one (H,W) float32 plane (loss.py:112-113)."""
+    _f32(mask_hw, "mask")
+    Hs, Ws = mask_hw.shape
+    Hd, Wd = int(size[0]), int(size[1])
+    out = torch.empty(Hd, Wd, dtype=torch.float32, device=mask_hw.device)
+    _lib.check(_lib.lib().adpst_resize_bilinear(_lib.ptr(mask_hw), Hs, Ws, _lib.ptr(out), Hd, Wd, _lib.stream_ptr()))
+    return out
+
+
+def content_layer(target, output, scale, loss_acc, d_out=None, accumulate=False):
+    """loss_acc (float64[1]) += scale*mean((t-o)^2); d_out (=|+=) scale*2(o-t)/n  (loss.py:90-92)."""
+    _f32(target, "target"); _f32(output, "output")
+    if target.shape != output.shape:
+        raise ValueError("content target %s and output %s differ in shape" % (tuple(target.shape), tuple(output.shape)))
+    _lib.check(_lib.lib().adpst_content_layer(_lib.ptr(target), _lib.ptr(output), output.numel(), float(scale),
+                                              _lib.ptr(loss_acc), _lib.ptr(d_out), int(bool(accumulate)),
+                                              _lib.stream_ptr()))
+
+
+def axpby(out, a, alpha, b=None, beta=0.0):
+    _f32(out, "out"); _f32(a, "a")
+    _lib.check(_lib.lib().adpst_axpby(_lib.ptr(out), _lib.ptr(a), float(alpha), _lib.ptr(b), float(beta), out.numel(),
+                                      _lib.stream_ptr()))
+    return out
+
+
+def gram_workspace(HW, C, K, device):
+    n = int(_lib.lib().adpst_gram_workspace_bytes(HW, C, K))
+    return torch.empty(max(n, 16), dtype=torch.uint8, device=device)
+
+
+def gram_masked(F, masks, K, workspace=None):
+    """F: (HW,C) float32; masks: (K,HW) float32 or None.  Returns (K,C,C) float32  (loss.py:96-102)."""
+    _f32(F, "F")
+    HW, C = F.shape
+    if masks is not None:
+        _f32(masks, "masks")
+        if tuple(masks.shape) != (K, HW):
+            raise ValueError("masks must have shape (K, HW)")
+    elif K != 1:
+        raise ValueError("K must be 1 without masks")
+    ws = workspace if workspace is not None else gram_workspace(HW, C, K, F.device)
+    G = torch.empty(K, C, C, dtype=torch.float32, device=F.device)
+    _lib.check(_lib.lib().adpst_gram_masked(_lib.ptr(F), HW, C, _lib.ptr(masks), K, _lib.ptr(G), _lib.ptr(ws),
+                                            _lib.stream_ptr()))
+    return G
+
+
+def style_layer_backward(F, masks, K, G, A, scale, loss_acc, dF, accumulate=False, workspace=None):
+    """One layer of loss.py:104-137: accumulates the loss value and writes/adds its gradient w.r.t. F."""
+    _f32(F, "F"); _f32(G, "G"); _f32(A, "A")
+    HW, C = F.shape
+    ws = workspace if workspace is not None else gram_workspace(HW, C, K, F.device)
+    _lib.check(_lib.lib().adpst_style_layer_backward(_lib.ptr(F), HW, C, _lib.ptr(masks), K, _lib.ptr(G), _lib.ptr(A),
+                                                     float(scale), _lib.ptr(loss_acc), _lib.ptr(dF),
+                                                     int(bool(accumulate)), _lib.ptr(ws), _lib.stream_ptr()))

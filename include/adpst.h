@@ -1,0 +1,137 @@
+/* adpst.h -- C-ABI of libadpst.so: the B200 (sm_100a) hot path of automated-deep-photo-style-transfer.
+ *
+ * The reference has NO native / FFI layer: its boundary is the Python classes
+ *   components/loss.py:6-165            Loss
+ *   components/matting_v2.py:6-251      MattingLaplacian (matrix-free)
+ *   components/matting_v3.py:13-102     MattingLaplacian (explicit COO)
+ *   components/VGG19/model.py:4-41      StyleContentModel
+ *   style_transfer.py:321-344           Adam + train_step
+ * Each entry point below names the reference lines it replaces.  The host-side mirror of those classes
+ * (automated-deep-photo-style-transfer_b200/components/*.py) binds this file through ctypes.
+ *
+ * Conventions
+ *   - every pointer marked "dev" is a CUDA device pointer owned by the caller (torch allocates);
+ *   - images / activations are NHWC with N == 1, float32 unless a dtype argument says otherwise;
+ *   - every call is asynchronous on `stream` (a cudaStream_t passed as void*); no internal threads,
+ *     no global state except the per-thread last-error string;
+ *   - return value: ADPST_OK or an error code; adpst_last_error() gives the message.
+ *   - there is no CPU fallback: without a CUDA device every compute entry point returns ADPST_ERR_CUDA.
+ */
+#ifndef ADPST_H
+#define ADPST_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* adpst_stream_t;
+
+enum { ADPST_OK = 0, ADPST_ERR_INVALID = 1, ADPST_ERR_CUDA = 2, ADPST_ERR_UNSUPPORTED = 3 };
+enum { ADPST_F32 = 0, ADPST_F64 = 1 };
+enum { ADPST_LAP_V2 = 2, ADPST_LAP_V3 = 3 };
+enum { ADPST_VGG_NUM_CONV = 13, ADPST_VGG_NUM_POOL = 4 };
+
+int adpst_version(void);
+const char* adpst_last_error(void);
+
+/* ------------------------------------------------------------------------------------------------
+ * Matting Laplacian (matrix-free for both variants)
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct adpst_laplacian adpst_laplacian;
+
+/* matting_v2.py:11-52 (mode V2: symmetric padding, one window per pixel) and
+ * matting_v3.py:27-39,61-102 (mode V3: fully interior windows only).
+ * image_dev: (H,W,3) of `io_dtype`; it is copied into the handle.  compute_dtype: arithmetic type of the
+ * stencil (F64 reproduces the reference's float64 path, loss.py:160; F32 is the fast path). */
+int adpst_laplacian_create(int mode, int H, int W, int radius, double epsilon, const void* image_dev,
+                           int io_dtype, int compute_dtype, adpst_stream_t stream, adpst_laplacian** out);
+void adpst_laplacian_destroy(adpst_laplacian* h);
+
+/* matting_v2.py:147-176 _matmul / matting_v3.py:50-51 _matmul, fused with loss.py:160-161.
+ * x_dev: (H*W,3) io_dtype.  y_dev (may be NULL): receives y_scale * (L x), same dtype.
+ * xLx_dev (may be NULL): device double, receives x^T L x accumulated in float64. */
+int adpst_laplacian_matvec(adpst_laplacian* h, const void* x_dev, void* y_dev, double y_scale,
+                           double* xLx_dev, adpst_stream_t stream);
+
+/* matting_v2.py:49-52: window means (H,W,3) and regularised inverse covariances (H,W,3,3), io_dtype. */
+int adpst_laplacian_coefficients(adpst_laplacian* h, void* means_dev, void* delta_inv_dev, adpst_stream_t stream);
+
+/* matting_v3.py:97-102: COO triplets in the reference's emission order, duplicates kept.
+ * nnz = 81 (H-2r)(W-2r) for r = 1 (general: (2r+1)^4 per window). vals_dev has io_dtype. */
+int64_t adpst_laplacian_nnz(const adpst_laplacian* h);
+int adpst_laplacian_export_coo(adpst_laplacian* h, int64_t* rows_dev, int64_t* cols_dev, void* vals_dev,
+                               adpst_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Optimiser: style_transfer.py:321-326,342-343  (TF/Keras Adam + clip_by_value(0,1)), fused.
+ * state_dev: device int32[2] = {completed steps t, 0}; the kernel uses t+1 and the LAST block increments t, so the
+ * call is CUDA-graph replayable.  In place on x, m, v.
+ * ---------------------------------------------------------------------------------------------- */
+int adpst_adam_clip_step(float* x_dev, const float* grad_dev, float* m_dev, float* v_dev, size_t n,
+                         int32_t* state_dev, float lr, float beta1, float beta2, float epsilon,
+                         adpst_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * VGG19 extractor: components/VGG19/model.py:4-41 (forward) and the tape.gradient of
+ * style_transfer.py:341 (data gradient only; weights are frozen, model.py:11,25).
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct adpst_vgg adpst_vgg;
+
+/* kernels_dev[i]: HWIO (3,3,Cin,Cout) float32, biases_dev[i]: (Cout,), i over the 13 convolutions
+ * block1_conv1 .. block5_conv1 in network order.  The handle keeps re-laid-out copies. */
+int adpst_vgg_create(const float* const* kernels_dev, const float* const* biases_dev,
+                     adpst_stream_t stream, adpst_vgg** out);
+void adpst_vgg_destroy(adpst_vgg* h);
+/* shape of conv output i (post-ReLU) for an H x W input. */
+int adpst_vgg_conv_shape(int i, int H, int W, int* h, int* w, int* c);
+/* shape of pool output j (j = 0..3). */
+int adpst_vgg_pool_shape(int j, int H, int W, int* h, int* w, int* c);
+
+/* model.py:27-30: x255, RGB->BGR, mean subtraction, then convs/pools up to conv index `last` (inclusive).
+ * acts_dev[i]: conv i output (1,h,w,c) post-ReLU; pools_dev[j]: pool j output.  All caller-allocated. */
+int adpst_vgg_forward(adpst_vgg* h, const float* image_dev, int H, int W, float* const* acts_dev,
+                      float* const* pools_dev, int last, adpst_stream_t stream);
+
+/* Backward to the image.  seeds_dev[i] (may be NULL): dLoss/d(conv i output), added where the chain passes.
+ * scratch_dev: two buffers, each at least as large as the largest activation (conv 0).
+ * dimage_dev: (1,H,W,3) gradient w.r.t. the [0,1] RGB image (the x255 and channel flip are folded in). */
+int adpst_vgg_backward(adpst_vgg* h, int H, int W, const float* const* acts_dev, const float* const* pools_dev,
+                       const float* const* seeds_dev, int last, float* scratch0_dev, float* scratch1_dev,
+                       float* dimage_dev, adpst_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Loss terms: components/loss.py
+ * ---------------------------------------------------------------------------------------------- */
+/* tf.image.resize bilinear, half-pixel centres, no antialias (loss.py:112-113); single channel. */
+int adpst_resize_bilinear(const float* src_dev, int Hs, int Ws, float* dst_dev, int Hd, int Wd,
+                          adpst_stream_t stream);
+
+/* loss.py:96-102 for K masks at once: G[k] = (F*m_k)^T (F*m_k).  F: (HW,C); masks: (K,HW) or NULL (K==1,
+ * all ones); G: (K,C,C).  workspace_dev: at least adpst_gram_workspace_bytes(HW,C,K) bytes. */
+size_t adpst_gram_workspace_bytes(int HW, int C, int K);
+int adpst_gram_masked(const float* F_dev, int HW, int C, const float* masks_dev, int K, float* G_dev,
+                      void* workspace_dev, adpst_stream_t stream);
+
+/* loss.py:104-137 for one layer, forward value and gradient seed:
+ *   loss += scale * sum_k mean((A_k - G_k)^2) / (2 C^2 HW^2)          (accumulated into *loss_dev, float64)
+ *   dF    = scale * d/dF of that term                                  (written, or added if accumulate != 0)
+ * G_dev is the transfer Gram from adpst_gram_masked on the same F / masks; A_dev the style Gram. */
+int adpst_style_layer_backward(const float* F_dev, int HW, int C, const float* masks_dev, int K,
+                               const float* G_dev, const float* A_dev, double scale, double* loss_dev,
+                               float* dF_dev, int accumulate, void* workspace_dev, adpst_stream_t stream);
+
+/* loss.py:90-92: loss += scale * mean((target - output)^2); dOut = scale * 2 (output - target) / n. */
+int adpst_content_layer(const float* target_dev, const float* output_dev, size_t n, double scale,
+                        double* loss_dev, float* dOut_dev, int accumulate, adpst_stream_t stream);
+
+/* out[i] = a[i] + alpha * b[i] (float32; b is float32).  Used to combine image gradients. */
+int adpst_axpby(float* out_dev, const float* a_dev, float alpha, const float* b_dev, float beta, size_t n,
+                adpst_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ADPST_H */

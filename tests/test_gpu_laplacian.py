@@ -1,0 +1,165 @@
+"""GPU parity: matting Laplacian (v2 / v3) through the reference-shaped Python classes -> ctypes -> libadpst.so,
+against the numpy float64 oracle and the reference-generated golden vectors.
+
+Tolerances (north star: 1e-5 relative for Laplacian values and Lx; sparsity pattern bit-exact):
+  float64 arithmetic: 1e-9 of max|y| (generic x), 1e-6 of max|y| when x = I (|y| itself is ~1e-6 of generic)
+  float32 arithmetic: 1e-5 of max|y| on uniform synthetic images with random x (the case the criterion names)
+"""
+import importlib
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import PKG_NAME, golden
+from oracle import matting
+
+pytestmark = pytest.mark.gpu
+
+
+def _v2():
+    return importlib.import_module(PKG_NAME + ".components.matting_v2")
+
+
+def _v3():
+    return importlib.import_module(PKG_NAME + ".components.matting_v3")
+
+
+def _rel(a, b):
+    a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+    return np.abs(a - b).max() / max(np.abs(b).max(), 1e-300)
+
+
+@pytest.mark.parametrize("H,W", [(1, 1), (2, 3), (5, 7), (16, 32), (33, 70), (64, 64)])
+@pytest.mark.parametrize("eps", [1e-7, 1e-5])
+def test_v2_float64_matches_oracle(H, W, eps, synth):
+    img = synth.image(H, W, 100 + H)[0].astype(np.float64)
+    x = np.random.default_rng(200 + W).random((H * W, 3))
+    ref = matting.V2Operator(img, eps, 1)
+    op = _v2().MattingLaplacian(torch.as_tensor(img).cuda(), epsilon=eps, window_radius=1)
+    assert tuple(op.shape) == (H * W, H * W) and op.size == (H, W, 3) and op.window_area == 9 and op.radius == 1
+    y = op.matmul(torch.as_tensor(x).cuda())
+    assert y.dtype == torch.float64 and tuple(y.shape) == (H * W, 3)
+    assert _rel(y.cpu().numpy(), ref.matmul(x)) < 1e-9
+    yi = op.matmul(torch.as_tensor(img.reshape(-1, 3)).cuda()).cpu().numpy()       # x = I, iteration 0
+    assert _rel(yi, ref.matmul(img.reshape(-1, 3))) < 1e-6
+
+
+@pytest.mark.parametrize("r", [2, 3])
+def test_v2_larger_radius(r, synth):
+    H, W = 21, 37
+    img = synth.image(H, W, 7)[0].astype(np.float64)
+    x = np.random.default_rng(8).random((H * W, 3))
+    ref = matting.V2Operator(img, 1e-5, r)
+    op = _v2().MattingLaplacian(torch.as_tensor(img).cuda(), epsilon=1e-5, window_radius=r)
+    assert _rel(op.matmul(torch.as_tensor(x).cuda()).cpu().numpy(), ref.matmul(x)) < 1e-9
+
+
+def test_v2_coefficient_fields(synth):
+    H, W = 19, 23
+    img = synth.image(H, W, 9)[0].astype(np.float64)
+    ref = matting.V2Operator(img, 1e-7, 1)
+    op = _v2().MattingLaplacian(torch.as_tensor(img).cuda(), epsilon=1e-7, window_radius=1)
+    assert tuple(op.means.shape) == (H, W, 3, 1) and tuple(op.delta_inv.shape) == (H, W, 3, 3)
+    assert _rel(op.means.cpu().numpy(), ref.means) < 1e-12
+    assert _rel(op.delta_inv.cpu().numpy(), ref.delta_inv) < 1e-8
+
+
+def test_v2_float32_storage_float64_arithmetic_hot_path(synth):
+    """What Loss uses: image/x/y are float32 in HBM, the stencil runs in float64."""
+    H, W = 48, 80
+    for make in (synth.image, synth.smooth_image):
+        img32 = make(H, W, 11)[0]
+        x32 = synth.image(H, W, 12)[0].reshape(-1, 3)
+        ref = matting.V2Operator(img32.astype(np.float64), 1e-7, 1)
+        op = _v2().MattingLaplacian(torch.as_tensor(img32).cuda(), epsilon=1e-7, window_radius=1,
+                                    storage_dtype=torch.float32, compute_dtype=torch.float64)
+        for xx in (x32, img32.reshape(-1, 3)):
+            want = ref.matmul(xx.astype(np.float64))
+            q, y = None, None
+            y, q = op.quadratic_form(torch.as_tensor(xx).cuda(), want_y=True, y_scale=2.0)
+            assert y.dtype == torch.float32
+            got = y.cpu().numpy().astype(np.float64) / 2.0
+            assert np.abs(got - want).max() <= 1e-6 * np.abs(want).max() + 1e-7 * np.abs(want).max()
+            quad = float(np.sum(xx.astype(np.float64) * want))
+            assert abs(float(q) - quad) <= 1e-9 * max(abs(quad), 1e-12) + 1e-12 * np.abs(want).sum()
+
+
+def test_v2_float32_arithmetic_fast_path(synth):
+    H, W = 64, 96
+    img32 = synth.image(H, W, 13)[0]
+    x32 = synth.image(H, W, 14)[0].reshape(-1, 3)
+    ref = matting.V2Operator(img32.astype(np.float64), 1e-7, 1)
+    op = _v2().MattingLaplacian(torch.as_tensor(img32).cuda(), epsilon=1e-7, window_radius=1)   # float32 operator
+    y = op.matmul(torch.as_tensor(x32).cuda())
+    assert y.dtype == torch.float32
+    assert _rel(y.cpu().numpy(), ref.matmul(x32.astype(np.float64))) < 1e-5
+
+
+def test_matmul_other_column_counts(synth):
+    H, W = 12, 17
+    img = synth.image(H, W, 15)[0].astype(np.float64)
+    ref = matting.V2Operator(img, 1e-5, 1)
+    op = _v2().MattingLaplacian(torch.as_tensor(img).cuda(), epsilon=1e-5)
+    for C in (1, 2, 4, 7):
+        x = np.random.default_rng(C).random((H * W, C))
+        assert _rel(op.matmul(torch.as_tensor(x).cuda()).cpu().numpy(), ref.matmul(x)) < 1e-9
+    with pytest.raises(TypeError):
+        op.matmul(torch.zeros(H * W, 3, dtype=torch.float32).cuda())        # dtype mismatch raises, as LinearOperator does
+    with pytest.raises(ValueError):
+        op.matmul(torch.zeros(H * W + 1, 3, dtype=torch.float64).cuda())
+
+
+@pytest.mark.parametrize("tag", ["a", "b", "c"])
+def test_v3_matches_reference_golden(tag):
+    g = golden("v3_%s.npz" % tag)
+    img = g["image"]
+    H, W, _ = img.shape
+    op = _v3().MattingLaplacian(torch.as_tensor(img).cuda(), epsilon=float(g["eps"]), window_radius=1)
+    y = op.matmul(torch.as_tensor(g["x"]).cuda()).cpu().numpy()
+    assert _rel(y, g["Lx"]) < 1e-9
+    yi = op.matmul(torch.as_tensor(img.reshape(-1, 3)).cuda()).cpu().numpy()
+    assert np.abs(yi - g["LI"]).max() < 1e-6 * max(np.abs(g["LI"]).max(), 1e-12) + 1e-13
+    coo = op.laplacian
+    assert op.nnz == 81 * (H - 2) * (W - 2) == len(g["vals"])
+    idx = coo.indices.cpu().numpy()
+    assert idx.dtype == np.int64
+    assert np.array_equal(idx[:, 0], g["rows"]) and np.array_equal(idx[:, 1], g["cols"])     # bit-exact pattern
+    assert np.abs(coo.values.cpu().numpy() - g["vals"]).max() < 1e-9 * np.abs(g["vals"]).max()
+    assert tuple(coo.dense_shape) == (H * W, H * W)
+
+
+@pytest.mark.parametrize("H,W", [(2, 2), (3, 3), (3, 9), (40, 50)])
+def test_v3_small_and_ragged(H, W, synth):
+    img = synth.image(H, W, 31)[0].astype(np.float64)
+    x = np.random.default_rng(32).random((H * W, 3))
+    op = _v3().MattingLaplacian(torch.as_tensor(img).cuda(), epsilon=1e-7)
+    y = op.matmul(torch.as_tensor(x).cuda()).cpu().numpy()
+    if H < 3 or W < 3:
+        assert op.nnz == 0 and np.abs(y).max() == 0.0          # no interior window: the zero operator
+    else:
+        ref = matting.V3Operator(img, 1e-7, 1)
+        assert _rel(y, ref.matmul(x)) < 1e-9
+
+
+def test_full_size_properties_1024(synth):
+    """BASELINE config 2 size: size-independent properties (symmetric, L.1 = 0, PSD, v2 == v3 on the interior)."""
+    H = W = 1024
+    img = torch.as_tensor(synth.image(H, W, 0)[0]).cuda()
+    gen = torch.Generator(device="cuda").manual_seed(1)
+    x = torch.rand(H * W, 3, device="cuda", generator=gen)
+    z = torch.rand(H * W, 3, device="cuda", generator=gen)
+    v2 = _v2().MattingLaplacian(img, epsilon=1e-7, storage_dtype=torch.float32, compute_dtype=torch.float64)
+    v3 = _v3().MattingLaplacian(img, epsilon=1e-7, storage_dtype=torch.float32, compute_dtype=torch.float64)
+    for op in (v2, v3):
+        yx, qx = op.quadratic_form(x, want_y=True)
+        yz, _ = op.quadratic_form(z, want_y=True)
+        y1, _ = op.quadratic_form(torch.ones_like(x), want_y=True)
+        assert float(y1.abs().max()) < 1e-5                                   # L.1 = 0 (float32 output rounding)
+        a, b = float((yx.double() * z.double()).sum()), float((x.double() * yz.double()).sum())
+        assert abs(a - b) < 1e-6 * abs(a)                                     # <Lx, z> = <x, Lz>
+        assert float(qx) > 0 and abs(float(qx) - float((x.double() * yx.double()).sum())) < 1e-6 * float(qx)
+    y2, _ = v2.quadratic_form(x, want_y=True)
+    y3, _ = v3.quadratic_form(x, want_y=True)
+    d = (y2 - y3).reshape(H, W, 3)
+    assert float(d[2:-2, 2:-2].abs().max()) < 1e-5 and float(d.abs().max()) > 1e-2
