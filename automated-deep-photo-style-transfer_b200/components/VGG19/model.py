@@ -1,0 +1,172 @@
+"""Drop-in for /root/reference/components/VGG19/model.py (vgg_layers :4-16, StyleContentModel :18-41).
+
+Keras `applications.vgg19` is replaced by the VGG19 handle of libadpst (csrc/vgg_simt.cu, conv_tc.cu): the x255,
+RGB->BGR, mean subtraction of `call` (:28-29) is folded into the first convolution's load.  There is no autodiff
+tape; `backward(seeds)` plays the role of tape.gradient (style_transfer.py:341) for the frozen network.
+"""
+import ctypes
+import os
+
+import numpy as np
+import torch
+
+from ... import _lib
+from ...synth import CONV_LAYERS
+
+LAYER_INDEX = {name: i for i, (name, _, _) in enumerate(CONV_LAYERS)}
+POOL_AFTER = (1, 3, 7, 11)
+
+
+def _load_weights(weights):
+    """weights: dict name -> (kernel HWIO (3,3,Cin,Cout), bias (Cout,)), or a path to an .npz with
+    '<name>/kernel' and '<name>/bias' entries.  The reference downloads ImageNet weights through Keras
+    (model.py:7); there is no network here, so they must be supplied."""
+    if weights is None:
+        path = os.environ.get("ADPST_VGG19_WEIGHTS", os.path.join(os.path.dirname(__file__), "..", "..", "..", "weights",
+                                                                 "vgg19_conv.npz"))
+        if not os.path.exists(path):
+            raise FileNotFoundError(
+                "VGG19 weights not found (%s). Pass weights=<dict or .npz path> or set ADPST_VGG19_WEIGHTS; "
+                "Keras' ImageNet download of the reference (VGG19/model.py:7) is not available offline." % path)
+        weights = path
+    if isinstance(weights, (str, os.PathLike)):
+        z = np.load(weights)
+        weights = {n: (z[n + "/kernel"], z[n + "/bias"]) for n, _, _ in CONV_LAYERS}
+    out = []
+    for name, cin, cout in CONV_LAYERS:
+        k, b = weights[name]
+        k, b = np.asarray(k, np.float32), np.asarray(b, np.float32)
+        if k.shape != (3, 3, cin, cout) or b.shape != (cout,):
+            raise ValueError("%s: expected kernel (3,3,%d,%d) and bias (%d,), got %s / %s" %
+                             (name, cin, cout, cout, k.shape, b.shape))
+        out.append((k, b))
+    return out
+
+
+class VGG19Handle:
+    """Owns one adpst_vgg* (weights re-laid-out on the device)."""
+
+    def __init__(self, weights=None, device=None):
+        _lib.require_cuda()
+        self.device = torch.device(device if device is not None else "cuda")
+        kb = _load_weights(weights)
+        ks = [torch.as_tensor(k).to(self.device).contiguous() for k, _ in kb]
+        bs = [torch.as_tensor(b).to(self.device).contiguous() for _, b in kb]
+        h = ctypes.c_void_p()
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.lib().adpst_vgg_create(_lib.ptr_array(ks), _lib.ptr_array(bs), _lib.stream_ptr(),
+                                                   ctypes.byref(h)))
+            torch.cuda.current_stream().synchronize()        # ks / bs may be freed after this
+        self._h = h
+
+    def __del__(self):
+        h, self._h = getattr(self, "_h", None), None
+        if h:
+            try:
+                _lib.lib().adpst_vgg_destroy(h)
+            except Exception:
+                pass
+
+    @staticmethod
+    def conv_shape(i, H, W):
+        h, w, c = ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
+        _lib.check(_lib.lib().adpst_vgg_conv_shape(i, H, W, ctypes.byref(h), ctypes.byref(w), ctypes.byref(c)))
+        return h.value, w.value, c.value
+
+    @staticmethod
+    def pool_shape(j, H, W):
+        h, w, c = ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
+        _lib.check(_lib.lib().adpst_vgg_pool_shape(j, H, W, ctypes.byref(h), ctypes.byref(w), ctypes.byref(c)))
+        return h.value, w.value, c.value
+
+
+class Activations:
+    """Caller-owned activation set of one forward pass (conv outputs post-ReLU and pool outputs)."""
+
+    def __init__(self, H, W, last, device):
+        self.H, self.W, self.last = H, W, last
+        self.acts = [None] * _lib.VGG_NUM_CONV
+        self.pools = [None] * _lib.VGG_NUM_POOL
+        for i in range(last + 1):
+            h, w, c = VGG19Handle.conv_shape(i, H, W)
+            if h < 1 or w < 1:
+                raise ValueError("a %dx%d image is too small for VGG19 layer %s" % (H, W, CONV_LAYERS[i][0]))
+            self.acts[i] = torch.empty(1, h, w, c, dtype=torch.float32, device=device)
+        for j, after in enumerate(POOL_AFTER):
+            if after < last:
+                h, w, c = VGG19Handle.pool_shape(j, H, W)
+                self.pools[j] = torch.empty(1, h, w, c, dtype=torch.float32, device=device)
+
+
+def vgg_layers(layer_names, shape=None, weights=None, device=None):
+    """reference :4-16.  Returns the handle and the conv indices of the requested layers."""
+    for n in layer_names:
+        if n not in LAYER_INDEX:
+            raise ValueError("unknown VGG19 layer %r (available: %s)" % (n, ", ".join(LAYER_INDEX)))
+    return VGG19Handle(weights, device), [LAYER_INDEX[n] for n in layer_names]
+
+
+class StyleContentModel:
+    """reference :18-41.  `model(image)` -> {'content': {name: (1,h,w,C)}, 'style': {name: (1,h,w,C)}}, post-ReLU.
+
+    Extensions (no tape here): the activations of the latest call stay referenced in `self.last` so that
+    `backward(seeds)` can return d(sum_i <seed_i, layer_i>)/d(image)."""
+
+    def __init__(self, content_layers, style_layers, shape=None, weights=None, device=None):
+        self.vgg, idx = vgg_layers(list(content_layers) + list(style_layers), shape, weights, device)
+        self.content_layers = list(content_layers)
+        self.style_layers = list(style_layers)
+        self.limit = len(content_layers)                                      # :24
+        self.indices = idx
+        self.last_index = max(idx)
+        self.device = self.vgg.device
+        self.last = None
+        self._scratch = None
+
+    def __call__(self, inputs, reuse=False):
+        return self.call(inputs, reuse)
+
+    def call(self, inputs, reuse=False):                                      # :27-41
+        """reuse=True overwrites the activation buffers of the previous call (what train_step does every
+        iteration); the default allocates fresh tensors, so earlier results (the targets) stay valid."""
+        if inputs.dim() != 4 or inputs.shape[0] != 1 or inputs.shape[3] != 3:
+            raise ValueError("expected an image of shape (1, H, W, 3), got %s" % (tuple(inputs.shape),))
+        if inputs.dtype != torch.float32 or not inputs.is_cuda:
+            raise TypeError("expected a float32 CUDA image")
+        x = inputs.contiguous()
+        H, W = int(x.shape[1]), int(x.shape[2])
+        A = self.last if (reuse and self.last is not None and (self.last.H, self.last.W) == (H, W)) else \
+            Activations(H, W, self.last_index, self.device)
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.lib().adpst_vgg_forward(self.vgg._h, _lib.ptr(x), H, W, _lib.ptr_array(A.acts),
+                                                    _lib.ptr_array(A.pools), self.last_index, _lib.stream_ptr()))
+        self.last = A
+        names = self.content_layers + self.style_layers
+        outs = [A.acts[i] for i in self.indices]
+        content = {n: o for n, o in zip(names[:self.limit], outs[:self.limit])}
+        style = {n: o for n, o in zip(names[self.limit:], outs[self.limit:])}
+        return {"content": content, "style": style}
+
+    def backward(self, seeds, out=None):
+        """seeds: dict layer name -> dLoss/d(layer output) (1,h,w,C) float32.  Returns dLoss/d(image) (1,H,W,3)."""
+        A = self.last
+        if A is None:
+            raise RuntimeError("backward() needs a preceding forward call")
+        arr = [None] * _lib.VGG_NUM_CONV
+        for n, t in seeds.items():
+            i = LAYER_INDEX[n]
+            if t.shape != A.acts[i].shape or t.dtype != torch.float32 or not t.is_contiguous():
+                raise ValueError("seed for %s must be a contiguous float32 tensor of shape %s" %
+                                 (n, tuple(A.acts[i].shape)))
+            arr[i] = t
+        top = max(i for i, t in enumerate(arr) if t is not None)
+        if self._scratch is None or self._scratch[0].numel() < A.acts[0].numel():
+            self._scratch = (torch.empty(A.acts[0].numel(), dtype=torch.float32, device=self.device),
+                             torch.empty(A.acts[0].numel(), dtype=torch.float32, device=self.device))
+        if out is None:
+            out = torch.empty(1, A.H, A.W, 3, dtype=torch.float32, device=self.device)
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.lib().adpst_vgg_backward(self.vgg._h, A.H, A.W, _lib.ptr_array(A.acts), _lib.ptr_array(A.pools),
+                                                     _lib.ptr_array(arr), top, _lib.ptr(self._scratch[0]),
+                                                     _lib.ptr(self._scratch[1]), _lib.ptr(out), _lib.stream_ptr()))
+        return out

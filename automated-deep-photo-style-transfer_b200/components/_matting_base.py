@@ -54,8 +54,9 @@ class LaplacianHandle:
     def HW(self):
         return self.H * self.W
 
-    def apply3(self, x, want_y=True, want_quad=False, y_scale=1.0, out=None):
-        """x: (HW,3) storage_dtype contiguous.  Returns (y or None, xLx 0-dim float64 tensor or None)."""
+    def apply3(self, x, want_y=True, want_quad=False, y_scale=1.0, out=None, quad_out=None):
+        """x: (HW,3) storage_dtype contiguous.  Returns (y or None, xLx 0-dim float64 tensor or None).
+        quad_out: optional 1-element float64 device tensor that receives x^T L x instead of the internal one."""
         if x.dtype != self.storage_dtype:
             raise TypeError("x has dtype %s, operator stores %s" % (x.dtype, self.storage_dtype))
         if x.numel() != self.HW * 3:
@@ -63,11 +64,13 @@ class LaplacianHandle:
         y = None
         if want_y:
             y = out if out is not None else torch.empty_like(x)
-        q = self._xlx if want_quad else None
+        q = (quad_out if quad_out is not None else self._xlx) if want_quad else None
+        if q is not None and (q.dtype != torch.float64 or q.numel() != 1 or not q.is_cuda):
+            raise TypeError("quad_out must be a 1-element float64 CUDA tensor")
         with torch.cuda.device(self.device):
             _lib.check(_lib.lib().adpst_laplacian_matvec(self._h, _lib.ptr(x), _lib.ptr(y), float(y_scale), _lib.ptr(q),
                                                          _lib.stream_ptr()))
-        return y, (q[0] if want_quad else None)
+        return y, (q.reshape(-1)[0] if want_quad else None)
 
     def matmul(self, x):
         """(HW, C') -> (HW, C').  C' != 3 is processed three columns at a time (zero padded)."""

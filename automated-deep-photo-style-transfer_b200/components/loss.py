@@ -1,0 +1,208 @@
+"""Drop-in for /root/reference/components/loss.py (class Loss :6-161, dict_zip :163-165).
+
+Same constructor and call signature, same dictionary keys (including the reference's spelling of
+'Photorealism regualarization').  Differences forced by the platform, all explicit:
+  * there is no autodiff tape: evaluating the loss also writes the gradient seeds (d total / d layer output) and the
+    photorealism gradient, which `gradient(extractor)` turns into d total / d image;
+  * the NIMA term (loss.py:141-153, InceptionResNetV2 with weights that are not in the tree) is out of scope:
+    `nima_weight` must be 0 and 'NIMA loss' is reported as 0;
+  * the style Grams of the style target are constant and are computed once here, not every call (loss.py:130);
+  * `matting` selects the Laplacian variant ('v2' as hard-wired in the reference, loss.py:4, or 'v3').
+All arithmetic happens in libadpst kernels; the returned values are views of one float32 device vector.
+"""
+import torch
+
+from .. import kernels
+from .matting_v2 import MattingLaplacian as MattingLaplacianV2
+from .matting_v3 import MattingLaplacian as MattingLaplacianV3
+
+
+class Loss:
+    r"""Loss functions are computed within this class (reference loss.py:6-9)."""
+
+    def __init__(self, content_target, style_target, args, content_masks=None, style_masks=None, matting="v2"):
+        self.content_target = content_target
+        self.style_target = style_target
+        self.content_masks = content_masks
+        self.style_masks = style_masks
+
+        self.loss_names = {                                                    # loss.py:16-21
+            'content': 'Content loss',
+            'style':   'Style loss',
+            'nima':    'NIMA loss',
+            'photo':   'Photorealism regualarization'
+        }
+        self.loss_weights = {                                                  # loss.py:28-33
+            'content': float(args.content_weight),
+            'style':   float(args.style_weight),
+            'nima':    float(getattr(args, 'nima_weight', 0.0)),
+            'photo':   float(args.regularization_weight)
+        }
+        if self.loss_weights['nima'] != 0.0:
+            raise NotImplementedError("the NIMA term (loss.py:141-153) is not part of this hot path: nima_weight must "
+                                      "be 0 (got %g)" % self.loss_weights['nima'])
+        if (content_masks is None) != (style_masks is None):
+            pass        # reference: masks are used only if both are given (loss.py:110); otherwise all-ones
+        if content_masks is not None and style_masks is not None and len(content_masks) != len(style_masks):
+            raise ValueError("content and style masks differ in count (%d vs %d)" % (len(content_masks), len(style_masks)))
+        if matting not in ("v2", "v3"):
+            raise ValueError("matting must be 'v2' or 'v3'")
+        self.matting_variant = matting
+        self.matting_params = {                                                # loss.py:38-41
+            'epsilon': args.matting_epsilon,
+            'window_radius': args.matting_window_radius,
+        }
+        self.matting_laplacian = None
+
+        any_t = next(iter(content_target.values())) if len(content_target) else next(iter(style_target.values()))
+        self.device = any_t.device
+        self._acc = torch.zeros(3, dtype=torch.float64, device=self.device)    # content, style, photo (unweighted)
+        self._out = torch.zeros(5, dtype=torch.float32, device=self.device)    # content, style, nima, photo, total
+        self._layer_cache = {}      # style layer name -> dict(masks, K, A, ws, seed)
+        self._content_seeds = {}
+        self._photo_grad = None
+        self._seeds = None
+
+    def initialize_matting_laplacian(self, image):                            # loss.py:45-46
+        """image: (H,W,3) float64 (as in style_transfer.py:315) or float32.  If every value is exactly representable
+        in float32 (always true for the script: the image was decoded to float32), HBM traffic is float32 and the
+        stencil arithmetic float64; otherwise everything is float64."""
+        img = torch.as_tensor(image)
+        if not img.is_cuda:
+            img = img.to(self.device)
+        exact = img.dtype == torch.float32 or bool((img.to(torch.float32).to(img.dtype) == img).all())
+        cls = MattingLaplacianV2 if self.matting_variant == "v2" else MattingLaplacianV3
+        self.matting_laplacian = cls(img, storage_dtype=torch.float32 if exact else torch.float64,
+                                     compute_dtype=torch.float64, **self.matting_params)
+
+    def __call__(self, image, outputs):                                       # loss.py:48-49
+        return self.compute_loss(image, outputs)
+
+    # ------------------------------------------------------------------------------------------
+    def _style_layer_state(self, name, target, output):
+        st = self._layer_cache.get(name)
+        if st is not None and st["shape"] == tuple(output.shape):
+            return st
+        _, h, w, C = output.shape
+        _, hs, ws_, Cs = target.shape
+        if C != Cs:
+            raise ValueError("%s: target has %d channels, output %d" % (name, Cs, C))
+        exist = self.content_masks is not None and self.style_masks is not None     # loss.py:110
+        if exist:
+            K = len(self.content_masks)
+            cm = torch.stack([kernels.resize_bilinear(_plane(m, self.device), (h, w)).reshape(-1)
+                              for m in self.content_masks]).contiguous()             # loss.py:112-117
+            sm = torch.stack([kernels.resize_bilinear(_plane(m, self.device), (hs, ws_)).reshape(-1)
+                              for m in self.style_masks]).contiguous()
+        else:
+            K, cm, sm = 1, None, None                                                # loss.py:119-120
+        ws = kernels.gram_workspace(max(h * w, hs * ws_), C, K, self.device)
+        A = kernels.gram_masked(target.reshape(hs * ws_, C), sm, K, ws)              # constant style Grams
+        st = {"shape": tuple(output.shape), "K": K, "masks": cm, "A": A, "ws": ws, "seed": torch.empty_like(output)}
+        self._layer_cache[name] = st
+        return st
+
+    def compute_loss(self, image, outputs):                                   # loss.py:53-78
+        content_output, style_output = outputs['content'], outputs['style']
+        wts = self.loss_weights
+        self._acc.zero_()
+        seeds = {}
+        n_args = 2.0                                                          # len(args) in iter_on_layers, loss.py:85
+
+        for name, target in self.content_target.items():                     # loss.py:59, :90-92
+            out = content_output[name]
+            seed = self._content_seeds.get(name)
+            if seed is None or seed.shape != out.shape:
+                seed = self._content_seeds[name] = torch.empty_like(out)
+            kernels.content_layer(target, out, 1.0 / n_args, wts['content'] / n_args, self._acc[0:1], seed)
+            seeds[name] = seed
+
+        for name, target in self.style_target.items():                       # loss.py:62, :104-137
+            out = style_output[name]
+            st = self._style_layer_state(name, target, out)
+            _, h, w, C = out.shape
+            F = out.reshape(h * w, C)
+            G = kernels.gram_masked(F, st["masks"], st["K"], st["ws"])
+            shared = name in seeds                                            # a layer can be both content and style
+            dF = seeds[name] if shared else st["seed"]
+            kernels.style_layer_backward(F, st["masks"], st["K"], G, st["A"], 1.0 / n_args, wts['style'] / n_args,
+                                         self._acc[1:2], dF.reshape(h * w, C), accumulate=shared, workspace=st["ws"])
+            seeds[name] = dF
+
+        self._photo_grad = None
+        if wts['photo'] > 0:                                                  # loss.py:67-69, :157-161
+            if self.matting_laplacian is None:
+                raise RuntimeError("regularization_weight > 0 but initialize_matting_laplacian() was not called")
+            self._photo_grad = self.calculate_photorealism_regularization(image, _with_gradient=True)
+
+        kernels.loss_finalize(self._acc, wts['content'], wts['style'], wts['photo'], self._out)   # loss.py:72
+        self._seeds = seeds
+        loss_dict = {self.loss_names['content']: self._out[0], self.loss_names['style']: self._out[1],
+                     self.loss_names['nima']: self._out[2]}
+        if wts['photo'] > 0:
+            loss_dict[self.loss_names['photo']] = self._out[3]
+        loss_dict['Total loss'] = self._out[4]                                # loss.py:76
+        return loss_dict
+
+    def gradient(self, extractor, out=None):
+        """d(Total loss)/d(image) for the latest compute_loss call: the role of tape.gradient in
+        style_transfer.py:341.  `extractor` is the StyleContentModel whose outputs were passed in."""
+        if self._seeds is None:
+            raise RuntimeError("gradient() needs a preceding compute_loss() call")
+        g = extractor.backward(self._seeds, out=out)
+        if self._photo_grad is not None:
+            kernels.axpby(g, g, 1.0, self._photo_grad.reshape(g.shape), 1.0)
+        return g
+
+    # ------------------------------------------------------------------------------------------
+    # the reference's static helpers, evaluated on the GPU
+    @staticmethod
+    def calculate_layer_content_loss(target, output):                        # loss.py:90-92
+        acc = torch.zeros(1, dtype=torch.float64, device=output.device)
+        kernels.content_layer(target.contiguous(), output.contiguous(), 1.0, 0.0, acc, None)
+        return acc[0].to(output.dtype)
+
+    @staticmethod
+    def calculate_gram_matrix(convolution_layer, mask):                      # loss.py:96-102
+        C = convolution_layer.shape[3]
+        F = convolution_layer.reshape(-1, C).contiguous()
+        m = None if mask is None else mask.to(torch.float32).reshape(1, -1).contiguous()
+        return kernels.gram_masked(F, m, 1)[0]
+
+    def calculate_layer_style_loss(self, target, output):                    # loss.py:104-137
+        st = self._style_layer_state("<adhoc %s>" % (tuple(output.shape),), target, output)
+        _, h, w, C = output.shape
+        F = output.reshape(h * w, C).contiguous()
+        G = kernels.gram_masked(F, st["masks"], st["K"], st["ws"])
+        acc = torch.zeros(1, dtype=torch.float64, device=output.device)
+        kernels.style_layer_backward(F, st["masks"], st["K"], G, st["A"], 1.0, 0.0, acc, None, workspace=st["ws"])
+        return acc[0].to(output.dtype)
+
+    def calculate_photorealism_regularization(self, image, _with_gradient=False):   # loss.py:157-161
+        lap = self.matting_laplacian
+        HW = lap.shape[-1]
+        p = image.reshape(HW, -1)
+        if not _with_gradient:
+            _, q = lap.quadratic_form(p, want_y=False)
+            return q.to(image.dtype)
+        if self._photo_grad_buf is None or self._photo_grad_buf.shape != p.shape or self._photo_grad_buf.dtype != lap._op.storage_dtype:
+            self._photo_grad_buf = torch.empty(HW, 3, dtype=lap._op.storage_dtype, device=image.device)
+        # y = 2 w_p L x is the gradient of w_p x^T L x (L symmetric); x^T L x lands in the float64 accumulator
+        y, _ = lap.quadratic_form(p, want_y=True, y_scale=2.0 * self.loss_weights['photo'], out=self._photo_grad_buf,
+                                  quad_out=self._acc[2:3])
+        return y if y.dtype == torch.float32 else y.to(torch.float32)
+
+    _photo_grad_buf = None
+
+
+def _plane(mask, device):
+    """(1,H,W,1) / (H,W) mask (numpy or tensor) -> contiguous float32 CUDA plane (H,W)."""
+    m = torch.as_tensor(mask)
+    if m.dim() == 4:
+        m = m[0, :, :, 0]
+    return m.to(device=device, dtype=torch.float32).contiguous()
+
+
+def dict_zip(*dicts):                                                         # loss.py:163-165
+    for k in dicts[0].keys():
+        yield [d[k] for d in dicts]

@@ -54,6 +54,6 @@ class MattingLaplacian:
         return self._ensure_coeffs()[1]
 
     # extension used by Loss: x^T L x (float64) and optionally y_scale * L x in one pass over HBM
-    def quadratic_form(self, x, want_y=False, y_scale=1.0, out=None):
+    def quadratic_form(self, x, want_y=False, y_scale=1.0, out=None, quad_out=None):
         x = as_cuda_tensor(x, self._op.storage_dtype).reshape(-1, 3)
-        return self._op.apply3(x, want_y=want_y, want_quad=True, y_scale=y_scale, out=out)
+        return self._op.apply3(x, want_y=want_y, want_quad=True, y_scale=y_scale, out=out, quad_out=quad_out)

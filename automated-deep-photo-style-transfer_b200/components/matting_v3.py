@@ -53,6 +53,6 @@ class MattingLaplacian:
             self._coo = SparseCOO(torch.stack([rows, cols], 1), vals.to(self.dtype), self.shape)
         return self._coo
 
-    def quadratic_form(self, x, want_y=False, y_scale=1.0, out=None):
+    def quadratic_form(self, x, want_y=False, y_scale=1.0, out=None, quad_out=None):
         x = x.to(self._op.storage_dtype).reshape(-1, 3).contiguous()
-        return self._op.apply3(x, want_y=want_y, want_quad=True, y_scale=y_scale, out=out)
+        return self._op.apply3(x, want_y=want_y, want_quad=True, y_scale=y_scale, out=out, quad_out=quad_out)

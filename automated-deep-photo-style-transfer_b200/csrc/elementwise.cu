@@ -61,10 +61,10 @@ adam_clip_kernel(float* __restrict__ x, const float* __restrict__ g, float* __re
 // content layer: loss += scale * mean((t-o)^2); dOut (=|+=) scale * 2 (o-t) / n
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
-content_kernel(const float* __restrict__ tgt, const float* __restrict__ out, size_t n, double scale,
-               double* __restrict__ loss, float* __restrict__ dOut, int accumulate) {
+content_kernel(const float* __restrict__ tgt, const float* __restrict__ out, size_t n, double loss_scale,
+               double grad_scale, double* __restrict__ loss, float* __restrict__ dOut, int accumulate) {
     __shared__ double red[32];
-    const float gs = float(2.0 * scale / double(n));
+    const float gs = float(2.0 * grad_scale / double(n));
     double acc = 0.0;
     const size_t stride = size_t(gridDim.x) * blockDim.x;
     for (size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) {
@@ -73,7 +73,7 @@ content_kernel(const float* __restrict__ tgt, const float* __restrict__ out, siz
         if (dOut) dOut[i] = accumulate ? dOut[i] + gs * d : gs * d;
     }
     acc = block_sum<double>(acc, red);
-    if (threadIdx.x == 0 && loss) atomicAdd(loss, acc * scale / double(n));
+    if (threadIdx.x == 0 && loss) atomicAdd(loss, acc * loss_scale / double(n));
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -103,6 +103,14 @@ axpby_kernel(float* __restrict__ out, const float* __restrict__ a, float alpha, 
         out[i] = alpha * a[i] + (b ? beta * b[i] : 0.0f);
 }
 
+__global__ void loss_finalize_kernel(const double* __restrict__ acc, double wc, double ws, double wp,
+                                     float* __restrict__ out) {
+    const double c = acc[0], s = acc[1], p = acc[2];
+    out[0] = float(c); out[1] = float(s); out[2] = 0.0f; out[3] = float(p);
+    // loss.py:72: the terms are float32 tensors when they are weighted and added
+    out[4] = float(wc) * float(c) + float(ws) * float(s) + (wp > 0.0 ? float(wp) * float(p) : 0.0f);
+}
+
 }  // namespace adpst
 
 extern "C" {
@@ -121,12 +129,12 @@ int adpst_adam_clip_step(float* x_dev, const float* grad_dev, float* m_dev, floa
     return ADPST_OK;
 }
 
-int adpst_content_layer(const float* target_dev, const float* output_dev, size_t n, double scale, double* loss_dev,
-                        float* dOut_dev, int accumulate, adpst_stream_t stream) {
+int adpst_content_layer(const float* target_dev, const float* output_dev, size_t n, double loss_scale, double grad_scale,
+                        double* loss_dev, float* dOut_dev, int accumulate, adpst_stream_t stream) {
     using namespace adpst;
     ADPST_REQUIRE(target_dev && output_dev && n > 0, "content_layer: NULL or empty input");
-    content_kernel<<<grid_for(n, 256), 256, 0, as_stream(stream)>>>(target_dev, output_dev, n, scale, loss_dev, dOut_dev,
-                                                                    accumulate);
+    content_kernel<<<grid_for(n, 256), 256, 0, as_stream(stream)>>>(target_dev, output_dev, n, loss_scale, grad_scale,
+                                                                    loss_dev, dOut_dev, accumulate);
     ADPST_LAUNCH_CHECK();
     return ADPST_OK;
 }
@@ -136,6 +144,15 @@ int adpst_resize_bilinear(const float* src_dev, int Hs, int Ws, float* dst_dev, 
     ADPST_REQUIRE(src_dev && dst_dev && Hs > 0 && Ws > 0 && Hd > 0 && Wd > 0, "resize_bilinear: bad argument");
     dim3 block(32, 8), grid((Wd + 31) / 32, (Hd + 7) / 8);
     resize_bilinear_kernel<<<grid, block, 0, as_stream(stream)>>>(src_dev, Hs, Ws, dst_dev, Hd, Wd);
+    ADPST_LAUNCH_CHECK();
+    return ADPST_OK;
+}
+
+int adpst_loss_finalize(const double* acc_dev, double w_content, double w_style, double w_photo, float* out_dev,
+                        adpst_stream_t stream) {
+    using namespace adpst;
+    ADPST_REQUIRE(acc_dev && out_dev, "loss_finalize: NULL argument");
+    loss_finalize_kernel<<<1, 1, 0, as_stream(stream)>>>(acc_dev, w_content, w_style, w_photo, out_dev);
     ADPST_LAUNCH_CHECK();
     return ADPST_OK;
 }

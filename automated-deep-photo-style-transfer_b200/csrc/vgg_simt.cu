@@ -1,0 +1,489 @@
+// vgg_simt.cu -- VGG19 (block1_conv1 .. block5_conv1) forward and data-gradient, float32 CUDA-core path.
+//
+// Replaces   components/VGG19/model.py:27-41  (x255, caffe preprocess, Keras VGG19 convs/pools, post-ReLU taps)
+//            style_transfer.py:341            (tape.gradient through the extractor; weights frozen model.py:11,25)
+//
+// This is the exact-float32 path: every product and sum is IEEE float32, so it holds the 1e-5 parity bar by
+// construction.  The tcgen05 (3xTF32) implicit-GEMM kernels in conv_tc.cu are validated against it.
+//
+// Layout: activations NHWC (N = 1); forward weights [tap][Cin][Cout] (= Keras HWIO), gradient weights
+// [tap'][Cout][Cin] with the taps flipped, so the data gradient is the same 3x3 SAME convolution.
+#include "common.cuh"
+
+namespace adpst {
+
+constexpr int kNumConv = ADPST_VGG_NUM_CONV;
+// channels and "pool before this conv" flags of the 13 convolutions
+__host__ __device__ constexpr int conv_cin(int i) {
+    return i == 0 ? 3 : i <= 2 ? 64 : i <= 4 ? 128 : i <= 8 ? 256 : 512;
+}
+__host__ __device__ constexpr int conv_cout(int i) { return i <= 1 ? 64 : i <= 3 ? 128 : i <= 7 ? 256 : 512; }
+// pool j sits after conv {1, 3, 7, 11}
+static const int kPoolAfter[ADPST_VGG_NUM_POOL] = {1, 3, 7, 11};
+static inline int pools_before(int conv) { return conv >= 12 ? 4 : conv >= 8 ? 3 : conv >= 4 ? 2 : conv >= 2 ? 1 : 0; }
+
+// ---------------------------------------------------------------------------------------------
+// 3x3 SAME convolution as an implicit GEMM on CUDA cores.
+//   CTA tile: 8 x 16 pixels x 64 output channels, 128 threads, 8 px x 8 ch per thread, Cin in chunks of 8.
+// MODE_FWD : y = relu(acc + bias)
+// MODE_BWD : g = acc (+ seed);  y = mask_src > 0 ? g : 0      (seed / mask_src optional)
+// PRE      : the input is the [0,1] RGB image; 255*x - mean with the channel flip is applied on load
+//            (model.py:28-29); zero padding applies to the preprocessed tensor.
+// ---------------------------------------------------------------------------------------------
+constexpr int CT_H = 8, CT_W = 16, CT_N = 64, CT_K = 8, CT_THREADS = 128, CT_XP = 20;
+enum { MODE_FWD = 0, MODE_BWD = 1 };
+
+template <int MODE, bool PRE>
+__global__ void __launch_bounds__(CT_THREADS)
+conv3x3_simt_kernel(const float* __restrict__ X, const float* __restrict__ Wt, const float* __restrict__ bias,
+                    float* __restrict__ Y, const float* __restrict__ seed, const float* __restrict__ mask_src,
+                    int H, int W, int Cin, int Cout, int tiles_w) {
+    __shared__ __align__(16) float sX[CT_K][CT_H + 2][CT_XP];
+    __shared__ __align__(16) float sW[9][CT_K][CT_N];
+
+    const int tile = blockIdx.x;
+    const int y0 = (tile / tiles_w) * CT_H, x0 = (tile % tiles_w) * CT_W;
+    const int n0 = blockIdx.y * CT_N;
+    const int tid = threadIdx.x;
+    const int tx = tid & 7, ty = tid >> 3;
+    const int row = ty >> 1, wseg = (ty & 1) * 8;
+
+    float acc[8][8];
+#pragma unroll
+    for (int p = 0; p < 8; ++p)
+#pragma unroll
+        for (int n = 0; n < 8; ++n) acc[p][n] = 0.0f;
+
+    for (int ci0 = 0; ci0 < Cin; ci0 += CT_K) {
+        // ---- stage the input halo tile, transposed to [ci][row][col]
+        if (PRE) {
+            for (int px = tid; px < (CT_H + 2) * (CT_W + 2); px += CT_THREADS) {
+                const int r = px / (CT_W + 2), c = px - r * (CT_W + 2);
+                const int gy = y0 - 1 + r, gx = x0 - 1 + c;
+                float v0 = 0.f, v1 = 0.f, v2 = 0.f;
+                if (gy >= 0 && gy < H && gx >= 0 && gx < W) {
+                    const float* q = X + (size_t(gy) * W + gx) * 3;
+                    v0 = 255.0f * q[2] - 103.939f;      // B
+                    v1 = 255.0f * q[1] - 116.779f;      // G
+                    v2 = 255.0f * q[0] - 123.68f;       // R
+                }
+                sX[0][r][c] = v0; sX[1][r][c] = v1; sX[2][r][c] = v2;
+#pragma unroll
+                for (int k = 3; k < CT_K; ++k) sX[k][r][c] = 0.f;
+            }
+        } else {
+            for (int idx = tid; idx < (CT_H + 2) * (CT_W + 2) * 2; idx += CT_THREADS) {
+                const int px = idx >> 1, half = idx & 1;
+                const int r = px / (CT_W + 2), c = px - r * (CT_W + 2);
+                const int gy = y0 - 1 + r, gx = x0 - 1 + c;
+                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (gy >= 0 && gy < H && gx >= 0 && gx < W)
+                    v = __ldg(reinterpret_cast<const float4*>(X + (size_t(gy) * W + gx) * Cin + ci0 + half * 4));
+                sX[half * 4 + 0][r][c] = v.x; sX[half * 4 + 1][r][c] = v.y;
+                sX[half * 4 + 2][r][c] = v.z; sX[half * 4 + 3][r][c] = v.w;
+            }
+        }
+        // ---- stage the weights of this chunk: [tap][ci][64]
+        for (int idx = tid; idx < 9 * CT_K * (CT_N / 4); idx += CT_THREADS) {
+            const int tap = idx / (CT_K * (CT_N / 4));
+            const int rem = idx - tap * (CT_K * (CT_N / 4));
+            const int ci = rem / (CT_N / 4), n4 = rem - ci * (CT_N / 4);
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (ci0 + ci < Cin)
+                v = __ldg(reinterpret_cast<const float4*>(Wt + (size_t(tap) * Cin + ci0 + ci) * Cout + n0 + n4 * 4));
+            *reinterpret_cast<float4*>(&sW[tap][ci][n4 * 4]) = v;
+        }
+        __syncthreads();
+
+#pragma unroll
+        for (int kh = 0; kh < 3; ++kh) {
+#pragma unroll 2
+            for (int ci = 0; ci < CT_K; ++ci) {
+                float xv[10];
+                const float* xr = &sX[ci][row + kh][wseg];
+                const float4 a = *reinterpret_cast<const float4*>(xr);
+                const float4 b = *reinterpret_cast<const float4*>(xr + 4);
+                const float2 c = *reinterpret_cast<const float2*>(xr + 8);
+                xv[0] = a.x; xv[1] = a.y; xv[2] = a.z; xv[3] = a.w; xv[4] = b.x; xv[5] = b.y; xv[6] = b.z; xv[7] = b.w;
+                xv[8] = c.x; xv[9] = c.y;
+#pragma unroll
+                for (int kw = 0; kw < 3; ++kw) {
+                    const float4 w0 = *reinterpret_cast<const float4*>(&sW[kh * 3 + kw][ci][tx * 8]);
+                    const float4 w1 = *reinterpret_cast<const float4*>(&sW[kh * 3 + kw][ci][tx * 8 + 4]);
+                    const float wv[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+#pragma unroll
+                    for (int p = 0; p < 8; ++p)
+#pragma unroll
+                        for (int n = 0; n < 8; ++n) acc[p][n] = fmaf(xv[p + kw], wv[n], acc[p][n]);
+                }
+            }
+        }
+        __syncthreads();
+    }
+
+    // ---- epilogue
+    const int gy = y0 + row;
+    if (gy >= H) return;
+    const int nb = n0 + tx * 8;
+    float bv[8];
+    if (MODE == MODE_FWD) {
+        const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias + nb));
+        const float4 b1 = __ldg(reinterpret_cast<const float4*>(bias + nb + 4));
+        bv[0] = b0.x; bv[1] = b0.y; bv[2] = b0.z; bv[3] = b0.w; bv[4] = b1.x; bv[5] = b1.y; bv[6] = b1.z; bv[7] = b1.w;
+    }
+#pragma unroll
+    for (int p = 0; p < 8; ++p) {
+        const int gx = x0 + wseg + p;
+        if (gx >= W) continue;
+        const size_t o = (size_t(gy) * W + gx) * Cout + nb;
+        float r[8];
+        if (MODE == MODE_FWD) {
+#pragma unroll
+            for (int n = 0; n < 8; ++n) r[n] = fmaxf(acc[p][n] + bv[n], 0.0f);
+        } else {
+#pragma unroll
+            for (int n = 0; n < 8; ++n) r[n] = acc[p][n];
+            if (seed != nullptr) {
+                const float4 s0 = __ldg(reinterpret_cast<const float4*>(seed + o));
+                const float4 s1 = __ldg(reinterpret_cast<const float4*>(seed + o + 4));
+                r[0] += s0.x; r[1] += s0.y; r[2] += s0.z; r[3] += s0.w; r[4] += s1.x; r[5] += s1.y; r[6] += s1.z; r[7] += s1.w;
+            }
+            if (mask_src != nullptr) {
+                const float4 m0 = __ldg(reinterpret_cast<const float4*>(mask_src + o));
+                const float4 m1 = __ldg(reinterpret_cast<const float4*>(mask_src + o + 4));
+                const float mv[8] = {m0.x, m0.y, m0.z, m0.w, m1.x, m1.y, m1.z, m1.w};
+#pragma unroll
+                for (int n = 0; n < 8; ++n) r[n] = mv[n] > 0.0f ? r[n] : 0.0f;
+            }
+        }
+        *reinterpret_cast<float4*>(Y + o) = make_float4(r[0], r[1], r[2], r[3]);
+        *reinterpret_cast<float4*>(Y + o + 4) = make_float4(r[4], r[5], r[6], r[7]);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// data gradient of block1_conv1 back to the [0,1] RGB image (Cout' = 3: too thin for the tiled kernel)
+//   dImg[p, rgb] = 255 * sum_{tap, co} dPre[p + tap - 1, co] * W[2-kh][2-kw][ci = 2 - rgb][co]
+// Wg: [tap'][3 (rgb)][64] already flipped / permuted / scaled by 255.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128)
+conv1_dgrad_image_kernel(const float* __restrict__ dPre, const float* __restrict__ Wg, float* __restrict__ dImg, int H,
+                         int W) {
+    __shared__ __align__(16) float sW[9 * 3 * 64];
+    for (int i = threadIdx.x; i < 9 * 3 * 64; i += blockDim.x) sW[i] = Wg[i];
+    __syncthreads();
+    const int gx = blockIdx.x * 32 + (threadIdx.x & 31), gy = blockIdx.y * 4 + (threadIdx.x >> 5);
+    if (gx >= W || gy >= H) return;
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f;
+#pragma unroll
+    for (int kh = 0; kh < 3; ++kh) {
+        const int yy = gy + kh - 1;
+        if (yy < 0 || yy >= H) continue;
+#pragma unroll
+        for (int kw = 0; kw < 3; ++kw) {
+            const int xx = gx + kw - 1;
+            if (xx < 0 || xx >= W) continue;
+            const float4* q = reinterpret_cast<const float4*>(dPre + (size_t(yy) * W + xx) * 64);
+            const float* w = sW + (kh * 3 + kw) * 192;
+#pragma unroll 4
+            for (int c4 = 0; c4 < 16; ++c4) {
+                const float4 v = __ldg(q + c4);
+                const float4 w0 = *reinterpret_cast<const float4*>(w + c4 * 4);
+                const float4 w1 = *reinterpret_cast<const float4*>(w + 64 + c4 * 4);
+                const float4 w2 = *reinterpret_cast<const float4*>(w + 128 + c4 * 4);
+                a0 = fmaf(v.x, w0.x, a0); a0 = fmaf(v.y, w0.y, a0); a0 = fmaf(v.z, w0.z, a0); a0 = fmaf(v.w, w0.w, a0);
+                a1 = fmaf(v.x, w1.x, a1); a1 = fmaf(v.y, w1.y, a1); a1 = fmaf(v.z, w1.z, a1); a1 = fmaf(v.w, w1.w, a1);
+                a2 = fmaf(v.x, w2.x, a2); a2 = fmaf(v.y, w2.y, a2); a2 = fmaf(v.z, w2.z, a2); a2 = fmaf(v.w, w2.w, a2);
+            }
+        }
+    }
+    float* o = dImg + (size_t(gy) * W + gx) * 3;
+    o[0] = a0; o[1] = a1; o[2] = a2;
+}
+
+// ---------------------------------------------------------------------------------------------
+// 2x2/2 VALID max-pool, forward and (fused with the ReLU mask and an optional loss seed) backward
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+maxpool2_kernel(const float* __restrict__ X, float* __restrict__ P, int H, int W, int C) {
+    const int Hp = H / 2, Wp = W / 2, C4 = C / 4;
+    const size_t total = size_t(Hp) * Wp * C4;
+    for (size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += size_t(gridDim.x) * blockDim.x) {
+        const int c4 = int(i % C4);
+        const size_t pp = i / C4;
+        const int px = int(pp % Wp), py = int(pp / Wp);
+        const float4* b = reinterpret_cast<const float4*>(X + (size_t(2 * py) * W + 2 * px) * C) + c4;
+        const float4 v00 = __ldg(b), v01 = __ldg(b + C4);
+        const float4 v10 = __ldg(b + size_t(W) * C4), v11 = __ldg(b + size_t(W) * C4 + C4);
+        float4 m;
+        m.x = fmaxf(fmaxf(v00.x, v01.x), fmaxf(v10.x, v11.x));
+        m.y = fmaxf(fmaxf(v00.y, v01.y), fmaxf(v10.y, v11.y));
+        m.z = fmaxf(fmaxf(v00.z, v01.z), fmaxf(v10.z, v11.z));
+        m.w = fmaxf(fmaxf(v00.w, v01.w), fmaxf(v10.w, v11.w));
+        reinterpret_cast<float4*>(P)[i] = m;
+    }
+}
+
+// dPre[pos] = Y[pos] > 0 ? ((pos is the first max of its window ? dP[window] : 0) + seed[pos]) : 0
+// One thread per (full-resolution pixel, 4 channels); pixels outside every window (odd H/W) only see the seed.
+__global__ void __launch_bounds__(256)
+unpool_relu_kernel(const float* __restrict__ Y, const float* __restrict__ dP, const float* __restrict__ seed,
+                   float* __restrict__ dPre, int H, int W, int C) {
+    const int Hp = H / 2, Wp = W / 2, C4 = C / 4;
+    const size_t total = size_t(H) * W * C4;
+    for (size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += size_t(gridDim.x) * blockDim.x) {
+        const int c4 = int(i % C4);
+        const size_t pp = i / C4;
+        const int x = int(pp % W), y = int(pp / W);
+        const float4 me = __ldg(reinterpret_cast<const float4*>(Y) + i);
+        float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
+        const int py = y >> 1, px = x >> 1;
+        if (py < Hp && px < Wp) {
+            const float4* b = reinterpret_cast<const float4*>(Y + (size_t(2 * py) * W + 2 * px) * C) + c4;
+            const float4 v[4] = {__ldg(b), __ldg(b + C4), __ldg(b + size_t(W) * C4), __ldg(b + size_t(W) * C4 + C4)};
+            const float4 d = __ldg(reinterpret_cast<const float4*>(dP + (size_t(py) * Wp + px) * C) + c4);
+            const int self = (y & 1) * 2 + (x & 1);
+            const float* vf = reinterpret_cast<const float*>(v);
+            const float df[4] = {d.x, d.y, d.z, d.w};
+            float gf[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                int arg = 0;
+                float best = vf[k];
+#pragma unroll
+                for (int j = 1; j < 4; ++j)
+                    if (vf[j * 4 + k] > best) { best = vf[j * 4 + k]; arg = j; }
+                gf[k] = (arg == self) ? df[k] : 0.0f;
+            }
+            g = make_float4(gf[0], gf[1], gf[2], gf[3]);
+        }
+        if (seed != nullptr) {
+            const float4 s = __ldg(reinterpret_cast<const float4*>(seed) + i);
+            g.x += s.x; g.y += s.y; g.z += s.z; g.w += s.w;
+        }
+        g.x = me.x > 0.f ? g.x : 0.f; g.y = me.y > 0.f ? g.y : 0.f;
+        g.z = me.z > 0.f ? g.z : 0.f; g.w = me.w > 0.f ? g.w : 0.f;
+        reinterpret_cast<float4*>(dPre)[i] = g;
+    }
+}
+
+// dPre = Y > 0 ? seed : 0     (top of the chain)
+__global__ void __launch_bounds__(256)
+relu_mask_kernel(const float* __restrict__ Y, const float* __restrict__ seed, float* __restrict__ dPre, size_t n4) {
+    for (size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n4; i += size_t(gridDim.x) * blockDim.x) {
+        const float4 y = __ldg(reinterpret_cast<const float4*>(Y) + i);
+        float4 s = __ldg(reinterpret_cast<const float4*>(seed) + i);
+        s.x = y.x > 0.f ? s.x : 0.f; s.y = y.y > 0.f ? s.y : 0.f; s.z = y.z > 0.f ? s.z : 0.f; s.w = y.w > 0.f ? s.w : 0.f;
+        reinterpret_cast<float4*>(dPre)[i] = s;
+    }
+}
+
+// gradient weights: Wb[tap'][co][ci] = W[8 - tap'][ci][co]
+__global__ void flip_transpose_weights_kernel(const float* __restrict__ Wf, float* __restrict__ Wb, int Cin, int Cout) {
+    const size_t total = size_t(9) * Cin * Cout;
+    for (size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += size_t(gridDim.x) * blockDim.x) {
+        const int ci = int(i % Cin);
+        const size_t r = i / Cin;
+        const int co = int(r % Cout), tap = int(r / Cout);
+        Wb[i] = Wf[(size_t(8 - tap) * Cin + ci) * Cout + co];
+    }
+}
+
+// image-gradient weights of conv 0: Wg[tap'][rgb][co] = 255 * W[8 - tap'][ci = 2 - rgb][co]
+__global__ void conv1_image_weights_kernel(const float* __restrict__ Wf, float* __restrict__ Wg) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= 9 * 3 * 64) return;
+    const int co = i % 64, rgb = (i / 64) % 3, tap = i / 192;
+    Wg[i] = 255.0f * Wf[(size_t(8 - tap) * 3 + (2 - rgb)) * 64 + co];
+}
+
+static inline unsigned stream_grid(size_t items, int threads = 256) {
+    const size_t want = (items + threads - 1) / threads, cap = size_t(num_sms()) * 16;
+    return unsigned(want < cap ? (want ? want : 1) : cap);
+}
+
+}  // namespace adpst
+
+// ---------------------------------------------------------------------------------------------
+// handle + orchestration
+// ---------------------------------------------------------------------------------------------
+struct adpst_vgg {
+    float* wf[adpst::kNumConv] = {};    // [tap][Cin][Cout]
+    float* wb[adpst::kNumConv] = {};    // [tap'][Cout][Cin]  (wb[0] unused)
+    float* bias[adpst::kNumConv] = {};
+    float* wg0 = nullptr;               // [tap'][3][64]
+};
+
+namespace adpst {
+
+static void layer_hw(int conv, int H, int W, int* h, int* w) {
+    const int p = pools_before(conv);
+    *h = H >> p;     // floor division by 2, p times (VALID pooling)
+    *w = W >> p;
+}
+
+static int launch_conv(int mode, bool pre, const float* X, const float* Wt, const float* bias, float* Y, const float* seed,
+                       const float* mask, int H, int W, int Cin, int Cout, cudaStream_t st) {
+    ADPST_REQUIRE(Cout % CT_N == 0, "conv3x3: Cout=%d must be a multiple of %d", Cout, CT_N);
+    ADPST_REQUIRE(pre || Cin % CT_K == 0, "conv3x3: Cin=%d must be a multiple of %d", Cin, CT_K);
+    const int tw = (W + CT_W - 1) / CT_W, th = (H + CT_H - 1) / CT_H;
+    dim3 grid(tw * th, Cout / CT_N);
+    if (mode == MODE_FWD && pre)
+        conv3x3_simt_kernel<MODE_FWD, true><<<grid, CT_THREADS, 0, st>>>(X, Wt, bias, Y, seed, mask, H, W, Cin, Cout, tw);
+    else if (mode == MODE_FWD)
+        conv3x3_simt_kernel<MODE_FWD, false><<<grid, CT_THREADS, 0, st>>>(X, Wt, bias, Y, seed, mask, H, W, Cin, Cout, tw);
+    else
+        conv3x3_simt_kernel<MODE_BWD, false><<<grid, CT_THREADS, 0, st>>>(X, Wt, bias, Y, seed, mask, H, W, Cin, Cout, tw);
+    ADPST_LAUNCH_CHECK();
+    return ADPST_OK;
+}
+
+}  // namespace adpst
+
+extern "C" {
+
+int adpst_vgg_conv_shape(int i, int H, int W, int* h, int* w, int* c) {
+    using namespace adpst;
+    ADPST_REQUIRE(i >= 0 && i < kNumConv && h && w && c, "vgg_conv_shape: bad argument");
+    layer_hw(i, H, W, h, w);
+    *c = conv_cout(i);
+    return ADPST_OK;
+}
+
+int adpst_vgg_pool_shape(int j, int H, int W, int* h, int* w, int* c) {
+    using namespace adpst;
+    ADPST_REQUIRE(j >= 0 && j < ADPST_VGG_NUM_POOL && h && w && c, "vgg_pool_shape: bad argument");
+    *h = H >> (j + 1);
+    *w = W >> (j + 1);
+    *c = conv_cout(kPoolAfter[j]);
+    return ADPST_OK;
+}
+
+int adpst_vgg_create(const float* const* kernels_dev, const float* const* biases_dev, adpst_stream_t stream,
+                     adpst_vgg** out) {
+    using namespace adpst;
+    ADPST_REQUIRE(kernels_dev && biases_dev && out, "vgg_create: NULL argument");
+    *out = nullptr;
+    cudaStream_t st = as_stream(stream);
+    auto* h = new adpst_vgg();
+    cudaError_t e = cudaSuccess;
+    for (int i = 0; i < kNumConv && e == cudaSuccess; ++i) {
+        if (!kernels_dev[i] || !biases_dev[i]) {
+            adpst_vgg_destroy(h);
+            return fail(ADPST_ERR_INVALID, "vgg_create: kernel/bias %d is NULL", i);
+        }
+        const size_t nw = size_t(9) * conv_cin(i) * conv_cout(i);
+        e = cudaMalloc(reinterpret_cast<void**>(&h->wf[i]), nw * 4);
+        if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&h->bias[i]), size_t(conv_cout(i)) * 4);
+        if (e == cudaSuccess && i > 0) e = cudaMalloc(reinterpret_cast<void**>(&h->wb[i]), nw * 4);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(h->wf[i], kernels_dev[i], nw * 4, cudaMemcpyDeviceToDevice, st);
+        if (e == cudaSuccess)
+            e = cudaMemcpyAsync(h->bias[i], biases_dev[i], size_t(conv_cout(i)) * 4, cudaMemcpyDeviceToDevice, st);
+        if (e == cudaSuccess && i > 0) {
+            flip_transpose_weights_kernel<<<stream_grid(nw), 256, 0, st>>>(h->wf[i], h->wb[i], conv_cin(i), conv_cout(i));
+            e = cudaGetLastError();
+        }
+    }
+    if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&h->wg0), 9 * 3 * 64 * 4);
+    if (e == cudaSuccess) {
+        conv1_image_weights_kernel<<<(9 * 3 * 64 + 255) / 256, 256, 0, st>>>(h->wf[0], h->wg0);
+        e = cudaGetLastError();
+    }
+    if (e != cudaSuccess) {
+        adpst_vgg_destroy(h);
+        return fail(ADPST_ERR_CUDA, "vgg_create: %s", cudaGetErrorString(e));
+    }
+    *out = h;
+    return ADPST_OK;
+}
+
+void adpst_vgg_destroy(adpst_vgg* h) {
+    if (!h) return;
+    for (int i = 0; i < adpst::kNumConv; ++i) {
+        if (h->wf[i]) cudaFree(h->wf[i]);
+        if (h->wb[i]) cudaFree(h->wb[i]);
+        if (h->bias[i]) cudaFree(h->bias[i]);
+    }
+    if (h->wg0) cudaFree(h->wg0);
+    delete h;
+}
+
+int adpst_vgg_forward(adpst_vgg* h, const float* image_dev, int H, int W, float* const* acts_dev,
+                      float* const* pools_dev, int last, adpst_stream_t stream) {
+    using namespace adpst;
+    ADPST_REQUIRE(h && image_dev && acts_dev && pools_dev, "vgg_forward: NULL argument");
+    ADPST_REQUIRE(last >= 0 && last < kNumConv, "vgg_forward: last=%d out of range", last);
+    ADPST_REQUIRE(H >= 1 && W >= 1, "vgg_forward: empty image");
+    ADPST_REQUIRE((H >> pools_before(last)) >= 1 && (W >> pools_before(last)) >= 1,
+                  "vgg_forward: %dx%d image is too small for conv %d", H, W, last);
+    cudaStream_t st = as_stream(stream);
+    const float* x = image_dev;
+    for (int i = 0; i <= last; ++i) {
+        int lh, lw;
+        layer_hw(i, H, W, &lh, &lw);
+        ADPST_REQUIRE(acts_dev[i] != nullptr, "vgg_forward: acts[%d] is NULL", i);
+        int rc = launch_conv(MODE_FWD, i == 0, x, h->wf[i], h->bias[i], acts_dev[i], nullptr, nullptr, lh, lw, conv_cin(i),
+                             conv_cout(i), st);
+        if (rc != ADPST_OK) return rc;
+        x = acts_dev[i];
+        for (int j = 0; j < ADPST_VGG_NUM_POOL; ++j) {
+            if (kPoolAfter[j] == i && i < last) {
+                ADPST_REQUIRE(pools_dev[j] != nullptr, "vgg_forward: pools[%d] is NULL", j);
+                const size_t items = size_t(lh / 2) * (lw / 2) * (conv_cout(i) / 4);
+                maxpool2_kernel<<<stream_grid(items), 256, 0, st>>>(acts_dev[i], pools_dev[j], lh, lw, conv_cout(i));
+                ADPST_LAUNCH_CHECK();
+                x = pools_dev[j];
+            }
+        }
+    }
+    return ADPST_OK;
+}
+
+int adpst_vgg_backward(adpst_vgg* h, int H, int W, const float* const* acts_dev, const float* const* pools_dev,
+                       const float* const* seeds_dev, int last, float* scratch0_dev, float* scratch1_dev,
+                       float* dimage_dev, adpst_stream_t stream) {
+    using namespace adpst;
+    (void)pools_dev;
+    ADPST_REQUIRE(h && acts_dev && seeds_dev && scratch0_dev && scratch1_dev && dimage_dev, "vgg_backward: NULL argument");
+    ADPST_REQUIRE(last >= 0 && last < kNumConv, "vgg_backward: last=%d out of range", last);
+    ADPST_REQUIRE(seeds_dev[last] != nullptr, "vgg_backward: the seed of the last layer (%d) is required", last);
+    cudaStream_t st = as_stream(stream);
+    float* cur = scratch0_dev;   // holds dLoss/d(pre-activation of conv i)
+    float* nxt = scratch1_dev;
+    int lh, lw;
+    layer_hw(last, H, W, &lh, &lw);
+    {
+        const size_t n4 = size_t(lh) * lw * conv_cout(last) / 4;
+        relu_mask_kernel<<<stream_grid(n4), 256, 0, st>>>(acts_dev[last], seeds_dev[last], cur, n4);
+        ADPST_LAUNCH_CHECK();
+    }
+    for (int i = last; i >= 1; --i) {
+        layer_hw(i, H, W, &lh, &lw);
+        bool pooled_input = false;
+        for (int j = 0; j < ADPST_VGG_NUM_POOL; ++j) pooled_input |= (kPoolAfter[j] == i - 1);
+        if (!pooled_input) {
+            // input of conv i is the post-ReLU output of conv i-1 at the same resolution
+            int rc = launch_conv(MODE_BWD, false, cur, h->wb[i], nullptr, nxt, seeds_dev[i - 1], acts_dev[i - 1], lh, lw,
+                                 conv_cout(i), conv_cin(i), st);
+            if (rc != ADPST_OK) return rc;
+            float* t = cur; cur = nxt; nxt = t;
+        } else {
+            // gradient w.r.t. the pooled tensor, then route through the pool + ReLU of conv i-1
+            int rc = launch_conv(MODE_BWD, false, cur, h->wb[i], nullptr, nxt, nullptr, nullptr, lh, lw, conv_cout(i),
+                                 conv_cin(i), st);
+            if (rc != ADPST_OK) return rc;
+            int ph, pw;
+            layer_hw(i - 1, H, W, &ph, &pw);
+            const size_t items = size_t(ph) * pw * (conv_cout(i - 1) / 4);
+            unpool_relu_kernel<<<stream_grid(items), 256, 0, st>>>(acts_dev[i - 1], nxt, seeds_dev[i - 1], cur, ph, pw,
+                                                                   conv_cout(i - 1));
+            ADPST_LAUNCH_CHECK();
+        }
+    }
+    dim3 grid((W + 31) / 32, (H + 3) / 4);
+    conv1_dgrad_image_kernel<<<grid, 128, 0, st>>>(cur, h->wg0, dimage_dev, H, W);
+    ADPST_LAUNCH_CHECK();
+    return ADPST_OK;
+}
+
+}  // extern "C"

@@ -46,13 +46,13 @@ def resize_bilinear(mask_hw, size):
     return out
 
 
-def content_layer(target, output, scale, loss_acc, d_out=None, accumulate=False):
-    """loss_acc (float64[1]) += scale*mean((t-o)^2); d_out (=|+=) scale*2(o-t)/n  (loss.py:90-92)."""
+def content_layer(target, output, loss_scale, grad_scale, loss_acc, d_out=None, accumulate=False):
+    """loss_acc (float64[1]) += loss_scale*mean((t-o)^2); d_out (=|+=) grad_scale*2(o-t)/n  (loss.py:90-92)."""
     _f32(target, "target"); _f32(output, "output")
     if target.shape != output.shape:
         raise ValueError("content target %s and output %s differ in shape" % (tuple(target.shape), tuple(output.shape)))
-    _lib.check(_lib.lib().adpst_content_layer(_lib.ptr(target), _lib.ptr(output), output.numel(), float(scale),
-                                              _lib.ptr(loss_acc), _lib.ptr(d_out), int(bool(accumulate)),
+    _lib.check(_lib.lib().adpst_content_layer(_lib.ptr(target), _lib.ptr(output), output.numel(), float(loss_scale),
+                                              float(grad_scale), _lib.ptr(loss_acc), _lib.ptr(d_out), int(bool(accumulate)),
                                               _lib.stream_ptr()))
 
 
@@ -85,11 +85,18 @@ def gram_masked(F, masks, K, workspace=None):
     return G
 
 
-def style_layer_backward(F, masks, K, G, A, scale, loss_acc, dF, accumulate=False, workspace=None):
+def style_layer_backward(F, masks, K, G, A, loss_scale, grad_scale, loss_acc, dF, accumulate=False, workspace=None):
     """One layer of loss.py:104-137: accumulates the loss value and writes/adds its gradient w.r.t. F."""
     _f32(F, "F"); _f32(G, "G"); _f32(A, "A")
     HW, C = F.shape
     ws = workspace if workspace is not None else gram_workspace(HW, C, K, F.device)
     _lib.check(_lib.lib().adpst_style_layer_backward(_lib.ptr(F), HW, C, _lib.ptr(masks), K, _lib.ptr(G), _lib.ptr(A),
-                                                     float(scale), _lib.ptr(loss_acc), _lib.ptr(dF),
+                                                     float(loss_scale), float(grad_scale), _lib.ptr(loss_acc), _lib.ptr(dF),
                                                      int(bool(accumulate)), _lib.ptr(ws), _lib.stream_ptr()))
+
+
+def loss_finalize(acc, w_content, w_style, w_photo, out):
+    """acc: float64[3] {content, style, photo}; out: float32[5] {content, style, nima, photo, total}  (loss.py:72-76)."""
+    _lib.check(_lib.lib().adpst_loss_finalize(_lib.ptr(acc), float(w_content), float(w_style), float(w_photo),
+                                              _lib.ptr(out), _lib.stream_ptr()))
+    return out

@@ -115,19 +115,29 @@ size_t adpst_gram_workspace_bytes(int HW, int C, int K);
 int adpst_gram_masked(const float* F_dev, int HW, int C, const float* masks_dev, int K, float* G_dev,
                       void* workspace_dev, adpst_stream_t stream);
 
-/* loss.py:104-137 for one layer, forward value and gradient seed:
- *   loss += scale * sum_k mean((A_k - G_k)^2) / (2 C^2 HW^2)          (accumulated into *loss_dev, float64)
- *   dF    = scale * d/dF of that term                                  (written, or added if accumulate != 0)
- * G_dev is the transfer Gram from adpst_gram_masked on the same F / masks; A_dev the style Gram. */
+/* loss.py:104-137 for one layer, forward value and gradient seed.  With
+ *   L = sum_k mean((A_k - G_k)^2) / (2 C^2 HW^2):
+ *   *loss_dev += loss_scale * L                      (float64 accumulator, may be NULL)
+ *   dF (=|+=)  grad_scale * dL/dF                     (written, or added if accumulate != 0; may be NULL)
+ * G_dev is the transfer Gram from adpst_gram_masked on the same F / masks; A_dev the style Gram.
+ * loss_scale carries the 1/len(args) of loss.py:85, grad_scale additionally the style weight. */
 int adpst_style_layer_backward(const float* F_dev, int HW, int C, const float* masks_dev, int K,
-                               const float* G_dev, const float* A_dev, double scale, double* loss_dev,
-                               float* dF_dev, int accumulate, void* workspace_dev, adpst_stream_t stream);
+                               const float* G_dev, const float* A_dev, double loss_scale, double grad_scale,
+                               double* loss_dev, float* dF_dev, int accumulate, void* workspace_dev,
+                               adpst_stream_t stream);
 
-/* loss.py:90-92: loss += scale * mean((target - output)^2); dOut = scale * 2 (output - target) / n. */
-int adpst_content_layer(const float* target_dev, const float* output_dev, size_t n, double scale,
-                        double* loss_dev, float* dOut_dev, int accumulate, adpst_stream_t stream);
+/* loss.py:90-92 with L = mean((target - output)^2):
+ *   *loss_dev += loss_scale * L;   dOut (=|+=) grad_scale * 2 (output - target) / n. */
+int adpst_content_layer(const float* target_dev, const float* output_dev, size_t n, double loss_scale,
+                        double grad_scale, double* loss_dev, float* dOut_dev, int accumulate,
+                        adpst_stream_t stream);
 
-/* out[i] = a[i] + alpha * b[i] (float32; b is float32).  Used to combine image gradients. */
+/* loss.py:72-76: acc_dev = float64 {content, style, photo} (unweighted);  out_dev = float32
+ * {content, style, nima (0), photo, total = sum w_i * loss_i}.  One tiny launch, keeps the step graph-replayable. */
+int adpst_loss_finalize(const double* acc_dev, double w_content, double w_style, double w_photo, float* out_dev,
+                        adpst_stream_t stream);
+
+/* out[i] = alpha * a[i] + beta * b[i] (float32; b may be NULL).  Used to combine image gradients. */
 int adpst_axpby(float* out_dev, const float* a_dev, float alpha, const float* b_dev, float beta, size_t n,
                 adpst_stream_t stream);
 

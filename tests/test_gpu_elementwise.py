@@ -53,12 +53,12 @@ def test_content_layer_value_and_gradient():
     o = rng.standard_normal((1, 16, 16, 512)).astype(np.float32) * 50
     acc = torch.zeros(1, dtype=torch.float64, device="cuda")
     d = torch.empty(t.shape, dtype=torch.float32, device="cuda")
-    k.content_layer(torch.as_tensor(t).cuda(), torch.as_tensor(o).cuda(), 0.5, acc, d)
+    k.content_layer(torch.as_tensor(t).cuda(), torch.as_tensor(o).cuda(), 0.5, 0.5, acc, d)
     oo = torch.as_tensor(o.astype(np.float64)).requires_grad_(True)
     loss = 0.5 * model.layer_content_loss(torch.as_tensor(t.astype(np.float64)), oo)
     (g,) = torch.autograd.grad(loss, oo)
     assert abs(float(acc) - float(loss)) < 1e-9 * float(loss)
     assert np.abs(d.cpu().numpy() - g.numpy()).max() < 1e-6 * np.abs(g.numpy()).max()
-    k.content_layer(torch.as_tensor(t).cuda(), torch.as_tensor(o).cuda(), 0.5, acc, d, accumulate=True)
+    k.content_layer(torch.as_tensor(t).cuda(), torch.as_tensor(o).cuda(), 0.5, 0.5, acc, d, accumulate=True)
     assert np.abs(d.cpu().numpy() - 2 * g.numpy()).max() < 2e-6 * np.abs(g.numpy()).max()
     assert abs(float(acc) - 2 * float(loss)) < 1e-9 * float(loss)

@@ -25,9 +25,11 @@ def _v3():
     return importlib.import_module(PKG_NAME + ".components.matting_v3")
 
 
-def _rel(a, b):
+def _rel(a, b, floor=1e-3):
+    """max |a-b| relative to max|b|; `floor` keeps the zero operator (1x1 image, no interior window) testable:
+    generic |Lx| is O(1) for x in [0,1), so anything below 1e-3 is compared absolutely at that scale."""
     a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
-    return np.abs(a - b).max() / max(np.abs(b).max(), 1e-300)
+    return np.abs(a - b).max() / max(np.abs(b).max(), floor)
 
 
 @pytest.mark.parametrize("H,W", [(1, 1), (2, 3), (5, 7), (16, 32), (33, 70), (64, 64)])
@@ -42,7 +44,7 @@ def test_v2_float64_matches_oracle(H, W, eps, synth):
     assert y.dtype == torch.float64 and tuple(y.shape) == (H * W, 3)
     assert _rel(y.cpu().numpy(), ref.matmul(x)) < 1e-9
     yi = op.matmul(torch.as_tensor(img.reshape(-1, 3)).cuda()).cpu().numpy()       # x = I, iteration 0
-    assert _rel(yi, ref.matmul(img.reshape(-1, 3))) < 1e-6
+    assert _rel(yi, ref.matmul(img.reshape(-1, 3)), floor=1e-9) < 1e-6
 
 
 @pytest.mark.parametrize("r", [2, 3])

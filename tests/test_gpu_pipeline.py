@@ -1,0 +1,196 @@
+"""GPU parity of the VGG19 extractor, masked Gram / style / content terms, the total loss, its gradient and the full
+train_step against the torch-CPU float64 oracle on identical synthetic inputs (random-init VGG19, synthetic masks).
+
+Tolerance: 1e-5 relative (north star) for every loss scalar and, in max-norm, for feature maps and gradients.
+Measured float32 noise floor of the restatement itself (torch-CPU float32 vs float64): ~1e-7.
+"""
+import argparse
+import importlib
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import PKG_NAME
+from oracle import masks as omasks
+from oracle import model
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-5
+
+
+def _m(name):
+    return importlib.import_module(PKG_NAME + "." + name)
+
+
+def _rel(a, b):
+    a = np.asarray(a, np.float64); b = np.asarray(b, np.float64)
+    return np.abs(a - b).max() / max(np.abs(b).max(), 1e-30)
+
+
+def _args(**kw):
+    d = dict(content_weight=1.0, style_weight=100.0, nima_weight=0.0, regularization_weight=1e4,
+             matting_epsilon=1e-7, matting_window_radius=1, adam_lr=0.1, adam_beta1=0.9, adam_beta2=0.999,
+             adam_epsilon=1e-8, iter=3)
+    d.update(kw)
+    return argparse.Namespace(**d)
+
+
+def _cfg(a):
+    return {"weights": {"content": a.content_weight, "style": a.style_weight, "nima": 0.0, "photo": a.regularization_weight},
+            "matting_epsilon": a.matting_epsilon, "matting_window_radius": a.matting_window_radius,
+            "adam": {"lr": a.adam_lr, "beta1": a.adam_beta1, "beta2": a.adam_beta2, "epsilon": a.adam_epsilon}}
+
+
+@pytest.fixture(scope="module")
+def weights(synth):
+    return synth.vgg_weights(seed=5)
+
+
+@pytest.mark.parametrize("H,W", [(64, 64), (37, 50), (16, 16), (96, 138)])
+def test_vgg_forward_all_taps(H, W, weights, synth):
+    vgg = _m("components.VGG19.model")
+    names = [n for n, _, _ in synth.CONV_LAYERS]
+    ext = vgg.StyleContentModel(names[:1], names[1:], weights=weights)
+    img = synth.image(H, W, 0)
+    out = ext(torch.as_tensor(img).cuda())
+    ref = model.vgg_forward(torch.as_tensor(img), weights)
+    got = dict(out["content"]); got.update(out["style"])
+    for n in names:
+        assert tuple(got[n].shape) == tuple(ref[n].shape), n
+        assert _rel(got[n].cpu().numpy(), ref[n].numpy()) < TOL, n
+
+
+@pytest.mark.parametrize("H,W", [(32, 32), (37, 50)])
+def test_vgg_backward_matches_autograd(H, W, weights, synth):
+    """d(sum_i <seed_i, layer_i>)/d(image) with random seeds on the six tapped layers."""
+    vgg = _m("components.VGG19.model")
+    ext = vgg.StyleContentModel(model.CONTENT_LAYERS, model.STYLE_LAYERS, weights=weights)
+    img = synth.image(H, W, 3)
+    out = ext(torch.as_tensor(img).cuda())
+    rng = np.random.default_rng(4)
+    seeds, flat = {}, dict(out["content"]); flat.update(out["style"])
+    for n, t in flat.items():
+        seeds[n] = rng.standard_normal(tuple(t.shape)).astype(np.float32)
+    g = ext.backward({n: torch.as_tensor(s).cuda() for n, s in seeds.items()})
+    x = torch.as_tensor(img, dtype=torch.float64).requires_grad_(True)
+    ref = model.vgg_forward(x, weights)
+    tot = sum((ref[n] * torch.as_tensor(s, dtype=torch.float64)).sum() for n, s in seeds.items())
+    (gr,) = torch.autograd.grad(tot, x)
+    assert _rel(g.cpu().numpy(), gr.numpy()) < TOL
+
+
+@pytest.mark.parametrize("HW,C,K", [(64 * 64, 64, 3), (1000, 128, 1), (777, 256, 4), (256, 512, 2)])
+def test_masked_gram_and_style_gradient(HW, C, K):
+    k = _m("kernels")
+    rng = np.random.default_rng(HW + C)
+    F = (rng.random((HW, C)) * 50).astype(np.float32)
+    S = (rng.random((HW // 2 + 3, C)) * 50).astype(np.float32)
+    if K > 1:
+        lab = rng.integers(0, K, HW)
+        m = np.stack([(lab == i).astype(np.float32) for i in range(K)])
+        soft = rng.random((K, HW)) < 0.05                       # some fractional boundary pixels
+        m = np.where(soft, rng.random((K, HW)).astype(np.float32), m).astype(np.float32)
+        ms = rng.random((K, S.shape[0])).astype(np.float32)
+    else:
+        m, ms = None, None
+    Fd = torch.as_tensor(F).cuda()
+    md = None if m is None else torch.as_tensor(m).cuda()
+    G = k.gram_masked(Fd, md, K)
+    A = k.gram_masked(torch.as_tensor(S).cuda(), None if ms is None else torch.as_tensor(ms).cuda(), K)
+    Ft = torch.as_tensor(F, dtype=torch.float64).requires_grad_(True)
+    St = torch.as_tensor(S, dtype=torch.float64)
+    loss = 0.0
+    for i in range(K):
+        mi = torch.ones(HW, dtype=torch.float64) if m is None else torch.as_tensor(m[i], dtype=torch.float64)
+        si = torch.ones(S.shape[0], dtype=torch.float64) if ms is None else torch.as_tensor(ms[i], dtype=torch.float64)
+        g_t = model.gram_matrix(Ft.reshape(1, 1, HW, C), mi)
+        g_s = model.gram_matrix(St.reshape(1, 1, -1, C), si)
+        assert _rel(G[i].cpu().numpy(), g_t.detach().numpy()) < TOL
+        assert _rel(A[i].cpu().numpy(), g_s.numpy()) < TOL
+        loss = loss + torch.mean((g_s - g_t) ** 2) / (2 * float(C) ** 2 * float(HW) ** 2)
+    (gF,) = torch.autograd.grad(loss * 50.0, Ft)
+    acc = torch.zeros(1, dtype=torch.float64, device="cuda")
+    dF = torch.empty_like(Fd)
+    k.style_layer_backward(Fd, md, K, G, A, 0.5, 50.0, acc, dF)
+    assert abs(float(acc) - 0.5 * float(loss)) < TOL * 0.5 * float(loss)
+    assert _rel(dF.cpu().numpy(), gF.numpy()) < 5 * TOL     # G - A cancels digits: allow for float32 Gram rounding
+
+
+def _setup(H, W, K, weights, synth, args, matting="v2", Hs=None, Ws=None):
+    vgg, lossm = _m("components.VGG19.model"), _m("components.loss")
+    Hs, Ws = Hs or H, Ws or W
+    content, style = synth.image(H, W, 0), synth.image(Hs, Ws, 1)
+    cm = sm = cm_o = sm_o = None
+    if K:
+        cell = max(4, min(H, W, Hs, Ws) // 4)
+        segc, segs = synth.label_image(H, W, K, 9, cell=cell), synth.label_image(Hs, Ws, K, 10, cell=cell)
+        sem = _m("components.semantic_merge")
+        cm, sm = sem.mask_for_tf(sem.extract_segmentation_masks(segc)), sem.mask_for_tf(sem.extract_segmentation_masks(segs))
+        cm_o = [torch.as_tensor(m) for m in omasks.mask_for_tf(omasks.extract_segmentation_masks(segc))]
+        sm_o = [torch.as_tensor(m) for m in omasks.mask_for_tf(omasks.extract_segmentation_masks(segs))]
+        assert len(cm) == len(cm_o) == K and all(np.array_equal(a.numpy(), b.numpy()) for a, b in zip(cm, cm_o))
+    ext = vgg.StyleContentModel(model.CONTENT_LAYERS, model.STYLE_LAYERS, shape=(None, None, 3), weights=weights)
+    c_dev, s_dev = torch.as_tensor(content).cuda(), torch.as_tensor(style).cuda()
+    loss = lossm.Loss(ext(c_dev)["content"], ext(s_dev)["style"], args, cm, sm, matting=matting)
+    if args.regularization_weight > 0:
+        loss.initialize_matting_laplacian(c_dev[0].double())
+    ora = model.TrainState(torch.as_tensor(content), torch.as_tensor(style), weights, _cfg(args), cm_o, sm_o)
+    return ext, loss, ora, c_dev
+
+
+@pytest.mark.parametrize("H,W,K,photo", [(64, 64, 3, 1e4), (64, 64, 0, 0.0), (37, 50, 2, 1e4), (48, 80, 4, 0.0)])
+def test_total_loss_and_image_gradient(H, W, K, photo, weights, synth):
+    args = _args(regularization_weight=photo)
+    ext, loss, ora, c_dev = _setup(H, W, K, weights, synth, args)
+    # evaluate away from the content image (at x = content the content term and its gradient vanish)
+    pert = np.sign(synth.image(H, W, 3) - 0.5).astype(np.float32) * 0.1
+    x = torch.clamp(c_dev + torch.as_tensor(pert).cuda(), 0, 1).contiguous()
+    d = loss(x, ext(x, reuse=True))
+    g = loss.gradient(ext)
+    do, go = ora.loss_and_grad(x.cpu().double())
+    assert set(d) == set(do) or (photo == 0 and set(d) == set(do) - {"Photorealism regualarization"}) or set(d) == set(do)
+    for name, v in d.items():
+        assert abs(float(v) - do[name]) <= TOL * abs(do[name]) + 1e-12, name
+    assert _rel(g.cpu().numpy(), go.numpy()) < TOL
+
+
+def test_style_and_content_sizes_differ(weights, synth):
+    """Defaults of the reference: content 96x138, style 96x168 (blanc.jpg / bear.jpeg)."""
+    args = _args(regularization_weight=0.0)
+    ext, loss, ora, c_dev = _setup(48, 69, 2, weights, synth, args, Hs=48, Ws=84)
+    x = torch.clamp(c_dev * 0.9 + 0.05, 0, 1).contiguous()
+    d = loss(x, ext(x, reuse=True))
+    g = loss.gradient(ext)
+    do, go = ora.loss_and_grad(x.cpu().double())
+    for name, v in d.items():
+        assert abs(float(v) - do[name]) <= TOL * abs(do[name]) + 1e-12, name
+    assert _rel(g.cpu().numpy(), go.numpy()) < TOL
+
+
+@pytest.mark.parametrize("graph", [False, True])
+def test_train_steps_follow_oracle(graph, weights, synth):
+    st = _m("style_transfer")
+    args = _args()
+    ext, loss, ora, c_dev = _setup(64, 64, 3, weights, synth, args)
+    opt = st.Adam(args.adam_lr, args.adam_beta1, args.adam_beta2, args.adam_epsilon)
+    step = st.make_train_step(ext, loss, opt, use_cuda_graph=graph)
+    x = c_dev.clone()
+    for it in range(3):
+        d = {k: float(v) for k, v in step(x).items()}
+        do = ora.train_step()
+        for name in d:
+            assert abs(d[name] - do[name]) <= 1e-4 * abs(do[name]) + 1e-6, (it, name)
+        # Adam's first steps are +-lr*sign(g): a pixel whose gradient is ~0 may flip; count, don't max
+        diff = (x.cpu().double() - ora.image).abs()
+        assert float((diff > 1e-3).double().mean()) < 1e-3, it
+    assert opt.iterations == 3
+    mse = float(((x.cpu().double() - ora.image) ** 2).mean())
+    assert 10 * np.log10(1.0 / max(mse, 1e-30)) > 50.0           # PSNR bar of the north star
+
+
+def test_nima_weight_is_refused(weights, synth):
+    lossm = _m("components.loss")
+    t = {"block4_conv2": torch.zeros(1, 2, 2, 512, device="cuda")}
+    with pytest.raises(NotImplementedError):
+        lossm.Loss(t, {}, _args(nima_weight=1e5))
