@@ -121,6 +121,7 @@ class StyleContentModel:
         self.last_index = max(idx)
         self.device = self.vgg.device
         self.last = None
+        self._loop = None
         self._scratch = None
 
     def __call__(self, inputs, reuse=False):
@@ -135,8 +136,14 @@ class StyleContentModel:
             raise TypeError("expected a float32 CUDA image")
         x = inputs.contiguous()
         H, W = int(x.shape[1]), int(x.shape[2])
-        A = self.last if (reuse and self.last is not None and (self.last.H, self.last.W) == (H, W)) else \
-            Activations(H, W, self.last_index, self.device)
+        if reuse:
+            # a private buffer set that only reuse=True calls ever write: results handed out by reuse=False calls
+            # (the content / style targets) are never overwritten
+            if self._loop is None or (self._loop.H, self._loop.W) != (H, W):
+                self._loop = Activations(H, W, self.last_index, self.device)
+            A = self._loop
+        else:
+            A = Activations(H, W, self.last_index, self.device)
         with torch.cuda.device(self.device):
             _lib.check(_lib.lib().adpst_vgg_forward(self.vgg._h, _lib.ptr(x), H, W, _lib.ptr_array(A.acts),
                                                     _lib.ptr_array(A.pools), self.last_index, _lib.stream_ptr()))

@@ -70,7 +70,10 @@ class LaplacianHandle:
         with torch.cuda.device(self.device):
             _lib.check(_lib.lib().adpst_laplacian_matvec(self._h, _lib.ptr(x), _lib.ptr(y), float(y_scale), _lib.ptr(q),
                                                          _lib.stream_ptr()))
-        return y, (q.reshape(-1)[0] if want_quad else None)
+        if not want_quad:
+            return y, None
+        # the internal scalar is overwritten by the next call: hand out a copy unless the caller owns the buffer
+        return y, (q.reshape(-1)[0] if quad_out is not None else q.reshape(-1)[0].clone())
 
     def matmul(self, x):
         """(HW, C') -> (HW, C').  C' != 3 is processed three columns at a time (zero padded)."""

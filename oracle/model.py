@@ -183,11 +183,18 @@ def compute_loss(image, outputs, content_target, style_target, weights_cfg, lap=
 
 def adam_clip_step(x, g, m, v, t, lr=0.1, beta1=0.9, beta2=0.999, eps=1e-8):
     """tf.optimizers.Adam.apply_gradients + clip_by_value  (style_transfer.py:321-326,342-343).
-    Keras/TF formulation: alpha_t = lr*sqrt(1-b2^t)/(1-b1^t); x -= alpha_t*m/(sqrt(v)+eps)."""
-    m = beta1 * m + (1 - beta1) * g
-    v = beta2 * v + (1 - beta2) * g * g
-    alpha = lr * np.sqrt(1 - beta2 ** t) / (1 - beta1 ** t)
-    x = x - alpha * m / (torch.sqrt(v) + eps)
+    Keras/TF formulation: alpha_t = lr*sqrt(1-b2^t)/(1-b1^t); x -= alpha_t*m/(sqrt(v)+eps)  (eps outside the
+    bias correction).  The variable is float32, so TF holds the hyper-parameters as float32 tensors and forms
+    (1-beta), beta^t in float32; that is modelled here (it shifts v by 1.3e-5 relative), the state itself stays in
+    the dtype of x."""
+    f = np.float32
+    b1, b2 = f(beta1), f(beta2)
+    om1, om2 = float(f(1) - b1), float(f(1) - b2)
+    b1p, b2p = f(b1 ** f(t)), f(b2 ** f(t))
+    alpha = float(f(lr) * np.sqrt(f(1) - b2p) / (f(1) - b1p))
+    m = m + (g - m) * om1
+    v = v + (g * g - v) * om2
+    x = x - alpha * m / (torch.sqrt(v) + float(f(eps)))
     return torch.clamp(x, 0.0, 1.0), m, v
 
 

@@ -24,14 +24,17 @@ def test_adam_clip_three_steps(n):
     st = k.AdamState(x)
     xo = torch.as_tensor(x0.astype(np.float64))
     mo, vo = torch.zeros_like(xo), torch.zeros_like(xo)
+    gmax = 0.0
     for t in range(1, 4):
         g = (rng.standard_normal(n) * 10.0 ** rng.integers(-3, 3)).astype(np.float32)
+        gmax = max(gmax, float(np.abs(g).max()))
         k.adam_clip_step(x, torch.as_tensor(g).cuda(), st, 0.1, 0.9, 0.999, 1e-8)
         xo, mo, vo = model.adam_clip_step(xo, torch.as_tensor(g.astype(np.float64)), mo, vo, t)
         assert st.step == t
         np.testing.assert_allclose(x.cpu().numpy(), xo.numpy(), atol=2e-6, rtol=0)     # float32 state vs float64 oracle
-        np.testing.assert_allclose(st.m.cpu().numpy(), mo.numpy(), rtol=1e-5, atol=1e-12)
-        np.testing.assert_allclose(st.v.cpu().numpy(), vo.numpy(), rtol=1e-5, atol=1e-12)
+        # float32 slots: m = b1*m + (1-b1)*g cancels when g changes sign, so the error is absolute in |g|
+        np.testing.assert_allclose(st.m.cpu().numpy(), mo.numpy(), rtol=1e-5, atol=1e-6 * gmax)
+        np.testing.assert_allclose(st.v.cpu().numpy(), vo.numpy(), rtol=1e-5, atol=1e-6 * gmax * gmax)
     assert float(x.min()) >= 0.0 and float(x.max()) <= 1.0
 
 
@@ -57,8 +60,8 @@ def test_content_layer_value_and_gradient():
     oo = torch.as_tensor(o.astype(np.float64)).requires_grad_(True)
     loss = 0.5 * model.layer_content_loss(torch.as_tensor(t.astype(np.float64)), oo)
     (g,) = torch.autograd.grad(loss, oo)
-    assert abs(float(acc) - float(loss)) < 1e-9 * float(loss)
+    assert abs(float(acc) - float(loss.detach())) < 1e-9 * float(loss.detach())
     assert np.abs(d.cpu().numpy() - g.numpy()).max() < 1e-6 * np.abs(g.numpy()).max()
     k.content_layer(torch.as_tensor(t).cuda(), torch.as_tensor(o).cuda(), 0.5, 0.5, acc, d, accumulate=True)
     assert np.abs(d.cpu().numpy() - 2 * g.numpy()).max() < 2e-6 * np.abs(g.numpy()).max()
-    assert abs(float(acc) - 2 * float(loss)) < 1e-9 * float(loss)
+    assert abs(float(acc) - 2 * float(loss.detach())) < 1e-9 * float(loss.detach())
