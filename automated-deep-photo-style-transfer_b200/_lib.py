@@ -26,6 +26,7 @@ _pp = _c.POINTER(_c.c_void_p)
 SIGNATURES = {
     "adpst_version": (_i, []),
     "adpst_last_error": (_c.c_char_p, []),
+    "adpst_launch_count": (_c.c_ulonglong, []),
     "adpst_laplacian_create": (_i, [_i, _i, _i, _i, _d, _vp, _i, _i, _vp, _pp]),
     "adpst_laplacian_destroy": (None, [_vp]),
     "adpst_laplacian_matvec": (_i, [_vp, _vp, _vp, _d, _vp, _vp]),
@@ -38,6 +39,8 @@ SIGNATURES = {
     "adpst_vgg_conv_shape": (_i, [_i, _i, _i, _c.POINTER(_i), _c.POINTER(_i), _c.POINTER(_i)]),
     "adpst_vgg_pool_shape": (_i, [_i, _i, _i, _c.POINTER(_i), _c.POINTER(_i), _c.POINTER(_i)]),
     "adpst_vgg_forward": (_i, [_vp, _vp, _i, _i, _pp, _pp, _i, _vp]),
+    "adpst_vgg_conv_forward": (_i, [_vp, _i, _vp, _i, _i, _vp, _vp]),
+    "adpst_vgg_conv_dgrad": (_i, [_vp, _i, _vp, _i, _i, _vp, _vp]),
     "adpst_vgg_backward": (_i, [_vp, _i, _i, _pp, _pp, _pp, _i, _vp, _vp, _vp, _vp]),
     "adpst_resize_bilinear": (_i, [_vp, _i, _i, _vp, _i, _i, _vp]),
     "adpst_gram_workspace_bytes": (_sz, [_i, _i, _i]),
@@ -73,6 +76,10 @@ def lib():
 def missing_symbols():
     L = lib()
     return [n for n in SIGNATURES if not hasattr(L, n)]
+
+
+def launch_count():
+    return int(lib().adpst_launch_count())
 
 
 def check(code):

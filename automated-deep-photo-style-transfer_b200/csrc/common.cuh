@@ -20,7 +20,12 @@ int fail(int code, const char* fmt, ...);
                                  cudaGetErrorString(_e));                                   \
     } while (0)
 
-#define ADPST_LAUNCH_CHECK() ADPST_CUDA_CHECK(cudaGetLastError())
+// every kernel launch of the library goes through this macro, so adpst_launch_count() is the number of OUR kernels
+#define ADPST_LAUNCH_CHECK()                     \
+    do {                                         \
+        ::adpst::count_launch();                 \
+        ADPST_CUDA_CHECK(cudaGetLastError());    \
+    } while (0)
 
 #define ADPST_REQUIRE(cond, ...)                                            \
     do {                                                                    \
@@ -30,6 +35,7 @@ int fail(int code, const char* fmt, ...);
 static inline cudaStream_t as_stream(adpst_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }
 
 int num_sms();
+void count_launch();
 
 template <typename T>
 __device__ __forceinline__ T warp_sum(T v) {

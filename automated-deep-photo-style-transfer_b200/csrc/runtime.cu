@@ -1,6 +1,8 @@
 // runtime.cu -- error reporting and device queries shared by every entry point.
 #include <stdarg.h>
 
+#include <atomic>
+
 #include "common.cuh"
 
 namespace adpst {
@@ -18,6 +20,9 @@ int fail(int code, const char* fmt, ...) {
     g_last_error = buf;
     return code;
 }
+
+static std::atomic<unsigned long long> g_launches{0};
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 
 int num_sms() {
     static int cached = 0;
@@ -39,5 +44,7 @@ extern "C" {
 int adpst_version(void) { return 100; }
 
 const char* adpst_last_error(void) { return adpst::g_last_error.c_str(); }
+
+unsigned long long adpst_launch_count(void) { return adpst::g_launches.load(std::memory_order_relaxed); }
 
 }  // extern "C"

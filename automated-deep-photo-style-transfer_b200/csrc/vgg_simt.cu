@@ -439,6 +439,20 @@ int adpst_vgg_forward(adpst_vgg* h, const float* image_dev, int H, int W, float*
     return ADPST_OK;
 }
 
+int adpst_vgg_conv_forward(adpst_vgg* h, int i, const float* x_dev, int lh, int lw, float* y_dev, adpst_stream_t stream) {
+    using namespace adpst;
+    ADPST_REQUIRE(h && x_dev && y_dev && i >= 0 && i < kNumConv && lh > 0 && lw > 0, "vgg_conv_forward: bad argument");
+    return launch_conv(MODE_FWD, i == 0, x_dev, h->wf[i], h->bias[i], y_dev, nullptr, nullptr, lh, lw, conv_cin(i),
+                       conv_cout(i), as_stream(stream));
+}
+
+int adpst_vgg_conv_dgrad(adpst_vgg* h, int i, const float* dpre_dev, int lh, int lw, float* dx_dev, adpst_stream_t stream) {
+    using namespace adpst;
+    ADPST_REQUIRE(h && dpre_dev && dx_dev && i >= 1 && i < kNumConv && lh > 0 && lw > 0, "vgg_conv_dgrad: bad argument");
+    return launch_conv(MODE_BWD, false, dpre_dev, h->wb[i], nullptr, dx_dev, nullptr, nullptr, lh, lw, conv_cout(i),
+                       conv_cin(i), as_stream(stream));
+}
+
 int adpst_vgg_backward(adpst_vgg* h, int H, int W, const float* const* acts_dev, const float* const* pools_dev,
                        const float* const* seeds_dev, int last, float* scratch0_dev, float* scratch1_dev,
                        float* dimage_dev, adpst_stream_t stream) {

@@ -36,6 +36,8 @@ enum { ADPST_VGG_NUM_CONV = 13, ADPST_VGG_NUM_POOL = 4 };
 
 int adpst_version(void);
 const char* adpst_last_error(void);
+/* number of CUDA kernels this library has launched so far in this process (bench.py reports it as gpu_launches). */
+unsigned long long adpst_launch_count(void);
 
 /* ------------------------------------------------------------------------------------------------
  * Matting Laplacian (matrix-free for both variants)
@@ -94,6 +96,12 @@ int adpst_vgg_pool_shape(int j, int H, int W, int* h, int* w, int* c);
  * acts_dev[i]: conv i output (1,h,w,c) post-ReLU; pools_dev[j]: pool j output.  All caller-allocated. */
 int adpst_vgg_forward(adpst_vgg* h, const float* image_dev, int H, int W, float* const* acts_dev,
                       float* const* pools_dev, int last, adpst_stream_t stream);
+
+/* One layer in isolation (parity tests, per-kernel roofline in bench.py).
+ * conv_forward: y = relu(conv_i(x) + b_i); for i == 0, x is the [0,1] RGB image (h,w,3).
+ * conv_dgrad  : dx = conv_i^T(dpre) (i >= 1), no mask, no seed. */
+int adpst_vgg_conv_forward(adpst_vgg* h, int i, const float* x_dev, int lh, int lw, float* y_dev, adpst_stream_t stream);
+int adpst_vgg_conv_dgrad(adpst_vgg* h, int i, const float* dpre_dev, int lh, int lw, float* dx_dev, adpst_stream_t stream);
 
 /* Backward to the image.  seeds_dev[i] (may be NULL): dLoss/d(conv i output), added where the chain passes.
  * scratch_dev: two buffers, each at least as large as the largest activation (conv 0).
