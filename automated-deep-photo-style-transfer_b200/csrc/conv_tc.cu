@@ -1,0 +1,329 @@
+// conv_tc.cu -- 3x3 SAME convolution (forward and data gradient) as an implicit GEMM on the 5th-generation tensor
+// cores: TMA -> shared memory -> tcgen05.mma (kind::tf32) -> TMEM -> fused epilogue -> HBM.
+//
+// Replaces the Keras Conv2D calls behind components/VGG19/model.py:30 and their tape gradient (style_transfer.py:341).
+//
+// GEMM view per CTA:  D[128 pixels, BN channels] = sum over (tap, Cin chunk of 32)  A[128, 32] * B[BN, 32]^T
+//   A: an 8 x 16 pixel tile of the NHWC activation, shifted by the tap; ONE 4-D TMA box (C=32, W=16, H=8, N=1) lands it
+//      K-major with the 128-byte swizzle the UMMA descriptor expects, and TMA's out-of-bounds zero fill IS the SAME
+//      padding, so there is no im2col buffer and no border code.
+//   B: weights pre-arranged [tap][Cout][Cin] (K-major), 2-D TMA box (32, BN).
+//
+// Precision: the reference computes in float32 and parity is 1e-5.  One TF32 MMA (10-bit mantissa) is 1e-3.
+// Every product is therefore formed as  a_hi*b_hi + a_hi*b_lo + a_lo*b_hi  ("3xTF32"), all three accumulating into the
+// same fp32 TMEM accumulator:
+//   a_hi = a with the 13 low mantissa bits cleared (exactly representable in TF32, so the tensor core's own
+//          fp32->tf32 conversion cannot change it),  a_lo = a - a_hi (exact in fp32, <= 13 significant bits).
+//   b_hi / b_lo are split once when the weights are loaded; a_hi / a_lo are split in shared memory by the
+//   "transform" warps between the TMA landing and the MMA issue.
+// The dropped a_lo*b_lo term and the tf32 rounding of the lo parts are O(2^-22) relative.
+//
+// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer (one elected lane),
+// warps 2..5 = operand transform during the main loop, then the epilogue (TMEM -> registers -> bias/ReLU or
+// seed/mask -> global).  Three mbarrier rings: full (TMA landed) -> ready (A split done) -> empty (MMAs retired).
+#include "tc_common.cuh"
+#include "vgg.cuh"
+
+namespace adpst {
+namespace tc {
+
+EncodeTiledFn encode_tiled_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+    return fn;
+}
+
+int make_tensor_map_f32(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                        const uint32_t* box) {
+    EncodeTiledFn fn = encode_tiled_fn();
+    if (!fn) return fail(ADPST_ERR_CUDA, "cuTensorMapEncodeTiled is not available from the driver");
+    cuuint64_t d[5], s[5];
+    cuuint32_t b[5], e[5];
+    for (int i = 0; i < rank; ++i) { d[i] = dims[i]; b[i] = box[i]; e[i] = 1; }
+    for (int i = 0; i + 1 < rank; ++i) s[i] = strides_bytes[i];
+    CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, cuuint32_t(rank), const_cast<void*>(base), d, s, b, e,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(ADPST_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", int(r));
+    return ADPST_OK;
+}
+
+}  // namespace tc
+
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int TC_TH = 8, TC_TW = 16, TC_BM = TC_TH * TC_TW;     // 128 pixels = UMMA M
+constexpr int TC_BK = 32;                                        // 32 fp32 = one 128-byte swizzle row
+constexpr int TC_THREADS = 192;
+constexpr int TC_A_BYTES = TC_BM * TC_BK * 4;                    // 16 KB
+
+template <int BN> struct TcCfg {
+    static constexpr int STAGES = BN >= 256 ? 2 : BN >= 128 ? 3 : 2;
+    static constexpr int B_BYTES = BN * TC_BK * 4;
+    static constexpr int STAGE_BYTES = 2 * TC_A_BYTES + 2 * B_BYTES;        // A, A_lo, B_hi, B_lo
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*alignment slack*/ + 256 /*barriers*/;
+    static constexpr uint32_t TMEM_COLS = BN < 32 ? 32 : BN;                // power of two >= 32
+};
+
+template <int BN, int MODE>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmBhi,
+                  const __grid_constant__ CUtensorMap tmBlo, const float* __restrict__ bias, float* __restrict__ Y,
+                  const float* __restrict__ seed, const float* __restrict__ mask_src, int H, int W, int Cin, int Cout,
+                  int tiles_w) {
+    using Cfg = TcCfg<BN>;
+    constexpr int STAGES = Cfg::STAGES;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES);
+    uint64_t* full = bars;                  // [STAGES]  TMA bytes landed
+    uint64_t* ready = bars + STAGES;        // [STAGES]  A split into hi/lo
+    uint64_t* empty = bars + 2 * STAGES;    // [STAGES]  MMAs that read the stage have retired
+    uint64_t* accum = bars + 3 * STAGES;    // [1]       accumulator complete
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * STAGES + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int tile = blockIdx.x;
+    const int y0 = (tile / tiles_w) * TC_TH, x0 = (tile % tiles_w) * TC_TW;
+    const int n0 = blockIdx.y * BN;
+    const int kchunks = Cin / TC_BK;
+    const int iters = 9 * kchunks;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < STAGES; ++s) {
+            tc::mbar_init(&full[s], 1);
+            tc::mbar_init(&ready[s], 128);
+            tc::mbar_init(&empty[s], 1);
+        }
+        tc::mbar_init(accum, 1);
+        tc::fence_barrier_init();
+        tc::tma_prefetch_desc(&tmA);
+        tc::tma_prefetch_desc(&tmBhi);
+        tc::tma_prefetch_desc(&tmBlo);
+    }
+    if (warp == 1) tc::tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
+    tc::tcgen05_fence_before();
+    __syncthreads();
+    tc::tcgen05_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ================= TMA producer =================
+        if (lane == 0) {
+            for (int it = 0; it < iters; ++it) {
+                const int s = it % STAGES, round = it / STAGES;
+                tc::mbar_wait(&empty[s], (round & 1) ^ 1);
+                const int tap = it / kchunks, kc = it - tap * kchunks;
+                const int kh = tap / 3, kw = tap - kh * 3;
+                uint8_t* st = smem + s * Cfg::STAGE_BYTES;
+                tc::mbar_arrive_expect_tx(&full[s], TC_A_BYTES + 2 * Cfg::B_BYTES);
+                tc::tma_load_4d(st, &tmA, &full[s], kc * TC_BK, x0 + kw - 1, y0 + kh - 1, 0);
+                tc::tma_load_2d(st + 2 * TC_A_BYTES, &tmBhi, &full[s], kc * TC_BK, tap * Cout + n0);
+                tc::tma_load_2d(st + 2 * TC_A_BYTES + Cfg::B_BYTES, &tmBlo, &full[s], kc * TC_BK, tap * Cout + n0);
+            }
+        }
+    } else if (warp == 1) {
+        // ================= MMA issuer =================
+        if (lane == 0) {
+            constexpr uint32_t idesc = tc::umma_idesc_tf32(TC_BM, BN);
+            for (int it = 0; it < iters; ++it) {
+                const int s = it % STAGES, round = it / STAGES;
+                tc::mbar_wait(&full[s], round & 1);      // B operands (TMA) ...
+                tc::mbar_wait(&ready[s], round & 1);     // ... and the A hi/lo split (transform warps)
+                tc::tcgen05_fence_after();
+                const uint32_t a_hi = tc::smem_u32(smem + s * Cfg::STAGE_BYTES);
+                const uint32_t a_lo = a_hi + TC_A_BYTES;
+                const uint32_t b_hi = a_hi + 2 * TC_A_BYTES;
+                const uint32_t b_lo = b_hi + Cfg::B_BYTES;
+#pragma unroll
+                for (int k = 0; k < TC_BK / 8; ++k) {                 // UMMA K = 8 for tf32 = 32 bytes along the row
+                    const uint64_t dah = tc::umma_desc_kmajor_sw128(a_hi + k * 32, 1024);
+                    const uint64_t dal = tc::umma_desc_kmajor_sw128(a_lo + k * 32, 1024);
+                    const uint64_t dbh = tc::umma_desc_kmajor_sw128(b_hi + k * 32, 1024);
+                    const uint64_t dbl = tc::umma_desc_kmajor_sw128(b_lo + k * 32, 1024);
+                    tc::umma_tf32(tmem_base, dal, dbh, idesc, (it | k) != 0);     // small terms first
+                    tc::umma_tf32(tmem_base, dah, dbl, idesc, 1);
+                    tc::umma_tf32(tmem_base, dah, dbh, idesc, 1);
+                }
+                tc::umma_commit(&empty[s]);
+            }
+            tc::umma_commit(accum);
+        }
+    } else {
+        // ================= operand transform (main loop) =================
+        const int t = threadIdx.x - 64;                               // 0..127
+        for (int it = 0; it < iters; ++it) {
+            const int s = it % STAGES, round = it / STAGES;
+            tc::mbar_wait(&full[s], round & 1);
+            float4* a = reinterpret_cast<float4*>(smem + s * Cfg::STAGE_BYTES);
+            float4* alo = reinterpret_cast<float4*>(smem + s * Cfg::STAGE_BYTES + TC_A_BYTES);
+            // elementwise, layout-agnostic: the swizzled position of an element is the same in both buffers
+#pragma unroll
+            for (int j = 0; j < TC_A_BYTES / 16 / 128; ++j) {
+                const int idx = j * 128 + t;
+                const float4 v = a[idx];
+                float4 h, l;
+                h.x = __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u); l.x = v.x - h.x;
+                h.y = __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u); l.y = v.y - h.y;
+                h.z = __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u); l.z = v.z - h.z;
+                h.w = __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u); l.w = v.w - h.w;
+                a[idx] = h;
+                alo[idx] = l;
+            }
+            tc::fence_proxy_async_smem();          // generic-proxy writes -> visible to the tensor core (async proxy)
+            tc::mbar_arrive(&ready[s]);
+        }
+        // ================= epilogue =================
+        tc::mbar_wait(accum, 0);
+        tc::tcgen05_fence_after();
+        const int q = warp & 3;                                        // TMEM lane quarter this warp may read
+        const int m = q * 32 + lane;                                   // accumulator row = pixel within the tile
+        const int gy = y0 + m / TC_TW, gx = x0 + m % TC_TW;
+        const bool inb = gy < H && gx < W;
+        const size_t rowoff = (size_t(gy) * W + gx) * size_t(Cout) + n0;
+#pragma unroll 1
+        for (int c0 = 0; c0 < BN; c0 += 32) {
+            uint32_t v[32];
+            tc::tmem_ld_32x32(tmem_base + (uint32_t(q * 32) << 16) + uint32_t(c0), v);
+            tc::tmem_ld_wait();
+            if (inb) {
+                float r[32];
+#pragma unroll
+                for (int j = 0; j < 32; ++j) r[j] = __uint_as_float(v[j]);
+                if (MODE == MODE_FWD) {
+#pragma unroll
+                    for (int j = 0; j < 32; j += 4) {
+                        const float4 b = __ldg(reinterpret_cast<const float4*>(bias + n0 + c0 + j));
+                        r[j] = fmaxf(r[j] + b.x, 0.f); r[j + 1] = fmaxf(r[j + 1] + b.y, 0.f);
+                        r[j + 2] = fmaxf(r[j + 2] + b.z, 0.f); r[j + 3] = fmaxf(r[j + 3] + b.w, 0.f);
+                    }
+                } else {
+                    if (seed != nullptr) {
+#pragma unroll
+                        for (int j = 0; j < 32; j += 4) {
+                            const float4 sd = __ldg(reinterpret_cast<const float4*>(seed + rowoff + c0 + j));
+                            r[j] += sd.x; r[j + 1] += sd.y; r[j + 2] += sd.z; r[j + 3] += sd.w;
+                        }
+                    }
+                    if (mask_src != nullptr) {
+#pragma unroll
+                        for (int j = 0; j < 32; j += 4) {
+                            const float4 mk = __ldg(reinterpret_cast<const float4*>(mask_src + rowoff + c0 + j));
+                            r[j] = mk.x > 0.f ? r[j] : 0.f; r[j + 1] = mk.y > 0.f ? r[j + 1] : 0.f;
+                            r[j + 2] = mk.z > 0.f ? r[j + 2] : 0.f; r[j + 3] = mk.w > 0.f ? r[j + 3] : 0.f;
+                        }
+                    }
+                }
+#pragma unroll
+                for (int j = 0; j < 32; j += 4)
+                    *reinterpret_cast<float4*>(Y + rowoff + c0 + j) = make_float4(r[j], r[j + 1], r[j + 2], r[j + 3]);
+            }
+        }
+        tc::tcgen05_fence_before();
+    }
+    __syncthreads();
+    if (warp == 1) {
+        tc::tcgen05_fence_after();
+        tc::tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// weight preparation: K-major [tap][N][K] hi / lo split
+//   forward : N = Cout, K = Cin :  B[tap][co][ci] = W[tap][ci][co]
+//   gradient: N = Cin,  K = Cout:  B[tap][ci][co] = W[8-tap][ci][co]
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void split_weights_kernel(const float* __restrict__ Wf, float* __restrict__ hi, float* __restrict__ lo, int Cin,
+                                     int Cout, int gradient) {
+    const size_t total = size_t(9) * Cin * Cout;
+    for (size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += size_t(gridDim.x) * blockDim.x) {
+        float w;
+        if (!gradient) {
+            const int ci = int(i % Cin);
+            const size_t r = i / Cin;
+            const int co = int(r % Cout), tap = int(r / Cout);
+            w = Wf[(size_t(tap) * Cin + ci) * Cout + co];
+        } else {
+            const int co = int(i % Cout);
+            const size_t r = i / Cout;
+            const int ci = int(r % Cin), tap = int(r / Cin);
+            w = Wf[(size_t(8 - tap) * Cin + ci) * Cout + co];
+        }
+        const float h = __uint_as_float(__float_as_uint(w) & 0xFFFFE000u);
+        hi[i] = h;
+        lo[i] = w - h;
+    }
+}
+
+int prepare_tc_weights(adpst_vgg* h, int i, cudaStream_t st) {
+    const int cin = conv_cin(i), cout = conv_cout(i);
+    const size_t n = size_t(9) * cin * cout;
+    for (int g = 0; g < 2; ++g) {
+        ADPST_CUDA_CHECK(cudaMalloc(reinterpret_cast<void**>(&h->tc_hi[g][i]), n * 4));
+        ADPST_CUDA_CHECK(cudaMalloc(reinterpret_cast<void**>(&h->tc_lo[g][i]), n * 4));
+        split_weights_kernel<<<unsigned((n + 255) / 256 < 2048 ? (n + 255) / 256 : 2048), 256, 0, st>>>(
+            h->wf[i], h->tc_hi[g][i], h->tc_lo[g][i], cin, cout, g);
+        ADPST_LAUNCH_CHECK();
+        // tensor map of the [9*N][K] matrix (K innermost)
+        const int N = g ? cin : cout, K = g ? cout : cin;
+        const int BN = N >= 256 ? 256 : N;
+        const uint64_t dims[2] = {uint64_t(K), uint64_t(9) * N};
+        const uint64_t strides[1] = {uint64_t(K) * 4};
+        const uint32_t box[2] = {uint32_t(TC_BK), uint32_t(BN)};
+        int rc = tc::make_tensor_map_f32(&h->tm_hi[g][i], h->tc_hi[g][i], 2, dims, strides, box);
+        if (rc != ADPST_OK) return rc;
+        rc = tc::make_tensor_map_f32(&h->tm_lo[g][i], h->tc_lo[g][i], 2, dims, strides, box);
+        if (rc != ADPST_OK) return rc;
+    }
+    return ADPST_OK;
+}
+
+bool conv_tc_eligible(int Cin, int Cout) { return Cin % TC_BK == 0 && (Cout == 64 || Cout == 128 || Cout % 256 == 0); }
+
+template <int BN, int MODE>
+static int launch_tc(const CUtensorMap& tmA, const CUtensorMap& tmBhi, const CUtensorMap& tmBlo, const float* bias, float* Y,
+                     const float* seed, const float* mask, int H, int W, int Cin, int Cout, cudaStream_t st) {
+    using Cfg = TcCfg<BN>;
+    auto kern = conv3x3_tc_kernel<BN, MODE>;
+    static bool configured = false;
+    if (!configured) {
+        ADPST_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+        configured = true;
+    }
+    const int tw = (W + TC_TW - 1) / TC_TW, th = (H + TC_TH - 1) / TC_TH;
+    dim3 grid(tw * th, Cout / BN);
+    kern<<<grid, TC_THREADS, Cfg::SMEM_BYTES, st>>>(tmA, tmBhi, tmBlo, bias, Y, seed, mask, H, W, Cin, Cout, tw);
+    ADPST_LAUNCH_CHECK();
+    return ADPST_OK;
+}
+
+// X: (H,W,Cin) activation; gradient = 0: conv i forward (bias + ReLU), 1: data gradient of conv i (Cin/Cout are the GEMM's
+// K and N, i.e. already swapped for the gradient).
+int launch_conv_tc(adpst_vgg* h, int i, int gradient, const float* X, float* Y, const float* seed, const float* mask, int H,
+                   int W, int Cin, int Cout, cudaStream_t st) {
+    CUtensorMap tmA;
+    const uint64_t dims[4] = {uint64_t(Cin), uint64_t(W), uint64_t(H), 1};
+    const uint64_t strides[3] = {uint64_t(Cin) * 4, uint64_t(W) * Cin * 4, uint64_t(H) * W * Cin * 4};
+    const uint32_t box[4] = {uint32_t(TC_BK), uint32_t(TC_TW), uint32_t(TC_TH), 1};
+    int rc = tc::make_tensor_map_f32(&tmA, X, 4, dims, strides, box);
+    if (rc != ADPST_OK) return rc;
+    const CUtensorMap& bh = h->tm_hi[gradient][i];
+    const CUtensorMap& bl = h->tm_lo[gradient][i];
+    const float* bias = gradient ? nullptr : h->bias[i];
+    const int BN = Cout >= 256 ? 256 : Cout;
+    if (!gradient) {
+        if (BN == 256) return launch_tc<256, MODE_FWD>(tmA, bh, bl, bias, Y, seed, mask, H, W, Cin, Cout, st);
+        if (BN == 128) return launch_tc<128, MODE_FWD>(tmA, bh, bl, bias, Y, seed, mask, H, W, Cin, Cout, st);
+        return launch_tc<64, MODE_FWD>(tmA, bh, bl, bias, Y, seed, mask, H, W, Cin, Cout, st);
+    }
+    if (BN == 256) return launch_tc<256, MODE_BWD>(tmA, bh, bl, bias, Y, seed, mask, H, W, Cin, Cout, st);
+    if (BN == 128) return launch_tc<128, MODE_BWD>(tmA, bh, bl, bias, Y, seed, mask, H, W, Cin, Cout, st);
+    return launch_tc<64, MODE_BWD>(tmA, bh, bl, bias, Y, seed, mask, H, W, Cin, Cout, st);
+}
+
+}  // namespace adpst

@@ -1,0 +1,39 @@
+// vgg.cuh -- shared declarations of the VGG19 handle (vgg_simt.cu owns the C-ABI, conv_tc.cu the tensor-core path).
+#pragma once
+#include <cuda.h>
+
+#include "common.cuh"
+
+namespace adpst {
+
+constexpr int kNumConv = ADPST_VGG_NUM_CONV;
+// channels of the 13 convolutions block1_conv1 .. block5_conv1
+__host__ __device__ constexpr int conv_cin(int i) { return i == 0 ? 3 : i <= 2 ? 64 : i <= 4 ? 128 : i <= 8 ? 256 : 512; }
+__host__ __device__ constexpr int conv_cout(int i) { return i <= 1 ? 64 : i <= 3 ? 128 : i <= 7 ? 256 : 512; }
+
+enum { MODE_FWD = 0, MODE_BWD = 1 };
+enum { CONV_PATH_TENSOR = 0, CONV_PATH_SIMT = 1 };
+
+}  // namespace adpst
+
+struct adpst_vgg {
+    // exact-fp32 CUDA-core path
+    float* wf[adpst::kNumConv] = {};    // [tap][Cin][Cout]
+    float* wb[adpst::kNumConv] = {};    // [tap'][Cout][Cin]  (wb[0] unused)
+    float* bias[adpst::kNumConv] = {};
+    float* wg0 = nullptr;               // [tap'][3][64]
+    // tcgen05 path: K-major hi/lo splits, index 0 = forward, 1 = data gradient; tensor maps over [9*N][K]
+    float* tc_hi[2][adpst::kNumConv] = {};
+    float* tc_lo[2][adpst::kNumConv] = {};
+    CUtensorMap tm_hi[2][adpst::kNumConv];
+    CUtensorMap tm_lo[2][adpst::kNumConv];
+    bool tc_ready = false;
+    int conv_path = adpst::CONV_PATH_TENSOR;
+};
+
+namespace adpst {
+bool conv_tc_eligible(int Cin, int Cout);
+int prepare_tc_weights(adpst_vgg* h, int i, cudaStream_t st);
+int launch_conv_tc(adpst_vgg* h, int i, int gradient, const float* X, float* Y, const float* seed, const float* mask, int H,
+                   int W, int Cin, int Cout, cudaStream_t st);
+}  // namespace adpst

@@ -8,16 +8,10 @@
 //
 // Layout: activations NHWC (N = 1); forward weights [tap][Cin][Cout] (= Keras HWIO), gradient weights
 // [tap'][Cout][Cin] with the taps flipped, so the data gradient is the same 3x3 SAME convolution.
-#include "common.cuh"
+#include "vgg.cuh"
 
 namespace adpst {
 
-constexpr int kNumConv = ADPST_VGG_NUM_CONV;
-// channels and "pool before this conv" flags of the 13 convolutions
-__host__ __device__ constexpr int conv_cin(int i) {
-    return i == 0 ? 3 : i <= 2 ? 64 : i <= 4 ? 128 : i <= 8 ? 256 : 512;
-}
-__host__ __device__ constexpr int conv_cout(int i) { return i <= 1 ? 64 : i <= 3 ? 128 : i <= 7 ? 256 : 512; }
 // pool j sits after conv {1, 3, 7, 11}
 static const int kPoolAfter[ADPST_VGG_NUM_POOL] = {1, 3, 7, 11};
 static inline int pools_before(int conv) { return conv >= 12 ? 4 : conv >= 8 ? 3 : conv >= 4 ? 2 : conv >= 2 ? 1 : 0; }
@@ -31,7 +25,6 @@ static inline int pools_before(int conv) { return conv >= 12 ? 4 : conv >= 8 ? 3
 //            (model.py:28-29); zero padding applies to the preprocessed tensor.
 // ---------------------------------------------------------------------------------------------
 constexpr int CT_H = 8, CT_W = 16, CT_N = 64, CT_K = 8, CT_THREADS = 128, CT_XP = 20;
-enum { MODE_FWD = 0, MODE_BWD = 1 };
 
 template <int MODE, bool PRE>
 __global__ void __launch_bounds__(CT_THREADS)
@@ -307,13 +300,6 @@ static inline unsigned stream_grid(size_t items, int threads = 256) {
 // ---------------------------------------------------------------------------------------------
 // handle + orchestration
 // ---------------------------------------------------------------------------------------------
-struct adpst_vgg {
-    float* wf[adpst::kNumConv] = {};    // [tap][Cin][Cout]
-    float* wb[adpst::kNumConv] = {};    // [tap'][Cout][Cin]  (wb[0] unused)
-    float* bias[adpst::kNumConv] = {};
-    float* wg0 = nullptr;               // [tap'][3][64]
-};
-
 namespace adpst {
 
 static void layer_hw(int conv, int H, int W, int* h, int* w) {
@@ -322,7 +308,7 @@ static void layer_hw(int conv, int H, int W, int* h, int* w) {
     *w = W >> p;
 }
 
-static int launch_conv(int mode, bool pre, const float* X, const float* Wt, const float* bias, float* Y, const float* seed,
+static int launch_conv_simt(int mode, bool pre, const float* X, const float* Wt, const float* bias, float* Y, const float* seed,
                        const float* mask, int H, int W, int Cin, int Cout, cudaStream_t st) {
     ADPST_REQUIRE(Cout % CT_N == 0, "conv3x3: Cout=%d must be a multiple of %d", Cout, CT_N);
     ADPST_REQUIRE(pre || Cin % CT_K == 0, "conv3x3: Cin=%d must be a multiple of %d", Cin, CT_K);
@@ -336,6 +322,18 @@ static int launch_conv(int mode, bool pre, const float* X, const float* Wt, cons
         conv3x3_simt_kernel<MODE_BWD, false><<<grid, CT_THREADS, 0, st>>>(X, Wt, bias, Y, seed, mask, H, W, Cin, Cout, tw);
     ADPST_LAUNCH_CHECK();
     return ADPST_OK;
+}
+
+// One convolution of the network: tensor-core path when the shape allows it, exact-fp32 CUDA-core path otherwise
+// (block1_conv1: Cin = 3) or when the handle was switched to CONV_PATH_SIMT (validation).
+static int launch_conv(adpst_vgg* h, int i, int mode, const float* X, float* Y, const float* seed, const float* mask,
+                       int lh, int lw, cudaStream_t st) {
+    const bool grad = (mode == MODE_BWD);
+    const int K = grad ? conv_cout(i) : conv_cin(i), N = grad ? conv_cin(i) : conv_cout(i);
+    if (h->conv_path == CONV_PATH_TENSOR && h->tc_ready && i > 0 && conv_tc_eligible(K, N))
+        return launch_conv_tc(h, i, grad ? 1 : 0, X, Y, seed, mask, lh, lw, K, N, st);
+    return launch_conv_simt(mode, i == 0 && !grad, X, grad ? h->wb[i] : h->wf[i], grad ? nullptr : h->bias[i], Y, seed, mask,
+                            lh, lw, K, N, st);
 }
 
 }  // namespace adpst
@@ -393,6 +391,11 @@ int adpst_vgg_create(const float* const* kernels_dev, const float* const* biases
         adpst_vgg_destroy(h);
         return fail(ADPST_ERR_CUDA, "vgg_create: %s", cudaGetErrorString(e));
     }
+    for (int i = 1; i < kNumConv; ++i) {
+        int rc = prepare_tc_weights(h, i, st);
+        if (rc != ADPST_OK) { adpst_vgg_destroy(h); return rc; }
+    }
+    h->tc_ready = true;
     *out = h;
     return ADPST_OK;
 }
@@ -403,6 +406,10 @@ void adpst_vgg_destroy(adpst_vgg* h) {
         if (h->wf[i]) cudaFree(h->wf[i]);
         if (h->wb[i]) cudaFree(h->wb[i]);
         if (h->bias[i]) cudaFree(h->bias[i]);
+        for (int g = 0; g < 2; ++g) {
+            if (h->tc_hi[g][i]) cudaFree(h->tc_hi[g][i]);
+            if (h->tc_lo[g][i]) cudaFree(h->tc_lo[g][i]);
+        }
     }
     if (h->wg0) cudaFree(h->wg0);
     delete h;
@@ -422,8 +429,7 @@ int adpst_vgg_forward(adpst_vgg* h, const float* image_dev, int H, int W, float*
         int lh, lw;
         layer_hw(i, H, W, &lh, &lw);
         ADPST_REQUIRE(acts_dev[i] != nullptr, "vgg_forward: acts[%d] is NULL", i);
-        int rc = launch_conv(MODE_FWD, i == 0, x, h->wf[i], h->bias[i], acts_dev[i], nullptr, nullptr, lh, lw, conv_cin(i),
-                             conv_cout(i), st);
+        int rc = launch_conv(h, i, MODE_FWD, x, acts_dev[i], nullptr, nullptr, lh, lw, st);
         if (rc != ADPST_OK) return rc;
         x = acts_dev[i];
         for (int j = 0; j < ADPST_VGG_NUM_POOL; ++j) {
@@ -439,18 +445,23 @@ int adpst_vgg_forward(adpst_vgg* h, const float* image_dev, int H, int W, float*
     return ADPST_OK;
 }
 
+int adpst_vgg_set_conv_path(adpst_vgg* h, int path) {
+    using namespace adpst;
+    ADPST_REQUIRE(h && (path == CONV_PATH_TENSOR || path == CONV_PATH_SIMT), "vgg_set_conv_path: bad argument");
+    h->conv_path = path;
+    return ADPST_OK;
+}
+
 int adpst_vgg_conv_forward(adpst_vgg* h, int i, const float* x_dev, int lh, int lw, float* y_dev, adpst_stream_t stream) {
     using namespace adpst;
     ADPST_REQUIRE(h && x_dev && y_dev && i >= 0 && i < kNumConv && lh > 0 && lw > 0, "vgg_conv_forward: bad argument");
-    return launch_conv(MODE_FWD, i == 0, x_dev, h->wf[i], h->bias[i], y_dev, nullptr, nullptr, lh, lw, conv_cin(i),
-                       conv_cout(i), as_stream(stream));
+    return launch_conv(h, i, MODE_FWD, x_dev, y_dev, nullptr, nullptr, lh, lw, as_stream(stream));
 }
 
 int adpst_vgg_conv_dgrad(adpst_vgg* h, int i, const float* dpre_dev, int lh, int lw, float* dx_dev, adpst_stream_t stream) {
     using namespace adpst;
     ADPST_REQUIRE(h && dpre_dev && dx_dev && i >= 1 && i < kNumConv && lh > 0 && lw > 0, "vgg_conv_dgrad: bad argument");
-    return launch_conv(MODE_BWD, false, dpre_dev, h->wb[i], nullptr, dx_dev, nullptr, nullptr, lh, lw, conv_cout(i),
-                       conv_cin(i), as_stream(stream));
+    return launch_conv(h, i, MODE_BWD, dpre_dev, dx_dev, nullptr, nullptr, lh, lw, as_stream(stream));
 }
 
 int adpst_vgg_backward(adpst_vgg* h, int H, int W, const float* const* acts_dev, const float* const* pools_dev,
@@ -477,14 +488,12 @@ int adpst_vgg_backward(adpst_vgg* h, int H, int W, const float* const* acts_dev,
         for (int j = 0; j < ADPST_VGG_NUM_POOL; ++j) pooled_input |= (kPoolAfter[j] == i - 1);
         if (!pooled_input) {
             // input of conv i is the post-ReLU output of conv i-1 at the same resolution
-            int rc = launch_conv(MODE_BWD, false, cur, h->wb[i], nullptr, nxt, seeds_dev[i - 1], acts_dev[i - 1], lh, lw,
-                                 conv_cout(i), conv_cin(i), st);
+            int rc = launch_conv(h, i, MODE_BWD, cur, nxt, seeds_dev[i - 1], acts_dev[i - 1], lh, lw, st);
             if (rc != ADPST_OK) return rc;
             float* t = cur; cur = nxt; nxt = t;
         } else {
             // gradient w.r.t. the pooled tensor, then route through the pool + ReLU of conv i-1
-            int rc = launch_conv(MODE_BWD, false, cur, h->wb[i], nullptr, nxt, nullptr, nullptr, lh, lw, conv_cout(i),
-                                 conv_cin(i), st);
+            int rc = launch_conv(h, i, MODE_BWD, cur, nxt, nullptr, nullptr, lh, lw, st);
             if (rc != ADPST_OK) return rc;
             int ph, pw;
             layer_hw(i - 1, H, W, &ph, &pw);

@@ -97,6 +97,10 @@ int adpst_vgg_pool_shape(int j, int H, int W, int* h, int* w, int* c);
 int adpst_vgg_forward(adpst_vgg* h, const float* image_dev, int H, int W, float* const* acts_dev,
                       float* const* pools_dev, int last, adpst_stream_t stream);
 
+/* Convolution kernel family used by this handle: 0 = tcgen05 3xTF32 implicit GEMM (default; block1_conv1 and the
+ * gradient to the image always use the CUDA-core kernels), 1 = exact-float32 CUDA-core kernels everywhere (validation). */
+int adpst_vgg_set_conv_path(adpst_vgg* h, int path);
+
 /* One layer in isolation (parity tests, per-kernel roofline in bench.py).
  * conv_forward: y = relu(conv_i(x) + b_i); for i == 0, x is the [0,1] RGB image (h,w,3).
  * conv_dgrad  : dx = conv_i^T(dpre) (i >= 1), no mask, no seed. */
