@@ -58,6 +58,12 @@ class VGG19Handle:
                                                    ctypes.byref(h)))
             torch.cuda.current_stream().synchronize()        # ks / bs may be freed after this
         self._h = h
+        if os.environ.get("ADPST_CONV_PATH", "").lower() == "simt":      # validation switch: exact-fp32 CUDA-core kernels
+            self.set_conv_path("simt")
+
+    def set_conv_path(self, path):
+        """'tensor' (default: tcgen05 3xTF32 implicit GEMM) or 'simt' (exact float32 CUDA-core kernels, validation)."""
+        _lib.check(_lib.lib().adpst_vgg_set_conv_path(self._h, {"tensor": 0, "simt": 1}[path]))
 
     def __del__(self):
         h, self._h = getattr(self, "_h", None), None

@@ -12,15 +12,17 @@
 // Precision: the reference computes in float32 and parity is 1e-5.  One TF32 MMA (10-bit mantissa) is 1e-3.
 // Every product is therefore formed as  a_hi*b_hi + a_hi*b_lo + a_lo*b_hi  ("3xTF32"), all three accumulating into the
 // same fp32 TMEM accumulator:
-//   a_hi = a with the 13 low mantissa bits cleared (exactly representable in TF32, so the tensor core's own
-//          fp32->tf32 conversion cannot change it),  a_lo = a - a_hi (exact in fp32, <= 13 significant bits).
+//   a_hi = a rounded to TF32 with cvt.rna (exactly representable, so the tensor core's own fp32->tf32 conversion -- a
+//          truncation, measured -- cannot change it),  a_lo = rna_tf32(a - a_hi)  (a - a_hi is exact in fp32).
+//          Rounding instead of masking keeps both splits unbiased; a biased split compounds over the 12 layers.
 //   b_hi / b_lo are split once when the weights are loaded; a_hi / a_lo are split in shared memory by the
 //   "transform" warps between the TMA landing and the MMA issue.
 // The dropped a_lo*b_lo term and the tf32 rounding of the lo parts are O(2^-22) relative.
 //
-// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer (one elected lane),
-// warps 2..5 = operand transform during the main loop, then the epilogue (TMEM -> registers -> bias/ReLU or
-// seed/mask -> global).  Three mbarrier rings: full (TMA landed) -> ready (A split done) -> empty (MMAs retired).
+// Warp roles (320 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer (one elected lane),
+// warps 2..5 = operand transform (A hi/lo split), warps 6..9 = chunk promotion TMEM -> registers, then the epilogue
+// (bias/ReLU or seed/mask -> global).  mbarrier rings: full (TMA landed) -> ready (A split done) -> empty (MMAs retired),
+// chunk_full / chunk_empty for the two TMEM chunk buffers.
 #include "tc_common.cuh"
 #include "vgg.cuh"
 
@@ -57,17 +59,27 @@ int make_tensor_map_f32(CUtensorMap* out, const void* base, int rank, const uint
 }  // namespace tc
 
 // ---------------------------------------------------------------------------------------------------------------
+// Accumulation accuracy.  Measured on B200 (scripts/tc_error_probe.py): tcgen05.mma adds into its fp32 accumulator with
+// truncation, a systematic bias of about -2^-26 of the accumulator per MMA; over K = 4608 (1728 MMAs) that is -2.7e-5,
+// above the 1e-5 parity bar.  Therefore:
+//   * the big term a_hi*b_hi is accumulated in TMEM only over CHUNK_ITERS stages (8 MMAs) at a time, in two TMEM buffers
+//     used alternately; four "drain" warps promote each finished chunk into fp32 REGISTERS with round-to-nearest adds
+//     while the tensor core already works on the next chunk;
+//   * the two small terms (2^-11 of the big one) accumulate in a third TMEM buffer for the whole tile -- their bias is
+//     2^-11 smaller and negligible -- and are added once at the end.
+// ---------------------------------------------------------------------------------------------------------------
 constexpr int TC_TH = 8, TC_TW = 16, TC_BM = TC_TH * TC_TW;     // 128 pixels = UMMA M
 constexpr int TC_BK = 32;                                        // 32 fp32 = one 128-byte swizzle row
-constexpr int TC_THREADS = 192;
+constexpr int TC_THREADS = 320;                                  // TMA, MMA, 4 transform warps, 4 drain/epilogue warps
 constexpr int TC_A_BYTES = TC_BM * TC_BK * 4;                    // 16 KB
+constexpr int TC_CHUNK_ITERS = 2;                                // stages per promoted chunk (8 big MMAs)
 
 template <int BN> struct TcCfg {
-    static constexpr int STAGES = BN >= 256 ? 2 : BN >= 128 ? 3 : 2;
+    static constexpr int STAGES = BN >= 128 ? 3 : 4;
     static constexpr int B_BYTES = BN * TC_BK * 4;
-    static constexpr int STAGE_BYTES = 2 * TC_A_BYTES + 2 * B_BYTES;        // A, A_lo, B_hi, B_lo
+    static constexpr int STAGE_BYTES = 2 * TC_A_BYTES + 2 * B_BYTES;        // A (hi in place), A_lo, B_hi, B_lo
     static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*alignment slack*/ + 256 /*barriers*/;
-    static constexpr uint32_t TMEM_COLS = BN < 32 ? 32 : BN;                // power of two >= 32
+    static constexpr uint32_t TMEM_COLS = 4 * BN;                           // big0 | big1 | small | (unused), power of two
 };
 
 template <int BN, int MODE>
@@ -78,14 +90,17 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                   int tiles_w) {
     using Cfg = TcCfg<BN>;
     constexpr int STAGES = Cfg::STAGES;
+    static_assert(BN == 64 || BN == 128, "tile width");
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES);
-    uint64_t* full = bars;                  // [STAGES]  TMA bytes landed
-    uint64_t* ready = bars + STAGES;        // [STAGES]  A split into hi/lo
-    uint64_t* empty = bars + 2 * STAGES;    // [STAGES]  MMAs that read the stage have retired
-    uint64_t* accum = bars + 3 * STAGES;    // [1]       accumulator complete
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * STAGES + 1);
+    uint64_t* full = bars;                      // [STAGES]  TMA bytes landed
+    uint64_t* ready = bars + STAGES;            // [STAGES]  A split into hi/lo
+    uint64_t* empty = bars + 2 * STAGES;        // [STAGES]  MMAs that read the stage have retired
+    uint64_t* chunk_full = bars + 3 * STAGES;   // [2]       a big-term chunk is complete in TMEM buffer b
+    uint64_t* chunk_empty = chunk_full + 2;     // [2]       the drain warps have consumed TMEM buffer b
+    uint64_t* small_full = chunk_empty + 2;     // [1]       every MMA of the tile has retired
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(small_full + 1);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int tile = blockIdx.x;
@@ -93,6 +108,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     const int n0 = blockIdx.y * BN;
     const int kchunks = Cin / TC_BK;
     const int iters = 9 * kchunks;
+    const int nchunks = (iters + TC_CHUNK_ITERS - 1) / TC_CHUNK_ITERS;
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < STAGES; ++s) {
@@ -100,7 +116,11 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             tc::mbar_init(&ready[s], 128);
             tc::mbar_init(&empty[s], 1);
         }
-        tc::mbar_init(accum, 1);
+        for (int b = 0; b < 2; ++b) {
+            tc::mbar_init(&chunk_full[b], 1);
+            tc::mbar_init(&chunk_empty[b], 128);
+        }
+        tc::mbar_init(small_full, 1);
         tc::fence_barrier_init();
         tc::tma_prefetch_desc(&tmA);
         tc::tma_prefetch_desc(&tmBhi);
@@ -111,6 +131,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     __syncthreads();
     tc::tcgen05_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    const uint32_t tmem_small = tmem_base + 2 * BN;
 
     if (warp == 0) {
         // ================= TMA producer =================
@@ -133,29 +154,36 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             constexpr uint32_t idesc = tc::umma_idesc_tf32(TC_BM, BN);
             for (int it = 0; it < iters; ++it) {
                 const int s = it % STAGES, round = it / STAGES;
-                tc::mbar_wait(&full[s], round & 1);      // B operands (TMA) ...
-                tc::mbar_wait(&ready[s], round & 1);     // ... and the A hi/lo split (transform warps)
+                const int c = it / TC_CHUNK_ITERS, cpos = it - c * TC_CHUNK_ITERS;
+                const uint32_t tmem_big = tmem_base + uint32_t(c & 1) * BN;
+                if (cpos == 0) {                                          // TMEM buffer must have been drained
+                    tc::mbar_wait(&chunk_empty[c & 1], ((c >> 1) & 1) ^ 1);
+                    tc::tcgen05_fence_after();
+                }
+                tc::mbar_wait(&full[s], round & 1);                       // B operands (TMA) ...
+                tc::mbar_wait(&ready[s], round & 1);                      // ... and the A hi/lo split (transform warps)
                 tc::tcgen05_fence_after();
                 const uint32_t a_hi = tc::smem_u32(smem + s * Cfg::STAGE_BYTES);
                 const uint32_t a_lo = a_hi + TC_A_BYTES;
                 const uint32_t b_hi = a_hi + 2 * TC_A_BYTES;
                 const uint32_t b_lo = b_hi + Cfg::B_BYTES;
 #pragma unroll
-                for (int k = 0; k < TC_BK / 8; ++k) {                 // UMMA K = 8 for tf32 = 32 bytes along the row
+                for (int k = 0; k < TC_BK / 8; ++k) {                     // UMMA K = 8 for tf32 = 32 bytes along the row
                     const uint64_t dah = tc::umma_desc_kmajor_sw128(a_hi + k * 32, 1024);
                     const uint64_t dal = tc::umma_desc_kmajor_sw128(a_lo + k * 32, 1024);
                     const uint64_t dbh = tc::umma_desc_kmajor_sw128(b_hi + k * 32, 1024);
                     const uint64_t dbl = tc::umma_desc_kmajor_sw128(b_lo + k * 32, 1024);
-                    tc::umma_tf32(tmem_base, dal, dbh, idesc, (it | k) != 0);     // small terms first
-                    tc::umma_tf32(tmem_base, dah, dbl, idesc, 1);
-                    tc::umma_tf32(tmem_base, dah, dbh, idesc, 1);
+                    tc::umma_tf32(tmem_small, dal, dbh, idesc, (it | k) != 0);
+                    tc::umma_tf32(tmem_small, dah, dbl, idesc, 1);
+                    tc::umma_tf32(tmem_big, dah, dbh, idesc, (cpos | k) != 0);
                 }
                 tc::umma_commit(&empty[s]);
+                if (cpos == TC_CHUNK_ITERS - 1 || it == iters - 1) tc::umma_commit(&chunk_full[c & 1]);
             }
-            tc::umma_commit(accum);
+            tc::umma_commit(small_full);
         }
-    } else {
-        // ================= operand transform (main loop) =================
+    } else if (warp < 6) {
+        // ================= operand transform =================
         const int t = threadIdx.x - 64;                               // 0..127
         for (int it = 0; it < iters; ++it) {
             const int s = it % STAGES, round = it / STAGES;
@@ -168,33 +196,53 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                 const int idx = j * 128 + t;
                 const float4 v = a[idx];
                 float4 h, l;
-                h.x = __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u); l.x = v.x - h.x;
-                h.y = __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u); l.y = v.y - h.y;
-                h.z = __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u); l.z = v.z - h.z;
-                h.w = __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u); l.w = v.w - h.w;
+                h.x = tc::round_tf32(v.x); l.x = tc::round_tf32(v.x - h.x);
+                h.y = tc::round_tf32(v.y); l.y = tc::round_tf32(v.y - h.y);
+                h.z = tc::round_tf32(v.z); l.z = tc::round_tf32(v.z - h.z);
+                h.w = tc::round_tf32(v.w); l.w = tc::round_tf32(v.w - h.w);
                 a[idx] = h;
                 alo[idx] = l;
             }
             tc::fence_proxy_async_smem();          // generic-proxy writes -> visible to the tensor core (async proxy)
             tc::mbar_arrive(&ready[s]);
         }
-        // ================= epilogue =================
-        tc::mbar_wait(accum, 0);
-        tc::tcgen05_fence_after();
+    } else {
+        // ================= drain (chunk promotion) + epilogue =================
         const int q = warp & 3;                                        // TMEM lane quarter this warp may read
+        const uint32_t lane_base = uint32_t(q * 32) << 16;
+        float acc[BN];
+#pragma unroll
+        for (int j = 0; j < BN; ++j) acc[j] = 0.f;
+        for (int c = 0; c < nchunks; ++c) {
+            tc::mbar_wait(&chunk_full[c & 1], (c >> 1) & 1);
+            tc::tcgen05_fence_after();
+            const uint32_t src = tmem_base + uint32_t(c & 1) * BN + lane_base;
+#pragma unroll
+            for (int c0 = 0; c0 < BN; c0 += 32) {
+                uint32_t v[32];
+                tc::tmem_ld_32x32(src + c0, v);
+                tc::tmem_ld_wait();
+#pragma unroll
+                for (int j = 0; j < 32; ++j) acc[c0 + j] += __uint_as_float(v[j]);
+            }
+            tc::tcgen05_fence_before();
+            tc::mbar_arrive(&chunk_empty[c & 1]);
+        }
+        tc::mbar_wait(small_full, 0);
+        tc::tcgen05_fence_after();
         const int m = q * 32 + lane;                                   // accumulator row = pixel within the tile
         const int gy = y0 + m / TC_TW, gx = x0 + m % TC_TW;
         const bool inb = gy < H && gx < W;
         const size_t rowoff = (size_t(gy) * W + gx) * size_t(Cout) + n0;
-#pragma unroll 1
+#pragma unroll
         for (int c0 = 0; c0 < BN; c0 += 32) {
             uint32_t v[32];
-            tc::tmem_ld_32x32(tmem_base + (uint32_t(q * 32) << 16) + uint32_t(c0), v);
+            tc::tmem_ld_32x32(tmem_small + lane_base + c0, v);
             tc::tmem_ld_wait();
             if (inb) {
                 float r[32];
 #pragma unroll
-                for (int j = 0; j < 32; ++j) r[j] = __uint_as_float(v[j]);
+                for (int j = 0; j < 32; ++j) r[j] = acc[c0 + j] + __uint_as_float(v[j]);
                 if (MODE == MODE_FWD) {
 #pragma unroll
                     for (int j = 0; j < 32; j += 4) {
@@ -254,9 +302,9 @@ __global__ void split_weights_kernel(const float* __restrict__ Wf, float* __rest
             const int ci = int(r % Cin), tap = int(r / Cin);
             w = Wf[(size_t(8 - tap) * Cin + ci) * Cout + co];
         }
-        const float h = __uint_as_float(__float_as_uint(w) & 0xFFFFE000u);
+        const float h = tc::round_tf32(w);
         hi[i] = h;
-        lo[i] = w - h;
+        lo[i] = tc::round_tf32(w - h);
     }
 }
 
@@ -271,7 +319,7 @@ int prepare_tc_weights(adpst_vgg* h, int i, cudaStream_t st) {
         ADPST_LAUNCH_CHECK();
         // tensor map of the [9*N][K] matrix (K innermost)
         const int N = g ? cin : cout, K = g ? cout : cin;
-        const int BN = N >= 256 ? 256 : N;
+        const int BN = N >= 128 ? 128 : N;
         const uint64_t dims[2] = {uint64_t(K), uint64_t(9) * N};
         const uint64_t strides[1] = {uint64_t(K) * 4};
         const uint32_t box[2] = {uint32_t(TC_BK), uint32_t(BN)};
@@ -283,7 +331,7 @@ int prepare_tc_weights(adpst_vgg* h, int i, cudaStream_t st) {
     return ADPST_OK;
 }
 
-bool conv_tc_eligible(int Cin, int Cout) { return Cin % TC_BK == 0 && (Cout == 64 || Cout == 128 || Cout % 256 == 0); }
+bool conv_tc_eligible(int Cin, int Cout) { return Cin % TC_BK == 0 && (Cout == 64 || Cout % 128 == 0); }
 
 template <int BN, int MODE>
 static int launch_tc(const CUtensorMap& tmA, const CUtensorMap& tmBhi, const CUtensorMap& tmBlo, const float* bias, float* Y,
@@ -315,13 +363,11 @@ int launch_conv_tc(adpst_vgg* h, int i, int gradient, const float* X, float* Y, 
     const CUtensorMap& bh = h->tm_hi[gradient][i];
     const CUtensorMap& bl = h->tm_lo[gradient][i];
     const float* bias = gradient ? nullptr : h->bias[i];
-    const int BN = Cout >= 256 ? 256 : Cout;
+    const int BN = Cout >= 128 ? 128 : Cout;
     if (!gradient) {
-        if (BN == 256) return launch_tc<256, MODE_FWD>(tmA, bh, bl, bias, Y, seed, mask, H, W, Cin, Cout, st);
         if (BN == 128) return launch_tc<128, MODE_FWD>(tmA, bh, bl, bias, Y, seed, mask, H, W, Cin, Cout, st);
         return launch_tc<64, MODE_FWD>(tmA, bh, bl, bias, Y, seed, mask, H, W, Cin, Cout, st);
     }
-    if (BN == 256) return launch_tc<256, MODE_BWD>(tmA, bh, bl, bias, Y, seed, mask, H, W, Cin, Cout, st);
     if (BN == 128) return launch_tc<128, MODE_BWD>(tmA, bh, bl, bias, Y, seed, mask, H, W, Cin, Cout, st);
     return launch_tc<64, MODE_BWD>(tmA, bh, bl, bias, Y, seed, mask, H, W, Cin, Cout, st);
 }

@@ -39,7 +39,7 @@ def test_forward_matches_fp32_kernel(i, h, w, ext, synth):
     y_ref = _run(ext, "adpst_vgg_conv_forward", i, x, h, w, cout, 1)
     assert torch.isfinite(y_tc).all()
     err = float((y_tc - y_ref).abs().max() / y_ref.abs().max())
-    assert err < 3e-6, err
+    assert err < 6e-6, err       # both kernels are ~1-3e-6 from float64 at K = 4608
 
 
 @pytest.mark.parametrize("i", [1, 2, 4, 8, 12])
@@ -52,4 +52,22 @@ def test_dgrad_matches_fp32_kernel(i, h, w, ext, synth):
     y_ref = _run(ext, "adpst_vgg_conv_dgrad", i, d, h, w, cin, 1)
     assert torch.isfinite(y_tc).all()
     err = float((y_tc - y_ref).abs().max() / y_ref.abs().max())
-    assert err < 3e-6, err
+    assert err < 6e-6, err
+
+
+@pytest.mark.parametrize("i", [1, 4, 9, 12])
+def test_forward_is_unbiased_against_float64(i, ext, synth):
+    """The tensor core accumulates with truncation (-2^-26 per MMA); chunk promotion must remove the bias."""
+    import torch.nn.functional as F
+    cin, cout = synth.CONV_LAYERS[i][1], synth.CONV_LAYERS[i][2]
+    h = w = 32
+    g = torch.Generator(device="cuda").manual_seed(i)
+    x = (torch.rand(h, w, cin, device="cuda", generator=g) * 200.0).contiguous()
+    k, b = synth.vgg_weights(seed=7)[synth.CONV_LAYERS[i][0]]
+    ref = F.relu(F.conv2d(x.double().permute(2, 0, 1)[None], torch.as_tensor(k).double().cuda().permute(3, 2, 0, 1),
+                          torch.as_tensor(b).double().cuda(), padding=1))[0].permute(1, 2, 0)
+    y = _run(ext, "adpst_vgg_conv_forward", i, x, h, w, cout, 0).double()
+    sc = float(ref.abs().max())
+    assert float((y - ref).abs().max()) / sc < 5e-6
+    big = ref > 0.1 * sc
+    assert abs(float(((y - ref) / ref)[big].mean())) < 1e-6      # was -2.7e-5 at K = 4608 without promotion
