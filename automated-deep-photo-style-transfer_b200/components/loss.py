@@ -125,8 +125,9 @@ class Loss:
             G = kernels.gram_masked(F, st["masks"], st["K"], st["ws"])
             shared = name in seeds                                            # a layer can be both content and style
             dF = seeds[name] if shared else st["seed"]
-            kernels.style_layer_backward(F, st["masks"], st["K"], G, st["A"], 1.0 / n_args, wts['style'] / n_args,
-                                         self._acc[1:2], dF.reshape(h * w, C), accumulate=shared, workspace=st["ws"])
+            kernels.style_layer_backward(out.reshape(h, w, C), st["masks"], st["K"], G, st["A"], 1.0 / n_args,
+                                         wts['style'] / n_args, self._acc[1:2], dF.reshape(h * w, C), accumulate=shared,
+                                         workspace=st["ws"])
             seeds[name] = dF
 
         self._photo_grad = None

@@ -73,21 +73,29 @@ constexpr int TC_BK = 32;                                        // 32 fp32 = on
 constexpr int TC_THREADS = 320;                                  // TMA, MMA, 4 transform warps, 4 drain/epilogue warps
 constexpr int TC_A_BYTES = TC_BM * TC_BK * 4;                    // 16 KB
 constexpr int TC_CHUNK_ITERS = 2;                                // stages per promoted chunk (8 big MMAs)
+constexpr int TC_MAX_CLASSES = 32;                               // style mode: classes per launch (active set is a bit mask)
 
 template <int BN> struct TcCfg {
     static constexpr int STAGES = BN >= 128 ? 3 : 4;
     static constexpr int B_BYTES = BN * TC_BK * 4;
     static constexpr int STAGE_BYTES = 2 * TC_A_BYTES + 2 * B_BYTES;        // A (hi in place), A_lo, B_hi, B_lo
-    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*alignment slack*/ + 256 /*barriers*/;
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*alignment slack*/ + 256 /*barriers*/ +
+                                      TC_MAX_CLASSES * TC_BM * 4 /*per-pixel class weights (style mode)*/;
     static constexpr uint32_t TMEM_COLS = 4 * BN;                           // big0 | big1 | small | (unused), power of two
 };
+
+// position of the n-th (0-based) set bit of m
+__device__ __forceinline__ int nth_set_bit(uint32_t m, int n) {
+    for (int i = 0; i < n; ++i) m &= m - 1;
+    return __ffs(int(m)) - 1;
+}
 
 template <int BN, int MODE>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmBhi,
                   const __grid_constant__ CUtensorMap tmBlo, const float* __restrict__ bias, float* __restrict__ Y,
                   const float* __restrict__ seed, const float* __restrict__ mask_src, int H, int W, int Cin, int Cout,
-                  int tiles_w) {
+                  int tiles_w, const float* __restrict__ cls_masks, int num_cls) {
     using Cfg = TcCfg<BN>;
     constexpr int STAGES = Cfg::STAGES;
     static_assert(BN == 64 || BN == 128, "tile width");
@@ -101,13 +109,34 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     uint64_t* chunk_empty = chunk_full + 2;     // [2]       the drain warps have consumed TMEM buffer b
     uint64_t* small_full = chunk_empty + 2;     // [1]       every MMA of the tile has retired
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(small_full + 1);
+    float* cls_w = reinterpret_cast<float*>(bars + 32);                // [num_cls][128]  (style mode)
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int tile = blockIdx.x;
     const int y0 = (tile / tiles_w) * TC_TH, x0 = (tile % tiles_w) * TC_TW;
     const int n0 = blockIdx.y * BN;
     const int kchunks = Cin / TC_BK;
-    const int iters = 9 * kchunks;
+    // "taps" of the K loop: the 9 filter taps (convolution) or the classes whose mask is non-zero somewhere in this pixel
+    // tile (style gradient: dF = sum_k w_k F D_k is a 1x1 convolution per class with a per-pixel weight w_k = m_k^2).
+    uint32_t active = 0x1FFu;
+    if (MODE == MODE_STYLE) {
+        active = 0u;
+        const int t = threadIdx.x;
+        const int gy = y0 + t / TC_TW, gx = x0 + t % TC_TW;
+        for (int k = 0; k < num_cls; ++k) {
+            float w = 0.f;
+            if (t < TC_BM) {
+                if (gy < H && gx < W) {
+                    w = cls_masks ? __ldg(cls_masks + size_t(k) * H * W + size_t(gy) * W + gx) : 1.0f;
+                    w *= w;
+                }
+                cls_w[k * TC_BM + t] = w;
+            }
+            if (__syncthreads_or(w != 0.f)) active |= 1u << k;
+        }
+    }
+    const int ntaps = __popc(active);
+    const int iters = ntaps * kchunks;
     const int nchunks = (iters + TC_CHUNK_ITERS - 1) / TC_CHUNK_ITERS;
 
     if (threadIdx.x == 0) {
@@ -139,8 +168,9 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             for (int it = 0; it < iters; ++it) {
                 const int s = it % STAGES, round = it / STAGES;
                 tc::mbar_wait(&empty[s], (round & 1) ^ 1);
-                const int tap = it / kchunks, kc = it - tap * kchunks;
-                const int kh = tap / 3, kw = tap - kh * 3;
+                const int slot = it / kchunks, kc = it - slot * kchunks;
+                const int tap = (MODE == MODE_STYLE) ? nth_set_bit(active, slot) : slot;
+                const int kh = (MODE == MODE_STYLE) ? 1 : tap / 3, kw = (MODE == MODE_STYLE) ? 1 : tap - (tap / 3) * 3;
                 uint8_t* st = smem + s * Cfg::STAGE_BYTES;
                 tc::mbar_arrive_expect_tx(&full[s], TC_A_BYTES + 2 * Cfg::B_BYTES);
                 tc::tma_load_4d(st, &tmA, &full[s], kc * TC_BK, x0 + kw - 1, y0 + kh - 1, 0);
@@ -180,7 +210,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                 tc::umma_commit(&empty[s]);
                 if (cpos == TC_CHUNK_ITERS - 1 || it == iters - 1) tc::umma_commit(&chunk_full[c & 1]);
             }
-            tc::umma_commit(small_full);
+            if (iters > 0) tc::umma_commit(small_full);
         }
     } else if (warp < 6) {
         // ================= operand transform =================
@@ -190,11 +220,17 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             tc::mbar_wait(&full[s], round & 1);
             float4* a = reinterpret_cast<float4*>(smem + s * Cfg::STAGE_BYTES);
             float4* alo = reinterpret_cast<float4*>(smem + s * Cfg::STAGE_BYTES + TC_A_BYTES);
+            const float* wrow = nullptr;
+            if (MODE == MODE_STYLE) wrow = cls_w + nth_set_bit(active, it / kchunks) * TC_BM;
             // elementwise, layout-agnostic: the swizzled position of an element is the same in both buffers
 #pragma unroll
             for (int j = 0; j < TC_A_BYTES / 16 / 128; ++j) {
                 const int idx = j * 128 + t;
-                const float4 v = a[idx];
+                float4 v = a[idx];
+                if (MODE == MODE_STYLE) {                 // the swizzle permutes 16-byte chunks within a 128-byte row only
+                    const float w = wrow[idx >> 3];
+                    v.x *= w; v.y *= w; v.z *= w; v.w *= w;
+                }
                 float4 h, l;
                 h.x = tc::round_tf32(v.x); l.x = tc::round_tf32(v.x - h.x);
                 h.y = tc::round_tf32(v.y); l.y = tc::round_tf32(v.y - h.y);
@@ -228,8 +264,10 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             tc::tcgen05_fence_before();
             tc::mbar_arrive(&chunk_empty[c & 1]);
         }
-        tc::mbar_wait(small_full, 0);
-        tc::tcgen05_fence_after();
+        if (iters > 0) {
+            tc::mbar_wait(small_full, 0);
+            tc::tcgen05_fence_after();
+        }
         const int m = q * 32 + lane;                                   // accumulator row = pixel within the tile
         const int gy = y0 + m / TC_TW, gx = x0 + m % TC_TW;
         const bool inb = gy < H && gx < W;
@@ -237,13 +275,26 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 #pragma unroll
         for (int c0 = 0; c0 < BN; c0 += 32) {
             uint32_t v[32];
-            tc::tmem_ld_32x32(tmem_small + lane_base + c0, v);
-            tc::tmem_ld_wait();
+            if (iters > 0) {
+                tc::tmem_ld_32x32(tmem_small + lane_base + c0, v);
+                tc::tmem_ld_wait();
+            } else {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v[j] = 0u;
+            }
             if (inb) {
                 float r[32];
 #pragma unroll
                 for (int j = 0; j < 32; ++j) r[j] = acc[c0 + j] + __uint_as_float(v[j]);
-                if (MODE == MODE_FWD) {
+                if (MODE == MODE_STYLE) {
+                    if (seed != nullptr) {                                 // accumulate into an existing gradient seed
+#pragma unroll
+                        for (int j = 0; j < 32; j += 4) {
+                            const float4 sd = *reinterpret_cast<const float4*>(seed + rowoff + c0 + j);
+                            r[j] += sd.x; r[j + 1] += sd.y; r[j + 2] += sd.z; r[j + 3] += sd.w;
+                        }
+                    }
+                } else if (MODE == MODE_FWD) {
 #pragma unroll
                     for (int j = 0; j < 32; j += 4) {
                         const float4 b = __ldg(reinterpret_cast<const float4*>(bias + n0 + c0 + j));
@@ -335,7 +386,8 @@ bool conv_tc_eligible(int Cin, int Cout) { return Cin % TC_BK == 0 && (Cout == 6
 
 template <int BN, int MODE>
 static int launch_tc(const CUtensorMap& tmA, const CUtensorMap& tmBhi, const CUtensorMap& tmBlo, const float* bias, float* Y,
-                     const float* seed, const float* mask, int H, int W, int Cin, int Cout, cudaStream_t st) {
+                     const float* seed, const float* mask, int H, int W, int Cin, int Cout, cudaStream_t st,
+                     const float* cls_masks = nullptr, int num_cls = 0) {
     using Cfg = TcCfg<BN>;
     auto kern = conv3x3_tc_kernel<BN, MODE>;
     static bool configured = false;
@@ -345,7 +397,8 @@ static int launch_tc(const CUtensorMap& tmA, const CUtensorMap& tmBhi, const CUt
     }
     const int tw = (W + TC_TW - 1) / TC_TW, th = (H + TC_TH - 1) / TC_TH;
     dim3 grid(tw * th, Cout / BN);
-    kern<<<grid, TC_THREADS, Cfg::SMEM_BYTES, st>>>(tmA, tmBhi, tmBlo, bias, Y, seed, mask, H, W, Cin, Cout, tw);
+    kern<<<grid, TC_THREADS, Cfg::SMEM_BYTES, st>>>(tmA, tmBhi, tmBlo, bias, Y, seed, mask, H, W, Cin, Cout, tw, cls_masks,
+                                                    num_cls);
     ADPST_LAUNCH_CHECK();
     return ADPST_OK;
 }
@@ -370,6 +423,36 @@ int launch_conv_tc(adpst_vgg* h, int i, int gradient, const float* X, float* Y, 
     }
     if (BN == 128) return launch_tc<128, MODE_BWD>(tmA, bh, bl, bias, Y, seed, mask, H, W, Cin, Cout, st);
     return launch_tc<64, MODE_BWD>(tmA, bh, bl, bias, Y, seed, mask, H, W, Cin, Cout, st);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// style gradient (components/loss.py:104-137, backward):  dF[px,:] (=|+=) sum_k m_k[px]^2 F[px,:] D_k
+// The same kernel with the classes in the role of the filter taps: A = F tile scaled per pixel by m_k^2 in the transform
+// warps, B = D_k (symmetric, so K-major == MN-major).  Classes whose mask vanishes on the whole 8x16 pixel tile are
+// skipped (exact).
+// ---------------------------------------------------------------------------------------------------------------
+bool style_tc_eligible(int C) { return C == 64 || C % 128 == 0; }
+
+int launch_style_dF_tc(const float* F, int H, int W, int C, const float* masks, int K, const float* D_hi, const float* D_lo,
+                       float* dF, int accumulate, cudaStream_t st) {
+    ADPST_REQUIRE(K >= 1 && K <= TC_MAX_CLASSES, "style gradient: K=%d classes not supported (max %d)", K, TC_MAX_CLASSES);
+    CUtensorMap tmA, tmH, tmL;
+    const uint64_t dims[4] = {uint64_t(C), uint64_t(W), uint64_t(H), 1};
+    const uint64_t strides[3] = {uint64_t(C) * 4, uint64_t(W) * C * 4, uint64_t(H) * W * C * 4};
+    const uint32_t box[4] = {uint32_t(TC_BK), uint32_t(TC_TW), uint32_t(TC_TH), 1};
+    int rc = tc::make_tensor_map_f32(&tmA, F, 4, dims, strides, box);
+    if (rc != ADPST_OK) return rc;
+    const int BN = C >= 128 ? 128 : C;
+    const uint64_t ddims[2] = {uint64_t(C), uint64_t(K) * C};
+    const uint64_t dstr[1] = {uint64_t(C) * 4};
+    const uint32_t dbox[2] = {uint32_t(TC_BK), uint32_t(BN)};
+    rc = tc::make_tensor_map_f32(&tmH, D_hi, 2, ddims, dstr, dbox);
+    if (rc != ADPST_OK) return rc;
+    rc = tc::make_tensor_map_f32(&tmL, D_lo, 2, ddims, dstr, dbox);
+    if (rc != ADPST_OK) return rc;
+    const float* seed = accumulate ? dF : nullptr;
+    if (BN == 128) return launch_tc<128, MODE_STYLE>(tmA, tmH, tmL, nullptr, dF, seed, nullptr, H, W, C, C, st, masks, K);
+    return launch_tc<64, MODE_STYLE>(tmA, tmH, tmL, nullptr, dF, seed, nullptr, H, W, C, C, st, masks, K);
 }
 
 }  // namespace adpst

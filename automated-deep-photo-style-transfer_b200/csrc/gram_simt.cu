@@ -9,7 +9,8 @@
 //   forward : G_k[c1,c2] = sum_px m_k[px]^2 F[px,c1] F[px,c2]   (upper-triangular 64x64 tiles, split over pixels,
 //             partials reduced in float64 in a fixed order -> deterministic)
 //   backward: D_k = 2 s / (C^4 HW^2) (G_k - A_k);   dF[px,:] = sum_k m_k[px]^2 F[px,:] D_k
-#include "common.cuh"
+#include "tc_common.cuh"
+#include "vgg.cuh"
 
 namespace adpst {
 
@@ -123,10 +124,15 @@ style_diff_kernel(const float* __restrict__ G, const float* __restrict__ A, floa
                   double loss_coef, double* __restrict__ loss) {
     __shared__ double red[32];
     double acc = 0.0;
+    // D | D_hi | D_lo: the float32 matrix for the CUDA-core kernel and its TF32 hi/lo split for the tensor-core kernel
     for (size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += size_t(gridDim.x) * blockDim.x) {
         const double d = double(G[i]) - double(A[i]);
         acc += d * d;
-        D[i] = float(coef * d);
+        const float v = float(coef * d);
+        const float h = tc::round_tf32(v);
+        D[i] = v;
+        D[n + i] = h;
+        D[2 * n + i] = tc::round_tf32(v - h);
     }
     acc = block_sum<double>(acc, red);
     if (threadIdx.x == 0 && loss) atomicAdd(loss, acc * loss_coef);
@@ -206,7 +212,7 @@ size_t adpst_gram_workspace_bytes(int HW, int C, int K) {
     using namespace adpst;
     if (HW <= 0 || C <= 0 || K <= 0) return 0;
     const size_t partials = size_t(K) * gram_splits(HW, C, K) * C * C * sizeof(float);
-    const size_t dmat = size_t(K) * C * C * sizeof(float);
+    const size_t dmat = size_t(3) * K * C * C * sizeof(float);     // D, D_hi, D_lo
     return partials > dmat ? partials : dmat;
 }
 
@@ -230,12 +236,13 @@ int adpst_gram_masked(const float* F_dev, int HW, int C, const float* masks_dev,
     return ADPST_OK;
 }
 
-int adpst_style_layer_backward(const float* F_dev, int HW, int C, const float* masks_dev, int K, const float* G_dev,
+int adpst_style_layer_backward(const float* F_dev, int h, int w, int C, const float* masks_dev, int K, const float* G_dev,
                                const float* A_dev, double loss_scale, double grad_scale, double* loss_dev, float* dF_dev,
-                               int accumulate, void* workspace_dev, adpst_stream_t stream) {
+                               int accumulate, int path, void* workspace_dev, adpst_stream_t stream) {
     using namespace adpst;
     ADPST_REQUIRE(F_dev && G_dev && A_dev && workspace_dev, "style_layer_backward: NULL argument");
-    ADPST_REQUIRE(HW > 0 && K > 0, "style_layer_backward: empty input");
+    ADPST_REQUIRE(h > 0 && w > 0 && K > 0, "style_layer_backward: empty input");
+    const int HW = h * w;
     ADPST_REQUIRE(C > 0 && C % GT == 0, "style_layer_backward: C=%d must be a multiple of %d", C, GT);
     ADPST_REQUIRE(masks_dev || K == 1, "style_layer_backward: K=%d needs masks", K);
     cudaStream_t st = as_stream(stream);
@@ -248,6 +255,8 @@ int adpst_style_layer_backward(const float* F_dev, int HW, int C, const float* m
                                                                                                loss_coef, loss_dev);
     ADPST_LAUNCH_CHECK();
     if (dF_dev) {
+        if (path == CONV_PATH_TENSOR && style_tc_eligible(C) && K <= 32)
+            return launch_style_dF_tc(F_dev, h, w, C, masks_dev, K, D + n, D + 2 * n, dF_dev, accumulate, st);
         dim3 grid((HW + GT - 1) / GT, C / GT);
         style_dF_kernel<<<grid, GTHREADS, 0, st>>>(F_dev, masks_dev, D, dF_dev, HW, C, K, accumulate);
         ADPST_LAUNCH_CHECK();

@@ -11,7 +11,7 @@ constexpr int kNumConv = ADPST_VGG_NUM_CONV;
 __host__ __device__ constexpr int conv_cin(int i) { return i == 0 ? 3 : i <= 2 ? 64 : i <= 4 ? 128 : i <= 8 ? 256 : 512; }
 __host__ __device__ constexpr int conv_cout(int i) { return i <= 1 ? 64 : i <= 3 ? 128 : i <= 7 ? 256 : 512; }
 
-enum { MODE_FWD = 0, MODE_BWD = 1 };
+enum { MODE_FWD = 0, MODE_BWD = 1, MODE_STYLE = 2 };
 enum { CONV_PATH_TENSOR = 0, CONV_PATH_SIMT = 1 };
 
 }  // namespace adpst
@@ -36,4 +36,8 @@ bool conv_tc_eligible(int Cin, int Cout);
 int prepare_tc_weights(adpst_vgg* h, int i, cudaStream_t st);
 int launch_conv_tc(adpst_vgg* h, int i, int gradient, const float* X, float* Y, const float* seed, const float* mask, int H,
                    int W, int Cin, int Cout, cudaStream_t st);
+// style gradient on the tensor cores: dF[px,:] (=|+=) sum_k m_k[px]^2 F[px,:] D_k, D given as TF32 hi/lo splits (K,C,C)
+bool style_tc_eligible(int C);
+int launch_style_dF_tc(const float* F, int H, int W, int C, const float* masks, int K, const float* D_hi, const float* D_lo,
+                       float* dF, int accumulate, cudaStream_t st);
 }  // namespace adpst

@@ -85,14 +85,19 @@ def gram_masked(F, masks, K, workspace=None):
     return G
 
 
-def style_layer_backward(F, masks, K, G, A, loss_scale, grad_scale, loss_acc, dF, accumulate=False, workspace=None):
-    """One layer of loss.py:104-137: accumulates the loss value and writes/adds its gradient w.r.t. F."""
+def style_layer_backward(F, masks, K, G, A, loss_scale, grad_scale, loss_acc, dF, accumulate=False, workspace=None,
+                         path="tensor"):
+    """One layer of loss.py:104-137: accumulates the loss value and writes/adds its gradient w.r.t. F.
+    F: (h, w, C) feature map (a (HW, C) matrix is treated as h = HW, w = 1... use the 3-D form for 2-D tiling)."""
     _f32(F, "F"); _f32(G, "G"); _f32(A, "A")
-    HW, C = F.shape
-    ws = workspace if workspace is not None else gram_workspace(HW, C, K, F.device)
-    _lib.check(_lib.lib().adpst_style_layer_backward(_lib.ptr(F), HW, C, _lib.ptr(masks), K, _lib.ptr(G), _lib.ptr(A),
+    if F.dim() == 2:
+        F = F.reshape(F.shape[0], 1, F.shape[1])
+    h, w, C = F.shape
+    ws = workspace if workspace is not None else gram_workspace(h * w, C, K, F.device)
+    _lib.check(_lib.lib().adpst_style_layer_backward(_lib.ptr(F), h, w, C, _lib.ptr(masks), K, _lib.ptr(G), _lib.ptr(A),
                                                      float(loss_scale), float(grad_scale), _lib.ptr(loss_acc), _lib.ptr(dF),
-                                                     int(bool(accumulate)), _lib.ptr(ws), _lib.stream_ptr()))
+                                                     int(bool(accumulate)), {"tensor": 0, "simt": 1}[path], _lib.ptr(ws),
+                                                     _lib.stream_ptr()))
 
 
 def loss_finalize(acc, w_content, w_style, w_photo, out):

@@ -132,10 +132,12 @@ int adpst_gram_masked(const float* F_dev, int HW, int C, const float* masks_dev,
  *   *loss_dev += loss_scale * L                      (float64 accumulator, may be NULL)
  *   dF (=|+=)  grad_scale * dL/dF                     (written, or added if accumulate != 0; may be NULL)
  * G_dev is the transfer Gram from adpst_gram_masked on the same F / masks; A_dev the style Gram.
- * loss_scale carries the 1/len(args) of loss.py:85, grad_scale additionally the style weight. */
-int adpst_style_layer_backward(const float* F_dev, int HW, int C, const float* masks_dev, int K,
+ * loss_scale carries the 1/len(args) of loss.py:85, grad_scale additionally the style weight.
+ * F is the (h,w,C) feature map; path: 0 = tcgen05 3xTF32 kernel (8x16-pixel tiles, classes absent from a tile skipped),
+ * 1 = exact-float32 CUDA-core kernel (validation). */
+int adpst_style_layer_backward(const float* F_dev, int h, int w, int C, const float* masks_dev, int K,
                                const float* G_dev, const float* A_dev, double loss_scale, double grad_scale,
-                               double* loss_dev, float* dF_dev, int accumulate, void* workspace_dev,
+                               double* loss_dev, float* dF_dev, int accumulate, int path, void* workspace_dev,
                                adpst_stream_t stream);
 
 /* loss.py:90-92 with L = mean((target - output)^2):

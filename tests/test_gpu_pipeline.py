@@ -100,14 +100,19 @@ def test_vgg_backward_matches_autograd(H, W, weights, synth):
     assert _rel(g.cpu().numpy(), gr.numpy()) < TOL
 
 
-@pytest.mark.parametrize("HW,C,K", [(64 * 64, 64, 3), (1000, 128, 1), (777, 256, 4), (256, 512, 2)])
-def test_masked_gram_and_style_gradient(HW, C, K):
+@pytest.mark.parametrize("path", ["tensor", "simt"])
+@pytest.mark.parametrize("hw,C,K", [((64, 64), 64, 3), ((25, 40), 128, 1), ((21, 37), 256, 4), ((16, 16), 512, 2),
+                                    ((40, 48), 128, 8)])
+def test_masked_gram_and_style_gradient(hw, C, K, path):
     k = _m("kernels")
+    HW = hw[0] * hw[1]
     rng = np.random.default_rng(HW + C)
     F = (rng.random((HW, C)) * 50).astype(np.float32)
     S = (rng.random((HW // 2 + 3, C)) * 50).astype(np.float32)
     if K > 1:
         lab = rng.integers(0, K, HW)
+        if K == 8:                                             # blocky labels: some classes absent from whole tiles
+            lab = np.kron(rng.integers(0, K, (hw[0] // 8, hw[1] // 8)), np.ones((8, 8), dtype=np.int64)).reshape(-1)
         m = np.stack([(lab == i).astype(np.float32) for i in range(K)])
         soft = rng.random((K, HW)) < 0.05                       # some fractional boundary pixels
         m = np.where(soft, rng.random((K, HW)).astype(np.float32), m).astype(np.float32)
@@ -132,9 +137,12 @@ def test_masked_gram_and_style_gradient(HW, C, K):
     (gF,) = torch.autograd.grad(loss * 50.0, Ft)
     acc = torch.zeros(1, dtype=torch.float64, device="cuda")
     dF = torch.empty_like(Fd)
-    k.style_layer_backward(Fd, md, K, G, A, 0.5, 50.0, acc, dF)
-    assert abs(float(acc) - 0.5 * float(loss)) < TOL * 0.5 * float(loss)
+    k.style_layer_backward(Fd.reshape(hw[0], hw[1], C), md, K, G, A, 0.5, 50.0, acc, dF, path=path)
+    assert abs(float(acc) - 0.5 * float(loss.detach())) < TOL * 0.5 * float(loss.detach())
     assert _rel(dF.cpu().numpy(), gF.numpy()) < 5 * TOL     # G - A cancels digits: allow for float32 Gram rounding
+    dF2 = dF.clone()
+    k.style_layer_backward(Fd.reshape(hw[0], hw[1], C), md, K, G, A, 0.5, 50.0, acc, dF2, accumulate=True, path=path)
+    assert _rel(dF2.cpu().numpy(), 2 * gF.numpy()) < 5 * TOL
 
 
 def _setup(H, W, K, weights, synth, args, matting="v2", Hs=None, Ws=None):
