@@ -97,8 +97,11 @@ class Loss:
         else:
             K, cm, sm = 1, None, None                                                # loss.py:119-120
         ws = kernels.gram_workspace(max(h * w, hs * ws_), C, K, self.device)
-        A = kernels.gram_masked(target.reshape(hs * ws_, C), sm, K, ws)              # constant style Grams
-        st = {"shape": tuple(output.shape), "K": K, "masks": cm, "A": A, "ws": ws, "seed": torch.empty_like(output)}
+        A = kernels.gram_masked(target.reshape(hs, ws_, C), sm, K, ws,
+                                patches=kernels.gram_patch_lists(sm, hs, ws_, K, self.device))   # constant style Grams
+        st = {"shape": tuple(output.shape), "K": K, "masks": cm, "A": A, "ws": ws, "seed": torch.empty_like(output),
+              "patches": kernels.gram_patch_lists(cm, h, w, K, self.device),
+              "G": torch.empty(K, C, C, dtype=torch.float32, device=self.device)}
         self._layer_cache[name] = st
         return st
 
@@ -121,8 +124,7 @@ class Loss:
             out = style_output[name]
             st = self._style_layer_state(name, target, out)
             _, h, w, C = out.shape
-            F = out.reshape(h * w, C)
-            G = kernels.gram_masked(F, st["masks"], st["K"], st["ws"])
+            G = kernels.gram_masked(out.reshape(h, w, C), st["masks"], st["K"], st["ws"], patches=st["patches"], out=st["G"])
             shared = name in seeds                                            # a layer can be both content and style
             dF = seeds[name] if shared else st["seed"]
             kernels.style_layer_backward(out.reshape(h, w, C), st["masks"], st["K"], G, st["A"], 1.0 / n_args,
@@ -165,16 +167,16 @@ class Loss:
 
     @staticmethod
     def calculate_gram_matrix(convolution_layer, mask):                      # loss.py:96-102
-        C = convolution_layer.shape[3]
-        F = convolution_layer.reshape(-1, C).contiguous()
+        _, h, w, C = convolution_layer.shape
+        F = convolution_layer.reshape(h, w, C).contiguous()
         m = None if mask is None else mask.to(torch.float32).reshape(1, -1).contiguous()
-        return kernels.gram_masked(F, m, 1)[0]
+        return kernels.gram_masked(F, m, 1, patches=kernels.gram_patch_lists(m, h, w, 1, F.device))[0]
 
     def calculate_layer_style_loss(self, target, output):                    # loss.py:104-137
         st = self._style_layer_state("<adhoc %s>" % (tuple(output.shape),), target, output)
         _, h, w, C = output.shape
-        F = output.reshape(h * w, C).contiguous()
-        G = kernels.gram_masked(F, st["masks"], st["K"], st["ws"])
+        F = output.reshape(h, w, C).contiguous()
+        G = kernels.gram_masked(F, st["masks"], st["K"], st["ws"], patches=st["patches"])
         acc = torch.zeros(1, dtype=torch.float64, device=output.device)
         kernels.style_layer_backward(F, st["masks"], st["K"], G, st["A"], 1.0, 0.0, acc, None, workspace=st["ws"])
         return acc[0].to(output.dtype)

@@ -21,6 +21,13 @@ constexpr int GTHREADS = 256;
 static inline int gram_tiles(int C) { return (C + GT - 1) / GT; }
 static inline int gram_pairs(int C) { const int t = gram_tiles(C); return t * (t + 1) / 2; }
 
+// pixel splits of the tensor-core kernel: enough CTAs for ~2 per SM
+static inline int gram_splits_tc(int C, int K) {
+    const int t = gram_tc_tiles(C), ctas = t * (t + 1) / 2 * K;
+    const int s = (2 * num_sms() + ctas - 1) / ctas;
+    return s < 1 ? 1 : s;
+}
+
 static inline int gram_splits(int HW, int C, int K) {
     const int ctas = gram_pairs(C) * K;
     int s = (4 * num_sms() + ctas - 1) / ctas;
@@ -211,24 +218,36 @@ extern "C" {
 size_t adpst_gram_workspace_bytes(int HW, int C, int K) {
     using namespace adpst;
     if (HW <= 0 || C <= 0 || K <= 0) return 0;
-    const size_t partials = size_t(K) * gram_splits(HW, C, K) * C * C * sizeof(float);
+    int splits = gram_splits(HW, C, K);
+    if (gram_tc_eligible(C) && gram_splits_tc(C, K) > splits) splits = gram_splits_tc(C, K);
+    const size_t partials = size_t(K) * splits * C * C * sizeof(float);
     const size_t dmat = size_t(3) * K * C * C * sizeof(float);     // D, D_hi, D_lo
     return partials > dmat ? partials : dmat;
 }
 
-int adpst_gram_masked(const float* F_dev, int HW, int C, const float* masks_dev, int K, float* G_dev, void* workspace_dev,
-                      adpst_stream_t stream) {
+int adpst_gram_masked(const float* F_dev, int h, int w, int C, const float* masks_dev, int K, const int* patch_ids_dev,
+                      const int* patch_off_dev, float* G_dev, int path, void* workspace_dev, adpst_stream_t stream) {
     using namespace adpst;
     ADPST_REQUIRE(F_dev && G_dev && workspace_dev, "gram_masked: NULL argument");
-    ADPST_REQUIRE(HW > 0 && K > 0, "gram_masked: empty input");
+    ADPST_REQUIRE(h > 0 && w > 0 && K > 0, "gram_masked: empty input");
     ADPST_REQUIRE(C > 0 && C % GT == 0, "gram_masked: C=%d must be a multiple of %d", C, GT);
     ADPST_REQUIRE(masks_dev || K == 1, "gram_masked: K=%d needs masks", K);
     cudaStream_t st = as_stream(stream);
-    const int splits = gram_splits(HW, C, K), tiles = gram_tiles(C);
-    dim3 grid(gram_pairs(C), K * splits);
-    gram_partial_kernel<<<grid, GTHREADS, 0, st>>>(F_dev, masks_dev, static_cast<float*>(workspace_dev), HW, C, K, splits,
-                                                   tiles);
-    ADPST_LAUNCH_CHECK();
+    const int HW = h * w;
+    int splits;
+    if (path == CONV_PATH_TENSOR && patch_ids_dev && patch_off_dev && gram_tc_eligible(C)) {
+        splits = gram_splits_tc(C, K);
+        int rc = launch_gram_tc(F_dev, h, w, C, masks_dev, K, patch_ids_dev, patch_off_dev, static_cast<float*>(workspace_dev),
+                                splits, st);
+        if (rc != ADPST_OK) return rc;
+    } else {
+        splits = gram_splits(HW, C, K);
+        const int tiles = gram_tiles(C);
+        dim3 grid(gram_pairs(C), K * splits);
+        gram_partial_kernel<<<grid, GTHREADS, 0, st>>>(F_dev, masks_dev, static_cast<float*>(workspace_dev), HW, C, K, splits,
+                                                       tiles);
+        ADPST_LAUNCH_CHECK();
+    }
     const size_t total = size_t(K) * C * C;
     gram_reduce_kernel<<<unsigned((total + 255) / 256 < 4096 ? (total + 255) / 256 : 4096), 256, 0, st>>>(
         static_cast<const float*>(workspace_dev), G_dev, C, K, splits);

@@ -40,4 +40,9 @@ int launch_conv_tc(adpst_vgg* h, int i, int gradient, const float* X, float* Y, 
 bool style_tc_eligible(int C);
 int launch_style_dF_tc(const float* F, int H, int W, int C, const float* masks, int K, const float* D_hi, const float* D_lo,
                        float* dF, int accumulate, cudaStream_t st);
+// masked Gram partials on the tensor cores (gram_tc.cu)
+bool gram_tc_eligible(int C);
+int gram_tc_tiles(int C);
+int launch_gram_tc(const float* F, int H, int W, int C, const float* masks, int K, const int* patch_ids, const int* patch_off,
+                   float* ws, int splits, cudaStream_t st);
 }  // namespace adpst

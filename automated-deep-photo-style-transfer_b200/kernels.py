@@ -68,20 +68,46 @@ def gram_workspace(HW, C, K, device):
     return torch.empty(max(n, 16), dtype=torch.uint8, device=device)
 
 
-def gram_masked(F, masks, K, workspace=None):
-    """F: (HW,C) float32; masks: (K,HW) float32 or None.  Returns (K,C,C) float32  (loss.py:96-102)."""
+PATCH_H, PATCH_W = 2, 16        # pixel patch of one pipeline stage of the tensor-core Gram kernel (csrc/gram_tc.cu)
+
+
+def gram_patch_lists(masks, h, w, K, device):
+    """Patches (2 x 16 pixels, row-major patch index) on which each class mask is non-zero, grouped by class.
+    masks: (K, h*w) float32 or None.  Returns (patch_ids int32, patch_off int32[K+1]).  Host-side set-up (the masks
+    are constant over the optimisation), plain tensor plumbing."""
+    ph, pw = -(-h // PATCH_H), -(-w // PATCH_W)
+    if masks is None:
+        active = torch.ones(1, ph * pw, dtype=torch.bool, device=device)
+    else:
+        m = torch.zeros(K, ph * PATCH_H, pw * PATCH_W, dtype=torch.float32, device=device)
+        m[:, :h, :w] = masks.reshape(K, h, w)
+        active = (m.reshape(K, ph, PATCH_H, pw, PATCH_W) != 0).any(dim=4).any(dim=2).reshape(K, ph * pw)
+    ids = active.nonzero()[:, 1].to(torch.int32).contiguous()
+    off = torch.zeros(active.shape[0] + 1, dtype=torch.int32, device=device)
+    off[1:] = active.sum(1).cumsum(0).to(torch.int32)
+    if ids.numel() == 0:
+        ids = torch.zeros(1, dtype=torch.int32, device=device)
+    return ids, off
+
+
+def gram_masked(F, masks, K, workspace=None, patches=None, path="tensor", out=None):
+    """F: (h,w,C) float32 feature map ((HW,C) is taken as h = HW, w = 1); masks: (K,h*w) float32 or None.
+    Returns (K,C,C) float32  (loss.py:96-102).  `patches` = gram_patch_lists(...) enables the tcgen05 kernel."""
     _f32(F, "F")
-    HW, C = F.shape
+    if F.dim() == 2:
+        F = F.reshape(F.shape[0], 1, F.shape[1])
+    h, w, C = F.shape
     if masks is not None:
         _f32(masks, "masks")
-        if tuple(masks.shape) != (K, HW):
-            raise ValueError("masks must have shape (K, HW)")
+        if tuple(masks.shape) != (K, h * w):
+            raise ValueError("masks must have shape (K, h*w)")
     elif K != 1:
         raise ValueError("K must be 1 without masks")
-    ws = workspace if workspace is not None else gram_workspace(HW, C, K, F.device)
-    G = torch.empty(K, C, C, dtype=torch.float32, device=F.device)
-    _lib.check(_lib.lib().adpst_gram_masked(_lib.ptr(F), HW, C, _lib.ptr(masks), K, _lib.ptr(G), _lib.ptr(ws),
-                                            _lib.stream_ptr()))
+    ws = workspace if workspace is not None else gram_workspace(h * w, C, K, F.device)
+    G = out if out is not None else torch.empty(K, C, C, dtype=torch.float32, device=F.device)
+    ids, off = patches if patches is not None else (None, None)
+    _lib.check(_lib.lib().adpst_gram_masked(_lib.ptr(F), h, w, C, _lib.ptr(masks), K, _lib.ptr(ids), _lib.ptr(off), _lib.ptr(G),
+                                            {"tensor": 0, "simt": 1}[path], _lib.ptr(ws), _lib.stream_ptr()))
     return G
 
 

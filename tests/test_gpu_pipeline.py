@@ -121,8 +121,9 @@ def test_masked_gram_and_style_gradient(hw, C, K, path):
         m, ms = None, None
     Fd = torch.as_tensor(F).cuda()
     md = None if m is None else torch.as_tensor(m).cuda()
-    G = k.gram_masked(Fd, md, K)
-    A = k.gram_masked(torch.as_tensor(S).cuda(), None if ms is None else torch.as_tensor(ms).cuda(), K)
+    F3 = Fd.reshape(hw[0], hw[1], C)
+    G = k.gram_masked(F3, md, K, path=path, patches=k.gram_patch_lists(md, hw[0], hw[1], K, "cuda") if path == "tensor" else None)
+    A = k.gram_masked(torch.as_tensor(S).cuda(), None if ms is None else torch.as_tensor(ms).cuda(), K, path="simt")
     Ft = torch.as_tensor(F, dtype=torch.float64).requires_grad_(True)
     St = torch.as_tensor(S, dtype=torch.float64)
     loss = 0.0
