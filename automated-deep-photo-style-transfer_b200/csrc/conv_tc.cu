@@ -165,10 +165,9 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     if (warp == 0) {
         // ================= TMA producer =================
         if (lane == 0) {
+            int s = 0, round = 0, slot = 0, kc = 0;
             for (int it = 0; it < iters; ++it) {
-                const int s = it % STAGES, round = it / STAGES;
                 tc::mbar_wait(&empty[s], (round & 1) ^ 1);
-                const int slot = it / kchunks, kc = it - slot * kchunks;
                 const int tap = (MODE == MODE_STYLE) ? nth_set_bit(active, slot) : slot;
                 const int kh = (MODE == MODE_STYLE) ? 1 : tap / 3, kw = (MODE == MODE_STYLE) ? 1 : tap - (tap / 3) * 3;
                 uint8_t* st = smem + s * Cfg::STAGE_BYTES;
@@ -176,42 +175,47 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                 tc::tma_load_4d(st, &tmA, &full[s], kc * TC_BK, x0 + kw - 1, y0 + kh - 1, 0);
                 tc::tma_load_2d(st + 2 * TC_A_BYTES, &tmBhi, &full[s], kc * TC_BK, tap * Cout + n0);
                 tc::tma_load_2d(st + 2 * TC_A_BYTES + Cfg::B_BYTES, &tmBlo, &full[s], kc * TC_BK, tap * Cout + n0);
+                if (++s == STAGES) { s = 0; ++round; }
+                if (++kc == kchunks) { kc = 0; ++slot; }
             }
         }
     } else if (warp == 1) {
         // ================= MMA issuer =================
-        if (lane == 0) {
-            constexpr uint32_t idesc = tc::umma_idesc_tf32(TC_BM, BN);
-            for (int it = 0; it < iters; ++it) {
-                const int s = it % STAGES, round = it / STAGES;
-                const int c = it / TC_CHUNK_ITERS, cpos = it - c * TC_CHUNK_ITERS;
-                const uint32_t tmem_big = tmem_base + uint32_t(c & 1) * BN;
-                if (cpos == 0) {                                          // TMEM buffer must have been drained
-                    tc::mbar_wait(&chunk_empty[c & 1], ((c >> 1) & 1) ^ 1);
-                    tc::tcgen05_fence_after();
-                }
-                tc::mbar_wait(&full[s], round & 1);                       // B operands (TMA) ...
-                tc::mbar_wait(&ready[s], round & 1);                      // ... and the A hi/lo split (transform warps)
-                tc::tcgen05_fence_after();
-                const uint32_t a_hi = tc::smem_u32(smem + s * Cfg::STAGE_BYTES);
-                const uint32_t a_lo = a_hi + TC_A_BYTES;
-                const uint32_t b_hi = a_hi + 2 * TC_A_BYTES;
-                const uint32_t b_lo = b_hi + Cfg::B_BYTES;
+        // The whole warp runs the loop (warp-uniform control flow, descriptors live in uniform registers); one elected
+        // lane issues.  Descriptors are built once: per stage and K-step only the 14-bit address field changes.
+        constexpr uint32_t idesc = tc::umma_idesc_tf32(TC_BM, BN);
+        const uint32_t stage0 = tc::smem_u32(smem);
+        const uint64_t d_ahi = tc::umma_desc_kmajor_sw128(stage0, 1024);
+        const uint64_t d_alo = tc::umma_desc_kmajor_sw128(stage0 + TC_A_BYTES, 1024);
+        const uint64_t d_bhi = tc::umma_desc_kmajor_sw128(stage0 + 2 * TC_A_BYTES, 1024);
+        const uint64_t d_blo = tc::umma_desc_kmajor_sw128(stage0 + 2 * TC_A_BYTES + Cfg::B_BYTES, 1024);
+        int s = 0, round = 0;
+        for (int it = 0; it < iters; ++it) {
+            const int c = it / TC_CHUNK_ITERS, cpos = it - c * TC_CHUNK_ITERS;
+            const uint32_t tmem_big = tmem_base + uint32_t(c & 1) * BN;
+            if (cpos == 0) {                                          // TMEM buffer must have been drained
+                tc::mbar_wait(&chunk_empty[c & 1], ((c >> 1) & 1) ^ 1);
+            }
+            tc::mbar_wait(&full[s], round & 1);                       // B operands (TMA) ...
+            tc::mbar_wait(&ready[s], round & 1);                      // ... and the A hi/lo split (transform warps)
+            tc::tcgen05_fence_after();
+            const uint64_t soff = uint64_t(uint32_t(s) * uint32_t(Cfg::STAGE_BYTES >> 4));
+            if (tc::elect_one_sync()) {
 #pragma unroll
-                for (int k = 0; k < TC_BK / 8; ++k) {                     // UMMA K = 8 for tf32 = 32 bytes along the row
-                    const uint64_t dah = tc::umma_desc_kmajor_sw128(a_hi + k * 32, 1024);
-                    const uint64_t dal = tc::umma_desc_kmajor_sw128(a_lo + k * 32, 1024);
-                    const uint64_t dbh = tc::umma_desc_kmajor_sw128(b_hi + k * 32, 1024);
-                    const uint64_t dbl = tc::umma_desc_kmajor_sw128(b_lo + k * 32, 1024);
-                    tc::umma_tf32(tmem_small, dal, dbh, idesc, (it | k) != 0);
-                    tc::umma_tf32(tmem_small, dah, dbl, idesc, 1);
-                    tc::umma_tf32(tmem_big, dah, dbh, idesc, (cpos | k) != 0);
+                for (int k = 0; k < TC_BK / 8; ++k) {                 // UMMA K = 8 for tf32 = 32 bytes along the row
+                    const uint64_t koff = soff + uint64_t(k * 2);     // (k * 32 bytes) >> 4
+                    tc::umma_tf32(tmem_small, d_alo + koff, d_bhi + koff, idesc, (it | k) != 0);
+                    tc::umma_tf32(tmem_small, d_ahi + koff, d_blo + koff, idesc, 1);
+                    tc::umma_tf32(tmem_big, d_ahi + koff, d_bhi + koff, idesc, (cpos | k) != 0);
                 }
                 tc::umma_commit(&empty[s]);
                 if (cpos == TC_CHUNK_ITERS - 1 || it == iters - 1) tc::umma_commit(&chunk_full[c & 1]);
             }
-            if (iters > 0) tc::umma_commit(small_full);
+            __syncwarp();
+            if (++s == STAGES) { s = 0; ++round; }
         }
+        if (iters > 0 && tc::elect_one_sync()) tc::umma_commit(small_full);
+        __syncwarp();
     } else if (warp < 6) {
         // ================= operand transform =================
         const int t = threadIdx.x - 64;                               // 0..127

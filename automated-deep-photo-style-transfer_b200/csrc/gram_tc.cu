@@ -113,39 +113,38 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap tmF, const float* __restrict_
             }
         }
     } else if (warp == 1) {
-        // ================= MMA issuer =================
-        if (lane == 0) {
-            constexpr uint32_t idesc = tc::umma_idesc_tf32(128, BN);
-            for (int it = 0; it < iters; ++it) {
-                const int s = it % GM_STAGES, round = it / GM_STAGES;
-                const int c = it / GM_CHUNK_ITERS, cpos = it - c * GM_CHUNK_ITERS;
-                const uint32_t tmem_big = tmem_base + uint32_t(c & 1) * BN;
-                if (cpos == 0) {
-                    tc::mbar_wait(&chunk_empty[c & 1], ((c >> 1) & 1) ^ 1);
-                    tc::tcgen05_fence_after();
-                }
-                tc::mbar_wait(&full[s], round & 1);
-                tc::mbar_wait(&ready[s], round & 1);
-                tc::tcgen05_fence_after();
-                const uint32_t stg = tc::smem_u32(smem + s * Cfg::STAGE_BYTES);
-                const uint32_t a_hi = stg + Cfg::OFF_AHI, a_lo = stg + Cfg::OFF_ALO;
-                const uint32_t b_hi = diag ? a_hi : stg + Cfg::OFF_BHI;
-                const uint32_t b_lo = diag ? a_lo : stg + Cfg::OFF_BLO;
+        // ================= MMA issuer (warp-uniform loop, one elected lane issues; see conv_tc.cu) =================
+        constexpr uint32_t idesc = tc::umma_idesc_tf32(128, BN);
+        const uint32_t stage0 = tc::smem_u32(smem);
+        const uint64_t d_ahi = tc::umma_desc_kmajor_sw128(stage0 + Cfg::OFF_AHI, 1024);
+        const uint64_t d_alo = tc::umma_desc_kmajor_sw128(stage0 + Cfg::OFF_ALO, 1024);
+        const uint64_t d_bhi = diag ? d_ahi : tc::umma_desc_kmajor_sw128(stage0 + Cfg::OFF_BHI, 1024);
+        const uint64_t d_blo = diag ? d_alo : tc::umma_desc_kmajor_sw128(stage0 + Cfg::OFF_BLO, 1024);
+        int s = 0, round = 0;
+        for (int it = 0; it < iters; ++it) {
+            const int c = it / GM_CHUNK_ITERS, cpos = it - c * GM_CHUNK_ITERS;
+            const uint32_t tmem_big = tmem_base + uint32_t(c & 1) * BN;
+            if (cpos == 0) tc::mbar_wait(&chunk_empty[c & 1], ((c >> 1) & 1) ^ 1);
+            tc::mbar_wait(&full[s], round & 1);
+            tc::mbar_wait(&ready[s], round & 1);
+            tc::tcgen05_fence_after();
+            const uint64_t soff = uint64_t(uint32_t(s) * uint32_t(Cfg::STAGE_BYTES >> 4));
+            if (tc::elect_one_sync()) {
 #pragma unroll
                 for (int ks = 0; ks < GM_PX / 8; ++ks) {                  // 8 pixels per MMA = 32 bytes along the K-major row
-                    const uint64_t dah = tc::umma_desc_kmajor_sw128(a_hi + ks * 32, 1024);
-                    const uint64_t dal = tc::umma_desc_kmajor_sw128(a_lo + ks * 32, 1024);
-                    const uint64_t dbh = tc::umma_desc_kmajor_sw128(b_hi + ks * 32, 1024);
-                    const uint64_t dbl = tc::umma_desc_kmajor_sw128(b_lo + ks * 32, 1024);
-                    tc::umma_tf32(tmem_small, dal, dbh, idesc, (it | ks) != 0);
-                    tc::umma_tf32(tmem_small, dah, dbl, idesc, 1);
-                    tc::umma_tf32(tmem_big, dah, dbh, idesc, (cpos | ks) != 0);
+                    const uint64_t koff = soff + uint64_t(ks * 2);
+                    tc::umma_tf32(tmem_small, d_alo + koff, d_bhi + koff, idesc, (it | ks) != 0);
+                    tc::umma_tf32(tmem_small, d_ahi + koff, d_blo + koff, idesc, 1);
+                    tc::umma_tf32(tmem_big, d_ahi + koff, d_bhi + koff, idesc, (cpos | ks) != 0);
                 }
                 tc::umma_commit(&empty[s]);
                 if (cpos == GM_CHUNK_ITERS - 1 || it == iters - 1) tc::umma_commit(&chunk_full[c & 1]);
             }
-            if (iters > 0) tc::umma_commit(small_full);
+            __syncwarp();
+            if (++s == GM_STAGES) { s = 0; ++round; }
         }
+        if (iters > 0 && tc::elect_one_sync()) tc::umma_commit(small_full);
+        __syncwarp();
     } else if (warp < 6) {
         // ================= operand transform: X = m_k * F, split into TF32 hi / lo =================
         const int t = threadIdx.x - 64;                                 // 0..127

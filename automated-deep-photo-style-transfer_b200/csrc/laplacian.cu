@@ -232,6 +232,209 @@ lap_matvec_kernel(const TIO* __restrict__ img, const TIO* __restrict__ x, TIO* _
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// r = 1 fast path: "marching warp".  The tile kernel above spends its time in shared memory (108 LDS.64 per pixel to
+// gather the 9 windows of a pixel).  Here nothing goes through shared memory:
+//   * a warp owns a strip of 28 output columns; lane l holds image column c0 - 2 + l;
+//   * it marches down the rows keeping, in registers, a ring of the last three raw rows (own column and both
+//     neighbours, refreshed with 12 shuffles per row) and a ring of the last three rows of horizontally summed window
+//     coefficients (a_k: 9, b_k: 3);
+//   * per row step: load one row of I and x (36 B/px of HBM traffic in total, prefetched one row ahead), compute the
+//     window centred one row up from the 3x3 register patch, 3-sum its coefficients across lanes with shuffles, and
+//     emit the output row two rows up as cnt*x - (A^T I + B).
+// Lanes 0,1,30,31 and the first/last two rows of a strip are halo: 28/32 * RW/(RW+2) of the arithmetic is useful.
+// ---------------------------------------------------------------------------------------------
+constexpr int LM_COLS = 28;           // output columns per warp
+constexpr int LM_WARPS = 4;           // warps per CTA
+
+template <typename TC> __device__ __forceinline__ TC shfl_up1(TC v) { return __shfl_up_sync(0xffffffffu, v, 1); }
+template <typename TC> __device__ __forceinline__ TC shfl_dn1(TC v) { return __shfl_down_sync(0xffffffffu, v, 1); }
+
+template <typename TC>
+struct LapMarchState {
+    float rI[3][9], rX[3][9];        // [row slot][column (left, centre, right) * 3 + channel]
+    TC hc[3][12];                     // [row slot][a (9), b (3)] summed over the three window columns
+};
+
+// One row step.  S = ring slot of the incoming raw row (compile time, so the rings stay in registers).
+template <typename TC, int S>
+__device__ __forceinline__ void lap_march_step(LapMarchState<TC>& st, const float (&nI)[3], const float (&nX)[3], int ir, int r0,
+                                               int r_end, int gx, int lane, int H, int W, bool v2, TC eps, TC y_scale,
+                                               float* __restrict__ y, double& acc) {
+    constexpr int S1 = (S + 1) % 3, S2 = (S + 2) % 3;     // rows ir-2, ir-1 ; S holds row ir
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        st.rI[S][3 + c] = nI[c];
+        st.rX[S][3 + c] = nX[c];
+        st.rI[S][c] = shfl_up1(nI[c]);      st.rX[S][c] = shfl_up1(nX[c]);
+        st.rI[S][6 + c] = shfl_dn1(nI[c]);  st.rX[S][6 + c] = shfl_dn1(nX[c]);
+    }
+    if (ir < r0) return;                     // warp-uniform
+    // ---- window centred on (wr = ir - 1, gx): rows S1, S2, S of the ring
+    const int wr = ir - 1;
+    TC a[9], b[3];
+    {
+        const bool valid = (lane >= 1 && lane <= 30) && (v2 || (wr >= 1 && wr < H - 1 && gx >= 1 && gx < W - 1));
+        TC mu[3], pbar[3], M[6], Rc[9];
+        constexpr TC inv_n = TC(1) / TC(9);
+        TC s[3] = {0, 0, 0}, t[3] = {0, 0, 0};
+#pragma unroll
+        for (int i = 0; i < 6; ++i) M[i] = 0;
+#pragma unroll
+        for (int i = 0; i < 9; ++i) Rc[i] = 0;
+        if constexpr (std::is_same<TC, double>::value) {
+#pragma unroll
+            for (int rr = 0; rr < 3; ++rr) {
+                const float* pi = rr == 0 ? st.rI[S1] : rr == 1 ? st.rI[S2] : st.rI[S];
+                const float* px = rr == 0 ? st.rX[S1] : rr == 1 ? st.rX[S2] : st.rX[S];
+#pragma unroll
+                for (int cc = 0; cc < 3; ++cc) {
+                    const TC i0 = pi[cc * 3], i1 = pi[cc * 3 + 1], i2 = pi[cc * 3 + 2];
+                    const TC x0 = px[cc * 3], x1 = px[cc * 3 + 1], x2 = px[cc * 3 + 2];
+                    s[0] += i0; s[1] += i1; s[2] += i2;
+                    t[0] += x0; t[1] += x1; t[2] += x2;
+                    M[0] += i0 * i0; M[1] += i0 * i1; M[2] += i0 * i2;
+                    M[3] += i1 * i1; M[4] += i1 * i2; M[5] += i2 * i2;
+                    Rc[0] += i0 * x0; Rc[1] += i0 * x1; Rc[2] += i0 * x2;
+                    Rc[3] += i1 * x0; Rc[4] += i1 * x1; Rc[5] += i1 * x2;
+                    Rc[6] += i2 * x0; Rc[7] += i2 * x1; Rc[8] += i2 * x2;
+                }
+            }
+#pragma unroll
+            for (int c = 0; c < 3; ++c) { mu[c] = s[c] * inv_n; pbar[c] = t[c] * inv_n; }
+            M[0] -= s[0] * mu[0]; M[1] -= s[0] * mu[1]; M[2] -= s[0] * mu[2];
+            M[3] -= s[1] * mu[1]; M[4] -= s[1] * mu[2]; M[5] -= s[2] * mu[2];
+#pragma unroll
+            for (int j = 0; j < 3; ++j)
+#pragma unroll
+                for (int c = 0; c < 3; ++c) Rc[j * 3 + c] -= s[j] * pbar[c];
+        } else {
+#pragma unroll
+            for (int rr = 0; rr < 3; ++rr) {
+                const float* pi = rr == 0 ? st.rI[S1] : rr == 1 ? st.rI[S2] : st.rI[S];
+                const float* px = rr == 0 ? st.rX[S1] : rr == 1 ? st.rX[S2] : st.rX[S];
+#pragma unroll
+                for (int k = 0; k < 9; ++k) { s[k % 3] += pi[k]; t[k % 3] += px[k]; }
+            }
+#pragma unroll
+            for (int c = 0; c < 3; ++c) { mu[c] = s[c] * inv_n; pbar[c] = t[c] * inv_n; }
+#pragma unroll
+            for (int rr = 0; rr < 3; ++rr) {
+                const float* pi = rr == 0 ? st.rI[S1] : rr == 1 ? st.rI[S2] : st.rI[S];
+                const float* px = rr == 0 ? st.rX[S1] : rr == 1 ? st.rX[S2] : st.rX[S];
+#pragma unroll
+                for (int cc = 0; cc < 3; ++cc) {
+                    const TC i0 = pi[cc * 3] - mu[0], i1 = pi[cc * 3 + 1] - mu[1], i2 = pi[cc * 3 + 2] - mu[2];
+                    const TC x0 = px[cc * 3] - pbar[0], x1 = px[cc * 3 + 1] - pbar[1], x2 = px[cc * 3 + 2] - pbar[2];
+                    M[0] += i0 * i0; M[1] += i0 * i1; M[2] += i0 * i2;
+                    M[3] += i1 * i1; M[4] += i1 * i2; M[5] += i2 * i2;
+                    Rc[0] += i0 * x0; Rc[1] += i0 * x1; Rc[2] += i0 * x2;
+                    Rc[3] += i1 * x0; Rc[4] += i1 * x1; Rc[5] += i1 * x2;
+                    Rc[6] += i2 * x0; Rc[7] += i2 * x1; Rc[8] += i2 * x2;
+                }
+            }
+        }
+        M[0] += eps; M[3] += eps; M[5] += eps;
+        TC Mi[6];
+        sym3_inverse(M, Mi);
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            a[c] = Mi[0] * Rc[c] + Mi[1] * Rc[3 + c] + Mi[2] * Rc[6 + c];
+            a[3 + c] = Mi[1] * Rc[c] + Mi[3] * Rc[3 + c] + Mi[4] * Rc[6 + c];
+            a[6 + c] = Mi[2] * Rc[c] + Mi[4] * Rc[3 + c] + Mi[5] * Rc[6 + c];
+            b[c] = pbar[c] - (a[c] * mu[0] + a[3 + c] * mu[1] + a[6 + c] * mu[2]);
+        }
+        if (!valid) {
+#pragma unroll
+            for (int i = 0; i < 9; ++i) a[i] = 0;
+            b[0] = b[1] = b[2] = 0;
+        }
+    }
+    // ---- sum the coefficients of the three window columns (lanes l-1, l, l+1) into ring slot S1 (oldest, now free)
+#pragma unroll
+    for (int i = 0; i < 9; ++i) st.hc[S1][i] = a[i] + shfl_up1(a[i]) + shfl_dn1(a[i]);
+#pragma unroll
+    for (int c = 0; c < 3; ++c) st.hc[S1][9 + c] = b[c] + shfl_up1(b[c]) + shfl_dn1(b[c]);
+    if (ir < r0 + 2) return;                 // warp-uniform
+    // ---- output row orow = ir - 2: window rows orow-1, orow, orow+1 = the three ring slots
+    const int orow = ir - 2;
+    if (lane >= 2 && lane <= 29 && gx < W && orow < H && orow < r_end) {
+        TC cnt = TC(9);
+        if (!v2) {
+            const int ylo = max(orow - 1, 1), yhi = min(orow + 1, H - 2);
+            const int xlo = max(gx - 1, 1), xhi = min(gx + 1, W - 2);
+            cnt = TC(max(yhi - ylo + 1, 0) * max(xhi - xlo + 1, 0));
+        }
+        const TC i0 = st.rI[S1][3], i1 = st.rI[S1][4], i2 = st.rI[S1][5];     // raw row ir-2, own column
+        const size_t g = (size_t(orow) * W + gx) * 3;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            const TC A0 = st.hc[0][c] + st.hc[1][c] + st.hc[2][c];
+            const TC A1 = st.hc[0][3 + c] + st.hc[1][3 + c] + st.hc[2][3 + c];
+            const TC A2 = st.hc[0][6 + c] + st.hc[1][6 + c] + st.hc[2][6 + c];
+            const TC B = st.hc[0][9 + c] + st.hc[1][9 + c] + st.hc[2][9 + c];
+            const TC xc = st.rX[S1][3 + c];
+            const TC yc = cnt * xc - (A0 * i0 + A1 * i1 + A2 * i2 + B);
+            acc += double(xc) * double(yc);
+            if (y != nullptr) y[g + c] = float(y_scale * yc);
+        }
+    }
+}
+
+template <typename TC>
+__global__ void __launch_bounds__(LM_WARPS * 32)
+lap_march_kernel(const float* __restrict__ img, const float* __restrict__ x, float* __restrict__ y, double* __restrict__ partial,
+                 int H, int W, int mode, TC eps, TC y_scale, int RW, int strips_x, int total_warps) {
+    __shared__ double sRed[32];
+    const int lane = threadIdx.x & 31;
+    const int gw = blockIdx.x * LM_WARPS + (threadIdx.x >> 5);
+    double acc = 0.0;
+    if (gw < total_warps) {                                    // warp-uniform
+        const int sy = gw / strips_x, sx = gw - sy * strips_x;
+        const int c0 = sx * LM_COLS, r0 = sy * RW, r_end = min(r0 + RW, H);
+        const int gx = c0 - 2 + lane;
+        const bool v2 = (mode == ADPST_LAP_V2);
+        const int mx = v2 ? reflect_symmetric(gx, W) : gx;
+        const bool col_ok = v2 || (gx >= 0 && gx < W);
+        LapMarchState<TC> st;
+#pragma unroll
+        for (int i = 0; i < 3; ++i)
+#pragma unroll
+            for (int j = 0; j < 12; ++j) st.hc[i][j] = 0;
+        auto load_row = [&](int ir, float (&vI)[3], float (&vX)[3]) {
+            int my = ir;
+            bool ok = col_ok;
+            if (v2) my = reflect_symmetric(ir, H);
+            else ok = ok && ir >= 0 && ir < H;
+            vI[0] = vI[1] = vI[2] = vX[0] = vX[1] = vX[2] = 0.f;
+            if (ok) {
+                const size_t g = (size_t(my) * W + mx) * 3;
+                vI[0] = __ldg(img + g); vI[1] = __ldg(img + g + 1); vI[2] = __ldg(img + g + 2);
+                vX[0] = __ldg(x + g);   vX[1] = __ldg(x + g + 1);   vX[2] = __ldg(x + g + 2);
+            }
+        };
+        float cI[3], cX[3], nI[3], nX[3];
+        const int ir_begin = r0 - 2, ir_last = r_end + 1;         // inclusive
+        load_row(ir_begin, cI, cX);
+        for (int ir = ir_begin; ir <= ir_last; ir += 3) {
+            load_row(ir + 1, nI, nX);                               // prefetch one row ahead
+            lap_march_step<TC, 0>(st, cI, cX, ir, r0, r_end, gx, lane, H, W, v2, eps, y_scale, y, acc);
+            if (ir + 1 > ir_last) break;
+            load_row(ir + 2, cI, cX);
+            lap_march_step<TC, 1>(st, nI, nX, ir + 1, r0, r_end, gx, lane, H, W, v2, eps, y_scale, y, acc);
+            if (ir + 2 > ir_last) break;
+            load_row(ir + 3, nI, nX);
+            lap_march_step<TC, 2>(st, cI, cX, ir + 2, r0, r_end, gx, lane, H, W, v2, eps, y_scale, y, acc);
+#pragma unroll
+            for (int c = 0; c < 3; ++c) { cI[c] = nI[c]; cX[c] = nX[c]; }
+        }
+    }
+    if (partial != nullptr) {
+        const double tot = block_sum<double>(acc, sRed);
+        if (threadIdx.x == 0) partial[blockIdx.x] = tot;
+    }
+}
+
 __global__ void sum_partials_kernel(const double* __restrict__ partial, int n, double* __restrict__ out) {
     __shared__ double red[32];
     double a = 0.0;
@@ -356,12 +559,42 @@ struct adpst_laplacian {
     void* image = nullptr;       // (H,W,3) io_dtype, owned
     double* partials = nullptr;  // one per CTA, owned
     int npartials = 0;
+    bool force_tile_kernel = false;   // validation: use the shared-memory tile kernel for r = 1 as well
 };
 
 namespace adpst {
 
+// rows per marching warp: enough warps for ~2 waves of 8 warps per SM, at most 64 rows (halo overhead (RW+2)/RW)
+static inline int march_rows(int H, int W) {
+    const int strips = (W + LM_COLS - 1) / LM_COLS;
+    const int want = 16 * num_sms();
+    int rw = 64;
+    while (rw > 16 && strips * ((H + rw - 1) / rw) < want) rw /= 2;
+    return rw;
+}
+
+template <typename TC>
+static int launch_march(adpst_laplacian* h, const void* x, void* y, double y_scale, double* xLx, cudaStream_t st) {
+    const int RW = march_rows(h->H, h->W);
+    const int strips_x = (h->W + LM_COLS - 1) / LM_COLS, total = strips_x * ((h->H + RW - 1) / RW);
+    const int ctas = (total + LM_WARPS - 1) / LM_WARPS;
+    if (ctas > h->npartials) return fail(ADPST_ERR_INVALID, "laplacian: partial buffer too small (%d > %d)", ctas, h->npartials);
+    lap_march_kernel<TC><<<ctas, LM_WARPS * 32, 0, st>>>(static_cast<const float*>(h->image), static_cast<const float*>(x),
+                                                         static_cast<float*>(y), xLx ? h->partials : nullptr, h->H, h->W,
+                                                         h->mode, TC(h->eps), TC(y_scale), RW, strips_x, total);
+    ADPST_LAUNCH_CHECK();
+    if (xLx) {
+        sum_partials_kernel<<<1, 256, 0, st>>>(h->partials, ctas, xLx);
+        ADPST_LAUNCH_CHECK();
+    }
+    return ADPST_OK;
+}
+
 template <typename TIO, typename TC, int R>
 static int launch_matvec(adpst_laplacian* h, const void* x, void* y, double y_scale, double* xLx, cudaStream_t st) {
+    if constexpr (R == 1 && std::is_same<TIO, float>::value) {
+        if (!h->force_tile_kernel) return launch_march<TC>(h, x, y, y_scale, xLx, st);
+    }
     using T = LapTile<R>;
     auto kern = lap_matvec_kernel<TIO, TC, R>;
     const size_t smem = T::template smem_bytes<TIO, TC>();
@@ -463,7 +696,7 @@ int adpst_laplacian_create(int mode, int H, int W, int radius, double epsilon, c
     const size_t bytes = size_t(H) * W * 3 * (io_dtype == ADPST_F64 ? 8 : 4);
     cudaError_t e = cudaMalloc(&h->image, bytes);
     if (e == cudaSuccess) {
-        h->npartials = ((W + 31) / 32) * ((H + 15) / 16);
+        h->npartials = ((W + 31) / 32) * ((H + 15) / 16) + 64;
         e = cudaMalloc(reinterpret_cast<void**>(&h->partials), sizeof(double) * h->npartials);
     }
     if (e == cudaSuccess) e = cudaMemcpyAsync(h->image, image_dev, bytes, cudaMemcpyDeviceToDevice, as_stream(stream));

@@ -17,6 +17,14 @@ __device__ __forceinline__ float round_tf32(float x) {
     return __uint_as_float(u);
 }
 
+// One lane of the (converged) warp is elected; the predicate is known to be warp-uniform-single, which lets the compiler
+// keep UMMA descriptors in uniform registers instead of shuttling them per instruction.
+__device__ __forceinline__ bool elect_one_sync() {
+    uint32_t pred;
+    asm volatile("{ .reg .pred p; elect.sync _|p, 0xffffffff; selp.u32 %0, 1, 0, p; }" : "=r"(pred));
+    return pred != 0;
+}
+
 // ---- mbarrier ---------------------------------------------------------------------------------------------------
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
