@@ -15,14 +15,17 @@
 //   a_hi = a rounded to TF32 with cvt.rna (exactly representable, so the tensor core's own fp32->tf32 conversion -- a
 //          truncation, measured -- cannot change it),  a_lo = rna_tf32(a - a_hi)  (a - a_hi is exact in fp32).
 //          Rounding instead of masking keeps both splits unbiased; a biased split compounds over the 12 layers.
-//   b_hi / b_lo are split once when the weights are loaded; a_hi / a_lo are split in shared memory by the
-//   "transform" warps between the TMA landing and the MMA issue.
+//   b_hi / b_lo are split once when the weights are loaded; a_hi / a_lo are split by the "transform" warps between the
+//   TMA landing and the MMA issue and handed to the tensor core through TENSOR MEMORY (tcgen05.st; the MMA's A operand
+//   is a TMEM address), not shared memory.
 // The dropped a_lo*b_lo term and the tf32 rounding of the lo parts are O(2^-22) relative.
 //
 // Warp roles (320 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer (one elected lane),
 // warps 2..5 = operand transform (A hi/lo split), warps 6..9 = chunk promotion TMEM -> registers, then the epilogue
 // (bias/ReLU or seed/mask -> global).  mbarrier rings: full (TMA landed) -> ready (A split done) -> empty (MMAs retired),
 // chunk_full / chunk_empty for the two TMEM chunk buffers.
+#include <stdlib.h>
+
 #include "tc_common.cuh"
 #include "vgg.cuh"
 
@@ -49,9 +52,12 @@ int make_tensor_map_f32(CUtensorMap* out, const void* base, int rank, const uint
     cuuint32_t b[5], e[5];
     for (int i = 0; i < rank; ++i) { d[i] = dims[i]; b[i] = box[i]; e[i] = 1; }
     for (int i = 0; i + 1 < rank; ++i) s[i] = strides_bytes[i];
+    static int promo = -1;
+    if (promo < 0) { const char* ev = getenv("ADPST_TMA_PROMO"); promo = ev ? atoi(ev) : 2; }
+    const CUtensorMapL2promotion pr = promo == 0 ? CU_TENSOR_MAP_L2_PROMOTION_NONE : promo == 1 ? CU_TENSOR_MAP_L2_PROMOTION_L2_128B
+                                                                                                : CU_TENSOR_MAP_L2_PROMOTION_L2_256B;
     CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, cuuint32_t(rank), const_cast<void*>(base), d, s, b, e,
-                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, pr, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return fail(ADPST_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", int(r));
     return ADPST_OK;
 }
@@ -76,12 +82,13 @@ constexpr int TC_CHUNK_ITERS = 2;                                // stages per p
 constexpr int TC_MAX_CLASSES = 32;                               // style mode: classes per launch (active set is a bit mask)
 
 template <int BN> struct TcCfg {
-    static constexpr int STAGES = BN >= 128 ? 3 : 4;
+    static constexpr int STAGES = 4;
     static constexpr int B_BYTES = BN * TC_BK * 4;
-    static constexpr int STAGE_BYTES = 2 * TC_A_BYTES + 2 * B_BYTES;        // A (hi in place), A_lo, B_hi, B_lo
+    static constexpr int STAGE_BYTES = TC_A_BYTES + 2 * B_BYTES;            // A (raw, as landed), B_hi, B_lo
     static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*alignment slack*/ + 256 /*barriers*/ +
                                       TC_MAX_CLASSES * TC_BM * 4 /*per-pixel class weights (style mode)*/;
-    static constexpr uint32_t TMEM_COLS = 4 * BN;                           // big0 | big1 | small | (unused), power of two
+    // tensor memory columns: big0 | big1 | small | A operand slots (2 x (hi: 32 columns, lo: 32 columns))
+    static constexpr uint32_t COL_SMALL = 2 * BN, COL_A = 3 * BN, TMEM_COLS = 512;
 };
 
 // position of the n-th (0-based) set bit of m
@@ -95,20 +102,22 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
 conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmBhi,
                   const __grid_constant__ CUtensorMap tmBlo, const float* __restrict__ bias, float* __restrict__ Y,
                   const float* __restrict__ seed, const float* __restrict__ mask_src, int H, int W, int Cin, int Cout,
-                  int tiles_w, const float* __restrict__ cls_masks, int num_cls) {
+                  int tiles_w, const float* __restrict__ cls_masks, int num_cls, long long* __restrict__ dbg, int dbg_block) {
     using Cfg = TcCfg<BN>;
     constexpr int STAGES = Cfg::STAGES;
     static_assert(BN == 64 || BN == 128, "tile width");
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES);
-    uint64_t* full = bars;                      // [STAGES]  TMA bytes landed
+    uint64_t* full = bars;                      // [STAGES]  A tile landed (the transform warps start on it at once)
     uint64_t* ready = bars + STAGES;            // [STAGES]  A split into hi/lo
     uint64_t* empty = bars + 2 * STAGES;        // [STAGES]  MMAs that read the stage have retired
-    uint64_t* chunk_full = bars + 3 * STAGES;   // [2]       a big-term chunk is complete in TMEM buffer b
+    uint64_t* fullB = bars + 3 * STAGES;        // [STAGES]  (unused; kept so the barrier offsets stay put)
+    uint64_t* chunk_full = bars + 4 * STAGES;   // [2]       a big-term chunk is complete in TMEM buffer b
     uint64_t* chunk_empty = chunk_full + 2;     // [2]       the drain warps have consumed TMEM buffer b
     uint64_t* small_full = chunk_empty + 2;     // [1]       every MMA of the tile has retired
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(small_full + 1);
+    uint64_t* a_free = small_full + 1;          // [2]       the MMAs that read TMEM A slot j have retired
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(a_free + 2);
     float* cls_w = reinterpret_cast<float*>(bars + 32);                // [num_cls][128]  (style mode)
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -137,12 +146,16 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     }
     const int ntaps = __popc(active);
     const int iters = ntaps * kchunks;
-    const int nchunks = (iters + TC_CHUNK_ITERS - 1) / TC_CHUNK_ITERS;
+    constexpr int chunk_iters = TC_CHUNK_ITERS;
+    const int nchunks = (iters + chunk_iters - 1) / chunk_iters;
+    // timeline instrumentation (development): dbg[role * 4096 + it * 2 + {0,1}] = clock64 for one chosen CTA
+    const bool trace = dbg != nullptr && int(blockIdx.x) == dbg_block && blockIdx.y == 0;
+    if (trace && threadIdx.x == 0) dbg[4 * 4096] = clock64();
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < STAGES; ++s) {
             tc::mbar_init(&full[s], 1);
-            tc::mbar_init(&ready[s], 128);
+            tc::mbar_init(&ready[s], 128 + 1);      // 128 transform threads + the producer's expect_tx arrival (B bytes)
             tc::mbar_init(&empty[s], 1);
         }
         for (int b = 0; b < 2; ++b) {
@@ -150,6 +163,8 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             tc::mbar_init(&chunk_empty[b], 128);
         }
         tc::mbar_init(small_full, 1);
+        tc::mbar_init(&a_free[0], 1);
+        tc::mbar_init(&a_free[1], 1);
         tc::fence_barrier_init();
         tc::tma_prefetch_desc(&tmA);
         tc::tma_prefetch_desc(&tmBhi);
@@ -160,7 +175,8 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     __syncthreads();
     tc::tcgen05_fence_after();
     const uint32_t tmem_base = *tmem_slot;
-    const uint32_t tmem_small = tmem_base + 2 * BN;
+    const uint32_t tmem_small = tmem_base + Cfg::COL_SMALL;
+    const uint32_t tmem_a = tmem_base + Cfg::COL_A;
 
     if (warp == 0) {
         // ================= TMA producer =================
@@ -171,12 +187,13 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                 const int tap = (MODE == MODE_STYLE) ? nth_set_bit(active, slot) : slot;
                 const int kh = (MODE == MODE_STYLE) ? 1 : tap / 3, kw = (MODE == MODE_STYLE) ? 1 : tap - (tap / 3) * 3;
                 uint8_t* st = smem + s * Cfg::STAGE_BYTES;
-                tc::mbar_arrive_expect_tx(&full[s], TC_A_BYTES + 2 * Cfg::B_BYTES);
+                tc::mbar_arrive_expect_tx(&full[s], TC_A_BYTES);
                 tc::tma_load_4d(st, &tmA, &full[s], kc * TC_BK, x0 + kw - 1, y0 + kh - 1, 0);
-                tc::tma_load_2d(st + 2 * TC_A_BYTES, &tmBhi, &full[s], kc * TC_BK, tap * Cout + n0);
-                tc::tma_load_2d(st + 2 * TC_A_BYTES + Cfg::B_BYTES, &tmBlo, &full[s], kc * TC_BK, tap * Cout + n0);
+                tc::mbar_arrive_expect_tx(&ready[s], 2 * Cfg::B_BYTES);
+                tc::tma_load_2d(st + TC_A_BYTES, &tmBhi, &ready[s], kc * TC_BK, tap * Cout + n0);
+                tc::tma_load_2d(st + TC_A_BYTES + Cfg::B_BYTES, &tmBlo, &ready[s], kc * TC_BK, tap * Cout + n0);
                 if (++s == STAGES) { s = 0; ++round; }
-                if (++kc == kchunks) { kc = 0; ++slot; }
+                if (++kc == kchunks) { kc = 0; if (++slot == ntaps) slot = 0; }
             }
         }
     } else if (warp == 1) {
@@ -185,31 +202,32 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         // lane issues.  Descriptors are built once: per stage and K-step only the 14-bit address field changes.
         constexpr uint32_t idesc = tc::umma_idesc_tf32(TC_BM, BN);
         const uint32_t stage0 = tc::smem_u32(smem);
-        const uint64_t d_ahi = tc::umma_desc_kmajor_sw128(stage0, 1024);
-        const uint64_t d_alo = tc::umma_desc_kmajor_sw128(stage0 + TC_A_BYTES, 1024);
-        const uint64_t d_bhi = tc::umma_desc_kmajor_sw128(stage0 + 2 * TC_A_BYTES, 1024);
-        const uint64_t d_blo = tc::umma_desc_kmajor_sw128(stage0 + 2 * TC_A_BYTES + Cfg::B_BYTES, 1024);
+        const uint64_t d_bhi = tc::umma_desc_kmajor_sw128(stage0 + TC_A_BYTES, 1024);
+        const uint64_t d_blo = tc::umma_desc_kmajor_sw128(stage0 + TC_A_BYTES + Cfg::B_BYTES, 1024);
         int s = 0, round = 0;
         for (int it = 0; it < iters; ++it) {
-            const int c = it / TC_CHUNK_ITERS, cpos = it - c * TC_CHUNK_ITERS;
+            const int c = it / chunk_iters, cpos = it - c * chunk_iters;
             const uint32_t tmem_big = tmem_base + uint32_t(c & 1) * BN;
+            const uint32_t a_hi = tmem_a + uint32_t(it & 1) * 64, a_lo = a_hi + 32;
             if (cpos == 0) {                                          // TMEM buffer must have been drained
                 tc::mbar_wait(&chunk_empty[c & 1], ((c >> 1) & 1) ^ 1);
             }
-            tc::mbar_wait(&full[s], round & 1);                       // B operands (TMA) ...
-            tc::mbar_wait(&ready[s], round & 1);                      // ... and the A hi/lo split (transform warps)
+            // ONE wait per stage: ready[s] completes when the B tiles have landed (transaction bytes) and the 128 transform
+            // threads have stored A hi/lo into tensor memory.  Every poll here is time the tensor pipe may idle.
+            tc::mbar_wait(&ready[s], round & 1);
             tc::tcgen05_fence_after();
             const uint64_t soff = uint64_t(uint32_t(s) * uint32_t(Cfg::STAGE_BYTES >> 4));
             if (tc::elect_one_sync()) {
 #pragma unroll
-                for (int k = 0; k < TC_BK / 8; ++k) {                 // UMMA K = 8 for tf32 = 32 bytes along the row
+                for (int k = 0; k < TC_BK / 8; ++k) {                 // UMMA K = 8: 8 TMEM columns of A, 32 bytes of each B row
                     const uint64_t koff = soff + uint64_t(k * 2);     // (k * 32 bytes) >> 4
-                    tc::umma_tf32(tmem_small, d_alo + koff, d_bhi + koff, idesc, (it | k) != 0);
-                    tc::umma_tf32(tmem_small, d_ahi + koff, d_blo + koff, idesc, 1);
-                    tc::umma_tf32(tmem_big, d_ahi + koff, d_bhi + koff, idesc, (cpos | k) != 0);
+                    tc::umma_tf32_ts(tmem_small, a_lo + k * 8, d_bhi + koff, idesc, (it | k) != 0);
+                    tc::umma_tf32_ts(tmem_small, a_hi + k * 8, d_blo + koff, idesc, 1);
+                    tc::umma_tf32_ts(tmem_big, a_hi + k * 8, d_bhi + koff, idesc, (cpos | k) != 0);
                 }
                 tc::umma_commit(&empty[s]);
-                if (cpos == TC_CHUNK_ITERS - 1 || it == iters - 1) tc::umma_commit(&chunk_full[c & 1]);
+                tc::umma_commit(&a_free[it & 1]);
+                if (cpos == chunk_iters - 1 || it == iters - 1) tc::umma_commit(&chunk_full[c & 1]);
             }
             __syncwarp();
             if (++s == STAGES) { s = 0; ++round; }
@@ -218,33 +236,40 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         __syncwarp();
     } else if (warp < 6) {
         // ================= operand transform =================
-        const int t = threadIdx.x - 64;                               // 0..127
+        // Thread (warp w, lane l) owns row m = 32 (w & 3) + l of the A tile (= TMEM lane m).  It reads the row's 32 floats
+        // from the landed tile (undoing the 128-byte swizzle), splits them into TF32 hi / lo and stores both into tensor
+        // memory: the MMA then takes A from TMEM, which removes the A_lo round trip and all A operand reads from shared
+        // memory -- the kernel was shared-memory-bandwidth bound (measured: 192 KB of smem traffic per stage at 128 B/clk).
+        const int q = warp & 3;
+        const int m = q * 32 + lane;
+        const uint32_t lane_base = uint32_t(q * 32) << 16;
+        int s = 0, round = 0;
         for (int it = 0; it < iters; ++it) {
-            const int s = it % STAGES, round = it / STAGES;
             tc::mbar_wait(&full[s], round & 1);
-            float4* a = reinterpret_cast<float4*>(smem + s * Cfg::STAGE_BYTES);
-            float4* alo = reinterpret_cast<float4*>(smem + s * Cfg::STAGE_BYTES + TC_A_BYTES);
-            const float* wrow = nullptr;
-            if (MODE == MODE_STYLE) wrow = cls_w + nth_set_bit(active, it / kchunks) * TC_BM;
-            // elementwise, layout-agnostic: the swizzled position of an element is the same in both buffers
+            const uint8_t* arow = smem + s * Cfg::STAGE_BYTES + m * 128;
+            float wgt = 1.0f;
+            if (MODE == MODE_STYLE) wgt = cls_w[nth_set_bit(active, it / kchunks) * TC_BM + m];
+            uint32_t hi[32], lo[32];
 #pragma unroll
-            for (int j = 0; j < TC_A_BYTES / 16 / 128; ++j) {
-                const int idx = j * 128 + t;
-                float4 v = a[idx];
-                if (MODE == MODE_STYLE) {                 // the swizzle permutes 16-byte chunks within a 128-byte row only
-                    const float w = wrow[idx >> 3];
-                    v.x *= w; v.y *= w; v.z *= w; v.w *= w;
-                }
-                float4 h, l;
-                h.x = tc::round_tf32(v.x); l.x = tc::round_tf32(v.x - h.x);
-                h.y = tc::round_tf32(v.y); l.y = tc::round_tf32(v.y - h.y);
-                h.z = tc::round_tf32(v.z); l.z = tc::round_tf32(v.z - h.z);
-                h.w = tc::round_tf32(v.w); l.w = tc::round_tf32(v.w - h.w);
-                a[idx] = h;
-                alo[idx] = l;
+            for (int c = 0; c < 8; ++c) {
+                float4 v = *reinterpret_cast<const float4*>(arow + ((c ^ (m & 7)) << 4));
+                if (MODE == MODE_STYLE) { v.x *= wgt; v.y *= wgt; v.z *= wgt; v.w *= wgt; }
+                const float h0 = tc::round_tf32(v.x), h1 = tc::round_tf32(v.y), h2 = tc::round_tf32(v.z), h3 = tc::round_tf32(v.w);
+                hi[c * 4 + 0] = __float_as_uint(h0); lo[c * 4 + 0] = __float_as_uint(tc::round_tf32(v.x - h0));
+                hi[c * 4 + 1] = __float_as_uint(h1); lo[c * 4 + 1] = __float_as_uint(tc::round_tf32(v.y - h1));
+                hi[c * 4 + 2] = __float_as_uint(h2); lo[c * 4 + 2] = __float_as_uint(tc::round_tf32(v.z - h2));
+                hi[c * 4 + 3] = __float_as_uint(h3); lo[c * 4 + 3] = __float_as_uint(tc::round_tf32(v.w - h3));
             }
-            tc::fence_proxy_async_smem();          // generic-proxy writes -> visible to the tensor core (async proxy)
+            // the MMAs that read this TMEM slot two iterations ago must have retired
+            tc::mbar_wait(&a_free[it & 1], (((it >> 1) & 1) ^ 1));
+            tc::tcgen05_fence_after();
+            const uint32_t dst = tmem_a + uint32_t(it & 1) * 64 + lane_base;
+            tc::tmem_st_32x32(dst, hi);
+            tc::tmem_st_32x32(dst + 32, lo);
+            tc::tmem_st_wait();
+            tc::tcgen05_fence_before();
             tc::mbar_arrive(&ready[s]);
+            if (++s == STAGES) { s = 0; ++round; }
         }
     } else {
         // ================= drain (chunk promotion) + epilogue =================
@@ -330,6 +355,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         tc::tcgen05_fence_before();
     }
     __syncthreads();
+    if (trace && threadIdx.x == 0) dbg[4 * 4096 + 1] = clock64();
     if (warp == 1) {
         tc::tcgen05_fence_after();
         tc::tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
@@ -388,6 +414,10 @@ int prepare_tc_weights(adpst_vgg* h, int i, cudaStream_t st) {
 
 bool conv_tc_eligible(int Cin, int Cout) { return Cin % TC_BK == 0 && (Cout == 64 || Cout % 128 == 0); }
 
+static long long* g_trace_buf = nullptr;
+static int g_trace_block = -1;
+void conv_tc_set_trace(long long* buf, int block) { g_trace_buf = buf; g_trace_block = block; }
+
 template <int BN, int MODE>
 static int launch_tc(const CUtensorMap& tmA, const CUtensorMap& tmBhi, const CUtensorMap& tmBlo, const float* bias, float* Y,
                      const float* seed, const float* mask, int H, int W, int Cin, int Cout, cudaStream_t st,
@@ -402,7 +432,7 @@ static int launch_tc(const CUtensorMap& tmA, const CUtensorMap& tmBhi, const CUt
     const int tw = (W + TC_TW - 1) / TC_TW, th = (H + TC_TH - 1) / TC_TH;
     dim3 grid(tw * th, Cout / BN);
     kern<<<grid, TC_THREADS, Cfg::SMEM_BYTES, st>>>(tmA, tmBhi, tmBlo, bias, Y, seed, mask, H, W, Cin, Cout, tw, cls_masks,
-                                                    num_cls);
+                                                    num_cls, g_trace_buf, g_trace_block);
     ADPST_LAUNCH_CHECK();
     return ADPST_OK;
 }

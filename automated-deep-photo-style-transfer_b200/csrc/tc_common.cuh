@@ -10,11 +10,12 @@ namespace tc {
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
 
-// fp32 -> tf32 (10-bit mantissa) with round-to-nearest; the result is an fp32 whose 13 low mantissa bits are zero.
+// fp32 -> tf32 (10-bit mantissa), round to nearest with ties away from zero (what cvt.rna.tf32.f32 computes), done with
+// two integer instructions: conversion instructions issue at a fraction of the ALU rate and the operand-transform warps
+// perform 8 of these per float4.  The result is an fp32 whose 13 low mantissa bits are zero.  (Inf/NaN inputs are not
+// expected on this path; finite values within 2^-11 of FLT_MAX would round to Inf exactly as cvt.rna does.)
 __device__ __forceinline__ float round_tf32(float x) {
-    uint32_t u;
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
-    return __uint_as_float(u);
+    return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u);
 }
 
 // One lane of the (converged) warp is elected; the predicate is known to be warp-uniform-single, which lets the compiler
@@ -37,19 +38,24 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t by
     asm volatile("{ .reg .b64 st; mbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1; }" ::"r"(smem_u32(bar)), "r"(bytes)
                  : "memory");
 }
-// Bounded wait: a protocol bug traps (reported as a launch failure) instead of hanging the GPU.
+// Bounded wait: a protocol bug traps (reported as a launch failure) instead of hanging the GPU.  The first poll is
+// outside the timed loop: on the MMA-issuing thread every cycle spent here is a cycle the tensor pipe may idle.
+__device__ __forceinline__ bool mbar_try_wait(uint32_t addr, uint32_t parity) {
+    uint32_t done;
+    asm volatile(
+        "{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+        : "=r"(done)
+        : "r"(addr), "r"(parity)
+        : "memory");
+    return done != 0;
+}
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     const uint32_t addr = smem_u32(bar);
+    if (mbar_try_wait(addr, parity)) return;
     const long long t0 = clock64();
-    uint32_t done;
-    do {
-        asm volatile(
-            "{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
-            : "=r"(done)
-            : "r"(addr), "r"(parity)
-            : "memory");
-        if (!done && clock64() - t0 > 4000000000LL) __trap();
-    } while (!done);
+    while (!mbar_try_wait(addr, parity)) {
+        if (clock64() - t0 > 4000000000LL) __trap();
+    }
 }
 
 // ---- fences -----------------------------------------------------------------------------------------------------
@@ -98,6 +104,19 @@ __device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t (&v)[32])
         : "r"(taddr)
         : "memory");
 }
+// Store 32 consecutive 32-bit columns of this thread's TMEM lane (the mirror image of tmem_ld_32x32).
+__device__ __forceinline__ void tmem_st_32x32(uint32_t taddr, const uint32_t (&v)[32]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+        "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};" ::"r"(taddr),
+        "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]),
+        "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]), "r"(v[16]), "r"(v[17]), "r"(v[18]),
+        "r"(v[19]), "r"(v[20]), "r"(v[21]), "r"(v[22]), "r"(v[23]), "r"(v[24]), "r"(v[25]), "r"(v[26]), "r"(v[27]),
+        "r"(v[28]), "r"(v[29]), "r"(v[30]), "r"(v[31])
+        : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // ---- UMMA -------------------------------------------------------------------------------------------------------
@@ -122,6 +141,14 @@ __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint6
     asm volatile(
         "{ .reg .pred p; setp.ne.b32 p, %4, 0; tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p; }" ::"r"(tmem_d),
         "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// Same with the A operand in tensor memory (lane = row of A, 8 consecutive 32-bit columns = the K slice): no shared-memory
+// read for A.
+__device__ __forceinline__ void umma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{ .reg .pred p; setp.ne.b32 p, %4, 0; tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p; }" ::"r"(tmem_d),
+        "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate)
         : "memory");
 }
 // All previously issued MMAs of this thread arrive on `bar` when they retire (implies fence::before_thread_sync).

@@ -33,6 +33,7 @@ struct adpst_vgg {
 
 namespace adpst {
 bool conv_tc_eligible(int Cin, int Cout);
+void conv_tc_set_trace(long long* buf, int block);
 int prepare_tc_weights(adpst_vgg* h, int i, cudaStream_t st);
 int launch_conv_tc(adpst_vgg* h, int i, int gradient, const float* X, float* Y, const float* seed, const float* mask, int H,
                    int W, int Cin, int Cout, cudaStream_t st);

@@ -452,6 +452,12 @@ int adpst_vgg_set_conv_path(adpst_vgg* h, int path) {
     return ADPST_OK;
 }
 
+/* development: per-stage clock64 timeline of one CTA of the tensor-core conv kernel (buf: 5*4096 int64, NULL = off) */
+int adpst_debug_conv_trace(long long* buf_dev, int block) {
+    adpst::conv_tc_set_trace(buf_dev, block);
+    return ADPST_OK;
+}
+
 int adpst_vgg_conv_forward(adpst_vgg* h, int i, const float* x_dev, int lh, int lw, float* y_dev, adpst_stream_t stream) {
     using namespace adpst;
     ADPST_REQUIRE(h && x_dev && y_dev && i >= 0 && i < kNumConv && lh > 0 && lw > 0, "vgg_conv_forward: bad argument");

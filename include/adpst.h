@@ -101,6 +101,9 @@ int adpst_vgg_forward(adpst_vgg* h, const float* image_dev, int H, int W, float*
  * gradient to the image always use the CUDA-core kernels), 1 = exact-float32 CUDA-core kernels everywhere (validation). */
 int adpst_vgg_set_conv_path(adpst_vgg* h, int path);
 
+/* Development aid: clock64 timeline of one CTA of the tensor-core conv kernel (buf_dev: 5*4096 int64; NULL disables). */
+int adpst_debug_conv_trace(long long* buf_dev, int block);
+
 /* One layer in isolation (parity tests, per-kernel roofline in bench.py).
  * conv_forward: y = relu(conv_i(x) + b_i); for i == 0, x is the [0,1] RGB image (h,w,3).
  * conv_dgrad  : dx = conv_i^T(dpre) (i >= 1), no mask, no seed. */
