@@ -102,7 +102,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
 conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmBhi,
                   const __grid_constant__ CUtensorMap tmBlo, const float* __restrict__ bias, float* __restrict__ Y,
                   const float* __restrict__ seed, const float* __restrict__ mask_src, int H, int W, int Cin, int Cout,
-                  int tiles_w, const float* __restrict__ cls_masks, int num_cls, long long* __restrict__ dbg, int dbg_block) {
+                  int tiles_w, const float* __restrict__ cls_masks, int num_cls, long long* __restrict__ dbg, int dbg_block, int dbg_flags) {
     using Cfg = TcCfg<BN>;
     constexpr int STAGES = Cfg::STAGES;
     static_assert(BN == 64 || BN == 128, "tile width");
@@ -187,11 +187,17 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                 const int tap = (MODE == MODE_STYLE) ? nth_set_bit(active, slot) : slot;
                 const int kh = (MODE == MODE_STYLE) ? 1 : tap / 3, kw = (MODE == MODE_STYLE) ? 1 : tap - (tap / 3) * 3;
                 uint8_t* st = smem + s * Cfg::STAGE_BYTES;
-                tc::mbar_arrive_expect_tx(&full[s], TC_A_BYTES);
-                tc::tma_load_4d(st, &tmA, &full[s], kc * TC_BK, x0 + kw - 1, y0 + kh - 1, 0);
-                tc::mbar_arrive_expect_tx(&ready[s], 2 * Cfg::B_BYTES);
-                tc::tma_load_2d(st + TC_A_BYTES, &tmBhi, &ready[s], kc * TC_BK, tap * Cout + n0);
-                tc::tma_load_2d(st + TC_A_BYTES + Cfg::B_BYTES, &tmBlo, &ready[s], kc * TC_BK, tap * Cout + n0);
+                if (dbg_flags & 8) tc::mbar_arrive(&full[s]);
+                else {
+                    tc::mbar_arrive_expect_tx(&full[s], TC_A_BYTES);
+                    tc::tma_load_4d(st, &tmA, &full[s], kc * TC_BK, x0 + kw - 1, y0 + kh - 1, 0);
+                }
+                if (dbg_flags & 4) tc::mbar_arrive(&ready[s]);
+                else {
+                    tc::mbar_arrive_expect_tx(&ready[s], 2 * Cfg::B_BYTES);
+                    tc::tma_load_2d(st + TC_A_BYTES, &tmBhi, &ready[s], kc * TC_BK, tap * Cout + n0);
+                    tc::tma_load_2d(st + TC_A_BYTES + Cfg::B_BYTES, &tmBlo, &ready[s], kc * TC_BK, tap * Cout + n0);
+                }
                 if (++s == STAGES) { s = 0; ++round; }
                 if (++kc == kchunks) { kc = 0; if (++slot == ntaps) slot = 0; }
             }
@@ -214,7 +220,10 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             }
             // ONE wait per stage: ready[s] completes when the B tiles have landed (transaction bytes) and the 128 transform
             // threads have stored A hi/lo into tensor memory.  Every poll here is time the tensor pipe may idle.
+            long long tr0 = 0, tr1 = 0;
+            if (trace) tr0 = clock64();
             tc::mbar_wait(&ready[s], round & 1);
+            if (trace) tr1 = clock64();
             tc::tcgen05_fence_after();
             const uint64_t soff = uint64_t(uint32_t(s) * uint32_t(Cfg::STAGE_BYTES >> 4));
             if (tc::elect_one_sync()) {
@@ -230,6 +239,9 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                 if (cpos == chunk_iters - 1 || it == iters - 1) tc::umma_commit(&chunk_full[c & 1]);
             }
             __syncwarp();
+            if (trace && lane == 0 && it < 1000) {
+                dbg[2 * 4096 + it * 4] = tr0; dbg[2 * 4096 + it * 4 + 1] = tr1; dbg[2 * 4096 + it * 4 + 2] = clock64();
+            }
             if (++s == STAGES) { s = 0; ++round; }
         }
         if (iters > 0 && tc::elect_one_sync()) tc::umma_commit(small_full);
@@ -246,6 +258,12 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         int s = 0, round = 0;
         for (int it = 0; it < iters; ++it) {
             tc::mbar_wait(&full[s], round & 1);
+            if (dbg_flags & 2) {
+                tc::mbar_wait(&a_free[it & 1], (((it >> 1) & 1) ^ 1));
+                tc::mbar_arrive(&ready[s]);
+                if (++s == STAGES) { s = 0; ++round; }
+                continue;
+            }
             const uint8_t* arow = smem + s * Cfg::STAGE_BYTES + m * 128;
             float wgt = 1.0f;
             if (MODE == MODE_STYLE) wgt = cls_w[nth_set_bit(active, it / kchunks) * TC_BM + m];
@@ -284,6 +302,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             const uint32_t src = tmem_base + uint32_t(c & 1) * BN + lane_base;
 #pragma unroll
             for (int c0 = 0; c0 < BN; c0 += 32) {
+                if (dbg_flags & 1) break;
                 uint32_t v[32];
                 tc::tmem_ld_32x32(src + c0, v);
                 tc::tmem_ld_wait();
@@ -416,6 +435,9 @@ bool conv_tc_eligible(int Cin, int Cout) { return Cin % TC_BK == 0 && (Cout == 6
 
 static long long* g_trace_buf = nullptr;
 static int g_trace_block = -1;
+// timing experiments only (results are wrong when set): 1 = drain skips tcgen05.ld, 2 = transform skips its work,
+// 4 = producer skips the B loads, 8 = producer skips the A load
+static int g_dbg_flags = getenv("ADPST_TC_DBG") ? atoi(getenv("ADPST_TC_DBG")) : 0;
 void conv_tc_set_trace(long long* buf, int block) { g_trace_buf = buf; g_trace_block = block; }
 
 template <int BN, int MODE>
@@ -432,7 +454,7 @@ static int launch_tc(const CUtensorMap& tmA, const CUtensorMap& tmBhi, const CUt
     const int tw = (W + TC_TW - 1) / TC_TW, th = (H + TC_TH - 1) / TC_TH;
     dim3 grid(tw * th, Cout / BN);
     kern<<<grid, TC_THREADS, Cfg::SMEM_BYTES, st>>>(tmA, tmBhi, tmBlo, bias, Y, seed, mask, H, W, Cin, Cout, tw, cls_masks,
-                                                    num_cls, g_trace_buf, g_trace_block);
+                                                    num_cls, g_trace_buf, g_trace_block, g_dbg_flags);
     ADPST_LAUNCH_CHECK();
     return ADPST_OK;
 }

@@ -125,8 +125,7 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap tmF, const float* __restrict_
             const int c = it / GM_CHUNK_ITERS, cpos = it - c * GM_CHUNK_ITERS;
             const uint32_t tmem_big = tmem_base + uint32_t(c & 1) * BN;
             if (cpos == 0) tc::mbar_wait(&chunk_empty[c & 1], ((c >> 1) & 1) ^ 1);
-            tc::mbar_wait(&full[s], round & 1);
-            tc::mbar_wait(&ready[s], round & 1);
+            tc::mbar_wait(&ready[s], round & 1);      // the transform warps arrive only after the TMA tile landed
             tc::tcgen05_fence_after();
             const uint64_t soff = uint64_t(uint32_t(s) * uint32_t(Cfg::STAGE_BYTES >> 4));
             if (tc::elect_one_sync()) {

@@ -381,6 +381,172 @@ __device__ __forceinline__ void lap_march_step(LapMarchState<TC>& st, const floa
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// float64-arithmetic variant of the marching warp ("v2"): fewer float64 instructions and no float->double conversions
+// in the inner loop (both matter: the float64 pipe issues 64 lanes/clk/SM and F2F only 16).
+//   * each lane keeps only ITS OWN column of the last three raw rows, already converted to double at load time;
+//   * window moments are separable: lane k sums the 21 raw moments of its own column over the three rows (exact in
+//     float64: the inputs are float32) and the window sum is C[k-1] + C[k] + C[k+1], fetched with shuffles;
+//   * the 3-wide sum of the coefficients is replaced by "contributions": lane k evaluates V_k^T I_l + VB_k for the
+//     three pixels l = k-1, k, k+1 its window column touches (V = coefficients summed over the three window rows, in
+//     registers) and ships 3 numbers to each neighbour instead of receiving 12 from each.
+// ---------------------------------------------------------------------------------------------
+struct LapMarch2State {
+    double rI[3][3], rX[3][3];       // [row slot][channel], own column
+    double cf[3][12];                 // [window-row slot][a (9), b (3)], own window column
+};
+
+__device__ __forceinline__ double shfl_up1d(double v) { return __shfl_up_sync(0xffffffffu, v, 1); }
+__device__ __forceinline__ double shfl_dn1d(double v) { return __shfl_down_sync(0xffffffffu, v, 1); }
+
+template <int S>
+__device__ __forceinline__ void lap_march2_step(LapMarch2State& st, const float (&nI)[3], const float (&nX)[3], int ir, int r0,
+                                                int r_end, int gx, int lane, int H, int W, bool v2, double eps,
+                                                double y_scale, float* __restrict__ y, double& acc) {
+    constexpr int S1 = (S + 1) % 3;                       // slot of row ir-2 (S holds row ir)
+#pragma unroll
+    for (int c = 0; c < 3; ++c) { st.rI[S][c] = double(nI[c]); st.rX[S][c] = double(nX[c]); }
+    // ---- raw moments of this lane's column over rows ir-2..ir:  s(3) t(3) Q(6) R(9)
+    double cm[21];
+#pragma unroll
+    for (int i = 0; i < 21; ++i) cm[i] = 0.0;
+#pragma unroll
+    for (int rr = 0; rr < 3; ++rr) {
+        const double i0 = st.rI[rr][0], i1 = st.rI[rr][1], i2 = st.rI[rr][2];
+        const double x0 = st.rX[rr][0], x1 = st.rX[rr][1], x2 = st.rX[rr][2];
+        cm[0] += i0; cm[1] += i1; cm[2] += i2; cm[3] += x0; cm[4] += x1; cm[5] += x2;
+        cm[6] += i0 * i0; cm[7] += i0 * i1; cm[8] += i0 * i2; cm[9] += i1 * i1; cm[10] += i1 * i2; cm[11] += i2 * i2;
+        cm[12] += i0 * x0; cm[13] += i0 * x1; cm[14] += i0 * x2;
+        cm[15] += i1 * x0; cm[16] += i1 * x1; cm[17] += i1 * x2;
+        cm[18] += i2 * x0; cm[19] += i2 * x1; cm[20] += i2 * x2;
+    }
+    // ---- window (wr = ir - 1, column gx) = columns gx-1, gx, gx+1
+    double wm[21];
+#pragma unroll
+    for (int i = 0; i < 21; ++i) wm[i] = cm[i] + shfl_up1d(cm[i]) + shfl_dn1d(cm[i]);
+    const int wr = ir - 1;
+    const bool valid = (lane >= 1 && lane <= 30) && (v2 || (wr >= 1 && wr < H - 1 && gx >= 1 && gx < W - 1));
+    {
+        constexpr double inv_n = 1.0 / 9.0;
+        double mu[3], pbar[3], M[6], Rc[9], Mi[6];
+#pragma unroll
+        for (int c = 0; c < 3; ++c) { mu[c] = wm[c] * inv_n; pbar[c] = wm[3 + c] * inv_n; }
+        M[0] = wm[6] - wm[0] * mu[0] + eps; M[1] = wm[7] - wm[0] * mu[1]; M[2] = wm[8] - wm[0] * mu[2];
+        M[3] = wm[9] - wm[1] * mu[1] + eps; M[4] = wm[10] - wm[1] * mu[2]; M[5] = wm[11] - wm[2] * mu[2] + eps;
+#pragma unroll
+        for (int j = 0; j < 3; ++j)
+#pragma unroll
+            for (int c = 0; c < 3; ++c) Rc[j * 3 + c] = wm[12 + j * 3 + c] - wm[j] * pbar[c];
+        sym3_inverse(M, Mi);
+        double* a = st.cf[S1];                               // oldest window-row slot, free now
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            a[c] = Mi[0] * Rc[c] + Mi[1] * Rc[3 + c] + Mi[2] * Rc[6 + c];
+            a[3 + c] = Mi[1] * Rc[c] + Mi[3] * Rc[3 + c] + Mi[4] * Rc[6 + c];
+            a[6 + c] = Mi[2] * Rc[c] + Mi[4] * Rc[3 + c] + Mi[5] * Rc[6 + c];
+            a[9 + c] = pbar[c] - (a[c] * mu[0] + a[3 + c] * mu[1] + a[6 + c] * mu[2]);
+        }
+        if (!valid) {
+#pragma unroll
+            for (int i = 0; i < 12; ++i) a[i] = 0.0;
+        }
+    }
+    // ---- output row orow = ir - 2 (window rows orow-1 .. orow+1 are the three cf slots)
+    const int orow = ir - 2;
+    double V[12];
+#pragma unroll
+    for (int i = 0; i < 12; ++i) V[i] = st.cf[0][i] + st.cf[1][i] + st.cf[2][i];
+    const double i0 = st.rI[S1][0], i1 = st.rI[S1][1], i2 = st.rI[S1][2];          // pixel (orow, gx)
+    const double l0 = shfl_up1d(i0), l1 = shfl_up1d(i1), l2 = shfl_up1d(i2);       // pixel (orow, gx-1)
+    const double q0 = shfl_dn1d(i0), q1 = shfl_dn1d(i1), q2 = shfl_dn1d(i2);       // pixel (orow, gx+1)
+    double uL[3], uC[3], uR[3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        uL[c] = V[c] * l0 + V[3 + c] * l1 + V[6 + c] * l2 + V[9 + c];
+        uC[c] = V[c] * i0 + V[3 + c] * i1 + V[6 + c] * i2 + V[9 + c];
+        uR[c] = V[c] * q0 + V[3 + c] * q1 + V[6 + c] * q2 + V[9 + c];
+    }
+    // pixel l collects: window column l-1's "right" value, its own, window column l+1's "left" value
+    double tot[3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) tot[c] = uC[c] + shfl_up1d(uR[c]) + shfl_dn1d(uL[c]);
+    if (ir >= r0 + 2 && lane >= 2 && lane <= 29 && gx < W && orow < H && orow < r_end) {
+        double cnt = 9.0;
+        if (!v2) {
+            const int ylo = max(orow - 1, 1), yhi = min(orow + 1, H - 2);
+            const int xlo = max(gx - 1, 1), xhi = min(gx + 1, W - 2);
+            cnt = double(max(yhi - ylo + 1, 0) * max(xhi - xlo + 1, 0));
+        }
+        const size_t g = (size_t(orow) * W + gx) * 3;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            const double xc = st.rX[S1][c];
+            const double yc = cnt * xc - tot[c];
+            acc += xc * yc;
+            if (y != nullptr) y[g + c] = float(y_scale * yc);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(LM_WARPS * 32)
+lap_march2_kernel(const float* __restrict__ img, const float* __restrict__ x, float* __restrict__ y, double* __restrict__ partial,
+                  int H, int W, int mode, double eps, double y_scale, int RW, int strips_x, int total_warps) {
+    __shared__ double sRed[32];
+    const int lane = threadIdx.x & 31;
+    int gw = blockIdx.x * LM_WARPS + (threadIdx.x >> 5);
+    const bool live = gw < total_warps;                        // spare warps of the last CTA run an empty strip
+    if (!live) gw = 0;
+    double acc = 0.0;
+    {
+        const int sy = gw / strips_x, sx = gw - sy * strips_x;
+        const int c0 = sx * LM_COLS, r0 = sy * RW, r_end = live ? min(r0 + RW, H) : r0;
+        const int gx = c0 - 2 + lane;
+        const bool v2 = (mode == ADPST_LAP_V2);
+        const int mx = v2 ? reflect_symmetric(gx, W) : gx;
+        const bool col_ok = v2 || (gx >= 0 && gx < W);
+        LapMarch2State st;
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+#pragma unroll
+            for (int j = 0; j < 12; ++j) st.cf[i][j] = 0.0;
+#pragma unroll
+            for (int j = 0; j < 3; ++j) { st.rI[i][j] = 0.0; st.rX[i][j] = 0.0; }
+        }
+        auto load_row = [&](int ir, float (&vI)[3], float (&vX)[3]) {
+            int my = ir;
+            bool ok = col_ok && live;
+            if (v2) my = reflect_symmetric(ir, H);
+            else ok = ok && ir >= 0 && ir < H;
+            vI[0] = vI[1] = vI[2] = vX[0] = vX[1] = vX[2] = 0.f;
+            if (ok) {
+                const size_t g = (size_t(my) * W + mx) * 3;
+                vI[0] = __ldg(img + g); vI[1] = __ldg(img + g + 1); vI[2] = __ldg(img + g + 2);
+                vX[0] = __ldg(x + g);   vX[1] = __ldg(x + g + 1);   vX[2] = __ldg(x + g + 2);
+            }
+        };
+        float cI[3], cX[3], nI[3], nX[3];
+        const int ir_begin = r0 - 2;
+        const int nsteps = live ? (r_end + 1 - ir_begin + 1) : 0;          // rows r0-2 .. r_end+1
+        const int ntriples = (nsteps + 2) / 3;                               // a partial last triple only computes halo rows
+        load_row(ir_begin, cI, cX);
+        for (int tpl = 0; tpl < ntriples; ++tpl) {
+            const int ir = ir_begin + 3 * tpl;
+            load_row(ir + 1, nI, nX);
+            lap_march2_step<0>(st, cI, cX, ir, r0, r_end, gx, lane, H, W, v2, eps, y_scale, y, acc);
+            load_row(ir + 2, cI, cX);
+            lap_march2_step<1>(st, nI, nX, ir + 1, r0, r_end, gx, lane, H, W, v2, eps, y_scale, y, acc);
+            load_row(ir + 3, nI, nX);
+            lap_march2_step<2>(st, cI, cX, ir + 2, r0, r_end, gx, lane, H, W, v2, eps, y_scale, y, acc);
+#pragma unroll
+            for (int c = 0; c < 3; ++c) { cI[c] = nI[c]; cX[c] = nX[c]; }
+        }
+    }
+    if (partial != nullptr) {
+        const double tot = block_sum<double>(acc, sRed);
+        if (threadIdx.x == 0) partial[blockIdx.x] = tot;
+    }
+}
+
 template <typename TC>
 __global__ void __launch_bounds__(LM_WARPS * 32)
 lap_march_kernel(const float* __restrict__ img, const float* __restrict__ x, float* __restrict__ y, double* __restrict__ partial,
@@ -579,9 +745,14 @@ static int launch_march(adpst_laplacian* h, const void* x, void* y, double y_sca
     const int strips_x = (h->W + LM_COLS - 1) / LM_COLS, total = strips_x * ((h->H + RW - 1) / RW);
     const int ctas = (total + LM_WARPS - 1) / LM_WARPS;
     if (ctas > h->npartials) return fail(ADPST_ERR_INVALID, "laplacian: partial buffer too small (%d > %d)", ctas, h->npartials);
-    lap_march_kernel<TC><<<ctas, LM_WARPS * 32, 0, st>>>(static_cast<const float*>(h->image), static_cast<const float*>(x),
-                                                         static_cast<float*>(y), xLx ? h->partials : nullptr, h->H, h->W,
-                                                         h->mode, TC(h->eps), TC(y_scale), RW, strips_x, total);
+    if constexpr (std::is_same<TC, double>::value)
+        lap_march2_kernel<<<ctas, LM_WARPS * 32, 0, st>>>(static_cast<const float*>(h->image), static_cast<const float*>(x),
+                                                          static_cast<float*>(y), xLx ? h->partials : nullptr, h->H, h->W,
+                                                          h->mode, h->eps, y_scale, RW, strips_x, total);
+    else
+        lap_march_kernel<TC><<<ctas, LM_WARPS * 32, 0, st>>>(static_cast<const float*>(h->image), static_cast<const float*>(x),
+                                                             static_cast<float*>(y), xLx ? h->partials : nullptr, h->H, h->W,
+                                                             h->mode, TC(h->eps), TC(y_scale), RW, strips_x, total);
     ADPST_LAUNCH_CHECK();
     if (xLx) {
         sum_partials_kernel<<<1, 256, 0, st>>>(h->partials, ctas, xLx);

@@ -159,39 +159,58 @@ conv3x3_simt_kernel(const float* __restrict__ X, const float* __restrict__ Wt, c
 //   dImg[p, rgb] = 255 * sum_{tap, co} dPre[p + tap - 1, co] * W[2-kh][2-kw][ci = 2 - rgb][co]
 // Wg: [tap'][3 (rgb)][64] already flipped / permuted / scaled by 255.
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128)
+// 16 x 32 pixel tile per CTA; the 18 x 34 x 64 halo of dPre is staged in shared memory in two 32-channel halves
+// (78 KB each would not leave room for two CTAs per SM), so every dPre value is read from HBM/L2 ~1.2 times instead of 9.
+constexpr int IG_TH = 16, IG_TW = 32, IG_CH = 32;
+constexpr int IG_PITCH = IG_CH + 4;                   // floats per staged pixel (16-byte aligned, bank-skewed)
+constexpr int IG_SMEM = (IG_TH + 2) * (IG_TW + 2) * IG_PITCH * 4 + 9 * 3 * 64 * 4;
+
+__global__ void __launch_bounds__(512)
 conv1_dgrad_image_kernel(const float* __restrict__ dPre, const float* __restrict__ Wg, float* __restrict__ dImg, int H,
                          int W) {
-    __shared__ __align__(16) float sW[9 * 3 * 64];
+    extern __shared__ __align__(16) float ig_smem[];
+    float* sD = ig_smem;                                              // [(TH+2)*(TW+2)][IG_PITCH]
+    float* sW = ig_smem + (IG_TH + 2) * (IG_TW + 2) * IG_PITCH;       // [tap][rgb][64]
     for (int i = threadIdx.x; i < 9 * 3 * 64; i += blockDim.x) sW[i] = Wg[i];
-    __syncthreads();
-    const int gx = blockIdx.x * 32 + (threadIdx.x & 31), gy = blockIdx.y * 4 + (threadIdx.x >> 5);
-    if (gx >= W || gy >= H) return;
+    const int x0 = blockIdx.x * IG_TW, y0 = blockIdx.y * IG_TH;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
     float a0 = 0.f, a1 = 0.f, a2 = 0.f;
+    for (int half = 0; half < 64 / IG_CH; ++half) {
+        __syncthreads();
+        for (int i = threadIdx.x; i < (IG_TH + 2) * (IG_TW + 2) * (IG_CH / 4); i += blockDim.x) {
+            const int px = i / (IG_CH / 4), c4 = i - px * (IG_CH / 4);
+            const int r = px / (IG_TW + 2), c = px - r * (IG_TW + 2);
+            const int gy = y0 - 1 + r, gx = x0 - 1 + c;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (gy >= 0 && gy < H && gx >= 0 && gx < W)
+                v = __ldg(reinterpret_cast<const float4*>(dPre + (size_t(gy) * W + gx) * 64 + half * IG_CH) + c4);
+            *reinterpret_cast<float4*>(sD + px * IG_PITCH + c4 * 4) = v;
+        }
+        __syncthreads();
 #pragma unroll
-    for (int kh = 0; kh < 3; ++kh) {
-        const int yy = gy + kh - 1;
-        if (yy < 0 || yy >= H) continue;
+        for (int kh = 0; kh < 3; ++kh) {
 #pragma unroll
-        for (int kw = 0; kw < 3; ++kw) {
-            const int xx = gx + kw - 1;
-            if (xx < 0 || xx >= W) continue;
-            const float4* q = reinterpret_cast<const float4*>(dPre + (size_t(yy) * W + xx) * 64);
-            const float* w = sW + (kh * 3 + kw) * 192;
-#pragma unroll 4
-            for (int c4 = 0; c4 < 16; ++c4) {
-                const float4 v = __ldg(q + c4);
-                const float4 w0 = *reinterpret_cast<const float4*>(w + c4 * 4);
-                const float4 w1 = *reinterpret_cast<const float4*>(w + 64 + c4 * 4);
-                const float4 w2 = *reinterpret_cast<const float4*>(w + 128 + c4 * 4);
-                a0 = fmaf(v.x, w0.x, a0); a0 = fmaf(v.y, w0.y, a0); a0 = fmaf(v.z, w0.z, a0); a0 = fmaf(v.w, w0.w, a0);
-                a1 = fmaf(v.x, w1.x, a1); a1 = fmaf(v.y, w1.y, a1); a1 = fmaf(v.z, w1.z, a1); a1 = fmaf(v.w, w1.w, a1);
-                a2 = fmaf(v.x, w2.x, a2); a2 = fmaf(v.y, w2.y, a2); a2 = fmaf(v.z, w2.z, a2); a2 = fmaf(v.w, w2.w, a2);
+            for (int kw = 0; kw < 3; ++kw) {
+                const float4* q = reinterpret_cast<const float4*>(sD + ((ty + kh) * (IG_TW + 2) + tx + kw) * IG_PITCH);
+                const float* w = sW + (kh * 3 + kw) * 192 + half * IG_CH;
+#pragma unroll
+                for (int c4 = 0; c4 < IG_CH / 4; ++c4) {
+                    const float4 v = q[c4];
+                    const float4 w0 = *reinterpret_cast<const float4*>(w + c4 * 4);
+                    const float4 w1 = *reinterpret_cast<const float4*>(w + 64 + c4 * 4);
+                    const float4 w2 = *reinterpret_cast<const float4*>(w + 128 + c4 * 4);
+                    a0 = fmaf(v.x, w0.x, a0); a0 = fmaf(v.y, w0.y, a0); a0 = fmaf(v.z, w0.z, a0); a0 = fmaf(v.w, w0.w, a0);
+                    a1 = fmaf(v.x, w1.x, a1); a1 = fmaf(v.y, w1.y, a1); a1 = fmaf(v.z, w1.z, a1); a1 = fmaf(v.w, w1.w, a1);
+                    a2 = fmaf(v.x, w2.x, a2); a2 = fmaf(v.y, w2.y, a2); a2 = fmaf(v.z, w2.z, a2); a2 = fmaf(v.w, w2.w, a2);
+                }
             }
         }
     }
-    float* o = dImg + (size_t(gy) * W + gx) * 3;
-    o[0] = a0; o[1] = a1; o[2] = a2;
+    const int gx = x0 + tx, gy = y0 + ty;
+    if (gx < W && gy < H) {
+        float* o = dImg + (size_t(gy) * W + gx) * 3;
+        o[0] = a0; o[1] = a1; o[2] = a2;
+    }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -509,8 +528,13 @@ int adpst_vgg_backward(adpst_vgg* h, int H, int W, const float* const* acts_dev,
             ADPST_LAUNCH_CHECK();
         }
     }
-    dim3 grid((W + 31) / 32, (H + 3) / 4);
-    conv1_dgrad_image_kernel<<<grid, 128, 0, st>>>(cur, h->wg0, dimage_dev, H, W);
+    static bool ig_configured = false;
+    if (!ig_configured) {
+        ADPST_CUDA_CHECK(cudaFuncSetAttribute(conv1_dgrad_image_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, IG_SMEM));
+        ig_configured = true;
+    }
+    dim3 grid((W + IG_TW - 1) / IG_TW, (H + IG_TH - 1) / IG_TH);
+    conv1_dgrad_image_kernel<<<grid, IG_TH * IG_TW, IG_SMEM, st>>>(cur, h->wg0, dimage_dev, H, W);
     ADPST_LAUNCH_CHECK();
     return ADPST_OK;
 }

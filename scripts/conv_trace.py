@@ -19,12 +19,7 @@ b = buf.cpu().numpy()
 t0, t1 = b[4 * 4096], b[4 * 4096 + 1]
 iters = 9 * cin // 32
 print("CTA total %d clk; iters %d; per iter %.0f" % (t1 - t0, iters, (t1 - t0) / iters))
-prod = b[0:2 * iters:2] - t0
-tr = b[4096:4096 + 4 * iters].reshape(iters, 4) - t0
 mm = b[2 * 4096:2 * 4096 + 4 * iters].reshape(iters, 4) - t0
-sl = slice(24, 36)
-print("producer issue        ", prod[sl])
-print("transform: A seen     ", tr[sl, 0]); print("  split done (regs)   ", tr[sl, 1]); print("  a_free seen         ", tr[sl, 2]); print("  stored+arrived      ", tr[sl, 3])
-print("mma: arrive           ", mm[sl, 0]); print("  B seen              ", mm[sl, 1]); print("  ready seen          ", mm[sl, 2]); print("  issued+committed    ", mm[sl, 3])
-print("mma per-iter: wait B %s, wait ready %s, issue %s" % ((mm[sl, 1] - mm[sl, 0]), (mm[sl, 2] - mm[sl, 1]), (mm[sl, 3] - mm[sl, 2])))
-print("transform per-iter: A lat %s, split %s, wait a_free %s, store %s" % (tr[sl, 0] - prod[sl], tr[sl, 1] - tr[sl, 0], tr[sl, 2] - tr[sl, 1], tr[sl, 3] - tr[sl, 2]))
+sl = slice(24, 40)
+print("mma: arrive      ", mm[sl, 0]); print("     ready seen  ", mm[sl, 1]); print("     issued      ", mm[sl, 2])
+print("wait %s\nissue %s\nloop gap %s" % (mm[sl, 1] - mm[sl, 0], mm[sl, 2] - mm[sl, 1], mm[1:, 0][sl] - mm[:-1, 2][sl]))
