@@ -269,7 +269,8 @@ __device__ __forceinline__ void lap_march_step(LapMarchState<TC>& st, const floa
         st.rI[S][c] = shfl_up1(nI[c]);      st.rX[S][c] = shfl_up1(nX[c]);
         st.rI[S][6 + c] = shfl_dn1(nI[c]);  st.rX[S][6 + c] = shfl_dn1(nX[c]);
     }
-    if (ir < r0) return;                     // warp-uniform
+    // (computed on every step: no early exits, so that no control flow the compiler cannot prove warp-uniform surrounds
+    //  the shuffles; the first two steps of a strip produce unused values)
     // ---- window centred on (wr = ir - 1, gx): rows S1, S2, S of the ring
     const int wr = ir - 1;
     TC a[9], b[3];
@@ -355,10 +356,9 @@ __device__ __forceinline__ void lap_march_step(LapMarchState<TC>& st, const floa
     for (int i = 0; i < 9; ++i) st.hc[S1][i] = a[i] + shfl_up1(a[i]) + shfl_dn1(a[i]);
 #pragma unroll
     for (int c = 0; c < 3; ++c) st.hc[S1][9 + c] = b[c] + shfl_up1(b[c]) + shfl_dn1(b[c]);
-    if (ir < r0 + 2) return;                 // warp-uniform
     // ---- output row orow = ir - 2: window rows orow-1, orow, orow+1 = the three ring slots
     const int orow = ir - 2;
-    if (lane >= 2 && lane <= 29 && gx < W && orow < H && orow < r_end) {
+    if (ir >= r0 + 2 && lane >= 2 && lane <= 29 && gx < W && orow < H && orow < r_end) {
         TC cnt = TC(9);
         if (!v2) {
             const int ylo = max(orow - 1, 1), yhi = min(orow + 1, H - 2);
@@ -405,13 +405,22 @@ __device__ __forceinline__ void lap_march2_step(LapMarch2State& st, const float 
                                                 double y_scale, float* __restrict__ y, double& acc) {
     constexpr int S1 = (S + 1) % 3;                       // slot of row ir-2 (S holds row ir)
 #pragma unroll
-    for (int c = 0; c < 3; ++c) { st.rI[S][c] = double(nI[c]); st.rX[S][c] = double(nX[c]); }
+    for (int c = 0; c < 3; ++c) { st.rI[S][c] = f32_to_f64_exact(nI[c]); st.rX[S][c] = f32_to_f64_exact(nX[c]); }
     // ---- raw moments of this lane's column over rows ir-2..ir:  s(3) t(3) Q(6) R(9)
+    // (no zero-initialised accumulators: zeroing a register pair compiles to CS2R, which issues on the slow XU pipe --
+    //  measured at 100 % XU utilisation before this was removed)
     double cm[21];
+    {
+        const double i0 = st.rI[0][0], i1 = st.rI[0][1], i2 = st.rI[0][2];
+        const double x0 = st.rX[0][0], x1 = st.rX[0][1], x2 = st.rX[0][2];
+        cm[0] = i0; cm[1] = i1; cm[2] = i2; cm[3] = x0; cm[4] = x1; cm[5] = x2;
+        cm[6] = i0 * i0; cm[7] = i0 * i1; cm[8] = i0 * i2; cm[9] = i1 * i1; cm[10] = i1 * i2; cm[11] = i2 * i2;
+        cm[12] = i0 * x0; cm[13] = i0 * x1; cm[14] = i0 * x2;
+        cm[15] = i1 * x0; cm[16] = i1 * x1; cm[17] = i1 * x2;
+        cm[18] = i2 * x0; cm[19] = i2 * x1; cm[20] = i2 * x2;
+    }
 #pragma unroll
-    for (int i = 0; i < 21; ++i) cm[i] = 0.0;
-#pragma unroll
-    for (int rr = 0; rr < 3; ++rr) {
+    for (int rr = 1; rr < 3; ++rr) {
         const double i0 = st.rI[rr][0], i1 = st.rI[rr][1], i2 = st.rI[rr][2];
         const double x0 = st.rX[rr][0], x1 = st.rX[rr][1], x2 = st.rX[rr][2];
         cm[0] += i0; cm[1] += i1; cm[2] += i2; cm[3] += x0; cm[4] += x1; cm[5] += x2;
@@ -421,9 +430,12 @@ __device__ __forceinline__ void lap_march2_step(LapMarch2State& st, const float 
         cm[18] += i2 * x0; cm[19] += i2 * x1; cm[20] += i2 * x2;
     }
     // ---- window (wr = ir - 1, column gx) = columns gx-1, gx, gx+1
-    double wm[21];
+    double (&wm)[21] = cm;
 #pragma unroll
-    for (int i = 0; i < 21; ++i) wm[i] = cm[i] + shfl_up1d(cm[i]) + shfl_dn1d(cm[i]);
+    for (int i = 0; i < 21; ++i) {
+        const double up = shfl_up1d(cm[i]), dn = shfl_dn1d(cm[i]);
+        cm[i] += up + dn;
+    }
     const int wr = ir - 1;
     const bool valid = (lane >= 1 && lane <= 30) && (v2 || (wr >= 1 && wr < H - 1 && gx >= 1 && gx < W - 1));
     {
@@ -446,10 +458,9 @@ __device__ __forceinline__ void lap_march2_step(LapMarch2State& st, const float 
             a[6 + c] = Mi[2] * Rc[c] + Mi[4] * Rc[3 + c] + Mi[5] * Rc[6 + c];
             a[9 + c] = pbar[c] - (a[c] * mu[0] + a[3 + c] * mu[1] + a[6 + c] * mu[2]);
         }
-        if (!valid) {
+        const double keep = valid ? 1.0 : 0.0;                // multiply instead of zero-fill (see the CS2R note above)
 #pragma unroll
-            for (int i = 0; i < 12; ++i) a[i] = 0.0;
-        }
+        for (int i = 0; i < 12; ++i) a[i] *= keep;
     }
     // ---- output row orow = ir - 2 (window rows orow-1 .. orow+1 are the three cf slots)
     const int orow = ir - 2;
@@ -475,7 +486,8 @@ __device__ __forceinline__ void lap_march2_step(LapMarch2State& st, const float 
         if (!v2) {
             const int ylo = max(orow - 1, 1), yhi = min(orow + 1, H - 2);
             const int xlo = max(gx - 1, 1), xhi = min(gx + 1, W - 2);
-            cnt = double(max(yhi - ylo + 1, 0) * max(xhi - xlo + 1, 0));
+            const int nwin = max(yhi - ylo + 1, 0) * max(xhi - xlo + 1, 0);      // 0..9, table instead of I2F
+            cnt = nwin == 9 ? 9.0 : nwin == 6 ? 6.0 : nwin == 4 ? 4.0 : nwin == 3 ? 3.0 : nwin == 2 ? 2.0 : nwin == 1 ? 1.0 : 0.0;
         }
         const size_t g = (size_t(orow) * W + gx) * 3;
 #pragma unroll
@@ -483,7 +495,7 @@ __device__ __forceinline__ void lap_march2_step(LapMarch2State& st, const float 
             const double xc = st.rX[S1][c];
             const double yc = cnt * xc - tot[c];
             acc += xc * yc;
-            if (y != nullptr) y[g + c] = float(y_scale * yc);
+            if (y != nullptr) y[g + c] = f64_to_f32_rn(y_scale * yc);
         }
     }
 }
@@ -526,8 +538,9 @@ lap_march2_kernel(const float* __restrict__ img, const float* __restrict__ x, fl
         };
         float cI[3], cX[3], nI[3], nX[3];
         const int ir_begin = r0 - 2;
-        const int nsteps = live ? (r_end + 1 - ir_begin + 1) : 0;          // rows r0-2 .. r_end+1
-        const int ntriples = (nsteps + 2) / 3;                               // a partial last triple only computes halo rows
+        // rows r0-2 .. r0+RW+1 for every warp: the trip count depends on kernel parameters only, so the compiler can keep
+        // the shuffles outside divergence handling; rows past the image / the strip are predicated off at the store
+        const int ntriples = (RW + 4 + 2) / 3;
         load_row(ir_begin, cI, cX);
         for (int tpl = 0; tpl < ntriples; ++tpl) {
             const int ir = ir_begin + 3 * tpl;
@@ -553,23 +566,28 @@ lap_march_kernel(const float* __restrict__ img, const float* __restrict__ x, flo
                  int H, int W, int mode, TC eps, TC y_scale, int RW, int strips_x, int total_warps) {
     __shared__ double sRed[32];
     const int lane = threadIdx.x & 31;
-    const int gw = blockIdx.x * LM_WARPS + (threadIdx.x >> 5);
+    int gw = blockIdx.x * LM_WARPS + (threadIdx.x >> 5);
+    const bool live = gw < total_warps;                        // spare warps of the last CTA run an empty strip
+    if (!live) gw = 0;
     double acc = 0.0;
-    if (gw < total_warps) {                                    // warp-uniform
+    {
         const int sy = gw / strips_x, sx = gw - sy * strips_x;
-        const int c0 = sx * LM_COLS, r0 = sy * RW, r_end = min(r0 + RW, H);
+        const int c0 = sx * LM_COLS, r0 = sy * RW, r_end = live ? min(r0 + RW, H) : r0;
         const int gx = c0 - 2 + lane;
         const bool v2 = (mode == ADPST_LAP_V2);
         const int mx = v2 ? reflect_symmetric(gx, W) : gx;
         const bool col_ok = v2 || (gx >= 0 && gx < W);
         LapMarchState<TC> st;
 #pragma unroll
-        for (int i = 0; i < 3; ++i)
+        for (int i = 0; i < 3; ++i) {
 #pragma unroll
             for (int j = 0; j < 12; ++j) st.hc[i][j] = 0;
+#pragma unroll
+            for (int j = 0; j < 9; ++j) { st.rI[i][j] = 0.f; st.rX[i][j] = 0.f; }
+        }
         auto load_row = [&](int ir, float (&vI)[3], float (&vX)[3]) {
             int my = ir;
-            bool ok = col_ok;
+            bool ok = col_ok && live;
             if (v2) my = reflect_symmetric(ir, H);
             else ok = ok && ir >= 0 && ir < H;
             vI[0] = vI[1] = vI[2] = vX[0] = vX[1] = vX[2] = 0.f;
@@ -580,15 +598,15 @@ lap_march_kernel(const float* __restrict__ img, const float* __restrict__ x, flo
             }
         };
         float cI[3], cX[3], nI[3], nX[3];
-        const int ir_begin = r0 - 2, ir_last = r_end + 1;         // inclusive
+        const int ir_begin = r0 - 2;
+        const int ntriples = (RW + 4 + 2) / 3;                      // same trip count for every warp (see lap_march2_kernel)
         load_row(ir_begin, cI, cX);
-        for (int ir = ir_begin; ir <= ir_last; ir += 3) {
+        for (int tpl = 0; tpl < ntriples; ++tpl) {
+            const int ir = ir_begin + 3 * tpl;
             load_row(ir + 1, nI, nX);                               // prefetch one row ahead
             lap_march_step<TC, 0>(st, cI, cX, ir, r0, r_end, gx, lane, H, W, v2, eps, y_scale, y, acc);
-            if (ir + 1 > ir_last) break;
             load_row(ir + 2, cI, cX);
             lap_march_step<TC, 1>(st, nI, nX, ir + 1, r0, r_end, gx, lane, H, W, v2, eps, y_scale, y, acc);
-            if (ir + 2 > ir_last) break;
             load_row(ir + 3, nI, nX);
             lap_march_step<TC, 2>(st, cI, cX, ir + 2, r0, r_end, gx, lane, H, W, v2, eps, y_scale, y, acc);
 #pragma unroll
@@ -731,9 +749,9 @@ struct adpst_laplacian {
 namespace adpst {
 
 // rows per marching warp: enough warps for ~2 waves of 8 warps per SM, at most 64 rows (halo overhead (RW+2)/RW)
-static inline int march_rows(int H, int W) {
+static inline int march_rows(int H, int W, int warps_per_sm) {
     const int strips = (W + LM_COLS - 1) / LM_COLS;
-    const int want = 16 * num_sms();
+    const int want = warps_per_sm * num_sms();   // taller strips waste fewer halo rows, more warps hide more latency
     int rw = 64;
     while (rw > 16 && strips * ((H + rw - 1) / rw) < want) rw /= 2;
     return rw;
@@ -741,7 +759,8 @@ static inline int march_rows(int H, int W) {
 
 template <typename TC>
 static int launch_march(adpst_laplacian* h, const void* x, void* y, double y_scale, double* xLx, cudaStream_t st) {
-    const int RW = march_rows(h->H, h->W);
+    // float64 kernel: 255 registers -> 8 resident warps per SM, one full wave; float32 kernel: 12+ resident, two waves
+    const int RW = march_rows(h->H, h->W, std::is_same<TC, double>::value ? 8 : 16);
     const int strips_x = (h->W + LM_COLS - 1) / LM_COLS, total = strips_x * ((h->H + RW - 1) / RW);
     const int ctas = (total + LM_WARPS - 1) / LM_WARPS;
     if (ctas > h->npartials) return fail(ADPST_ERR_INVALID, "laplacian: partial buffer too small (%d > %d)", ctas, h->npartials);
