@@ -30,6 +30,7 @@ SIGNATURES = {
     "adpst_laplacian_create": (_i, [_i, _i, _i, _i, _d, _vp, _i, _i, _vp, _pp]),
     "adpst_laplacian_destroy": (None, [_vp]),
     "adpst_laplacian_matvec": (_i, [_vp, _vp, _vp, _d, _vp, _vp]),
+    "adpst_laplacian_set_quadratic_window": (_i, [_vp, _i, _i]),
     "adpst_laplacian_coefficients": (_i, [_vp, _vp, _vp, _vp]),
     "adpst_laplacian_nnz": (_c.c_int64, [_vp]),
     "adpst_laplacian_export_coo": (_i, [_vp, _vp, _vp, _vp, _vp]),
@@ -47,8 +48,8 @@ SIGNATURES = {
     "adpst_resize_bilinear": (_i, [_vp, _i, _i, _vp, _i, _i, _vp]),
     "adpst_gram_workspace_bytes": (_sz, [_i, _i, _i]),
     "adpst_gram_masked": (_i, [_vp, _i, _i, _i, _vp, _i, _vp, _vp, _vp, _i, _vp, _vp]),
-    "adpst_style_layer_backward": (_i, [_vp, _i, _i, _i, _vp, _i, _vp, _vp, _d, _d, _vp, _vp, _i, _i, _vp, _vp]),
-    "adpst_content_layer": (_i, [_vp, _vp, _sz, _d, _d, _vp, _vp, _i, _vp]),
+    "adpst_style_layer_backward": (_i, [_vp, _i, _i, _i, _vp, _i, _vp, _vp, _d, _d, _vp, _vp, _i, _i, _d, _vp, _vp]),
+    "adpst_content_layer": (_i, [_vp, _vp, _sz, _d, _d, _vp, _vp, _i, _d, _i, _i, _i, _i, _vp]),
     "adpst_loss_finalize": (_i, [_vp, _d, _d, _d, _vp, _vp]),
     "adpst_axpby": (_i, [_vp, _vp, _f, _vp, _f, _sz, _vp]),
 }

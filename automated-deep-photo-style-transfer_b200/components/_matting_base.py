@@ -50,6 +50,10 @@ class LaplacianHandle:
             except Exception:
                 pass
 
+    def set_quadratic_window(self, col_lo, col_hi):
+        """Restrict x^T L x to columns [col_lo, col_hi) (spatially tiled runs); (0, 0) = all columns."""
+        _lib.check(_lib.lib().adpst_laplacian_set_quadratic_window(self._h, int(col_lo), int(col_hi)))
+
     @property
     def HW(self):
         return self.H * self.W

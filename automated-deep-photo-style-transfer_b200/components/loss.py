@@ -20,7 +20,11 @@ from .matting_v3 import MattingLaplacian as MattingLaplacianV3
 class Loss:
     r"""Loss functions are computed within this class (reference loss.py:6-9)."""
 
-    def __init__(self, content_target, style_target, args, content_masks=None, style_masks=None, matting="v2"):
+    def __init__(self, content_target, style_target, args, content_masks=None, style_masks=None, matting="v2",
+                 tile=None, style_tile=None):
+        """tile / style_tile (extensions, see tiled.py): `Tile` descriptions when the transfer / style image handed to
+        this object is one column strip (with halo) of a larger image that is spread over several GPUs."""
+        self.tile, self.style_tile = tile, style_tile
         self.content_target = content_target
         self.style_target = style_target
         self.content_masks = content_masks
@@ -74,6 +78,8 @@ class Loss:
         cls = MattingLaplacianV2 if self.matting_variant == "v2" else MattingLaplacianV3
         self.matting_laplacian = cls(img, storage_dtype=torch.float32 if exact else torch.float64,
                                      compute_dtype=torch.float64, **self.matting_params)
+        if self.tile is not None:        # the scalar x^T L x counts this rank's own columns only
+            self.matting_laplacian._op.set_quadratic_window(*self.tile.own_cols(int(img.shape[1])))
 
     def __call__(self, image, outputs):                                       # loss.py:48-49
         return self.compute_loss(image, outputs)
@@ -96,48 +102,87 @@ class Loss:
                               for m in self.style_masks]).contiguous()
         else:
             K, cm, sm = 1, None, None                                                # loss.py:119-120
+        # spatial tiling: the Gram partial of this rank counts only its own columns (mask x column indicator; exact,
+        # because strip boundaries are multiples of 16 px and bilinear half-pixel resizing never straddles them), while the
+        # gradient uses the full local masks and the normaliser the pixel count of the whole image
+        cm_own = self.tile.own_masks(cm, K, h, w, self.device) if self.tile is not None else cm
+        sm_own = self.style_tile.own_masks(sm, K, hs, ws_, self.device) if self.style_tile is not None else sm
         ws = kernels.gram_workspace(max(h * w, hs * ws_), C, K, self.device)
-        A = kernels.gram_masked(target.reshape(hs, ws_, C), sm, K, ws,
-                                patches=kernels.gram_patch_lists(sm, hs, ws_, K, self.device))   # constant style Grams
-        st = {"shape": tuple(output.shape), "K": K, "masks": cm, "A": A, "ws": ws, "seed": torch.empty_like(output),
-              "patches": kernels.gram_patch_lists(cm, h, w, K, self.device),
-              "G": torch.empty(K, C, C, dtype=torch.float32, device=self.device)}
+        A = kernels.gram_masked(target.reshape(hs, ws_, C), sm_own, K, ws,
+                                patches=kernels.gram_patch_lists(sm_own, hs, ws_, K, self.device))   # constant style Grams
+        st = {"shape": tuple(output.shape), "K": K, "masks": cm, "own_masks": cm_own, "A": A, "ws": ws,
+              "seed": torch.empty_like(output), "patches": kernels.gram_patch_lists(cm_own, h, w, K, self.device),
+              "G": torch.empty(K, C, C, dtype=torch.float32, device=self.device),
+              "hw_norm": float(h * self.tile.global_cols(w)) if self.tile is not None else 0.0}
         self._layer_cache[name] = st
         return st
 
     def compute_loss(self, image, outputs):                                   # loss.py:53-78
+        self.forward_partials(image, outputs)
+        return self.finish()
+
+    def style_targets_partial(self):
+        """Spatially tiled runs: the style Grams A computed at set-up are per-rank partials; sum them over the ranks once."""
+        return [st["A"] for st in self._layer_cache.values()]
+
+    def prepare(self, outputs):
+        """Build the per-layer state (masks, style Grams, buffers) for these output shapes without evaluating anything."""
+        for name, target in self.style_target.items():
+            self._style_layer_state(name, target, outputs['style'][name])
+
+    def forward_partials(self, image, outputs):
+        """First half of compute_loss: everything that is local to this image (or image strip).  Returns the tensors that
+        must be summed over the ranks of a spatially tiled run before finish(): the per-layer Gram partials and the
+        float64 accumulator {content, (unused), photo}.  A single-device run just calls finish() afterwards."""
         content_output, style_output = outputs['content'], outputs['style']
         wts = self.loss_weights
         self._acc.zero_()
         seeds = {}
         n_args = 2.0                                                          # len(args) in iter_on_layers, loss.py:85
-
         for name, target in self.content_target.items():                     # loss.py:59, :90-92
             out = content_output[name]
             seed = self._content_seeds.get(name)
             if seed is None or seed.shape != out.shape:
                 seed = self._content_seeds[name] = torch.empty_like(out)
-            kernels.content_layer(target, out, 1.0 / n_args, wts['content'] / n_args, self._acc[0:1], seed)
+            if self.tile is None:
+                kernels.content_layer(target, out, 1.0 / n_args, wts['content'] / n_args, self._acc[0:1], seed)
+            else:
+                _, h, w, C = out.shape
+                kernels.content_layer(target, out, 1.0 / n_args, wts['content'] / n_args, self._acc[0:1], seed,
+                                      n_norm=float(h) * self.tile.global_cols(w) * C, own_cols=self.tile.own_cols(w))
             seeds[name] = seed
-
-        for name, target in self.style_target.items():                       # loss.py:62, :104-137
+        partials = []
+        for name, target in self.style_target.items():                       # loss.py:62, :96-102
             out = style_output[name]
             st = self._style_layer_state(name, target, out)
             _, h, w, C = out.shape
-            G = kernels.gram_masked(out.reshape(h, w, C), st["masks"], st["K"], st["ws"], patches=st["patches"], out=st["G"])
-            shared = name in seeds                                            # a layer can be both content and style
-            dF = seeds[name] if shared else st["seed"]
-            kernels.style_layer_backward(out.reshape(h, w, C), st["masks"], st["K"], G, st["A"], 1.0 / n_args,
-                                         wts['style'] / n_args, self._acc[1:2], dF.reshape(h * w, C), accumulate=shared,
-                                         workspace=st["ws"])
-            seeds[name] = dF
-
+            partials.append(kernels.gram_masked(out.reshape(h, w, C), st["own_masks"], st["K"], st["ws"],
+                                                patches=st["patches"], out=st["G"]))
         self._photo_grad = None
         if wts['photo'] > 0:                                                  # loss.py:67-69, :157-161
             if self.matting_laplacian is None:
                 raise RuntimeError("regularization_weight > 0 but initialize_matting_laplacian() was not called")
             self._photo_grad = self.calculate_photorealism_regularization(image, _with_gradient=True)
+        self._pending = (outputs, seeds)
+        return partials + [self._acc]
 
+    def finish(self):
+        """Second half of compute_loss: style loss and its gradient seeds from the (global) Grams, weighted total."""
+        outputs, seeds = self._pending
+        style_output = outputs['style']
+        wts = self.loss_weights
+        n_args = 2.0
+        self._acc[1:2].zero_()       # a cross-rank sum of the accumulator must not multiply the (global) style term
+        for name, target in self.style_target.items():                       # loss.py:104-137
+            out = style_output[name]
+            st = self._layer_cache[name]
+            _, h, w, C = out.shape
+            shared = name in seeds                                            # a layer can be both content and style
+            dF = seeds[name] if shared else st["seed"]
+            kernels.style_layer_backward(out.reshape(h, w, C), st["masks"], st["K"], st["G"], st["A"], 1.0 / n_args,
+                                         wts['style'] / n_args, self._acc[1:2], dF.reshape(h * w, C), accumulate=shared,
+                                         workspace=st["ws"], hw_norm=st["hw_norm"])
+            seeds[name] = dF
         kernels.loss_finalize(self._acc, wts['content'], wts['style'], wts['photo'], self._out)   # loss.py:72
         self._seeds = seeds
         loss_dict = {self.loss_names['content']: self._out[0], self.loss_names['style']: self._out[1],

@@ -62,18 +62,22 @@ adam_clip_kernel(float* __restrict__ x, const float* __restrict__ g, float* __re
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 content_kernel(const float* __restrict__ tgt, const float* __restrict__ out, size_t n, double loss_scale,
-               double grad_scale, double* __restrict__ loss, float* __restrict__ dOut, int accumulate) {
+               double grad_scale, double* __restrict__ loss, float* __restrict__ dOut, int accumulate, double n_norm,
+               int row_elems, int col_lo_elems, int col_hi_elems) {
     __shared__ double red[32];
-    const float gs = float(2.0 * grad_scale / double(n));
+    const float gs = float(2.0 * grad_scale / n_norm);
     double acc = 0.0;
     const size_t stride = size_t(gridDim.x) * blockDim.x;
     for (size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) {
         const float d = out[i] - tgt[i];
-        acc += double(d) * double(d);
+        // spatially tiled runs: the scalar counts only this rank's own columns, the gradient seed covers the halo too
+        bool own = true;
+        if (row_elems > 0) { const int e = int(i % size_t(row_elems)); own = e >= col_lo_elems && e < col_hi_elems; }
+        if (own) acc += double(d) * double(d);
         if (dOut) dOut[i] = accumulate ? dOut[i] + gs * d : gs * d;
     }
     acc = block_sum<double>(acc, red);
-    if (threadIdx.x == 0 && loss) atomicAdd(loss, acc * loss_scale / double(n));
+    if (threadIdx.x == 0 && loss) atomicAdd(loss, acc * loss_scale / n_norm);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -130,11 +134,16 @@ int adpst_adam_clip_step(float* x_dev, const float* grad_dev, float* m_dev, floa
 }
 
 int adpst_content_layer(const float* target_dev, const float* output_dev, size_t n, double loss_scale, double grad_scale,
-                        double* loss_dev, float* dOut_dev, int accumulate, adpst_stream_t stream) {
+                        double* loss_dev, float* dOut_dev, int accumulate, double n_norm, int w, int C, int col_lo, int col_hi,
+                        adpst_stream_t stream) {
     using namespace adpst;
     ADPST_REQUIRE(target_dev && output_dev && n > 0, "content_layer: NULL or empty input");
+    ADPST_REQUIRE(w == 0 || (C > 0 && col_lo >= 0 && col_hi <= w && col_lo <= col_hi && n % (size_t(w) * C) == 0),
+                  "content_layer: bad column window");
+    if (n_norm <= 0.0) n_norm = double(n);
     content_kernel<<<grid_for(n, 256), 256, 0, as_stream(stream)>>>(target_dev, output_dev, n, loss_scale, grad_scale,
-                                                                    loss_dev, dOut_dev, accumulate);
+                                                                    loss_dev, dOut_dev, accumulate, n_norm, w * C, col_lo * C,
+                                                                    col_hi * C);
     ADPST_LAUNCH_CHECK();
     return ADPST_OK;
 }

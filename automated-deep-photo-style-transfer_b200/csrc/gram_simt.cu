@@ -257,7 +257,7 @@ int adpst_gram_masked(const float* F_dev, int h, int w, int C, const float* mask
 
 int adpst_style_layer_backward(const float* F_dev, int h, int w, int C, const float* masks_dev, int K, const float* G_dev,
                                const float* A_dev, double loss_scale, double grad_scale, double* loss_dev, float* dF_dev,
-                               int accumulate, int path, void* workspace_dev, adpst_stream_t stream) {
+                               int accumulate, int path, double hw_norm, void* workspace_dev, adpst_stream_t stream) {
     using namespace adpst;
     ADPST_REQUIRE(F_dev && G_dev && A_dev && workspace_dev, "style_layer_backward: NULL argument");
     ADPST_REQUIRE(h > 0 && w > 0 && K > 0, "style_layer_backward: empty input");
@@ -265,7 +265,9 @@ int adpst_style_layer_backward(const float* F_dev, int h, int w, int C, const fl
     ADPST_REQUIRE(C > 0 && C % GT == 0, "style_layer_backward: C=%d must be a multiple of %d", C, GT);
     ADPST_REQUIRE(masks_dev || K == 1, "style_layer_backward: K=%d needs masks", K);
     cudaStream_t st = as_stream(stream);
-    const double c2 = double(C) * double(C), hw2 = double(HW) * double(HW);
+    // spatially tiled runs normalise by the pixel count of the WHOLE image (loss.py:123), not of the local tile
+    const double hwn = hw_norm > 0.0 ? hw_norm : double(HW);
+    const double c2 = double(C) * double(C), hw2 = hwn * hwn;
     const double coef = 2.0 * grad_scale / (c2 * c2 * hw2);        // D_k = coef (G_k - A_k)
     const double loss_coef = loss_scale / (2.0 * c2 * c2 * hw2);   // L = sum_k sum (G_k - A_k)^2 / (2 C^4 HW^2)
     const size_t n = size_t(K) * C * C;

@@ -128,7 +128,7 @@ template <int R> struct LapTile {
 template <typename TIO, typename TC, int R>
 __global__ void __launch_bounds__(LapTile<R>::THREADS)
 lap_matvec_kernel(const TIO* __restrict__ img, const TIO* __restrict__ x, TIO* __restrict__ y,
-                  double* __restrict__ partial, int H, int W, int mode, TC eps, TC y_scale) {
+                  double* __restrict__ partial, int H, int W, int mode, TC eps, TC y_scale, int qlo, int qhi) {
     using T = LapTile<R>;
     constexpr int D = 2 * R + 1;
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -222,7 +222,7 @@ lap_matvec_kernel(const TIO* __restrict__ img, const TIO* __restrict__ x, TIO* _
         for (int c = 0; c < 3; ++c) {
             const TC xc = sX[pi + c];
             const TC yc = cnt * xc - (A[c] * i0 + A[3 + c] * i1 + A[6 + c] * i2 + B[c]);
-            acc += double(xc) * double(yc);
+            if (gx >= qlo && gx < qhi) acc += double(xc) * double(yc);
             if (y != nullptr) y[g + c] = TIO(y_scale * yc);
         }
     }
@@ -260,7 +260,7 @@ struct LapMarchState {
 template <typename TC, int S>
 __device__ __forceinline__ void lap_march_step(LapMarchState<TC>& st, const float (&nI)[3], const float (&nX)[3], int ir, int r0,
                                                int r_end, int gx, int lane, int H, int W, bool v2, TC eps, TC y_scale,
-                                               float* __restrict__ y, double& acc) {
+                                               float* __restrict__ y, double& acc, int qlo, int qhi) {
     constexpr int S1 = (S + 1) % 3, S2 = (S + 2) % 3;     // rows ir-2, ir-1 ; S holds row ir
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
@@ -375,7 +375,7 @@ __device__ __forceinline__ void lap_march_step(LapMarchState<TC>& st, const floa
             const TC B = st.hc[0][9 + c] + st.hc[1][9 + c] + st.hc[2][9 + c];
             const TC xc = st.rX[S1][3 + c];
             const TC yc = cnt * xc - (A0 * i0 + A1 * i1 + A2 * i2 + B);
-            acc += double(xc) * double(yc);
+            if (gx >= qlo && gx < qhi) acc += double(xc) * double(yc);
             if (y != nullptr) y[g + c] = float(y_scale * yc);
         }
     }
@@ -402,7 +402,7 @@ __device__ __forceinline__ double shfl_dn1d(double v) { return __shfl_down_sync(
 template <int S>
 __device__ __forceinline__ void lap_march2_step(LapMarch2State& st, const float (&nI)[3], const float (&nX)[3], int ir, int r0,
                                                 int r_end, int gx, int lane, int H, int W, bool v2, double eps,
-                                                double y_scale, float* __restrict__ y, double& acc) {
+                                                double y_scale, float* __restrict__ y, double& acc, int qlo, int qhi) {
     constexpr int S1 = (S + 1) % 3;                       // slot of row ir-2 (S holds row ir)
 #pragma unroll
     for (int c = 0; c < 3; ++c) { st.rI[S][c] = f32_to_f64_exact(nI[c]); st.rX[S][c] = f32_to_f64_exact(nX[c]); }
@@ -494,7 +494,7 @@ __device__ __forceinline__ void lap_march2_step(LapMarch2State& st, const float 
         for (int c = 0; c < 3; ++c) {
             const double xc = st.rX[S1][c];
             const double yc = cnt * xc - tot[c];
-            acc += xc * yc;
+            if (gx >= qlo && gx < qhi) acc += xc * yc;
             if (y != nullptr) y[g + c] = f64_to_f32_rn(y_scale * yc);
         }
     }
@@ -502,7 +502,7 @@ __device__ __forceinline__ void lap_march2_step(LapMarch2State& st, const float 
 
 __global__ void __launch_bounds__(LM_WARPS * 32)
 lap_march2_kernel(const float* __restrict__ img, const float* __restrict__ x, float* __restrict__ y, double* __restrict__ partial,
-                  int H, int W, int mode, double eps, double y_scale, int RW, int strips_x, int total_warps) {
+                  int H, int W, int mode, double eps, double y_scale, int RW, int strips_x, int total_warps, int qlo, int qhi) {
     __shared__ double sRed[32];
     const int lane = threadIdx.x & 31;
     int gw = blockIdx.x * LM_WARPS + (threadIdx.x >> 5);
@@ -545,11 +545,11 @@ lap_march2_kernel(const float* __restrict__ img, const float* __restrict__ x, fl
         for (int tpl = 0; tpl < ntriples; ++tpl) {
             const int ir = ir_begin + 3 * tpl;
             load_row(ir + 1, nI, nX);
-            lap_march2_step<0>(st, cI, cX, ir, r0, r_end, gx, lane, H, W, v2, eps, y_scale, y, acc);
+            lap_march2_step<0>(st, cI, cX, ir, r0, r_end, gx, lane, H, W, v2, eps, y_scale, y, acc, qlo, qhi);
             load_row(ir + 2, cI, cX);
-            lap_march2_step<1>(st, nI, nX, ir + 1, r0, r_end, gx, lane, H, W, v2, eps, y_scale, y, acc);
+            lap_march2_step<1>(st, nI, nX, ir + 1, r0, r_end, gx, lane, H, W, v2, eps, y_scale, y, acc, qlo, qhi);
             load_row(ir + 3, nI, nX);
-            lap_march2_step<2>(st, cI, cX, ir + 2, r0, r_end, gx, lane, H, W, v2, eps, y_scale, y, acc);
+            lap_march2_step<2>(st, cI, cX, ir + 2, r0, r_end, gx, lane, H, W, v2, eps, y_scale, y, acc, qlo, qhi);
 #pragma unroll
             for (int c = 0; c < 3; ++c) { cI[c] = nI[c]; cX[c] = nX[c]; }
         }
@@ -563,7 +563,7 @@ lap_march2_kernel(const float* __restrict__ img, const float* __restrict__ x, fl
 template <typename TC>
 __global__ void __launch_bounds__(LM_WARPS * 32)
 lap_march_kernel(const float* __restrict__ img, const float* __restrict__ x, float* __restrict__ y, double* __restrict__ partial,
-                 int H, int W, int mode, TC eps, TC y_scale, int RW, int strips_x, int total_warps) {
+                 int H, int W, int mode, TC eps, TC y_scale, int RW, int strips_x, int total_warps, int qlo, int qhi) {
     __shared__ double sRed[32];
     const int lane = threadIdx.x & 31;
     int gw = blockIdx.x * LM_WARPS + (threadIdx.x >> 5);
@@ -604,11 +604,11 @@ lap_march_kernel(const float* __restrict__ img, const float* __restrict__ x, flo
         for (int tpl = 0; tpl < ntriples; ++tpl) {
             const int ir = ir_begin + 3 * tpl;
             load_row(ir + 1, nI, nX);                               // prefetch one row ahead
-            lap_march_step<TC, 0>(st, cI, cX, ir, r0, r_end, gx, lane, H, W, v2, eps, y_scale, y, acc);
+            lap_march_step<TC, 0>(st, cI, cX, ir, r0, r_end, gx, lane, H, W, v2, eps, y_scale, y, acc, qlo, qhi);
             load_row(ir + 2, cI, cX);
-            lap_march_step<TC, 1>(st, nI, nX, ir + 1, r0, r_end, gx, lane, H, W, v2, eps, y_scale, y, acc);
+            lap_march_step<TC, 1>(st, nI, nX, ir + 1, r0, r_end, gx, lane, H, W, v2, eps, y_scale, y, acc, qlo, qhi);
             load_row(ir + 3, nI, nX);
-            lap_march_step<TC, 2>(st, cI, cX, ir + 2, r0, r_end, gx, lane, H, W, v2, eps, y_scale, y, acc);
+            lap_march_step<TC, 2>(st, cI, cX, ir + 2, r0, r_end, gx, lane, H, W, v2, eps, y_scale, y, acc, qlo, qhi);
 #pragma unroll
             for (int c = 0; c < 3; ++c) { cI[c] = nI[c]; cX[c] = nX[c]; }
         }
@@ -744,6 +744,7 @@ struct adpst_laplacian {
     double* partials = nullptr;  // one per CTA, owned
     int npartials = 0;
     bool force_tile_kernel = false;   // validation: use the shared-memory tile kernel for r = 1 as well
+    int q_col_lo = 0, q_col_hi = 0;   // x^T L x restricted to these columns (spatially tiled runs); (0,0) = all
 };
 
 namespace adpst {
@@ -760,6 +761,7 @@ static inline int march_rows(int H, int W, int warps_per_sm) {
 template <typename TC>
 static int launch_march(adpst_laplacian* h, const void* x, void* y, double y_scale, double* xLx, cudaStream_t st) {
     // float64 kernel: 255 registers -> 8 resident warps per SM, one full wave; float32 kernel: 12+ resident, two waves
+    const int qlo = h->q_col_hi > h->q_col_lo ? h->q_col_lo : 0, qhi = h->q_col_hi > h->q_col_lo ? h->q_col_hi : h->W;
     const int RW = march_rows(h->H, h->W, std::is_same<TC, double>::value ? 8 : 16);
     const int strips_x = (h->W + LM_COLS - 1) / LM_COLS, total = strips_x * ((h->H + RW - 1) / RW);
     const int ctas = (total + LM_WARPS - 1) / LM_WARPS;
@@ -767,11 +769,11 @@ static int launch_march(adpst_laplacian* h, const void* x, void* y, double y_sca
     if constexpr (std::is_same<TC, double>::value)
         lap_march2_kernel<<<ctas, LM_WARPS * 32, 0, st>>>(static_cast<const float*>(h->image), static_cast<const float*>(x),
                                                           static_cast<float*>(y), xLx ? h->partials : nullptr, h->H, h->W,
-                                                          h->mode, h->eps, y_scale, RW, strips_x, total);
+                                                          h->mode, h->eps, y_scale, RW, strips_x, total, qlo, qhi);
     else
         lap_march_kernel<TC><<<ctas, LM_WARPS * 32, 0, st>>>(static_cast<const float*>(h->image), static_cast<const float*>(x),
                                                              static_cast<float*>(y), xLx ? h->partials : nullptr, h->H, h->W,
-                                                             h->mode, TC(h->eps), TC(y_scale), RW, strips_x, total);
+                                                             h->mode, TC(h->eps), TC(y_scale), RW, strips_x, total, qlo, qhi);
     ADPST_LAUNCH_CHECK();
     if (xLx) {
         sum_partials_kernel<<<1, 256, 0, st>>>(h->partials, ctas, xLx);
@@ -786,6 +788,7 @@ static int launch_matvec(adpst_laplacian* h, const void* x, void* y, double y_sc
         if (!h->force_tile_kernel) return launch_march<TC>(h, x, y, y_scale, xLx, st);
     }
     using T = LapTile<R>;
+    const int qlo = h->q_col_hi > h->q_col_lo ? h->q_col_lo : 0, qhi = h->q_col_hi > h->q_col_lo ? h->q_col_hi : h->W;
     auto kern = lap_matvec_kernel<TIO, TC, R>;
     const size_t smem = T::template smem_bytes<TIO, TC>();
     static bool configured = false;            // per instantiation
@@ -796,7 +799,7 @@ static int launch_matvec(adpst_laplacian* h, const void* x, void* y, double y_sc
     dim3 grid((h->W + T::TW - 1) / T::TW, (h->H + T::TH - 1) / T::TH);
     kern<<<grid, T::THREADS, smem, st>>>(static_cast<const TIO*>(h->image), static_cast<const TIO*>(x),
                                           static_cast<TIO*>(y), xLx ? h->partials : nullptr, h->H, h->W, h->mode,
-                                          TC(h->eps), TC(y_scale));
+                                          TC(h->eps), TC(y_scale), qlo, qhi);
     ADPST_LAUNCH_CHECK();
     if (xLx) {
         sum_partials_kernel<<<1, 256, 0, st>>>(h->partials, int(grid.x * grid.y), xLx);
@@ -919,6 +922,14 @@ int adpst_laplacian_coefficients(adpst_laplacian* h, void* means_dev, void* delt
     if (h->mode != ADPST_LAP_V2)
         return fail(ADPST_ERR_UNSUPPORTED, "laplacian_coefficients: only the v2 operator has means/delta_inv fields");
     return dispatch_coeffs(h, means_dev, delta_inv_dev, as_stream(stream));
+}
+
+int adpst_laplacian_set_quadratic_window(adpst_laplacian* h, int col_lo, int col_hi) {
+    using namespace adpst;
+    ADPST_REQUIRE(h != nullptr && col_lo >= 0 && col_hi <= h->W && col_lo <= col_hi, "laplacian_set_quadratic_window: bad window");
+    h->q_col_lo = col_lo;
+    h->q_col_hi = col_hi;
+    return ADPST_OK;
 }
 
 int64_t adpst_laplacian_nnz(const adpst_laplacian* h) {

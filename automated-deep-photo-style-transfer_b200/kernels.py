@@ -46,13 +46,17 @@ def resize_bilinear(mask_hw, size):
     return out
 
 
-def content_layer(target, output, loss_scale, grad_scale, loss_acc, d_out=None, accumulate=False):
-    """loss_acc (float64[1]) += loss_scale*mean((t-o)^2); d_out (=|+=) grad_scale*2(o-t)/n  (loss.py:90-92)."""
+def content_layer(target, output, loss_scale, grad_scale, loss_acc, d_out=None, accumulate=False, n_norm=0.0, own_cols=None):
+    """loss_acc (float64[1]) += loss_scale*mean((t-o)^2); d_out (=|+=) grad_scale*2(o-t)/n  (loss.py:90-92).
+    Spatially tiled runs: n_norm = element count of the whole layer, own_cols = (lo, hi) columns of this (1,h,w,C) tile
+    that count towards the scalar."""
     _f32(target, "target"); _f32(output, "output")
     if target.shape != output.shape:
         raise ValueError("content target %s and output %s differ in shape" % (tuple(target.shape), tuple(output.shape)))
     _lib.check(_lib.lib().adpst_content_layer(_lib.ptr(target), _lib.ptr(output), output.numel(), float(loss_scale),
                                               float(grad_scale), _lib.ptr(loss_acc), _lib.ptr(d_out), int(bool(accumulate)),
+                                              float(n_norm), *((int(output.shape[2]), int(output.shape[3]), int(own_cols[0]),
+                                                                int(own_cols[1])) if own_cols is not None else (0, 0, 0, 0)),
                                               _lib.stream_ptr()))
 
 
@@ -112,7 +116,7 @@ def gram_masked(F, masks, K, workspace=None, patches=None, path="tensor", out=No
 
 
 def style_layer_backward(F, masks, K, G, A, loss_scale, grad_scale, loss_acc, dF, accumulate=False, workspace=None,
-                         path="tensor"):
+                         path="tensor", hw_norm=0.0):
     """One layer of loss.py:104-137: accumulates the loss value and writes/adds its gradient w.r.t. F.
     F: (h, w, C) feature map (a (HW, C) matrix is treated as h = HW, w = 1... use the 3-D form for 2-D tiling)."""
     _f32(F, "F"); _f32(G, "G"); _f32(A, "A")
@@ -122,8 +126,8 @@ def style_layer_backward(F, masks, K, G, A, loss_scale, grad_scale, loss_acc, dF
     ws = workspace if workspace is not None else gram_workspace(h * w, C, K, F.device)
     _lib.check(_lib.lib().adpst_style_layer_backward(_lib.ptr(F), h, w, C, _lib.ptr(masks), K, _lib.ptr(G), _lib.ptr(A),
                                                      float(loss_scale), float(grad_scale), _lib.ptr(loss_acc), _lib.ptr(dF),
-                                                     int(bool(accumulate)), {"tensor": 0, "simt": 1}[path], _lib.ptr(ws),
-                                                     _lib.stream_ptr()))
+                                                     int(bool(accumulate)), {"tensor": 0, "simt": 1}[path], float(hw_norm),
+                                                     _lib.ptr(ws), _lib.stream_ptr()))
 
 
 def loss_finalize(acc, w_content, w_style, w_photo, out):

@@ -356,6 +356,55 @@ def cpu_baseline(size, K):
                       "of the reference step; TensorFlow itself is not installable here)" % (n, size, size, K)}
 
 
+def run_tiled(args):
+    """BASELINE configs[3]: ONE 3840x2160 image, column strips over N GPUs (tiled.py): overlapped halos instead of
+    per-layer exchange, NCCL all-reduce of the Gram partials, NCCL all-gather of the updated strips.  Strong scaling."""
+    import torch
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1")); rank = int(os.environ.get("RANK", "0")); local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    synth = importlib.import_module(PKG + ".synth"); tiled = importlib.import_module(PKG + ".tiled")
+    sem = importlib.import_module(PKG + ".components.semantic_merge")
+    H, W, K = args.tiled_h, args.tiled_w, args.classes
+    hp = hyper(None)
+    content, style = synth.image(H, W, 0), synth.image(H, W, 1)
+    cm = sem.mask_for_tf(sem.extract_segmentation_masks(synth.label_image(H, W, K, 9, cell=64)))
+    sm = sem.mask_for_tf(sem.extract_segmentation_masks(synth.label_image(H, W, K, 10, cell=64)))
+    if world > 1:
+        job = tiled.TiledStyleTransfer(content, style, hp, cm, sm, synth.vgg_weights(), rank, world)
+    else:
+        job = tiled.TiledStyleTransfer(content, style, hp, cm, sm, synth.vgg_weights(), 0, 1, reduce_sum=lambda t: None,
+                                       gather=lambda s: [s])
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+    for _ in range(max(args.warmup, 3)):
+        d = job.step()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier(); e0.record()
+    for _ in range(args.steps):
+        d = job.step()
+    e1.record(); barrier()
+    ms = torch.tensor([e0.elapsed_time(e1)], device="cuda")
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    if rank == 0:
+        t = job.tile
+        print(json.dumps({"metric": "adam_iters_per_sec_%dx%d_spatially_tiled" % (W, H), "value": args.steps / (float(ms) * 1e-3),
+                          "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+                          "ms_per_step": float(ms) / args.steps, "higher_is_better": True, "scaling": "strong",
+                          "vs_baseline": None, "dtype": "f32 + f64 (Laplacian arithmetic)", "data": "synthetic",
+                          "config": {"workload": "configs[3]: one %dx%d image, %d classes, column strips of %d px + %d px halo per "
+                                                 "interior side (local width %d), Gram all-reduce + strip all-gather per step"
+                                                 % (W, H, K, W // world, tiled.HALO, t.local_w)},
+                          "final_total_loss": float(d["Total loss"])}))
+    if world > 1:
+        dist.barrier(); dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -365,9 +414,14 @@ def main():
     ap.add_argument("--size", type=int, default=1024)
     ap.add_argument("--classes", type=int, default=8)
     ap.add_argument("--no-cpu-baseline", dest="no_cpu_baseline", action="store_true")
+    ap.add_argument("--tiled", action="store_true", help="configs[3]: one large image tiled spatially over the GPUs")
+    ap.add_argument("--tiled-h", dest="tiled_h", type=int, default=2160)
+    ap.add_argument("--tiled-w", dest="tiled_w", type=int, default=3840)
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
+    elif args.tiled:
+        run_tiled(args)
     else:
         run_ours(args)
 

@@ -58,6 +58,10 @@ void adpst_laplacian_destroy(adpst_laplacian* h);
 int adpst_laplacian_matvec(adpst_laplacian* h, const void* x_dev, void* y_dev, double y_scale,
                            double* xLx_dev, adpst_stream_t stream);
 
+/* Spatially tiled runs (one image split into column strips with halos): restrict the scalar x^T L x to columns
+ * [col_lo, col_hi) of the local strip; y is still produced for every column.  (0,0) restores the full sum. */
+int adpst_laplacian_set_quadratic_window(adpst_laplacian* h, int col_lo, int col_hi);
+
 /* matting_v2.py:49-52: window means (H,W,3) and regularised inverse covariances (H,W,3,3), io_dtype. */
 int adpst_laplacian_coefficients(adpst_laplacian* h, void* means_dev, void* delta_inv_dev, adpst_stream_t stream);
 
@@ -141,17 +145,20 @@ int adpst_gram_masked(const float* F_dev, int h, int w, int C, const float* mask
  * G_dev is the transfer Gram from adpst_gram_masked on the same F / masks; A_dev the style Gram.
  * loss_scale carries the 1/len(args) of loss.py:85, grad_scale additionally the style weight.
  * F is the (h,w,C) feature map; path: 0 = tcgen05 3xTF32 kernel (8x16-pixel tiles, classes absent from a tile skipped),
- * 1 = exact-float32 CUDA-core kernel (validation). */
+ * 1 = exact-float32 CUDA-core kernel (validation).  hw_norm > 0 replaces h*w in the normaliser (spatially tiled runs:
+ * the pixel count of the whole image). */
 int adpst_style_layer_backward(const float* F_dev, int h, int w, int C, const float* masks_dev, int K,
                                const float* G_dev, const float* A_dev, double loss_scale, double grad_scale,
-                               double* loss_dev, float* dF_dev, int accumulate, int path, void* workspace_dev,
-                               adpst_stream_t stream);
+                               double* loss_dev, float* dF_dev, int accumulate, int path, double hw_norm,
+                               void* workspace_dev, adpst_stream_t stream);
 
 /* loss.py:90-92 with L = mean((target - output)^2):
- *   *loss_dev += loss_scale * L;   dOut (=|+=) grad_scale * 2 (output - target) / n. */
+ *   *loss_dev += loss_scale * L;   dOut (=|+=) grad_scale * 2 (output - target) / n.
+ * Spatially tiled runs: n_norm > 0 replaces n (element count of the whole layer) and, with w > 0, the scalar sums only
+ * columns [col_lo, col_hi) of the (.., w, C) map; pass 0, 0, 0, 0, 0 otherwise. */
 int adpst_content_layer(const float* target_dev, const float* output_dev, size_t n, double loss_scale,
-                        double grad_scale, double* loss_dev, float* dOut_dev, int accumulate,
-                        adpst_stream_t stream);
+                        double grad_scale, double* loss_dev, float* dOut_dev, int accumulate, double n_norm, int w, int C,
+                        int col_lo, int col_hi, adpst_stream_t stream);
 
 /* loss.py:72-76: acc_dev = float64 {content, style, photo} (unweighted);  out_dev = float32
  * {content, style, nima (0), photo, total = sum w_i * loss_i}.  One tiny launch, keeps the step graph-replayable. */

@@ -1,0 +1,59 @@
+"""GPU: one image split into column strips (spatial tiling, BASELINE configs[3]) must reproduce the single-device
+optimisation: same loss values, same updated image.  The ranks are emulated inside one process (reductions = plain sums);
+the NCCL path uses the same phases and is exercised by bench.py --tiled on >= 2 GPUs."""
+import argparse
+import importlib
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import PKG_NAME
+
+pytestmark = pytest.mark.gpu
+
+
+def _m(name):
+    return importlib.import_module(PKG_NAME + "." + name)
+
+
+def _args():
+    return argparse.Namespace(content_weight=1.0, style_weight=100.0, nima_weight=0.0, regularization_weight=1e4,
+                              matting_epsilon=1e-7, matting_window_radius=1, adam_lr=0.1, adam_beta1=0.9, adam_beta2=0.999,
+                              adam_epsilon=1e-8)
+
+
+@pytest.mark.parametrize("world,W,K", [(2, 512, 3), (4, 640, 0)])
+def test_tiled_matches_single_device(world, W, K, synth):
+    st, tiled, vgg, lossm, sem = _m("style_transfer"), _m("tiled"), _m("components.VGG19.model"), _m("components.loss"), \
+        _m("components.semantic_merge")
+    H = 48
+    args = _args()
+    weights = synth.vgg_weights(seed=5)
+    content, style = synth.image(H, W, 0), synth.image(H, W, 1)
+    cm = sm = None
+    if K:
+        cm = sem.mask_for_tf(sem.extract_segmentation_masks(synth.label_image(H, W, K, 9, cell=16)))
+        sm = sem.mask_for_tf(sem.extract_segmentation_masks(synth.label_image(H, W, K, 10, cell=16)))
+    # single-device reference run (same kernels, whole image)
+    ext = vgg.StyleContentModel(st.CONTENT_LAYERS, st.STYLE_LAYERS, weights=weights)
+    c_dev, s_dev = torch.as_tensor(content).cuda(), torch.as_tensor(style).cuda()
+    loss = lossm.Loss(ext(c_dev)["content"], ext(s_dev)["style"], args, cm, sm)
+    loss.initialize_matting_laplacian(c_dev[0].double())
+    step = st.make_train_step(ext, loss, st.Adam(args.adam_lr, args.adam_beta1, args.adam_beta2, args.adam_epsilon))
+    x = c_dev.clone()
+    ref = [{k: float(v) for k, v in step(x).items()} for _ in range(3)]
+    # tiled run, ranks emulated in this process
+    ranks = [tiled.TiledStyleTransfer(content, style, args, cm, sm, weights, r, world, reduce_sum=lambda t: None,
+                                      gather=lambda s: None) for r in range(world)]
+    got = tiled.run_emulated(ranks, 3)
+    for it in range(3):
+        for name, v in ref[it].items():
+            assert abs(got[it][name] - v) <= 2e-5 * abs(v) + 1e-9, (it, name, got[it][name], v)
+    stitched = torch.cat([r.own_strip() for r in ranks], dim=1)
+    diff = (stitched - x[0]).abs()
+    assert float((diff > 1e-3).float().mean()) < 1e-3          # Adam steps of +-lr: count flips, do not take the max
+    # every rank's halo holds the neighbours' updated pixels
+    for r in ranks:
+        t = r.tile
+        assert float((r.image[0] - x[0, :, t.ext_lo:t.ext_hi]).abs().gt(1e-3).float().mean()) < 1e-3

@@ -86,3 +86,22 @@ def test_reference_arm_non_zero_ranks_exit_quietly():
     r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2"],
                        env=env, capture_output=True, text=True, timeout=120)
     assert r.returncode == 0 and r.stdout.strip() == ""
+
+
+def test_tile_geometry():
+    """Spatial tiling (BASELINE configs[3]): strip / halo arithmetic, CPU only."""
+    tiled = importlib.import_module(PKG_NAME + ".tiled")
+    t = tiled.Tile(3840, 3, 8)
+    assert (t.own_lo, t.own_hi, t.ext_lo, t.ext_hi, t.local_w) == (1440, 1920, 1280, 2080, 800)
+    assert t.own_cols(800) == (160, 640) and t.own_cols(50) == (10, 40) and t.global_cols(50) == 240
+    t0 = tiled.Tile(3840, 0, 8)
+    assert (t0.ext_lo, t0.ext_hi) == (0, 640) and t0.own_cols(640) == (0, 480)
+    with pytest.raises(ValueError):
+        tiled.Tile(1000, 0, 8)
+    # every pixel is owned by exactly one rank and every halo is twice the block5_conv1 receptive-field radius
+    owned = np.zeros(3840, int)
+    for r in range(8):
+        tr = tiled.Tile(3840, r, 8)
+        owned[tr.own_lo:tr.own_hi] += 1
+        assert tr.own_lo - tr.ext_lo in (0, tiled.HALO) and tr.ext_hi - tr.own_hi in (0, tiled.HALO)
+    assert (owned == 1).all() and tiled.HALO >= 2 * 78 and tiled.HALO % 16 == 0
