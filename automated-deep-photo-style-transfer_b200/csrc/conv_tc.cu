@@ -20,9 +20,9 @@
 //   is a TMEM address), not shared memory.
 // The dropped a_lo*b_lo term and the tf32 rounding of the lo parts are O(2^-22) relative.
 //
-// Warp roles (320 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer (one elected lane),
-// warps 2..5 = operand transform (A hi/lo split), warps 6..9 = chunk promotion TMEM -> registers, then the epilogue
-// (bias/ReLU or seed/mask -> global).  mbarrier rings: full (TMA landed) -> ready (A split done) -> empty (MMAs retired),
+// Warp roles (352 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer for the big term, warp 10 = MMA
+// issuer for the small terms, warps 2..5 = operand transform (A hi/lo split into tensor memory), warps 6..9 = chunk
+// promotion TMEM -> registers, then the epilogue (bias/ReLU or seed/mask -> global).  mbarrier rings: full (TMA landed) -> ready (A split done) -> empty (MMAs retired),
 // chunk_full / chunk_empty for the two TMEM chunk buffers.
 #include <stdlib.h>
 
@@ -76,7 +76,7 @@ int make_tensor_map_f32(CUtensorMap* out, const void* base, int rank, const uint
 // ---------------------------------------------------------------------------------------------------------------
 constexpr int TC_TH = 8, TC_TW = 16, TC_BM = TC_TH * TC_TW;     // 128 pixels = UMMA M
 constexpr int TC_BK = 32;                                        // 32 fp32 = one 128-byte swizzle row
-constexpr int TC_THREADS = 320;                                  // TMA, MMA, 4 transform warps, 4 drain/epilogue warps
+constexpr int TC_THREADS = 352;                                  // TMA, MMA(big), 4 transform, 4 drain/epilogue, MMA(small)
 constexpr int TC_A_BYTES = TC_BM * TC_BK * 4;                    // 16 KB
 constexpr int TC_CHUNK_ITERS = 2;                                // stages per promoted chunk (8 big MMAs)
 constexpr int TC_MAX_CLASSES = 32;                               // style mode: classes per launch (active set is a bit mask)
@@ -156,15 +156,15 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         for (int s = 0; s < STAGES; ++s) {
             tc::mbar_init(&full[s], 1);
             tc::mbar_init(&ready[s], 128 + 1);      // 128 transform threads + the producer's expect_tx arrival (B bytes)
-            tc::mbar_init(&empty[s], 1);
+            tc::mbar_init(&empty[s], 2);            // both MMA-issuing warps commit
         }
         for (int b = 0; b < 2; ++b) {
             tc::mbar_init(&chunk_full[b], 1);
             tc::mbar_init(&chunk_empty[b], 128);
         }
         tc::mbar_init(small_full, 1);
-        tc::mbar_init(&a_free[0], 1);
-        tc::mbar_init(&a_free[1], 1);
+        tc::mbar_init(&a_free[0], 2);
+        tc::mbar_init(&a_free[1], 2);
         tc::fence_barrier_init();
         tc::tma_prefetch_desc(&tmA);
         tc::tma_prefetch_desc(&tmBhi);
@@ -203,45 +203,64 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             }
         }
     } else if (warp == 1) {
-        // ================= MMA issuer =================
-        // The whole warp runs the loop (warp-uniform control flow, descriptors live in uniform registers); one elected
-        // lane issues.  Descriptors are built once: per stage and K-step only the 14-bit address field changes.
+        // ================= MMA issuer, big term =================
+        // Issuing one tcgen05.mma costs the issuing thread 40-48 clk (measured, tests/cuda/umma_queue_probe.cu) while a
+        // 128x128x8 TF32 MMA executes in 64 clk, so ONE thread that also has ~240 clk of barrier work per stage cannot
+        // keep the pipe fed with 12 MMAs per stage.  The issue is therefore split over two warps that own DIFFERENT
+        // accumulators (no cross-thread ordering needed): this warp issues a_hi*b_hi into the chunk buffers, warp 10
+        // issues the two small terms.  Both commit to empty[] / a_free[] (arrival count 2).
+        // The whole warp runs the loop (warp-uniform control flow, descriptors in uniform registers); one elected lane
+        // issues.  Descriptors are built once: per stage and K-step only the 14-bit address field changes.
+        constexpr uint32_t idesc = tc::umma_idesc_tf32(TC_BM, BN);
+        const uint32_t stage0 = tc::smem_u32(smem);
+        const uint64_t d_bhi = tc::umma_desc_kmajor_sw128(stage0 + TC_A_BYTES, 1024);
+        int s = 0, round = 0;
+        for (int it = 0; it < iters; ++it) {
+            const int c = it / chunk_iters, cpos = it - c * chunk_iters;
+            const uint32_t tmem_big = tmem_base + uint32_t(c & 1) * BN;
+            const uint32_t a_hi = tmem_a + uint32_t(it & 1) * 64;
+            if (cpos == 0) {                                          // TMEM buffer must have been drained
+                tc::mbar_wait(&chunk_empty[c & 1], ((c >> 1) & 1) ^ 1);
+            }
+            // ONE wait per stage: ready[s] completes when the B tiles have landed (transaction bytes) and the 128 transform
+            // threads have stored A hi/lo into tensor memory.
+            tc::mbar_wait(&ready[s], round & 1);
+            tc::tcgen05_fence_after();
+            const uint64_t soff = uint64_t(uint32_t(s) * uint32_t(Cfg::STAGE_BYTES >> 4));
+            if (tc::elect_one_sync()) {
+#pragma unroll
+                for (int k = 0; k < TC_BK / 8; ++k)                   // UMMA K = 8: 8 TMEM columns of A, 32 bytes of each B row
+                    tc::umma_tf32_ts(tmem_big, a_hi + k * 8, d_bhi + soff + uint64_t(k * 2), idesc, (cpos | k) != 0);
+                tc::umma_commit(&empty[s]);
+                tc::umma_commit(&a_free[it & 1]);
+                if (cpos == chunk_iters - 1 || it == iters - 1) tc::umma_commit(&chunk_full[c & 1]);
+            }
+            __syncwarp();
+            if (++s == STAGES) { s = 0; ++round; }
+        }
+    } else if (warp == 10) {
+        // ================= MMA issuer, small terms: a_lo*b_hi + a_hi*b_lo into the tile-long accumulator =================
         constexpr uint32_t idesc = tc::umma_idesc_tf32(TC_BM, BN);
         const uint32_t stage0 = tc::smem_u32(smem);
         const uint64_t d_bhi = tc::umma_desc_kmajor_sw128(stage0 + TC_A_BYTES, 1024);
         const uint64_t d_blo = tc::umma_desc_kmajor_sw128(stage0 + TC_A_BYTES + Cfg::B_BYTES, 1024);
         int s = 0, round = 0;
         for (int it = 0; it < iters; ++it) {
-            const int c = it / chunk_iters, cpos = it - c * chunk_iters;
-            const uint32_t tmem_big = tmem_base + uint32_t(c & 1) * BN;
             const uint32_t a_hi = tmem_a + uint32_t(it & 1) * 64, a_lo = a_hi + 32;
-            if (cpos == 0) {                                          // TMEM buffer must have been drained
-                tc::mbar_wait(&chunk_empty[c & 1], ((c >> 1) & 1) ^ 1);
-            }
-            // ONE wait per stage: ready[s] completes when the B tiles have landed (transaction bytes) and the 128 transform
-            // threads have stored A hi/lo into tensor memory.  Every poll here is time the tensor pipe may idle.
-            long long tr0 = 0, tr1 = 0;
-            if (trace) tr0 = clock64();
             tc::mbar_wait(&ready[s], round & 1);
-            if (trace) tr1 = clock64();
             tc::tcgen05_fence_after();
             const uint64_t soff = uint64_t(uint32_t(s) * uint32_t(Cfg::STAGE_BYTES >> 4));
             if (tc::elect_one_sync()) {
 #pragma unroll
-                for (int k = 0; k < TC_BK / 8; ++k) {                 // UMMA K = 8: 8 TMEM columns of A, 32 bytes of each B row
-                    const uint64_t koff = soff + uint64_t(k * 2);     // (k * 32 bytes) >> 4
+                for (int k = 0; k < TC_BK / 8; ++k) {
+                    const uint64_t koff = soff + uint64_t(k * 2);
                     tc::umma_tf32_ts(tmem_small, a_lo + k * 8, d_bhi + koff, idesc, (it | k) != 0);
                     tc::umma_tf32_ts(tmem_small, a_hi + k * 8, d_blo + koff, idesc, 1);
-                    tc::umma_tf32_ts(tmem_big, a_hi + k * 8, d_bhi + koff, idesc, (cpos | k) != 0);
                 }
                 tc::umma_commit(&empty[s]);
                 tc::umma_commit(&a_free[it & 1]);
-                if (cpos == chunk_iters - 1 || it == iters - 1) tc::umma_commit(&chunk_full[c & 1]);
             }
             __syncwarp();
-            if (trace && lane == 0 && it < 1000) {
-                dbg[2 * 4096 + it * 4] = tr0; dbg[2 * 4096 + it * 4 + 1] = tr1; dbg[2 * 4096 + it * 4 + 2] = clock64();
-            }
             if (++s == STAGES) { s = 0; ++round; }
         }
         if (iters > 0 && tc::elect_one_sync()) tc::umma_commit(small_full);
@@ -289,7 +308,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             tc::mbar_arrive(&ready[s]);
             if (++s == STAGES) { s = 0; ++round; }
         }
-    } else {
+    } else if (warp < 10) {
         // ================= drain (chunk promotion) + epilogue =================
         const int q = warp & 3;                                        // TMEM lane quarter this warp may read
         const uint32_t lane_base = uint32_t(q * 32) << 16;

@@ -11,13 +11,23 @@ __global__ void pat(long long* out, int iters, const __grid_constant__ CUtensorM
     uint8_t* smem = (uint8_t*)(((uintptr_t)raw + 1023) & ~uintptr_t(1023));
     __shared__ uint64_t bar, bar2, tbar;
     __shared__ uint32_t slot;
-    for (int i = threadIdx.x; i < 49152 / 4; i += blockDim.x) ((float*)smem)[i] = 1.0f;
+    for (int i = threadIdx.x; i < 49152 / 4; i += blockDim.x) {
+        unsigned h = (i + blockIdx.x * 7919u) * 2654435761u; h ^= h >> 13; h *= 0x5bd1e995u; h ^= h >> 15;
+        ((float*)smem)[i] = (BG == 7) ? __uint_as_float((h & 0x007FE000u) | 0x3F800000u) - 1.5f : 1.0f;   // BG 7: random tf32 operands
+    }
     if (threadIdx.x == 0) { mbar_init(&bar, 1); mbar_init(&bar2, 1 << 20); mbar_init(&tbar, 1); fence_barrier_init(); }
     fence_proxy_async_smem();
     if (threadIdx.x < 32) tmem_alloc(&slot, 512);
     tcgen05_fence_before(); __syncthreads(); tcgen05_fence_after();
     const uint32_t tm = slot;
     const uint32_t big = tm, small = tm + 256, a_hi = tm + 384, a_lo = tm + 416;
+    if (BG == 7 && threadIdx.x < 128) {      // random A operand in tensor memory too
+        uint32_t v[32]; for (int j = 0; j < 32; ++j) { unsigned h = (threadIdx.x * 33u + j + blockIdx.x) * 2654435761u; h ^= h >> 13; v[j] = (h & 0x007FE000u) | 0x3F000000u; }
+        const uint32_t lb = uint32_t((threadIdx.x >> 5) * 32) << 16;
+        tmem_st_32x32(tm + 384 + lb, v); tmem_st_32x32(tm + 416 + lb, v); tmem_st_32x32(tm + 448 + lb, v); tmem_st_32x32(tm + 480 + lb, v); tmem_st_wait();
+        tcgen05_fence_before();
+    }
+    __syncthreads(); tcgen05_fence_after();
     __shared__ volatile int stop;
     if (threadIdx.x == 0) stop = 0;
     __syncthreads();
@@ -105,6 +115,6 @@ int main() {
     CUresult r = cuTensorMapEncodeTiled(&tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, g, dims, str, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
                                         CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     printf("encode %d\n", int(r));
-    run<0, 0>(d, tm); run<0, 5>(d, tm);
+    run<0, 0>(d, tm); run<0, 7>(d, tm);
     return 0;
 }

@@ -3,6 +3,7 @@
 #include "../../automated-deep-photo-style-transfer_b200/csrc/tc_common.cuh"
 using namespace adpst::tc;
 
+template <int MODE>   // 0: SS one accumulator, 1: TS one accumulator, 2: TS small/small/big, 3: SS small/small/big
 __global__ void q(long long* out) {
     extern __shared__ uint8_t raw[];
     uint8_t* smem = (uint8_t*)(((uintptr_t)raw + 1023) & ~uintptr_t(1023));
@@ -21,7 +22,11 @@ __global__ void q(long long* out) {
             long long t0 = clock64(), t1 = 0;
             if (elect_one_sync()) {
 #pragma unroll 1
-                for (int i = 0; i < n; ++i) umma_tf32(tm, da + uint64_t((i & 3) * 2), db + uint64_t((i & 3) * 2), idesc, 1);
+                for (int i = 0; i < n; ++i) {
+                    const uint32_t acc = (MODE >= 2) ? ((i % 3 == 2) ? tm : tm + 256) : tm;
+                    if (MODE == 1 || MODE == 2) umma_tf32_ts(acc, tm + 384 + (i & 3) * 8, db + uint64_t((i & 3) * 2), idesc, 1);
+                    else umma_tf32(acc, da + uint64_t((i & 3) * 2), db + uint64_t((i & 3) * 2), idesc, 1);
+                }
                 t1 = clock64();
                 umma_commit(&bar[n]);
             }
@@ -37,9 +42,12 @@ __global__ void q(long long* out) {
 }
 int main() {
     long long* d; cudaMalloc(&d, 8 * 64); cudaMemset(d, 0, 8 * 64);
-    cudaFuncSetAttribute(q, cudaFuncAttributeMaxDynamicSharedMemorySize, 40000);
-    q<<<1, 128, 40000>>>(d); printf("%s\n", cudaGetErrorString(cudaDeviceSynchronize()));
-    long long h[64]; cudaMemcpy(h, d, sizeof(h), cudaMemcpyDeviceToHost);
-    for (int n = 1; n <= 16; ++n) printf("n=%2d issue %5lld clk, complete %5lld clk\n", n, h[n * 2], h[n * 2 + 1]);
+    long long h[4][64];
+    cudaFuncSetAttribute(q<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 40000); q<0><<<1, 128, 40000>>>(d); cudaDeviceSynchronize(); cudaMemcpy(h[0], d, sizeof(h[0]), cudaMemcpyDeviceToHost);
+    cudaFuncSetAttribute(q<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 40000); q<1><<<1, 128, 40000>>>(d); cudaDeviceSynchronize(); cudaMemcpy(h[1], d, sizeof(h[0]), cudaMemcpyDeviceToHost);
+    cudaFuncSetAttribute(q<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 40000); q<2><<<1, 128, 40000>>>(d); cudaDeviceSynchronize(); cudaMemcpy(h[2], d, sizeof(h[0]), cudaMemcpyDeviceToHost);
+    cudaFuncSetAttribute(q<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 40000); q<3><<<1, 128, 40000>>>(d); printf("%s\n", cudaGetErrorString(cudaDeviceSynchronize())); cudaMemcpy(h[3], d, sizeof(h[0]), cudaMemcpyDeviceToHost);
+    printf("issue time (clk) for n MMAs: SS-1acc  TS-1acc  TS-3acc  SS-3acc\n");
+    for (int n = 1; n <= 16; ++n) printf("n=%2d  %6lld %6lld %6lld %6lld\n", n, h[0][n * 2], h[1][n * 2], h[2][n * 2], h[3][n * 2]);
     return 0;
 }
