@@ -6,6 +6,7 @@ tape; `backward(seeds)` plays the role of tape.gradient (style_transfer.py:341) 
 """
 import ctypes
 import os
+import weakref
 
 import numpy as np
 import torch
@@ -58,12 +59,17 @@ class VGG19Handle:
                                                    ctypes.byref(h)))
             torch.cuda.current_stream().synchronize()        # ks / bs may be freed after this
         self._h = h
+        self.generation = 0              # forward passes run on this handle (its max|activation| slots describe the latest)
         if os.environ.get("ADPST_CONV_PATH", "").lower() == "simt":      # validation switch: exact-fp32 CUDA-core kernels
             self.set_conv_path("simt")
 
     def set_conv_path(self, path):
-        """'tensor' (default: tcgen05 3xTF32 implicit GEMM) or 'simt' (exact float32 CUDA-core kernels, validation)."""
+        """'tensor' (default: tcgen05 3xFP16 implicit GEMM) or 'simt' (exact float32 CUDA-core kernels, validation)."""
         _lib.check(_lib.lib().adpst_vgg_set_conv_path(self._h, {"tensor": 0, "simt": 1}[path]))
+
+    def act_absmax_ptr(self, i):
+        """Device address of the slot holding max|conv i output| of the latest forward pass."""
+        return _lib.lib().adpst_vgg_act_absmax(self._h, i)
 
     def __del__(self):
         h, self._h = getattr(self, "_h", None), None
@@ -154,8 +160,11 @@ class StyleContentModel:
             _lib.check(_lib.lib().adpst_vgg_forward(self.vgg._h, _lib.ptr(x), H, W, _lib.ptr_array(A.acts),
                                                     _lib.ptr_array(A.pools), self.last_index, _lib.stream_ptr()))
         self.last = A
+        self.vgg.generation += 1
         names = self.content_layers + self.style_layers
         outs = [A.acts[i] for i in self.indices]
+        for i, o in zip(self.indices, outs):                                  # see kernels.act_absmax_slot
+            o._adpst_absmax = (weakref.ref(self.vgg), self.vgg.generation, i)
         content = {n: o for n, o in zip(names[:self.limit], outs[:self.limit])}
         style = {n: o for n, o in zip(names[self.limit:], outs[self.limit:])}
         return {"content": content, "style": style}

@@ -181,7 +181,7 @@ class Loss:
             dF = seeds[name] if shared else st["seed"]
             kernels.style_layer_backward(out.reshape(h, w, C), st["masks"], st["K"], st["G"], st["A"], 1.0 / n_args,
                                          wts['style'] / n_args, self._acc[1:2], dF.reshape(h * w, C), accumulate=shared,
-                                         workspace=st["ws"], hw_norm=st["hw_norm"])
+                                         workspace=st["ws"], hw_norm=st["hw_norm"], f_absmax=kernels.act_absmax_slot(out))
             seeds[name] = dF
         kernels.loss_finalize(self._acc, wts['content'], wts['style'], wts['photo'], self._out)   # loss.py:72
         self._seeds = seeds

@@ -9,6 +9,7 @@
 //   forward : G_k[c1,c2] = sum_px m_k[px]^2 F[px,c1] F[px,c2]   (upper-triangular 64x64 tiles, split over pixels,
 //             partials reduced in float64 in a fixed order -> deterministic)
 //   backward: D_k = 2 s / (C^4 HW^2) (G_k - A_k);   dF[px,:] = sum_k m_k[px]^2 F[px,:] D_k
+#include <cuda_fp16.h>
 #include "tc_common.cuh"
 #include "vgg.cuh"
 
@@ -128,21 +129,34 @@ gram_reduce_kernel(const float* __restrict__ ws, float* __restrict__ G, int C, i
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 style_diff_kernel(const float* __restrict__ G, const float* __restrict__ A, float* __restrict__ D, size_t n, double coef,
-                  double loss_coef, double* __restrict__ loss) {
+                  double loss_coef, double* __restrict__ loss, uint32_t* __restrict__ d_absmax) {
     __shared__ double red[32];
     double acc = 0.0;
-    // D | D_hi | D_lo: the float32 matrix for the CUDA-core kernel and its TF32 hi/lo split for the tensor-core kernel
+    float amax = 0.f;
     for (size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += size_t(gridDim.x) * blockDim.x) {
         const double d = double(G[i]) - double(A[i]);
         acc += d * d;
         const float v = float(coef * d);
-        const float h = tc::round_tf32(v);
         D[i] = v;
-        D[n + i] = h;
-        D[2 * n + i] = tc::round_tf32(v - h);
+        amax = fmaxf(amax, fabsf(v));
     }
+    const uint32_t wm = __reduce_max_sync(0xffffffffu, __float_as_uint(amax));     // for the FP16 scale (tc_common.cuh)
+    if ((threadIdx.x & 31) == 0 && wm != 0u) atomicMax(d_absmax, wm);
     acc = block_sum<double>(acc, red);
     if (threadIdx.x == 0 && loss) atomicAdd(loss, acc * loss_coef);
+}
+
+// FP16 hi / lo planes of D for the tensor-core kernel, scaled by the power of two of max|D|
+__global__ void __launch_bounds__(256)
+style_split_kernel(const float* __restrict__ D, __half* __restrict__ hi, __half* __restrict__ lo, size_t n,
+                   const uint32_t* __restrict__ d_absmax) {
+    const float sd = tc::pow2f_int(tc::f16_scale_exponent(*d_absmax));
+    for (size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += size_t(gridDim.x) * blockDim.x) {
+        const float t = D[i] * sd;
+        const __half h = __float2half_rn(t);
+        hi[i] = h;
+        lo[i] = __float2half_rn((t - __half2float(h)) * 2048.0f);
+    }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -221,7 +235,7 @@ size_t adpst_gram_workspace_bytes(int HW, int C, int K) {
     int splits = gram_splits(HW, C, K);
     if (gram_tc_eligible(C) && gram_splits_tc(C, K) > splits) splits = gram_splits_tc(C, K);
     const size_t partials = size_t(K) * splits * C * C * sizeof(float);
-    const size_t dmat = size_t(3) * K * C * C * sizeof(float);     // D, D_hi, D_lo
+    const size_t dmat = size_t(3) * K * C * C * sizeof(float);     // D (fp32), D_hi, D_lo (fp16), two scale slots
     return partials > dmat ? partials : dmat;
 }
 
@@ -257,7 +271,8 @@ int adpst_gram_masked(const float* F_dev, int h, int w, int C, const float* mask
 
 int adpst_style_layer_backward(const float* F_dev, int h, int w, int C, const float* masks_dev, int K, const float* G_dev,
                                const float* A_dev, double loss_scale, double grad_scale, double* loss_dev, float* dF_dev,
-                               int accumulate, int path, double hw_norm, void* workspace_dev, adpst_stream_t stream) {
+                               int accumulate, int path, double hw_norm, const uint32_t* F_absmax_dev, void* workspace_dev,
+                               adpst_stream_t stream) {
     using namespace adpst;
     ADPST_REQUIRE(F_dev && G_dev && A_dev && workspace_dev, "style_layer_backward: NULL argument");
     ADPST_REQUIRE(h > 0 && w > 0 && K > 0, "style_layer_backward: empty input");
@@ -271,13 +286,26 @@ int adpst_style_layer_backward(const float* F_dev, int h, int w, int C, const fl
     const double coef = 2.0 * grad_scale / (c2 * c2 * hw2);        // D_k = coef (G_k - A_k)
     const double loss_coef = loss_scale / (2.0 * c2 * c2 * hw2);   // L = sum_k sum (G_k - A_k)^2 / (2 C^4 HW^2)
     const size_t n = size_t(K) * C * C;
+    // workspace: D (n float32) | D_hi (n fp16) | D_lo (n fp16) | slot: max|D| | slot: max|F| (when the caller has none)
     float* D = static_cast<float*>(workspace_dev);
-    style_diff_kernel<<<unsigned((n + 255) / 256 < 1024 ? (n + 255) / 256 : 1024), 256, 0, st>>>(G_dev, A_dev, D, n, coef,
-                                                                                               loss_coef, loss_dev);
+    __half* Dhi = reinterpret_cast<__half*>(D + n);
+    __half* Dlo = Dhi + n;
+    uint32_t* slots = reinterpret_cast<uint32_t*>(D + 2 * n);
+    const unsigned dgrid = unsigned((n + 255) / 256 < 1024 ? (n + 255) / 256 : 1024);
+    ADPST_CUDA_CHECK(cudaMemsetAsync(slots, 0, sizeof(uint32_t), st));
+    style_diff_kernel<<<dgrid, 256, 0, st>>>(G_dev, A_dev, D, n, coef, loss_coef, loss_dev, slots);
     ADPST_LAUNCH_CHECK();
     if (dF_dev) {
-        if (path == CONV_PATH_TENSOR && style_tc_eligible(C) && K <= 32)
-            return launch_style_dF_tc(F_dev, h, w, C, masks_dev, K, D + n, D + 2 * n, dF_dev, accumulate, st);
+        if (path == CONV_PATH_TENSOR && style_tc_eligible(C) && K <= 32) {
+            style_split_kernel<<<dgrid, 256, 0, st>>>(D, Dhi, Dlo, n, slots);
+            ADPST_LAUNCH_CHECK();
+            if (F_absmax_dev == nullptr) {
+                int rc = launch_absmax(F_dev, size_t(HW) * C, slots + 1, st);
+                if (rc != ADPST_OK) return rc;
+                F_absmax_dev = slots + 1;
+            }
+            return launch_style_dF_tc(F_dev, h, w, C, masks_dev, K, Dhi, Dlo, F_absmax_dev, slots, dF_dev, accumulate, st);
+        }
         dim3 grid((HW + GT - 1) / GT, C / GT);
         style_dF_kernel<<<grid, GTHREADS, 0, st>>>(F_dev, masks_dev, D, dF_dev, HW, C, K, accumulate);
         ADPST_LAUNCH_CHECK();

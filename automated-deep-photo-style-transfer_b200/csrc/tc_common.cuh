@@ -116,6 +116,15 @@ __device__ __forceinline__ void tmem_st_32x32(uint32_t taddr, const uint32_t (&v
         "r"(v[28]), "r"(v[29]), "r"(v[30]), "r"(v[31])
         : "memory");
 }
+// Store 16 consecutive 32-bit columns of this thread's TMEM lane.
+__device__ __forceinline__ void tmem_st_32x16(uint32_t taddr, const uint32_t (&v)[16]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(taddr),
+        "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]),
+        "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15])
+        : "memory");
+}
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
@@ -151,9 +160,42 @@ __device__ __forceinline__ void umma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, u
         "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate)
         : "memory");
 }
+// Instruction descriptor for kind::f16 with both operands FP16 (format 0), fp32 accumulate, both operands K-major.
+__host__ __device__ constexpr uint32_t umma_idesc_f16(int M, int N) {
+    return (1u << 4) | (0u << 7) | (0u << 10) | (uint32_t(N >> 3) << 17) | (uint32_t(M >> 4) << 24);
+}
+// kind::f16, A operand in tensor memory: lane = row of A, 8 consecutive 32-bit columns = 16 packed fp16 (the K slice;
+// element k sits in column k/2, bits 16*(k%2)..), B from shared memory.
+__device__ __forceinline__ void umma_f16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{ .reg .pred p; setp.ne.b32 p, %4, 0; tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p; }" ::"r"(tmem_d),
+        "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
 // All previously issued MMAs of this thread arrive on `bar` when they retire (implies fence::before_thread_sync).
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+// ---- FP16 operand splitting ("3xFP16": a*b = ah*bh + ah*bl + al*bh with fp32 accumulation) ------------------------
+// A float32 tensor whose largest magnitude is known is mapped into FP16's range by a power-of-two scale s chosen so that
+// 2^14 <= max|a| * s < 2^15.  Then  t = a*s (exact),  hi = fp16_rn(t) (11 significant bits, like TF32),
+// lo = fp16_rn((t - hi) * 2^11) (t - hi is exact in fp32; the 2^11 keeps lo out of the subnormal range), so
+// a*s = hi + lo * 2^-11 to 22 bits.  Values below 2^-29 of the tensor's maximum lose RELATIVE precision (fp16 subnormals)
+// but their absolute error stays below 2^-50 of the maximum.  The accumulators are rescaled by powers of two (exact).
+// `bits` = float bits of max|a| (non-negative floats order like unsigned integers, so the producers use atomicMax).
+__host__ __device__ __forceinline__ int f16_scale_exponent(uint32_t absmax_bits) {
+    const int E = int(absmax_bits >> 23) & 0xFF;          // max = 1.m * 2^(E-127)
+    if (E == 0) return 0;                                   // all-zero (or subnormal) tensor: s = 1
+    int e = 14 - (E - 127);
+    return e > 60 ? 60 : (e < -60 ? -60 : e);              // |e_a + e_b| <= 120: one exact fp32 rescale at the end
+}
+__host__ __device__ __forceinline__ float pow2f_int(int e) {  // 2^e, |e| <= 126
+#ifdef __CUDA_ARCH__
+    return __uint_as_float(uint32_t(e + 127) << 23);
+#else
+    union { uint32_t u; float f; } c; c.u = uint32_t(e + 127) << 23; return c.f;
+#endif
 }
 
 // ---- host: tensor maps --------------------------------------------------------------------------------------------
@@ -164,6 +206,9 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
 EncodeTiledFn encode_tiled_fn();
 // fp32 tensor, `rank` dims (innermost first), byte strides for dims 1..rank-1, 128B swizzle, zero fill out of bounds.
 int make_tensor_map_f32(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                        const uint32_t* box);
+// same for an fp16 tensor (the box's innermost extent must be 64 elements = one 128-byte swizzle row)
+int make_tensor_map_f16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
                         const uint32_t* box);
 
 }  // namespace tc

@@ -213,6 +213,14 @@ conv1_dgrad_image_kernel(const float* __restrict__ dPre, const float* __restrict
     }
 }
 
+// max|.| of what a kernel wrote, as float bits, for the FP16 scale of the tensor-core consumer (tc_common.cuh): one
+// atomicMax per warp.  Every thread of the (converged) warp must call it.
+__device__ __forceinline__ void record_absmax(float amax, uint32_t* __restrict__ slot) {
+    if (slot == nullptr) return;
+    const uint32_t wm = __reduce_max_sync(0xffffffffu, __float_as_uint(amax));
+    if ((threadIdx.x & 31) == 0 && wm != 0u) atomicMax(slot, wm);
+}
+
 // ---------------------------------------------------------------------------------------------
 // 2x2/2 VALID max-pool, forward and (fused with the ReLU mask and an optional loss seed) backward
 // ---------------------------------------------------------------------------------------------
@@ -240,9 +248,10 @@ maxpool2_kernel(const float* __restrict__ X, float* __restrict__ P, int H, int W
 // One thread per (full-resolution pixel, 4 channels); pixels outside every window (odd H/W) only see the seed.
 __global__ void __launch_bounds__(256)
 unpool_relu_kernel(const float* __restrict__ Y, const float* __restrict__ dP, const float* __restrict__ seed,
-                   float* __restrict__ dPre, int H, int W, int C) {
+                   float* __restrict__ dPre, int H, int W, int C, uint32_t* __restrict__ out_absmax) {
     const int Hp = H / 2, Wp = W / 2, C4 = C / 4;
     const size_t total = size_t(H) * W * C4;
+    float amax = 0.f;
     for (size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += size_t(gridDim.x) * blockDim.x) {
         const int c4 = int(i % C4);
         const size_t pp = i / C4;
@@ -275,19 +284,25 @@ unpool_relu_kernel(const float* __restrict__ Y, const float* __restrict__ dP, co
         }
         g.x = me.x > 0.f ? g.x : 0.f; g.y = me.y > 0.f ? g.y : 0.f;
         g.z = me.z > 0.f ? g.z : 0.f; g.w = me.w > 0.f ? g.w : 0.f;
+        amax = fmaxf(fmaxf(amax, fmaxf(fabsf(g.x), fabsf(g.y))), fmaxf(fabsf(g.z), fabsf(g.w)));
         reinterpret_cast<float4*>(dPre)[i] = g;
     }
+    record_absmax(amax, out_absmax);
 }
 
 // dPre = Y > 0 ? seed : 0     (top of the chain)
 __global__ void __launch_bounds__(256)
-relu_mask_kernel(const float* __restrict__ Y, const float* __restrict__ seed, float* __restrict__ dPre, size_t n4) {
+relu_mask_kernel(const float* __restrict__ Y, const float* __restrict__ seed, float* __restrict__ dPre, size_t n4,
+                 uint32_t* __restrict__ out_absmax) {
+    float amax = 0.f;
     for (size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n4; i += size_t(gridDim.x) * blockDim.x) {
         const float4 y = __ldg(reinterpret_cast<const float4*>(Y) + i);
         float4 s = __ldg(reinterpret_cast<const float4*>(seed) + i);
         s.x = y.x > 0.f ? s.x : 0.f; s.y = y.y > 0.f ? s.y : 0.f; s.z = y.z > 0.f ? s.z : 0.f; s.w = y.w > 0.f ? s.w : 0.f;
+        amax = fmaxf(fmaxf(amax, fmaxf(fabsf(s.x), fabsf(s.y))), fmaxf(fabsf(s.z), fabsf(s.w)));
         reinterpret_cast<float4*>(dPre)[i] = s;
     }
+    record_absmax(amax, out_absmax);
 }
 
 // gradient weights: Wb[tap'][co][ci] = W[8 - tap'][ci][co]
@@ -345,14 +360,27 @@ static int launch_conv_simt(int mode, bool pre, const float* X, const float* Wt,
 
 // One convolution of the network: tensor-core path when the shape allows it, exact-fp32 CUDA-core path otherwise
 // (block1_conv1: Cin = 3) or when the handle was switched to CONV_PATH_SIMT (validation).
+// x_absmax: slot with max|X| (NULL: measured here with an extra pass over X); y_absmax (may be NULL): slot that receives
+// max|Y| (must have been zeroed).  The CUDA-core path neither needs nor produces them, so when it runs and the caller
+// wants max|Y| it is measured with a separate pass.
 static int launch_conv(adpst_vgg* h, int i, int mode, const float* X, float* Y, const float* seed, const float* mask,
-                       int lh, int lw, cudaStream_t st) {
+                       int lh, int lw, const uint32_t* x_absmax, uint32_t* y_absmax, cudaStream_t st) {
     const bool grad = (mode == MODE_BWD);
     const int K = grad ? conv_cout(i) : conv_cin(i), N = grad ? conv_cin(i) : conv_cout(i);
-    if (h->conv_path == CONV_PATH_TENSOR && h->tc_ready && i > 0 && conv_tc_eligible(K, N))
-        return launch_conv_tc(h, i, grad ? 1 : 0, X, Y, seed, mask, lh, lw, K, N, st);
-    return launch_conv_simt(mode, i == 0 && !grad, X, grad ? h->wb[i] : h->wf[i], grad ? nullptr : h->bias[i], Y, seed, mask,
-                            lh, lw, K, N, st);
+    if (h->conv_path == CONV_PATH_TENSOR && h->tc_ready && i > 0 && conv_tc_eligible(K, N)) {
+        if (x_absmax == nullptr) {
+            uint32_t* scratch = h->amax + AMAX_SCRATCH;
+            int rc = launch_absmax(X, size_t(lh) * lw * K, scratch, st);
+            if (rc != ADPST_OK) return rc;
+            x_absmax = scratch;
+        }
+        return launch_conv_tc(h, i, grad ? 1 : 0, X, Y, seed, mask, lh, lw, K, N, x_absmax, y_absmax, st);
+    }
+    int rc = launch_conv_simt(mode, i == 0 && !grad, X, grad ? h->wb[i] : h->wf[i], grad ? nullptr : h->bias[i], Y, seed, mask,
+                              lh, lw, K, N, st);
+    if (rc == ADPST_OK && y_absmax != nullptr)
+        rc = launch_absmax(Y, size_t(lh) * lw * N, y_absmax, st);
+    return rc;
 }
 
 }  // namespace adpst
@@ -410,6 +438,11 @@ int adpst_vgg_create(const float* const* kernels_dev, const float* const* biases
         adpst_vgg_destroy(h);
         return fail(ADPST_ERR_CUDA, "vgg_create: %s", cudaGetErrorString(e));
     }
+    if (cudaMalloc(reinterpret_cast<void**>(&h->amax), AMAX_SLOTS * sizeof(uint32_t)) != cudaSuccess ||
+        cudaMemsetAsync(h->amax, 0, AMAX_SLOTS * sizeof(uint32_t), st) != cudaSuccess) {
+        adpst_vgg_destroy(h);
+        return fail(ADPST_ERR_CUDA, "vgg_create: cannot allocate the scale slots");
+    }
     for (int i = 1; i < kNumConv; ++i) {
         int rc = prepare_tc_weights(h, i, st);
         if (rc != ADPST_OK) { adpst_vgg_destroy(h); return rc; }
@@ -431,6 +464,7 @@ void adpst_vgg_destroy(adpst_vgg* h) {
         }
     }
     if (h->wg0) cudaFree(h->wg0);
+    if (h->amax) cudaFree(h->amax);
     delete h;
 }
 
@@ -444,11 +478,14 @@ int adpst_vgg_forward(adpst_vgg* h, const float* image_dev, int H, int W, float*
                   "vgg_forward: %dx%d image is too small for conv %d", H, W, last);
     cudaStream_t st = as_stream(stream);
     const float* x = image_dev;
+    ADPST_CUDA_CHECK(cudaMemsetAsync(h->amax + AMAX_ACT, 0, kNumConv * sizeof(uint32_t), st));
     for (int i = 0; i <= last; ++i) {
         int lh, lw;
         layer_hw(i, H, W, &lh, &lw);
         ADPST_REQUIRE(acts_dev[i] != nullptr, "vgg_forward: acts[%d] is NULL", i);
-        int rc = launch_conv(h, i, MODE_FWD, x, acts_dev[i], nullptr, nullptr, lh, lw, st);
+        // a max-pool keeps the maximum of a post-ReLU map, so the pooled tensor shares the slot of the conv before it
+        int rc = launch_conv(h, i, MODE_FWD, x, acts_dev[i], nullptr, nullptr, lh, lw, i > 0 ? h->amax + AMAX_ACT + i - 1 : nullptr,
+                             h->amax + AMAX_ACT + i, st);
         if (rc != ADPST_OK) return rc;
         x = acts_dev[i];
         for (int j = 0; j < ADPST_VGG_NUM_POOL; ++j) {
@@ -471,22 +508,35 @@ int adpst_vgg_set_conv_path(adpst_vgg* h, int path) {
     return ADPST_OK;
 }
 
+int adpst_absmax(const float* x_dev, size_t n, uint32_t* slot_dev, adpst_stream_t stream) {
+    using namespace adpst;
+    ADPST_REQUIRE(x_dev && slot_dev, "absmax: NULL argument");
+    return launch_absmax(x_dev, n, slot_dev, as_stream(stream));
+}
+
+const uint32_t* adpst_vgg_act_absmax(const adpst_vgg* h, int i) {
+    if (!h || i < 0 || i >= adpst::kNumConv || !h->amax) return nullptr;
+    return h->amax + adpst::AMAX_ACT + i;
+}
+
 /* development: per-stage clock64 timeline of one CTA of the tensor-core conv kernel (buf: 5*4096 int64, NULL = off) */
 int adpst_debug_conv_trace(long long* buf_dev, int block) {
     adpst::conv_tc_set_trace(buf_dev, block);
     return ADPST_OK;
 }
 
-int adpst_vgg_conv_forward(adpst_vgg* h, int i, const float* x_dev, int lh, int lw, float* y_dev, adpst_stream_t stream) {
+int adpst_vgg_conv_forward(adpst_vgg* h, int i, const float* x_dev, int lh, int lw, float* y_dev,
+                           const uint32_t* x_absmax_dev, adpst_stream_t stream) {
     using namespace adpst;
     ADPST_REQUIRE(h && x_dev && y_dev && i >= 0 && i < kNumConv && lh > 0 && lw > 0, "vgg_conv_forward: bad argument");
-    return launch_conv(h, i, MODE_FWD, x_dev, y_dev, nullptr, nullptr, lh, lw, as_stream(stream));
+    return launch_conv(h, i, MODE_FWD, x_dev, y_dev, nullptr, nullptr, lh, lw, x_absmax_dev, nullptr, as_stream(stream));
 }
 
-int adpst_vgg_conv_dgrad(adpst_vgg* h, int i, const float* dpre_dev, int lh, int lw, float* dx_dev, adpst_stream_t stream) {
+int adpst_vgg_conv_dgrad(adpst_vgg* h, int i, const float* dpre_dev, int lh, int lw, float* dx_dev,
+                         const uint32_t* dpre_absmax_dev, adpst_stream_t stream) {
     using namespace adpst;
     ADPST_REQUIRE(h && dpre_dev && dx_dev && i >= 1 && i < kNumConv && lh > 0 && lw > 0, "vgg_conv_dgrad: bad argument");
-    return launch_conv(h, i, MODE_BWD, dpre_dev, dx_dev, nullptr, nullptr, lh, lw, as_stream(stream));
+    return launch_conv(h, i, MODE_BWD, dpre_dev, dx_dev, nullptr, nullptr, lh, lw, dpre_absmax_dev, nullptr, as_stream(stream));
 }
 
 int adpst_vgg_backward(adpst_vgg* h, int H, int W, const float* const* acts_dev, const float* const* pools_dev,
@@ -502,9 +552,11 @@ int adpst_vgg_backward(adpst_vgg* h, int H, int W, const float* const* acts_dev,
     float* nxt = scratch1_dev;
     int lh, lw;
     layer_hw(last, H, W, &lh, &lw);
+    uint32_t* gmax = h->amax + AMAX_GRAD;          // gmax[i]: max|dLoss/d(pre-activation of conv i)|
+    ADPST_CUDA_CHECK(cudaMemsetAsync(gmax, 0, kNumConv * sizeof(uint32_t), st));
     {
         const size_t n4 = size_t(lh) * lw * conv_cout(last) / 4;
-        relu_mask_kernel<<<stream_grid(n4), 256, 0, st>>>(acts_dev[last], seeds_dev[last], cur, n4);
+        relu_mask_kernel<<<stream_grid(n4), 256, 0, st>>>(acts_dev[last], seeds_dev[last], cur, n4, gmax + last);
         ADPST_LAUNCH_CHECK();
     }
     for (int i = last; i >= 1; --i) {
@@ -513,18 +565,18 @@ int adpst_vgg_backward(adpst_vgg* h, int H, int W, const float* const* acts_dev,
         for (int j = 0; j < ADPST_VGG_NUM_POOL; ++j) pooled_input |= (kPoolAfter[j] == i - 1);
         if (!pooled_input) {
             // input of conv i is the post-ReLU output of conv i-1 at the same resolution
-            int rc = launch_conv(h, i, MODE_BWD, cur, nxt, seeds_dev[i - 1], acts_dev[i - 1], lh, lw, st);
+            int rc = launch_conv(h, i, MODE_BWD, cur, nxt, seeds_dev[i - 1], acts_dev[i - 1], lh, lw, gmax + i, gmax + i - 1, st);
             if (rc != ADPST_OK) return rc;
             float* t = cur; cur = nxt; nxt = t;
         } else {
             // gradient w.r.t. the pooled tensor, then route through the pool + ReLU of conv i-1
-            int rc = launch_conv(h, i, MODE_BWD, cur, nxt, nullptr, nullptr, lh, lw, st);
+            int rc = launch_conv(h, i, MODE_BWD, cur, nxt, nullptr, nullptr, lh, lw, gmax + i, nullptr, st);
             if (rc != ADPST_OK) return rc;
             int ph, pw;
             layer_hw(i - 1, H, W, &ph, &pw);
             const size_t items = size_t(ph) * pw * (conv_cout(i - 1) / 4);
             unpool_relu_kernel<<<stream_grid(items), 256, 0, st>>>(acts_dev[i - 1], nxt, seeds_dev[i - 1], cur, ph, pw,
-                                                                   conv_cout(i - 1));
+                                                                   conv_cout(i - 1), gmax + i - 1);
             ADPST_LAUNCH_CHECK();
         }
     }

@@ -115,10 +115,24 @@ def gram_masked(F, masks, K, workspace=None, patches=None, path="tensor", out=No
     return G
 
 
+def act_absmax_slot(t):
+    """Device address of the slot holding max|t| if `t` is an output of the latest forward pass of its VGG19 handle
+    (components/VGG19/model.py tags its outputs), else None: the consumer then measures max|t| itself."""
+    tag = getattr(t, "_adpst_absmax", None)
+    if tag is None:
+        return None
+    handle, generation, index = tag
+    handle = handle()
+    if handle is None or handle.generation != generation:
+        return None
+    return handle.act_absmax_ptr(index)
+
+
 def style_layer_backward(F, masks, K, G, A, loss_scale, grad_scale, loss_acc, dF, accumulate=False, workspace=None,
-                         path="tensor", hw_norm=0.0):
+                         path="tensor", hw_norm=0.0, f_absmax=None):
     """One layer of loss.py:104-137: accumulates the loss value and writes/adds its gradient w.r.t. F.
-    F: (h, w, C) feature map (a (HW, C) matrix is treated as h = HW, w = 1... use the 3-D form for 2-D tiling)."""
+    F: (h, w, C) feature map (a (HW, C) matrix is treated as h = HW, w = 1... use the 3-D form for 2-D tiling).
+    f_absmax: device address of a slot holding max|F| (act_absmax_slot), or None to have it measured."""
     _f32(F, "F"); _f32(G, "G"); _f32(A, "A")
     if F.dim() == 2:
         F = F.reshape(F.shape[0], 1, F.shape[1])
@@ -127,7 +141,7 @@ def style_layer_backward(F, masks, K, G, A, loss_scale, grad_scale, loss_acc, dF
     _lib.check(_lib.lib().adpst_style_layer_backward(_lib.ptr(F), h, w, C, _lib.ptr(masks), K, _lib.ptr(G), _lib.ptr(A),
                                                      float(loss_scale), float(grad_scale), _lib.ptr(loss_acc), _lib.ptr(dF),
                                                      int(bool(accumulate)), {"tensor": 0, "simt": 1}[path], float(hw_norm),
-                                                     _lib.ptr(ws), _lib.stream_ptr()))
+                                                     ctypes.c_void_p(f_absmax or 0), _lib.ptr(ws), _lib.stream_ptr()))
 
 
 def loss_finalize(acc, w_content, w_style, w_photo, out):

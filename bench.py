@@ -283,11 +283,11 @@ def run_ours(args):
         for i, h, cin, cout, f in fwd:
             src = x if i == 0 else (A.pools[[1, 3, 7, 11].index(i - 1)] if (i - 1) in (1, 3, 7, 11) else A.acts[i - 1])
             t = time_launches(lambda: lib.check(lib.lib().adpst_vgg_conv_forward(ext.vgg._h, i, lib.ptr(src), h, h,
-                                                                                 lib.ptr(scratch), stream)), flush, 3)
+                                                                                 lib.ptr(scratch), None, stream)), flush, 3)
             tot_f += f; tot_t += t; n_launch += 1
         for i, h, cin, cout, f in bwd:
             t = time_launches(lambda: lib.check(lib.lib().adpst_vgg_conv_dgrad(ext.vgg._h, i, lib.ptr(A.acts[i]), h, h,
-                                                                               lib.ptr(scratch), stream)), flush, 3)
+                                                                               lib.ptr(scratch), None, stream)), flush, 3)
             tot_f += f; tot_t += t; n_launch += 1
         conv_tflops = tot_f / (tot_t * 1e-3) / 1e12
         # The reference computes these convolutions in float32 (1e-5 parity): the tensor-core kernel forms every product as

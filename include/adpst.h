@@ -101,18 +101,30 @@ int adpst_vgg_pool_shape(int j, int H, int W, int* h, int* w, int* c);
 int adpst_vgg_forward(adpst_vgg* h, const float* image_dev, int H, int W, float* const* acts_dev,
                       float* const* pools_dev, int last, adpst_stream_t stream);
 
-/* Convolution kernel family used by this handle: 0 = tcgen05 3xTF32 implicit GEMM (default; block1_conv1 and the
- * gradient to the image always use the CUDA-core kernels), 1 = exact-float32 CUDA-core kernels everywhere (validation). */
+/* Convolution kernel family used by this handle: 0 = tcgen05 3xFP16 implicit GEMM, float32-accurate (default;
+ * block1_conv1 and the gradient to the image always use the CUDA-core kernels), 1 = exact-float32 CUDA-core kernels
+ * everywhere (validation). */
 int adpst_vgg_set_conv_path(adpst_vgg* h, int path);
 
 /* Development aid: clock64 timeline of one CTA of the tensor-core conv kernel (buf_dev: 5*4096 int64; NULL disables). */
 int adpst_debug_conv_trace(long long* buf_dev, int block);
 
+/* The tensor-core kernels split float32 operands into FP16 pairs after a power-of-two scale derived from the
+ * tensor's largest magnitude.  Inside adpst_vgg_forward / adpst_vgg_backward every kernel records max|output| for its
+ * consumer; tensors that enter from outside either come with a device slot holding the float32 bit pattern of
+ * max|x| (adpst_absmax) or the entry point measures it with one extra pass (slot argument NULL). */
+int adpst_absmax(const float* x_dev, size_t n, uint32_t* slot_dev, adpst_stream_t stream);
+/* slot of conv i's output as left by the most recent adpst_vgg_forward on this handle (device pointer). */
+const uint32_t* adpst_vgg_act_absmax(const adpst_vgg* h, int i);
+
 /* One layer in isolation (parity tests, per-kernel roofline in bench.py).
  * conv_forward: y = relu(conv_i(x) + b_i); for i == 0, x is the [0,1] RGB image (h,w,3).
- * conv_dgrad  : dx = conv_i^T(dpre) (i >= 1), no mask, no seed. */
-int adpst_vgg_conv_forward(adpst_vgg* h, int i, const float* x_dev, int lh, int lw, float* y_dev, adpst_stream_t stream);
-int adpst_vgg_conv_dgrad(adpst_vgg* h, int i, const float* dpre_dev, int lh, int lw, float* dx_dev, adpst_stream_t stream);
+ * conv_dgrad  : dx = conv_i^T(dpre) (i >= 1), no mask, no seed.
+ * x_absmax_dev / dpre_absmax_dev: see above (may be NULL). */
+int adpst_vgg_conv_forward(adpst_vgg* h, int i, const float* x_dev, int lh, int lw, float* y_dev,
+                           const uint32_t* x_absmax_dev, adpst_stream_t stream);
+int adpst_vgg_conv_dgrad(adpst_vgg* h, int i, const float* dpre_dev, int lh, int lw, float* dx_dev,
+                         const uint32_t* dpre_absmax_dev, adpst_stream_t stream);
 
 /* Backward to the image.  seeds_dev[i] (may be NULL): dLoss/d(conv i output), added where the chain passes.
  * scratch_dev: two buffers, each at least as large as the largest activation (conv 0).
@@ -144,13 +156,14 @@ int adpst_gram_masked(const float* F_dev, int h, int w, int C, const float* mask
  *   dF (=|+=)  grad_scale * dL/dF                     (written, or added if accumulate != 0; may be NULL)
  * G_dev is the transfer Gram from adpst_gram_masked on the same F / masks; A_dev the style Gram.
  * loss_scale carries the 1/len(args) of loss.py:85, grad_scale additionally the style weight.
- * F is the (h,w,C) feature map; path: 0 = tcgen05 3xTF32 kernel (8x16-pixel tiles, classes absent from a tile skipped),
+ * F is the (h,w,C) feature map; path: 0 = tcgen05 3xFP16 kernel (8x16-pixel tiles, classes absent from a tile skipped),
  * 1 = exact-float32 CUDA-core kernel (validation).  hw_norm > 0 replaces h*w in the normaliser (spatially tiled runs:
- * the pixel count of the whole image). */
+ * the pixel count of the whole image).  F_absmax_dev: slot holding max|F| (adpst_vgg_act_absmax / adpst_absmax), or
+ * NULL to have it measured here. */
 int adpst_style_layer_backward(const float* F_dev, int h, int w, int C, const float* masks_dev, int K,
                                const float* G_dev, const float* A_dev, double loss_scale, double grad_scale,
                                double* loss_dev, float* dF_dev, int accumulate, int path, double hw_norm,
-                               void* workspace_dev, adpst_stream_t stream);
+                               const uint32_t* F_absmax_dev, void* workspace_dev, adpst_stream_t stream);
 
 /* loss.py:90-92 with L = mean((target - output)^2):
  *   *loss_dev += loss_scale * L;   dOut (=|+=) grad_scale * 2 (output - target) / n.

@@ -11,9 +11,9 @@ layer, hw, blk = int(sys.argv[1]), int(sys.argv[2]), int(sys.argv[3])
 cin, cout = synth.CONV_LAYERS[layer][1], synth.CONV_LAYERS[layer][2]
 x = torch.rand(hw, hw, cin, device="cuda") * 100; y = torch.empty(hw, hw, cout, device="cuda")
 buf = torch.zeros(5 * 4096, dtype=torch.int64, device="cuda")
-for _ in range(2): lib.check(L.adpst_vgg_conv_forward(ext.vgg._h, layer, lib.ptr(x), hw, hw, lib.ptr(y), lib.stream_ptr()))
+for _ in range(2): lib.check(L.adpst_vgg_conv_forward(ext.vgg._h, layer, lib.ptr(x), hw, hw, lib.ptr(y), None, lib.stream_ptr()))
 lib.check(L.adpst_debug_conv_trace(lib.ptr(buf), blk))
-lib.check(L.adpst_vgg_conv_forward(ext.vgg._h, layer, lib.ptr(x), hw, hw, lib.ptr(y), lib.stream_ptr())); torch.cuda.synchronize()
+lib.check(L.adpst_vgg_conv_forward(ext.vgg._h, layer, lib.ptr(x), hw, hw, lib.ptr(y), None, lib.stream_ptr())); torch.cuda.synchronize()
 lib.check(L.adpst_debug_conv_trace(None, -1))
 b = buf.cpu().numpy()
 t0, t1 = b[4 * 4096], b[4 * 4096 + 1]

@@ -13,12 +13,12 @@ cin, cout = synth.CONV_LAYERS[layer][1], synth.CONV_LAYERS[layer][2]
 x = torch.rand(hw, hw, cin, device="cuda") * 100
 y = torch.empty(hw, hw, cout, device="cuda")
 for _ in range(3):
-    lib.check(L.adpst_vgg_conv_forward(ext.vgg._h, layer, lib.ptr(x), hw, hw, lib.ptr(y), lib.stream_ptr()))
+    lib.check(L.adpst_vgg_conv_forward(ext.vgg._h, layer, lib.ptr(x), hw, hw, lib.ptr(y), None, lib.stream_ptr()))
 torch.cuda.synchronize()
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 e0.record()
 for _ in range(5):
-    lib.check(L.adpst_vgg_conv_forward(ext.vgg._h, layer, lib.ptr(x), hw, hw, lib.ptr(y), lib.stream_ptr()))
+    lib.check(L.adpst_vgg_conv_forward(ext.vgg._h, layer, lib.ptr(x), hw, hw, lib.ptr(y), None, lib.stream_ptr()))
 e1.record(); torch.cuda.synchronize()
 ms = e0.elapsed_time(e1) / 5
 print("layer %d %dx%d: %.3f ms, %.1f TFLOP/s" % (layer, hw, hw, ms, 2.0 * hw * hw * 9 * cin * cout / ms / 1e9))

@@ -11,7 +11,7 @@ ext = vgg.StyleContentModel(names[:1], names[1:], weights=W)
 def run(fn, i, x, h, w, c, path):
     lib.check(L.adpst_vgg_set_conv_path(ext.vgg._h, path))
     y = torch.empty(h, w, c, dtype=torch.float32, device="cuda")
-    lib.check(getattr(L, fn)(ext.vgg._h, i, lib.ptr(x), h, w, lib.ptr(y), lib.stream_ptr())); torch.cuda.synchronize()
+    lib.check(getattr(L, fn)(ext.vgg._h, i, lib.ptr(x), h, w, lib.ptr(y), None, lib.stream_ptr())); torch.cuda.synchronize()
     lib.check(L.adpst_vgg_set_conv_path(ext.vgg._h, 0)); return y
 for i in (1, 2, 4, 8, 9, 12):
     cin, cout = synth.CONV_LAYERS[i][1], synth.CONV_LAYERS[i][2]

@@ -9,7 +9,7 @@ ext = vgg.StyleContentModel(names[:1], names[1:], weights=synth.vgg_weights(seed
 def run(fn, i, x, h, w, c, path):
     lib.check(L.adpst_vgg_set_conv_path(ext.vgg._h, path))
     y = torch.full((h, w, c), float("nan"), dtype=torch.float32, device="cuda")
-    lib.check(getattr(L, fn)(ext.vgg._h, i, lib.ptr(x), h, w, lib.ptr(y), lib.stream_ptr())); torch.cuda.synchronize()
+    lib.check(getattr(L, fn)(ext.vgg._h, i, lib.ptr(x), h, w, lib.ptr(y), None, lib.stream_ptr())); torch.cuda.synchronize()
     lib.check(L.adpst_vgg_set_conv_path(ext.vgg._h, 0)); return y
 bad = 0
 for (h, w) in [(48, 80), (24, 40), (12, 20), (6, 10), (3, 5), (48, 69), (24, 34), (12, 17), (6, 8), (3, 4), (8, 16), (9, 17), (16, 32)]:

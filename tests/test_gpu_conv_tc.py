@@ -23,7 +23,7 @@ def _run(ext, fn_name, i, x, h, w, cout, path):
     L = lib.lib()
     lib.check(L.adpst_vgg_set_conv_path(ext.vgg._h, path))
     y = torch.full((h, w, cout), float("nan"), dtype=torch.float32, device="cuda")
-    lib.check(getattr(L, fn_name)(ext.vgg._h, i, lib.ptr(x), h, w, lib.ptr(y), lib.stream_ptr()))
+    lib.check(getattr(L, fn_name)(ext.vgg._h, i, lib.ptr(x), h, w, lib.ptr(y), None, lib.stream_ptr()))
     torch.cuda.synchronize()
     lib.check(L.adpst_vgg_set_conv_path(ext.vgg._h, 0))
     return y
