@@ -97,8 +97,7 @@ template <int BN> struct TcCfg {
     static constexpr int STAGES = BN == 128 ? 3 : 4;
     static constexpr int B_BYTES = BN * TC_BK * 2;                          // BN rows x 64 fp16
     static constexpr int STAGE_BYTES = TC_A_BYTES + 2 * B_BYTES;            // A (raw fp32, as landed), B_hi, B_lo
-    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*alignment slack*/ + 256 /*barriers*/ +
-                                      TC_MAX_CLASSES * TC_BM * 4 /*per-pixel class weights (style mode)*/;
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*alignment slack*/ + 256 /*barriers*/;
     // tensor memory columns: big0 | big1 | small | A operand slots (2 x (hi: 32 columns of packed fp16 pairs, lo: 32))
     static constexpr uint32_t COL_SMALL = 2 * BN, COL_A = 3 * BN, TMEM_COLS = 512;
 };
@@ -111,14 +110,20 @@ __device__ __forceinline__ int nth_set_bit(uint32_t m, int n) {
 
 __device__ __forceinline__ uint32_t h2_bits(__half2 h) { return *reinterpret_cast<uint32_t*>(&h); }
 
+// Persistent kernel: gridDim.x CTAs (one per SM) walk the work items (pixel tile, block of BN output channels) with
+// stride gridDim.x; the output-channel block is the fastest index, so CTAs that run side by side read the same A tile
+// (L2 hits) and all of them the same weights.  Every warp role keeps its pipeline position (stage, phase, chunk buffer)
+// across work items, so the TMA loads, operand splits and MMAs of the next item run while the drain warps are still
+// writing the previous item's outputs: per-item prologue/epilogue cost is hidden, which is what the short K loops
+// (Cin = 64: nine stages per item; style gradient: one or two) need.
 template <int BN, int MODE>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmBhi,
                   const __grid_constant__ CUtensorMap tmBlo, const float* __restrict__ bias, float* __restrict__ Y,
                   const float* __restrict__ seed, const float* __restrict__ mask_src, int H, int W, int Cin, int Cout,
-                  int tiles_w, const float* __restrict__ cls_masks, int num_cls, const uint32_t* __restrict__ a_absmax,
-                  const uint32_t* __restrict__ b_absmax, uint32_t* __restrict__ y_absmax, long long* __restrict__ dbg,
-                  int dbg_block) {
+                  int tiles_w, int num_tiles, const float* __restrict__ cls_masks, const uint32_t* __restrict__ tile_active,
+                  const uint32_t* __restrict__ a_absmax, const uint32_t* __restrict__ b_absmax,
+                  const uint32_t* __restrict__ w_absmax, uint32_t* __restrict__ y_absmax) {
     using Cfg = TcCfg<BN>;
     constexpr int STAGES = Cfg::STAGES;
     static_assert(BN == 64 || BN == 128, "tile width");
@@ -130,52 +135,23 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     uint64_t* empty = bars + 8;                 // [STAGES]  MMAs that read the stage have retired
     uint64_t* chunk_full = bars + 12;           // [2]       a big-term chunk is complete in TMEM buffer b
     uint64_t* chunk_empty = chunk_full + 2;     // [2]       the drain warps have consumed TMEM buffer b
-    uint64_t* small_full = chunk_empty + 2;     // [1]       every MMA of the tile has retired
-    uint64_t* a_free = small_full + 1;          // [2]       the MMAs that read TMEM A slot j have retired
+    uint64_t* small_full = chunk_empty + 2;     // [1]       every MMA of the work item has retired
+    uint64_t* small_empty = small_full + 1;     // [1]       the drain warps have read the small-term accumulator
+    uint64_t* a_free = small_empty + 1;         // [2]       the MMAs that read TMEM A slot j have retired
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(a_free + 2);
-    uint32_t* wmax_bits = tmem_slot + 1;        // style mode: largest class weight in this pixel tile
-    float* cls_w = reinterpret_cast<float*>(bars + 32);                // [num_cls][128]  (style mode)
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int tile = blockIdx.x;
-    const int y0 = (tile / tiles_w) * TC_TH, x0 = (tile % tiles_w) * TC_TW;
-    const int n0 = blockIdx.y * BN;
     const int kchunks = Cin / TC_BK;
-    // "taps" of the K loop: the 9 filter taps (convolution) or the classes whose mask is non-zero somewhere in this pixel
-    // tile (style gradient: dF = sum_k w_k F D_k is a 1x1 convolution per class with a per-pixel weight w_k = m_k^2).
-    uint32_t active = 0x1FFu;
-    if (MODE == MODE_STYLE) {
-        active = 0u;
-        if (threadIdx.x == 0) *wmax_bits = 0u;
-        __syncthreads();
-        const int t = threadIdx.x;
-        const int gy = y0 + t / TC_TW, gx = x0 + t % TC_TW;
-        for (int k = 0; k < num_cls; ++k) {
-            float w = 0.f;
-            if (t < TC_BM) {
-                if (gy < H && gx < W) {
-                    w = cls_masks ? __ldg(cls_masks + size_t(k) * H * W + size_t(gy) * W + gx) : 1.0f;
-                    w *= w;
-                }
-                cls_w[k * TC_BM + t] = w;
-                if (w > 1.0f) atomicMax(wmax_bits, __float_as_uint(w));
-            }
-            if (__syncthreads_or(w != 0.f)) active |= 1u << k;
-        }
-    }
-    const int ntaps = __popc(active);
-    const int iters = ntaps * kchunks;
+    const int nblk = Cout / BN;
+    const int total = num_tiles * nblk;
     constexpr int chunk_iters = TC_CHUNK_ITERS;
-    const int nchunks = (iters + chunk_iters - 1) / chunk_iters;
     // operand scales (powers of two): s_a from the input tensor's recorded max|.|, s_b from the weights'
     int ea = tc::f16_scale_exponent(__ldg(a_absmax));
     const int eb = tc::f16_scale_exponent(__ldg(b_absmax));
     if (MODE == MODE_STYLE) {
-        const uint32_t wb = *wmax_bits;                                // class weights above 1 (masks outside [0,1])
-        if (wb != 0u) ea -= int(wb >> 23) - 127 + 1;
+        const uint32_t wb = __ldg(w_absmax);                           // class weights above 1 (masks outside [0,1])
+        if (wb > 0x3F800000u) ea -= int(wb >> 23) - 127 + 1;
     }
-    const bool trace = dbg != nullptr && int(blockIdx.x) == dbg_block && blockIdx.y == 0;
-    if (trace && threadIdx.x == 0) dbg[4 * 4096] = clock64();
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < STAGES; ++s) {
@@ -188,6 +164,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             tc::mbar_init(&chunk_empty[b], 128);
         }
         tc::mbar_init(small_full, 1);
+        tc::mbar_init(small_empty, 128);
         tc::mbar_init(&a_free[0], 2);
         tc::mbar_init(&a_free[1], 2);
         tc::fence_barrier_init();
@@ -203,23 +180,35 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     const uint32_t tmem_small = tmem_base + Cfg::COL_SMALL;
     const uint32_t tmem_a = tmem_base + Cfg::COL_A;
 
+    // "taps" of an item's K loop: the 9 filter taps (convolution) or the classes whose mask is non-zero somewhere in the
+    // pixel tile (style gradient: dF = sum_k w_k F D_k is a 1x1 convolution per class with a per-pixel weight
+    // w_k = m_k^2; the per-tile class sets come from style_tiles_kernel).
+    auto item_active = [&](int tile) -> uint32_t { return MODE == MODE_STYLE ? __ldg(tile_active + tile) : 0x1FFu; };
+
     if (warp == 0) {
         // ================= TMA producer =================
         if (lane == 0) {
-            int s = 0, round = 0, slot = 0, kc = 0;
-            for (int it = 0; it < iters; ++it) {
-                tc::mbar_wait(&empty[s], (round & 1) ^ 1);
-                const int tap = (MODE == MODE_STYLE) ? nth_set_bit(active, slot) : slot;
-                const int kh = (MODE == MODE_STYLE) ? 1 : tap / 3, kw = (MODE == MODE_STYLE) ? 1 : tap - (tap / 3) * 3;
-                uint8_t* st = smem + s * Cfg::STAGE_BYTES;
-                tc::mbar_arrive_expect_tx(&full[s], TC_A_BYTES);
-                tc::tma_load_4d(st, &tmA, &full[s], kc * TC_BK, x0 + kw - 1, y0 + kh - 1, 0);
-                tc::tma_load_4d(st + TC_A_BOX_BYTES, &tmA, &full[s], kc * TC_BK + 32, x0 + kw - 1, y0 + kh - 1, 0);
-                tc::mbar_arrive_expect_tx(&ready[s], 2 * Cfg::B_BYTES);
-                tc::tma_load_2d(st + TC_A_BYTES, &tmBhi, &ready[s], kc * TC_BK, tap * Cout + n0);
-                tc::tma_load_2d(st + TC_A_BYTES + Cfg::B_BYTES, &tmBlo, &ready[s], kc * TC_BK, tap * Cout + n0);
-                if (++s == STAGES) { s = 0; ++round; }
-                if (++kc == kchunks) { kc = 0; if (++slot == ntaps) slot = 0; }
+            int s = 0, round = 0;
+            for (int w = blockIdx.x; w < total; w += gridDim.x) {
+                const int tile = w / nblk, n0 = (w - tile * nblk) * BN;
+                const int y0 = (tile / tiles_w) * TC_TH, x0 = (tile % tiles_w) * TC_TW;
+                const uint32_t active = item_active(tile);
+                const int ntaps = __popc(active);
+                for (int slot = 0; slot < ntaps; ++slot) {
+                    const int tap = (MODE == MODE_STYLE) ? nth_set_bit(active, slot) : slot;
+                    const int kh = (MODE == MODE_STYLE) ? 1 : tap / 3, kw = (MODE == MODE_STYLE) ? 1 : tap - (tap / 3) * 3;
+                    for (int kc = 0; kc < kchunks; ++kc) {
+                        tc::mbar_wait(&empty[s], (round & 1) ^ 1);
+                        uint8_t* st = smem + s * Cfg::STAGE_BYTES;
+                        tc::mbar_arrive_expect_tx(&full[s], TC_A_BYTES);
+                        tc::tma_load_4d(st, &tmA, &full[s], kc * TC_BK, x0 + kw - 1, y0 + kh - 1, 0);
+                        tc::tma_load_4d(st + TC_A_BOX_BYTES, &tmA, &full[s], kc * TC_BK + 32, x0 + kw - 1, y0 + kh - 1, 0);
+                        tc::mbar_arrive_expect_tx(&ready[s], 2 * Cfg::B_BYTES);
+                        tc::tma_load_2d(st + TC_A_BYTES, &tmBhi, &ready[s], kc * TC_BK, tap * Cout + n0);
+                        tc::tma_load_2d(st + TC_A_BYTES + Cfg::B_BYTES, &tmBlo, &ready[s], kc * TC_BK, tap * Cout + n0);
+                        if (++s == STAGES) { s = 0; ++round; }
+                    }
+                }
             }
         }
     } else if (warp == 1) {
@@ -234,57 +223,68 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         constexpr uint32_t idesc = tc::umma_idesc_f16(TC_BM, BN);
         const uint32_t stage0 = tc::smem_u32(smem);
         const uint64_t d_bhi = tc::umma_desc_kmajor_sw128(stage0 + TC_A_BYTES, 1024);
-        int s = 0, round = 0;
-        for (int it = 0; it < iters; ++it) {
-            const int c = it / chunk_iters, cpos = it - c * chunk_iters;
-            const uint32_t tmem_big = tmem_base + uint32_t(c & 1) * BN;
-            const uint32_t a_hi = tmem_a + uint32_t(it & 1) * 64;
-            if (cpos == 0) {                                          // TMEM buffer must have been drained
-                tc::mbar_wait(&chunk_empty[c & 1], ((c >> 1) & 1) ^ 1);
-            }
-            // ONE wait per stage: ready[s] completes when the B tiles have landed (transaction bytes) and the 128 transform
-            // threads have stored A hi/lo into tensor memory.
-            tc::mbar_wait(&ready[s], round & 1);
-            tc::tcgen05_fence_after();
-            const uint64_t soff = uint64_t(uint32_t(s) * uint32_t(Cfg::STAGE_BYTES >> 4));
-            if (tc::elect_one_sync()) {
+        int s = 0, round = 0, git = 0, gc = 0;                         // stage / phase, global iteration, global chunk
+        for (int w = blockIdx.x; w < total; w += gridDim.x) {
+            const int iters = __popc(item_active(w / nblk)) * kchunks;
+            for (int it = 0; it < iters; ++it, ++git) {
+                const int cpos = it % chunk_iters;
+                const uint32_t tmem_big = tmem_base + uint32_t(gc & 1) * BN;
+                const uint32_t a_hi = tmem_a + uint32_t(git & 1) * 64;
+                if (cpos == 0) tc::mbar_wait(&chunk_empty[gc & 1], ((gc >> 1) & 1) ^ 1);   // TMEM buffer drained
+                // ONE wait per stage: ready[s] completes when the B tiles have landed (transaction bytes) and the 128
+                // transform threads have stored A hi/lo into tensor memory.
+                tc::mbar_wait(&ready[s], round & 1);
+                tc::tcgen05_fence_after();
+                const uint64_t soff = uint64_t(uint32_t(s) * uint32_t(Cfg::STAGE_BYTES >> 4));
+                const bool close = (cpos == chunk_iters - 1 || it == iters - 1);
+                if (tc::elect_one_sync()) {
 #pragma unroll
-                for (int k = 0; k < TC_BK / 16; ++k)                  // UMMA K = 16: 8 TMEM columns of A, 32 bytes of each B row
-                    tc::umma_f16_ts(tmem_big, a_hi + k * 8, d_bhi + soff + uint64_t(k * 2), idesc, (cpos | k) != 0);
-                tc::umma_commit(&empty[s]);
-                tc::umma_commit(&a_free[it & 1]);
-                if (cpos == chunk_iters - 1 || it == iters - 1) tc::umma_commit(&chunk_full[c & 1]);
+                    for (int k = 0; k < TC_BK / 16; ++k)              // UMMA K = 16: 8 TMEM columns of A, 32 bytes of each B row
+                        tc::umma_f16_ts(tmem_big, a_hi + k * 8, d_bhi + soff + uint64_t(k * 2), idesc, (cpos | k) != 0);
+                    tc::umma_commit(&empty[s]);
+                    tc::umma_commit(&a_free[git & 1]);
+                    if (close) tc::umma_commit(&chunk_full[gc & 1]);
+                }
+                __syncwarp();
+                if (close) ++gc;
+                if (++s == STAGES) { s = 0; ++round; }
             }
-            __syncwarp();
-            if (++s == STAGES) { s = 0; ++round; }
         }
     } else if (warp == 10) {
-        // ================= MMA issuer, small terms: a_lo*b_hi + a_hi*b_lo into the tile-long accumulator =================
+        // ================= MMA issuer, small terms: a_lo*b_hi + a_hi*b_lo into the item-long accumulator =================
         constexpr uint32_t idesc = tc::umma_idesc_f16(TC_BM, BN);
         const uint32_t stage0 = tc::smem_u32(smem);
         const uint64_t d_bhi = tc::umma_desc_kmajor_sw128(stage0 + TC_A_BYTES, 1024);
         const uint64_t d_blo = tc::umma_desc_kmajor_sw128(stage0 + TC_A_BYTES + Cfg::B_BYTES, 1024);
-        int s = 0, round = 0;
-        for (int it = 0; it < iters; ++it) {
-            const uint32_t a_hi = tmem_a + uint32_t(it & 1) * 64, a_lo = a_hi + 32;
-            tc::mbar_wait(&ready[s], round & 1);
-            tc::tcgen05_fence_after();
-            const uint64_t soff = uint64_t(uint32_t(s) * uint32_t(Cfg::STAGE_BYTES >> 4));
-            if (tc::elect_one_sync()) {
-#pragma unroll
-                for (int k = 0; k < TC_BK / 16; ++k) {
-                    const uint64_t koff = soff + uint64_t(k * 2);
-                    tc::umma_f16_ts(tmem_small, a_lo + k * 8, d_bhi + koff, idesc, (it | k) != 0);
-                    tc::umma_f16_ts(tmem_small, a_hi + k * 8, d_blo + koff, idesc, 1);
-                }
-                tc::umma_commit(&empty[s]);
-                tc::umma_commit(&a_free[it & 1]);
+        int s = 0, round = 0, git = 0, sj = 0;                         // sj: items with a non-empty K loop so far
+        for (int w = blockIdx.x; w < total; w += gridDim.x) {
+            const int iters = __popc(item_active(w / nblk)) * kchunks;
+            if (iters == 0) continue;
+            if (sj > 0) {                                              // the previous item's small terms must have been read
+                tc::mbar_wait(small_empty, (sj - 1) & 1);
+                tc::tcgen05_fence_after();
             }
-            __syncwarp();
-            if (++s == STAGES) { s = 0; ++round; }
+            for (int it = 0; it < iters; ++it, ++git) {
+                const uint32_t a_hi = tmem_a + uint32_t(git & 1) * 64, a_lo = a_hi + 32;
+                tc::mbar_wait(&ready[s], round & 1);
+                tc::tcgen05_fence_after();
+                const uint64_t soff = uint64_t(uint32_t(s) * uint32_t(Cfg::STAGE_BYTES >> 4));
+                if (tc::elect_one_sync()) {
+#pragma unroll
+                    for (int k = 0; k < TC_BK / 16; ++k) {
+                        const uint64_t koff = soff + uint64_t(k * 2);
+                        tc::umma_f16_ts(tmem_small, a_lo + k * 8, d_bhi + koff, idesc, (it | k) != 0);
+                        tc::umma_f16_ts(tmem_small, a_hi + k * 8, d_blo + koff, idesc, 1);
+                    }
+                    tc::umma_commit(&empty[s]);
+                    tc::umma_commit(&a_free[git & 1]);
+                    if (it == iters - 1) tc::umma_commit(small_full);
+                }
+                __syncwarp();
+                if (++s == STAGES) { s = 0; ++round; }
+            }
+            ++sj;
         }
-        if (iters > 0 && tc::elect_one_sync()) tc::umma_commit(small_full);
-        __syncwarp();
     } else if (warp < 6) {
         // ================= operand transform =================
         // Thread (warp w, lane l) owns row m = 32 (w & 3) + l of the A tile (= TMEM lane m).  It reads the row's 64 floats
@@ -295,123 +295,147 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         const int m = q * 32 + lane;
         const uint32_t lane_base = uint32_t(q * 32) << 16;
         const float sa = tc::pow2f_int(ea);
-        int s = 0, round = 0;
-        for (int it = 0; it < iters; ++it) {
-            tc::mbar_wait(&full[s], round & 1);
-            float scl = sa;
-            if (MODE == MODE_STYLE) scl *= cls_w[nth_set_bit(active, it / kchunks) * TC_BM + m];
-            const uint32_t dst = tmem_a + uint32_t(it & 1) * 64 + lane_base;
-#pragma unroll
-            for (int half = 0; half < 2; ++half) {
-                const uint8_t* arow = smem + s * Cfg::STAGE_BYTES + half * TC_A_BOX_BYTES + m * 128;
-                uint32_t hi[16], lo[16];
-#pragma unroll
-                for (int c = 0; c < 8; ++c) {
-                    const float4 v = *reinterpret_cast<const float4*>(arow + ((c ^ (m & 7)) << 4));
-                    const float t0 = v.x * scl, t1 = v.y * scl, t2 = v.z * scl, t3 = v.w * scl;
-                    const __half2 h01 = __floats2half2_rn(t0, t1), h23 = __floats2half2_rn(t2, t3);
-                    const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
-                    const __half2 l01 = __floats2half2_rn((t0 - f01.x) * 2048.0f, (t1 - f01.y) * 2048.0f);
-                    const __half2 l23 = __floats2half2_rn((t2 - f23.x) * 2048.0f, (t3 - f23.y) * 2048.0f);
-                    hi[c * 2] = h2_bits(h01); hi[c * 2 + 1] = h2_bits(h23);
-                    lo[c * 2] = h2_bits(l01); lo[c * 2 + 1] = h2_bits(l23);
+        int s = 0, round = 0, git = 0;
+        for (int w = blockIdx.x; w < total; w += gridDim.x) {
+            const int tile = w / nblk;
+            const uint32_t active = item_active(tile);
+            const int ntaps = __popc(active);
+            const int gy = (tile / tiles_w) * TC_TH + m / TC_TW, gx = (tile % tiles_w) * TC_TW + m % TC_TW;
+            for (int slot = 0; slot < ntaps; ++slot) {
+                float scl = sa;
+                if (MODE == MODE_STYLE) {
+                    float wk = 0.f;
+                    if (gy < H && gx < W) {
+                        wk = cls_masks ? __ldg(cls_masks + size_t(nth_set_bit(active, slot)) * H * W + size_t(gy) * W + gx) : 1.0f;
+                        wk *= wk;
+                    }
+                    scl *= wk;
                 }
-                if (half == 0) {
-                    // the MMAs that read this TMEM slot two iterations ago must have retired
-                    tc::mbar_wait(&a_free[it & 1], (((it >> 1) & 1) ^ 1));
-                    tc::tcgen05_fence_after();
+                for (int kc = 0; kc < kchunks; ++kc, ++git) {
+                    tc::mbar_wait(&full[s], round & 1);
+                    const uint32_t dst = tmem_a + uint32_t(git & 1) * 64 + lane_base;
+#pragma unroll
+                    for (int half = 0; half < 2; ++half) {
+                        const uint8_t* arow = smem + s * Cfg::STAGE_BYTES + half * TC_A_BOX_BYTES + m * 128;
+                        uint32_t hi[16], lo[16];
+#pragma unroll
+                        for (int c = 0; c < 8; ++c) {
+                            const float4 v = *reinterpret_cast<const float4*>(arow + ((c ^ (m & 7)) << 4));
+                            const float t0 = v.x * scl, t1 = v.y * scl, t2 = v.z * scl, t3 = v.w * scl;
+                            const __half2 h01 = __floats2half2_rn(t0, t1), h23 = __floats2half2_rn(t2, t3);
+                            const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
+                            const __half2 l01 = __floats2half2_rn((t0 - f01.x) * 2048.0f, (t1 - f01.y) * 2048.0f);
+                            const __half2 l23 = __floats2half2_rn((t2 - f23.x) * 2048.0f, (t3 - f23.y) * 2048.0f);
+                            hi[c * 2] = h2_bits(h01); hi[c * 2 + 1] = h2_bits(h23);
+                            lo[c * 2] = h2_bits(l01); lo[c * 2 + 1] = h2_bits(l23);
+                        }
+                        if (half == 0) {
+                            // the MMAs that read this TMEM slot two iterations ago must have retired
+                            tc::mbar_wait(&a_free[git & 1], (((git >> 1) & 1) ^ 1));
+                            tc::tcgen05_fence_after();
+                        }
+                        tc::tmem_st_32x16(dst + half * 16, hi);
+                        tc::tmem_st_32x16(dst + 32 + half * 16, lo);
+                    }
+                    tc::tmem_st_wait();
+                    tc::tcgen05_fence_before();
+                    tc::mbar_arrive(&ready[s]);
+                    if (++s == STAGES) { s = 0; ++round; }
                 }
-                tc::tmem_st_32x16(dst + half * 16, hi);
-                tc::tmem_st_32x16(dst + 32 + half * 16, lo);
             }
-            tc::tmem_st_wait();
-            tc::tcgen05_fence_before();
-            tc::mbar_arrive(&ready[s]);
-            if (++s == STAGES) { s = 0; ++round; }
         }
     } else if (warp < 10) {
         // ================= drain (chunk promotion) + epilogue =================
         const int q = warp & 3;                                        // TMEM lane quarter this warp may read
         const uint32_t lane_base = uint32_t(q * 32) << 16;
-        float acc[BN];
-#pragma unroll
-        for (int j = 0; j < BN; ++j) acc[j] = 0.f;
-        for (int c = 0; c < nchunks; ++c) {
-            tc::mbar_wait(&chunk_full[c & 1], (c >> 1) & 1);
-            tc::tcgen05_fence_after();
-            const uint32_t src = tmem_base + uint32_t(c & 1) * BN + lane_base;
-#pragma unroll
-            for (int c0 = 0; c0 < BN; c0 += 32) {
-                uint32_t v[32];
-                tc::tmem_ld_32x32(src + c0, v);
-                tc::tmem_ld_wait();
-#pragma unroll
-                for (int j = 0; j < 32; ++j) acc[c0 + j] += __uint_as_float(v[j]);
-            }
-            tc::tcgen05_fence_before();
-            tc::mbar_arrive(&chunk_empty[c & 1]);
-        }
-        if (iters > 0) {
-            tc::mbar_wait(small_full, 0);
-            tc::tcgen05_fence_after();
-        }
         const float inv_big = tc::pow2f_int(-(ea + eb)), inv_small = tc::pow2f_int(-(ea + eb) - 11);
         const int m = q * 32 + lane;                                   // accumulator row = pixel within the tile
-        const int gy = y0 + m / TC_TW, gx = x0 + m % TC_TW;
-        const bool inb = gy < H && gx < W;
-        const size_t rowoff = (size_t(gy) * W + gx) * size_t(Cout) + n0;
         float amax = 0.f;
+        int gc = 0, sj = 0;
+        for (int w = blockIdx.x; w < total; w += gridDim.x) {
+            const int tile = w / nblk, n0 = (w - tile * nblk) * BN;
+            const int iters = __popc(item_active(tile)) * kchunks;
+            const int nchunks = (iters + chunk_iters - 1) / chunk_iters;
+            float acc[BN];
 #pragma unroll
-        for (int c0 = 0; c0 < BN; c0 += 32) {
-            uint32_t v[32];
-            if (iters > 0) {
-                tc::tmem_ld_32x32(tmem_small + lane_base + c0, v);
-                tc::tmem_ld_wait();
-            } else {
+            for (int j = 0; j < BN; ++j) acc[j] = 0.f;
+            for (int c = 0; c < nchunks; ++c, ++gc) {
+                tc::mbar_wait(&chunk_full[gc & 1], (gc >> 1) & 1);
+                tc::tcgen05_fence_after();
+                const uint32_t src = tmem_base + uint32_t(gc & 1) * BN + lane_base;
 #pragma unroll
-                for (int j = 0; j < 32; ++j) v[j] = 0u;
-            }
-            if (inb) {
-                float r[32];
+                for (int c0 = 0; c0 < BN; c0 += 32) {
+                    uint32_t v[32];
+                    tc::tmem_ld_32x32(src + c0, v);
+                    tc::tmem_ld_wait();
 #pragma unroll
-                for (int j = 0; j < 32; ++j) r[j] = fmaf(__uint_as_float(v[j]), inv_small, acc[c0 + j] * inv_big);
-                if (MODE == MODE_STYLE) {
-                    if (seed != nullptr) {                                 // accumulate into an existing gradient seed
-#pragma unroll
-                        for (int j = 0; j < 32; j += 4) {
-                            const float4 sd = *reinterpret_cast<const float4*>(seed + rowoff + c0 + j);
-                            r[j] += sd.x; r[j + 1] += sd.y; r[j + 2] += sd.z; r[j + 3] += sd.w;
-                        }
-                    }
-                } else if (MODE == MODE_FWD) {
-#pragma unroll
-                    for (int j = 0; j < 32; j += 4) {
-                        const float4 b = __ldg(reinterpret_cast<const float4*>(bias + n0 + c0 + j));
-                        r[j] = fmaxf(r[j] + b.x, 0.f); r[j + 1] = fmaxf(r[j + 1] + b.y, 0.f);
-                        r[j + 2] = fmaxf(r[j + 2] + b.z, 0.f); r[j + 3] = fmaxf(r[j + 3] + b.w, 0.f);
-                    }
-                } else {
-                    if (seed != nullptr) {
-#pragma unroll
-                        for (int j = 0; j < 32; j += 4) {
-                            const float4 sd = __ldg(reinterpret_cast<const float4*>(seed + rowoff + c0 + j));
-                            r[j] += sd.x; r[j + 1] += sd.y; r[j + 2] += sd.z; r[j + 3] += sd.w;
-                        }
-                    }
-                    if (mask_src != nullptr) {
-#pragma unroll
-                        for (int j = 0; j < 32; j += 4) {
-                            const float4 mk = __ldg(reinterpret_cast<const float4*>(mask_src + rowoff + c0 + j));
-                            r[j] = mk.x > 0.f ? r[j] : 0.f; r[j + 1] = mk.y > 0.f ? r[j + 1] : 0.f;
-                            r[j + 2] = mk.z > 0.f ? r[j + 2] : 0.f; r[j + 3] = mk.w > 0.f ? r[j + 3] : 0.f;
-                        }
-                    }
+                    for (int j = 0; j < 32; ++j) acc[c0 + j] += __uint_as_float(v[j]);
                 }
+                tc::tcgen05_fence_before();
+                tc::mbar_arrive(&chunk_empty[gc & 1]);
+            }
+            if (iters > 0) {
+                // fold in the small terms and hand their accumulator back at once: the next item's MMAs are already running
+                tc::mbar_wait(small_full, sj & 1);
+                tc::tcgen05_fence_after();
 #pragma unroll
-                for (int j = 0; j < 32; ++j) amax = fmaxf(amax, fabsf(r[j]));
+                for (int c0 = 0; c0 < BN; c0 += 32) {
+                    uint32_t v[32];
+                    tc::tmem_ld_32x32(tmem_small + lane_base + c0, v);
+                    tc::tmem_ld_wait();
 #pragma unroll
-                for (int j = 0; j < 32; j += 4)
-                    *reinterpret_cast<float4*>(Y + rowoff + c0 + j) = make_float4(r[j], r[j + 1], r[j + 2], r[j + 3]);
+                    for (int j = 0; j < 32; ++j) acc[c0 + j] = fmaf(__uint_as_float(v[j]), inv_small, acc[c0 + j] * inv_big);
+                }
+                tc::tcgen05_fence_before();
+                tc::mbar_arrive(small_empty);
+                ++sj;
+            }
+            const int gy = (tile / tiles_w) * TC_TH + m / TC_TW, gx = (tile % tiles_w) * TC_TW + m % TC_TW;
+            if (gy < H && gx < W) {
+                const size_t rowoff = (size_t(gy) * W + gx) * size_t(Cout) + n0;
+#pragma unroll
+                for (int c0 = 0; c0 < BN; c0 += 32) {
+                    float r[32];
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) r[j] = acc[c0 + j];
+                    if (MODE == MODE_STYLE) {
+                        if (seed != nullptr) {                             // accumulate into an existing gradient seed
+#pragma unroll
+                            for (int j = 0; j < 32; j += 4) {
+                                const float4 sd = *reinterpret_cast<const float4*>(seed + rowoff + c0 + j);
+                                r[j] += sd.x; r[j + 1] += sd.y; r[j + 2] += sd.z; r[j + 3] += sd.w;
+                            }
+                        }
+                    } else if (MODE == MODE_FWD) {
+#pragma unroll
+                        for (int j = 0; j < 32; j += 4) {
+                            const float4 b = __ldg(reinterpret_cast<const float4*>(bias + n0 + c0 + j));
+                            r[j] = fmaxf(r[j] + b.x, 0.f); r[j + 1] = fmaxf(r[j + 1] + b.y, 0.f);
+                            r[j + 2] = fmaxf(r[j + 2] + b.z, 0.f); r[j + 3] = fmaxf(r[j + 3] + b.w, 0.f);
+                        }
+                    } else {
+                        if (seed != nullptr) {
+#pragma unroll
+                            for (int j = 0; j < 32; j += 4) {
+                                const float4 sd = __ldg(reinterpret_cast<const float4*>(seed + rowoff + c0 + j));
+                                r[j] += sd.x; r[j + 1] += sd.y; r[j + 2] += sd.z; r[j + 3] += sd.w;
+                            }
+                        }
+                        if (mask_src != nullptr) {
+#pragma unroll
+                            for (int j = 0; j < 32; j += 4) {
+                                const float4 mk = __ldg(reinterpret_cast<const float4*>(mask_src + rowoff + c0 + j));
+                                r[j] = mk.x > 0.f ? r[j] : 0.f; r[j + 1] = mk.y > 0.f ? r[j + 1] : 0.f;
+                                r[j + 2] = mk.z > 0.f ? r[j + 2] : 0.f; r[j + 3] = mk.w > 0.f ? r[j + 3] : 0.f;
+                            }
+                        }
+                    }
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) amax = fmaxf(amax, fabsf(r[j]));
+#pragma unroll
+                    for (int j = 0; j < 32; j += 4)
+                        *reinterpret_cast<float4*>(Y + rowoff + c0 + j) = make_float4(r[j], r[j + 1], r[j + 2], r[j + 3]);
+                }
             }
         }
         if (y_absmax != nullptr) {                                     // max|Y| for the consumer's FP16 scale
@@ -421,11 +445,34 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         tc::tcgen05_fence_before();
     }
     __syncthreads();
-    if (trace && threadIdx.x == 0) dbg[4 * 4096 + 1] = clock64();
     if (warp == 1) {
         tc::tcgen05_fence_after();
         tc::tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
     }
+}
+
+// style gradient: per 8x16-pixel tile the set of classes whose weight m_k^2 is non-zero somewhere in the tile (bit mask),
+// and the largest weight of the whole map (float bits, atomicMax; zeroed by the launcher)
+__global__ void __launch_bounds__(TC_BM)
+style_tiles_kernel(const float* __restrict__ cls_masks, int num_cls, int H, int W, int tiles_w, uint32_t* __restrict__ tile_active,
+                   uint32_t* __restrict__ w_absmax) {
+    const int tile = blockIdx.x, t = threadIdx.x;
+    const int gy = (tile / tiles_w) * TC_TH + t / TC_TW, gx = (tile % tiles_w) * TC_TW + t % TC_TW;
+    const bool inb = gy < H && gx < W;
+    uint32_t active = 0u;
+    float wmax = 0.f;
+    for (int k = 0; k < num_cls; ++k) {
+        float w = 0.f;
+        if (inb) {
+            w = cls_masks ? __ldg(cls_masks + size_t(k) * H * W + size_t(gy) * W + gx) : 1.0f;
+            w *= w;
+        }
+        wmax = fmaxf(wmax, w);
+        if (__syncthreads_or(w != 0.f)) active |= 1u << k;
+    }
+    if (t == 0) tile_active[tile] = active;
+    const uint32_t wm = __reduce_max_sync(0xffffffffu, __float_as_uint(wmax));
+    if ((t & 31) == 0 && wm != 0u) atomicMax(w_absmax, wm);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -508,15 +555,13 @@ int prepare_tc_weights(adpst_vgg* h, int i, cudaStream_t st) {
 
 bool conv_tc_eligible(int Cin, int Cout) { return Cin % TC_BK == 0 && (Cout == 64 || Cout % 128 == 0); }
 
-static long long* g_trace_buf = nullptr;
-static int g_trace_block = -1;
-void conv_tc_set_trace(long long* buf, int block) { g_trace_buf = buf; g_trace_block = block; }
+void conv_tc_set_trace(long long*, int) {}     // (the per-stage timeline instrumentation was removed with the persistent kernel)
 
 template <int BN, int MODE>
 static int launch_tc(const CUtensorMap& tmA, const CUtensorMap& tmBhi, const CUtensorMap& tmBlo, const float* bias, float* Y,
                      const float* seed, const float* mask, int H, int W, int Cin, int Cout, const uint32_t* a_absmax,
                      const uint32_t* b_absmax, uint32_t* y_absmax, cudaStream_t st, const float* cls_masks = nullptr,
-                     int num_cls = 0) {
+                     const uint32_t* tile_active = nullptr, const uint32_t* w_absmax = nullptr) {
     using Cfg = TcCfg<BN>;
     auto kern = conv3x3_tc_kernel<BN, MODE>;
     static bool configured = false;
@@ -525,9 +570,10 @@ static int launch_tc(const CUtensorMap& tmA, const CUtensorMap& tmBhi, const CUt
         configured = true;
     }
     const int tw = (W + TC_TW - 1) / TC_TW, th = (H + TC_TH - 1) / TC_TH;
-    dim3 grid(tw * th, Cout / BN);
-    kern<<<grid, TC_THREADS, Cfg::SMEM_BYTES, st>>>(tmA, tmBhi, tmBlo, bias, Y, seed, mask, H, W, Cin, Cout, tw, cls_masks,
-                                                    num_cls, a_absmax, b_absmax, y_absmax, g_trace_buf, g_trace_block);
+    const int total = tw * th * (Cout / BN);
+    const int grid = total < num_sms() ? total : num_sms();
+    kern<<<grid, TC_THREADS, Cfg::SMEM_BYTES, st>>>(tmA, tmBhi, tmBlo, bias, Y, seed, mask, H, W, Cin, Cout, tw, tw * th,
+                                                    cls_masks, tile_active, a_absmax, b_absmax, w_absmax, y_absmax);
     ADPST_LAUNCH_CHECK();
     return ADPST_OK;
 }
@@ -570,8 +616,12 @@ int launch_conv_tc(adpst_vgg* h, int i, int gradient, const float* X, float* Y, 
 // ---------------------------------------------------------------------------------------------------------------
 bool style_tc_eligible(int C) { return C == 64 || C % 128 == 0; }
 
+size_t style_tc_scratch_bytes(int HW) { return size_t(HW) * 4 + 64; }
+
+// scratch: style_tc_scratch_bytes(H*W) bytes of device memory (per-tile class sets and the weight slot)
 int launch_style_dF_tc(const float* F, int H, int W, int C, const float* masks, int K, const void* D_hi, const void* D_lo,
-                       const uint32_t* f_absmax, const uint32_t* d_absmax, float* dF, int accumulate, cudaStream_t st) {
+                       const uint32_t* f_absmax, const uint32_t* d_absmax, float* dF, int accumulate, void* scratch,
+                       cudaStream_t st) {
     ADPST_REQUIRE(K >= 1 && K <= TC_MAX_CLASSES, "style gradient: K=%d classes not supported (max %d)", K, TC_MAX_CLASSES);
     CUtensorMap tmA, tmH, tmL;
     int rc = make_act_map(&tmA, F, H, W, C);
@@ -584,12 +634,18 @@ int launch_style_dF_tc(const float* F, int H, int W, int C, const float* masks, 
     if (rc != ADPST_OK) return rc;
     rc = tc::make_tensor_map_f16(&tmL, D_lo, 2, ddims, dstr, dbox);
     if (rc != ADPST_OK) return rc;
+    const int tw = (W + TC_TW - 1) / TC_TW, th = (H + TC_TH - 1) / TC_TH;
+    uint32_t* wslot = static_cast<uint32_t*>(scratch);
+    uint32_t* tile_active = wslot + 16;
+    ADPST_CUDA_CHECK(cudaMemsetAsync(wslot, 0, sizeof(uint32_t), st));
+    style_tiles_kernel<<<tw * th, TC_BM, 0, st>>>(masks, K, H, W, tw, tile_active, wslot);
+    ADPST_LAUNCH_CHECK();
     const float* seed = accumulate ? dF : nullptr;
     if (BN == 128)
         return launch_tc<128, MODE_STYLE>(tmA, tmH, tmL, nullptr, dF, seed, nullptr, H, W, C, C, f_absmax, d_absmax, nullptr, st,
-                                          masks, K);
+                                          masks, tile_active, wslot);
     return launch_tc<64, MODE_STYLE>(tmA, tmH, tmL, nullptr, dF, seed, nullptr, H, W, C, C, f_absmax, d_absmax, nullptr, st, masks,
-                                     K);
+                                     tile_active, wslot);
 }
 
 }  // namespace adpst

@@ -235,7 +235,8 @@ size_t adpst_gram_workspace_bytes(int HW, int C, int K) {
     int splits = gram_splits(HW, C, K);
     if (gram_tc_eligible(C) && gram_splits_tc(C, K) > splits) splits = gram_splits_tc(C, K);
     const size_t partials = size_t(K) * splits * C * C * sizeof(float);
-    const size_t dmat = size_t(3) * K * C * C * sizeof(float);     // D (fp32), D_hi, D_lo (fp16), two scale slots
+    // D (fp32), D_hi, D_lo (fp16), two scale slots, then the tensor-core style gradient's scratch
+    const size_t dmat = size_t(2) * K * C * C * sizeof(float) + 64 + style_tc_scratch_bytes(HW);
     return partials > dmat ? partials : dmat;
 }
 
@@ -304,7 +305,8 @@ int adpst_style_layer_backward(const float* F_dev, int h, int w, int C, const fl
                 if (rc != ADPST_OK) return rc;
                 F_absmax_dev = slots + 1;
             }
-            return launch_style_dF_tc(F_dev, h, w, C, masks_dev, K, Dhi, Dlo, F_absmax_dev, slots, dF_dev, accumulate, st);
+            return launch_style_dF_tc(F_dev, h, w, C, masks_dev, K, Dhi, Dlo, F_absmax_dev, slots, dF_dev, accumulate, slots + 16,
+                                      st);
         }
         dim3 grid((HW + GT - 1) / GT, C / GT);
         style_dF_kernel<<<grid, GTHREADS, 0, st>>>(F_dev, masks_dev, D, dF_dev, HW, C, K, accumulate);
