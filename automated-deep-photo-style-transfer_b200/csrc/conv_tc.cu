@@ -88,16 +88,28 @@ int make_tensor_map_f16(CUtensorMap* out, const void* base, int rank, const uint
 constexpr int TC_TH = 8, TC_TW = 16, TC_BM = TC_TH * TC_TW;     // 128 pixels = UMMA M
 constexpr int TC_BK = 64;                                        // K per stage: 64 fp16 = one 128-byte swizzle row of B
 constexpr int TC_THREADS = 352;                                  // TMA, MMA(big), 4 transform, 4 drain/epilogue, MMA(small)
-constexpr int TC_A_BOX_BYTES = TC_BM * 32 * 4;                   // one landed box: 128 pixels x 32 channels fp32 = 16 KB
-constexpr int TC_A_BYTES = 2 * TC_A_BOX_BYTES;                   // 32 KB
+constexpr int TC_HW = TC_TW + 2, TC_HH = TC_TH + 2;              // the tile plus its 1-pixel halo: 18 x 10 pixels
+constexpr int TC_A_BOX_BYTES = 23 * 1024;                        // one landed box: 180 halo pixels x 32 channels fp32 = 23040 B,
+                                                                 // padded to the 1024-byte alignment of the 128-byte swizzle
+constexpr int TC_A_TX_BYTES = 2 * TC_HW * TC_HH * 32 * 4;        // bytes TMA actually delivers per A stage
+constexpr int TC_A_BYTES = 2 * TC_A_BOX_BYTES;                   // 46 KB: channels [0,32) and [32,64) of the K chunk
 constexpr int TC_CHUNK_ITERS = 2;                                // stages per promoted chunk (8 big MMAs)
 constexpr int TC_MAX_CLASSES = 32;                               // style mode: classes per launch (active set is a bit mask)
 
+// Shared-memory bandwidth (128 B/clk/SM) is what bounds this kernel, not the tensor pipe: per K chunk of 64 and BN = 128
+// the MMAs read 48 KB of B (one operand per MMA, 12 MMAs) in 768 clk, TMA writes 32 KB of B, and the A operand costs its
+// TMA write plus the transform warps' reads.  So the A tile is NOT reloaded per filter tap: one (8+2) x (16+2) pixel halo
+// tile per K chunk serves all nine taps (the transform warps read their row at the tap's offset), which cuts the A bytes
+// written to shared memory -- and fetched from L2 -- from 9 x 32 KB to 45 KB per chunk.
+// Two rings: the A halo tile lives for nine stages, the B tiles until the MMAs that use them retire.
 template <int BN> struct TcCfg {
-    static constexpr int STAGES = BN == 128 ? 3 : 4;
+    static constexpr int A_STAGES = 2;
+    static constexpr int B_STAGES = BN == 128 ? 4 : 6;
     static constexpr int B_BYTES = BN * TC_BK * 2;                          // BN rows x 64 fp16
-    static constexpr int STAGE_BYTES = TC_A_BYTES + 2 * B_BYTES;            // A (raw fp32, as landed), B_hi, B_lo
-    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*alignment slack*/ + 256 /*barriers*/;
+    static constexpr int B_STAGE_BYTES = 2 * B_BYTES;                       // B_hi, B_lo
+    static constexpr int OFF_B = A_STAGES * TC_A_BYTES;
+    static constexpr int OFF_BARS = OFF_B + B_STAGES * B_STAGE_BYTES;
+    static constexpr int SMEM_BYTES = OFF_BARS + 1024 /*alignment slack*/ + 256 /*barriers*/;
     // tensor memory columns: big0 | big1 | small | A operand slots (2 x (hi: 32 columns of packed fp16 pairs, lo: 32))
     static constexpr uint32_t COL_SMALL = 2 * BN, COL_A = 3 * BN, TMEM_COLS = 512;
 };
@@ -125,15 +137,16 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                   const uint32_t* __restrict__ a_absmax, const uint32_t* __restrict__ b_absmax,
                   const uint32_t* __restrict__ w_absmax, uint32_t* __restrict__ y_absmax) {
     using Cfg = TcCfg<BN>;
-    constexpr int STAGES = Cfg::STAGES;
+    constexpr int AST = Cfg::A_STAGES, BST = Cfg::B_STAGES;
     static_assert(BN == 64 || BN == 128, "tile width");
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES);
-    uint64_t* full = bars;                      // [STAGES]  A tile landed (the transform warps start on it at once)
-    uint64_t* ready = bars + 4;                 // [STAGES]  B tiles landed and A split into hi/lo in tensor memory
-    uint64_t* empty = bars + 8;                 // [STAGES]  MMAs that read the stage have retired
-    uint64_t* chunk_full = bars + 12;           // [2]       a big-term chunk is complete in TMEM buffer b
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::OFF_BARS);
+    uint64_t* full = bars;                      // [AST]  A tile landed (the transform warps start on it at once)
+    uint64_t* a_empty = bars + 3;               // [AST]  the transform warps have read the A tile
+    uint64_t* ready = bars + 6;                 // [BST]  B tiles landed and A split into hi/lo in tensor memory
+    uint64_t* empty = bars + 12;                // [BST]  MMAs that read the B tiles have retired
+    uint64_t* chunk_full = bars + 18;           // [2]    a big-term chunk is complete in TMEM buffer b
     uint64_t* chunk_empty = chunk_full + 2;     // [2]       the drain warps have consumed TMEM buffer b
     uint64_t* small_full = chunk_empty + 2;     // [1]       every MMA of the work item has retired
     uint64_t* small_empty = small_full + 1;     // [1]       the drain warps have read the small-term accumulator
@@ -154,8 +167,11 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     }
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < STAGES; ++s) {
+        for (int s = 0; s < AST; ++s) {
             tc::mbar_init(&full[s], 1);
+            tc::mbar_init(&a_empty[s], 128);
+        }
+        for (int s = 0; s < BST; ++s) {
             tc::mbar_init(&ready[s], 128 + 1);      // 128 transform threads + the producer's expect_tx arrival (B bytes)
             tc::mbar_init(&empty[s], 2);            // both MMA-issuing warps commit
         }
@@ -188,25 +204,29 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     if (warp == 0) {
         // ================= TMA producer =================
         if (lane == 0) {
-            int s = 0, round = 0;
+            int sa = 0, ra = 0, s = 0, round = 0;                      // A ring slot / phase, B ring slot / phase
             for (int w = blockIdx.x; w < total; w += gridDim.x) {
                 const int tile = w / nblk, n0 = (w - tile * nblk) * BN;
                 const int y0 = (tile / tiles_w) * TC_TH, x0 = (tile % tiles_w) * TC_TW;
                 const uint32_t active = item_active(tile);
                 const int ntaps = __popc(active);
-                for (int slot = 0; slot < ntaps; ++slot) {
-                    const int tap = (MODE == MODE_STYLE) ? nth_set_bit(active, slot) : slot;
-                    const int kh = (MODE == MODE_STYLE) ? 1 : tap / 3, kw = (MODE == MODE_STYLE) ? 1 : tap - (tap / 3) * 3;
-                    for (int kc = 0; kc < kchunks; ++kc) {
+                if (ntaps == 0) continue;
+                for (int kc = 0; kc < kchunks; ++kc) {
+                    // the halo tile of this K chunk: 10 x 18 pixels x 64 channels, zero-filled outside the image (= SAME padding)
+                    tc::mbar_wait(&a_empty[sa], (ra & 1) ^ 1);
+                    uint8_t* sta = smem + sa * TC_A_BYTES;
+                    tc::mbar_arrive_expect_tx(&full[sa], TC_A_TX_BYTES);
+                    tc::tma_load_4d(sta, &tmA, &full[sa], kc * TC_BK, x0 - 1, y0 - 1, 0);
+                    tc::tma_load_4d(sta + TC_A_BOX_BYTES, &tmA, &full[sa], kc * TC_BK + 32, x0 - 1, y0 - 1, 0);
+                    if (++sa == AST) { sa = 0; ++ra; }
+                    for (int slot = 0; slot < ntaps; ++slot) {
+                        const int tap = (MODE == MODE_STYLE) ? nth_set_bit(active, slot) : slot;
                         tc::mbar_wait(&empty[s], (round & 1) ^ 1);
-                        uint8_t* st = smem + s * Cfg::STAGE_BYTES;
-                        tc::mbar_arrive_expect_tx(&full[s], TC_A_BYTES);
-                        tc::tma_load_4d(st, &tmA, &full[s], kc * TC_BK, x0 + kw - 1, y0 + kh - 1, 0);
-                        tc::tma_load_4d(st + TC_A_BOX_BYTES, &tmA, &full[s], kc * TC_BK + 32, x0 + kw - 1, y0 + kh - 1, 0);
+                        uint8_t* stb = smem + Cfg::OFF_B + s * Cfg::B_STAGE_BYTES;
                         tc::mbar_arrive_expect_tx(&ready[s], 2 * Cfg::B_BYTES);
-                        tc::tma_load_2d(st + TC_A_BYTES, &tmBhi, &ready[s], kc * TC_BK, tap * Cout + n0);
-                        tc::tma_load_2d(st + TC_A_BYTES + Cfg::B_BYTES, &tmBlo, &ready[s], kc * TC_BK, tap * Cout + n0);
-                        if (++s == STAGES) { s = 0; ++round; }
+                        tc::tma_load_2d(stb, &tmBhi, &ready[s], kc * TC_BK, tap * Cout + n0);
+                        tc::tma_load_2d(stb + Cfg::B_BYTES, &tmBlo, &ready[s], kc * TC_BK, tap * Cout + n0);
+                        if (++s == BST) { s = 0; ++round; }
                     }
                 }
             }
@@ -222,7 +242,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         // issues.  Descriptors are built once: per stage and K-step only the 14-bit address field changes.
         constexpr uint32_t idesc = tc::umma_idesc_f16(TC_BM, BN);
         const uint32_t stage0 = tc::smem_u32(smem);
-        const uint64_t d_bhi = tc::umma_desc_kmajor_sw128(stage0 + TC_A_BYTES, 1024);
+        const uint64_t d_bhi = tc::umma_desc_kmajor_sw128(stage0 + Cfg::OFF_B, 1024);
         int s = 0, round = 0, git = 0, gc = 0;                         // stage / phase, global iteration, global chunk
         for (int w = blockIdx.x; w < total; w += gridDim.x) {
             const int iters = __popc(item_active(w / nblk)) * kchunks;
@@ -235,7 +255,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                 // transform threads have stored A hi/lo into tensor memory.
                 tc::mbar_wait(&ready[s], round & 1);
                 tc::tcgen05_fence_after();
-                const uint64_t soff = uint64_t(uint32_t(s) * uint32_t(Cfg::STAGE_BYTES >> 4));
+                const uint64_t soff = uint64_t(uint32_t(s) * uint32_t(Cfg::B_STAGE_BYTES >> 4));
                 const bool close = (cpos == chunk_iters - 1 || it == iters - 1);
                 if (tc::elect_one_sync()) {
 #pragma unroll
@@ -247,15 +267,15 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                 }
                 __syncwarp();
                 if (close) ++gc;
-                if (++s == STAGES) { s = 0; ++round; }
+                if (++s == BST) { s = 0; ++round; }
             }
         }
     } else if (warp == 10) {
         // ================= MMA issuer, small terms: a_lo*b_hi + a_hi*b_lo into the item-long accumulator =================
         constexpr uint32_t idesc = tc::umma_idesc_f16(TC_BM, BN);
         const uint32_t stage0 = tc::smem_u32(smem);
-        const uint64_t d_bhi = tc::umma_desc_kmajor_sw128(stage0 + TC_A_BYTES, 1024);
-        const uint64_t d_blo = tc::umma_desc_kmajor_sw128(stage0 + TC_A_BYTES + Cfg::B_BYTES, 1024);
+        const uint64_t d_bhi = tc::umma_desc_kmajor_sw128(stage0 + Cfg::OFF_B, 1024);
+        const uint64_t d_blo = tc::umma_desc_kmajor_sw128(stage0 + Cfg::OFF_B + Cfg::B_BYTES, 1024);
         int s = 0, round = 0, git = 0, sj = 0;                         // sj: items with a non-empty K loop so far
         for (int w = blockIdx.x; w < total; w += gridDim.x) {
             const int iters = __popc(item_active(w / nblk)) * kchunks;
@@ -268,7 +288,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                 const uint32_t a_hi = tmem_a + uint32_t(git & 1) * 64, a_lo = a_hi + 32;
                 tc::mbar_wait(&ready[s], round & 1);
                 tc::tcgen05_fence_after();
-                const uint64_t soff = uint64_t(uint32_t(s) * uint32_t(Cfg::STAGE_BYTES >> 4));
+                const uint64_t soff = uint64_t(uint32_t(s) * uint32_t(Cfg::B_STAGE_BYTES >> 4));
                 if (tc::elect_one_sync()) {
 #pragma unroll
                     for (int k = 0; k < TC_BK / 16; ++k) {
@@ -281,7 +301,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                     if (it == iters - 1) tc::umma_commit(small_full);
                 }
                 __syncwarp();
-                if (++s == STAGES) { s = 0; ++round; }
+                if (++s == BST) { s = 0; ++round; }
             }
             ++sj;
         }
@@ -294,54 +314,63 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         const int q = warp & 3;
         const int m = q * 32 + lane;
         const uint32_t lane_base = uint32_t(q * 32) << 16;
-        const float sa = tc::pow2f_int(ea);
-        int s = 0, round = 0, git = 0;
+        const float scale_a = tc::pow2f_int(ea);
+        int sa = 0, ra = 0, s = 0, git = 0;
         for (int w = blockIdx.x; w < total; w += gridDim.x) {
             const int tile = w / nblk;
             const uint32_t active = item_active(tile);
             const int ntaps = __popc(active);
-            const int gy = (tile / tiles_w) * TC_TH + m / TC_TW, gx = (tile % tiles_w) * TC_TW + m % TC_TW;
-            for (int slot = 0; slot < ntaps; ++slot) {
-                float scl = sa;
-                if (MODE == MODE_STYLE) {
-                    float wk = 0.f;
-                    if (gy < H && gx < W) {
-                        wk = cls_masks ? __ldg(cls_masks + size_t(nth_set_bit(active, slot)) * H * W + size_t(gy) * W + gx) : 1.0f;
-                        wk *= wk;
+            if (ntaps == 0) continue;
+            const int ty = m / TC_TW, tx = m % TC_TW;
+            const int gy = (tile / tiles_w) * TC_TH + ty, gx = (tile % tiles_w) * TC_TW + tx;
+            for (int kc = 0; kc < kchunks; ++kc) {
+                tc::mbar_wait(&full[sa], ra & 1);
+                for (int slot = 0; slot < ntaps; ++slot, ++git) {
+                    float scl = scale_a;
+                    int kh = 1, kw = 1;
+                    if (MODE == MODE_STYLE) {
+                        float wk = 0.f;
+                        if (gy < H && gx < W) {
+                            wk = cls_masks ? __ldg(cls_masks + size_t(nth_set_bit(active, slot)) * H * W + size_t(gy) * W + gx) : 1.0f;
+                            wk *= wk;
+                        }
+                        scl *= wk;
+                    } else {
+                        kh = slot / 3; kw = slot - kh * 3;
                     }
-                    scl *= wk;
-                }
-                for (int kc = 0; kc < kchunks; ++kc, ++git) {
-                    tc::mbar_wait(&full[s], round & 1);
+                    const int r = (ty + kh) * TC_HW + tx + kw;             // this thread's pixel, shifted by the tap, in the halo tile
                     const uint32_t dst = tmem_a + uint32_t(git & 1) * 64 + lane_base;
+                    uint32_t hi[2][16], lo[2][16];
 #pragma unroll
                     for (int half = 0; half < 2; ++half) {
-                        const uint8_t* arow = smem + s * Cfg::STAGE_BYTES + half * TC_A_BOX_BYTES + m * 128;
-                        uint32_t hi[16], lo[16];
+                        const uint8_t* arow = smem + sa * TC_A_BYTES + half * TC_A_BOX_BYTES + r * 128;
 #pragma unroll
                         for (int c = 0; c < 8; ++c) {
-                            const float4 v = *reinterpret_cast<const float4*>(arow + ((c ^ (m & 7)) << 4));
+                            const float4 v = *reinterpret_cast<const float4*>(arow + ((c ^ (r & 7)) << 4));
                             const float t0 = v.x * scl, t1 = v.y * scl, t2 = v.z * scl, t3 = v.w * scl;
                             const __half2 h01 = __floats2half2_rn(t0, t1), h23 = __floats2half2_rn(t2, t3);
                             const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
                             const __half2 l01 = __floats2half2_rn((t0 - f01.x) * 2048.0f, (t1 - f01.y) * 2048.0f);
                             const __half2 l23 = __floats2half2_rn((t2 - f23.x) * 2048.0f, (t3 - f23.y) * 2048.0f);
-                            hi[c * 2] = h2_bits(h01); hi[c * 2 + 1] = h2_bits(h23);
-                            lo[c * 2] = h2_bits(l01); lo[c * 2 + 1] = h2_bits(l23);
+                            hi[half][c * 2] = h2_bits(h01); hi[half][c * 2 + 1] = h2_bits(h23);
+                            lo[half][c * 2] = h2_bits(l01); lo[half][c * 2 + 1] = h2_bits(l23);
                         }
-                        if (half == 0) {
-                            // the MMAs that read this TMEM slot two iterations ago must have retired
-                            tc::mbar_wait(&a_free[git & 1], (((git >> 1) & 1) ^ 1));
-                            tc::tcgen05_fence_after();
-                        }
-                        tc::tmem_st_32x16(dst + half * 16, hi);
-                        tc::tmem_st_32x16(dst + 32 + half * 16, lo);
                     }
+                    // the MMAs that read this TMEM slot two iterations ago must have retired
+                    tc::mbar_wait(&a_free[git & 1], (((git >> 1) & 1) ^ 1));
+                    tc::tcgen05_fence_after();
+                    tc::tmem_st_32x16(dst, hi[0]);
+                    tc::tmem_st_32x16(dst + 16, hi[1]);
+                    tc::tmem_st_32x16(dst + 32, lo[0]);
+                    tc::tmem_st_32x16(dst + 48, lo[1]);
                     tc::tmem_st_wait();
                     tc::tcgen05_fence_before();
                     tc::mbar_arrive(&ready[s]);
-                    if (++s == STAGES) { s = 0; ++round; }
+                    if (++s == BST) s = 0;
                 }
+                // every tap has consumed the halo tile (the tcgen05.st above needed the loaded values): release its slot
+                tc::mbar_arrive(&a_empty[sa]);
+                if (++sa == AST) { sa = 0; ++ra; }
             }
         }
     } else if (warp < 10) {
@@ -581,7 +610,7 @@ static int launch_tc(const CUtensorMap& tmA, const CUtensorMap& tmBhi, const CUt
 static int make_act_map(CUtensorMap* tm, const float* X, int H, int W, int C) {
     const uint64_t dims[4] = {uint64_t(C), uint64_t(W), uint64_t(H), 1};
     const uint64_t strides[3] = {uint64_t(C) * 4, uint64_t(W) * C * 4, uint64_t(H) * W * C * 4};
-    const uint32_t box[4] = {32u, uint32_t(TC_TW), uint32_t(TC_TH), 1};
+    const uint32_t box[4] = {32u, uint32_t(TC_HW), uint32_t(TC_HH), 1};      // the pixel tile plus its 1-pixel halo
     return tc::make_tensor_map_f32(tm, X, 4, dims, strides, box);
 }
 
