@@ -14,6 +14,7 @@
 //   v3: only windows that lie fully inside the image exist (matting_v3.py:77); cnt_i = number of such windows
 //       that contain i.
 // Window statistics are recomputed from I every call (36 B/px of traffic instead of 72+).
+#include <stdlib.h>
 #include <type_traits>
 
 #include "common.cuh"
@@ -619,6 +620,231 @@ lap_march_kernel(const float* __restrict__ img, const float* __restrict__ x, flo
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// float64 marching warp, third generation ("march3"): what runs for r = 1, float32 I/O, float64 arithmetic.
+// The kernel is bound by the float64 pipe (64 lanes/clk/SM), not by HBM, so the design minimises float64 instructions
+// and shuffles per pixel:
+//   * every lane owns TWO adjacent columns: a 3-wide horizontal sum of a field costs 3 adds and 2 shuffles per column
+//     pair (q = v0 + v1, W0 = q + left neighbour's v1, W1 = q + right neighbour's v0) instead of 4 adds and 4 shuffles,
+//     the strip is 64 columns wide (60 useful: 94 %), and the two windows give the scheduler independent work;
+//   * the 12 coefficient fields are not kept for three window rows; a finished window row is contracted with the image
+//     at once and ADDED into the three output rows it touches (z[o] += Ha^T I_o + Hb), so the carried state per column
+//     is 9 doubles instead of 36;
+//   * 1/n, eps and the validity mask ride on operations that exist anyway (eps/3 is the addend of the first diagonal
+//     product of each column, b is carried as n*b and divided in the final FMA, invalid windows are selected away with
+//     integer moves).
+// Lanes 0 and 31 and the first/last two rows of a strip are halo.
+// ---------------------------------------------------------------------------------------------
+constexpr int L3_COLS = 60;           // output columns per warp
+constexpr int L3_WARPS = 4;           // warps per CTA
+
+struct Lap3State {
+    double rI[3][2][3], rX[3][2][3];  // [row slot][column of the pair][channel]
+    double z[3][2][3];                // [output row slot][column][x channel]: sum over windows of a^T I + b, so far
+};
+
+__device__ __forceinline__ double sel_f64(bool keep, double v) {   // keep ? v : 0, without the float64 pipe
+    return __hiloint2double(keep ? __double2hiint(v) : 0, keep ? __double2loint(v) : 0);
+}
+
+template <int S>
+__device__ __forceinline__ void lap_march3_step(Lap3State& st, const float (&nI)[6], const float (&nX)[6], int ir, int r0,
+                                                int r_end, int gx0, int lane, int H, int W, bool v2, double eps3,
+                                                double y_scale, float* __restrict__ y, double& acc, int qlo, int qhi) {
+    constexpr int S1 = (S + 1) % 3, S2 = (S + 2) % 3;     // slots of rows ir-2, ir-1 (S holds row ir)
+    constexpr double inv_n = 1.0 / 9.0;
+#pragma unroll
+    for (int col = 0; col < 2; ++col)
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            st.rI[S][col][c] = f32_to_f64_exact(nI[col * 3 + c]);
+            st.rX[S][col][c] = f32_to_f64_exact(nX[col * 3 + c]);
+        }
+    // ---- raw moments of each own column over rows ir-2..ir:  s(3) t(3) Q(6) R(9); exact in float64
+    double cm[2][21];
+#pragma unroll
+    for (int col = 0; col < 2; ++col) {
+        {
+            const double i0 = st.rI[S1][col][0], i1 = st.rI[S1][col][1], i2 = st.rI[S1][col][2];
+            const double x0 = st.rX[S1][col][0], x1 = st.rX[S1][col][1], x2 = st.rX[S1][col][2];
+            double* m = cm[col];
+            m[0] = i0; m[1] = i1; m[2] = i2; m[3] = x0; m[4] = x1; m[5] = x2;
+            m[6] = fma(i0, i0, eps3); m[7] = i0 * i1; m[8] = i0 * i2; m[9] = fma(i1, i1, eps3); m[10] = i1 * i2;
+            m[11] = fma(i2, i2, eps3);
+            m[12] = i0 * x0; m[13] = i0 * x1; m[14] = i0 * x2;
+            m[15] = i1 * x0; m[16] = i1 * x1; m[17] = i1 * x2;
+            m[18] = i2 * x0; m[19] = i2 * x1; m[20] = i2 * x2;
+        }
+#pragma unroll
+        for (int rr = 0; rr < 2; ++rr) {
+            const int slot = rr == 0 ? S2 : S;
+            const double i0 = st.rI[slot][col][0], i1 = st.rI[slot][col][1], i2 = st.rI[slot][col][2];
+            const double x0 = st.rX[slot][col][0], x1 = st.rX[slot][col][1], x2 = st.rX[slot][col][2];
+            double* m = cm[col];
+            m[0] += i0; m[1] += i1; m[2] += i2; m[3] += x0; m[4] += x1; m[5] += x2;
+            m[6] = fma(i0, i0, m[6]); m[7] = fma(i0, i1, m[7]); m[8] = fma(i0, i2, m[8]);
+            m[9] = fma(i1, i1, m[9]); m[10] = fma(i1, i2, m[10]); m[11] = fma(i2, i2, m[11]);
+            m[12] = fma(i0, x0, m[12]); m[13] = fma(i0, x1, m[13]); m[14] = fma(i0, x2, m[14]);
+            m[15] = fma(i1, x0, m[15]); m[16] = fma(i1, x1, m[16]); m[17] = fma(i1, x2, m[17]);
+            m[18] = fma(i2, x0, m[18]); m[19] = fma(i2, x1, m[19]); m[20] = fma(i2, x2, m[20]);
+        }
+    }
+    // ---- windows centred on (wr = ir-1, gx0) and (wr, gx0+1): columns gx0-1..gx0+1 and gx0..gx0+2
+    const int wr = ir - 1;
+    double cf[2][12];                                          // a (9: [image channel j][x channel c] at j*3+c), n*b (3)
+    {
+        double wm[2][21];
+#pragma unroll
+        for (int i = 0; i < 21; ++i) {
+            const double q = cm[0][i] + cm[1][i];
+            wm[0][i] = q + shfl_up1d(cm[1][i]);
+            wm[1][i] = q + shfl_dn1d(cm[0][i]);
+        }
+#pragma unroll
+        for (int col = 0; col < 2; ++col) {
+            const double* w = wm[col];
+            const int gx = gx0 + col;
+            const bool valid = v2 || (wr >= 1 && wr < H - 1 && gx >= 1 && gx < W - 1);
+            const double mu0 = w[0] * inv_n, mu1 = w[1] * inv_n, mu2 = w[2] * inv_n;
+            double M[6], Rc[9], Mi[6];
+            M[0] = fma(-w[0], mu0, w[6]); M[1] = fma(-w[0], mu1, w[7]); M[2] = fma(-w[0], mu2, w[8]);
+            M[3] = fma(-w[1], mu1, w[9]); M[4] = fma(-w[1], mu2, w[10]); M[5] = fma(-w[2], mu2, w[11]);
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                Rc[c] = fma(-mu0, w[3 + c], w[12 + c]);
+                Rc[3 + c] = fma(-mu1, w[3 + c], w[15 + c]);
+                Rc[6 + c] = fma(-mu2, w[3 + c], w[18 + c]);
+            }
+            sym3_inverse(M, Mi);
+            double* a = cf[col];
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                const double a0 = fma(Mi[2], Rc[6 + c], fma(Mi[1], Rc[3 + c], Mi[0] * Rc[c]));
+                const double a1 = fma(Mi[4], Rc[6 + c], fma(Mi[3], Rc[3 + c], Mi[1] * Rc[c]));
+                const double a2 = fma(Mi[5], Rc[6 + c], fma(Mi[4], Rc[3 + c], Mi[2] * Rc[c]));
+                const double nb = fma(-a2, w[2], fma(-a1, w[1], fma(-a0, w[0], w[3 + c])));      // n*b = t - a^T s
+                a[c] = sel_f64(valid, a0); a[3 + c] = sel_f64(valid, a1); a[6 + c] = sel_f64(valid, a2);
+                a[9 + c] = sel_f64(valid, nb);
+            }
+        }
+    }
+    // ---- coefficients summed over the three window columns around each own column
+    double hc[2][12];
+#pragma unroll
+    for (int i = 0; i < 12; ++i) {
+        const double q = cf[0][i] + cf[1][i];
+        hc[0][i] = q + shfl_up1d(cf[1][i]);
+        hc[1][i] = q + shfl_dn1d(cf[0][i]);
+    }
+    // ---- window row wr touches output rows wr-1 (slot S1, complete after this), wr (slot S2), wr+1 (slot S, first term)
+#pragma unroll
+    for (int col = 0; col < 2; ++col) {
+        const double* h = hc[col];
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            const double hb = h[9 + c] * inv_n;
+            st.z[S1][col][c] = fma(h[6 + c], st.rI[S1][col][2], fma(h[3 + c], st.rI[S1][col][1], fma(h[c], st.rI[S1][col][0], st.z[S1][col][c] + hb)));
+            st.z[S2][col][c] = fma(h[6 + c], st.rI[S2][col][2], fma(h[3 + c], st.rI[S2][col][1], fma(h[c], st.rI[S2][col][0], st.z[S2][col][c] + hb)));
+            st.z[S][col][c] = fma(h[6 + c], st.rI[S][col][2], fma(h[3 + c], st.rI[S][col][1], fma(h[c], st.rI[S][col][0], hb)));
+        }
+    }
+    // ---- output row orow = ir - 2
+    const int orow = ir - 2;
+    if (ir >= r0 + 2 && lane >= 1 && lane <= 30 && orow < H && orow < r_end) {
+#pragma unroll
+        for (int col = 0; col < 2; ++col) {
+            const int gx = gx0 + col;
+            if (gx < W) {
+                double cnt = 9.0;
+                if (!v2) {
+                    const int ylo = max(orow - 1, 1), yhi = min(orow + 1, H - 2);
+                    const int xlo = max(gx - 1, 1), xhi = min(gx + 1, W - 2);
+                    const int nwin = max(yhi - ylo + 1, 0) * max(xhi - xlo + 1, 0);      // 0..9, table instead of I2F
+                    cnt = nwin == 9 ? 9.0 : nwin == 6 ? 6.0 : nwin == 4 ? 4.0 : nwin == 3 ? 3.0 : nwin == 2 ? 2.0 : nwin == 1 ? 1.0 : 0.0;
+                }
+                const size_t g = (size_t(orow) * W + gx) * 3;
+                const bool inq = gx >= qlo && gx < qhi;
+#pragma unroll
+                for (int c = 0; c < 3; ++c) {
+                    const double xc = st.rX[S1][col][c];
+                    const double yc = fma(cnt, xc, -st.z[S1][col][c]);
+                    if (inq) acc = fma(xc, yc, acc);
+                    if (y != nullptr) y[g + c] = f64_to_f32_rn(y_scale * yc);
+                }
+            }
+        }
+    }
+}
+
+__global__ void __launch_bounds__(L3_WARPS * 32)
+lap_march3_kernel(const float* __restrict__ img, const float* __restrict__ x, float* __restrict__ y, double* __restrict__ partial,
+                  int H, int W, int mode, double eps, double y_scale, int RW, int strips_x, int total_warps, int qlo, int qhi) {
+    __shared__ double sRed[32];
+    const int lane = threadIdx.x & 31;
+    int gw = blockIdx.x * L3_WARPS + (threadIdx.x >> 5);
+    const bool live = gw < total_warps;                        // spare warps of the last CTA run an empty strip
+    if (!live) gw = 0;
+    double acc = 0.0;
+    {
+        const int sy = gw / strips_x, sx = gw - sy * strips_x;
+        const int c0 = sx * L3_COLS, r0 = sy * RW, r_end = live ? min(r0 + RW, H) : r0;
+        const int gx0 = c0 - 2 + 2 * lane;
+        const bool v2 = (mode == ADPST_LAP_V2);
+        int mx[2];
+        bool col_ok[2];
+#pragma unroll
+        for (int col = 0; col < 2; ++col) {
+            const int gx = gx0 + col;
+            mx[col] = v2 ? reflect_symmetric(gx, W) : gx;
+            col_ok[col] = live && (v2 || (gx >= 0 && gx < W));
+        }
+        Lap3State st;
+#pragma unroll
+        for (int i = 0; i < 3; ++i)
+#pragma unroll
+            for (int col = 0; col < 2; ++col)
+#pragma unroll
+                for (int j = 0; j < 3; ++j) { st.rI[i][col][j] = 0.0; st.rX[i][col][j] = 0.0; st.z[i][col][j] = 0.0; }
+        auto load_row = [&](int ir, float (&vI)[6], float (&vX)[6]) {
+            int my = ir;
+            bool row_ok = true;
+            if (v2) my = reflect_symmetric(ir, H);
+            else row_ok = ir >= 0 && ir < H;
+#pragma unroll
+            for (int col = 0; col < 2; ++col) {
+                vI[col * 3] = vI[col * 3 + 1] = vI[col * 3 + 2] = vX[col * 3] = vX[col * 3 + 1] = vX[col * 3 + 2] = 0.f;
+                if (row_ok && col_ok[col]) {
+                    const size_t g = (size_t(my) * W + mx[col]) * 3;
+                    vI[col * 3] = __ldg(img + g); vI[col * 3 + 1] = __ldg(img + g + 1); vI[col * 3 + 2] = __ldg(img + g + 2);
+                    vX[col * 3] = __ldg(x + g);   vX[col * 3 + 1] = __ldg(x + g + 1);   vX[col * 3 + 2] = __ldg(x + g + 2);
+                }
+            }
+        };
+        float cI[6], cX[6], nI[6], nX[6];
+        const int ir_begin = r0 - 2;
+        // rows r0-2 .. r0+RW+1 for every warp: the trip count depends on kernel parameters only, so the shuffles stay
+        // outside divergence handling; rows past the image / the strip are predicated off at the store
+        const int ntriples = (RW + 4 + 2) / 3;
+        const double eps3 = eps * (1.0 / 3.0);
+        load_row(ir_begin, cI, cX);
+        for (int tpl = 0; tpl < ntriples; ++tpl) {
+            const int ir = ir_begin + 3 * tpl;
+            load_row(ir + 1, nI, nX);                               // one row ahead
+            lap_march3_step<0>(st, cI, cX, ir, r0, r_end, gx0, lane, H, W, v2, eps3, y_scale, y, acc, qlo, qhi);
+            load_row(ir + 2, cI, cX);
+            lap_march3_step<1>(st, nI, nX, ir + 1, r0, r_end, gx0, lane, H, W, v2, eps3, y_scale, y, acc, qlo, qhi);
+            load_row(ir + 3, nI, nX);
+            lap_march3_step<2>(st, cI, cX, ir + 2, r0, r_end, gx0, lane, H, W, v2, eps3, y_scale, y, acc, qlo, qhi);
+#pragma unroll
+            for (int c = 0; c < 6; ++c) { cI[c] = nI[c]; cX[c] = nX[c]; }
+        }
+    }
+    if (partial != nullptr) {
+        const double tot = block_sum<double>(acc, sRed);
+        if (threadIdx.x == 0) partial[blockIdx.x] = tot;
+    }
+}
+
 __global__ void sum_partials_kernel(const double* __restrict__ partial, int n, double* __restrict__ out) {
     __shared__ double red[32];
     double a = 0.0;
@@ -750,8 +976,8 @@ struct adpst_laplacian {
 namespace adpst {
 
 // rows per marching warp: enough warps for ~2 waves of 8 warps per SM, at most 64 rows (halo overhead (RW+2)/RW)
-static inline int march_rows(int H, int W, int warps_per_sm) {
-    const int strips = (W + LM_COLS - 1) / LM_COLS;
+static inline int march_rows(int H, int W, int warps_per_sm, int cols = LM_COLS) {
+    const int strips = (W + cols - 1) / cols;
     const int want = warps_per_sm * num_sms();   // taller strips waste fewer halo rows, more warps hide more latency
     int rw = 64;
     while (rw > 16 && strips * ((H + rw - 1) / rw) < want) rw /= 2;
@@ -762,15 +988,24 @@ template <typename TC>
 static int launch_march(adpst_laplacian* h, const void* x, void* y, double y_scale, double* xLx, cudaStream_t st) {
     // float64 kernel: 255 registers -> 8 resident warps per SM, one full wave; float32 kernel: 12+ resident, two waves
     const int qlo = h->q_col_hi > h->q_col_lo ? h->q_col_lo : 0, qhi = h->q_col_hi > h->q_col_lo ? h->q_col_hi : h->W;
-    const int RW = march_rows(h->H, h->W, std::is_same<TC, double>::value ? 8 : 16);
-    const int strips_x = (h->W + LM_COLS - 1) / LM_COLS, total = strips_x * ((h->H + RW - 1) / RW);
+    constexpr bool f64 = std::is_same<TC, double>::value;
+    static const int variant = getenv("ADPST_LAP_KERNEL") ? atoi(getenv("ADPST_LAP_KERNEL")) : 3;   // 2: previous generation
+    const int cols = (f64 && variant == 3) ? L3_COLS : LM_COLS;
+    static const int rw_override = getenv("ADPST_LAP_RW") ? atoi(getenv("ADPST_LAP_RW")) : 0;      // experiments
+    const int RW = rw_override > 0 ? rw_override : march_rows(h->H, h->W, f64 ? 8 : 16, cols);
+    const int strips_x = (h->W + cols - 1) / cols, total = strips_x * ((h->H + RW - 1) / RW);
     const int ctas = (total + LM_WARPS - 1) / LM_WARPS;
     if (ctas > h->npartials) return fail(ADPST_ERR_INVALID, "laplacian: partial buffer too small (%d > %d)", ctas, h->npartials);
-    if constexpr (std::is_same<TC, double>::value)
-        lap_march2_kernel<<<ctas, LM_WARPS * 32, 0, st>>>(static_cast<const float*>(h->image), static_cast<const float*>(x),
-                                                          static_cast<float*>(y), xLx ? h->partials : nullptr, h->H, h->W,
-                                                          h->mode, h->eps, y_scale, RW, strips_x, total, qlo, qhi);
-    else
+    if constexpr (f64) {
+        if (variant == 3)
+            lap_march3_kernel<<<ctas, L3_WARPS * 32, 0, st>>>(static_cast<const float*>(h->image), static_cast<const float*>(x),
+                                                              static_cast<float*>(y), xLx ? h->partials : nullptr, h->H, h->W,
+                                                              h->mode, h->eps, y_scale, RW, strips_x, total, qlo, qhi);
+        else
+            lap_march2_kernel<<<ctas, LM_WARPS * 32, 0, st>>>(static_cast<const float*>(h->image), static_cast<const float*>(x),
+                                                              static_cast<float*>(y), xLx ? h->partials : nullptr, h->H, h->W,
+                                                              h->mode, h->eps, y_scale, RW, strips_x, total, qlo, qhi);
+    } else
         lap_march_kernel<TC><<<ctas, LM_WARPS * 32, 0, st>>>(static_cast<const float*>(h->image), static_cast<const float*>(x),
                                                              static_cast<float*>(y), xLx ? h->partials : nullptr, h->H, h->W,
                                                              h->mode, TC(h->eps), TC(y_scale), RW, strips_x, total, qlo, qhi);
