@@ -157,7 +157,7 @@ class Loss:
             st = self._style_layer_state(name, target, out)
             _, h, w, C = out.shape
             partials.append(kernels.gram_masked(out.reshape(h, w, C), st["own_masks"], st["K"], st["ws"],
-                                                patches=st["patches"], out=st["G"]))
+                                                patches=st["patches"], out=st["G"], f_absmax=kernels.act_absmax_slot(out)))
         self._photo_grad = None
         if wts['photo'] > 0:                                                  # loss.py:67-69, :157-161
             if self.matting_laplacian is None:

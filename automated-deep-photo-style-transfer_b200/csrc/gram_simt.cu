@@ -234,14 +234,15 @@ size_t adpst_gram_workspace_bytes(int HW, int C, int K) {
     if (HW <= 0 || C <= 0 || K <= 0) return 0;
     int splits = gram_splits(HW, C, K);
     if (gram_tc_eligible(C) && gram_splits_tc(C, K) > splits) splits = gram_splits_tc(C, K);
-    const size_t partials = size_t(K) * splits * C * C * sizeof(float);
+    const size_t partials = size_t(K) * splits * C * C * sizeof(float) + 64;       // + the Gram kernel's two scale slots
     // D (fp32), D_hi, D_lo (fp16), two scale slots, then the tensor-core style gradient's scratch
     const size_t dmat = size_t(2) * K * C * C * sizeof(float) + 64 + style_tc_scratch_bytes(HW);
     return partials > dmat ? partials : dmat;
 }
 
 int adpst_gram_masked(const float* F_dev, int h, int w, int C, const float* masks_dev, int K, const int* patch_ids_dev,
-                      const int* patch_off_dev, float* G_dev, int path, void* workspace_dev, adpst_stream_t stream) {
+                      const int* patch_off_dev, float* G_dev, int path, const uint32_t* F_absmax_dev, void* workspace_dev,
+                      adpst_stream_t stream) {
     using namespace adpst;
     ADPST_REQUIRE(F_dev && G_dev && workspace_dev, "gram_masked: NULL argument");
     ADPST_REQUIRE(h > 0 && w > 0 && K > 0, "gram_masked: empty input");
@@ -252,8 +253,17 @@ int adpst_gram_masked(const float* F_dev, int h, int w, int C, const float* mask
     int splits;
     if (path == CONV_PATH_TENSOR && patch_ids_dev && patch_off_dev && gram_tc_eligible(C)) {
         splits = gram_splits_tc(C, K);
-        int rc = launch_gram_tc(F_dev, h, w, C, masks_dev, K, patch_ids_dev, patch_off_dev, static_cast<float*>(workspace_dev),
-                                splits, st);
+        // two scale slots behind the partial tiles: max|mask| and, if the caller has no slot for it, max|F|
+        uint32_t* slots = reinterpret_cast<uint32_t*>(static_cast<float*>(workspace_dev) + size_t(K) * splits * C * C);
+        int rc = ADPST_OK;
+        if (masks_dev != nullptr) rc = launch_absmax(masks_dev, size_t(K) * HW, slots, st);
+        if (rc == ADPST_OK && F_absmax_dev == nullptr) {
+            rc = launch_absmax(F_dev, size_t(HW) * C, slots + 1, st);
+            F_absmax_dev = slots + 1;
+        }
+        if (rc == ADPST_OK)
+            rc = launch_gram_tc(F_dev, h, w, C, masks_dev, K, patch_ids_dev, patch_off_dev, static_cast<float*>(workspace_dev),
+                                splits, F_absmax_dev, masks_dev ? slots : nullptr, st);
         if (rc != ADPST_OK) return rc;
     } else {
         splits = gram_splits(HW, C, K);

@@ -3,35 +3,40 @@
 // Replaces components/loss.py:96-102 (calculate_gram_matrix) for all K classes of one layer:
 //     G_k = X_k^T X_k,   X_k = F * m_k  (rows = pixels scaled by the class mask, exactly the reference's formulation).
 //
-// GEMM view: D[c1, c2] = sum_px X[px, c1] X[px, c2]: the contraction runs over PIXELS, i.e. the operands are needed
-// channel-major x pixel ("K-major" with K = pixel) while HBM holds pixel-major x channel.  tcgen05 kind::tf32 does not
-// accept MN-major operands (measured: any MN-major tf32 descriptor yields zeros, tests/cuda/umma_mnmajor_probe.cu), so
-// the transpose happens on chip: one pipeline stage = a 2 x 16 pixel patch; TMA boxes (32 channels x 16 x 2 pixels) land
-// pixel-major, and the transform warps -- which touch every element anyway for the mask scaling and the TF32 hi/lo
-// split -- write the K-major, 128B-swizzled X^T tiles the MMA reads (conflict-free: a warp reads one 128-byte row and
-// writes 16-byte chunks to 8 different rows).  Diagonal tiles reuse the M-side operand for the N side.
+// GEMM view: D[c1, c2] = sum_px X[px, c1] X[px, c2]: the contraction runs over PIXELS while HBM holds pixel-major x
+// channel, i.e. both operands are "MN-major" (the M/N index -- the channel -- is the contiguous one).  tcgen05 kind::f16
+// accepts MN-major shared-memory operands (checked against a host reference by tests/cuda/umma_f16_mnmajor_probe.cu;
+// kind::tf32 does not), so there is no on-chip transpose: one pipeline stage = a 2 x 16 pixel patch; TMA boxes
+// (32 channels x 16 x 2 pixels) land pixel-major float32, and the transform warps -- which touch every element anyway
+// for the mask scaling and the FP16 hi/lo split -- write the operand tiles in the canonical MN-major 128-byte-swizzle
+// layout: one 128-byte row per pixel holding 64 channels, 8-pixel groups 1024 bytes apart, 64-channel groups 4096 bytes
+// apart.  Diagonal tiles reuse the M-side operand for the N side.
 // Only patches where the class mask is non-zero are visited (list built once per layer from the constant masks), so the
 // work is ~(1 + boundary fraction) * 2 HW C^2 instead of K * 2 HW C^2.
 //
-// Precision: 3xTF32 with unbiased hi/lo splits and chunk promotion to registers, as in conv_tc.cu.
+// Precision: three FP16 terms per product with power-of-two scaling (max|F| from the producer's slot, max|mask| measured
+// here), unbiased hi/lo splits and chunk promotion to registers, as in conv_tc.cu.
 // Output: per-(class, split) partial tiles in the workspace; gram_reduce_kernel sums them in float64 (deterministic) and
 // mirrors the upper triangle.
+#include <cuda_fp16.h>
+
 #include "tc_common.cuh"
 #include "vgg.cuh"
 
 namespace adpst {
 
-constexpr int GM_PH = 2, GM_PW = 16, GM_PX = GM_PH * GM_PW;     // 32 pixels per stage = 4 UMMA K-steps of 8
-constexpr int GM_BLK_BYTES = GM_PX * 128;                        // one (32 channel x 32 pixel) box: 4 KB
+constexpr int GM_PH = 2, GM_PW = 16, GM_PX = GM_PH * GM_PW;     // 32 pixels per stage = 2 UMMA K-steps of 16
+constexpr int GM_BLK_BYTES = GM_PX * 128;                        // one landed box (32 channels x 32 pixels fp32): 4 KB
 constexpr int GM_THREADS = 320;
-constexpr int GM_CHUNK_ITERS = 2;
-constexpr int GM_STAGES = 2;
+constexpr int GM_CHUNK_ITERS = 4;                                // stages per promoted chunk (8 big MMAs)
+constexpr int GM_STAGES = 3;
+constexpr int GM_GROUP_BYTES = (GM_PX / 8) * 1024;               // one 64-channel group of an operand tile: 4 KB
 
 template <int BN> struct GramCfg {
     static constexpr int RAW_A = 4 * GM_BLK_BYTES;                // landed by TMA: 4 blocks of [32 px][32 ch]
     static constexpr int RAW_B = (BN / 32) * GM_BLK_BYTES;
-    static constexpr int A_BYTES = 128 * 128;                     // operand: [128 ch][32 px] K-major, one 128-byte row per channel
-    static constexpr int B_BYTES = BN * 128;
+    static constexpr int A_BYTES = 2 * GM_GROUP_BYTES;            // fp16 operand tile: 128 channels x 32 pixels
+    static constexpr int B_BYTES = (BN / 64) * GM_GROUP_BYTES;
     static constexpr int OFF_RAW_B = RAW_A, OFF_AHI = RAW_A + RAW_B, OFF_ALO = OFF_AHI + A_BYTES, OFF_BHI = OFF_ALO + A_BYTES,
                          OFF_BLO = OFF_BHI + B_BYTES;
     static constexpr int STAGE_BYTES = OFF_BLO + B_BYTES;
@@ -39,19 +44,36 @@ template <int BN> struct GramCfg {
     static constexpr uint32_t TMEM_COLS = 4 * BN;
 };
 
+// shared-memory matrix descriptor, MN-major operand, 128-byte swizzle: LBO = distance between 64-element groups along
+// M/N, SBO = distance between 8-row groups along K
+__device__ __forceinline__ uint64_t umma_desc_mnmajor_sw128(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    uint64_t d = 0;
+    d |= uint64_t((smem_addr >> 4) & 0x3FFF);
+    d |= uint64_t((lbo_bytes >> 4) & 0x3FFF) << 16;
+    d |= uint64_t((sbo_bytes >> 4) & 0x3FFF) << 32;
+    d |= uint64_t(1) << 46;
+    d |= uint64_t(2) << 61;
+    return d;
+}
+__device__ __forceinline__ void umma_f16_ss(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile("{ .reg .pred p; setp.ne.b32 p, %4, 0; tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p; }" ::"r"(tmem_d),
+                 "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+                 : "memory");
+}
+
 template <int BN>
 __global__ void __launch_bounds__(GM_THREADS, 1)
 gram_tc_kernel(const __grid_constant__ CUtensorMap tmF, const float* __restrict__ masks, const int* __restrict__ patch_ids,
                const int* __restrict__ patch_off, float* __restrict__ ws, int H, int W, int C, int splits, int tiles,
-               int patches_w) {
+               int patches_w, const uint32_t* __restrict__ f_absmax, const uint32_t* __restrict__ m_absmax) {
     using Cfg = GramCfg<BN>;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + GM_STAGES * Cfg::STAGE_BYTES);
     uint64_t* full = bars;
-    uint64_t* ready = bars + GM_STAGES;
-    uint64_t* empty = bars + 2 * GM_STAGES;
-    uint64_t* chunk_full = bars + 3 * GM_STAGES;
+    uint64_t* ready = bars + 4;
+    uint64_t* empty = bars + 8;
+    uint64_t* chunk_full = bars + 12;
     uint64_t* chunk_empty = chunk_full + 2;
     uint64_t* small_full = chunk_empty + 2;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(small_full + 1);
@@ -70,6 +92,12 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap tmF, const float* __restrict_
     const int iters = my_end - my_begin;
     const int nchunks = (iters + GM_CHUNK_ITERS - 1) / GM_CHUNK_ITERS;
     const float* mk = masks ? masks + size_t(k) * H * W : nullptr;
+    // operand scale: max|F * m| <= max|F| * max|m|
+    int ex = tc::f16_scale_exponent(__ldg(f_absmax));
+    if (m_absmax != nullptr) {
+        const uint32_t mb = __ldg(m_absmax);
+        if (mb > 0x3F800000u) ex -= int(mb >> 23) - 127 + 1;          // masks above 1 (not produced by loss.py, but allowed)
+    }
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < GM_STAGES; ++s) {
@@ -114,12 +142,12 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap tmF, const float* __restrict_
         }
     } else if (warp == 1) {
         // ================= MMA issuer (warp-uniform loop, one elected lane issues; see conv_tc.cu) =================
-        constexpr uint32_t idesc = tc::umma_idesc_tf32(128, BN);
+        constexpr uint32_t idesc = tc::umma_idesc_f16(128, BN) | (1u << 15) | (1u << 16);      // A and B MN-major
         const uint32_t stage0 = tc::smem_u32(smem);
-        const uint64_t d_ahi = tc::umma_desc_kmajor_sw128(stage0 + Cfg::OFF_AHI, 1024);
-        const uint64_t d_alo = tc::umma_desc_kmajor_sw128(stage0 + Cfg::OFF_ALO, 1024);
-        const uint64_t d_bhi = diag ? d_ahi : tc::umma_desc_kmajor_sw128(stage0 + Cfg::OFF_BHI, 1024);
-        const uint64_t d_blo = diag ? d_alo : tc::umma_desc_kmajor_sw128(stage0 + Cfg::OFF_BLO, 1024);
+        const uint64_t d_ahi = umma_desc_mnmajor_sw128(stage0 + Cfg::OFF_AHI, GM_GROUP_BYTES, 1024);
+        const uint64_t d_alo = umma_desc_mnmajor_sw128(stage0 + Cfg::OFF_ALO, GM_GROUP_BYTES, 1024);
+        const uint64_t d_bhi = diag ? d_ahi : umma_desc_mnmajor_sw128(stage0 + Cfg::OFF_BHI, GM_GROUP_BYTES, 1024);
+        const uint64_t d_blo = diag ? d_alo : umma_desc_mnmajor_sw128(stage0 + Cfg::OFF_BLO, GM_GROUP_BYTES, 1024);
         int s = 0, round = 0;
         for (int it = 0; it < iters; ++it) {
             const int c = it / GM_CHUNK_ITERS, cpos = it - c * GM_CHUNK_ITERS;
@@ -130,11 +158,11 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap tmF, const float* __restrict_
             const uint64_t soff = uint64_t(uint32_t(s) * uint32_t(Cfg::STAGE_BYTES >> 4));
             if (tc::elect_one_sync()) {
 #pragma unroll
-                for (int ks = 0; ks < GM_PX / 8; ++ks) {                  // 8 pixels per MMA = 32 bytes along the K-major row
-                    const uint64_t koff = soff + uint64_t(ks * 2);
-                    tc::umma_tf32(tmem_small, d_alo + koff, d_bhi + koff, idesc, (it | ks) != 0);
-                    tc::umma_tf32(tmem_small, d_ahi + koff, d_blo + koff, idesc, 1);
-                    tc::umma_tf32(tmem_big, d_ahi + koff, d_bhi + koff, idesc, (cpos | ks) != 0);
+                for (int ks = 0; ks < GM_PX / 16; ++ks) {                 // 16 pixels per MMA = two 8-pixel groups (2048 bytes)
+                    const uint64_t koff = soff + uint64_t(ks * (2048 >> 4));
+                    umma_f16_ss(tmem_small, d_alo + koff, d_bhi + koff, idesc, (it | ks) != 0);
+                    umma_f16_ss(tmem_small, d_ahi + koff, d_blo + koff, idesc, 1);
+                    umma_f16_ss(tmem_big, d_ahi + koff, d_bhi + koff, idesc, (cpos | ks) != 0);
                 }
                 tc::umma_commit(&empty[s]);
                 if (cpos == GM_CHUNK_ITERS - 1 || it == iters - 1) tc::umma_commit(&chunk_full[c & 1]);
@@ -145,47 +173,50 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap tmF, const float* __restrict_
         if (iters > 0 && tc::elect_one_sync()) tc::umma_commit(small_full);
         __syncwarp();
     } else if (warp < 6) {
-        // ================= operand transform: X = m_k * F, split into TF32 hi / lo =================
+        // ================= operand transform: X = m_k * F * 2^ex, split into FP16 hi / lo =================
+        // Thread t owns pixel p = t % 32 and the channel quarter cq = t / 32 of the patch: it reads one 128-byte row of
+        // landed box cq and writes 64 bytes of the pixel's row in the hi tile and 64 bytes in the lo tile.
         const int t = threadIdx.x - 64;                                 // 0..127
+        const int p = t & 31, cq = t >> 5;
+        const float scale = tc::pow2f_int(ex);
+        // operand tile address of (channel group cq / 2, pixel p): + ((unit ^ (p & 7)) << 4) for 16-byte unit `unit`
+        const int orow = (cq >> 1) * GM_GROUP_BYTES + (p >> 3) * 1024 + (p & 7) * 128;
+        const int u0 = (cq & 1) * 4;
         for (int it = 0; it < iters; ++it) {
             const int s = it % GM_STAGES, round = it / GM_STAGES;
-            if (t < GM_PX) {
-                const int p = patch_ids[my_begin + it];
-                const int gy = (p / patches_w) * GM_PH + t / GM_PW, gx = (p % patches_w) * GM_PW + t % GM_PW;
-                float m = 0.f;
+            float m = 0.f;
+            {
+                const int pid = patch_ids[my_begin + it];
+                const int gy = (pid / patches_w) * GM_PH + p / GM_PW, gx = (pid % patches_w) * GM_PW + p % GM_PW;
                 if (gy < H && gx < W) m = mk ? __ldg(mk + size_t(gy) * W + gx) : 1.0f;
-                sMw[s * GM_PX + t] = m;
             }
-            asm volatile("bar.sync 1, 128;" ::: "memory");             // the four transform warps only
+            const float sm = m * scale;
             tc::mbar_wait(&full[s], round & 1);
-            const float* mw = sMw + s * GM_PX;
             uint8_t* st = smem + s * Cfg::STAGE_BYTES;
             const int nsets = diag ? 1 : 2;
             for (int set = 0; set < nsets; ++set) {
-                if (set == 1 && t >= BN) break;
-                // thread t owns channel row t of the operand: gathers its 32 pixels from the pixel-major landed tile
-                const uint8_t* raw = st + (set ? Cfg::OFF_RAW_B : 0) + (t >> 5) * GM_BLK_BYTES;
-                uint8_t* ohi = st + (set ? Cfg::OFF_BHI : Cfg::OFF_AHI) + (t >> 3) * 1024 + (t & 7) * 128;
-                uint8_t* olo = st + (set ? Cfg::OFF_BLO : Cfg::OFF_ALO) + (t >> 3) * 1024 + (t & 7) * 128;
-                const int col = t & 31;
+                if (set == 1 && cq * 32 >= BN) break;
+                const uint8_t* raw = st + (set ? Cfg::OFF_RAW_B : 0) + cq * GM_BLK_BYTES + p * 128;
+                uint8_t* ohi = st + (set ? Cfg::OFF_BHI : Cfg::OFF_AHI) + orow;
+                uint8_t* olo = st + (set ? Cfg::OFF_BLO : Cfg::OFF_ALO) + orow;
 #pragma unroll
-                for (int p4 = 0; p4 < GM_PX / 4; ++p4) {
-                    float x[4];
+                for (int u = 0; u < 4; ++u) {                            // 8 channels = one 16-byte unit of fp16
+                    // landed layout: row = pixel (128 B), 16-byte chunk index XOR (row & 7)
+                    const float4 v0 = *reinterpret_cast<const float4*>(raw + (((2 * u) ^ (p & 7)) << 4));
+                    const float4 v1 = *reinterpret_cast<const float4*>(raw + (((2 * u + 1) ^ (p & 7)) << 4));
+                    const float x[8] = {v0.x * sm, v0.y * sm, v0.z * sm, v0.w * sm, v1.x * sm, v1.y * sm, v1.z * sm, v1.w * sm};
+                    uint32_t hw[4], lw[4];
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
-                        const int px = p4 * 4 + j;
-                        // landed layout: row = pixel (128 B), 16-byte chunk index XOR (row & 7)
-                        const float v = *reinterpret_cast<const float*>(raw + px * 128 + ((((col >> 2) ^ (px & 7)) << 4) | ((col & 3) << 2)));
-                        x[j] = v * mw[px];
+                        const __half2 h = __floats2half2_rn(x[2 * j], x[2 * j + 1]);
+                        const float2 f = __half22float2(h);
+                        const __half2 l = __floats2half2_rn((x[2 * j] - f.x) * 2048.0f, (x[2 * j + 1] - f.y) * 2048.0f);
+                        hw[j] = *reinterpret_cast<const uint32_t*>(&h);
+                        lw[j] = *reinterpret_cast<const uint32_t*>(&l);
                     }
-                    float4 h, l;
-                    h.x = tc::round_tf32(x[0]); l.x = tc::round_tf32(x[0] - h.x);
-                    h.y = tc::round_tf32(x[1]); l.y = tc::round_tf32(x[1] - h.y);
-                    h.z = tc::round_tf32(x[2]); l.z = tc::round_tf32(x[2] - h.z);
-                    h.w = tc::round_tf32(x[3]); l.w = tc::round_tf32(x[3] - h.w);
-                    const int chunk = (p4 ^ (t & 7)) << 4;                 // operand layout: row = channel, same XOR swizzle
-                    *reinterpret_cast<float4*>(ohi + chunk) = h;
-                    *reinterpret_cast<float4*>(olo + chunk) = l;
+                    const int chunk = ((u0 + u) ^ (p & 7)) << 4;
+                    *reinterpret_cast<uint4*>(ohi + chunk) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+                    *reinterpret_cast<uint4*>(olo + chunk) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
                 }
             }
             tc::fence_proxy_async_smem();
@@ -217,6 +248,7 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap tmF, const float* __restrict_
             tc::mbar_wait(small_full, 0);
             tc::tcgen05_fence_after();
         }
+        const float inv_big = tc::pow2f_int(-2 * ex), inv_small = tc::pow2f_int(-2 * ex - 11);
         const int r = tm * 128 + q * 32 + lane;                         // Gram row (channel c1)
         float* out = ws + size_t(blockIdx.y) * C * C + size_t(r) * C + tn * BN;
 #pragma unroll
@@ -230,11 +262,11 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap tmF, const float* __restrict_
                 for (int j = 0; j < 32; ++j) v[j] = 0u;
             }
             if (q * 32 + lane < C - tm * 128) {                          // C == 64: rows 64..127 are duplicates
+                float o[32];
 #pragma unroll
-                for (int j = 0; j < 32; j += 4)
-                    *reinterpret_cast<float4*>(out + c0 + j) =
-                        make_float4(acc[c0 + j] + __uint_as_float(v[j]), acc[c0 + j + 1] + __uint_as_float(v[j + 1]),
-                                    acc[c0 + j + 2] + __uint_as_float(v[j + 2]), acc[c0 + j + 3] + __uint_as_float(v[j + 3]));
+                for (int j = 0; j < 32; ++j) o[j] = fmaf(__uint_as_float(v[j]), inv_small, acc[c0 + j] * inv_big);
+#pragma unroll
+                for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(out + c0 + j) = make_float4(o[j], o[j + 1], o[j + 2], o[j + 3]);
             }
         }
         tc::tcgen05_fence_before();
@@ -251,7 +283,8 @@ int gram_tc_tiles(int C) { return C <= 128 ? 1 : C / 128; }
 
 template <int BN>
 static int launch_gram_tc_t(const CUtensorMap& tmF, const float* masks, const int* patch_ids, const int* patch_off, float* ws,
-                            int H, int W, int C, int K, int splits, cudaStream_t st) {
+                            int H, int W, int C, int K, int splits, const uint32_t* f_absmax, const uint32_t* m_absmax,
+                            cudaStream_t st) {
     using Cfg = GramCfg<BN>;
     auto kern = gram_tc_kernel<BN>;
     static bool configured = false;
@@ -262,22 +295,23 @@ static int launch_gram_tc_t(const CUtensorMap& tmF, const float* masks, const in
     const int tiles = gram_tc_tiles(C);
     dim3 grid(tiles * (tiles + 1) / 2, K * splits);
     kern<<<grid, GM_THREADS, Cfg::SMEM_BYTES, st>>>(tmF, masks, patch_ids, patch_off, ws, H, W, C, splits, tiles,
-                                                    (W + GM_PW - 1) / GM_PW);
+                                                    (W + GM_PW - 1) / GM_PW, f_absmax, m_absmax);
     ADPST_LAUNCH_CHECK();
     return ADPST_OK;
 }
 
-// partial Grams of all classes into ws[(k*splits + s)][C][C] (upper-triangular 128-tiles only)
+// partial Grams of all classes into ws[(k*splits + s)][C][C] (upper-triangular 128-tiles only).
+// f_absmax: slot with max|F|; m_absmax: slot with max|mask| or NULL (all-ones mask).
 int launch_gram_tc(const float* F, int H, int W, int C, const float* masks, int K, const int* patch_ids, const int* patch_off,
-                   float* ws, int splits, cudaStream_t st) {
+                   float* ws, int splits, const uint32_t* f_absmax, const uint32_t* m_absmax, cudaStream_t st) {
     CUtensorMap tmF;
     const uint64_t dims[4] = {uint64_t(C), uint64_t(W), uint64_t(H), 1};
     const uint64_t strides[3] = {uint64_t(C) * 4, uint64_t(W) * C * 4, uint64_t(H) * W * C * 4};
     const uint32_t box[4] = {32u, uint32_t(GM_PW), uint32_t(GM_PH), 1};
     int rc = tc::make_tensor_map_f32(&tmF, F, 4, dims, strides, box);
     if (rc != ADPST_OK) return rc;
-    if (C == 64) return launch_gram_tc_t<64>(tmF, masks, patch_ids, patch_off, ws, H, W, C, K, splits, st);
-    return launch_gram_tc_t<128>(tmF, masks, patch_ids, patch_off, ws, H, W, C, K, splits, st);
+    if (C == 64) return launch_gram_tc_t<64>(tmF, masks, patch_ids, patch_off, ws, H, W, C, K, splits, f_absmax, m_absmax, st);
+    return launch_gram_tc_t<128>(tmF, masks, patch_ids, patch_off, ws, H, W, C, K, splits, f_absmax, m_absmax, st);
 }
 
 }  // namespace adpst

@@ -54,5 +54,5 @@ size_t style_tc_scratch_bytes(int HW);     // device scratch the style gradient 
 bool gram_tc_eligible(int C);
 int gram_tc_tiles(int C);
 int launch_gram_tc(const float* F, int H, int W, int C, const float* masks, int K, const int* patch_ids, const int* patch_off,
-                   float* ws, int splits, cudaStream_t st);
+                   float* ws, int splits, const uint32_t* f_absmax, const uint32_t* m_absmax, cudaStream_t st);
 }  // namespace adpst

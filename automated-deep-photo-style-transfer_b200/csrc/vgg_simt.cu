@@ -30,9 +30,10 @@ template <int MODE, bool PRE>
 __global__ void __launch_bounds__(CT_THREADS)
 conv3x3_simt_kernel(const float* __restrict__ X, const float* __restrict__ Wt, const float* __restrict__ bias,
                     float* __restrict__ Y, const float* __restrict__ seed, const float* __restrict__ mask_src,
-                    int H, int W, int Cin, int Cout, int tiles_w) {
-    __shared__ __align__(16) float sX[CT_K][CT_H + 2][CT_XP];
-    __shared__ __align__(16) float sW[9][CT_K][CT_N];
+                    int H, int W, int Cin, int Cout, int tiles_w, uint32_t* __restrict__ y_absmax) {
+    constexpr int KC = PRE ? 3 : CT_K;          // input channels per chunk: the RGB image is not padded to 8
+    __shared__ __align__(16) float sX[KC][CT_H + 2][CT_XP];
+    __shared__ __align__(16) float sW[9][KC][CT_N];
 
     const int tile = blockIdx.x;
     const int y0 = (tile / tiles_w) * CT_H, x0 = (tile % tiles_w) * CT_W;
@@ -47,7 +48,7 @@ conv3x3_simt_kernel(const float* __restrict__ X, const float* __restrict__ Wt, c
 #pragma unroll
         for (int n = 0; n < 8; ++n) acc[p][n] = 0.0f;
 
-    for (int ci0 = 0; ci0 < Cin; ci0 += CT_K) {
+    for (int ci0 = 0; ci0 < Cin; ci0 += KC) {
         // ---- stage the input halo tile, transposed to [ci][row][col]
         if (PRE) {
             for (int px = tid; px < (CT_H + 2) * (CT_W + 2); px += CT_THREADS) {
@@ -61,8 +62,6 @@ conv3x3_simt_kernel(const float* __restrict__ X, const float* __restrict__ Wt, c
                     v2 = 255.0f * q[0] - 123.68f;       // R
                 }
                 sX[0][r][c] = v0; sX[1][r][c] = v1; sX[2][r][c] = v2;
-#pragma unroll
-                for (int k = 3; k < CT_K; ++k) sX[k][r][c] = 0.f;
             }
         } else {
             for (int idx = tid; idx < (CT_H + 2) * (CT_W + 2) * 2; idx += CT_THREADS) {
@@ -72,14 +71,16 @@ conv3x3_simt_kernel(const float* __restrict__ X, const float* __restrict__ Wt, c
                 float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
                 if (gy >= 0 && gy < H && gx >= 0 && gx < W)
                     v = __ldg(reinterpret_cast<const float4*>(X + (size_t(gy) * W + gx) * Cin + ci0 + half * 4));
-                sX[half * 4 + 0][r][c] = v.x; sX[half * 4 + 1][r][c] = v.y;
-                sX[half * 4 + 2][r][c] = v.z; sX[half * 4 + 3][r][c] = v.w;
+                if (!PRE) {
+                    sX[half * 4 + 0][r][c] = v.x; sX[half * 4 + 1][r][c] = v.y;
+                    sX[half * 4 + 2][r][c] = v.z; sX[half * 4 + 3][r][c] = v.w;
+                }
             }
         }
         // ---- stage the weights of this chunk: [tap][ci][64]
-        for (int idx = tid; idx < 9 * CT_K * (CT_N / 4); idx += CT_THREADS) {
-            const int tap = idx / (CT_K * (CT_N / 4));
-            const int rem = idx - tap * (CT_K * (CT_N / 4));
+        for (int idx = tid; idx < 9 * KC * (CT_N / 4); idx += CT_THREADS) {
+            const int tap = idx / (KC * (CT_N / 4));
+            const int rem = idx - tap * (KC * (CT_N / 4));
             const int ci = rem / (CT_N / 4), n4 = rem - ci * (CT_N / 4);
             float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
             if (ci0 + ci < Cin)
@@ -90,8 +91,8 @@ conv3x3_simt_kernel(const float* __restrict__ X, const float* __restrict__ Wt, c
 
 #pragma unroll
         for (int kh = 0; kh < 3; ++kh) {
-#pragma unroll 2
-            for (int ci = 0; ci < CT_K; ++ci) {
+#pragma unroll(PRE ? 3 : 2)
+            for (int ci = 0; ci < KC; ++ci) {
                 float xv[10];
                 const float* xr = &sX[ci][row + kh][wseg];
                 const float4 a = *reinterpret_cast<const float4*>(xr);
@@ -116,8 +117,8 @@ conv3x3_simt_kernel(const float* __restrict__ X, const float* __restrict__ Wt, c
 
     // ---- epilogue
     const int gy = y0 + row;
-    if (gy >= H) return;
     const int nb = n0 + tx * 8;
+    float amax = 0.f;
     float bv[8];
     if (MODE == MODE_FWD) {
         const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias + nb));
@@ -127,7 +128,7 @@ conv3x3_simt_kernel(const float* __restrict__ X, const float* __restrict__ Wt, c
 #pragma unroll
     for (int p = 0; p < 8; ++p) {
         const int gx = x0 + wseg + p;
-        if (gx >= W) continue;
+        if (gx >= W || gy >= H) continue;
         const size_t o = (size_t(gy) * W + gx) * Cout + nb;
         float r[8];
         if (MODE == MODE_FWD) {
@@ -149,8 +150,14 @@ conv3x3_simt_kernel(const float* __restrict__ X, const float* __restrict__ Wt, c
                 for (int n = 0; n < 8; ++n) r[n] = mv[n] > 0.0f ? r[n] : 0.0f;
             }
         }
+#pragma unroll
+        for (int n = 0; n < 8; ++n) amax = fmaxf(amax, fabsf(r[n]));
         *reinterpret_cast<float4*>(Y + o) = make_float4(r[0], r[1], r[2], r[3]);
         *reinterpret_cast<float4*>(Y + o + 4) = make_float4(r[4], r[5], r[6], r[7]);
+    }
+    if (y_absmax != nullptr) {                  // max|Y| for the tensor-core consumer's FP16 scale (tc_common.cuh)
+        const uint32_t wm = __reduce_max_sync(0xffffffffu, __float_as_uint(amax));
+        if ((tid & 31) == 0 && wm != 0u) atomicMax(y_absmax, wm);
     }
 }
 
@@ -343,17 +350,17 @@ static void layer_hw(int conv, int H, int W, int* h, int* w) {
 }
 
 static int launch_conv_simt(int mode, bool pre, const float* X, const float* Wt, const float* bias, float* Y, const float* seed,
-                       const float* mask, int H, int W, int Cin, int Cout, cudaStream_t st) {
+                       const float* mask, int H, int W, int Cin, int Cout, uint32_t* y_absmax, cudaStream_t st) {
     ADPST_REQUIRE(Cout % CT_N == 0, "conv3x3: Cout=%d must be a multiple of %d", Cout, CT_N);
     ADPST_REQUIRE(pre || Cin % CT_K == 0, "conv3x3: Cin=%d must be a multiple of %d", Cin, CT_K);
     const int tw = (W + CT_W - 1) / CT_W, th = (H + CT_H - 1) / CT_H;
     dim3 grid(tw * th, Cout / CT_N);
     if (mode == MODE_FWD && pre)
-        conv3x3_simt_kernel<MODE_FWD, true><<<grid, CT_THREADS, 0, st>>>(X, Wt, bias, Y, seed, mask, H, W, Cin, Cout, tw);
+        conv3x3_simt_kernel<MODE_FWD, true><<<grid, CT_THREADS, 0, st>>>(X, Wt, bias, Y, seed, mask, H, W, Cin, Cout, tw, y_absmax);
     else if (mode == MODE_FWD)
-        conv3x3_simt_kernel<MODE_FWD, false><<<grid, CT_THREADS, 0, st>>>(X, Wt, bias, Y, seed, mask, H, W, Cin, Cout, tw);
+        conv3x3_simt_kernel<MODE_FWD, false><<<grid, CT_THREADS, 0, st>>>(X, Wt, bias, Y, seed, mask, H, W, Cin, Cout, tw, y_absmax);
     else
-        conv3x3_simt_kernel<MODE_BWD, false><<<grid, CT_THREADS, 0, st>>>(X, Wt, bias, Y, seed, mask, H, W, Cin, Cout, tw);
+        conv3x3_simt_kernel<MODE_BWD, false><<<grid, CT_THREADS, 0, st>>>(X, Wt, bias, Y, seed, mask, H, W, Cin, Cout, tw, y_absmax);
     ADPST_LAUNCH_CHECK();
     return ADPST_OK;
 }
@@ -361,8 +368,7 @@ static int launch_conv_simt(int mode, bool pre, const float* X, const float* Wt,
 // One convolution of the network: tensor-core path when the shape allows it, exact-fp32 CUDA-core path otherwise
 // (block1_conv1: Cin = 3) or when the handle was switched to CONV_PATH_SIMT (validation).
 // x_absmax: slot with max|X| (NULL: measured here with an extra pass over X); y_absmax (may be NULL): slot that receives
-// max|Y| (must have been zeroed).  The CUDA-core path neither needs nor produces them, so when it runs and the caller
-// wants max|Y| it is measured with a separate pass.
+// max|Y| (must have been zeroed; every kernel family records it in its epilogue).
 static int launch_conv(adpst_vgg* h, int i, int mode, const float* X, float* Y, const float* seed, const float* mask,
                        int lh, int lw, const uint32_t* x_absmax, uint32_t* y_absmax, cudaStream_t st) {
     const bool grad = (mode == MODE_BWD);
@@ -376,11 +382,8 @@ static int launch_conv(adpst_vgg* h, int i, int mode, const float* X, float* Y, 
         }
         return launch_conv_tc(h, i, grad ? 1 : 0, X, Y, seed, mask, lh, lw, K, N, x_absmax, y_absmax, st);
     }
-    int rc = launch_conv_simt(mode, i == 0 && !grad, X, grad ? h->wb[i] : h->wf[i], grad ? nullptr : h->bias[i], Y, seed, mask,
-                              lh, lw, K, N, st);
-    if (rc == ADPST_OK && y_absmax != nullptr)
-        rc = launch_absmax(Y, size_t(lh) * lw * N, y_absmax, st);
-    return rc;
+    return launch_conv_simt(mode, i == 0 && !grad, X, grad ? h->wb[i] : h->wf[i], grad ? nullptr : h->bias[i], Y, seed, mask,
+                            lh, lw, K, N, y_absmax, st);
 }
 
 }  // namespace adpst

@@ -94,7 +94,7 @@ def gram_patch_lists(masks, h, w, K, device):
     return ids, off
 
 
-def gram_masked(F, masks, K, workspace=None, patches=None, path="tensor", out=None):
+def gram_masked(F, masks, K, workspace=None, patches=None, path="tensor", out=None, f_absmax=None):
     """F: (h,w,C) float32 feature map ((HW,C) is taken as h = HW, w = 1); masks: (K,h*w) float32 or None.
     Returns (K,C,C) float32  (loss.py:96-102).  `patches` = gram_patch_lists(...) enables the tcgen05 kernel."""
     _f32(F, "F")
@@ -111,7 +111,8 @@ def gram_masked(F, masks, K, workspace=None, patches=None, path="tensor", out=No
     G = out if out is not None else torch.empty(K, C, C, dtype=torch.float32, device=F.device)
     ids, off = patches if patches is not None else (None, None)
     _lib.check(_lib.lib().adpst_gram_masked(_lib.ptr(F), h, w, C, _lib.ptr(masks), K, _lib.ptr(ids), _lib.ptr(off), _lib.ptr(G),
-                                            {"tensor": 0, "simt": 1}[path], _lib.ptr(ws), _lib.stream_ptr()))
+                                            {"tensor": 0, "simt": 1}[path], ctypes.c_void_p(f_absmax or 0), _lib.ptr(ws),
+                                            _lib.stream_ptr()))
     return G
 
 

@@ -142,13 +142,15 @@ int adpst_resize_bilinear(const float* src_dev, int Hs, int Ws, float* dst_dev, 
 
 /* loss.py:96-102 for K masks at once: G[k] = (F*m_k)^T (F*m_k).  F: (h,w,C) feature map; masks: (K,h*w) or NULL
  * (K==1, all ones); G: (K,C,C).  workspace_dev: at least adpst_gram_workspace_bytes(h*w,C,K) bytes.
- * path 0 (tcgen05 3xTF32): needs the list of 2x16-pixel patches on which each class mask is non-zero --
+ * path 0 (tcgen05 3xFP16): needs the list of 2x16-pixel patches on which each class mask is non-zero --
  *   patch_ids_dev: int32 patch indices (row-major over ceil(h/2) x ceil(w/16) patches) grouped by class,
  *   patch_off_dev: int32[K+1] offsets into it.  The masks are constant, so the caller builds the list once.
- * path 1, or NULL lists: exact-float32 CUDA-core kernel. */
+ * path 1, or NULL lists: exact-float32 CUDA-core kernel.
+ * F_absmax_dev: slot holding max|F| (adpst_vgg_act_absmax / adpst_absmax), or NULL to have it measured here. */
 size_t adpst_gram_workspace_bytes(int HW, int C, int K);
 int adpst_gram_masked(const float* F_dev, int h, int w, int C, const float* masks_dev, int K, const int* patch_ids_dev,
-                      const int* patch_off_dev, float* G_dev, int path, void* workspace_dev, adpst_stream_t stream);
+                      const int* patch_off_dev, float* G_dev, int path, const uint32_t* F_absmax_dev, void* workspace_dev,
+                      adpst_stream_t stream);
 
 /* loss.py:104-137 for one layer, forward value and gradient seed.  With
  *   L = sum_k mean((A_k - G_k)^2) / (2 C^2 HW^2):

@@ -47,9 +47,13 @@ def test_tiled_matches_single_device(world, W, K, synth):
     ranks = [tiled.TiledStyleTransfer(content, style, args, cm, sm, weights, r, world, reduce_sum=lambda t: None,
                                       gather=lambda s: None) for r in range(world)]
     got = tiled.run_emulated(ranks, 3)
+    # Iteration 0 evaluates identical images: 2e-5.  Afterwards the images themselves may differ in a few pixels: Adam's first
+    # steps are +-lr * sign(g), so a last-bit difference in a gradient that is ~0 moves that pixel by 2 lr (the image check
+    # below counts such flips); the loss values of later iterations are therefore only comparable to ~1e-4.
     for it in range(3):
+        tol = 2e-5 if it == 0 else 5e-4
         for name, v in ref[it].items():
-            assert abs(got[it][name] - v) <= 2e-5 * abs(v) + 1e-9, (it, name, got[it][name], v)
+            assert abs(got[it][name] - v) <= tol * abs(v) + 1e-9, (it, name, got[it][name], v)
     stitched = torch.cat([r.own_strip() for r in ranks], dim=1)
     diff = (stitched - x[0]).abs()
     assert float((diff > 1e-3).float().mean()) < 1e-3          # Adam steps of +-lr: count flips, do not take the max
