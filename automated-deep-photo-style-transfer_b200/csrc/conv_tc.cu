@@ -87,7 +87,9 @@ int make_tensor_map_f16(CUtensorMap* out, const void* base, int rank, const uint
 // ---------------------------------------------------------------------------------------------------------------
 constexpr int TC_TH = 8, TC_TW = 16, TC_BM = TC_TH * TC_TW;     // 128 pixels = UMMA M
 constexpr int TC_BK = 64;                                        // K per stage: 64 fp16 = one 128-byte swizzle row of B
-constexpr int TC_THREADS = 352;                                  // TMA, MMA(big), 4 transform, 4 drain/epilogue, MMA(small)
+constexpr int TC_THREADS = 512;                                  // 4 warpgroups: {TMA, MMA big, MMA small, -}, transform x2, drain
+// registers per thread after setmaxnreg (the launch gives every thread 65536 / 512 = 128):
+constexpr int TC_REGS_CTRL = 40, TC_REGS_XFORM = 112, TC_REGS_DRAIN = 224;     // 128 * (40 + 2 * 112 + 224) = 62464 <= 65536
 constexpr int TC_HW = TC_TW + 2, TC_HH = TC_TH + 2;              // the tile plus its 1-pixel halo: 18 x 10 pixels
 constexpr int TC_A_BOX_BYTES = 23 * 1024;                        // one landed box: 180 halo pixels x 32 channels fp32 = 23040 B,
                                                                  // padded to the 1024-byte alignment of the 128-byte swizzle
@@ -169,7 +171,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     if (threadIdx.x == 0) {
         for (int s = 0; s < AST; ++s) {
             tc::mbar_init(&full[s], 1);
-            tc::mbar_init(&a_empty[s], 128);
+            tc::mbar_init(&a_empty[s], 256);        // both transform warpgroups
         }
         for (int s = 0; s < BST; ++s) {
             tc::mbar_init(&ready[s], 128 + 1);      // 128 transform threads + the producer's expect_tx arrival (B bytes)
@@ -201,8 +203,11 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     // w_k = m_k^2; the per-tile class sets come from style_tiles_kernel).
     auto item_active = [&](int tile) -> uint32_t { return MODE == MODE_STYLE ? __ldg(tile_active + tile) : 0x1FFu; };
 
+    // Register budget per role (setmaxnreg, whole warpgroups): the control warps need almost none, the drain warps hold a
+    // 128 x BN fp32 tile row.
     if (warp == 0) {
         // ================= TMA producer =================
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(TC_REGS_CTRL));
         if (lane == 0) {
             int sa = 0, ra = 0, s = 0, round = 0;                      // A ring slot / phase, B ring slot / phase
             for (int w = blockIdx.x; w < total; w += gridDim.x) {
@@ -236,10 +241,11 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         // Issuing one tcgen05.mma costs the issuing thread 40-48 clk (measured, tests/cuda/umma_queue_probe.cu) while a
         // 128x128x16 FP16 MMA executes in 64 clk, so ONE thread that also has ~240 clk of barrier work per stage cannot
         // keep the pipe fed with 12 MMAs per stage.  The issue is therefore split over two warps that own DIFFERENT
-        // accumulators (no cross-thread ordering needed): this warp issues a_hi*b_hi into the chunk buffers, warp 10
+        // accumulators (no cross-thread ordering needed): this warp issues a_hi*b_hi into the chunk buffers, warp 2
         // issues the two small terms.  Both commit to empty[] / a_free[] (arrival count 2).
         // The whole warp runs the loop (warp-uniform control flow, descriptors in uniform registers); one elected lane
         // issues.  Descriptors are built once: per stage and K-step only the 14-bit address field changes.
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(TC_REGS_CTRL));
         constexpr uint32_t idesc = tc::umma_idesc_f16(TC_BM, BN);
         const uint32_t stage0 = tc::smem_u32(smem);
         const uint64_t d_bhi = tc::umma_desc_kmajor_sw128(stage0 + Cfg::OFF_B, 1024);
@@ -270,8 +276,9 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                 if (++s == BST) { s = 0; ++round; }
             }
         }
-    } else if (warp == 10) {
+    } else if (warp == 2) {
         // ================= MMA issuer, small terms: a_lo*b_hi + a_hi*b_lo into the item-long accumulator =================
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(TC_REGS_CTRL));
         constexpr uint32_t idesc = tc::umma_idesc_f16(TC_BM, BN);
         const uint32_t stage0 = tc::smem_u32(smem);
         const uint64_t d_bhi = tc::umma_desc_kmajor_sw128(stage0 + Cfg::OFF_B, 1024);
@@ -305,12 +312,19 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             }
             ++sj;
         }
-    } else if (warp < 6) {
-        // ================= operand transform =================
+    } else if (warp == 3) {
+        // (idle: completes the control warpgroup so that setmaxnreg applies to whole warpgroups)
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(TC_REGS_CTRL));
+    } else if (warp < 12) {
+        // ================= operand transform (two warpgroups, alternating stages) =================
         // Thread (warp w, lane l) owns row m = 32 (w & 3) + l of the A tile (= TMEM lane m).  It reads the row's 64 floats
-        // from the two landed boxes (undoing the 128-byte swizzle), scales them into FP16 range, splits them into hi / lo
+        // from the halo tile (undoing the 128-byte swizzle), scales them into FP16 range, splits them into hi / lo
         // and stores both, packed two per 32-bit column, into tensor memory: the MMA then takes A from TMEM, which removes
         // every A operand read from shared memory (the kernel was shared-memory-bandwidth bound with A in smem).
+        // One stage of this loop (16 loads, ~350 arithmetic instructions, tcgen05.st + wait) takes longer than the 768 clk
+        // its MMAs need, so warpgroup g handles the stages with (global stage index & 1) == g and owns TMEM A slot g.
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(TC_REGS_XFORM));
+        const int grp = (warp - 4) >> 2;
         const int q = warp & 3;
         const int m = q * 32 + lane;
         const uint32_t lane_base = uint32_t(q * 32) << 16;
@@ -326,6 +340,10 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             for (int kc = 0; kc < kchunks; ++kc) {
                 tc::mbar_wait(&full[sa], ra & 1);
                 for (int slot = 0; slot < ntaps; ++slot, ++git) {
+                    if ((git & 1) != grp) {                                 // the other warpgroup's stage
+                        if (++s == BST) s = 0;
+                        continue;
+                    }
                     float scl = scale_a;
                     int kh = 1, kw = 1;
                     if (MODE == MODE_STYLE) {
@@ -373,8 +391,9 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                 if (++sa == AST) { sa = 0; ++ra; }
             }
         }
-    } else if (warp < 10) {
+    } else {
         // ================= drain (chunk promotion) + epilogue =================
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(TC_REGS_DRAIN));
         const int q = warp & 3;                                        // TMEM lane quarter this warp may read
         const uint32_t lane_base = uint32_t(q * 32) << 16;
         const float inv_big = tc::pow2f_int(-(ea + eb)), inv_small = tc::pow2f_int(-(ea + eb) - 11);
