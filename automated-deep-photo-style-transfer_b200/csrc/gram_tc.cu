@@ -27,7 +27,8 @@ namespace adpst {
 
 constexpr int GM_PH = 2, GM_PW = 16, GM_PX = GM_PH * GM_PW;     // 32 pixels per stage = 2 UMMA K-steps of 16
 constexpr int GM_BLK_BYTES = GM_PX * 128;                        // one landed box (32 channels x 32 pixels fp32): 4 KB
-constexpr int GM_THREADS = 320;
+constexpr int GM_THREADS = 512;                                  // 4 warpgroups: {TMA, MMA, -, -}, transform x2, drain
+constexpr int GM_REGS_CTRL = 40, GM_REGS_XFORM = 112, GM_REGS_DRAIN = 224;      // setmaxnreg budget, as in conv_tc.cu
 constexpr int GM_CHUNK_ITERS = 4;                                // stages per promoted chunk (8 big MMAs)
 constexpr int GM_STAGES = 3;
 constexpr int GM_GROUP_BYTES = (GM_PX / 8) * 1024;               // one 64-channel group of an operand tile: 4 KB
@@ -40,7 +41,7 @@ template <int BN> struct GramCfg {
     static constexpr int OFF_RAW_B = RAW_A, OFF_AHI = RAW_A + RAW_B, OFF_ALO = OFF_AHI + A_BYTES, OFF_BHI = OFF_ALO + A_BYTES,
                          OFF_BLO = OFF_BHI + B_BYTES;
     static constexpr int STAGE_BYTES = OFF_BLO + B_BYTES;
-    static constexpr int SMEM_BYTES = GM_STAGES * STAGE_BYTES + 1024 + 256 + GM_STAGES * GM_PX * 4;
+    static constexpr int SMEM_BYTES = GM_STAGES * STAGE_BYTES + 1024 + 256;
     static constexpr uint32_t TMEM_COLS = 4 * BN;
 };
 
@@ -77,7 +78,6 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap tmF, const float* __restrict_
     uint64_t* chunk_empty = chunk_full + 2;
     uint64_t* small_full = chunk_empty + 2;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(small_full + 1);
-    float* sMw = reinterpret_cast<float*>(bars + 32);                  // [GM_STAGES][32] mask value per pixel of the patch
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     // tile pair (tm <= tn) in units of BN... the M side is always 128 channels, the N side BN channels
@@ -122,6 +122,7 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap tmF, const float* __restrict_
 
     if (warp == 0) {
         // ================= TMA producer =================
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(GM_REGS_CTRL));
         if (lane == 0) {
             for (int it = 0; it < iters; ++it) {
                 const int s = it % GM_STAGES, round = it / GM_STAGES;
@@ -142,6 +143,7 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap tmF, const float* __restrict_
         }
     } else if (warp == 1) {
         // ================= MMA issuer (warp-uniform loop, one elected lane issues; see conv_tc.cu) =================
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(GM_REGS_CTRL));
         constexpr uint32_t idesc = tc::umma_idesc_f16(128, BN) | (1u << 15) | (1u << 16);      // A and B MN-major
         const uint32_t stage0 = tc::smem_u32(smem);
         const uint64_t d_ahi = umma_desc_mnmajor_sw128(stage0 + Cfg::OFF_AHI, GM_GROUP_BYTES, 1024);
@@ -172,25 +174,34 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap tmF, const float* __restrict_
         }
         if (iters > 0 && tc::elect_one_sync()) tc::umma_commit(small_full);
         __syncwarp();
-    } else if (warp < 6) {
+    } else if (warp < 4) {
+        // (idle: completes the control warpgroup so that setmaxnreg applies to whole warpgroups)
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(GM_REGS_CTRL));
+    } else if (warp < 12) {
         // ================= operand transform: X = m_k * F * 2^ex, split into FP16 hi / lo =================
+        // Two warpgroups on alternating stages (one stage of this loop takes longer than its MMAs).
         // Thread t owns pixel p = t % 32 and the channel quarter cq = t / 32 of the patch: it reads one 128-byte row of
         // landed box cq and writes 64 bytes of the pixel's row in the hi tile and 64 bytes in the lo tile.
-        const int t = threadIdx.x - 64;                                 // 0..127
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(GM_REGS_XFORM));
+        const int grp = (warp - 4) >> 2;
+        const int t = (threadIdx.x - 128) & 127;                        // 0..127 within the warpgroup
         const int p = t & 31, cq = t >> 5;
         const float scale = tc::pow2f_int(ex);
         // operand tile address of (channel group cq / 2, pixel p): + ((unit ^ (p & 7)) << 4) for 16-byte unit `unit`
         const int orow = (cq >> 1) * GM_GROUP_BYTES + (p >> 3) * 1024 + (p & 7) * 128;
         const int u0 = (cq & 1) * 4;
-        for (int it = 0; it < iters; ++it) {
+        auto mask_of = [&](int it) -> float {                           // this pixel's mask value in the patch of stage `it`
+            if (it >= iters) return 0.f;
+            const int pid = patch_ids[my_begin + it];
+            const int gy = (pid / patches_w) * GM_PH + p / GM_PW, gx = (pid % patches_w) * GM_PW + p % GM_PW;
+            if (gy < H && gx < W) return mk ? __ldg(mk + size_t(gy) * W + gx) : 1.0f;
+            return 0.f;
+        };
+        float m_next = mask_of(grp);
+        for (int it = grp; it < iters; it += 2) {
             const int s = it % GM_STAGES, round = it / GM_STAGES;
-            float m = 0.f;
-            {
-                const int pid = patch_ids[my_begin + it];
-                const int gy = (pid / patches_w) * GM_PH + p / GM_PW, gx = (pid % patches_w) * GM_PW + p % GM_PW;
-                if (gy < H && gx < W) m = mk ? __ldg(mk + size_t(gy) * W + gx) : 1.0f;
-            }
-            const float sm = m * scale;
+            const float sm = m_next * scale;
+            m_next = mask_of(it + 2);                                   // the dependent global loads of the next stage, early
             tc::mbar_wait(&full[s], round & 1);
             uint8_t* st = smem + s * Cfg::STAGE_BYTES;
             const int nsets = diag ? 1 : 2;
@@ -224,6 +235,7 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap tmF, const float* __restrict_
         }
     } else {
         // ================= drain (chunk promotion) + store of the partial tile =================
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(GM_REGS_DRAIN));
         const int q = warp & 3;
         const uint32_t lane_base = uint32_t(q * 32) << 16;
         float acc[BN];
