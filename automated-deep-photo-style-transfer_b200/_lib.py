@@ -49,8 +49,10 @@ SIGNATURES = {
     "adpst_vgg_backward": (_i, [_vp, _i, _i, _pp, _pp, _pp, _i, _vp, _vp, _vp, _vp]),
     "adpst_resize_bilinear": (_i, [_vp, _i, _i, _vp, _i, _i, _vp]),
     "adpst_gram_workspace_bytes": (_sz, [_i, _i, _i]),
-    "adpst_gram_masked": (_i, [_vp, _i, _i, _i, _vp, _i, _vp, _vp, _vp, _i, _vp, _vp, _vp]),
-    "adpst_style_layer_backward": (_i, [_vp, _i, _i, _i, _vp, _i, _vp, _vp, _d, _d, _vp, _vp, _i, _i, _d, _vp, _vp, _vp]),
+    "adpst_gram_masked": (_i, [_vp, _i, _i, _i, _vp, _i, _vp, _vp, _vp, _i, _vp, _vp, _vp, _vp]),
+    "adpst_style_layer_backward": (_i, [_vp, _i, _i, _i, _vp, _i, _vp, _vp, _d, _d, _vp, _vp, _i, _i, _d, _vp, _vp, _vp, _vp]),
+    "adpst_style_tiles_bytes": (_sz, [_i]),
+    "adpst_style_tiles": (_i, [_vp, _i, _i, _i, _vp, _vp]),
     "adpst_content_layer": (_i, [_vp, _vp, _sz, _d, _d, _vp, _vp, _i, _d, _i, _i, _i, _i, _vp]),
     "adpst_loss_finalize": (_i, [_vp, _d, _d, _d, _vp, _vp]),
     "adpst_axpby": (_i, [_vp, _vp, _f, _vp, _f, _sz, _vp]),

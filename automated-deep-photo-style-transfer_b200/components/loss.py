@@ -112,6 +112,8 @@ class Loss:
                                 patches=kernels.gram_patch_lists(sm_own, hs, ws_, K, self.device))   # constant style Grams
         st = {"shape": tuple(output.shape), "K": K, "masks": cm, "own_masks": cm_own, "A": A, "ws": ws,
               "seed": torch.empty_like(output), "patches": kernels.gram_patch_lists(cm_own, h, w, K, self.device),
+              "tiles": kernels.style_tiles(cm, K, h, w, self.device),
+              "own_masks_absmax": kernels.absmax_slot(cm_own) if cm_own is not None else None,
               "G": torch.empty(K, C, C, dtype=torch.float32, device=self.device),
               "hw_norm": float(h * self.tile.global_cols(w)) if self.tile is not None else 0.0}
         self._layer_cache[name] = st
@@ -157,7 +159,8 @@ class Loss:
             st = self._style_layer_state(name, target, out)
             _, h, w, C = out.shape
             partials.append(kernels.gram_masked(out.reshape(h, w, C), st["own_masks"], st["K"], st["ws"],
-                                                patches=st["patches"], out=st["G"], f_absmax=kernels.act_absmax_slot(out)))
+                                                patches=st["patches"], out=st["G"], f_absmax=kernels.act_absmax_slot(out),
+                                                masks_absmax=st["own_masks_absmax"]))
         self._photo_grad = None
         if wts['photo'] > 0:                                                  # loss.py:67-69, :157-161
             if self.matting_laplacian is None:
@@ -181,7 +184,8 @@ class Loss:
             dF = seeds[name] if shared else st["seed"]
             kernels.style_layer_backward(out.reshape(h, w, C), st["masks"], st["K"], st["G"], st["A"], 1.0 / n_args,
                                          wts['style'] / n_args, self._acc[1:2], dF.reshape(h * w, C), accumulate=shared,
-                                         workspace=st["ws"], hw_norm=st["hw_norm"], f_absmax=kernels.act_absmax_slot(out))
+                                         workspace=st["ws"], hw_norm=st["hw_norm"], f_absmax=kernels.act_absmax_slot(out),
+                                         tiles=st["tiles"])
             seeds[name] = dF
         kernels.loss_finalize(self._acc, wts['content'], wts['style'], wts['photo'], self._out)   # loss.py:72
         self._seeds = seeds

@@ -666,9 +666,21 @@ bool style_tc_eligible(int C) { return C == 64 || C % 128 == 0; }
 
 size_t style_tc_scratch_bytes(int HW) { return size_t(HW) * 4 + 64; }
 
-// scratch: style_tc_scratch_bytes(H*W) bytes of device memory (per-tile class sets and the weight slot)
+// per-tile class sets of a (constant) mask stack: tiles[0] = float bits of the largest class weight, tiles[16 + t] = classes
+// present in 8x16-pixel tile t.  `tiles` holds style_tc_scratch_bytes(H*W) bytes.
+int launch_style_tiles(const float* masks, int K, int H, int W, void* tiles, cudaStream_t st) {
+    ADPST_REQUIRE(K >= 1 && K <= TC_MAX_CLASSES, "style gradient: K=%d classes not supported (max %d)", K, TC_MAX_CLASSES);
+    const int tw = (W + TC_TW - 1) / TC_TW, th = (H + TC_TH - 1) / TC_TH;
+    uint32_t* wslot = static_cast<uint32_t*>(tiles);
+    ADPST_CUDA_CHECK(cudaMemsetAsync(wslot, 0, sizeof(uint32_t), st));
+    style_tiles_kernel<<<tw * th, TC_BM, 0, st>>>(masks, K, H, W, tw, wslot + 16, wslot);
+    ADPST_LAUNCH_CHECK();
+    return ADPST_OK;
+}
+
+// tiles: the buffer launch_style_tiles filled for these masks
 int launch_style_dF_tc(const float* F, int H, int W, int C, const float* masks, int K, const void* D_hi, const void* D_lo,
-                       const uint32_t* f_absmax, const uint32_t* d_absmax, float* dF, int accumulate, void* scratch,
+                       const uint32_t* f_absmax, const uint32_t* d_absmax, float* dF, int accumulate, const void* tiles,
                        cudaStream_t st) {
     ADPST_REQUIRE(K >= 1 && K <= TC_MAX_CLASSES, "style gradient: K=%d classes not supported (max %d)", K, TC_MAX_CLASSES);
     CUtensorMap tmA, tmH, tmL;
@@ -682,12 +694,8 @@ int launch_style_dF_tc(const float* F, int H, int W, int C, const float* masks, 
     if (rc != ADPST_OK) return rc;
     rc = tc::make_tensor_map_f16(&tmL, D_lo, 2, ddims, dstr, dbox);
     if (rc != ADPST_OK) return rc;
-    const int tw = (W + TC_TW - 1) / TC_TW, th = (H + TC_TH - 1) / TC_TH;
-    uint32_t* wslot = static_cast<uint32_t*>(scratch);
-    uint32_t* tile_active = wslot + 16;
-    ADPST_CUDA_CHECK(cudaMemsetAsync(wslot, 0, sizeof(uint32_t), st));
-    style_tiles_kernel<<<tw * th, TC_BM, 0, st>>>(masks, K, H, W, tw, tile_active, wslot);
-    ADPST_LAUNCH_CHECK();
+    const uint32_t* wslot = static_cast<const uint32_t*>(tiles);
+    const uint32_t* tile_active = wslot + 16;
     const float* seed = accumulate ? dF : nullptr;
     if (BN == 128)
         return launch_tc<128, MODE_STYLE>(tmA, tmH, tmL, nullptr, dF, seed, nullptr, H, W, C, C, f_absmax, d_absmax, nullptr, st,

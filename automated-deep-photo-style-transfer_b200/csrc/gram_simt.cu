@@ -241,8 +241,8 @@ size_t adpst_gram_workspace_bytes(int HW, int C, int K) {
 }
 
 int adpst_gram_masked(const float* F_dev, int h, int w, int C, const float* masks_dev, int K, const int* patch_ids_dev,
-                      const int* patch_off_dev, float* G_dev, int path, const uint32_t* F_absmax_dev, void* workspace_dev,
-                      adpst_stream_t stream) {
+                      const int* patch_off_dev, float* G_dev, int path, const uint32_t* F_absmax_dev,
+                      const uint32_t* masks_absmax_dev, void* workspace_dev, adpst_stream_t stream) {
     using namespace adpst;
     ADPST_REQUIRE(F_dev && G_dev && workspace_dev, "gram_masked: NULL argument");
     ADPST_REQUIRE(h > 0 && w > 0 && K > 0, "gram_masked: empty input");
@@ -256,14 +256,17 @@ int adpst_gram_masked(const float* F_dev, int h, int w, int C, const float* mask
         // two scale slots behind the partial tiles: max|mask| and, if the caller has no slot for it, max|F|
         uint32_t* slots = reinterpret_cast<uint32_t*>(static_cast<float*>(workspace_dev) + size_t(K) * splits * C * C);
         int rc = ADPST_OK;
-        if (masks_dev != nullptr) rc = launch_absmax(masks_dev, size_t(K) * HW, slots, st);
+        if (masks_dev != nullptr && masks_absmax_dev == nullptr) {
+            rc = launch_absmax(masks_dev, size_t(K) * HW, slots, st);
+            masks_absmax_dev = slots;
+        }
         if (rc == ADPST_OK && F_absmax_dev == nullptr) {
             rc = launch_absmax(F_dev, size_t(HW) * C, slots + 1, st);
             F_absmax_dev = slots + 1;
         }
         if (rc == ADPST_OK)
             rc = launch_gram_tc(F_dev, h, w, C, masks_dev, K, patch_ids_dev, patch_off_dev, static_cast<float*>(workspace_dev),
-                                splits, F_absmax_dev, masks_dev ? slots : nullptr, st);
+                                splits, F_absmax_dev, masks_dev ? masks_absmax_dev : nullptr, st);
         if (rc != ADPST_OK) return rc;
     } else {
         splits = gram_splits(HW, C, K);
@@ -282,8 +285,8 @@ int adpst_gram_masked(const float* F_dev, int h, int w, int C, const float* mask
 
 int adpst_style_layer_backward(const float* F_dev, int h, int w, int C, const float* masks_dev, int K, const float* G_dev,
                                const float* A_dev, double loss_scale, double grad_scale, double* loss_dev, float* dF_dev,
-                               int accumulate, int path, double hw_norm, const uint32_t* F_absmax_dev, void* workspace_dev,
-                               adpst_stream_t stream) {
+                               int accumulate, int path, double hw_norm, const uint32_t* F_absmax_dev, const void* tiles_dev,
+                               void* workspace_dev, adpst_stream_t stream) {
     using namespace adpst;
     ADPST_REQUIRE(F_dev && G_dev && A_dev && workspace_dev, "style_layer_backward: NULL argument");
     ADPST_REQUIRE(h > 0 && w > 0 && K > 0, "style_layer_backward: empty input");
@@ -315,14 +318,27 @@ int adpst_style_layer_backward(const float* F_dev, int h, int w, int C, const fl
                 if (rc != ADPST_OK) return rc;
                 F_absmax_dev = slots + 1;
             }
-            return launch_style_dF_tc(F_dev, h, w, C, masks_dev, K, Dhi, Dlo, F_absmax_dev, slots, dF_dev, accumulate, slots + 16,
-                                      st);
+            if (tiles_dev == nullptr) {                      // the caller did not precompute the class sets of its masks
+                int rc = launch_style_tiles(masks_dev, K, h, w, slots + 16, st);
+                if (rc != ADPST_OK) return rc;
+                tiles_dev = slots + 16;
+            }
+            return launch_style_dF_tc(F_dev, h, w, C, masks_dev, K, Dhi, Dlo, F_absmax_dev, slots, dF_dev, accumulate, tiles_dev, st);
         }
         dim3 grid((HW + GT - 1) / GT, C / GT);
         style_dF_kernel<<<grid, GTHREADS, 0, st>>>(F_dev, masks_dev, D, dF_dev, HW, C, K, accumulate);
         ADPST_LAUNCH_CHECK();
     }
     return ADPST_OK;
+}
+
+size_t adpst_style_tiles_bytes(int HW) { return HW > 0 ? adpst::style_tc_scratch_bytes(HW) : 0; }
+
+int adpst_style_tiles(const float* masks_dev, int K, int h, int w, void* tiles_dev, adpst_stream_t stream) {
+    using namespace adpst;
+    ADPST_REQUIRE(tiles_dev && h > 0 && w > 0 && K > 0, "style_tiles: bad argument");
+    ADPST_REQUIRE(masks_dev || K == 1, "style_tiles: K=%d needs masks", K);
+    return launch_style_tiles(masks_dev, K, h, w, tiles_dev, as_stream(stream));
 }
 
 }  // extern "C"

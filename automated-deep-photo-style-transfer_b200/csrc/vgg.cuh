@@ -47,9 +47,10 @@ int launch_absmax(const float* x, size_t n, uint32_t* slot, cudaStream_t st);
 // scaled by the power of two of *d_absmax; *f_absmax = max|F|
 bool style_tc_eligible(int C);
 int launch_style_dF_tc(const float* F, int H, int W, int C, const float* masks, int K, const void* D_hi, const void* D_lo,
-                       const uint32_t* f_absmax, const uint32_t* d_absmax, float* dF, int accumulate, void* scratch,
+                       const uint32_t* f_absmax, const uint32_t* d_absmax, float* dF, int accumulate, const void* tiles,
                        cudaStream_t st);
-size_t style_tc_scratch_bytes(int HW);     // device scratch the style gradient needs (per-tile class sets)
+size_t style_tc_scratch_bytes(int HW);     // size of the per-tile class-set buffer of an H*W-pixel mask stack
+int launch_style_tiles(const float* masks, int K, int H, int W, void* tiles, cudaStream_t st);
 // masked Gram partials on the tensor cores (gram_tc.cu)
 bool gram_tc_eligible(int C);
 int gram_tc_tiles(int C);

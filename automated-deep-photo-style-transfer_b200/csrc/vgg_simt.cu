@@ -166,13 +166,17 @@ conv3x3_simt_kernel(const float* __restrict__ X, const float* __restrict__ Wt, c
 //   dImg[p, rgb] = 255 * sum_{tap, co} dPre[p + tap - 1, co] * W[2-kh][2-kw][ci = 2 - rgb][co]
 // Wg: [tap'][3 (rgb)][64] already flipped / permuted / scaled by 255.
 // ---------------------------------------------------------------------------------------------
-// 16 x 32 pixel tile per CTA; the 18 x 34 x 64 halo of dPre is staged in shared memory in two 32-channel halves
-// (78 KB each would not leave room for two CTAs per SM), so every dPre value is read from HBM/L2 ~1.2 times instead of 9.
-constexpr int IG_TH = 16, IG_TW = 32, IG_CH = 32;
+// 16 x 32 pixel tile per CTA, 128 threads; thread (warp w, lane l) owns the four pixels (4w .. 4w+3, l).  The 18 x 34 halo of
+// dPre is staged in shared memory 16 channels at a time (49 KB: four CTAs per SM), so every dPre value is read from
+// HBM/L2 ~1.2 times instead of 9.  Register blocking over four rows matters because the kernel is bound by shared-memory
+// wavefronts, not FMAs: per (kw, 4 channels) a thread issues 6 dPre loads + 9 broadcast weight loads for 144 FMAs
+// (one pixel per thread would need 7 loads for 12).
+constexpr int IG_TH = 16, IG_TW = 32, IG_CH = 16, IG_ROWS = 4;
+constexpr int IG_THREADS = (IG_TH / IG_ROWS) * IG_TW;
 constexpr int IG_PITCH = IG_CH + 4;                   // floats per staged pixel (16-byte aligned, bank-skewed)
 constexpr int IG_SMEM = (IG_TH + 2) * (IG_TW + 2) * IG_PITCH * 4 + 9 * 3 * 64 * 4;
 
-__global__ void __launch_bounds__(512)
+__global__ void __launch_bounds__(IG_THREADS)
 conv1_dgrad_image_kernel(const float* __restrict__ dPre, const float* __restrict__ Wg, float* __restrict__ dImg, int H,
                          int W) {
     extern __shared__ __align__(16) float ig_smem[];
@@ -180,9 +184,11 @@ conv1_dgrad_image_kernel(const float* __restrict__ dPre, const float* __restrict
     float* sW = ig_smem + (IG_TH + 2) * (IG_TW + 2) * IG_PITCH;       // [tap][rgb][64]
     for (int i = threadIdx.x; i < 9 * 3 * 64; i += blockDim.x) sW[i] = Wg[i];
     const int x0 = blockIdx.x * IG_TW, y0 = blockIdx.y * IG_TH;
-    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-    float a0 = 0.f, a1 = 0.f, a2 = 0.f;
-    for (int half = 0; half < 64 / IG_CH; ++half) {
+    const int tx = threadIdx.x & 31, ty = (threadIdx.x >> 5) * IG_ROWS;
+    float acc[IG_ROWS][3];
+#pragma unroll
+    for (int r = 0; r < IG_ROWS; ++r) acc[r][0] = acc[r][1] = acc[r][2] = 0.f;
+    for (int part = 0; part < 64 / IG_CH; ++part) {
         __syncthreads();
         for (int i = threadIdx.x; i < (IG_TH + 2) * (IG_TW + 2) * (IG_CH / 4); i += blockDim.x) {
             const int px = i / (IG_CH / 4), c4 = i - px * (IG_CH / 4);
@@ -190,33 +196,46 @@ conv1_dgrad_image_kernel(const float* __restrict__ dPre, const float* __restrict
             const int gy = y0 - 1 + r, gx = x0 - 1 + c;
             float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
             if (gy >= 0 && gy < H && gx >= 0 && gx < W)
-                v = __ldg(reinterpret_cast<const float4*>(dPre + (size_t(gy) * W + gx) * 64 + half * IG_CH) + c4);
+                v = __ldg(reinterpret_cast<const float4*>(dPre + (size_t(gy) * W + gx) * 64 + part * IG_CH) + c4);
             *reinterpret_cast<float4*>(sD + px * IG_PITCH + c4 * 4) = v;
         }
         __syncthreads();
 #pragma unroll
-        for (int kh = 0; kh < 3; ++kh) {
+        for (int kw = 0; kw < 3; ++kw) {
 #pragma unroll
-            for (int kw = 0; kw < 3; ++kw) {
-                const float4* q = reinterpret_cast<const float4*>(sD + ((ty + kh) * (IG_TW + 2) + tx + kw) * IG_PITCH);
-                const float* w = sW + (kh * 3 + kw) * 192 + half * IG_CH;
+            for (int c4 = 0; c4 < IG_CH / 4; ++c4) {
+                float4 d[IG_ROWS + 2];
 #pragma unroll
-                for (int c4 = 0; c4 < IG_CH / 4; ++c4) {
-                    const float4 v = q[c4];
-                    const float4 w0 = *reinterpret_cast<const float4*>(w + c4 * 4);
-                    const float4 w1 = *reinterpret_cast<const float4*>(w + 64 + c4 * 4);
-                    const float4 w2 = *reinterpret_cast<const float4*>(w + 128 + c4 * 4);
-                    a0 = fmaf(v.x, w0.x, a0); a0 = fmaf(v.y, w0.y, a0); a0 = fmaf(v.z, w0.z, a0); a0 = fmaf(v.w, w0.w, a0);
-                    a1 = fmaf(v.x, w1.x, a1); a1 = fmaf(v.y, w1.y, a1); a1 = fmaf(v.z, w1.z, a1); a1 = fmaf(v.w, w1.w, a1);
-                    a2 = fmaf(v.x, w2.x, a2); a2 = fmaf(v.y, w2.y, a2); a2 = fmaf(v.z, w2.z, a2); a2 = fmaf(v.w, w2.w, a2);
+                for (int j = 0; j < IG_ROWS + 2; ++j)
+                    d[j] = *reinterpret_cast<const float4*>(sD + ((ty + j) * (IG_TW + 2) + tx + kw) * IG_PITCH + c4 * 4);
+#pragma unroll
+                for (int kh = 0; kh < 3; ++kh) {
+                    const float* w = sW + (kh * 3 + kw) * 192 + part * IG_CH + c4 * 4;
+                    const float4 w0 = *reinterpret_cast<const float4*>(w);
+                    const float4 w1 = *reinterpret_cast<const float4*>(w + 64);
+                    const float4 w2 = *reinterpret_cast<const float4*>(w + 128);
+#pragma unroll
+                    for (int r = 0; r < IG_ROWS; ++r) {
+                        const float4 v = d[r + kh];
+                        acc[r][0] = fmaf(v.x, w0.x, acc[r][0]); acc[r][0] = fmaf(v.y, w0.y, acc[r][0]);
+                        acc[r][0] = fmaf(v.z, w0.z, acc[r][0]); acc[r][0] = fmaf(v.w, w0.w, acc[r][0]);
+                        acc[r][1] = fmaf(v.x, w1.x, acc[r][1]); acc[r][1] = fmaf(v.y, w1.y, acc[r][1]);
+                        acc[r][1] = fmaf(v.z, w1.z, acc[r][1]); acc[r][1] = fmaf(v.w, w1.w, acc[r][1]);
+                        acc[r][2] = fmaf(v.x, w2.x, acc[r][2]); acc[r][2] = fmaf(v.y, w2.y, acc[r][2]);
+                        acc[r][2] = fmaf(v.z, w2.z, acc[r][2]); acc[r][2] = fmaf(v.w, w2.w, acc[r][2]);
+                    }
                 }
             }
         }
     }
-    const int gx = x0 + tx, gy = y0 + ty;
-    if (gx < W && gy < H) {
-        float* o = dImg + (size_t(gy) * W + gx) * 3;
-        o[0] = a0; o[1] = a1; o[2] = a2;
+    const int gx = x0 + tx;
+#pragma unroll
+    for (int r = 0; r < IG_ROWS; ++r) {
+        const int gy = y0 + ty + r;
+        if (gx < W && gy < H) {
+            float* o = dImg + (size_t(gy) * W + gx) * 3;
+            o[0] = acc[r][0]; o[1] = acc[r][1]; o[2] = acc[r][2];
+        }
     }
 }
 
@@ -252,47 +271,60 @@ maxpool2_kernel(const float* __restrict__ X, float* __restrict__ P, int H, int W
 }
 
 // dPre[pos] = Y[pos] > 0 ? ((pos is the first max of its window ? dP[window] : 0) + seed[pos]) : 0
-// One thread per (full-resolution pixel, 4 channels); pixels outside every window (odd H/W) only see the seed.
+// One thread per (2x2 cell, 4 channels): every Y / seed / dPre element is touched exactly once.  Cells cut by an odd H or W
+// are not pooling windows (VALID pooling); their pixels only see the seed.
 __global__ void __launch_bounds__(256)
 unpool_relu_kernel(const float* __restrict__ Y, const float* __restrict__ dP, const float* __restrict__ seed,
                    float* __restrict__ dPre, int H, int W, int C, uint32_t* __restrict__ out_absmax) {
-    const int Hp = H / 2, Wp = W / 2, C4 = C / 4;
-    const size_t total = size_t(H) * W * C4;
+    const int Hp = H / 2, Wp = W / 2, Hc = (H + 1) / 2, Wc = (W + 1) / 2, C4 = C / 4;
+    const size_t total = size_t(Hc) * Wc * C4;
     float amax = 0.f;
     for (size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += size_t(gridDim.x) * blockDim.x) {
         const int c4 = int(i % C4);
-        const size_t pp = i / C4;
-        const int x = int(pp % W), y = int(pp / W);
-        const float4 me = __ldg(reinterpret_cast<const float4*>(Y) + i);
-        float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
-        const int py = y >> 1, px = x >> 1;
-        if (py < Hp && px < Wp) {
-            const float4* b = reinterpret_cast<const float4*>(Y + (size_t(2 * py) * W + 2 * px) * C) + c4;
-            const float4 v[4] = {__ldg(b), __ldg(b + C4), __ldg(b + size_t(W) * C4), __ldg(b + size_t(W) * C4 + C4)};
-            const float4 d = __ldg(reinterpret_cast<const float4*>(dP + (size_t(py) * Wp + px) * C) + c4);
-            const int self = (y & 1) * 2 + (x & 1);
+        const size_t cell = i / C4;
+        const int cx = int(cell % Wc), cy = int(cell / Wc);
+        const bool window = cy < Hp && cx < Wp;
+        float4 v[4], g[4];
+        bool ok[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int y = 2 * cy + (j >> 1), x = 2 * cx + (j & 1);
+            ok[j] = y < H && x < W;
+            v[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+            g[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (ok[j]) v[j] = __ldg(reinterpret_cast<const float4*>(Y + (size_t(y) * W + x) * C) + c4);
+        }
+        if (window) {
+            const float4 d = __ldg(reinterpret_cast<const float4*>(dP + (size_t(cy) * Wp + cx) * C) + c4);
             const float* vf = reinterpret_cast<const float*>(v);
+            float* gf = reinterpret_cast<float*>(g);
             const float df[4] = {d.x, d.y, d.z, d.w};
-            float gf[4];
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
                 int arg = 0;
                 float best = vf[k];
 #pragma unroll
                 for (int j = 1; j < 4; ++j)
-                    if (vf[j * 4 + k] > best) { best = vf[j * 4 + k]; arg = j; }
-                gf[k] = (arg == self) ? df[k] : 0.0f;
+                    if (vf[j * 4 + k] > best) { best = vf[j * 4 + k]; arg = j; }      // first maximum wins, as in TF
+#pragma unroll
+                for (int j = 0; j < 4; ++j) gf[j * 4 + k] = (arg == j) ? df[k] : 0.0f;
             }
-            g = make_float4(gf[0], gf[1], gf[2], gf[3]);
         }
-        if (seed != nullptr) {
-            const float4 s = __ldg(reinterpret_cast<const float4*>(seed) + i);
-            g.x += s.x; g.y += s.y; g.z += s.z; g.w += s.w;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            if (!ok[j]) continue;
+            const int y = 2 * cy + (j >> 1), x = 2 * cx + (j & 1);
+            const size_t o = (size_t(y) * W + x) * C4 + c4;
+            float4 r = g[j];
+            if (seed != nullptr) {
+                const float4 sd = __ldg(reinterpret_cast<const float4*>(seed) + o);
+                r.x += sd.x; r.y += sd.y; r.z += sd.z; r.w += sd.w;
+            }
+            r.x = v[j].x > 0.f ? r.x : 0.f; r.y = v[j].y > 0.f ? r.y : 0.f;
+            r.z = v[j].z > 0.f ? r.z : 0.f; r.w = v[j].w > 0.f ? r.w : 0.f;
+            amax = fmaxf(fmaxf(amax, fmaxf(fabsf(r.x), fabsf(r.y))), fmaxf(fabsf(r.z), fabsf(r.w)));
+            reinterpret_cast<float4*>(dPre)[o] = r;
         }
-        g.x = me.x > 0.f ? g.x : 0.f; g.y = me.y > 0.f ? g.y : 0.f;
-        g.z = me.z > 0.f ? g.z : 0.f; g.w = me.w > 0.f ? g.w : 0.f;
-        amax = fmaxf(fmaxf(amax, fmaxf(fabsf(g.x), fabsf(g.y))), fmaxf(fabsf(g.z), fabsf(g.w)));
-        reinterpret_cast<float4*>(dPre)[i] = g;
     }
     record_absmax(amax, out_absmax);
 }
@@ -577,7 +609,7 @@ int adpst_vgg_backward(adpst_vgg* h, int H, int W, const float* const* acts_dev,
             if (rc != ADPST_OK) return rc;
             int ph, pw;
             layer_hw(i - 1, H, W, &ph, &pw);
-            const size_t items = size_t(ph) * pw * (conv_cout(i - 1) / 4);
+            const size_t items = size_t((ph + 1) / 2) * ((pw + 1) / 2) * (conv_cout(i - 1) / 4);
             unpool_relu_kernel<<<stream_grid(items), 256, 0, st>>>(acts_dev[i - 1], nxt, seeds_dev[i - 1], cur, ph, pw,
                                                                    conv_cout(i - 1), gmax + i - 1);
             ADPST_LAUNCH_CHECK();
@@ -589,7 +621,7 @@ int adpst_vgg_backward(adpst_vgg* h, int H, int W, const float* const* acts_dev,
         ig_configured = true;
     }
     dim3 grid((W + IG_TW - 1) / IG_TW, (H + IG_TH - 1) / IG_TH);
-    conv1_dgrad_image_kernel<<<grid, IG_TH * IG_TW, IG_SMEM, st>>>(cur, h->wg0, dimage_dev, H, W);
+    conv1_dgrad_image_kernel<<<grid, IG_THREADS, IG_SMEM, st>>>(cur, h->wg0, dimage_dev, H, W);
     ADPST_LAUNCH_CHECK();
     return ADPST_OK;
 }

@@ -94,7 +94,14 @@ def gram_patch_lists(masks, h, w, K, device):
     return ids, off
 
 
-def gram_masked(F, masks, K, workspace=None, patches=None, path="tensor", out=None, f_absmax=None):
+def absmax_slot(t):
+    """A 1-element int32 tensor holding the float32 bit pattern of max|t| (the scale slot the tensor-core kernels read)."""
+    slot = torch.zeros(1, dtype=torch.int32, device=t.device)
+    _lib.check(_lib.lib().adpst_absmax(_lib.ptr(t), t.numel(), _lib.ptr(slot), _lib.stream_ptr()))
+    return slot
+
+
+def gram_masked(F, masks, K, workspace=None, patches=None, path="tensor", out=None, f_absmax=None, masks_absmax=None):
     """F: (h,w,C) float32 feature map ((HW,C) is taken as h = HW, w = 1); masks: (K,h*w) float32 or None.
     Returns (K,C,C) float32  (loss.py:96-102).  `patches` = gram_patch_lists(...) enables the tcgen05 kernel."""
     _f32(F, "F")
@@ -111,8 +118,8 @@ def gram_masked(F, masks, K, workspace=None, patches=None, path="tensor", out=No
     G = out if out is not None else torch.empty(K, C, C, dtype=torch.float32, device=F.device)
     ids, off = patches if patches is not None else (None, None)
     _lib.check(_lib.lib().adpst_gram_masked(_lib.ptr(F), h, w, C, _lib.ptr(masks), K, _lib.ptr(ids), _lib.ptr(off), _lib.ptr(G),
-                                            {"tensor": 0, "simt": 1}[path], ctypes.c_void_p(f_absmax or 0), _lib.ptr(ws),
-                                            _lib.stream_ptr()))
+                                            {"tensor": 0, "simt": 1}[path], ctypes.c_void_p(f_absmax or 0),
+                                            _lib.ptr(masks_absmax), _lib.ptr(ws), _lib.stream_ptr()))
     return G
 
 
@@ -129,8 +136,17 @@ def act_absmax_slot(t):
     return handle.act_absmax_ptr(index)
 
 
+def style_tiles(masks, K, h, w, device):
+    """Set-up for style_layer_backward: classes present in each 8x16-pixel tile of the (constant) masks."""
+    if K > 32:
+        return None                      # the tensor-core style gradient handles at most 32 classes per launch
+    out = torch.empty(int(_lib.lib().adpst_style_tiles_bytes(h * w)), dtype=torch.uint8, device=device)
+    _lib.check(_lib.lib().adpst_style_tiles(_lib.ptr(masks), K, h, w, _lib.ptr(out), _lib.stream_ptr()))
+    return out
+
+
 def style_layer_backward(F, masks, K, G, A, loss_scale, grad_scale, loss_acc, dF, accumulate=False, workspace=None,
-                         path="tensor", hw_norm=0.0, f_absmax=None):
+                         path="tensor", hw_norm=0.0, f_absmax=None, tiles=None):
     """One layer of loss.py:104-137: accumulates the loss value and writes/adds its gradient w.r.t. F.
     F: (h, w, C) feature map (a (HW, C) matrix is treated as h = HW, w = 1... use the 3-D form for 2-D tiling).
     f_absmax: device address of a slot holding max|F| (act_absmax_slot), or None to have it measured."""
@@ -142,7 +158,8 @@ def style_layer_backward(F, masks, K, G, A, loss_scale, grad_scale, loss_acc, dF
     _lib.check(_lib.lib().adpst_style_layer_backward(_lib.ptr(F), h, w, C, _lib.ptr(masks), K, _lib.ptr(G), _lib.ptr(A),
                                                      float(loss_scale), float(grad_scale), _lib.ptr(loss_acc), _lib.ptr(dF),
                                                      int(bool(accumulate)), {"tensor": 0, "simt": 1}[path], float(hw_norm),
-                                                     ctypes.c_void_p(f_absmax or 0), _lib.ptr(ws), _lib.stream_ptr()))
+                                                     ctypes.c_void_p(f_absmax or 0), _lib.ptr(tiles), _lib.ptr(ws),
+                                                     _lib.stream_ptr()))
 
 
 def loss_finalize(acc, w_content, w_style, w_photo, out):

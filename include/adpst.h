@@ -146,11 +146,12 @@ int adpst_resize_bilinear(const float* src_dev, int Hs, int Ws, float* dst_dev, 
  *   patch_ids_dev: int32 patch indices (row-major over ceil(h/2) x ceil(w/16) patches) grouped by class,
  *   patch_off_dev: int32[K+1] offsets into it.  The masks are constant, so the caller builds the list once.
  * path 1, or NULL lists: exact-float32 CUDA-core kernel.
- * F_absmax_dev: slot holding max|F| (adpst_vgg_act_absmax / adpst_absmax), or NULL to have it measured here. */
+ * F_absmax_dev / masks_absmax_dev: slots holding max|F| (adpst_vgg_act_absmax / adpst_absmax) and max|masks|
+ * (adpst_absmax, once: the masks are constant), or NULL to have them measured here. */
 size_t adpst_gram_workspace_bytes(int HW, int C, int K);
 int adpst_gram_masked(const float* F_dev, int h, int w, int C, const float* masks_dev, int K, const int* patch_ids_dev,
-                      const int* patch_off_dev, float* G_dev, int path, const uint32_t* F_absmax_dev, void* workspace_dev,
-                      adpst_stream_t stream);
+                      const int* patch_off_dev, float* G_dev, int path, const uint32_t* F_absmax_dev,
+                      const uint32_t* masks_absmax_dev, void* workspace_dev, adpst_stream_t stream);
 
 /* loss.py:104-137 for one layer, forward value and gradient seed.  With
  *   L = sum_k mean((A_k - G_k)^2) / (2 C^2 HW^2):
@@ -161,11 +162,18 @@ int adpst_gram_masked(const float* F_dev, int h, int w, int C, const float* mask
  * F is the (h,w,C) feature map; path: 0 = tcgen05 3xFP16 kernel (8x16-pixel tiles, classes absent from a tile skipped),
  * 1 = exact-float32 CUDA-core kernel (validation).  hw_norm > 0 replaces h*w in the normaliser (spatially tiled runs:
  * the pixel count of the whole image).  F_absmax_dev: slot holding max|F| (adpst_vgg_act_absmax / adpst_absmax), or
- * NULL to have it measured here. */
+ * NULL to have it measured here.  tiles_dev: per-tile class sets of these (constant) masks from adpst_style_tiles, or
+ * NULL to have them rebuilt on every call. */
 int adpst_style_layer_backward(const float* F_dev, int h, int w, int C, const float* masks_dev, int K,
                                const float* G_dev, const float* A_dev, double loss_scale, double grad_scale,
                                double* loss_dev, float* dF_dev, int accumulate, int path, double hw_norm,
-                               const uint32_t* F_absmax_dev, void* workspace_dev, adpst_stream_t stream);
+                               const uint32_t* F_absmax_dev, const void* tiles_dev, void* workspace_dev,
+                               adpst_stream_t stream);
+
+/* Set-up for the tensor-core style gradient: which classes are present in each 8x16-pixel tile of a (K,h*w) mask
+ * stack (masks_dev NULL: one all-ones class).  tiles_dev: adpst_style_tiles_bytes(h*w) bytes, filled once per layer. */
+size_t adpst_style_tiles_bytes(int HW);
+int adpst_style_tiles(const float* masks_dev, int K, int h, int w, void* tiles_dev, adpst_stream_t stream);
 
 /* loss.py:90-92 with L = mean((target - output)^2):
  *   *loss_dev += loss_scale * L;   dOut (=|+=) grad_scale * 2 (output - target) / n.
