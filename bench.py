@@ -300,7 +300,11 @@ def run_ours(args):
         roofline = {"kernel": "conv3x3_tc_kernel: persistent tcgen05 3xFP16 implicit GEMM, TMA-fed, A operand in TMEM (12 forward "
                               "+ 12 data-gradient launches per step; block1_conv1 forward is a CUDA-core kernel)", "bound": "tensor",
                     "achieved": conv_tflops, "peak": tf_sus, "unit": "TFLOP/s", "frac": conv_tflops / tf_sus,
-                    "traffic": None, "peak_source": which + " bf16 dense, sustained (kernel timed inside a long step)",
+                    # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch (block3_conv2 forward: 67 MB in, 67 MB out,
+                    # 2.4 MB of weights) from the ncu --set full capture summarised in profiles/r1_prof_conv_summary.csv
+                    "traffic": 91.9e6, "traffic_of": "block3_conv2 forward launch, ncu capture in profiles/ (algorithmic: 136.6 MB; "
+                                                     "part of the output is still in L2 when the kernel ends)",
+                    "peak_source": which + " bf16 dense, sustained (kernel timed inside a long step)",
                     "flops_per_launch_avg": tot_f / n_launch, "ms_per_launch_avg": tot_t / n_launch,
                     "share_of_step": tot_t / (total_ms / args.steps),
                     "fp32_accurate_ceiling": {"what": "3xFP16: peak_bf16 / 3 (MMAs per product)",
@@ -315,9 +319,16 @@ def run_ours(args):
         lx_gbs = 36.0 * S * S / (t_lx * 1e-3) / 1e9
         f32 = v2.MattingLaplacian(content[0], epsilon=1e-7, storage_dtype=torch.float32, compute_dtype=torch.float32)
         t_lx32 = time_launches(lambda: f32._op.apply3(xs, want_y=True, want_quad=True, y_scale=2e4, out=ybuf), flush, 10)
-        roofline_lx = {"kernel": "lap_matvec (float32 I/O, float64 arithmetic: the path Loss uses)", "bound": "hbm",
-                       "achieved": lx_gbs, "peak": hbm, "unit": "GB/s", "frac": lx_gbs / hbm, "traffic": None,
+        # The quoted roofline is HBM (36 B/px), as the metric asks; what actually bounds the kernel is the float64 pipe:
+        # ~250 float64 lane-operations per pixel (halo included) against 64 lanes/clk/SM.
+        f64_floor_ms = 250.0 * S * S / (64.0 * 148 * 1.965e9) * 1e3
+        roofline_lx = {"kernel": "lap_march3_kernel (float32 I/O, float64 arithmetic: the path Loss uses)", "bound": "hbm",
+                       "achieved": lx_gbs, "peak": hbm, "unit": "GB/s", "frac": lx_gbs / hbm,
+                       # dram bytes of one 2048x2048 launch (ncu capture in profiles/r1_prof_lap_summary.csv; 151 MB algorithmic)
+                       "traffic": 123.8e6, "traffic_of": "2048x2048 launch, ncu capture in profiles/",
                        "peak_source": which + " copy bandwidth", "bytes_per_launch": 36 * S * S, "ms_per_launch": t_lx,
+                       "float64_pipe_floor": {"what": "250 float64 lane-ops/px at 64 lanes/clk/SM x 148 SMs x 1.965 GHz",
+                                              "ms_per_launch": f64_floor_ms, "frac_of_floor": f64_floor_ms / t_lx},
                        "float32_arithmetic_variant": {"achieved": 36.0 * S * S / (t_lx32 * 1e-3) / 1e9,
                                                       "frac": 36.0 * S * S / (t_lx32 * 1e-3) / 1e9 / hbm,
                                                       "ms_per_launch": t_lx32}}
