@@ -218,6 +218,26 @@ def test_train_steps_follow_oracle(graph, weights, synth):
     assert 10 * np.log10(1.0 / max(mse, 1e-30)) > 50.0           # PSNR bar of the north star
 
 
+def test_hundred_adam_iterations_psnr(weights, synth):
+    """North star: after 100 Adam iterations the image is within 50 dB PSNR of the reference (here: the float64 oracle)."""
+    st = _m("style_transfer")
+    args = _args()
+    ext, loss, ora, c_dev = _setup(64, 64, 3, weights, synth, args)
+    opt = st.Adam(args.adam_lr, args.adam_beta1, args.adam_beta2, args.adam_epsilon)
+    step = st.make_train_step(ext, loss, opt, use_cuda_graph=True)
+    x = c_dev.clone()
+    for it in range(100):
+        d = step(x)
+        do = ora.train_step()
+    assert opt.iterations == 100
+    mse = float(((x.cpu().double() - ora.image) ** 2).mean())
+    psnr = 10 * np.log10(1.0 / max(mse, 1e-30))
+    rel = abs(float(d["Total loss"]) - do["Total loss"]) / abs(do["Total loss"])
+    print("PSNR after 100 iterations: %.1f dB, total loss rel. diff %.2e" % (psnr, rel))
+    assert psnr > 50.0
+    assert rel < 1e-3
+
+
 def test_nima_weight_is_refused(weights, synth):
     lossm = _m("components.loss")
     t = {"block4_conv2": torch.zeros(1, 2, 2, 512, device="cuda")}

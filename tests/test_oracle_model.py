@@ -78,3 +78,34 @@ def test_small_train_state_runs_and_content_loss_zero_at_start(synth):
     assert g.shape == (1, H, W, 3) and torch.isfinite(g).all()
     d2 = st.train_step()
     assert st.image.min() >= 0 and st.image.max() <= 1 and st.t == 1
+
+
+def test_vgg_restatement_matches_torchvision_vgg19(synth):
+    """The VGG19 arithmetic lives in Keras (un-vendored, un-pinned): the restatement is checked here against an INDEPENDENT
+    implementation of the same published network, torchvision.models.vgg19 (features[0:30] = block1_conv1 .. relu5_1),
+    loaded with the same seeded weights.  This pins topology, padding, pooling and the tap positions; it cannot pin
+    TensorFlow's own kernels."""
+    tv = pytest.importorskip("torchvision")
+    weights = synth.vgg_weights(seed=11)
+    net = tv.models.vgg19(weights=None).features[:30].double().eval()
+    convs = [m for m in net if isinstance(m, torch.nn.Conv2d)]
+    names = [it[0] for it in model.VGG_TOPOLOGY if it != "P"]
+    assert len(convs) == len(names) == 13
+    with torch.no_grad():
+        for m, n in zip(convs, names):
+            k, b = weights[n]
+            m.weight.copy_(torch.as_tensor(k).double().permute(3, 2, 0, 1))      # HWIO -> OIHW
+            m.bias.copy_(torch.as_tensor(b).double())
+    img = torch.as_tensor(synth.image(40, 56, 12)).double()
+    ours = model.vgg_forward(img, weights)
+    x = (img * 255.0).flip(-1) - torch.tensor(model.CAFFE_MEAN_BGR, dtype=torch.float64)   # Keras caffe-mode preprocess
+    x = x.permute(0, 3, 1, 2)
+    taps = {1: "block1_conv1", 6: "block2_conv1", 11: "block3_conv1", 20: "block4_conv1", 22: "block4_conv2", 29: "block5_conv1"}
+    with torch.no_grad():
+        for i, layer in enumerate(net):
+            x = layer(x)
+            if i in taps:
+                ref = x.permute(0, 2, 3, 1)
+                got = ours[taps[i]]
+                assert got.shape == ref.shape
+                assert float((got - ref).abs().max()) <= 1e-9 * float(ref.abs().max()), taps[i]
