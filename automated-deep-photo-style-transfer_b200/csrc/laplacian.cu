@@ -382,184 +382,8 @@ __device__ __forceinline__ void lap_march_step(LapMarchState<TC>& st, const floa
     }
 }
 
-// ---------------------------------------------------------------------------------------------
-// float64-arithmetic variant of the marching warp ("v2"): fewer float64 instructions and no float->double conversions
-// in the inner loop (both matter: the float64 pipe issues 64 lanes/clk/SM and F2F only 16).
-//   * each lane keeps only ITS OWN column of the last three raw rows, already converted to double at load time;
-//   * window moments are separable: lane k sums the 21 raw moments of its own column over the three rows (exact in
-//     float64: the inputs are float32) and the window sum is C[k-1] + C[k] + C[k+1], fetched with shuffles;
-//   * the 3-wide sum of the coefficients is replaced by "contributions": lane k evaluates V_k^T I_l + VB_k for the
-//     three pixels l = k-1, k, k+1 its window column touches (V = coefficients summed over the three window rows, in
-//     registers) and ships 3 numbers to each neighbour instead of receiving 12 from each.
-// ---------------------------------------------------------------------------------------------
-struct LapMarch2State {
-    double rI[3][3], rX[3][3];       // [row slot][channel], own column
-    double cf[3][12];                 // [window-row slot][a (9), b (3)], own window column
-};
-
 __device__ __forceinline__ double shfl_up1d(double v) { return __shfl_up_sync(0xffffffffu, v, 1); }
 __device__ __forceinline__ double shfl_dn1d(double v) { return __shfl_down_sync(0xffffffffu, v, 1); }
-
-template <int S>
-__device__ __forceinline__ void lap_march2_step(LapMarch2State& st, const float (&nI)[3], const float (&nX)[3], int ir, int r0,
-                                                int r_end, int gx, int lane, int H, int W, bool v2, double eps,
-                                                double y_scale, float* __restrict__ y, double& acc, int qlo, int qhi) {
-    constexpr int S1 = (S + 1) % 3;                       // slot of row ir-2 (S holds row ir)
-#pragma unroll
-    for (int c = 0; c < 3; ++c) { st.rI[S][c] = f32_to_f64_exact(nI[c]); st.rX[S][c] = f32_to_f64_exact(nX[c]); }
-    // ---- raw moments of this lane's column over rows ir-2..ir:  s(3) t(3) Q(6) R(9)
-    // (no zero-initialised accumulators: zeroing a register pair compiles to CS2R, which issues on the slow XU pipe --
-    //  measured at 100 % XU utilisation before this was removed)
-    double cm[21];
-    {
-        const double i0 = st.rI[0][0], i1 = st.rI[0][1], i2 = st.rI[0][2];
-        const double x0 = st.rX[0][0], x1 = st.rX[0][1], x2 = st.rX[0][2];
-        cm[0] = i0; cm[1] = i1; cm[2] = i2; cm[3] = x0; cm[4] = x1; cm[5] = x2;
-        cm[6] = i0 * i0; cm[7] = i0 * i1; cm[8] = i0 * i2; cm[9] = i1 * i1; cm[10] = i1 * i2; cm[11] = i2 * i2;
-        cm[12] = i0 * x0; cm[13] = i0 * x1; cm[14] = i0 * x2;
-        cm[15] = i1 * x0; cm[16] = i1 * x1; cm[17] = i1 * x2;
-        cm[18] = i2 * x0; cm[19] = i2 * x1; cm[20] = i2 * x2;
-    }
-#pragma unroll
-    for (int rr = 1; rr < 3; ++rr) {
-        const double i0 = st.rI[rr][0], i1 = st.rI[rr][1], i2 = st.rI[rr][2];
-        const double x0 = st.rX[rr][0], x1 = st.rX[rr][1], x2 = st.rX[rr][2];
-        cm[0] += i0; cm[1] += i1; cm[2] += i2; cm[3] += x0; cm[4] += x1; cm[5] += x2;
-        cm[6] += i0 * i0; cm[7] += i0 * i1; cm[8] += i0 * i2; cm[9] += i1 * i1; cm[10] += i1 * i2; cm[11] += i2 * i2;
-        cm[12] += i0 * x0; cm[13] += i0 * x1; cm[14] += i0 * x2;
-        cm[15] += i1 * x0; cm[16] += i1 * x1; cm[17] += i1 * x2;
-        cm[18] += i2 * x0; cm[19] += i2 * x1; cm[20] += i2 * x2;
-    }
-    // ---- window (wr = ir - 1, column gx) = columns gx-1, gx, gx+1
-    double (&wm)[21] = cm;
-#pragma unroll
-    for (int i = 0; i < 21; ++i) {
-        const double up = shfl_up1d(cm[i]), dn = shfl_dn1d(cm[i]);
-        cm[i] += up + dn;
-    }
-    const int wr = ir - 1;
-    const bool valid = (lane >= 1 && lane <= 30) && (v2 || (wr >= 1 && wr < H - 1 && gx >= 1 && gx < W - 1));
-    {
-        constexpr double inv_n = 1.0 / 9.0;
-        double mu[3], pbar[3], M[6], Rc[9], Mi[6];
-#pragma unroll
-        for (int c = 0; c < 3; ++c) { mu[c] = wm[c] * inv_n; pbar[c] = wm[3 + c] * inv_n; }
-        M[0] = wm[6] - wm[0] * mu[0] + eps; M[1] = wm[7] - wm[0] * mu[1]; M[2] = wm[8] - wm[0] * mu[2];
-        M[3] = wm[9] - wm[1] * mu[1] + eps; M[4] = wm[10] - wm[1] * mu[2]; M[5] = wm[11] - wm[2] * mu[2] + eps;
-#pragma unroll
-        for (int j = 0; j < 3; ++j)
-#pragma unroll
-            for (int c = 0; c < 3; ++c) Rc[j * 3 + c] = wm[12 + j * 3 + c] - wm[j] * pbar[c];
-        sym3_inverse(M, Mi);
-        double* a = st.cf[S1];                               // oldest window-row slot, free now
-#pragma unroll
-        for (int c = 0; c < 3; ++c) {
-            a[c] = Mi[0] * Rc[c] + Mi[1] * Rc[3 + c] + Mi[2] * Rc[6 + c];
-            a[3 + c] = Mi[1] * Rc[c] + Mi[3] * Rc[3 + c] + Mi[4] * Rc[6 + c];
-            a[6 + c] = Mi[2] * Rc[c] + Mi[4] * Rc[3 + c] + Mi[5] * Rc[6 + c];
-            a[9 + c] = pbar[c] - (a[c] * mu[0] + a[3 + c] * mu[1] + a[6 + c] * mu[2]);
-        }
-        const double keep = valid ? 1.0 : 0.0;                // multiply instead of zero-fill (see the CS2R note above)
-#pragma unroll
-        for (int i = 0; i < 12; ++i) a[i] *= keep;
-    }
-    // ---- output row orow = ir - 2 (window rows orow-1 .. orow+1 are the three cf slots)
-    const int orow = ir - 2;
-    double V[12];
-#pragma unroll
-    for (int i = 0; i < 12; ++i) V[i] = st.cf[0][i] + st.cf[1][i] + st.cf[2][i];
-    const double i0 = st.rI[S1][0], i1 = st.rI[S1][1], i2 = st.rI[S1][2];          // pixel (orow, gx)
-    const double l0 = shfl_up1d(i0), l1 = shfl_up1d(i1), l2 = shfl_up1d(i2);       // pixel (orow, gx-1)
-    const double q0 = shfl_dn1d(i0), q1 = shfl_dn1d(i1), q2 = shfl_dn1d(i2);       // pixel (orow, gx+1)
-    double uL[3], uC[3], uR[3];
-#pragma unroll
-    for (int c = 0; c < 3; ++c) {
-        uL[c] = V[c] * l0 + V[3 + c] * l1 + V[6 + c] * l2 + V[9 + c];
-        uC[c] = V[c] * i0 + V[3 + c] * i1 + V[6 + c] * i2 + V[9 + c];
-        uR[c] = V[c] * q0 + V[3 + c] * q1 + V[6 + c] * q2 + V[9 + c];
-    }
-    // pixel l collects: window column l-1's "right" value, its own, window column l+1's "left" value
-    double tot[3];
-#pragma unroll
-    for (int c = 0; c < 3; ++c) tot[c] = uC[c] + shfl_up1d(uR[c]) + shfl_dn1d(uL[c]);
-    if (ir >= r0 + 2 && lane >= 2 && lane <= 29 && gx < W && orow < H && orow < r_end) {
-        double cnt = 9.0;
-        if (!v2) {
-            const int ylo = max(orow - 1, 1), yhi = min(orow + 1, H - 2);
-            const int xlo = max(gx - 1, 1), xhi = min(gx + 1, W - 2);
-            const int nwin = max(yhi - ylo + 1, 0) * max(xhi - xlo + 1, 0);      // 0..9, table instead of I2F
-            cnt = nwin == 9 ? 9.0 : nwin == 6 ? 6.0 : nwin == 4 ? 4.0 : nwin == 3 ? 3.0 : nwin == 2 ? 2.0 : nwin == 1 ? 1.0 : 0.0;
-        }
-        const size_t g = (size_t(orow) * W + gx) * 3;
-#pragma unroll
-        for (int c = 0; c < 3; ++c) {
-            const double xc = st.rX[S1][c];
-            const double yc = cnt * xc - tot[c];
-            if (gx >= qlo && gx < qhi) acc += xc * yc;
-            if (y != nullptr) y[g + c] = f64_to_f32_rn(y_scale * yc);
-        }
-    }
-}
-
-__global__ void __launch_bounds__(LM_WARPS * 32)
-lap_march2_kernel(const float* __restrict__ img, const float* __restrict__ x, float* __restrict__ y, double* __restrict__ partial,
-                  int H, int W, int mode, double eps, double y_scale, int RW, int strips_x, int total_warps, int qlo, int qhi) {
-    __shared__ double sRed[32];
-    const int lane = threadIdx.x & 31;
-    int gw = blockIdx.x * LM_WARPS + (threadIdx.x >> 5);
-    const bool live = gw < total_warps;                        // spare warps of the last CTA run an empty strip
-    if (!live) gw = 0;
-    double acc = 0.0;
-    {
-        const int sy = gw / strips_x, sx = gw - sy * strips_x;
-        const int c0 = sx * LM_COLS, r0 = sy * RW, r_end = live ? min(r0 + RW, H) : r0;
-        const int gx = c0 - 2 + lane;
-        const bool v2 = (mode == ADPST_LAP_V2);
-        const int mx = v2 ? reflect_symmetric(gx, W) : gx;
-        const bool col_ok = v2 || (gx >= 0 && gx < W);
-        LapMarch2State st;
-#pragma unroll
-        for (int i = 0; i < 3; ++i) {
-#pragma unroll
-            for (int j = 0; j < 12; ++j) st.cf[i][j] = 0.0;
-#pragma unroll
-            for (int j = 0; j < 3; ++j) { st.rI[i][j] = 0.0; st.rX[i][j] = 0.0; }
-        }
-        auto load_row = [&](int ir, float (&vI)[3], float (&vX)[3]) {
-            int my = ir;
-            bool ok = col_ok && live;
-            if (v2) my = reflect_symmetric(ir, H);
-            else ok = ok && ir >= 0 && ir < H;
-            vI[0] = vI[1] = vI[2] = vX[0] = vX[1] = vX[2] = 0.f;
-            if (ok) {
-                const size_t g = (size_t(my) * W + mx) * 3;
-                vI[0] = __ldg(img + g); vI[1] = __ldg(img + g + 1); vI[2] = __ldg(img + g + 2);
-                vX[0] = __ldg(x + g);   vX[1] = __ldg(x + g + 1);   vX[2] = __ldg(x + g + 2);
-            }
-        };
-        float cI[3], cX[3], nI[3], nX[3];
-        const int ir_begin = r0 - 2;
-        // rows r0-2 .. r0+RW+1 for every warp: the trip count depends on kernel parameters only, so the compiler can keep
-        // the shuffles outside divergence handling; rows past the image / the strip are predicated off at the store
-        const int ntriples = (RW + 4 + 2) / 3;
-        load_row(ir_begin, cI, cX);
-        for (int tpl = 0; tpl < ntriples; ++tpl) {
-            const int ir = ir_begin + 3 * tpl;
-            load_row(ir + 1, nI, nX);
-            lap_march2_step<0>(st, cI, cX, ir, r0, r_end, gx, lane, H, W, v2, eps, y_scale, y, acc, qlo, qhi);
-            load_row(ir + 2, cI, cX);
-            lap_march2_step<1>(st, nI, nX, ir + 1, r0, r_end, gx, lane, H, W, v2, eps, y_scale, y, acc, qlo, qhi);
-            load_row(ir + 3, nI, nX);
-            lap_march2_step<2>(st, cI, cX, ir + 2, r0, r_end, gx, lane, H, W, v2, eps, y_scale, y, acc, qlo, qhi);
-#pragma unroll
-            for (int c = 0; c < 3; ++c) { cI[c] = nI[c]; cX[c] = nX[c]; }
-        }
-    }
-    if (partial != nullptr) {
-        const double tot = block_sum<double>(acc, sRed);
-        if (threadIdx.x == 0) partial[blockIdx.x] = tot;
-    }
-}
 
 template <typename TC>
 __global__ void __launch_bounds__(LM_WARPS * 32)
@@ -621,7 +445,7 @@ lap_march_kernel(const float* __restrict__ img, const float* __restrict__ x, flo
 }
 
 // ---------------------------------------------------------------------------------------------
-// float64 marching warp, third generation ("march3"): what runs for r = 1, float32 I/O, float64 arithmetic.
+// float64 marching warp ("march3"): what runs for r = 1, float32 I/O, float64 arithmetic.
 // The kernel is bound by the float64 pipe (64 lanes/clk/SM), not by HBM, so the design minimises float64 instructions
 // and shuffles per pixel:
 //   * every lane owns TWO adjacent columns: a 3-wide horizontal sum of a field costs 3 adds and 2 shuffles per column
@@ -631,8 +455,10 @@ lap_march_kernel(const float* __restrict__ img, const float* __restrict__ x, flo
 //     at once and ADDED into the three output rows it touches (z[o] += Ha^T I_o + Hb), so the carried state per column
 //     is 9 doubles instead of 36;
 //   * 1/n, eps and the validity mask ride on operations that exist anyway (eps/3 is the addend of the first diagonal
-//     product of each column, b is carried as n*b and divided in the final FMA, invalid windows are selected away with
-//     integer moves).
+//     product of each column, b is carried as n*b and divided in the final FMA, invalid windows -- v3 only -- are selected
+//     away with integer moves);
+//   * float <-> double conversions use the hardware F2F (18 per column pair and row; the XU pipe they issue on is at 1 %):
+//     an integer emulation costs ~100 issue slots per pixel and was measured 12 % slower.
 // Lanes 0 and 31 and the first/last two rows of a strip are halo.
 // ---------------------------------------------------------------------------------------------
 constexpr int L3_COLS = 60;           // output columns per warp
@@ -647,18 +473,19 @@ __device__ __forceinline__ double sel_f64(bool keep, double v) {   // keep ? v :
     return __hiloint2double(keep ? __double2hiint(v) : 0, keep ? __double2loint(v) : 0);
 }
 
-template <int S>
+template <int S, bool V2>
 __device__ __forceinline__ void lap_march3_step(Lap3State& st, const float (&nI)[6], const float (&nX)[6], int ir, int r0,
-                                                int r_end, int gx0, int lane, int H, int W, bool v2, double eps3,
+                                                int r_end, int gx0, int lane, int H, int W, double eps3,
                                                 double y_scale, float* __restrict__ y, double& acc, int qlo, int qhi) {
+    constexpr bool v2 = V2;
     constexpr int S1 = (S + 1) % 3, S2 = (S + 2) % 3;     // slots of rows ir-2, ir-1 (S holds row ir)
     constexpr double inv_n = 1.0 / 9.0;
 #pragma unroll
     for (int col = 0; col < 2; ++col)
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
-            st.rI[S][col][c] = f32_to_f64_exact(nI[col * 3 + c]);
-            st.rX[S][col][c] = f32_to_f64_exact(nX[col * 3 + c]);
+            st.rI[S][col][c] = double(nI[col * 3 + c]);
+            st.rX[S][col][c] = double(nX[col * 3 + c]);
         }
     // ---- raw moments of each own column over rows ir-2..ir:  s(3) t(3) Q(6) R(9); exact in float64
     double cm[2][21];
@@ -723,8 +550,12 @@ __device__ __forceinline__ void lap_march3_step(Lap3State& st, const float (&nI)
                 const double a1 = fma(Mi[4], Rc[6 + c], fma(Mi[3], Rc[3 + c], Mi[1] * Rc[c]));
                 const double a2 = fma(Mi[5], Rc[6 + c], fma(Mi[4], Rc[3 + c], Mi[2] * Rc[c]));
                 const double nb = fma(-a2, w[2], fma(-a1, w[1], fma(-a0, w[0], w[3 + c])));      // n*b = t - a^T s
-                a[c] = sel_f64(valid, a0); a[3 + c] = sel_f64(valid, a1); a[6 + c] = sel_f64(valid, a2);
-                a[9 + c] = sel_f64(valid, nb);
+                if (V2) {
+                    a[c] = a0; a[3 + c] = a1; a[6 + c] = a2; a[9 + c] = nb;          // every window exists (reflection)
+                } else {
+                    a[c] = sel_f64(valid, a0); a[3 + c] = sel_f64(valid, a1); a[6 + c] = sel_f64(valid, a2);
+                    a[9 + c] = sel_f64(valid, nb);
+                }
             }
         }
     }
@@ -769,16 +600,17 @@ __device__ __forceinline__ void lap_march3_step(Lap3State& st, const float (&nI)
                     const double xc = st.rX[S1][col][c];
                     const double yc = fma(cnt, xc, -st.z[S1][col][c]);
                     if (inq) acc = fma(xc, yc, acc);
-                    if (y != nullptr) y[g + c] = f64_to_f32_rn(y_scale * yc);
+                    if (y != nullptr) y[g + c] = __double2float_rn(y_scale * yc);
                 }
             }
         }
     }
 }
 
+template <bool V2>
 __global__ void __launch_bounds__(L3_WARPS * 32)
 lap_march3_kernel(const float* __restrict__ img, const float* __restrict__ x, float* __restrict__ y, double* __restrict__ partial,
-                  int H, int W, int mode, double eps, double y_scale, int RW, int strips_x, int total_warps, int qlo, int qhi) {
+                  int H, int W, double eps, double y_scale, int RW, int strips_x, int total_warps, int qlo, int qhi) {
     __shared__ double sRed[32];
     const int lane = threadIdx.x & 31;
     int gw = blockIdx.x * L3_WARPS + (threadIdx.x >> 5);
@@ -789,7 +621,7 @@ lap_march3_kernel(const float* __restrict__ img, const float* __restrict__ x, fl
         const int sy = gw / strips_x, sx = gw - sy * strips_x;
         const int c0 = sx * L3_COLS, r0 = sy * RW, r_end = live ? min(r0 + RW, H) : r0;
         const int gx0 = c0 - 2 + 2 * lane;
-        const bool v2 = (mode == ADPST_LAP_V2);
+        constexpr bool v2 = V2;
         int mx[2];
         bool col_ok[2];
 #pragma unroll
@@ -830,11 +662,11 @@ lap_march3_kernel(const float* __restrict__ img, const float* __restrict__ x, fl
         for (int tpl = 0; tpl < ntriples; ++tpl) {
             const int ir = ir_begin + 3 * tpl;
             load_row(ir + 1, nI, nX);                               // one row ahead
-            lap_march3_step<0>(st, cI, cX, ir, r0, r_end, gx0, lane, H, W, v2, eps3, y_scale, y, acc, qlo, qhi);
+            lap_march3_step<0, V2>(st, cI, cX, ir, r0, r_end, gx0, lane, H, W, eps3, y_scale, y, acc, qlo, qhi);
             load_row(ir + 2, cI, cX);
-            lap_march3_step<1>(st, nI, nX, ir + 1, r0, r_end, gx0, lane, H, W, v2, eps3, y_scale, y, acc, qlo, qhi);
+            lap_march3_step<1, V2>(st, nI, nX, ir + 1, r0, r_end, gx0, lane, H, W, eps3, y_scale, y, acc, qlo, qhi);
             load_row(ir + 3, nI, nX);
-            lap_march3_step<2>(st, cI, cX, ir + 2, r0, r_end, gx0, lane, H, W, v2, eps3, y_scale, y, acc, qlo, qhi);
+            lap_march3_step<2, V2>(st, cI, cX, ir + 2, r0, r_end, gx0, lane, H, W, eps3, y_scale, y, acc, qlo, qhi);
 #pragma unroll
             for (int c = 0; c < 6; ++c) { cI[c] = nI[c]; cX[c] = nX[c]; }
         }
@@ -989,22 +821,23 @@ static int launch_march(adpst_laplacian* h, const void* x, void* y, double y_sca
     // float64 kernel: 255 registers -> 8 resident warps per SM, one full wave; float32 kernel: 12+ resident, two waves
     const int qlo = h->q_col_hi > h->q_col_lo ? h->q_col_lo : 0, qhi = h->q_col_hi > h->q_col_lo ? h->q_col_hi : h->W;
     constexpr bool f64 = std::is_same<TC, double>::value;
-    static const int variant = getenv("ADPST_LAP_KERNEL") ? atoi(getenv("ADPST_LAP_KERNEL")) : 3;   // 2: previous generation
-    const int cols = (f64 && variant == 3) ? L3_COLS : LM_COLS;
+    const int cols = f64 ? L3_COLS : LM_COLS;
     static const int rw_override = getenv("ADPST_LAP_RW") ? atoi(getenv("ADPST_LAP_RW")) : 0;      // experiments
     const int RW = rw_override > 0 ? rw_override : march_rows(h->H, h->W, f64 ? 8 : 16, cols);
     const int strips_x = (h->W + cols - 1) / cols, total = strips_x * ((h->H + RW - 1) / RW);
     const int ctas = (total + LM_WARPS - 1) / LM_WARPS;
     if (ctas > h->npartials) return fail(ADPST_ERR_INVALID, "laplacian: partial buffer too small (%d > %d)", ctas, h->npartials);
     if constexpr (f64) {
-        if (variant == 3)
-            lap_march3_kernel<<<ctas, L3_WARPS * 32, 0, st>>>(static_cast<const float*>(h->image), static_cast<const float*>(x),
-                                                              static_cast<float*>(y), xLx ? h->partials : nullptr, h->H, h->W,
-                                                              h->mode, h->eps, y_scale, RW, strips_x, total, qlo, qhi);
+        const float* img = static_cast<const float*>(h->image);
+        const float* xf = static_cast<const float*>(x);
+        float* yf = static_cast<float*>(y);
+        double* part = xLx ? h->partials : nullptr;
+        if (h->mode == ADPST_LAP_V2)
+            lap_march3_kernel<true><<<ctas, L3_WARPS * 32, 0, st>>>(img, xf, yf, part, h->H, h->W, h->eps, y_scale, RW, strips_x,
+                                                                    total, qlo, qhi);
         else
-            lap_march2_kernel<<<ctas, LM_WARPS * 32, 0, st>>>(static_cast<const float*>(h->image), static_cast<const float*>(x),
-                                                              static_cast<float*>(y), xLx ? h->partials : nullptr, h->H, h->W,
-                                                              h->mode, h->eps, y_scale, RW, strips_x, total, qlo, qhi);
+            lap_march3_kernel<false><<<ctas, L3_WARPS * 32, 0, st>>>(img, xf, yf, part, h->H, h->W, h->eps, y_scale, RW, strips_x,
+                                                                     total, qlo, qhi);
     } else
         lap_march_kernel<TC><<<ctas, LM_WARPS * 32, 0, st>>>(static_cast<const float*>(h->image), static_cast<const float*>(x),
                                                              static_cast<float*>(y), xLx ? h->partials : nullptr, h->H, h->W,
