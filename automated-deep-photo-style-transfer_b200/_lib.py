@@ -41,7 +41,6 @@ SIGNATURES = {
     "adpst_vgg_pool_shape": (_i, [_i, _i, _i, _c.POINTER(_i), _c.POINTER(_i), _c.POINTER(_i)]),
     "adpst_vgg_forward": (_i, [_vp, _vp, _i, _i, _pp, _pp, _i, _vp]),
     "adpst_vgg_set_conv_path": (_i, [_vp, _i]),
-    "adpst_debug_conv_trace": (_i, [_vp, _i]),
     "adpst_absmax": (_i, [_vp, _sz, _vp, _vp]),
     "adpst_vgg_act_absmax": (_vp, [_vp, _i]),
     "adpst_vgg_conv_forward": (_i, [_vp, _i, _vp, _i, _i, _vp, _vp, _vp]),

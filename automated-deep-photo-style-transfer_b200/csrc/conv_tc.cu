@@ -603,8 +603,6 @@ int prepare_tc_weights(adpst_vgg* h, int i, cudaStream_t st) {
 
 bool conv_tc_eligible(int Cin, int Cout) { return Cin % TC_BK == 0 && (Cout == 64 || Cout % 128 == 0); }
 
-void conv_tc_set_trace(long long*, int) {}     // (the per-stage timeline instrumentation was removed with the persistent kernel)
-
 template <int BN, int MODE>
 static int launch_tc(const CUtensorMap& tmA, const CUtensorMap& tmBhi, const CUtensorMap& tmBlo, const float* bias, float* Y,
                      const float* seed, const float* mask, int H, int W, int Cin, int Cout, const uint32_t* a_absmax,

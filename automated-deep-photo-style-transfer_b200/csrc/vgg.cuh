@@ -37,7 +37,6 @@ struct adpst_vgg {
 
 namespace adpst {
 bool conv_tc_eligible(int Cin, int Cout);
-void conv_tc_set_trace(long long* buf, int block);
 int prepare_tc_weights(adpst_vgg* h, int i, cudaStream_t st);
 int launch_conv_tc(adpst_vgg* h, int i, int gradient, const float* X, float* Y, const float* seed, const float* mask, int H,
                    int W, int Cin, int Cout, const uint32_t* x_absmax, uint32_t* y_absmax, cudaStream_t st);

@@ -554,12 +554,6 @@ const uint32_t* adpst_vgg_act_absmax(const adpst_vgg* h, int i) {
     return h->amax + adpst::AMAX_ACT + i;
 }
 
-/* development: per-stage clock64 timeline of one CTA of the tensor-core conv kernel (buf: 5*4096 int64, NULL = off) */
-int adpst_debug_conv_trace(long long* buf_dev, int block) {
-    adpst::conv_tc_set_trace(buf_dev, block);
-    return ADPST_OK;
-}
-
 int adpst_vgg_conv_forward(adpst_vgg* h, int i, const float* x_dev, int lh, int lw, float* y_dev,
                            const uint32_t* x_absmax_dev, adpst_stream_t stream) {
     using namespace adpst;

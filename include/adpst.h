@@ -106,9 +106,6 @@ int adpst_vgg_forward(adpst_vgg* h, const float* image_dev, int H, int W, float*
  * everywhere (validation). */
 int adpst_vgg_set_conv_path(adpst_vgg* h, int path);
 
-/* Development aid: clock64 timeline of one CTA of the tensor-core conv kernel (buf_dev: 5*4096 int64; NULL disables). */
-int adpst_debug_conv_trace(long long* buf_dev, int block);
-
 /* The tensor-core kernels split float32 operands into FP16 pairs after a power-of-two scale derived from the
  * tensor's largest magnitude.  Inside adpst_vgg_forward / adpst_vgg_backward every kernel records max|output| for its
  * consumer; tensors that enter from outside either come with a device slot holding the float32 bit pattern of
