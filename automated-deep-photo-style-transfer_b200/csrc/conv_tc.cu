@@ -137,7 +137,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                   const float* __restrict__ seed, const float* __restrict__ mask_src, int H, int W, int Cin, int Cout,
                   int tiles_w, int num_tiles, const float* __restrict__ cls_masks, const uint32_t* __restrict__ tile_active,
                   const uint32_t* __restrict__ a_absmax, const uint32_t* __restrict__ b_absmax,
-                  const uint32_t* __restrict__ w_absmax, uint32_t* __restrict__ y_absmax) {
+                  const uint32_t* __restrict__ w_absmax, uint32_t* __restrict__ y_absmax, float* __restrict__ pool_out) {
     using Cfg = TcCfg<BN>;
     constexpr int AST = Cfg::A_STAGES, BST = Cfg::B_STAGES;
     static_assert(BN == 64 || BN == 128, "tile width");
@@ -439,7 +439,8 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                 ++sj;
             }
             const int gy = (tile / tiles_w) * TC_TH + m / TC_TW, gx = (tile % tiles_w) * TC_TW + m % TC_TW;
-            if (gy < H && gx < W) {
+            const bool inb = gy < H && gx < W;
+            if (inb || (MODE == MODE_FWD && pool_out != nullptr)) {        // (pooling shuffles need the whole warp)
                 const size_t rowoff = (size_t(gy) * W + gx) * size_t(Cout) + n0;
 #pragma unroll
                 for (int c0 = 0; c0 < BN; c0 += 32) {
@@ -461,6 +462,23 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                             r[j] = fmaxf(r[j] + b.x, 0.f); r[j + 1] = fmaxf(r[j + 1] + b.y, 0.f);
                             r[j + 2] = fmaxf(r[j + 2] + b.z, 0.f); r[j + 3] = fmaxf(r[j + 3] + b.w, 0.f);
                         }
+                        if (pool_out != nullptr) {
+                            // fused 2x2/2 VALID max-pool (model.py / Keras MaxPooling2D): the window partners of pixel
+                            // (ty, tx) are lanes ^1 (tx + 1) and ^16 (ty + 1) of this warp -- a warp holds tile rows 2q, 2q+1.
+                            // Windows that exist lie completely inside the image, so out-of-image lanes never contribute.
+                            const bool writer = (lane & 17) == 0 && gy + 1 < H && gx + 1 < W;
+                            float* prow = pool_out + (size_t(gy >> 1) * (W >> 1) + (gx >> 1)) * size_t(Cout) + n0 + c0;
+#pragma unroll
+                            for (int j = 0; j < 32; j += 4) {
+                                float pv[4];
+#pragma unroll
+                                for (int e = 0; e < 4; ++e) {
+                                    float v = fmaxf(r[j + e], __shfl_xor_sync(0xffffffffu, r[j + e], 1));
+                                    pv[e] = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, 16));
+                                }
+                                if (writer) *reinterpret_cast<float4*>(prow + j) = make_float4(pv[0], pv[1], pv[2], pv[3]);
+                            }
+                        }
                     } else {
                         if (seed != nullptr) {
 #pragma unroll
@@ -478,11 +496,13 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                             }
                         }
                     }
+                    if (inb) {
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) amax = fmaxf(amax, fabsf(r[j]));
+                        for (int j = 0; j < 32; ++j) amax = fmaxf(amax, fabsf(r[j]));
 #pragma unroll
-                    for (int j = 0; j < 32; j += 4)
-                        *reinterpret_cast<float4*>(Y + rowoff + c0 + j) = make_float4(r[j], r[j + 1], r[j + 2], r[j + 3]);
+                        for (int j = 0; j < 32; j += 4)
+                            *reinterpret_cast<float4*>(Y + rowoff + c0 + j) = make_float4(r[j], r[j + 1], r[j + 2], r[j + 3]);
+                    }
                 }
             }
         }
@@ -607,7 +627,7 @@ template <int BN, int MODE>
 static int launch_tc(const CUtensorMap& tmA, const CUtensorMap& tmBhi, const CUtensorMap& tmBlo, const float* bias, float* Y,
                      const float* seed, const float* mask, int H, int W, int Cin, int Cout, const uint32_t* a_absmax,
                      const uint32_t* b_absmax, uint32_t* y_absmax, cudaStream_t st, const float* cls_masks = nullptr,
-                     const uint32_t* tile_active = nullptr, const uint32_t* w_absmax = nullptr) {
+                     const uint32_t* tile_active = nullptr, const uint32_t* w_absmax = nullptr, float* pool_out = nullptr) {
     using Cfg = TcCfg<BN>;
     auto kern = conv3x3_tc_kernel<BN, MODE>;
     static bool configured = false;
@@ -619,7 +639,7 @@ static int launch_tc(const CUtensorMap& tmA, const CUtensorMap& tmBhi, const CUt
     const int total = tw * th * (Cout / BN);
     const int grid = total < num_sms() ? total : num_sms();
     kern<<<grid, TC_THREADS, Cfg::SMEM_BYTES, st>>>(tmA, tmBhi, tmBlo, bias, Y, seed, mask, H, W, Cin, Cout, tw, tw * th,
-                                                    cls_masks, tile_active, a_absmax, b_absmax, w_absmax, y_absmax);
+                                                    cls_masks, tile_active, a_absmax, b_absmax, w_absmax, y_absmax, pool_out);
     ADPST_LAUNCH_CHECK();
     return ADPST_OK;
 }
@@ -634,8 +654,9 @@ static int make_act_map(CUtensorMap* tm, const float* X, int H, int W, int C) {
 // X: (H,W,Cin) activation; gradient = 0: conv i forward (bias + ReLU), 1: data gradient of conv i (Cin/Cout are the GEMM's
 // K and N, i.e. already swapped for the gradient).  x_absmax: device slot holding max|X| (float bits); y_absmax (may be
 // NULL): slot that receives max|Y| (atomicMax; the caller zeroes it).
+// pool_out (forward only, may be NULL): receives the 2x2/2 max-pool of Y, (H/2, W/2, Cout).
 int launch_conv_tc(adpst_vgg* h, int i, int gradient, const float* X, float* Y, const float* seed, const float* mask, int H,
-                   int W, int Cin, int Cout, const uint32_t* x_absmax, uint32_t* y_absmax, cudaStream_t st) {
+                   int W, int Cin, int Cout, const uint32_t* x_absmax, uint32_t* y_absmax, float* pool_out, cudaStream_t st) {
     CUtensorMap tmA;
     int rc = make_act_map(&tmA, X, H, W, Cin);
     if (rc != ADPST_OK) return rc;
@@ -646,8 +667,10 @@ int launch_conv_tc(adpst_vgg* h, int i, int gradient, const float* X, float* Y, 
     const int BN = Cout >= 128 ? 128 : Cout;
     if (!gradient) {
         if (BN == 128)
-            return launch_tc<128, MODE_FWD>(tmA, bh, bl, bias, Y, seed, mask, H, W, Cin, Cout, x_absmax, wslot, y_absmax, st);
-        return launch_tc<64, MODE_FWD>(tmA, bh, bl, bias, Y, seed, mask, H, W, Cin, Cout, x_absmax, wslot, y_absmax, st);
+            return launch_tc<128, MODE_FWD>(tmA, bh, bl, bias, Y, seed, mask, H, W, Cin, Cout, x_absmax, wslot, y_absmax, st,
+                                            nullptr, nullptr, nullptr, pool_out);
+        return launch_tc<64, MODE_FWD>(tmA, bh, bl, bias, Y, seed, mask, H, W, Cin, Cout, x_absmax, wslot, y_absmax, st, nullptr,
+                                       nullptr, nullptr, pool_out);
     }
     if (BN == 128)
         return launch_tc<128, MODE_BWD>(tmA, bh, bl, bias, Y, seed, mask, H, W, Cin, Cout, x_absmax, wslot, y_absmax, st);

@@ -401,8 +401,10 @@ static int launch_conv_simt(int mode, bool pre, const float* X, const float* Wt,
 // (block1_conv1: Cin = 3) or when the handle was switched to CONV_PATH_SIMT (validation).
 // x_absmax: slot with max|X| (NULL: measured here with an extra pass over X); y_absmax (may be NULL): slot that receives
 // max|Y| (must have been zeroed; every kernel family records it in its epilogue).
+// pool_out (forward, may be NULL): where the following 2x2 max-pool goes; *pooled is set when the kernel wrote it.
 static int launch_conv(adpst_vgg* h, int i, int mode, const float* X, float* Y, const float* seed, const float* mask,
-                       int lh, int lw, const uint32_t* x_absmax, uint32_t* y_absmax, cudaStream_t st) {
+                       int lh, int lw, const uint32_t* x_absmax, uint32_t* y_absmax, cudaStream_t st,
+                       float* pool_out = nullptr, bool* pooled = nullptr) {
     const bool grad = (mode == MODE_BWD);
     const int K = grad ? conv_cout(i) : conv_cin(i), N = grad ? conv_cin(i) : conv_cout(i);
     if (h->conv_path == CONV_PATH_TENSOR && h->tc_ready && i > 0 && conv_tc_eligible(K, N)) {
@@ -412,7 +414,8 @@ static int launch_conv(adpst_vgg* h, int i, int mode, const float* X, float* Y, 
             if (rc != ADPST_OK) return rc;
             x_absmax = scratch;
         }
-        return launch_conv_tc(h, i, grad ? 1 : 0, X, Y, seed, mask, lh, lw, K, N, x_absmax, y_absmax, st);
+        if (pooled) *pooled = (pool_out != nullptr && !grad);
+        return launch_conv_tc(h, i, grad ? 1 : 0, X, Y, seed, mask, lh, lw, K, N, x_absmax, y_absmax, grad ? nullptr : pool_out, st);
     }
     return launch_conv_simt(mode, i == 0 && !grad, X, grad ? h->wb[i] : h->wf[i], grad ? nullptr : h->bias[i], Y, seed, mask,
                             lh, lw, K, N, y_absmax, st);
@@ -519,16 +522,26 @@ int adpst_vgg_forward(adpst_vgg* h, const float* image_dev, int H, int W, float*
         layer_hw(i, H, W, &lh, &lw);
         ADPST_REQUIRE(acts_dev[i] != nullptr, "vgg_forward: acts[%d] is NULL", i);
         // a max-pool keeps the maximum of a post-ReLU map, so the pooled tensor shares the slot of the conv before it
+        float* pool_out = nullptr;                 // the tensor-core kernel pools in its epilogue
+        for (int j = 0; j < ADPST_VGG_NUM_POOL; ++j)
+            if (kPoolAfter[j] == i && i < last) {
+                ADPST_REQUIRE(pools_dev[j] != nullptr, "vgg_forward: pools[%d] is NULL", j);
+                pool_out = pools_dev[j];
+            }
+        bool pooled = false;
         int rc = launch_conv(h, i, MODE_FWD, x, acts_dev[i], nullptr, nullptr, lh, lw, i > 0 ? h->amax + AMAX_ACT + i - 1 : nullptr,
-                             h->amax + AMAX_ACT + i, st);
+                             h->amax + AMAX_ACT + i, st, pool_out, &pooled);
         if (rc != ADPST_OK) return rc;
         x = acts_dev[i];
         for (int j = 0; j < ADPST_VGG_NUM_POOL; ++j) {
             if (kPoolAfter[j] == i && i < last) {
-                ADPST_REQUIRE(pools_dev[j] != nullptr, "vgg_forward: pools[%d] is NULL", j);
-                const size_t items = size_t(lh / 2) * (lw / 2) * (conv_cout(i) / 4);
-                maxpool2_kernel<<<stream_grid(items), 256, 0, st>>>(acts_dev[i], pools_dev[j], lh, lw, conv_cout(i));
-                ADPST_LAUNCH_CHECK();
+                if (!pooled) {
+                    const size_t items = size_t(lh / 2) * (lw / 2) * (conv_cout(i) / 4);
+                    if (items > 0) {
+                        maxpool2_kernel<<<stream_grid(items), 256, 0, st>>>(acts_dev[i], pools_dev[j], lh, lw, conv_cout(i));
+                        ADPST_LAUNCH_CHECK();
+                    }
+                }
                 x = pools_dev[j];
             }
         }
