@@ -130,10 +130,13 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap tmF, const float* __restrict_
                 const int p = patch_ids[my_begin + it];
                 const int y0 = (p / patches_w) * GM_PH, x0 = (p % patches_w) * GM_PW;
                 uint8_t* st = smem + s * Cfg::STAGE_BYTES;
-                tc::mbar_arrive_expect_tx(&full[s], Cfg::RAW_A + (diag ? 0 : Cfg::RAW_B));
+                // BN == 64 <=> C == 64: only 64 of the M = 128 operand rows exist; rows 64..127 are never written and the
+                // accumulator rows they produce are never read
+                constexpr int a_blocks = BN == 64 ? 2 : 4;
+                tc::mbar_arrive_expect_tx(&full[s], a_blocks * GM_BLK_BYTES + (diag ? 0 : Cfg::RAW_B));
 #pragma unroll
-                for (int b = 0; b < 4; ++b)          // C == 64: the two channel blocks are loaded twice (rows 64..127 unused)
-                    tc::tma_load_4d(st + b * GM_BLK_BYTES, &tmF, &full[s], (tm * 128 + b * 32) % C, x0, y0, 0);
+                for (int b = 0; b < a_blocks; ++b)
+                    tc::tma_load_4d(st + b * GM_BLK_BYTES, &tmF, &full[s], tm * 128 + b * 32, x0, y0, 0);
                 if (!diag) {
 #pragma unroll
                     for (int b = 0; b < BN / 32; ++b)
@@ -204,6 +207,35 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap tmF, const float* __restrict_
             m_next = mask_of(it + 2);                                   // the dependent global loads of the next stage, early
             tc::mbar_wait(&full[s], round & 1);
             uint8_t* st = smem + s * Cfg::STAGE_BYTES;
+            if constexpr (BN == 64) {
+                // C == 64: the 128 threads share 32 pixels x 64 channels, 16 channels (two 16-byte fp16 units) each
+                const int e = cq;                                        // channels 16 e .. 16 e + 15
+                const uint8_t* raw = st + (e >> 1) * GM_BLK_BYTES + p * 128;
+                uint8_t* ohi = st + Cfg::OFF_AHI + (p >> 3) * 1024 + (p & 7) * 128;
+                uint8_t* olo = st + Cfg::OFF_ALO + (p >> 3) * 1024 + (p & 7) * 128;
+#pragma unroll
+                for (int u = 0; u < 2; ++u) {
+                    const int c16 = (e & 1) * 4 + 2 * u;                 // 16-byte chunk of the landed 32-channel row
+                    const float4 v0 = *reinterpret_cast<const float4*>(raw + ((c16 ^ (p & 7)) << 4));
+                    const float4 v1 = *reinterpret_cast<const float4*>(raw + (((c16 + 1) ^ (p & 7)) << 4));
+                    const float x[8] = {v0.x * sm, v0.y * sm, v0.z * sm, v0.w * sm, v1.x * sm, v1.y * sm, v1.z * sm, v1.w * sm};
+                    uint32_t hw[4], lw[4];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const __half2 h = __floats2half2_rn(x[2 * j], x[2 * j + 1]);
+                        const float2 f = __half22float2(h);
+                        const __half2 l = __floats2half2_rn((x[2 * j] - f.x) * 2048.0f, (x[2 * j + 1] - f.y) * 2048.0f);
+                        hw[j] = *reinterpret_cast<const uint32_t*>(&h);
+                        lw[j] = *reinterpret_cast<const uint32_t*>(&l);
+                    }
+                    const int chunk = ((e * 2 + u) ^ (p & 7)) << 4;
+                    *reinterpret_cast<uint4*>(ohi + chunk) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+                    *reinterpret_cast<uint4*>(olo + chunk) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+                }
+                tc::fence_proxy_async_smem();
+                tc::mbar_arrive(&ready[s]);
+                continue;
+            }
             const int nsets = diag ? 1 : 2;
             for (int set = 0; set < nsets; ++set) {
                 if (set == 1 && cq * 32 >= BN) break;
