@@ -610,8 +610,10 @@ __device__ __forceinline__ void lap_march3_step(Lap3State& st, const float (&nI)
 template <bool V2>
 __global__ void __launch_bounds__(L3_WARPS * 32)
 lap_march3_kernel(const float* __restrict__ img, const float* __restrict__ x, float* __restrict__ y, double* __restrict__ partial,
-                  int H, int W, double eps, double y_scale, int RW, int strips_x, int total_warps, int qlo, int qhi) {
+                  int H, int W, double eps, double y_scale, int RW, int strips_x, int total_warps, int qlo, int qhi,
+                  unsigned int* __restrict__ ticket, double* __restrict__ xLx_out) {
     __shared__ double sRed[32];
+    __shared__ bool sLast;
     const int lane = threadIdx.x & 31;
     int gw = blockIdx.x * L3_WARPS + (threadIdx.x >> 5);
     const bool live = gw < total_warps;                        // spare warps of the last CTA run an empty strip
@@ -672,8 +674,22 @@ lap_march3_kernel(const float* __restrict__ img, const float* __restrict__ x, fl
         }
     }
     if (partial != nullptr) {
+        // x^T L x: per-CTA partials, summed in a fixed order by whichever CTA finishes last (deterministic, no second launch;
+        // the ticket counter is left at zero, so the kernel can be replayed from a CUDA graph)
         const double tot = block_sum<double>(acc, sRed);
-        if (threadIdx.x == 0) partial[blockIdx.x] = tot;
+        if (threadIdx.x == 0) {
+            partial[blockIdx.x] = tot;
+            __threadfence();
+            sLast = (atomicAdd(ticket, 1u) == gridDim.x - 1);
+        }
+        __syncthreads();
+        if (sLast) {
+            __threadfence();
+            double a = 0.0;
+            for (int i = threadIdx.x; i < int(gridDim.x); i += blockDim.x) a += partial[i];
+            a = block_sum<double>(a, sRed);
+            if (threadIdx.x == 0) { *xLx_out = a; *ticket = 0u; }
+        }
     }
 }
 
@@ -799,7 +815,7 @@ struct adpst_laplacian {
     int mode, H, W, R, io_dtype, compute_dtype;
     double eps;
     void* image = nullptr;       // (H,W,3) io_dtype, owned
-    double* partials = nullptr;  // one per CTA, owned
+    double* partials = nullptr;  // one per CTA, owned; followed by the "last CTA" ticket counter of the march3 kernel
     int npartials = 0;
     bool force_tile_kernel = false;   // validation: use the shared-memory tile kernel for r = 1 as well
     int q_col_lo = 0, q_col_hi = 0;   // x^T L x restricted to these columns (spatially tiled runs); (0,0) = all
@@ -832,20 +848,23 @@ static int launch_march(adpst_laplacian* h, const void* x, void* y, double y_sca
         const float* xf = static_cast<const float*>(x);
         float* yf = static_cast<float*>(y);
         double* part = xLx ? h->partials : nullptr;
+        unsigned int* ticket = reinterpret_cast<unsigned int*>(h->partials + h->npartials);
         if (h->mode == ADPST_LAP_V2)
             lap_march3_kernel<true><<<ctas, L3_WARPS * 32, 0, st>>>(img, xf, yf, part, h->H, h->W, h->eps, y_scale, RW, strips_x,
-                                                                    total, qlo, qhi);
+                                                                    total, qlo, qhi, ticket, xLx);
         else
             lap_march3_kernel<false><<<ctas, L3_WARPS * 32, 0, st>>>(img, xf, yf, part, h->H, h->W, h->eps, y_scale, RW, strips_x,
-                                                                     total, qlo, qhi);
-    } else
+                                                                     total, qlo, qhi, ticket, xLx);
+        ADPST_LAUNCH_CHECK();
+    } else {
         lap_march_kernel<TC><<<ctas, LM_WARPS * 32, 0, st>>>(static_cast<const float*>(h->image), static_cast<const float*>(x),
                                                              static_cast<float*>(y), xLx ? h->partials : nullptr, h->H, h->W,
                                                              h->mode, TC(h->eps), TC(y_scale), RW, strips_x, total, qlo, qhi);
-    ADPST_LAUNCH_CHECK();
-    if (xLx) {
-        sum_partials_kernel<<<1, 256, 0, st>>>(h->partials, ctas, xLx);
         ADPST_LAUNCH_CHECK();
+        if (xLx) {
+            sum_partials_kernel<<<1, 256, 0, st>>>(h->partials, ctas, xLx);
+            ADPST_LAUNCH_CHECK();
+        }
     }
     return ADPST_OK;
 }
@@ -958,7 +977,8 @@ int adpst_laplacian_create(int mode, int H, int W, int radius, double epsilon, c
     cudaError_t e = cudaMalloc(&h->image, bytes);
     if (e == cudaSuccess) {
         h->npartials = ((W + 31) / 32) * ((H + 15) / 16) + 64;
-        e = cudaMalloc(reinterpret_cast<void**>(&h->partials), sizeof(double) * h->npartials);
+        e = cudaMalloc(reinterpret_cast<void**>(&h->partials), sizeof(double) * (h->npartials + 1));
+        if (e == cudaSuccess) e = cudaMemsetAsync(h->partials + h->npartials, 0, sizeof(double), as_stream(stream));
     }
     if (e == cudaSuccess) e = cudaMemcpyAsync(h->image, image_dev, bytes, cudaMemcpyDeviceToDevice, as_stream(stream));
     if (e != cudaSuccess) {
