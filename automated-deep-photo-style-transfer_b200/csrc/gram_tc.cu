@@ -201,11 +201,15 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap tmF, const float* __restrict_
             return 0.f;
         };
         float m_next = mask_of(grp);
-        for (int it = grp; it < iters; it += 2) {
+        for (int it = 0; it < iters; ++it) {
             const int s = it % GM_STAGES, round = it / GM_STAGES;
+            // Every warpgroup observes EVERY phase of full[s], also for the stages the other one transforms: with an odd number
+            // of ring slots a group would otherwise see only every second phase of a slot, and a parity wait cannot tell a
+            // phase from the one two completions earlier (it could run past a TMA load that has not landed yet).
+            tc::mbar_wait(&full[s], round & 1);
+            if ((it & 1) != grp) continue;
             const float sm = m_next * scale;
             m_next = mask_of(it + 2);                                   // the dependent global loads of the next stage, early
-            tc::mbar_wait(&full[s], round & 1);
             uint8_t* st = smem + s * Cfg::STAGE_BYTES;
             if constexpr (BN == 64) {
                 // C == 64: the 128 threads share 32 pixels x 64 channels, 16 channels (two 16-byte fp16 units) each

@@ -1,6 +1,7 @@
 """Thin, typed Python wrappers over the C-ABI entry points that are not tied to a handle.
 Every function launches hand-written CUDA from libadpst.so on torch's current stream; none has a fallback."""
 import ctypes
+import os
 
 import torch
 
@@ -101,9 +102,15 @@ def absmax_slot(t):
     return slot
 
 
-def gram_masked(F, masks, K, workspace=None, patches=None, path="tensor", out=None, f_absmax=None, masks_absmax=None):
+# validation switch, like ADPST_CONV_PATH for the convolutions: "simt" routes the Gram and style-gradient kernels to the exact-float32
+# CUDA-core kernels
+_DEFAULT_PATH = "simt" if os.environ.get("ADPST_LOSS_PATH", "").lower() == "simt" else "tensor"
+
+
+def gram_masked(F, masks, K, workspace=None, patches=None, path=None, out=None, f_absmax=None, masks_absmax=None):
     """F: (h,w,C) float32 feature map ((HW,C) is taken as h = HW, w = 1); masks: (K,h*w) float32 or None.
     Returns (K,C,C) float32  (loss.py:96-102).  `patches` = gram_patch_lists(...) enables the tcgen05 kernel."""
+    path = path or _DEFAULT_PATH
     _f32(F, "F")
     if F.dim() == 2:
         F = F.reshape(F.shape[0], 1, F.shape[1])
@@ -146,10 +153,11 @@ def style_tiles(masks, K, h, w, device):
 
 
 def style_layer_backward(F, masks, K, G, A, loss_scale, grad_scale, loss_acc, dF, accumulate=False, workspace=None,
-                         path="tensor", hw_norm=0.0, f_absmax=None, tiles=None):
+                         path=None, hw_norm=0.0, f_absmax=None, tiles=None):
     """One layer of loss.py:104-137: accumulates the loss value and writes/adds its gradient w.r.t. F.
     F: (h, w, C) feature map (a (HW, C) matrix is treated as h = HW, w = 1... use the 3-D form for 2-D tiling).
     f_absmax: device address of a slot holding max|F| (act_absmax_slot), or None to have it measured."""
+    path = path or _DEFAULT_PATH
     _f32(F, "F"); _f32(G, "G"); _f32(A, "A")
     if F.dim() == 2:
         F = F.reshape(F.shape[0], 1, F.shape[1])
