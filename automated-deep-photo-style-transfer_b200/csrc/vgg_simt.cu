@@ -4,7 +4,7 @@
 //            style_transfer.py:341            (tape.gradient through the extractor; weights frozen model.py:11,25)
 //
 // This is the exact-float32 path: every product and sum is IEEE float32, so it holds the 1e-5 parity bar by
-// construction.  The tcgen05 (3xTF32) implicit-GEMM kernels in conv_tc.cu are validated against it.
+// construction.  The tcgen05 (3xFP16) implicit-GEMM kernels in conv_tc.cu are validated against it.
 //
 // Layout: activations NHWC (N = 1); forward weights [tap][Cin][Cout] (= Keras HWIO), gradient weights
 // [tap'][Cout][Cin] with the taps flipped, so the data gradient is the same 3x3 SAME convolution.

@@ -1,4 +1,4 @@
-"""Development helper: error of the tcgen05 3xTF32 conv vs the fp32 CUDA-core kernel and vs a float64 torch conv."""
+"""Development helper: error of the tcgen05 3xFP16 conv vs the fp32 CUDA-core kernel and vs a float64 torch conv."""
 import importlib, os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch, torch.nn.functional as F

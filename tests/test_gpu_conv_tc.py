@@ -1,4 +1,4 @@
-"""GPU: the tcgen05 3xTF32 implicit-GEMM convolution against the exact-float32 CUDA-core kernel, layer by layer,
+"""GPU: the tcgen05 3xFP16 implicit-GEMM convolution against the exact-float32 CUDA-core kernel, layer by layer,
 forward and data gradient, including ragged sizes (TMA zero fill = SAME padding, partial tiles)."""
 import importlib
 
