@@ -838,8 +838,7 @@ static int launch_march(adpst_laplacian* h, const void* x, void* y, double y_sca
     const int qlo = h->q_col_hi > h->q_col_lo ? h->q_col_lo : 0, qhi = h->q_col_hi > h->q_col_lo ? h->q_col_hi : h->W;
     constexpr bool f64 = std::is_same<TC, double>::value;
     const int cols = f64 ? L3_COLS : LM_COLS;
-    static const int rw_override = getenv("ADPST_LAP_RW") ? atoi(getenv("ADPST_LAP_RW")) : 0;      // experiments
-    const int RW = rw_override > 0 ? rw_override : march_rows(h->H, h->W, f64 ? 8 : 16, cols);
+    const int RW = march_rows(h->H, h->W, f64 ? 8 : 16, cols);
     const int strips_x = (h->W + cols - 1) / cols, total = strips_x * ((h->H + RW - 1) / RW);
     const int ctas = (total + LM_WARPS - 1) / LM_WARPS;
     if (ctas > h->npartials) return fail(ADPST_ERR_INVALID, "laplacian: partial buffer too small (%d > %d)", ctas, h->npartials);

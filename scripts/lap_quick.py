@@ -24,5 +24,4 @@ for size in sizes:
             a.record(); fn(); b.record(); torch.cuda.synchronize()
             ts.append(a.elapsed_time(b))
         ts.sort(); med = ts[len(ts) // 2]
-        print("%s %d: %.4f ms  %.0f GB/s algorithmic  (env kernel=%s rw=%s)" % (name, size, med, 36.0 * size * size / med / 1e6,
-              os.environ.get("ADPST_LAP_KERNEL", "3"), os.environ.get("ADPST_LAP_RW", "auto")), flush=True)
+        print("%s %d: %.4f ms  %.0f GB/s algorithmic" % (name, size, med, 36.0 * size * size / med / 1e6), flush=True)

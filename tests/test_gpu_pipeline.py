@@ -146,6 +146,61 @@ def test_masked_gram_and_style_gradient(hw, C, K, path):
     assert _rel(dF2.cpu().numpy(), 2 * gF.numpy()) < 5 * TOL
 
 
+def test_masks_above_one_and_wide_dynamic_range():
+    """The tensor-core kernels scale their FP16 operands by max|F| (and max|mask|): masks above 1 and feature maps with a
+    huge dynamic range (values 2^-30 of the maximum) must neither overflow nor lose the max-norm accuracy."""
+    k = _m("kernels")
+    h, w, C, K = 24, 32, 128, 3
+    rng = np.random.default_rng(5)
+    F = (rng.random((h * w, C)) * 2000).astype(np.float32)
+    F[::7] *= 2.0 ** -30                                   # rows far below the FP16 normal range after scaling
+    lab = rng.integers(0, K, h * w)
+    m = (np.stack([(lab == i) for i in range(K)]).astype(np.float32) * 3.0).astype(np.float32)      # weights up to 9
+    Fd, md = torch.as_tensor(F).cuda(), torch.as_tensor(m).cuda()
+    F3 = Fd.reshape(h, w, C)
+    Gt = k.gram_masked(F3, md, K, path="tensor", patches=k.gram_patch_lists(md, h, w, K, "cuda"))
+    X = torch.as_tensor(F, dtype=torch.float64)
+    ref = torch.stack([(X * float(1)) .T @ (X * torch.as_tensor(m[i], dtype=torch.float64)[:, None] ** 2) for i in range(K)])
+    assert torch.isfinite(Gt).all()
+    assert _rel(Gt.cpu().numpy(), ref.numpy()) < TOL
+    A = torch.zeros_like(Gt)
+    acc = torch.zeros(1, dtype=torch.float64, device="cuda")
+    dT, dS = torch.empty_like(Fd), torch.empty_like(Fd)
+    k.style_layer_backward(F3, md, K, Gt, A, 1.0, 1.0, acc, dT, path="tensor")
+    k.style_layer_backward(F3, md, K, Gt, A, 1.0, 1.0, acc, dS, path="simt")
+    assert torch.isfinite(dT).all()
+    assert _rel(dT.cpu().numpy(), dS.cpu().numpy()) < 5 * TOL
+
+
+def test_absmax_slot():
+    k = _m("kernels")
+    for n in (1, 3, 4, 1000, 4099):
+        x = (torch.rand(n, device="cuda") - 0.5) * 37.0
+        slot = k.absmax_slot(x)
+        assert float(slot.view(torch.float32)[0]) == float(x.abs().max())
+    assert int(k.absmax_slot(torch.zeros(16, device="cuda"))[0]) == 0
+
+
+def test_repeated_runs_are_stable(weights, synth):
+    """Two independent set-ups run the same 25 eager steps: no launch failure (pipeline races show up as rare ones) and the
+    same losses (reductions are order-fixed except the float64 atomics of the style term)."""
+    st = _m("style_transfer")
+    args = _args()
+    hist = []
+    for run in range(2):
+        ext, loss, _, c_dev = _setup(96, 128, 3, weights, synth, args)
+        step = st.make_train_step(ext, loss, st.Adam(args.adam_lr, args.adam_beta1, args.adam_beta2, args.adam_epsilon))
+        x = c_dev.clone()
+        out = []
+        for _ in range(25):
+            d = step(x)
+            out.append(float(d["Total loss"]))
+        torch.cuda.synchronize()
+        hist.append(out)
+    for a, b in zip(*hist):
+        assert abs(a - b) <= 1e-6 * abs(a)
+
+
 def _setup(H, W, K, weights, synth, args, matting="v2", Hs=None, Ws=None):
     vgg, lossm = _m("components.VGG19.model"), _m("components.loss")
     Hs, Ws = Hs or H, Ws or W
