@@ -364,7 +364,8 @@ def run_ours(args):
         out = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32 (VGG/Gram/Adam) + f64 (Laplacian arithmetic)", "data": "synthetic",
+            "dtype": "f32 (VGG/Gram: float32-accurate 3xFP16 tensor-core products, fp32 accumulation; Adam f32) + f64 (Laplacian arithmetic)",
+            "data": "synthetic",
             "config": {"workload": "configs[1]: one %dx%d content/style pair per GPU, %d semantic classes, content+masked-Gram "
                                    "style+photorealism loss, gradient, Adam+clip; matting_v2 eps=1e-7 r=1; random-init VGG19"
                                    % (S, S, K),
@@ -441,7 +442,7 @@ def run_tiled(args):
         print(json.dumps({"metric": "adam_iters_per_sec_%dx%d_spatially_tiled" % (W, H), "value": args.steps / (float(ms) * 1e-3),
                           "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
                           "ms_per_step": float(ms) / args.steps, "higher_is_better": True, "scaling": "strong",
-                          "vs_baseline": None, "dtype": "f32 + f64 (Laplacian arithmetic)", "data": "synthetic",
+                          "vs_baseline": None, "dtype": "f32 (float32-accurate 3xFP16 tensor-core products) + f64 (Laplacian arithmetic)", "data": "synthetic",
                           "config": {"workload": "configs[3]: one %dx%d image, %d classes, column strips of %d px + %d px halo per "
                                                  "interior side (local width %d), Gram all-reduce + strip all-gather per step"
                                                  % (W, H, K, W // world, tiled.HALO, t.local_w)},
