@@ -10,14 +10,6 @@ namespace tc {
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
 
-// fp32 -> tf32 (10-bit mantissa), round to nearest with ties away from zero (what cvt.rna.tf32.f32 computes), done with
-// two integer instructions: conversion instructions issue at a fraction of the ALU rate and the operand-transform warps
-// perform 8 of these per float4.  The result is an fp32 whose 13 low mantissa bits are zero.  (Inf/NaN inputs are not
-// expected on this path; finite values within 2^-11 of FLT_MAX would round to Inf exactly as cvt.rna does.)
-__device__ __forceinline__ float round_tf32(float x) {
-    return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u);
-}
-
 // One lane of the (converged) warp is elected; the predicate is known to be warp-uniform-single, which lets the compiler
 // keep UMMA descriptors in uniform registers instead of shuttling them per instruction.
 __device__ __forceinline__ bool elect_one_sync() {
@@ -140,6 +132,7 @@ __device__ __forceinline__ uint64_t umma_desc_kmajor_sw128(uint32_t smem_addr, u
     d |= uint64_t(2) << 61;
     return d;
 }
+// (kind::tf32 helpers: used only by the probes under tests/cuda -- the product kernels run kind::f16)
 // Instruction descriptor for kind::tf32, fp32 accumulate, both operands K-major.
 // [4,6) D format (1 = F32) | [7,10) A format (2 = TF32) | [10,13) B format | [15] A major | [16] B major | [17,23) N>>3 | [24,29) M>>4
 __host__ __device__ constexpr uint32_t umma_idesc_tf32(int M, int N) {
