@@ -329,6 +329,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         const int m = q * 32 + lane;
         const uint32_t lane_base = uint32_t(q * 32) << 16;
         const float scale_a = tc::pow2f_int(ea);
+        const uint32_t smem_base = tc::smem_u32(smem);
         int sa = 0, ra = 0, s = 0, git = 0;
         for (int w = blockIdx.x; w < total; w += gridDim.x) {
             const int tile = w / nblk;
@@ -361,10 +362,10 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                     uint32_t hi[2][16], lo[2][16];
 #pragma unroll
                     for (int half = 0; half < 2; ++half) {
-                        const uint8_t* arow = smem + sa * TC_A_BYTES + half * TC_A_BOX_BYTES + r * 128;
+                        const uint32_t arow = smem_base + uint32_t(sa * TC_A_BYTES + half * TC_A_BOX_BYTES + r * 128);
 #pragma unroll
                         for (int c = 0; c < 8; ++c) {
-                            const float4 v = *reinterpret_cast<const float4*>(arow + ((c ^ (r & 7)) << 4));
+                            const float4 v = tc::lds128(arow + uint32_t((c ^ (r & 7)) << 4));
                             const float t0 = v.x * scl, t1 = v.y * scl, t2 = v.z * scl, t3 = v.w * scl;
                             const __half2 h01 = __floats2half2_rn(t0, t1), h23 = __floats2half2_rn(t2, t3);
                             const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);

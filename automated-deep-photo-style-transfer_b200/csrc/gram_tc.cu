@@ -214,14 +214,14 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap tmF, const float* __restrict_
             if constexpr (BN == 64) {
                 // C == 64: the 128 threads share 32 pixels x 64 channels, 16 channels (two 16-byte fp16 units) each
                 const int e = cq;                                        // channels 16 e .. 16 e + 15
-                const uint8_t* raw = st + (e >> 1) * GM_BLK_BYTES + p * 128;
-                uint8_t* ohi = st + Cfg::OFF_AHI + (p >> 3) * 1024 + (p & 7) * 128;
-                uint8_t* olo = st + Cfg::OFF_ALO + (p >> 3) * 1024 + (p & 7) * 128;
+                const uint32_t raw = tc::smem_u32(st) + uint32_t((e >> 1) * GM_BLK_BYTES + p * 128);
+                const uint32_t ohi = tc::smem_u32(st) + uint32_t(Cfg::OFF_AHI + (p >> 3) * 1024 + (p & 7) * 128);
+                const uint32_t olo = tc::smem_u32(st) + uint32_t(Cfg::OFF_ALO + (p >> 3) * 1024 + (p & 7) * 128);
 #pragma unroll
                 for (int u = 0; u < 2; ++u) {
                     const int c16 = (e & 1) * 4 + 2 * u;                 // 16-byte chunk of the landed 32-channel row
-                    const float4 v0 = *reinterpret_cast<const float4*>(raw + ((c16 ^ (p & 7)) << 4));
-                    const float4 v1 = *reinterpret_cast<const float4*>(raw + (((c16 + 1) ^ (p & 7)) << 4));
+                    const float4 v0 = tc::lds128(raw + uint32_t((c16 ^ (p & 7)) << 4));
+                    const float4 v1 = tc::lds128(raw + uint32_t(((c16 + 1) ^ (p & 7)) << 4));
                     const float x[8] = {v0.x * sm, v0.y * sm, v0.z * sm, v0.w * sm, v1.x * sm, v1.y * sm, v1.z * sm, v1.w * sm};
                     uint32_t hw[4], lw[4];
 #pragma unroll
@@ -232,9 +232,9 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap tmF, const float* __restrict_
                         hw[j] = *reinterpret_cast<const uint32_t*>(&h);
                         lw[j] = *reinterpret_cast<const uint32_t*>(&l);
                     }
-                    const int chunk = ((e * 2 + u) ^ (p & 7)) << 4;
-                    *reinterpret_cast<uint4*>(ohi + chunk) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
-                    *reinterpret_cast<uint4*>(olo + chunk) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+                    const uint32_t chunk = uint32_t(((e * 2 + u) ^ (p & 7)) << 4);
+                    tc::sts128(ohi + chunk, hw[0], hw[1], hw[2], hw[3]);
+                    tc::sts128(olo + chunk, lw[0], lw[1], lw[2], lw[3]);
                 }
                 tc::fence_proxy_async_smem();
                 tc::mbar_arrive(&ready[s]);
@@ -243,14 +243,14 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap tmF, const float* __restrict_
             const int nsets = diag ? 1 : 2;
             for (int set = 0; set < nsets; ++set) {
                 if (set == 1 && cq * 32 >= BN) break;
-                const uint8_t* raw = st + (set ? Cfg::OFF_RAW_B : 0) + cq * GM_BLK_BYTES + p * 128;
-                uint8_t* ohi = st + (set ? Cfg::OFF_BHI : Cfg::OFF_AHI) + orow;
-                uint8_t* olo = st + (set ? Cfg::OFF_BLO : Cfg::OFF_ALO) + orow;
+                const uint32_t raw = tc::smem_u32(st) + uint32_t((set ? Cfg::OFF_RAW_B : 0) + cq * GM_BLK_BYTES + p * 128);
+                const uint32_t ohi = tc::smem_u32(st) + uint32_t((set ? Cfg::OFF_BHI : Cfg::OFF_AHI) + orow);
+                const uint32_t olo = tc::smem_u32(st) + uint32_t((set ? Cfg::OFF_BLO : Cfg::OFF_ALO) + orow);
 #pragma unroll
                 for (int u = 0; u < 4; ++u) {                            // 8 channels = one 16-byte unit of fp16
                     // landed layout: row = pixel (128 B), 16-byte chunk index XOR (row & 7)
-                    const float4 v0 = *reinterpret_cast<const float4*>(raw + (((2 * u) ^ (p & 7)) << 4));
-                    const float4 v1 = *reinterpret_cast<const float4*>(raw + (((2 * u + 1) ^ (p & 7)) << 4));
+                    const float4 v0 = tc::lds128(raw + uint32_t(((2 * u) ^ (p & 7)) << 4));
+                    const float4 v1 = tc::lds128(raw + uint32_t(((2 * u + 1) ^ (p & 7)) << 4));
                     const float x[8] = {v0.x * sm, v0.y * sm, v0.z * sm, v0.w * sm, v1.x * sm, v1.y * sm, v1.z * sm, v1.w * sm};
                     uint32_t hw[4], lw[4];
 #pragma unroll
@@ -261,9 +261,9 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap tmF, const float* __restrict_
                         hw[j] = *reinterpret_cast<const uint32_t*>(&h);
                         lw[j] = *reinterpret_cast<const uint32_t*>(&l);
                     }
-                    const int chunk = ((u0 + u) ^ (p & 7)) << 4;
-                    *reinterpret_cast<uint4*>(ohi + chunk) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
-                    *reinterpret_cast<uint4*>(olo + chunk) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+                    const uint32_t chunk = uint32_t(((u0 + u) ^ (p & 7)) << 4);
+                    tc::sts128(ohi + chunk, hw[0], hw[1], hw[2], hw[3]);
+                    tc::sts128(olo + chunk, lw[0], lw[1], lw[2], lw[3]);
                 }
             }
             tc::fence_proxy_async_smem();

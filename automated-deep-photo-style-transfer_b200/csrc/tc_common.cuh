@@ -18,6 +18,19 @@ __device__ __forceinline__ bool elect_one_sync() {
     return pred != 0;
 }
 
+// ---- explicit shared-memory accesses ----------------------------------------------------------------------------
+// The kernels carve their dynamic shared memory up by hand (1024-byte alignment via integer arithmetic), which hides the
+// address space from the compiler: plain dereferences become GENERIC loads/stores (LD.E / ST.E: longer latency, tracked
+// on the long scoreboard).  The transform warps therefore address shared memory with 32-bit shared addresses.
+__device__ __forceinline__ float4 lds128(uint32_t addr) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr) : "memory");
+    return v;
+}
+__device__ __forceinline__ void sts128(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+
 // ---- mbarrier ---------------------------------------------------------------------------------------------------
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
