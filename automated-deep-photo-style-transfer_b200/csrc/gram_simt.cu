@@ -107,20 +107,34 @@ gram_partial_kernel(const float* __restrict__ F, const float* __restrict__ masks
     }
 }
 
-// G[k][r][c] = sum_s ws[k][s][min-tile-order(r,c)]  (float64 accumulation, fixed order), mirrored to the lower triangle
+// G[k][r][c] = sum_s ws[k][s][r][c] for the 64x64 tiles on or above the diagonal (the only ones the Gram kernels write),
+// float64 accumulation in a fixed order; tiles above the diagonal are mirrored into the lower triangle through a
+// shared-memory transpose, so that every global access is a coalesced row segment.
+// grid = (C/32, C/32, K), block = (32, 8).
 __global__ void __launch_bounds__(256)
 gram_reduce_kernel(const float* __restrict__ ws, float* __restrict__ G, int C, int K, int splits) {
-    const size_t total = size_t(K) * C * C;
-    for (size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += size_t(gridDim.x) * blockDim.x) {
-        const int c = int(i % C);
-        const size_t t = i / C;
-        const int r = int(t % C), k = int(t / C);
-        int rr = r, cc = c;
-        if (r / GT > c / GT) { rr = c; cc = r; }               // tile below the diagonal: read its transpose
+    __shared__ float tile[32][33];
+    const int r0 = blockIdx.y * 32, c0 = blockIdx.x * 32, k = blockIdx.z;
+    const int tr = r0 / GT, tcx = c0 / GT;
+    if (tr > tcx) return;                                       // filled by the mirror of (tcx, tr)
+    const float* src = ws + (size_t(k) * splits) * C * C;
+    float* dst = G + size_t(k) * C * C;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int r = r0 + threadIdx.y + 8 * i, c = c0 + threadIdx.x;
         double a = 0.0;
-        const float* p = ws + (size_t(k) * splits) * C * C + size_t(rr) * C + cc;
+        const float* p = src + size_t(r) * C + c;
         for (int s = 0; s < splits; ++s) a += double(p[size_t(s) * C * C]);
-        G[i] = float(a);
+        const float v = float(a);
+        dst[size_t(r) * C + c] = v;
+        tile[threadIdx.y + 8 * i][threadIdx.x] = v;
+    }
+    if (tr == tcx) return;                                      // a diagonal tile holds both of its halves already
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int c = c0 + threadIdx.y + 8 * i, r = r0 + threadIdx.x;
+        dst[size_t(c) * C + r] = tile[threadIdx.x][threadIdx.y + 8 * i];
     }
 }
 
@@ -276,9 +290,8 @@ int adpst_gram_masked(const float* F_dev, int h, int w, int C, const float* mask
                                                        tiles);
         ADPST_LAUNCH_CHECK();
     }
-    const size_t total = size_t(K) * C * C;
-    gram_reduce_kernel<<<unsigned((total + 255) / 256 < 4096 ? (total + 255) / 256 : 4096), 256, 0, st>>>(
-        static_cast<const float*>(workspace_dev), G_dev, C, K, splits);
+    gram_reduce_kernel<<<dim3(C / 32, C / 32, K), dim3(32, 8), 0, st>>>(static_cast<const float*>(workspace_dev), G_dev, C, K,
+                                                                        splits);
     ADPST_LAUNCH_CHECK();
     return ADPST_OK;
 }
