@@ -168,3 +168,24 @@ def test_full_size_properties_1024(synth):
     y3, _ = v3.quadratic_form(x, want_y=True)
     d = (y2 - y3).reshape(H, W, 3)
     assert float(d[2:-2, 2:-2].abs().max()) < 1e-5 and float(d.abs().max()) > 1e-2
+
+
+@pytest.mark.parametrize("tag", ["a", "b", "c", "d"])
+def test_v2_matches_reference_code_golden(tag):
+    """Against tests/golden/v2_*.npz: outputs of the reference's own matting_v2.py (oracle/make_golden.py), r = 1, 2, 3."""
+    g = golden("v2_%s.npz" % tag)
+    img, eps, r = g["image"], float(g["eps"]), int(g["r"])
+    H, W, _ = img.shape
+    scale = np.abs(g["Lx"]).max()
+    for kw in ({}, {"storage_dtype": torch.float32, "compute_dtype": torch.float64}):
+        op = _v2().MattingLaplacian(torch.as_tensor(img).cuda(), epsilon=eps, window_radius=r, **kw)
+        assert tuple(op.shape) == tuple(g["shape"]) and op.radius == r and op.window_area == (2 * r + 1) ** 2
+        dt = op._op.operator_dtype if hasattr(op, "_op") else torch.float64
+        for x, ref, tol in ((g["x"], g["Lx"], 1e-9 if not kw else 2e-7), (img.reshape(H * W, 3), g["LI"], 1e-6 if not kw else 2e-6)):
+            y = op.matmul(torch.as_tensor(x).to(dt).cuda()).cpu().double().numpy()
+            # float32 storage rounds the OUTPUT to float32 (relative 6e-8 of each value); the arithmetic is float64
+            assert np.abs(y - ref).max() <= tol * max(np.abs(ref).max(), 1e-30) + (6e-8 * scale if kw else 0.0), (kw, np.abs(y - ref).max())
+    op = _v2().MattingLaplacian(torch.as_tensor(img).cuda(), epsilon=eps, window_radius=r)
+    if r == 1:
+        np.testing.assert_allclose(op.means.cpu().numpy().reshape(g["means"].shape), g["means"], rtol=0, atol=1e-12)
+        np.testing.assert_allclose(op.delta_inv.cpu().numpy().reshape(g["delta_inv"].shape), g["delta_inv"], rtol=1e-7)

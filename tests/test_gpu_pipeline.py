@@ -293,6 +293,34 @@ def test_hundred_adam_iterations_psnr(weights, synth):
     assert rel < 1e-3
 
 
+@pytest.mark.parametrize("tag", ["a", "b"])
+def test_loss_matches_reference_code_golden(tag):
+    """Against tests/golden/loss_*.npz: the loss dict of the reference's own components/loss.py (oracle/make_golden.py)
+    for given feature maps, masks and image -- content, masked-Gram style, photorealism, weighted total, key order."""
+    from conftest import golden
+    lossm = _m("components.loss")
+    g = golden("loss_%s.npz" % tag)
+    dev = lambda a: torch.as_tensor(np.asarray(a, np.float32)).cuda().contiguous()
+    ct = {k[3:]: dev(g[k]) for k in g.files if k.startswith("ct_")}
+    co = {k[3:]: dev(g[k]) for k in g.files if k.startswith("co_")}
+    st_ = {k[3:]: dev(g[k]) for k in g.files if k.startswith("st_")}
+    so = {k[3:]: dev(g[k]) for k in g.files if k.startswith("so_")}
+    K, wp = int(g["K"]), float(g["photo_weight"])
+    cm = [np.asarray(m, np.float32) for m in g["cmasks"]] if K else None
+    sm = [np.asarray(m, np.float32) for m in g["smasks"]] if K else None
+    image = dev(g["image"])
+    loss = lossm.Loss(ct, st_, _args(regularization_weight=wp), cm, sm)
+    if wp > 0:
+        loss.initialize_matting_laplacian(image[0].double())
+    d = loss(image, {"content": co, "style": so})
+    assert abs(float(d["Content loss"]) - float(g["content_loss"])) <= TOL * float(g["content_loss"])
+    assert abs(float(d["Style loss"]) - float(g["style_loss"])) <= TOL * float(g["style_loss"])
+    if wp > 0:
+        assert abs(float(d["Photorealism regualarization"]) - float(g["photo_loss"])) <= 1e-5 * float(g["photo_loss"])
+    assert abs(float(d["Total loss"]) - float(g["total_minus_nima"])) <= TOL * float(g["total_minus_nima"])
+    assert list(d.keys()) == [str(k) for k in g["keys"]]
+
+
 def test_nima_weight_is_refused(weights, synth):
     lossm = _m("components.loss")
     t = {"block4_conv2": torch.zeros(1, 2, 2, 512, device="cuda")}

@@ -64,3 +64,16 @@ def test_v2_x_equals_image_is_tiny(synth):
     op = matting.V2Operator(img, 1e-7, 1)
     y = op.matmul(img.reshape(-1, 3))
     assert np.abs(y).max() < 1e-4
+
+
+@pytest.mark.parametrize("tag", ["a", "b", "c", "d"])
+def test_v2_restatement_matches_reference_code(tag):
+    """tests/golden/v2_*.npz come from the reference's OWN matting_v2.py (its __init__ and _matmul), executed over the numpy
+    stand-in for its TensorFlow primitives (oracle/tf_shim.py, oracle/make_golden.py): fields, shape and mat-vecs."""
+    g = golden("v2_%s.npz" % tag)
+    op = matting.V2Operator(g["image"], float(g["eps"]), int(g["r"]))
+    assert tuple(op.shape) == tuple(g["shape"])
+    np.testing.assert_allclose(op.means, g["means"], rtol=0, atol=1e-14)
+    np.testing.assert_allclose(op.delta_inv, g["delta_inv"], rtol=1e-10, atol=0)
+    for x, y in ((g["x"], g["Lx"]), (g["image"].reshape(-1, 3), g["LI"])):
+        np.testing.assert_allclose(op.matmul(x), y, rtol=0, atol=1e-9 * max(np.abs(g["Lx"]).max(), 1e-30))
