@@ -30,7 +30,8 @@ constexpr int GM_BLK_BYTES = GM_PX * 128;                        // one landed b
 constexpr int GM_THREADS = 512;                                  // 4 warpgroups: {TMA, MMA, -, -}, transform x2, drain
 constexpr int GM_REGS_CTRL = 40, GM_REGS_XFORM = 112, GM_REGS_DRAIN = 224;      // setmaxnreg budget, as in conv_tc.cu
 constexpr int GM_CHUNK_ITERS = 4;                                // stages per promoted chunk (8 big MMAs)
-constexpr int GM_STAGES = 3;
+constexpr int GM_RAW_STAGES_MAX = 8;                             // landed float32 tiles in flight: 4 (BN = 128) or 8 (BN = 64)
+constexpr int GM_OP_STAGES = 2;                                  // FP16 operand tiles: slot g belongs to transform warpgroup g
 constexpr int GM_GROUP_BYTES = (GM_PX / 8) * 1024;               // one 64-channel group of an operand tile: 4 KB
 
 template <int BN> struct GramCfg {
@@ -38,10 +39,18 @@ template <int BN> struct GramCfg {
     static constexpr int RAW_B = (BN / 32) * GM_BLK_BYTES;
     static constexpr int A_BYTES = 2 * GM_GROUP_BYTES;            // fp16 operand tile: 128 channels x 32 pixels
     static constexpr int B_BYTES = (BN / 64) * GM_GROUP_BYTES;
-    static constexpr int OFF_RAW_B = RAW_A, OFF_AHI = RAW_A + RAW_B, OFF_ALO = OFF_AHI + A_BYTES, OFF_BHI = OFF_ALO + A_BYTES,
-                         OFF_BLO = OFF_BHI + B_BYTES;
-    static constexpr int STAGE_BYTES = OFF_BLO + B_BYTES;
-    static constexpr int SMEM_BYTES = GM_STAGES * STAGE_BYTES + 1024 + 256;
+    // Two rings.  The kernel is bound by the latency of its TMA loads (the activations come from HBM: ~3000 clk against
+    // ~400 clk of MMA work per stage), so the landed tiles get the deep ring; the operand tiles only need double buffering.
+    // Both ring sizes are even, so with the two transform warpgroups alternating stages every slot always belongs to the
+    // same warpgroup and it observes every phase of the slot's barriers (a parity wait cannot tell phases two apart).
+    static constexpr int RAW_STAGES = BN == 64 ? 8 : 4;           // (freed as soon as they have been read)
+    static constexpr int RAW_BYTES = BN == 64 ? 2 * GM_BLK_BYTES : RAW_A + RAW_B;   // C = 64: only two channel blocks exist
+    static constexpr int OFF_RAW_B = RAW_A;
+    static constexpr int OFF_AHI = 0, OFF_ALO = A_BYTES, OFF_BHI = 2 * A_BYTES, OFF_BLO = OFF_BHI + B_BYTES;
+    static constexpr int OP_BYTES = OFF_BLO + B_BYTES;
+    static constexpr int OFF_OP = RAW_STAGES * RAW_BYTES;
+    static constexpr int OFF_BARS = OFF_OP + GM_OP_STAGES * OP_BYTES;
+    static constexpr int SMEM_BYTES = OFF_BARS + 1024 + 256;
     static constexpr uint32_t TMEM_COLS = 4 * BN;
 };
 
@@ -70,11 +79,12 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap tmF, const float* __restrict_
     using Cfg = GramCfg<BN>;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + GM_STAGES * Cfg::STAGE_BYTES);
-    uint64_t* full = bars;
-    uint64_t* ready = bars + 4;
-    uint64_t* empty = bars + 8;
-    uint64_t* chunk_full = bars + 12;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::OFF_BARS);
+    uint64_t* full = bars;                      // [RAW_STAGES]    raw tile landed
+    uint64_t* raw_empty = bars + 8;             // [RAW_STAGES]    the transform warpgroup has read the raw tile
+    uint64_t* ready = bars + 16;                // [GM_OP_STAGES]  operand tiles written
+    uint64_t* empty = bars + 18;                // [GM_OP_STAGES]  the MMAs that read the operand tiles have retired
+    uint64_t* chunk_full = bars + 20;
     uint64_t* chunk_empty = chunk_full + 2;
     uint64_t* small_full = chunk_empty + 2;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(small_full + 1);
@@ -100,8 +110,11 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap tmF, const float* __restrict_
     }
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < GM_STAGES; ++s) {
+        for (int s = 0; s < Cfg::RAW_STAGES; ++s) {
             tc::mbar_init(&full[s], 1);
+            tc::mbar_init(&raw_empty[s], 128);
+        }
+        for (int s = 0; s < GM_OP_STAGES; ++s) {
             tc::mbar_init(&ready[s], 128);
             tc::mbar_init(&empty[s], 1);
         }
@@ -125,11 +138,11 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap tmF, const float* __restrict_
         asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(GM_REGS_CTRL));
         if (lane == 0) {
             for (int it = 0; it < iters; ++it) {
-                const int s = it % GM_STAGES, round = it / GM_STAGES;
-                tc::mbar_wait(&empty[s], (round & 1) ^ 1);
+                const int s = it % Cfg::RAW_STAGES, round = it / Cfg::RAW_STAGES;
+                tc::mbar_wait(&raw_empty[s], (round & 1) ^ 1);
                 const int p = patch_ids[my_begin + it];
                 const int y0 = (p / patches_w) * GM_PH, x0 = (p % patches_w) * GM_PW;
-                uint8_t* st = smem + s * Cfg::STAGE_BYTES;
+                uint8_t* st = smem + s * Cfg::RAW_BYTES;
                 // BN == 64 <=> C == 64: only 64 of the M = 128 operand rows exist; rows 64..127 are never written and the
                 // accumulator rows they produce are never read
                 constexpr int a_blocks = BN == 64 ? 2 : 4;
@@ -148,19 +161,19 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap tmF, const float* __restrict_
         // ================= MMA issuer (warp-uniform loop, one elected lane issues; see conv_tc.cu) =================
         asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(GM_REGS_CTRL));
         constexpr uint32_t idesc = tc::umma_idesc_f16(128, BN) | (1u << 15) | (1u << 16);      // A and B MN-major
-        const uint32_t stage0 = tc::smem_u32(smem);
+        const uint32_t stage0 = tc::smem_u32(smem) + Cfg::OFF_OP;
         const uint64_t d_ahi = umma_desc_mnmajor_sw128(stage0 + Cfg::OFF_AHI, GM_GROUP_BYTES, 1024);
         const uint64_t d_alo = umma_desc_mnmajor_sw128(stage0 + Cfg::OFF_ALO, GM_GROUP_BYTES, 1024);
         const uint64_t d_bhi = diag ? d_ahi : umma_desc_mnmajor_sw128(stage0 + Cfg::OFF_BHI, GM_GROUP_BYTES, 1024);
         const uint64_t d_blo = diag ? d_alo : umma_desc_mnmajor_sw128(stage0 + Cfg::OFF_BLO, GM_GROUP_BYTES, 1024);
-        int s = 0, round = 0;
         for (int it = 0; it < iters; ++it) {
+            const int s = it % GM_OP_STAGES, round = it / GM_OP_STAGES;
             const int c = it / GM_CHUNK_ITERS, cpos = it - c * GM_CHUNK_ITERS;
             const uint32_t tmem_big = tmem_base + uint32_t(c & 1) * BN;
             if (cpos == 0) tc::mbar_wait(&chunk_empty[c & 1], ((c >> 1) & 1) ^ 1);
-            tc::mbar_wait(&ready[s], round & 1);      // the transform warps arrive only after the TMA tile landed
+            tc::mbar_wait(&ready[s], round & 1);
             tc::tcgen05_fence_after();
-            const uint64_t soff = uint64_t(uint32_t(s) * uint32_t(Cfg::STAGE_BYTES >> 4));
+            const uint64_t soff = uint64_t(uint32_t(s) * uint32_t(Cfg::OP_BYTES >> 4));
             if (tc::elect_one_sync()) {
 #pragma unroll
                 for (int ks = 0; ks < GM_PX / 16; ++ks) {                 // 16 pixels per MMA = two 8-pixel groups (2048 bytes)
@@ -173,7 +186,6 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap tmF, const float* __restrict_
                 if (cpos == GM_CHUNK_ITERS - 1 || it == iters - 1) tc::umma_commit(&chunk_full[c & 1]);
             }
             __syncwarp();
-            if (++s == GM_STAGES) { s = 0; ++round; }
         }
         if (iters > 0 && tc::elect_one_sync()) tc::umma_commit(small_full);
         __syncwarp();
@@ -200,23 +212,23 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap tmF, const float* __restrict_
             if (gy < H && gx < W) return mk ? __ldg(mk + size_t(gy) * W + gx) : 1.0f;
             return 0.f;
         };
+        static_assert(Cfg::RAW_STAGES % 2 == 0 && Cfg::RAW_STAGES <= GM_RAW_STAGES_MAX && GM_OP_STAGES == 2, "every ring slot must always belong to the same warpgroup");
         float m_next = mask_of(grp);
-        for (int it = 0; it < iters; ++it) {
-            const int s = it % GM_STAGES, round = it / GM_STAGES;
-            // Every warpgroup observes EVERY phase of full[s], also for the stages the other one transforms: with an odd number
-            // of ring slots a group would otherwise see only every second phase of a slot, and a parity wait cannot tell a
-            // phase from the one two completions earlier (it could run past a TMA load that has not landed yet).
-            tc::mbar_wait(&full[s], round & 1);
-            if ((it & 1) != grp) continue;
+        for (int it = grp; it < iters; it += 2) {
+            // this warpgroup's stages: every second raw slot, operand slot grp
+            const int rs = it % Cfg::RAW_STAGES, rround = it / Cfg::RAW_STAGES, os = grp, oround = it >> 1;
             const float sm = m_next * scale;
             m_next = mask_of(it + 2);                                   // the dependent global loads of the next stage, early
-            uint8_t* st = smem + s * Cfg::STAGE_BYTES;
+            tc::mbar_wait(&full[rs], rround & 1);                       // the raw tile has landed
+            tc::mbar_wait(&empty[os], (oround & 1) ^ 1);                // the MMAs of stage it - 2 no longer read the operand slot
+            const uint8_t* st = smem + rs * Cfg::RAW_BYTES;             // raw tile
+            uint8_t* op = smem + Cfg::OFF_OP + os * Cfg::OP_BYTES;      // operand tiles
             if constexpr (BN == 64) {
                 // C == 64: the 128 threads share 32 pixels x 64 channels, 16 channels (two 16-byte fp16 units) each
                 const int e = cq;                                        // channels 16 e .. 16 e + 15
                 const uint32_t raw = tc::smem_u32(st) + uint32_t((e >> 1) * GM_BLK_BYTES + p * 128);
-                const uint32_t ohi = tc::smem_u32(st) + uint32_t(Cfg::OFF_AHI + (p >> 3) * 1024 + (p & 7) * 128);
-                const uint32_t olo = tc::smem_u32(st) + uint32_t(Cfg::OFF_ALO + (p >> 3) * 1024 + (p & 7) * 128);
+                const uint32_t ohi = tc::smem_u32(op) + uint32_t(Cfg::OFF_AHI + (p >> 3) * 1024 + (p & 7) * 128);
+                const uint32_t olo = tc::smem_u32(op) + uint32_t(Cfg::OFF_ALO + (p >> 3) * 1024 + (p & 7) * 128);
 #pragma unroll
                 for (int u = 0; u < 2; ++u) {
                     const int c16 = (e & 1) * 4 + 2 * u;                 // 16-byte chunk of the landed 32-channel row
@@ -236,16 +248,17 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap tmF, const float* __restrict_
                     tc::sts128(ohi + chunk, hw[0], hw[1], hw[2], hw[3]);
                     tc::sts128(olo + chunk, lw[0], lw[1], lw[2], lw[3]);
                 }
+                tc::mbar_arrive(&raw_empty[rs]);                         // (the stores above consumed every loaded value)
                 tc::fence_proxy_async_smem();
-                tc::mbar_arrive(&ready[s]);
+                tc::mbar_arrive(&ready[os]);
                 continue;
             }
             const int nsets = diag ? 1 : 2;
             for (int set = 0; set < nsets; ++set) {
                 if (set == 1 && cq * 32 >= BN) break;
                 const uint32_t raw = tc::smem_u32(st) + uint32_t((set ? Cfg::OFF_RAW_B : 0) + cq * GM_BLK_BYTES + p * 128);
-                const uint32_t ohi = tc::smem_u32(st) + uint32_t((set ? Cfg::OFF_BHI : Cfg::OFF_AHI) + orow);
-                const uint32_t olo = tc::smem_u32(st) + uint32_t((set ? Cfg::OFF_BLO : Cfg::OFF_ALO) + orow);
+                const uint32_t ohi = tc::smem_u32(op) + uint32_t((set ? Cfg::OFF_BHI : Cfg::OFF_AHI) + orow);
+                const uint32_t olo = tc::smem_u32(op) + uint32_t((set ? Cfg::OFF_BLO : Cfg::OFF_ALO) + orow);
 #pragma unroll
                 for (int u = 0; u < 4; ++u) {                            // 8 channels = one 16-byte unit of fp16
                     // landed layout: row = pixel (128 B), 16-byte chunk index XOR (row & 7)
@@ -266,8 +279,9 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap tmF, const float* __restrict_
                     tc::sts128(olo + chunk, lw[0], lw[1], lw[2], lw[3]);
                 }
             }
+            tc::mbar_arrive(&raw_empty[rs]);                             // (the stores above consumed every loaded value)
             tc::fence_proxy_async_smem();
-            tc::mbar_arrive(&ready[s]);
+            tc::mbar_arrive(&ready[os]);
         }
     } else {
         // ================= drain (chunk promotion) + store of the partial tile =================
