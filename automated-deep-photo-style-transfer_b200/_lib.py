@@ -53,7 +53,8 @@ SIGNATURES = {
     "adpst_style_tiles_bytes": (_sz, [_i]),
     "adpst_style_tiles": (_i, [_vp, _i, _i, _i, _vp, _vp]),
     "adpst_content_layer": (_i, [_vp, _vp, _sz, _d, _d, _vp, _vp, _i, _d, _i, _i, _i, _i, _vp]),
-    "adpst_loss_finalize": (_i, [_vp, _d, _d, _d, _vp, _vp]),
+    "adpst_tv_loss": (_i, [_vp, _i, _i, _d, _d, _vp, _vp, _i, _i, _i, _vp]),
+    "adpst_loss_finalize": (_i, [_vp, _d, _d, _d, _d, _vp, _vp]),
     "adpst_axpby": (_i, [_vp, _vp, _f, _vp, _f, _sz, _vp]),
 }
 

@@ -7,9 +7,13 @@ Same constructor and call signature, same dictionary keys (including the referen
   * the NIMA term (loss.py:141-153, InceptionResNetV2 with weights that are not in the tree) is out of scope:
     `nima_weight` must be 0 and 'NIMA loss' is reported as 0 (SURVEY D4);
   * the style Grams of the style target are constant and are computed once here, not every call (loss.py:130);
-  * `matting` selects the Laplacian variant ('v2' as hard-wired in the reference, loss.py:4, or 'v3').
+  * `matting` selects the Laplacian variant ('v2' as hard-wired in the reference, loss.py:4, or 'v3');
+  * `args.tv_weight` (optional attribute, default 0) adds a total-variation term -- an EXTENSION with no counterpart in
+    the reference.  With the default the dictionary, the total and the gradient are exactly the reference's.
 All arithmetic happens in libadpst kernels; the returned values are views of one float32 device vector.
 """
+import warnings
+
 import torch
 
 from .. import kernels
@@ -45,6 +49,14 @@ class Loss:
         if self.loss_weights['nima'] != 0.0:
             raise NotImplementedError("the NIMA term (loss.py:141-153) is not part of this hot path: nima_weight must "
                                       "be 0 (got %g)" % self.loss_weights['nima'])
+        if not Loss._nima_note_shown:
+            Loss._nima_note_shown = True
+            warnings.warn("automated-deep-photo-style-transfer_b200: the reference adds w_nima * (10 - NIMA score) with a default "
+                          "nima_weight of 1e5 (loss.py:64-72); that term is not built here, 'NIMA loss' is reported as 0 and "
+                          "'Total loss' / the gradient match a reference run with --nima_weight 0 only", stacklevel=2)
+        # EXTENSION (not in the reference): total-variation weight, tf.image.total_variation semantics; 0 = off
+        self.tv_weight = float(getattr(args, 'tv_weight', 0.0) or 0.0)
+        self.tv_name = 'Total variation loss'
         if (content_masks is None) != (style_masks is None):
             pass        # reference: masks are used only if both are given (loss.py:110); otherwise all-ones
         if content_masks is not None and style_masks is not None and len(content_masks) != len(style_masks):
@@ -60,8 +72,8 @@ class Loss:
 
         any_t = next(iter(content_target.values())) if len(content_target) else next(iter(style_target.values()))
         self.device = any_t.device
-        self._acc = torch.zeros(3, dtype=torch.float64, device=self.device)    # content, style, photo (unweighted)
-        self._out = torch.zeros(5, dtype=torch.float32, device=self.device)    # content, style, nima, photo, total
+        self._acc = torch.zeros(4, dtype=torch.float64, device=self.device)    # content, style, photo, tv (unweighted)
+        self._out = torch.zeros(6, dtype=torch.float32, device=self.device)    # content, style, nima, photo, total, tv
         self._layer_cache = {}      # style layer name -> dict(masks, K, A, ws, seed)
         self._content_seeds = {}
         self._photo_grad = None
@@ -166,6 +178,16 @@ class Loss:
             if self.matting_laplacian is None:
                 raise RuntimeError("regularization_weight > 0 but initialize_matting_laplacian() was not called")
             self._photo_grad = self.calculate_photorealism_regularization(image, _with_gradient=True)
+        if self.tv_weight > 0:                                                # extension: value -> _acc[3], gradient -> added
+            own = None if self.tile is None else self.tile.own_cols(int(image.shape[2]))
+            if self._photo_grad is None:
+                if self._tv_grad_buf is None or self._tv_grad_buf.shape != image.shape:
+                    self._tv_grad_buf = torch.empty_like(image)
+                kernels.tv_loss(image, 1.0, self.tv_weight, self._acc[3:4], self._tv_grad_buf, accumulate=False, own_cols=own)
+                self._photo_grad = self._tv_grad_buf
+            else:
+                kernels.tv_loss(image, 1.0, self.tv_weight, self._acc[3:4], self._photo_grad.reshape(image.shape),
+                                accumulate=True, own_cols=own)
         self._pending = (outputs, seeds)
         return partials + [self._acc]
 
@@ -187,12 +209,14 @@ class Loss:
                                          workspace=st["ws"], hw_norm=st["hw_norm"], f_absmax=kernels.act_absmax_slot(out),
                                          tiles=st["tiles"])
             seeds[name] = dF
-        kernels.loss_finalize(self._acc, wts['content'], wts['style'], wts['photo'], self._out)   # loss.py:72
+        kernels.loss_finalize(self._acc, wts['content'], wts['style'], wts['photo'], self._out, w_tv=self.tv_weight)   # loss.py:72
         self._seeds = seeds
         loss_dict = {self.loss_names['content']: self._out[0], self.loss_names['style']: self._out[1],
                      self.loss_names['nima']: self._out[2]}
         if wts['photo'] > 0:
             loss_dict[self.loss_names['photo']] = self._out[3]
+        if self.tv_weight > 0:
+            loss_dict[self.tv_name] = self._out[5]
         loss_dict['Total loss'] = self._out[4]                                # loss.py:76
         return loss_dict
 
@@ -245,6 +269,15 @@ class Loss:
         return y if y.dtype == torch.float32 else y.to(torch.float32)
 
     _photo_grad_buf = None
+    _tv_grad_buf = None
+    _nima_note_shown = False
+
+    @staticmethod
+    def calculate_total_variation(image):
+        """EXTENSION: tf.image.total_variation(image)[0] of a (1,H,W,3) float32 CUDA image."""
+        acc = torch.zeros(1, dtype=torch.float64, device=image.device)
+        kernels.tv_loss(image.contiguous(), 1.0, 0.0, acc, None)
+        return acc[0].to(image.dtype)
 
 
 def _plane(mask, device):

@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <atomic>
 #include <string>
 
 #include "adpst.h"
@@ -34,8 +35,22 @@ int fail(int code, const char* fmt, ...);
 
 static inline cudaStream_t as_stream(adpst_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }
 
-int num_sms();
+int num_sms();          // SM count of the CURRENT device (cached per device)
 void count_launch();
+
+// One-time per-DEVICE kernel set-up: cudaFuncSetAttribute(MaxDynamicSharedMemorySize) applies to the current device only,
+// and one process may drive several GPUs (the Python API takes device=).  `mask` is one static per kernel instantiation,
+// bit d = "done on device d"; the set-up itself is idempotent, so two racing threads are harmless.
+int current_device();
+#define ADPST_ONCE_PER_DEVICE(stmt)                                                           \
+    do {                                                                                      \
+        static std::atomic<unsigned long long> _done{0};                                      \
+        const unsigned long long _bit = 1ull << (::adpst::current_device() & 63);             \
+        if (!(_done.load(std::memory_order_acquire) & _bit)) {                                \
+            stmt;                                                                             \
+            _done.fetch_or(_bit, std::memory_order_release);                                  \
+        }                                                                                     \
+    } while (0)
 
 template <typename T>
 __device__ __forceinline__ T warp_sum(T v) {

@@ -107,12 +107,47 @@ axpby_kernel(float* __restrict__ out, const float* __restrict__ a, float alpha, 
         out[i] = alpha * a[i] + (b ? beta * b[i] : 0.0f);
 }
 
-__global__ void loss_finalize_kernel(const double* __restrict__ acc, double wc, double ws, double wp,
+__global__ void loss_finalize_kernel(const double* __restrict__ acc, double wc, double ws, double wp, double wtv,
                                      float* __restrict__ out) {
-    const double c = acc[0], s = acc[1], p = acc[2];
-    out[0] = float(c); out[1] = float(s); out[2] = 0.0f; out[3] = float(p);
-    // loss.py:72: the terms are float32 tensors when they are weighted and added
-    out[4] = float(wc) * float(c) + float(ws) * float(s) + (wp > 0.0 ? float(wp) * float(p) : 0.0f);
+    const double c = acc[0], s = acc[1], p = acc[2], tv = acc[3];
+    out[0] = float(c); out[1] = float(s); out[2] = 0.0f; out[3] = float(p); out[5] = float(tv);
+    // loss.py:72: the terms are float32 tensors when they are weighted and added, in insertion order
+    float total = float(wc) * float(c) + float(ws) * float(s) + (wp > 0.0 ? float(wp) * float(p) : 0.0f);
+    if (wtv > 0.0) total += float(wtv) * float(tv);      // extension term, after the reference's
+    out[4] = total;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Total variation (EXTENSION: not in the reference; semantics of tf.image.total_variation):
+//   TV(x) = sum |x[y+1,x,c] - x[y,x,c]| + sum |x[y,x+1,c] - x[y,x,c]|          (anisotropic L1, no normalisation)
+//   dTV/dx[y,x,c] = sgn(x[y,x]-x[y-1,x]) - sgn(x[y+1,x]-x[y,x]) + sgn(x[y,x]-x[y,x-1]) - sgn(x[y,x+1]-x[y,x]),  sgn(0) = 0
+// One pass: 12 B/px read (the four neighbours come from L1/L2), 12 B/px written (24 when accumulating into an existing
+// gradient buffer).  The value is reduced with warp shuffles, one float64 atomic per CTA.
+// Every element owns its "down" and "right" differences; the scalar counts the elements of columns [col_lo, col_hi).
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ float sgnf(float d) { return float(d > 0.f) - float(d < 0.f); }
+
+__global__ void __launch_bounds__(256)
+tv_kernel(const float* __restrict__ x, int H, int W, double loss_scale, float grad_scale, double* __restrict__ loss,
+          float* __restrict__ dX, int accumulate, int col_lo, int col_hi) {
+    __shared__ double red[32];
+    const int row = W * 3;
+    const size_t n = size_t(H) * row;
+    double acc = 0.0;
+    for (size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += size_t(gridDim.x) * blockDim.x) {
+        const int y = int(i / size_t(row)), e = int(i - size_t(y) * row), col = e / 3;
+        const float v = __ldg(x + i);
+        float g = 0.f;
+        double a = 0.0;
+        if (y > 0) g += sgnf(v - __ldg(x + i - row));
+        if (col > 0) g += sgnf(v - __ldg(x + i - 3));
+        if (y + 1 < H) { const float u = __ldg(x + i + row); g -= sgnf(u - v); a += fabs(double(u) - double(v)); }
+        if (col + 1 < W) { const float u = __ldg(x + i + 3); g -= sgnf(u - v); a += fabs(double(u) - double(v)); }
+        if (col >= col_lo && col < col_hi) acc += a;
+        if (dX) dX[i] = accumulate ? fmaf(grad_scale, g, dX[i]) : grad_scale * g;
+    }
+    acc = block_sum<double>(acc, red);
+    if (threadIdx.x == 0 && loss) atomicAdd(loss, acc * loss_scale);
 }
 
 }  // namespace adpst
@@ -157,11 +192,24 @@ int adpst_resize_bilinear(const float* src_dev, int Hs, int Ws, float* dst_dev, 
     return ADPST_OK;
 }
 
-int adpst_loss_finalize(const double* acc_dev, double w_content, double w_style, double w_photo, float* out_dev,
-                        adpst_stream_t stream) {
+int adpst_tv_loss(const float* x_dev, int H, int W, double loss_scale, double grad_scale, double* loss_dev, float* dX_dev,
+                  int accumulate, int col_lo, int col_hi, adpst_stream_t stream) {
+    using namespace adpst;
+    ADPST_REQUIRE(x_dev && H > 0 && W > 0, "tv_loss: NULL or empty image");
+    ADPST_REQUIRE(loss_dev || dX_dev, "tv_loss: nothing to compute (loss and dX NULL)");
+    if (col_lo == 0 && col_hi == 0) col_hi = W;
+    ADPST_REQUIRE(col_lo >= 0 && col_hi <= W && col_lo <= col_hi, "tv_loss: bad column window");
+    tv_kernel<<<grid_for(size_t(H) * W * 3, 256), 256, 0, as_stream(stream)>>>(x_dev, H, W, loss_scale, float(grad_scale),
+                                                                              loss_dev, dX_dev, accumulate, col_lo, col_hi);
+    ADPST_LAUNCH_CHECK();
+    return ADPST_OK;
+}
+
+int adpst_loss_finalize(const double* acc_dev, double w_content, double w_style, double w_photo, double w_tv,
+                        float* out_dev, adpst_stream_t stream) {
     using namespace adpst;
     ADPST_REQUIRE(acc_dev && out_dev, "loss_finalize: NULL argument");
-    loss_finalize_kernel<<<1, 1, 0, as_stream(stream)>>>(acc_dev, w_content, w_style, w_photo, out_dev);
+    loss_finalize_kernel<<<1, 1, 0, as_stream(stream)>>>(acc_dev, w_content, w_style, w_photo, w_tv, out_dev);
     ADPST_LAUNCH_CHECK();
     return ADPST_OK;
 }

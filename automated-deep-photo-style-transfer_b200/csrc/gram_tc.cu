@@ -349,11 +349,7 @@ static int launch_gram_tc_t(const CUtensorMap& tmF, const float* masks, const in
                             cudaStream_t st) {
     using Cfg = GramCfg<BN>;
     auto kern = gram_tc_kernel<BN>;
-    static bool configured = false;
-    if (!configured) {
-        ADPST_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
-        configured = true;
-    }
+    ADPST_ONCE_PER_DEVICE(ADPST_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES)));
     const int tiles = gram_tc_tiles(C);
     dim3 grid(tiles * (tiles + 1) / 2, K * splits);
     kern<<<grid, GM_THREADS, Cfg::SMEM_BYTES, st>>>(tmF, masks, patch_ids, patch_off, ws, H, W, C, splits, tiles,

@@ -877,11 +877,7 @@ static int launch_matvec(adpst_laplacian* h, const void* x, void* y, double y_sc
     const int qlo = h->q_col_hi > h->q_col_lo ? h->q_col_lo : 0, qhi = h->q_col_hi > h->q_col_lo ? h->q_col_hi : h->W;
     auto kern = lap_matvec_kernel<TIO, TC, R>;
     const size_t smem = T::template smem_bytes<TIO, TC>();
-    static bool configured = false;            // per instantiation
-    if (!configured) {
-        ADPST_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
-        configured = true;
-    }
+    ADPST_ONCE_PER_DEVICE(ADPST_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem))));
     dim3 grid((h->W + T::TW - 1) / T::TW, (h->H + T::TH - 1) / T::TH);
     kern<<<grid, T::THREADS, smem, st>>>(static_cast<const TIO*>(h->image), static_cast<const TIO*>(x),
                                           static_cast<TIO*>(y), xLx ? h->partials : nullptr, h->H, h->W, h->mode,

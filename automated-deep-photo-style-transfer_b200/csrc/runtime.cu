@@ -24,17 +24,20 @@ int fail(int code, const char* fmt, ...) {
 static std::atomic<unsigned long long> g_launches{0};
 void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 
+int current_device() {
+    int dev = 0;
+    return cudaGetDevice(&dev) == cudaSuccess ? dev : 0;
+}
+
 int num_sms() {
-    static int cached = 0;
-    if (cached == 0) {
-        int dev = 0, n = 0;
-        if (cudaGetDevice(&dev) == cudaSuccess &&
-            cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0)
-            cached = n;
-        else
-            return 148;
+    static std::atomic<int> cached[64];            // per device: a process may drive several (different) GPUs
+    const int dev = current_device() & 63;
+    int n = cached[dev].load(std::memory_order_relaxed);
+    if (n == 0) {
+        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) return 148;
+        cached[dev].store(n, std::memory_order_relaxed);
     }
-    return cached;
+    return n;
 }
 
 }  // namespace adpst

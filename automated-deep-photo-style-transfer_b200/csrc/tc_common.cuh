@@ -43,8 +43,15 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t by
     asm volatile("{ .reg .b64 st; mbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1; }" ::"r"(smem_u32(bar)), "r"(bytes)
                  : "memory");
 }
-// Bounded wait: a protocol bug traps (reported as a launch failure) instead of hanging the GPU.  The first poll is
-// outside the timed loop: on the MMA-issuing thread every cycle spent here is a cycle the tensor pipe may idle.
+// Wait on an mbarrier phase.  The first poll is outside the loop: on the MMA-issuing thread every cycle spent here is a
+// cycle the tensor pipe may idle.  After that the thread spins on try_wait (which itself suspends for a
+// hardware-bounded time) and, every 4096 polls, looks at the wall clock (%globaltimer, nanoseconds -- independent of SM
+// clock throttling, preemption and time-slicing): a wait that has made no progress for ADPST_MBAR_TIMEOUT_NS of REAL time
+// (default 30 s; a healthy stage takes microseconds) is a protocol bug and traps, which surfaces as a launch failure
+// instead of a hung GPU.  Build with -DADPST_MBAR_TIMEOUT_NS=0 to spin without any bound.
+#ifndef ADPST_MBAR_TIMEOUT_NS
+#define ADPST_MBAR_TIMEOUT_NS 30000000000ULL
+#endif
 __device__ __forceinline__ bool mbar_try_wait(uint32_t addr, uint32_t parity) {
     uint32_t done;
     asm volatile(
@@ -54,13 +61,27 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t addr, uint32_t parity) {
         : "memory");
     return done != 0;
 }
+__device__ __forceinline__ unsigned long long global_timer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     const uint32_t addr = smem_u32(bar);
     if (mbar_try_wait(addr, parity)) return;
-    const long long t0 = clock64();
-    while (!mbar_try_wait(addr, parity)) {
-        if (clock64() - t0 > 4000000000LL) __trap();
+#if ADPST_MBAR_TIMEOUT_NS > 0
+    unsigned long long t0 = 0;
+    for (uint32_t polls = 1;; ++polls) {
+        if (mbar_try_wait(addr, parity)) return;
+        if ((polls & 4095u) == 0) {
+            const unsigned long long now = global_timer_ns();
+            if (t0 == 0) t0 = now;
+            else if (now - t0 > ADPST_MBAR_TIMEOUT_NS) __trap();
+        }
     }
+#else
+    while (!mbar_try_wait(addr, parity)) {}
+#endif
 }
 
 // ---- fences -----------------------------------------------------------------------------------------------------

@@ -622,11 +622,7 @@ int adpst_vgg_backward(adpst_vgg* h, int H, int W, const float* const* acts_dev,
             ADPST_LAUNCH_CHECK();
         }
     }
-    static bool ig_configured = false;
-    if (!ig_configured) {
-        ADPST_CUDA_CHECK(cudaFuncSetAttribute(conv1_dgrad_image_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, IG_SMEM));
-        ig_configured = true;
-    }
+    ADPST_ONCE_PER_DEVICE(ADPST_CUDA_CHECK(cudaFuncSetAttribute(conv1_dgrad_image_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, IG_SMEM)));
     dim3 grid((W + IG_TW - 1) / IG_TW, (H + IG_TH - 1) / IG_TH);
     conv1_dgrad_image_kernel<<<grid, IG_THREADS, IG_SMEM, st>>>(cur, h->wg0, dimage_dev, H, W);
     ADPST_LAUNCH_CHECK();

@@ -1,11 +1,26 @@
 """Thin, typed Python wrappers over the C-ABI entry points that are not tied to a handle.
 Every function launches hand-written CUDA from libadpst.so on torch's current stream; none has a fallback."""
 import ctypes
+import functools
 import os
 
 import torch
 
 from . import _lib
+
+
+def _on_tensor_device(fn):
+    """Run `fn` with the device of its first CUDA tensor argument current: the launch then goes to THAT device's current
+    stream (an object built with device='cuda:N' may be driven while another device is current)."""
+    @functools.wraps(fn)
+    def wrapper(*args, **kw):
+        for a in list(args) + list(kw.values()):
+            t = a.m if isinstance(a, AdamState) else a
+            if isinstance(t, torch.Tensor) and t.is_cuda:
+                with torch.cuda.device(t.device):
+                    return fn(*args, **kw)
+        return fn(*args, **kw)
+    return wrapper
 
 
 def _f32(t, name):
@@ -27,6 +42,7 @@ class AdamState:
         return int(self.state[0])
 
 
+@_on_tensor_device
 def adam_clip_step(x, grad, st, lr=0.1, beta1=0.9, beta2=0.999, epsilon=1e-8):
     """In place: TF-flavour Adam update of x followed by clip to [0,1] (style_transfer.py:342-343)."""
     _f32(x, "x"); _f32(grad, "grad")
@@ -37,6 +53,7 @@ def adam_clip_step(x, grad, st, lr=0.1, beta1=0.9, beta2=0.999, epsilon=1e-8):
     return x
 
 
+@_on_tensor_device
 def resize_bilinear(mask_hw, size):
     """tf.image.resize(mask, size) for one (H,W) float32 plane (loss.py:112-113)."""
     _f32(mask_hw, "mask")
@@ -47,6 +64,7 @@ def resize_bilinear(mask_hw, size):
     return out
 
 
+@_on_tensor_device
 def content_layer(target, output, loss_scale, grad_scale, loss_acc, d_out=None, accumulate=False, n_norm=0.0, own_cols=None):
     """loss_acc (float64[1]) += loss_scale*mean((t-o)^2); d_out (=|+=) grad_scale*2(o-t)/n  (loss.py:90-92).
     Spatially tiled runs: n_norm = element count of the whole layer, own_cols = (lo, hi) columns of this (1,h,w,C) tile
@@ -61,6 +79,7 @@ def content_layer(target, output, loss_scale, grad_scale, loss_acc, d_out=None, 
                                               _lib.stream_ptr()))
 
 
+@_on_tensor_device
 def axpby(out, a, alpha, b=None, beta=0.0):
     _f32(out, "out"); _f32(a, "a")
     _lib.check(_lib.lib().adpst_axpby(_lib.ptr(out), _lib.ptr(a), float(alpha), _lib.ptr(b), float(beta), out.numel(),
@@ -95,6 +114,7 @@ def gram_patch_lists(masks, h, w, K, device):
     return ids, off
 
 
+@_on_tensor_device
 def absmax_slot(t):
     """A 1-element int32 tensor holding the float32 bit pattern of max|t| (the scale slot the tensor-core kernels read)."""
     slot = torch.zeros(1, dtype=torch.int32, device=t.device)
@@ -107,6 +127,7 @@ def absmax_slot(t):
 _DEFAULT_PATH = "simt" if os.environ.get("ADPST_LOSS_PATH", "").lower() == "simt" else "tensor"
 
 
+@_on_tensor_device
 def gram_masked(F, masks, K, workspace=None, patches=None, path=None, out=None, f_absmax=None, masks_absmax=None):
     """F: (h,w,C) float32 feature map ((HW,C) is taken as h = HW, w = 1); masks: (K,h*w) float32 or None.
     Returns (K,C,C) float32  (loss.py:96-102).  `patches` = gram_patch_lists(...) enables the tcgen05 kernel."""
@@ -148,10 +169,12 @@ def style_tiles(masks, K, h, w, device):
     if K > 32:
         return None                      # the tensor-core style gradient handles at most 32 classes per launch
     out = torch.empty(int(_lib.lib().adpst_style_tiles_bytes(h * w)), dtype=torch.uint8, device=device)
-    _lib.check(_lib.lib().adpst_style_tiles(_lib.ptr(masks), K, h, w, _lib.ptr(out), _lib.stream_ptr()))
+    with torch.cuda.device(out.device):
+        _lib.check(_lib.lib().adpst_style_tiles(_lib.ptr(masks), K, h, w, _lib.ptr(out), _lib.stream_ptr()))
     return out
 
 
+@_on_tensor_device
 def style_layer_backward(F, masks, K, G, A, loss_scale, grad_scale, loss_acc, dF, accumulate=False, workspace=None,
                          path=None, hw_norm=0.0, f_absmax=None, tiles=None):
     """One layer of loss.py:104-137: accumulates the loss value and writes/adds its gradient w.r.t. F.
@@ -170,8 +193,29 @@ def style_layer_backward(F, masks, K, G, A, loss_scale, grad_scale, loss_acc, dF
                                                      _lib.stream_ptr()))
 
 
-def loss_finalize(acc, w_content, w_style, w_photo, out):
-    """acc: float64[3] {content, style, photo}; out: float32[5] {content, style, nima, photo, total}  (loss.py:72-76)."""
-    _lib.check(_lib.lib().adpst_loss_finalize(_lib.ptr(acc), float(w_content), float(w_style), float(w_photo),
+@_on_tensor_device
+def loss_finalize(acc, w_content, w_style, w_photo, out, w_tv=0.0):
+    """acc: float64[4] {content, style, photo, tv}; out: float32[6] {content, style, nima, photo, total, tv}  (loss.py:72-76;
+    the tv term is an extension and enters the total only if w_tv > 0)."""
+    if acc.numel() < 4 or out.numel() < 6:
+        raise ValueError("loss_finalize: acc needs 4 float64 entries and out 6 float32 entries")
+    _lib.check(_lib.lib().adpst_loss_finalize(_lib.ptr(acc), float(w_content), float(w_style), float(w_photo), float(w_tv),
                                               _lib.ptr(out), _lib.stream_ptr()))
     return out
+
+
+@_on_tensor_device
+def tv_loss(image, loss_scale, grad_scale, loss_acc, d_image=None, accumulate=False, own_cols=None):
+    """EXTENSION (not in the reference): tf.image.total_variation of a (1,H,W,3) float32 image.
+    loss_acc (float64[1], may be None) += loss_scale * TV;  d_image (=|+=) grad_scale * dTV/dx."""
+    _f32(image, "image")
+    if image.dim() != 4 or image.shape[0] != 1 or image.shape[3] != 3:
+        raise ValueError("expected an image of shape (1, H, W, 3), got %s" % (tuple(image.shape),))
+    if d_image is not None:
+        _f32(d_image, "d_image")
+        if d_image.numel() != image.numel():
+            raise ValueError("d_image and image differ in size")
+    lo, hi = (0, 0) if own_cols is None else (int(own_cols[0]), int(own_cols[1]))
+    _lib.check(_lib.lib().adpst_tv_loss(_lib.ptr(image), int(image.shape[1]), int(image.shape[2]), float(loss_scale),
+                                        float(grad_scale), _lib.ptr(loss_acc), _lib.ptr(d_image), int(bool(accumulate)),
+                                        lo, hi, _lib.stream_ptr()))

@@ -180,10 +180,19 @@ int adpst_content_layer(const float* target_dev, const float* output_dev, size_t
                         double grad_scale, double* loss_dev, float* dOut_dev, int accumulate, double n_norm, int w, int C,
                         int col_lo, int col_hi, adpst_stream_t stream);
 
-/* loss.py:72-76: acc_dev = float64 {content, style, photo} (unweighted);  out_dev = float32
- * {content, style, nima (0), photo, total = sum w_i * loss_i}.  One tiny launch, keeps the step graph-replayable. */
-int adpst_loss_finalize(const double* acc_dev, double w_content, double w_style, double w_photo, float* out_dev,
-                        adpst_stream_t stream);
+/* EXTENSION -- no counterpart in the reference (it has no total-variation term; BASELINE.json's north star and
+ * configs[1] name one).  Semantics of tf.image.total_variation on the (H,W,3) image:
+ *   TV = sum |x[y+1,x,c]-x[y,x,c]| + sum |x[y,x+1,c]-x[y,x,c]|;   *loss_dev += loss_scale * TV  (float64, may be NULL);
+ *   dX (=|+=) grad_scale * dTV/dx  (sign differences, sgn(0) = 0; may be NULL).
+ * Spatially tiled runs: the scalar counts only columns [col_lo, col_hi) of the local strip; (0,0) = all. */
+int adpst_tv_loss(const float* x_dev, int H, int W, double loss_scale, double grad_scale, double* loss_dev, float* dX_dev,
+                  int accumulate, int col_lo, int col_hi, adpst_stream_t stream);
+
+/* loss.py:72-76: acc_dev = float64 {content, style, photo, tv} (unweighted);  out_dev = float32[6]
+ * {content, style, nima (0), photo, total = sum w_i * loss_i, tv}; the tv term (extension) enters the total only if
+ * w_tv > 0.  One tiny launch, keeps the step graph-replayable. */
+int adpst_loss_finalize(const double* acc_dev, double w_content, double w_style, double w_photo, double w_tv,
+                        float* out_dev, adpst_stream_t stream);
 
 /* out[i] = alpha * a[i] + beta * b[i] (float32; b may be NULL).  Used to combine image gradients. */
 int adpst_axpby(float* out_dev, const float* a_dev, float alpha, const float* b_dev, float beta, size_t n,

@@ -163,11 +163,22 @@ def photorealism(image_nhwc, lap):
 
 LOSS_NAMES = {"content": "Content loss", "style": "Style loss", "nima": "NIMA loss",
               "photo": "Photorealism regualarization"}            # loss.py:16-21 (typo is the reference's)
+TV_NAME = "Total variation loss"                                   # extension, see total_variation()
+
+
+def total_variation(image_nhwc):
+    """EXTENSION -- NOT IN THE REFERENCE (no TV term anywhere in /root/reference; BASELINE.json's north star
+    and configs[1] name one).  Parity unpinned by construction.  Definition = tf.image.total_variation(image)[0]:
+    anisotropic L1, sum |x[:,1:,:,:]-x[:,:-1,:,:]| + sum |x[:,:,1:,:]-x[:,:,:-1,:]|, no normalisation; autograd gives
+    sign() with sign(0) = 0, as tf.abs does."""
+    x = image_nhwc
+    return (x[:, 1:] - x[:, :-1]).abs().sum() + (x[:, :, 1:] - x[:, :, :-1]).abs().sum()
 
 
 def compute_loss(image, outputs, content_target, style_target, weights_cfg, lap=None,
-                 content_masks=None, style_masks=None):
-    """loss.py:53-78 with the NIMA term dropped (out of scope, weight must be 0)."""
+                 content_masks=None, style_masks=None, tv_weight=0.0):
+    """loss.py:53-78 with the NIMA term dropped (out of scope, weight must be 0).
+    tv_weight > 0 (extension, default off): adds TV_NAME after the reference's terms and tv_weight * TV to the total."""
     vals = {}
     vals["content"] = iter_on_layers(layer_content_loss, content_target, outputs["content"])
     vals["style"] = iter_on_layers(layer_style_loss, style_target, outputs["style"],
@@ -177,6 +188,9 @@ def compute_loss(image, outputs, content_target, style_target, weights_cfg, lap=
         vals["photo"] = photorealism(image, lap)
     total = sum(weights_cfg[k] * v for k, v in vals.items())
     d = {LOSS_NAMES[k]: v for k, v in vals.items()}
+    if tv_weight > 0:
+        d[TV_NAME] = total_variation(image)
+        total = total + tv_weight * d[TV_NAME]
     d["Total loss"] = total
     return d
 
@@ -218,15 +232,21 @@ class TrainState:
         self.v = torch.zeros_like(self.image)
         self.t = 0
 
-    def loss_and_grad(self, image=None):
+    def loss_and_grad(self, image=None, return_acts=False):
+        """Loss dict and d(Total loss)/d(image) at `image` (default: the current iterate).  return_acts: also the list of
+        all 13 conv outputs of this forward pass (detached), for ReLU-decision comparisons (oracle/parity.py)."""
         img = (self.image if image is None else image).clone().requires_grad_(True)
-        outs = extractor(img, self.weights, self.dtype)
+        acts = vgg_forward(img, self.weights, self.dtype)
+        outs = {"content": {n: acts[n] for n in CONTENT_LAYERS}, "style": {n: acts[n] for n in STYLE_LAYERS}}
         cm = None if self.cm is None else [m.to(self.dtype) for m in self.cm]
         sm = None if self.sm is None else [m.to(self.dtype) for m in self.sm]
         d = compute_loss(img, outs, self.content_target, self.style_target, self.cfg["weights"],
-                         self.lap, cm, sm)
+                         self.lap, cm, sm, tv_weight=self.cfg["weights"].get("tv", 0.0))
         (g,) = torch.autograd.grad(d["Total loss"], img)
-        return {k: float(v.detach()) for k, v in d.items()}, g
+        d = {k: float(v.detach()) for k, v in d.items()}
+        if return_acts:
+            return d, g, [acts[item[0]].detach() for item in VGG_TOPOLOGY if item != "P"]
+        return d, g
 
     def train_step(self):
         d, g = self.loss_and_grad()

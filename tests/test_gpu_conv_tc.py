@@ -71,3 +71,37 @@ def test_forward_is_unbiased_against_float64(i, ext, synth):
     assert float((y - ref).abs().max()) / sc < 5e-6
     big = ref > 0.1 * sc
     assert abs(float(((y - ref) / ref)[big].mean())) < 1e-6      # was -2.7e-5 at K = 4608 without promotion
+
+
+@pytest.mark.parametrize("i,h,w", [(1, 160, 256), (2, 128, 160), (3, 128, 160), (5, 96, 128), (9, 64, 96)])
+def test_dgrad_against_float64_many_items_per_cta(i, h, w, ext, synth):
+    """Data gradient of conv i against an independent float64 reference (torch conv_transpose2d on the CPU oracle side) at
+    sizes where every CTA of the persistent kernel walks SEVERAL work items (ring slots / barrier phases carried over):
+    160x256 / Cin 64: 320 items; 128x160 / Cin 64 (Cout 128): 160; / Cin 128: 160; 96x128 / 256: 192; 64x96 / 512: 192."""
+    import torch.nn.functional as F
+    cin, cout = synth.CONV_LAYERS[i][1], synth.CONV_LAYERS[i][2]
+    g = torch.Generator(device="cuda").manual_seed(31 * i + h)
+    d = torch.randn(h, w, cout, device="cuda", generator=g).contiguous()
+    k, _ = synth.vgg_weights(seed=7)[synth.CONV_LAYERS[i][0]]
+    wt = torch.as_tensor(k).double().cuda().permute(3, 2, 0, 1)                    # OIHW
+    ref = F.conv_transpose2d(d.double().permute(2, 0, 1)[None], wt, padding=1)[0].permute(1, 2, 0)
+    y = _run(ext, "adpst_vgg_conv_dgrad", i, d, h, w, cin, 0).double()
+    assert torch.isfinite(y).all()
+    sc = float(ref.abs().max())
+    assert float((y - ref).abs().max()) / sc < 5e-6
+    big = ref.abs() > 0.1 * sc
+    assert abs(float(((y - ref) / ref)[big].mean())) < 1e-6                       # no accumulation bias
+
+
+@pytest.mark.parametrize("i,h,w", [(1, 160, 256), (3, 128, 160), (6, 96, 128), (10, 64, 96)])
+def test_forward_against_float64_many_items_per_cta(i, h, w, ext, synth):
+    import torch.nn.functional as F
+    cin, cout = synth.CONV_LAYERS[i][1], synth.CONV_LAYERS[i][2]
+    g = torch.Generator(device="cuda").manual_seed(17 * i + w)
+    x = (torch.rand(h, w, cin, device="cuda", generator=g) * 200.0).contiguous()
+    k, b = synth.vgg_weights(seed=7)[synth.CONV_LAYERS[i][0]]
+    ref = F.relu(F.conv2d(x.double().permute(2, 0, 1)[None], torch.as_tensor(k).double().cuda().permute(3, 2, 0, 1),
+                          torch.as_tensor(b).double().cuda(), padding=1))[0].permute(1, 2, 0)
+    y = _run(ext, "adpst_vgg_conv_forward", i, x, h, w, cout, 0).double()
+    sc = float(ref.abs().max())
+    assert float((y - ref).abs().max()) / sc < 5e-6

@@ -65,3 +65,33 @@ def test_content_layer_value_and_gradient():
     k.content_layer(torch.as_tensor(t).cuda(), torch.as_tensor(o).cuda(), 0.5, 0.5, acc, d, accumulate=True)
     assert np.abs(d.cpu().numpy() - 2 * g.numpy()).max() < 2e-6 * np.abs(g.numpy()).max()
     assert abs(float(acc) - 2 * float(loss.detach())) < 1e-9 * float(loss.detach())
+
+
+@pytest.mark.parametrize("H,W", [(1, 1), (1, 7), (5, 1), (37, 50), (64, 64), (130, 257)])
+def test_total_variation_extension(H, W):
+    """EXTENSION (not in the reference): value and gradient of tf.image.total_variation against the torch-CPU float64
+    oracle, on an image quantised to k/8 so that many differences are exactly zero (sgn(0) = 0)."""
+    from oracle import model
+    k = importlib.import_module(PKG_NAME + ".kernels")
+    rng = np.random.default_rng(H * 1000 + W)
+    img = (np.round(rng.random((1, H, W, 3)) * 8) / 8).astype(np.float32)
+    x = torch.as_tensor(img).cuda()
+    acc = torch.zeros(1, dtype=torch.float64, device="cuda")
+    g = torch.full_like(x, float("nan"))
+    k.tv_loss(x, 0.5, 3.0, acc, g)
+    xo = torch.as_tensor(img, dtype=torch.float64).requires_grad_(True)
+    tv = model.total_variation(xo)
+    (go,) = torch.autograd.grad(3.0 * tv, xo) if H * W > 1 else (torch.zeros_like(xo),)
+    assert abs(float(acc) - 0.5 * float(tv)) <= 1e-12 * max(float(tv), 1.0)
+    assert torch.equal(g.cpu().double(), go)                       # sums of +-3: exact
+    g2 = g.clone()
+    k.tv_loss(x, 0.5, 3.0, None, g2, accumulate=True)
+    assert torch.equal(g2.cpu().double(), 2 * go)
+    # scalar restricted to a column window (spatially tiled runs): the windows partition the sum
+    if W >= 4:
+        parts = []
+        for lo, hi in ((0, W // 2), (W // 2, W)):
+            a = torch.zeros(1, dtype=torch.float64, device="cuda")
+            k.tv_loss(x, 1.0, 0.0, a, None, own_cols=(lo, hi))
+            parts.append(float(a))
+        assert abs(sum(parts) - float(tv)) <= 1e-12 * max(float(tv), 1.0)

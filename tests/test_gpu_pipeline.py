@@ -14,6 +14,7 @@ import torch
 from conftest import PKG_NAME
 from oracle import masks as omasks
 from oracle import model
+from oracle import parity
 
 pytestmark = pytest.mark.gpu
 TOL = 1e-5
@@ -29,23 +30,12 @@ def _rel(a, b):
 
 
 def _assert_gradient_close(g, go, ext, x, weights, synth):
-    """Max-norm 1e-5 -- unless a ReLU decision differs between the float32 GPU forward pass and the float64 oracle.
-    A pre-activation within rounding distance of zero flips its mask; that is a discrete, measure-zero event of ANY
-    float32 implementation (it changes the gradient inside one receptive field by O(1e-3)), so it is detected
-    explicitly and the comparison is then made on the bulk of the pixels."""
-    g, go = np.asarray(g, np.float64), np.asarray(go, np.float64)
-    scale = np.abs(go).max()
-    rel = np.abs(g - go).max() / scale
-    if rel < TOL:
-        return
+    """Max-norm 1e-5 everywhere outside the receptive fields of ReLU units whose decision differs between the float32 GPU
+    forward pass and the float64 oracle (oracle/parity.py): a pre-activation within rounding distance of zero flips its
+    mask in ANY float32 implementation and changes the gradient inside that one unit's receptive field only."""
     ref = model.vgg_forward(x.cpu().double(), weights)
-    flips = 0
-    for i, (name, _, _) in enumerate(synth.CONV_LAYERS):
-        if ext.last.acts[i] is not None:
-            flips += int(((ext.last.acts[i].cpu() > 0) != (ref[name] > 0)).sum())
-    assert flips > 0, "gradient off by %.2e with identical ReLU masks" % rel
-    d = np.abs(g - go).max(-1)
-    assert rel < 2e-2 and np.median(d) < 0.1 * TOL * scale and (d > TOL * scale).mean() < 0.5, (rel, flips)
+    ref_acts = [ref[name] for name, _, _ in synth.CONV_LAYERS]
+    return parity.assert_gradient_close(g, go, ext.last.acts, ref_acts, TOL)
 
 
 def _args(**kw):
@@ -57,7 +47,8 @@ def _args(**kw):
 
 
 def _cfg(a):
-    return {"weights": {"content": a.content_weight, "style": a.style_weight, "nima": 0.0, "photo": a.regularization_weight},
+    return {"weights": {"content": a.content_weight, "style": a.style_weight, "nima": 0.0, "photo": a.regularization_weight,
+                        "tv": getattr(a, "tv_weight", 0.0)},
             "matting_epsilon": a.matting_epsilon, "matting_window_radius": a.matting_window_radius,
             "adam": {"lr": a.adam_lr, "beta1": a.adam_beta1, "beta2": a.adam_beta2, "epsilon": a.adam_epsilon}}
 
@@ -234,6 +225,23 @@ def test_total_loss_and_image_gradient(H, W, K, photo, weights, synth):
     g = loss.gradient(ext)
     do, go = ora.loss_and_grad(x.cpu().double())
     assert set(d) == set(do) or (photo == 0 and set(d) == set(do) - {"Photorealism regualarization"}) or set(d) == set(do)
+    for name, v in d.items():
+        assert abs(float(v) - do[name]) <= TOL * abs(do[name]) + 1e-12, name
+    _assert_gradient_close(g.cpu().numpy(), go.numpy(), ext, x, weights, synth)
+
+
+@pytest.mark.parametrize("H,W,K,photo,tv", [(64, 64, 3, 1e4, 5.0), (37, 50, 0, 0.0, 2.0)])
+def test_tv_extension_total_and_gradient(H, W, K, photo, tv, weights, synth):
+    """tv_weight > 0 (extension, tf.image.total_variation semantics): extra dictionary key before 'Total loss', total and
+    gradient include the term; with tv_weight = 0 the dictionary is the reference's (checked by every other test)."""
+    args = _args(regularization_weight=photo, tv_weight=tv)
+    ext, loss, ora, c_dev = _setup(H, W, K, weights, synth, args)
+    pert = np.sign(synth.image(H, W, 3) - 0.5).astype(np.float32) * 0.1
+    x = torch.clamp(c_dev + torch.as_tensor(pert).cuda(), 0, 1).contiguous()
+    d = loss(x, ext(x, reuse=True))
+    g = loss.gradient(ext)
+    do, go = ora.loss_and_grad(x.cpu().double())
+    assert list(d) == list(do) and list(d)[-2:] == ["Total variation loss", "Total loss"]
     for name, v in d.items():
         assert abs(float(v) - do[name]) <= TOL * abs(do[name]) + 1e-12, name
     _assert_gradient_close(g.cpu().numpy(), go.numpy(), ext, x, weights, synth)
