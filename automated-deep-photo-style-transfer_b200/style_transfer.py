@@ -8,10 +8,15 @@ The reference inlines everything in `if __name__ == "__main__"`.  He
     step      = make_train_step(extractor, loss, opt)                               # :331-344
     for i in range(iters): loss_dict = step(transfer_image)                         # :353-367
 `style_transfer(...)` wraps exactly that and returns the best image like the reference's loop (:366-367).
-The flags of the reference's argparse block (:126-205) are reproduced by `build_parser()`.
+The flags of the reference's argparse block (:126-205) are reproduced by `build_parser()` and `main()` follows the script
+(:207-384): meta.json (:97-120), *_seg.png mask files (:223-264), best-image tracking (:366-367), loss printing (:360-364),
+per-iteration scalars and intermediate images (the reference's TensorBoard summaries, :372-381, as files).
 """
 import argparse
+import json
+import os
 import time
+from pathlib import Path
 
 import torch
 
@@ -121,60 +126,213 @@ def style_transfer(content_image, style_image, args, content_masks=None, style_m
 
 
 def tensor_to_image(tensor):
-    """style_transfer.py:69-79: uint8(255*x) by truncation, batch dimension dropped.  Returns a (H,W,3) uint8 tensor."""
+    """style_transfer.py:69-79: uint8(255*x) by truncation (tf.cast float -> uint8), batch dimension squeezed.
+    Returns a (H,W,3) uint8 tensor (the reference PNG-encodes it; `save_image` below does that on the host)."""
     return (255 * tensor).to(torch.uint8).squeeze(0)
 
 
+def load_image(filename, dtype="float32"):
+    """style_transfer.py:50-59: decode a JPEG/PNG to RGB, convert_image_dtype (uint8 -> float: multiply by 1/255 in the
+    target type), add the batch dimension.  Returns a (1,H,W,3) numpy array.  (cv2/libjpeg-turbo stands in for TensorFlow's
+    decoder, which is not installable here: decoded JPEG pixels may differ by +-1 between decoders.)"""
+    import cv2
+    import numpy as np
+    bgr = cv2.imread(str(filename), cv2.IMREAD_COLOR)
+    if bgr is None:
+        raise FileNotFoundError("Image file {} does not exist.".format(filename))
+    dt = np.dtype(dtype)
+    return (bgr[:, :, ::-1].astype(dt) * dt.type(1.0 / 255.0))[None]
+
+
+def save_image(image_u8, file):
+    """style_transfer.py:61-62 (+ encode_png of :79): write a (H,W,3) uint8 RGB tensor/array; the extension selects the codec."""
+    import cv2
+    import numpy as np
+    arr = image_u8.cpu().numpy() if isinstance(image_u8, torch.Tensor) else np.asarray(image_u8)
+    if not cv2.imwrite(str(file), np.ascontiguousarray(arr[:, :, ::-1])):
+        raise OSError("could not write %s" % file)
+
+
+def change_filename(dir_name, filename, suffix, extension=None):
+    r"""style_transfer.py:82-94.  change_filename('.', 'image.png', '_seg') -> ./image_seg.png"""
+    path, ext = os.path.splitext(filename)
+    if extension is None:
+        extension = ext
+    return os.path.join(dir_name, path + suffix + extension)
+
+
+def write_metadata(args, load_segmentation, experiment_path):
+    """style_transfer.py:97-120: the same keys, in the same order, into <experiment_path>/meta.json."""
+    meta = {
+        "init": args.init,
+        "iter": args.iter,
+        "content": args.content_image,
+        "style": args.style_image,
+        "content_weight": args.content_weight,
+        "style_weight": args.style_weight,
+        "regularization_weight": args.regularization_weight,
+        "nima_weight": args.nima_weight,
+        "semantic_thresh": args.semantic_thresh,
+        "similarity_metric": args.similarity_metric,
+        "load_segmentation": load_segmentation,
+        "adam": {
+            "learning_rate": args.adam_lr,
+            "beta1": args.adam_beta1,
+            "beta2": args.adam_beta2,
+            "epsilon": args.adam_epsilon
+        }
+    }
+    file = Path(experiment_path) / 'meta.json'
+    with file.open('w+') as f:
+        f.write(json.dumps(meta, indent=4))
+    return meta
+
+
 def build_parser():
-    """The hyper-parameter / experiment flags of style_transfer.py:126-205 with the reference's defaults."""
-    p = argparse.ArgumentParser(description="B200 hot path of automated deep photo style transfer")
-    p.add_argument('-c', '--content_image', type=str, default='blanc.jpg')
-    p.add_argument('-s', '--style_image', type=str, default='bear.jpeg')
-    p.add_argument('-o', '--output_image', type=str, default=None)
-    p.add_argument('--dtype', type=str, default='float32')
-    p.add_argument('--init', type=str, default='content', choices=['noise', 'content', 'style'])
-    p.add_argument('--iter', type=int, default=1000)
-    p.add_argument('--content_weight', type=float, default=1)
-    p.add_argument('--style_weight', type=float, default=100)
-    p.add_argument('--regularization_weight', type=float, default=10 ** 4)
-    p.add_argument('--nima_weight', type=float, default=0, help="reference default 1e5; NIMA is out of scope, must be 0")
-    p.add_argument('--adam_lr', type=float, default=0.1)
-    p.add_argument('--adam_beta1', type=float, default=0.9)
-    p.add_argument('--adam_beta2', type=float, default=0.999)
-    p.add_argument('--adam_epsilon', type=float, default=1e-08)
-    p.add_argument('--matting_epsilon', type=float, default=1e-5)
-    p.add_argument('--matting_window_radius', type=int, default=3)
-    p.add_argument('--print_loss_interval', type=int, default=1)
-    p.add_argument('--vgg_weights', type=str, default=None, help=".npz with '<layer>/kernel' and '<layer>/bias'")
-    p.add_argument('--matting', type=str, default='v2', choices=['v2', 'v3'])
-    return p
+    """The argument groups and flags of style_transfer.py:126-205 with the reference's defaults, except
+    --nima_weight (reference default 1e5: the NIMA term is outside this hot path, so the default is 0 and any other value is
+    refused with an explanation).  Flags after the 'Extensions' header do not exist in the reference."""
+    parser = argparse.ArgumentParser(description="B200 hot path of automated deep photo style transfer")
+    base = parser.add_argument_group('Base options')
+    expr = parser.add_argument_group('Experiment parameters')
+    param = parser.add_argument_group('Hyperparameters')
+    dirs = parser.add_argument_group('Storage directories')
+    misc = parser.add_argument_group('Miscellaneous')
+    ext = parser.add_argument_group('Extensions (not in the reference)')
+
+    base.add_argument("-c", "--content_image", type=str, help="Content image path", default="blanc.jpg")
+    base.add_argument("-s", "--style_image", type=str, help="Style image path", default="bear.jpeg")
+    base.add_argument("-o", "--output_image", type=str, help="Output image path, default: result.jpg", default="result.jpg")
+
+    expr.add_argument("--dtype", type=str, help="dtype of the input and output images., default: float32", default="float32")
+    expr.add_argument("--init", type=str, help="Initialization image., default: content",
+                      choices=["noise", "content", "style"], default="content")
+    expr.add_argument("--iter", type=int, help="Number of iterations", default=1000)
+    expr.add_argument("--similarity_metric", type=str, help="Semantic similarity metric for label grouping., default: li",
+                      choices=["li", "wpath", "jcn", "lin", "wup", "res"], default="li")
+
+    param.add_argument("--content_weight", type=float, help="Weight of the content loss., default: 1", default=1)
+    param.add_argument("--style_weight", type=float, help="Weight of the style loss., default: 100", default=1e2)
+    param.add_argument("--regularization_weight", type=float, help="Weight of the photorealism regularization.", default=1e4)
+    param.add_argument("--nima_weight", type=float, default=0,
+                       help="Weight for nima loss. Reference default 1e5; the NIMA term is not built here: must be 0")
+    param.add_argument("--adam_lr", type=float, help="Learning rate for the adam optimizer.", default=1e-1)
+    param.add_argument("--adam_beta1", type=float, help="Beta1 for the adam optimizer., default: 0.9", default=0.9)
+    param.add_argument("--adam_beta2", type=float, help="Beta2 for the adam optimizer., default: 0.999", default=0.999)
+    param.add_argument("--adam_epsilon", type=float, help="Epsilon for the adam optimizer., default: 1e-08", default=1e-08)
+    param.add_argument("--matting_epsilon", type=float, help="Epsilon regularization for matting laplacian computing.",
+                       default=1e-5)
+    param.add_argument("--matting_window_radius", type=int, help="Size of the windows considered by matting laplacian.",
+                       default=3)
+    param.add_argument("--semantic_thresh", type=float, help="Semantic threshold for label grouping., default: 0.5", default=0.5)
+
+    dirs.add_argument("--logs_dir", type=Path, help="Path to the per-iteration logs., default: ./logs", default=Path('logs'))
+    dirs.add_argument("--results_dir", type=Path, help='Where results are stored., default: ./experiments',
+                      default=Path('experiments'))
+    dirs.add_argument("--seg_dir", type=Path, help='Where segmented images are stored., default: ./raw_seg',
+                      default=Path('raw_seg'))
+
+    misc.add_argument("--gpu", type=str, help="Comma separated list of GPU(s) to use.", default="0")
+    misc.add_argument("--experiment_name", type=str, help="Name of the experiment., default: <timestamp>", default=None)
+    misc.add_argument("--intermediate_result_interval", type=int,
+                      help="Interval of iterations until a intermediate result is saved.", default=20)
+    misc.add_argument("--print_loss_interval", type=int,
+                      help="Interval of iterations until the current loss is printed to console.", default=10)
+
+    ext.add_argument('--vgg_weights', type=str, default=None,
+                     help=".npz with '<layer>/kernel' (3,3,Cin,Cout) and '<layer>/bias' (Keras downloads ImageNet weights, "
+                          "VGG19/model.py:7; offline they must be supplied, see also ADPST_VGG19_WEIGHTS)")
+    ext.add_argument('--matting', type=str, default='v2', choices=['v2', 'v3'],
+                     help="Laplacian variant (the reference hard-wires v2, loss.py:4)")
+    ext.add_argument('--use_masks', action='store_true',
+                     help="pass the segmentation masks to Loss (commented out in the reference script, :308-309)")
+    ext.add_argument('--tv_weight', type=float, default=0.0, help="total-variation weight (no such term in the reference)")
+    return parser
 
 
 def main(argv=None):
+    """python -m ... .style_transfer [flags]: the reference script, :207-384, on the B200 hot path."""
     import cv2
     import numpy as np
+    from .components.semantic_merge import extract_segmentation_masks, mask_for_tf, reduce_dict
     args = build_parser().parse_args(argv)
+    if args.nima_weight != 0:
+        raise SystemExit("--nima_weight %g: the NIMA term (components/loss.py:141-153, InceptionResNetV2 with weights that are "
+                         "not in the tree) is not part of this build; run with --nima_weight 0 (also in the reference, for "
+                         "identical objectives)" % args.nima_weight)
+    if args.gpu:                                                               # :210-211
+        os.environ.setdefault("CUDA_VISIBLE_DEVICES", args.gpu)
+    if not args.experiment_name:                                               # :217-219
+        from datetime import datetime
+        args.experiment_name = datetime.now().strftime('%Y-%m-%d_%H:%M')
+    experiment_path = args.results_dir / args.experiment_name
+    experiment_path.mkdir(parents=True, exist_ok=True)
+    args.seg_dir.mkdir(parents=True, exist_ok=True)
 
-    def load_image(fn):                                                        # style_transfer.py:55-64
-        bgr = cv2.imread(fn, cv2.IMREAD_COLOR)
-        if bgr is None:
-            raise SystemExit("Image file {} does not exist.".format(fn))
-        return (bgr[:, :, ::-1].astype(np.float32) * np.float32(1.0 / 255.0))[None]
+    # manual segmentation masks (:224-228)
+    content_segmentation_filename = change_filename(args.seg_dir, args.content_image, '_seg', '.png')
+    style_segmentation_filename = change_filename(args.seg_dir, args.style_image, '_seg', '.png')
+    load_segmentation = os.path.exists(content_segmentation_filename) and os.path.exists(style_segmentation_filename)
+    write_metadata(args, load_segmentation, experiment_path)
 
-    t0 = time.time()
+    for file in [args.content_image, args.style_image]:                       # :234-237
+        if not os.path.exists(file):
+            print("Image file {} does not exist.".format(file))
+            raise SystemExit(1)
+    content_image = load_image(args.content_image, args.dtype)               # :241-242
+    style_image = load_image(args.style_image, args.dtype)
 
-    def show(i, d, _img):
-        if i % args.print_loss_interval == 0:
+    content_masks = style_masks = None
+    if load_segmentation:                                                      # :245-250
+        print("Load segmentation from files.")
+        content_segmentation_masks = extract_segmentation_masks(cv2.imread(content_segmentation_filename))
+        style_segmentation_masks = extract_segmentation_masks(cv2.imread(style_segmentation_filename))
+        os.makedirs(os.path.dirname(content_segmentation_filename) or ".", exist_ok=True)
+        cv2.imwrite(content_segmentation_filename, reduce_dict(content_segmentation_masks, content_image))   # :261-264
+        cv2.imwrite(style_segmentation_filename, reduce_dict(style_segmentation_masks, style_image))
+        if args.use_masks:
+            if set(content_segmentation_masks) != set(style_segmentation_masks):
+                raise SystemExit("content and style segmentations use different colour sets (semantic_merge.py:127 asserts "
+                                 "equal key sets after merging)")
+            content_masks, style_masks = mask_for_tf(content_segmentation_masks), mask_for_tf(style_segmentation_masks)
+    else:
+        # :252-259 would run PSPNet + the WordNet merge; both are outside this hot path (weights / corpora absent)
+        print("No *_seg.png files in {}: running without segmentation masks (PSPNet segmentation is not part of this build)."
+              .format(args.seg_dir))
+        if args.use_masks:
+            raise SystemExit("--use_masks needs {} and {}".format(content_segmentation_filename, style_segmentation_filename))
+    if args.init != "content":                                                # :266-278; the reference ignores init (:329)
+        print("note: --init {} is parsed but, as in the reference (style_transfer.py:329), the variable starts from the "
+              "content image".format(args.init))
+
+    iterations_dir = experiment_path / 'iter'
+    iterations_dir.mkdir(exist_ok=True)
+    logs_path = args.logs_dir / args.experiment_name
+    logs_path.mkdir(parents=True, exist_ok=True)
+
+    print("Style transfer started")
+    scalars = (logs_path / 'scalars.jsonl').open('w')                          # stands in for tf.summary.scalar (:372-376)
+    t_loop = time.time()
+
+    def on_iteration(i, losses, image):
+        if i % args.print_loss_interval == 0:                                  # :360-364
             print("[Iter {}]".format(i), end='\t')
-            for k, v in d.items():
-                print('{}: {:<15.3f}'.format(k, v), end='')
+            for loss_name, loss_value in losses.items():
+                print('{}: {:<15.3f}'.format(loss_name, loss_value), end='')
             print()
+        scalars.write(json.dumps(dict(losses, step=i)) + "\n")
+        if i % args.intermediate_result_interval == 0:                         # :379-381 tf.summary.image
+            save_image(tensor_to_image(image), iterations_dir / "iter_{}.png".format(i))
 
-    best, hist = style_transfer(load_image(args.content_image), load_image(args.style_image), args,
-                                vgg_weights=args.vgg_weights, matting=args.matting, callback=show)
-    print("Style transfer finished. Average time per epoch: {:.5f}s\n".format((time.time() - t0) / max(args.iter, 1)))
-    if args.output_image:
-        cv2.imwrite(args.output_image, tensor_to_image(best).cpu().numpy()[:, :, ::-1])
+    best, history = style_transfer(content_image, style_image, args, content_masks, style_masks, vgg_weights=args.vgg_weights,
+                                   matting=args.matting, callback=on_iteration)
+    scalars.close()
+    print("Style transfer finished. Average time per epoch: {:.5f}s\n".format((time.time() - t_loop) / max(args.iter, 1)))
+    if args.output_image and best is not None:
+        out = experiment_path / os.path.basename(args.output_image)
+        save_image(tensor_to_image(best), out)
+        print("Best image (lowest total loss) written to {}".format(out))
+    return best, history
 
 
 if __name__ == "__main__":

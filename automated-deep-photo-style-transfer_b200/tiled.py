@@ -7,9 +7,11 @@ pooling alignment.  With that halo
     halo exchange is needed (redundant convolution work in the halo instead of 25 exchanges per iteration);
   * the matting Laplacian rows of the own pixels (5x5 footprint) are exact as well.
 What does cross the NVLink fabric, per iteration:
-  * the per-class Gram partials of the five style layers (each rank sums over its OWN pixels only) and the float64
-    loss accumulator: one sum-reduction (NCCL all-reduce; 19.5 MB of Grams at K = 8);
-  * the updated own strips, gathered so that every rank can refresh its halo pixels (NCCL all-gather).
+  * the per-class Gram partials of the five style layers (each rank sums over its OWN pixels only): ONE NCCL all-reduce of
+    one flat float32 buffer (the per-layer Gram tensors are views of it; 19.5 MB at K = 8), plus the 4-entry float64 loss
+    accumulator;
+  * the updated border columns: every rank sends the HALO columns next to each of its interior boundaries to that neighbour
+    and receives the neighbour's (NCCL point-to-point, batched; H x 160 x 3 floats per side) -- not whole strips.
 Strip boundaries must be multiples of 16 px so that pooling grids and the bilinear mask resizing of every layer align
 with the global image (then restricting a resized mask to the own columns is exact).
 """
@@ -74,7 +76,7 @@ class TiledStyleTransfer:
         self.tile = Tile(int(content.shape[2]), rank, world)
         self.style_tile = Tile(int(style.shape[2]), rank, world)
         self.reduce_sum = reduce_sum or _nccl_reduce_sum
-        self.gather = gather or _nccl_gather
+        self.gather = gather                            # None: point-to-point border exchange over NCCL (the default)
         c_loc = self.tile.crop(content).to(dev)
         s_loc = self.style_tile.crop(style).to(dev)
         cm = None if content_masks is None else [self.tile.crop(torch.as_tensor(m)) for m in content_masks]
@@ -89,13 +91,38 @@ class TiledStyleTransfer:
         self.image = c_loc.clone()                      # the local strip of the transfer image (own columns + halo)
         self._grad = torch.empty_like(self.image)
         self._targets_reduced = False
+        self._flat = None                               # flat float32 buffer behind the per-layer Gram partials
+        self._bytes = {"allreduce": 0, "halo": 0}
+
+    def _flatten_partials(self):
+        """Make the per-layer transfer Grams views of ONE buffer, so that a single all-reduce sums them all."""
+        sts = list(self.loss._layer_cache.values())
+        n = sum(st["G"].numel() for st in sts)
+        self._flat = torch.zeros(n, dtype=torch.float32, device=self.image.device)
+        o = 0
+        for st in sts:
+            g = st["G"]
+            st["G"] = self._flat[o:o + g.numel()].view(g.shape)
+            o += g.numel()
+
+    def describe_exchange(self):
+        if self.world == 1:
+            return "no exchange (single strip)"
+        return ("one NCCL all-reduce of the flattened Gram partials (%.1f MB) + float64[4] loss accumulator, point-to-point "
+                "exchange of the %d-px border columns with both neighbours" % (4e-6 * (self._flat.numel() if self._flat is not None else 0), HALO))
+
+    def exchange_bytes(self):
+        """Bytes this rank hands to NCCL per step: all-reduce payload and halo columns sent."""
+        return dict(self._bytes)
 
     # -- the three phases of one iteration; a multi-rank driver interleaves the reductions between them ------------
     def phase_partials(self):
         outputs = self.extractor(self.image, reuse=True)
-        if not self._targets_reduced:
-            self.loss.prepare(outputs)
-        return self.loss.forward_partials(self.image, outputs)
+        if self._flat is None:
+            self.loss.prepare(outputs)                  # per-layer state (idempotent), then one buffer behind all Gram partials
+            self._flatten_partials()
+        parts = self.loss.forward_partials(self.image, outputs)
+        return [self._flat, parts[-1]]                  # every Gram partial lives in the flat buffer; + the float64 accumulator
 
     def phase_finish(self):
         loss_dict = self.loss.finish()
@@ -116,6 +143,38 @@ class TiledStyleTransfer:
             if r != self.rank and a < b:
                 self.image[0, :, a - t.ext_lo:b - t.ext_lo] = s[:, a - lo:b - lo]
 
+    def exchange_borders(self):
+        """Halo refresh over NCCL point-to-point: send the HALO own columns next to each interior boundary to that neighbour,
+        receive the neighbour's into the halo columns.  Strips narrower than the halo would need data from farther ranks;
+        that case falls back to gathering whole strips."""
+        import torch.distributed as dist
+        t = self.tile
+        own_w = t.own_hi - t.own_lo
+        if own_w < HALO:
+            out = [torch.empty_like(self.own_strip()) for _ in range(self.world)]
+            dist.all_gather(out, self.own_strip())
+            self._bytes["halo"] = out[0].numel() * 4
+            self.refresh_halo(out)
+            return
+        lo, hi = t.own_lo - t.ext_lo, t.own_hi - t.ext_lo               # own columns in local coordinates
+        ops, recv = [], []
+        sent = 0
+        if self.rank > 0:                                               # left neighbour
+            snd = self.image[0, :, lo:lo + HALO].contiguous()
+            rcv = torch.empty_like(self.image[0, :, 0:lo])
+            ops += [dist.P2POp(dist.isend, snd, self.rank - 1), dist.P2POp(dist.irecv, rcv, self.rank - 1)]
+            recv.append((rcv, 0, lo)); sent += snd.numel() * 4
+        if self.rank < self.world - 1:                                  # right neighbour
+            snd = self.image[0, :, hi - HALO:hi].contiguous()
+            rcv = torch.empty_like(self.image[0, :, hi:t.local_w])
+            ops += [dist.P2POp(dist.isend, snd, self.rank + 1), dist.P2POp(dist.irecv, rcv, self.rank + 1)]
+            recv.append((rcv, hi, t.local_w)); sent += snd.numel() * 4
+        for req in dist.batch_isend_irecv(ops):
+            req.wait()
+        for rcv, a, b in recv:
+            self.image[0, :, a:b] = rcv
+        self._bytes["halo"] = sent
+
     def step(self):
         """One iteration with real collectives (one process per GPU)."""
         if not self._targets_reduced:
@@ -123,9 +182,14 @@ class TiledStyleTransfer:
             self.loss.prepare(outputs)
             self.reduce_sum(self.loss.style_targets_partial())
             self._targets_reduced = True
-        self.reduce_sum(self.phase_partials())
+        parts = self.phase_partials()
+        self._bytes["allreduce"] = sum(p.numel() * p.element_size() for p in parts)
+        self.reduce_sum(parts)
         loss_dict = self.phase_finish()
-        self.refresh_halo(self.gather(self.own_strip()))
+        if self.gather is not None:
+            self.refresh_halo(self.gather(self.own_strip()))
+        elif self.world > 1:
+            self.exchange_borders()
         return loss_dict
 
 
@@ -140,6 +204,15 @@ def _nccl_gather(strip):
     out = [torch.empty_like(strip) for _ in range(dist.get_world_size())]
     dist.all_gather(out, strip)
     return out
+
+
+def _gloo_reduce_sum(tensors):
+    """Host-side stand-in used by the CPU protocol tests: the same call sequence over a gloo group."""
+    import torch.distributed as dist
+    for t in tensors:
+        c = t.detach().cpu()
+        dist.all_reduce(c, op=dist.ReduceOp.SUM)
+        t.copy_(c)
 
 
 def run_emulated(ranks, iters):

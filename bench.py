@@ -6,20 +6,29 @@
         bench.py --gpus N --steps K --warmup W
 
 One "step" = one full train_step (style_transfer.py:331-344 of the reference): VGG19 forward to block5_conv1,
-content + masked-Gram style + photorealism (x^T L x) losses, gradient to the image, Adam + clip.
-Workload at every N: BASELINE.json configs[1] -- one 1024x1024 content/style pair per GPU, 8 semantic classes,
+content + masked-Gram style + photorealism (x^T L x) [+ TV, an extension the north star names] losses, gradient to the
+image, Adam + clip.
+Headline workload at every N: BASELINE.json configs[1] -- one 1024x1024 content/style pair per GPU, 8 semantic classes,
 matting_v2 Laplacian (eps 1e-7, r 1), synthetic U[0,1) images, seeded He-normal VGG19 weights.
 N > 1: independent pairs, one per rank, no data-path collective -> "scaling": "weak".
 
-Prints ONE JSON line (rank 0).  `value` is device-timed with the inputs resident in HBM (CUDA-graph replay);
-`e2e` is the same metric through the public train_step API with the image starting and ending in pinned HOST memory
-every step.  `roofline` describes the dominant kernel family (3x3 conv, tensor-bound) and `roofline_lx` the
-Laplacian mat-vec (HBM-bound).  `cpu_baseline` (rank 0, N = 1) times the oracle port on the host cores.
+Prints ONE JSON line (rank 0).
+  value        device-timed, inputs resident in HBM (CUDA-graph replay)
+  e2e          the same metric through the public train_step API with the image starting and ending in pinned HOST memory
+               every step (H2D + step + D2H of the image and the loss vector inside the timed region)
+  roofline     dominant kernel family (3x3 conv, tensor-bound); roofline_lx: the Laplacian mat-vec (HBM-bound)
+  parity       (N = 1) loss dictionary and image gradient of the SAME inputs from the float64 CPU oracle; the run exits
+               non-zero if a loss scalar is off by more than 1e-5 relative
+  cpu_baseline (N = 1) the CPU port of the step on the host cores
+  extras       records of the other BASELINE configs, measured in the same run so the driver's N = 1, 2, 4, 8 sweep sees
+               them:  roofline_lx_sweep (configs[4]), pairs_64x512 (configs[2], strong scaling), tiled_4k (configs[3])
+Single-config modes (own JSON line): --pairs P --pair-size S | --tiled | --lx-sweep | --config 0.
 
 --impl reference: the reference program itself needs TensorFlow/Keras (absent, no network), so the reference arm
 times the CPU port of the same path (oracle/: torch-CPU float32 VGG/Gram + float64 matting_v2), kind "port".
 """
 import argparse
+import glob
 import importlib
 import json
 import os
@@ -34,17 +43,30 @@ PKG = "automated-deep-photo-style-transfer_b200"
 
 METRIC = "adam_iters_per_sec_1024x1024"
 UNIT = "iter/s"
+DTYPE = "f32 (VGG/Gram: float32-accurate 3xFP16 tensor-core products, fp32 accumulation; Adam f32) + f64 (Laplacian arithmetic)"
 
 
-def hyper(size_classes):
+def hyper(tv_weight=0.0):
     return argparse.Namespace(content_weight=1.0, style_weight=100.0, nima_weight=0.0, regularization_weight=1e4,
                               matting_epsilon=1e-7, matting_window_radius=1, adam_lr=0.1, adam_beta1=0.9,
-                              adam_beta2=0.999, adam_epsilon=1e-8)
+                              adam_beta2=0.999, adam_epsilon=1e-8, tv_weight=float(tv_weight))
+
+
+def workload_string(size, classes, tv_weight):
+    """The SAME string in both arms (the driver compares config.workload)."""
+    tv = " + TV (extension, weight %g)" % tv_weight if tv_weight > 0 else ""
+    return ("configs[1]: one %dx%d content/style pair per GPU, %d semantic classes, content + masked-Gram style + "
+            "photorealism%s loss, gradient, Adam+clip; matting_v2 eps=1e-7 r=1; random-init VGG19; synthetic U[0,1) images"
+            % (size, size, classes, tv))
+
+
+def mod(name):
+    return importlib.import_module(PKG + "." + name)
 
 
 def conv_flops(size):
     """Algorithmic FLOPs of the 13 forward convolutions (2*h*w*9*Cin*Cout) and the 12 data gradients."""
-    synth = importlib.import_module(PKG + ".synth")
+    synth = mod("synth")
     fwd, bwd, h = [], [], size
     i = 0
     for item in synth.VGG_TOPOLOGY:
@@ -112,32 +134,71 @@ def peaks():
     return 6650.0, 1590.0, 1400.0, "fallback"
 
 
+def profile_traffic(kernel_substring):
+    """dram__bytes_read.sum + dram__bytes_write.sum of one launch of a kernel, read from the committed ncu summaries
+    (profiles/*summary*.csv, newest round first).  Returns (bytes or None, file name or None)."""
+    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "*summary*.csv")), reverse=True)
+    for f in files:
+        cur, rd, wr = None, None, None
+        for line in open(f):
+            parts = line.rstrip("\n").split(",")
+            if parts[0] == "Kernel Name":
+                if cur and rd is not None and wr is not None:
+                    return (rd + wr), os.path.basename(f)
+                cur, rd, wr = (line if kernel_substring in line else None), None, None
+            elif cur and len(parts) >= 3 and parts[0] in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+                scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(parts[1], None)
+                if scale is None:
+                    continue
+                v = float(parts[2]) * scale
+                if parts[0].startswith("dram__bytes_read"):
+                    rd = v
+                else:
+                    wr = v
+        if cur and rd is not None and wr is not None:
+            return (rd + wr), os.path.basename(f)
+    return None, None
+
+
 # ----------------------------------------------------------------------------------------------------------------
-# CPU port (oracle) timing: cpu_baseline leg and --impl reference
+# CPU port (oracle): cpu_baseline leg, parity leg and --impl reference
 # ----------------------------------------------------------------------------------------------------------------
-def cpu_port_state(size, K):
+def host_threads():
+    """All host cores for the CPU arm.  torch.distributed.run exports OMP_NUM_THREADS=1 to its workers; the reference arm
+    runs on rank 0 alone, so it takes the whole machine."""
+    import torch
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    torch.set_num_threads(max(1, n))
+    return torch.get_num_threads()
+
+
+def oracle_cfg(a):
+    return {"weights": {"content": a.content_weight, "style": a.style_weight, "nima": 0.0, "photo": a.regularization_weight,
+                        "tv": a.tv_weight},
+            "matting_epsilon": a.matting_epsilon, "matting_window_radius": a.matting_window_radius,
+            "adam": {"lr": a.adam_lr, "beta1": a.adam_beta1, "beta2": a.adam_beta2, "epsilon": a.adam_epsilon}}
+
+
+def cpu_port_state(size, K, tv_weight, dtype=None, seeds=(0, 1, 9, 10)):
     import torch
     from oracle import masks as omasks
     from oracle import model as omodel
-    synth = importlib.import_module(PKG + ".synth")
-    a = hyper(None)
-    cfg = {"weights": {"content": a.content_weight, "style": a.style_weight, "nima": 0.0, "photo": a.regularization_weight},
-           "matting_epsilon": a.matting_epsilon, "matting_window_radius": a.matting_window_radius,
-           "adam": {"lr": a.adam_lr, "beta1": a.adam_beta1, "beta2": a.adam_beta2, "epsilon": a.adam_epsilon}}
-    cm = [torch.as_tensor(m) for m in omasks.mask_for_tf(omasks.extract_segmentation_masks(synth.label_image(size, size, K, 9)))]
-    sm = [torch.as_tensor(m) for m in omasks.mask_for_tf(omasks.extract_segmentation_masks(synth.label_image(size, size, K, 10)))]
-    # float32 VGG / Gram (what TF-CPU would run), float64 matting Laplacian (what the reference runs)
-    return omodel.TrainState(torch.as_tensor(synth.image(size, size, 0)), torch.as_tensor(synth.image(size, size, 1)),
-                             synth.vgg_weights(), cfg, cm, sm, dtype=torch.float32)
+    synth = mod("synth")
+    a = hyper(tv_weight)
+    cm = [torch.as_tensor(m) for m in omasks.mask_for_tf(omasks.extract_segmentation_masks(synth.label_image(size, size, K, seeds[2])))]
+    sm = [torch.as_tensor(m) for m in omasks.mask_for_tf(omasks.extract_segmentation_masks(synth.label_image(size, size, K, seeds[3])))]
+    # default: float32 VGG / Gram (what TF-CPU would run), float64 matting Laplacian (what the reference runs)
+    return omodel.TrainState(torch.as_tensor(synth.image(size, size, seeds[0])), torch.as_tensor(synth.image(size, size, seeds[1])),
+                             synth.vgg_weights(), oracle_cfg(a), cm, sm, dtype=dtype or torch.float32)
 
 
 def run_reference(args):
-    """--impl reference: the CPU port of the same step on all host threads torch will use."""
+    """--impl reference: the CPU port of the same step on all host threads."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    import torch
-    st = cpu_port_state(args.size, args.classes)
+    cores = host_threads()
+    st = cpu_port_state(args.size, args.classes, args.tv_weight)
     budget = float(os.environ.get("ADPST_REF_BUDGET_S", "240"))
     t0 = time.perf_counter()
     st.train_step()
@@ -151,15 +212,14 @@ def run_reference(args):
         st.train_step()
     dt = time.perf_counter() - t0
     v = n / dt
-    cores = torch.get_num_threads()
     sample = "%d of the requested %d iterations at %dx%d, K=%d (time-bounded to %.0f s); %d warm-up" % (
         n, args.steps, args.size, args.size, args.classes, budget, warm + 1)
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "steps_executed": n, "warmup": args.warmup, "ms_per_step": 1e3 / v, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32 (VGG/Gram) + f64 (Laplacian)", "data": "synthetic",
-        "config": {"workload": "1x %dx%d pair, %d classes, matting_v2 eps=1e-7 r=1, CPU port of the reference step"
-                               % (args.size, args.size, args.classes)},
+        "config": {"workload": workload_string(args.size, args.classes, args.tv_weight),
+                   "arm": "CPU port of the reference step (oracle/: torch-CPU float32 VGG/Gram + float64 matting_v2)"},
         "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
                          "host_cpus": os.cpu_count()},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -167,10 +227,26 @@ def run_reference(args):
     }))
 
 
+def cpu_baseline(size, K, tv_weight):
+    """Oracle port on the host cores: bounded sample (10 iterations, about 30 s of CPU work at 1024x1024)."""
+    cores = host_threads()
+    st = cpu_port_state(size, K, tv_weight)
+    t0 = time.perf_counter(); st.train_step(); first = time.perf_counter() - t0
+    n = max(2, min(10, int(40.0 / max(first, 1e-3))))
+    t0 = time.perf_counter()
+    for _ in range(n):
+        st.train_step()
+    dt = time.perf_counter() - t0
+    return {"value": n / dt, "unit": UNIT, "cores": cores, "kind": "port", "host_cpus": os.cpu_count(),
+            "sample": "%d iterations at %dx%d, K=%d after 1 warm-up (torch-CPU float32 VGG/Gram + float64 matting_v2 port "
+                      "of the reference step; TensorFlow itself is not installable here)" % (n, size, size, K)}
+
+
 # ----------------------------------------------------------------------------------------------------------------
-# our arm
+# timing helpers
 # ----------------------------------------------------------------------------------------------------------------
 def time_launches(fn, flush, reps=5):
+    """Mean device time of fn() launched alone after an L2 flush (write of a buffer larger than the 126 MB L2)."""
     import torch
     fn(); torch.cuda.synchronize()
     ts = []
@@ -198,37 +274,351 @@ def time_rotating(fns, rounds=5):
     return a.elapsed_time(b) / (rounds * len(fns))
 
 
-def run_ours(args):
+class Dist:
+    """Rank bookkeeping; NCCL is used for the barrier and the MAX of elapsed times (and, in tiled mode, the data path)."""
+
+    def __init__(self):
+        import torch
+        import torch.distributed as dist
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.local = int(os.environ.get("LOCAL_RANK", "0"))
+        if not torch.cuda.is_available():
+            raise SystemExit("bench.py needs a CUDA device: there is no CPU fallback for the product path")
+        torch.cuda.set_device(self.local)
+        if self.world > 1:
+            dist.init_process_group("nccl", device_id=torch.device("cuda", self.local))
+        self.dist = dist
+
+    def barrier(self):
+        import torch
+        if self.world > 1:
+            self.dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_ms(self, ms):
+        import torch
+        t = torch.tensor([ms], device="cuda", dtype=torch.float64)
+        if self.world > 1:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return float(t)
+
+    def sum(self, v):
+        import torch
+        t = torch.tensor([v], device="cuda", dtype=torch.float64)
+        if self.world > 1:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM)
+        return float(t)
+
+    def close(self):
+        if self.world > 1:
+            self.dist.barrier()
+            self.dist.destroy_process_group()
+
+
+def build_pair(ext, size, K, hp, seeds, pinned=False):
+    """Set-up of one content/style pair on the current device: targets, Loss (style Grams, mask pyramids, patch lists),
+    Laplacian handle, optimiser.  Returns (loss, opt, content_dev, content_host)."""
     import torch
-    import torch.distributed as dist
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py needs a CUDA device: there is no CPU fallback for the product path")
-    torch.cuda.set_device(local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-
-    synth = importlib.import_module(PKG + ".synth")
-    st = importlib.import_module(PKG + ".style_transfer")
-    vggm = importlib.import_module(PKG + ".components.VGG19.model")
-    lossm = importlib.import_module(PKG + ".components.loss")
-    sem = importlib.import_module(PKG + ".components.semantic_merge")
-    v2 = importlib.import_module(PKG + ".components.matting_v2")
-    lib = importlib.import_module(PKG + "._lib")
-
-    S, K = args.size, args.classes
-    hp = hyper(None)
-    content_h = torch.as_tensor(synth.image(S, S, 2 * rank)).pin_memory()
-    style = torch.as_tensor(synth.image(S, S, 2 * rank + 1)).cuda()
+    synth, lossm, sem, st = mod("synth"), mod("components.loss"), mod("components.semantic_merge"), mod("style_transfer")
+    content_h = torch.as_tensor(synth.image(size, size, seeds[0]))
+    if pinned:
+        content_h = content_h.pin_memory()
+    style = torch.as_tensor(synth.image(size, size, seeds[1])).cuda()
     content = content_h.cuda()
-    cm = sem.mask_for_tf(sem.extract_segmentation_masks(synth.label_image(S, S, K, 9 + rank)))
-    sm = sem.mask_for_tf(sem.extract_segmentation_masks(synth.label_image(S, S, K, 10 + rank)))
-    ext = vggm.StyleContentModel(st.CONTENT_LAYERS, st.STYLE_LAYERS, shape=(None, None, 3), weights=synth.vgg_weights())
+    cm = sem.mask_for_tf(sem.extract_segmentation_masks(synth.label_image(size, size, K, seeds[2])))
+    sm = sem.mask_for_tf(sem.extract_segmentation_masks(synth.label_image(size, size, K, seeds[3])))
     loss = lossm.Loss(ext(content)["content"], ext(style)["style"], hp, cm, sm)
     loss.initialize_matting_laplacian(content[0].to(torch.float64))
     opt = st.Adam(hp.adam_lr, hp.adam_beta1, hp.adam_beta2, hp.adam_epsilon)
+    return loss, opt, content, content_h
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# roofline legs
+# ----------------------------------------------------------------------------------------------------------------
+def conv_roofline(ext, x, S, step_ms):
+    import torch
+    lib = mod("_lib")
+    hbm, tf_burst, tf_sus, which = peaks()
+    flush = torch.empty(512 << 20, dtype=torch.uint8, device="cuda")
+    fwd, bwd = conv_flops(S)
+    A = ext._loop
+    tot_f, tot_t, n_launch = 0.0, 0.0, 0
+    scratch = torch.empty(A.acts[0].numel(), dtype=torch.float32, device="cuda")
+    stream = lib.stream_ptr()
+    per_layer = []
+    for i, h, cin, cout, f in fwd:
+        if i == 0:
+            continue                                        # block1_conv1 (Cin = 3) is a CUDA-core kernel, not in this family
+        src = A.pools[[1, 3, 7, 11].index(i - 1)] if (i - 1) in (1, 3, 7, 11) else A.acts[i - 1]
+        slot = ext.vgg.act_absmax_ptr(i - 1)                # the scale slot the step's own forward pass left behind
+        t = time_launches(lambda: lib.check(lib.lib().adpst_vgg_conv_forward(ext.vgg._h, i, lib.ptr(src), h, h,
+                                                                             lib.ptr(scratch), slot, stream)), flush, 3)
+        tot_f += f; tot_t += t; n_launch += 1
+        per_layer.append({"conv": i, "dir": "fwd", "hw": h, "cin": cin, "cout": cout, "ms": round(t, 4), "tflops": round(f / t / 1e9, 1)})
+    for i, h, cin, cout, f in bwd:
+        slot = ext.vgg.act_absmax_ptr(i)
+        t = time_launches(lambda: lib.check(lib.lib().adpst_vgg_conv_dgrad(ext.vgg._h, i, lib.ptr(A.acts[i]), h, h,
+                                                                           lib.ptr(scratch), slot, stream)), flush, 3)
+        tot_f += f; tot_t += t; n_launch += 1
+        per_layer.append({"conv": i, "dir": "dgrad", "hw": h, "cin": cin, "cout": cout, "ms": round(t, 4), "tflops": round(f / t / 1e9, 1)})
+    conv_tflops = tot_f / (tot_t * 1e-3) / 1e12
+    traffic, traffic_file = profile_traffic("conv3x3_tc_kernel")
+    # The reference computes these convolutions in float32 (1e-5 parity): the tensor-core kernel forms every product from
+    # 3 FP16 MMAs (hi*hi + hi*lo + lo*hi, power-of-two scaled, fp32 accumulation), which run at the bf16 rate, so the
+    # ceiling for this arithmetic is peak_bf16 / 3; `frac` is still quoted against the measured bf16 peak, as the contract asks.
+    return {"kernel": "conv3x3_tc_kernel: persistent tcgen05 3xFP16 implicit GEMM, TMA-fed, A operand in TMEM (12 forward "
+                      "+ 12 data-gradient launches per step; block1_conv1 forward is a CUDA-core kernel)", "bound": "tensor",
+            "achieved": conv_tflops, "peak": tf_sus, "unit": "TFLOP/s", "frac": conv_tflops / tf_sus,
+            "traffic": traffic, "traffic_of": ("one launch, dram__bytes_read.sum + dram__bytes_write.sum from profiles/%s"
+                                               % traffic_file) if traffic_file else None,
+            "peak_source": which + " bf16 dense, sustained (kernel timed inside a long step)",
+            "flops_per_launch_avg": tot_f / n_launch, "ms_per_launch_avg": tot_t / n_launch, "launches": n_launch,
+            "share_of_step": tot_t / step_ms,
+            "fp32_accurate_ceiling": {"what": "3xFP16: peak_bf16 / 3 (MMAs per product)",
+                                      "peak": tf_sus / 3.0, "frac": conv_tflops / (tf_sus / 3.0)},
+            "per_layer": per_layer,
+            "note": "algorithmic FLOPs (2*h*w*9*Cin*Cout per layer); issued tensor FLOPs are 3x that; every launch timed "
+                    "alone with CUDA events after an L2 flush"}
+
+
+def lap_calls(S, mode, compute_dtype, nsets=None, image=None, eps=1e-7):
+    """Independent (operator, x, y) sets whose combined footprint exceeds L2 (each set is 36 B/px)."""
+    import torch
+    v2, v3 = mod("components.matting_v2"), mod("components.matting_v3")
+    cls = v2.MattingLaplacian if mode == "v2" else v3.MattingLaplacian
+    if nsets is None:
+        nsets = min(24, max(2, int(160e6 // (36 * S * S)) + 1))
+    g = torch.Generator(device="cuda").manual_seed(2)
+    calls, keep = [], []
+    for j in range(nsets):
+        img = torch.rand(S, S, 3, device="cuda", generator=g) if image is None else torch.roll(image, j, 0).contiguous()
+        op = cls(img, epsilon=eps, window_radius=1, storage_dtype=torch.float32, compute_dtype=compute_dtype)
+        xj = torch.rand(S * S, 3, device="cuda", generator=g)
+        yj, qj = torch.empty_like(xj), torch.zeros(1, dtype=torch.float64, device="cuda")
+        keep.append((op, xj, yj, qj))
+        calls.append(lambda op=op, xj=xj, yj=yj, qj=qj: op._op.apply3(xj, want_y=True, want_quad=True, y_scale=2e4,
+                                                                       out=yj, quad_out=qj))
+    return calls, keep, nsets
+
+
+def lx_roofline(S, content):
+    import torch
+    hbm, _, _, which = peaks()
+    calls, keep, nsets = lap_calls(S, "v2", torch.float64, image=content[0])
+    t_lx = time_rotating(calls)
+    del calls, keep
+    lx_gbs = 36.0 * S * S / (t_lx * 1e-3) / 1e9
+    traffic, traffic_file = profile_traffic("lap_")
+    # The quoted roofline is HBM (36 B/px), as the metric asks; float64 arithmetic bounds the kernel below that:
+    f64_floor_ms = 250.0 * S * S / (64.0 * 148 * 1.965e9) * 1e3
+    return {"kernel": "matrix-free matting-Laplacian mat-vec with fused x^T L x and 2 w L x (float32 I/O, float64 arithmetic: the "
+                      "path Loss uses)", "bound": "hbm",
+            "achieved": lx_gbs, "peak": hbm, "unit": "GB/s", "frac": lx_gbs / hbm,
+            "traffic": traffic, "traffic_of": ("one launch, from profiles/%s" % traffic_file) if traffic_file else None,
+            "peak_source": which + " copy bandwidth", "bytes_per_launch": 36 * S * S, "ms_per_launch": t_lx,
+            "l2": "%d independent operator/x/y sets (%.0f MB) rotated, calls queued back to back" % (nsets, nsets * 36e-6 * S * S),
+            "float64_pipe_floor": {"what": "250 float64 lane-ops/px at 64 lanes/clk/SM x 148 SMs x 1.965 GHz",
+                                   "ms_per_launch": f64_floor_ms, "frac_of_floor": f64_floor_ms / t_lx}}
+
+
+def lx_sweep(sizes=(256, 512, 1024, 2048, 4096, 8192)):
+    """BASELINE configs[4]: matting-Laplacian build + L.x sweep (v2 and v3 operators) against the HBM roofline.
+    mat-vec: 36 B/px algorithmic; build v2 (means + inverse covariances written out): 48 B/px; build v3 (COO export, the
+    reference's explicit matrix): 24 B per non-zero, 81 non-zeros per interior window -- capped at 2048^2 (8 GB of triplets;
+    the reference itself cannot build 8192^2: 87 GB)."""
+    import torch
+    hbm, _, _, which = peaks()
+    flush = torch.empty(512 << 20, dtype=torch.uint8, device="cuda")
+    rows = []
+    for S in sizes:
+        row = {"size": "%dx%d" % (S, S)}
+        for mode in ("v2", "v3"):
+            nsets = min(64, max(2, int(150e6 // (36 * S * S)) + 1)) if S < 4096 else 2
+            calls, keep, nsets = lap_calls(S, mode, torch.float64, nsets=nsets)
+            t = time_rotating(calls, rounds=3 if S >= 4096 else 5)
+            gbs = 36.0 * S * S / (t * 1e-3) / 1e9
+            row[mode] = {"matvec_ms": round(t, 4), "matvec_GBps": round(gbs, 1), "matvec_frac_hbm": round(gbs / hbm, 4),
+                         "l2": "%d sets rotated (%.0f MB)" % (nsets, nsets * 36e-6 * S * S)}
+            op = keep[0][0]
+            if mode == "v2":
+                means = torch.empty(S, S, 3, 1, dtype=torch.float32, device="cuda")
+                dinv = torch.empty(S, S, 3, 3, dtype=torch.float32, device="cuda")
+                lib = mod("_lib")
+                tb = time_launches(lambda: lib.check(lib.lib().adpst_laplacian_coefficients(op._op._h, lib.ptr(means), lib.ptr(dinv),
+                                                                                            lib.stream_ptr())), flush, 3)
+                row[mode].update(build_ms=round(tb, 4), build_GBps=round(48.0 * S * S / (tb * 1e-3) / 1e9, 1),
+                                 build_what="means + delta_inv fields (matting_v2.py:49-52), 48 B/px")
+                del means, dinv
+            elif S <= 2048:
+                nnz = op.nnz
+                lib = mod("_lib")
+                rws = torch.empty(nnz, dtype=torch.int64, device="cuda"); cls_ = torch.empty(nnz, dtype=torch.int64, device="cuda")
+                vals = torch.empty(nnz, dtype=torch.float32, device="cuda")
+                tb = time_launches(lambda: lib.check(lib.lib().adpst_laplacian_export_coo(op._op._h, lib.ptr(rws), lib.ptr(cls_),
+                                                                                          lib.ptr(vals), lib.stream_ptr())), flush, 2)
+                row[mode].update(build_ms=round(tb, 4), build_GBps=round(20.0 * nnz / (tb * 1e-3) / 1e9, 1), nnz=nnz,
+                                 build_what="COO triplets in the reference's order (matting_v3.py:61-102), 20 B per non-zero "
+                                            "(int64 row, int64 col, float32 value)")
+                del rws, cls_, vals
+            del calls, keep, op
+            torch.cuda.empty_cache()
+        rows.append(row)
+    return {"config": "configs[4]: matting-Laplacian build + L.x, 256^2 .. 8192^2, float32 I/O / float64 arithmetic, r = 1, eps 1e-7",
+            "peak_GBps": hbm, "peak_source": which + " copy bandwidth", "rows": rows}
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# parity leg (N = 1): the float64 oracle on the same inputs
+# ----------------------------------------------------------------------------------------------------------------
+def parity_check(ext, loss, content, S, K, tv_weight):
+    import numpy as np
+    import torch
+    from oracle import parity as oparity
+    host_threads()
+    synth = mod("synth")
+    pert = np.sign(synth.image(S, S, 3) - 0.5).astype(np.float32) * 0.1
+    x = torch.clamp(content + torch.as_tensor(pert).cuda(), 0, 1).contiguous()       # away from x = content
+    d = {k: float(v) for k, v in loss(x, ext(x, reuse=True)).items()}
+    g = loss.gradient(ext).cpu().numpy()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    ora = cpu_port_state(S, K, tv_weight, dtype=torch.float64)
+    do, go, ref_acts = ora.loss_and_grad(x.cpu().double(), return_acts=True)
+    rel = {k: abs(d[k] - do[k]) / max(abs(do[k]), 1e-300) for k in d if k != "NIMA loss"}
+    rep = oparity.gradient_report(g, go.numpy(), ext.last.acts, ref_acts, 1e-5)
+    worst = max(rel.values())
+    return {"config": "%dx%d K=%d, x = clip(content + 0.1 sign(noise)); float64 CPU oracle (oracle/model.py) on the same inputs"
+                      % (S, S, K),
+            "loss_rel_diff": {k: float("%.3g" % v) for k, v in rel.items()}, "max_rel_loss_diff": worst,
+            "grad_rel_maxnorm": rep["rel_maxnorm"],
+            "grad_rel_maxnorm_outside_flipped_relu_fields": rep["rel_maxnorm_outside_flipped_fields"],
+            "relu_flips": rep["relu_flips"], "relu_units": int(sum(a.numel() for a in ref_acts)),
+            "grad_frac_pixels_above_1e-5": rep["frac_pixels_above_tol"],
+            "pixels_inside_flipped_fields": rep["pixels_inside_flipped_fields"],
+            "tolerance": 1e-5, "ok": bool(worst <= 1e-5), "oracle_seconds": round(time.perf_counter() - t0, 1),
+            "keys_equal": list(d) == list(do)}
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# BASELINE configs[2]: a batch of independent pairs spread over the ranks (strong scaling, no collective)
+# ----------------------------------------------------------------------------------------------------------------
+def pairs_record(D, ext_cache, n_pairs, size, K, iters, tv_weight):
+    import torch
+    st, vggm, synth = mod("style_transfer"), mod("components.VGG19.model"), mod("synth")
+    hp = hyper(tv_weight)
+    ext = ext_cache.get("ext")
+    if ext is None:
+        ext = ext_cache["ext"] = vggm.StyleContentModel(st.CONTENT_LAYERS, st.STYLE_LAYERS, shape=(None, None, 3),
+                                                        weights=synth.vgg_weights())
+    mine = list(range(D.rank, n_pairs, D.world))
+    # one throw-away pair: allocator, lazily configured kernels
+    loss, opt, content, _ = build_pair(ext, size, K, hp, (1000, 1001, 9, 10))
+    step = st.make_train_step(ext, loss, opt, use_cuda_graph=True); x = content.clone(); step(x); torch.cuda.synchronize()
+    del loss, opt, step, x
+    D.barrier()
+    t_all = time.perf_counter()
+    setup_s, iter_ms, host_s = 0.0, 0.0, 0.0
+    last = None
+    for p in mine:
+        t0 = time.perf_counter()
+        # host-side synthetic data generation (stands in for image decoding) is reported separately
+        _ = synth.image(size, size, 2 * p), synth.image(size, size, 2 * p + 1)
+        host_s += time.perf_counter() - t0
+        t0 = time.perf_counter()
+        loss, opt, content, _ = build_pair(ext, size, K, hp, (2 * p, 2 * p + 1, 100 + p, 200 + p))
+        x = content.clone()
+        step = st.make_train_step(ext, loss, opt, use_cuda_graph=True)
+        step(x)                                             # captures the graph and runs iteration 1
+        torch.cuda.synchronize()
+        setup_s += time.perf_counter() - t0
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(iters - 1):
+            d = step(x)
+        e1.record(); torch.cuda.synchronize()
+        iter_ms += e0.elapsed_time(e1)
+        last = float(d["Total loss"])
+        del loss, opt, step
+    wall = time.perf_counter() - t_all
+    wall_max = D.max_ms(wall * 1e3) * 1e-3
+    setup_tot, iter_tot, host_tot = D.sum(setup_s), D.sum(iter_ms), D.sum(host_s)
+    per_setup_ms = 1e3 * (setup_tot - host_tot) / n_pairs
+    per_iter_ms = iter_tot / (n_pairs * (iters - 1))
+    return {"config": "configs[2]: %d independent %dx%d pairs (K=%d), round-robin over %d GPU(s), no collective; per pair: set-up "
+                      "(targets, style Grams, mask pyramids, patch lists, Laplacian handle, CUDA-graph capture incl. iteration 1) "
+                      "then %d graph-replayed iterations" % (n_pairs, size, size, K, D.world, iters - 1),
+            "scaling": "strong", "n_gpus": D.world, "pairs": n_pairs, "iterations_per_pair": iters,
+            "value": n_pairs * iters / wall_max, "unit": UNIT, "wall_s": wall_max,
+            "setup_ms_per_pair": per_setup_ms, "host_datagen_ms_per_pair": 1e3 * host_tot / n_pairs,
+            "iteration_ms": per_iter_ms, "iterations_only_iters_per_sec": D.world * 1e3 / per_iter_ms,
+            "setup_share_at_100_iterations": per_setup_ms / (per_setup_ms + 100 * per_iter_ms),
+            "last_total_loss_rank0": last}
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# BASELINE configs[3]: one large image, column strips over the ranks (tiled.py)
+# ----------------------------------------------------------------------------------------------------------------
+def tiled_record(D, H, W, K, steps, warmup, tv_weight, check_parity=True):
+    import torch
+    synth, tiled, sem = mod("synth"), mod("tiled"), mod("components.semantic_merge")
+    hp = hyper(tv_weight)
+    content, style = synth.image(H, W, 0), synth.image(H, W, 1)
+    cm = sem.mask_for_tf(sem.extract_segmentation_masks(synth.label_image(H, W, K, 9, cell=64)))
+    sm = sem.mask_for_tf(sem.extract_segmentation_masks(synth.label_image(H, W, K, 10, cell=64)))
+    weights = synth.vgg_weights()
+    if D.world > 1:
+        job = tiled.TiledStyleTransfer(content, style, hp, cm, sm, weights, D.rank, D.world)
+    else:
+        job = tiled.TiledStyleTransfer(content, style, hp, cm, sm, weights, 0, 1, reduce_sum=lambda t: None,
+                                       gather=lambda s: [s])
+    first = {k: float(v) for k, v in job.step().items()}           # iteration 0: evaluated at x = content on every rank
+    for _ in range(max(warmup, 3) - 1):
+        d = job.step()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    D.barrier(); e0.record()
+    for _ in range(steps):
+        d = job.step()
+    e1.record(); D.barrier()
+    ms = D.max_ms(e0.elapsed_time(e1))
+    t = job.tile
+    rec = {"config": "configs[3]: one %dx%d image, %d classes, column strips of %d px + %d px halo per interior side (local width "
+                     "%d) over %d GPU(s); per step: %s" % (W, H, K, W // D.world, tiled.HALO if D.world > 1 else 0, t.local_w,
+                                                           D.world, job.describe_exchange()),
+           "scaling": "strong", "n_gpus": D.world, "value": steps / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms / steps,
+           "steps": steps, "bytes_exchanged_per_step": job.exchange_bytes(), "final_total_loss": float(d["Total loss"]),
+           "first_iteration_losses": first}
+    if check_parity and D.world > 1:
+        # the N-rank loss dictionary of iteration 0 against the single-device evaluation of the whole image (rank 0)
+        ok, worst = True, 0.0
+        if D.rank == 0:
+            single = tiled.TiledStyleTransfer(content, style, hp, cm, sm, weights, 0, 1, reduce_sum=lambda t: None,
+                                              gather=lambda s: [s])
+            ref = {k: float(v) for k, v in single.step().items()}
+            worst = max(abs(first[k] - ref[k]) / max(abs(ref[k]), 1e-300) for k in ref if k != "NIMA loss")
+            ok = worst <= 2e-5
+            rec["parity_vs_single_device"] = {"iteration": 0, "max_rel_loss_diff": worst, "tolerance": 2e-5, "ok": ok,
+                                              "single_device_losses": ref}
+            del single
+        torch.cuda.empty_cache()
+    del job
+    torch.cuda.empty_cache()
+    return rec
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# our arm
+# ----------------------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    D = Dist()
+    world, rank, local = D.world, D.rank, D.local
+    synth, st, vggm, lib = mod("synth"), mod("style_transfer"), mod("components.VGG19.model"), mod("_lib")
+    S, K = args.size, args.classes
+    hp = hyper(args.tv_weight)
+    ext = vggm.StyleContentModel(st.CONTENT_LAYERS, st.STYLE_LAYERS, shape=(None, None, 3), weights=synth.vgg_weights())
+    loss, opt, content, content_h = build_pair(ext, S, K, hp, (2 * rank, 2 * rank + 1, 9 + rank, 10 + rank), pinned=True)
     x = content.clone()
 
     # launches per step (eager), then the replayable graph
@@ -239,39 +629,31 @@ def run_ours(args):
     x.copy_(content); opt._slots.m.zero_(); opt._slots.v.zero_(); opt._slots.state.zero_()
     step = st.make_train_step(ext, loss, opt, use_cuda_graph=True)
 
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
     for _ in range(max(args.warmup, 3)):
         step(x)
     sampler = ClockSampler(local)
-    barrier()
+    D.barrier()
     if rank == 0:
         sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
+    D.barrier()
     e0.record()
     for _ in range(args.steps):
         d = step(x)
     e1.record()
-    barrier()
-    ms = torch.tensor([e0.elapsed_time(e1)], device="cuda")
-    if world > 1:
-        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-    total_ms = float(ms)
+    D.barrier()
+    total_ms = D.max_ms(e0.elapsed_time(e1))
     clocks = sampler.stop() if rank == 0 else None
     final_total = float(d["Total loss"])
 
     # e2e: image starts and ends in pinned host memory every step; losses read back every step
     host_img = content_h.clone().pin_memory()
-    host_loss = torch.empty(5, dtype=torch.float32).pin_memory()
+    host_loss = torch.empty(loss._out.numel(), dtype=torch.float32).pin_memory()
     x.copy_(content); opt._slots.m.zero_(); opt._slots.v.zero_(); opt._slots.state.zero_()
     for _ in range(3):
         x.copy_(host_img, non_blocking=True); step(x); host_img.copy_(x, non_blocking=True)
         host_loss.copy_(loss._out, non_blocking=True); torch.cuda.current_stream().synchronize()
-    barrier()
+    D.barrier()
     t0 = time.perf_counter(); e0.record()
     for _ in range(args.steps):
         x.copy_(host_img, non_blocking=True)
@@ -279,176 +661,130 @@ def run_ours(args):
         host_img.copy_(x, non_blocking=True)
         host_loss.copy_(loss._out, non_blocking=True)
         torch.cuda.current_stream().synchronize()
-    e1.record(); barrier()
-    ms2 = torch.tensor([e0.elapsed_time(e1)], device="cuda")
-    if world > 1:
-        dist.all_reduce(ms2, op=dist.ReduceOp.MAX)
-    e2e_ms = float(ms2)
+    e1.record(); D.barrier()
+    e2e_ms = D.max_ms(e0.elapsed_time(e1))
     wall_e2e = time.perf_counter() - t0
 
     out = None
     if rank == 0:
-        hbm, tf_burst, tf_sus, which = peaks()
-        flush = torch.empty(512 << 20, dtype=torch.uint8, device="cuda")
-        # --- dominant kernel family: 3x3 convolutions, one launch per layer, timed alone with L2 flushed
-        fwd, bwd = conv_flops(S)
-        A = ext._loop
-        tot_f, tot_t, n_launch = 0.0, 0.0, 0
-        scratch = torch.empty(A.acts[0].numel(), dtype=torch.float32, device="cuda")
-        stream = lib.stream_ptr()
-        for i, h, cin, cout, f in fwd:
-            src = x if i == 0 else (A.pools[[1, 3, 7, 11].index(i - 1)] if (i - 1) in (1, 3, 7, 11) else A.acts[i - 1])
-            # the input's scale slot is the one the step's own forward pass left behind (max|conv i-1 output|)
-            slot = ext.vgg.act_absmax_ptr(i - 1) if i > 0 else None
-            t = time_launches(lambda: lib.check(lib.lib().adpst_vgg_conv_forward(ext.vgg._h, i, lib.ptr(src), h, h,
-                                                                                 lib.ptr(scratch), slot, stream)), flush, 3)
-            tot_f += f; tot_t += t; n_launch += 1
-        for i, h, cin, cout, f in bwd:
-            slot = ext.vgg.act_absmax_ptr(i)
-            t = time_launches(lambda: lib.check(lib.lib().adpst_vgg_conv_dgrad(ext.vgg._h, i, lib.ptr(A.acts[i]), h, h,
-                                                                               lib.ptr(scratch), slot, stream)), flush, 3)
-            tot_f += f; tot_t += t; n_launch += 1
-        conv_tflops = tot_f / (tot_t * 1e-3) / 1e12
-        # The reference computes these convolutions in float32 (1e-5 parity): the tensor-core kernel forms every product from
-        # 3 FP16 MMAs (hi*hi + hi*lo + lo*hi, power-of-two scaled, fp32 accumulation), which run at the bf16 rate, so the
-        # ceiling for this arithmetic is peak_bf16 / 3; `frac` is still quoted against the measured bf16 peak, as the
-        # contract asks.
-        roofline = {"kernel": "conv3x3_tc_kernel: persistent tcgen05 3xFP16 implicit GEMM, TMA-fed, A operand in TMEM (12 forward "
-                              "+ 12 data-gradient launches per step; block1_conv1 forward is a CUDA-core kernel)", "bound": "tensor",
-                    "achieved": conv_tflops, "peak": tf_sus, "unit": "TFLOP/s", "frac": conv_tflops / tf_sus,
-                    # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch (block3_conv2 forward: 67 MB in, 67 MB out,
-                    # 2.4 MB of weights) from the ncu --set full capture summarised in profiles/r1_prof_conv_summary.csv
-                    "traffic": 91.9e6, "traffic_of": "block3_conv2 forward launch, ncu capture in profiles/ (algorithmic: 136.6 MB; "
-                                                     "part of the output is still in L2 when the kernel ends)",
-                    "peak_source": which + " bf16 dense, sustained (kernel timed inside a long step)",
-                    "flops_per_launch_avg": tot_f / n_launch, "ms_per_launch_avg": tot_t / n_launch,
-                    "share_of_step": tot_t / (total_ms / args.steps),
-                    "fp32_accurate_ceiling": {"what": "3xFP16: peak_bf16 / 3 (MMAs per product)",
-                                              "peak": tf_sus / 3.0, "frac": conv_tflops / (tf_sus / 3.0)},
-                    "note": "algorithmic FLOPs (2*h*w*9*Cin*Cout per layer); issued tensor FLOPs are 3x that"}
-        # --- Laplacian mat-vec (fused x^T L x and 2Lx), 36 B/px algorithmic
-        # L2 is kept cold by rotating over enough independent (operator, x, y) sets to exceed it (each set is 36 B/px)
-        nsets = max(2, int(160e6 // (36 * S * S)) + 1)
-        xs = x.reshape(-1, 3)
-
-        def lap_calls(compute_dtype):
-            calls = []
-            for j in range(nsets):
-                op = v2.MattingLaplacian(torch.roll(content[0], j, 0).contiguous(), epsilon=1e-7, storage_dtype=torch.float32,
-                                         compute_dtype=compute_dtype)
-                xj, yj, qj = torch.roll(xs, j, 0).contiguous(), torch.empty_like(xs), torch.zeros(1, dtype=torch.float64, device="cuda")
-                calls.append(lambda op=op, xj=xj, yj=yj, qj=qj: op._op.apply3(xj, want_y=True, want_quad=True, y_scale=2e4,
-                                                                               out=yj, quad_out=qj))
-            return calls
-        t_lx = time_rotating(lap_calls(torch.float64))
-        lx_gbs = 36.0 * S * S / (t_lx * 1e-3) / 1e9
-        t_lx32 = time_rotating(lap_calls(torch.float32))
-        # The quoted roofline is HBM (36 B/px), as the metric asks; what actually bounds the kernel is the float64 pipe:
-        # ~250 float64 lane-operations per pixel (halo included) against 64 lanes/clk/SM.
-        f64_floor_ms = 250.0 * S * S / (64.0 * 148 * 1.965e9) * 1e3
-        roofline_lx = {"kernel": "lap_march3_kernel (float32 I/O, float64 arithmetic: the path Loss uses)", "bound": "hbm",
-                       "achieved": lx_gbs, "peak": hbm, "unit": "GB/s", "frac": lx_gbs / hbm,
-                       # dram bytes of one 2048x2048 launch (ncu capture in profiles/r1_prof_lap_summary.csv; 151 MB algorithmic)
-                       "traffic": 123.8e6, "traffic_of": "2048x2048 launch, ncu capture in profiles/",
-                       "peak_source": which + " copy bandwidth", "bytes_per_launch": 36 * S * S, "ms_per_launch": t_lx,
-                       "l2": "%d independent operator/x/y sets (%.0f MB) rotated, calls queued back to back" % (nsets, nsets * 36e-6 * S * S),
-                       "float64_pipe_floor": {"what": "250 float64 lane-ops/px at 64 lanes/clk/SM x 148 SMs x 1.965 GHz",
-                                              "ms_per_launch": f64_floor_ms, "frac_of_floor": f64_floor_ms / t_lx},
-                       "float32_arithmetic_variant": {"achieved": 36.0 * S * S / (t_lx32 * 1e-3) / 1e9,
-                                                      "frac": 36.0 * S * S / (t_lx32 * 1e-3) / 1e9 / hbm,
-                                                      "ms_per_launch": t_lx32}}
-        del flush, scratch
         value = world * args.steps / (total_ms * 1e-3)
         e2e = world * args.steps / (e2e_ms * 1e-3)
         nbytes = x.numel() * 4
         out = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32 (VGG/Gram: float32-accurate 3xFP16 tensor-core products, fp32 accumulation; Adam f32) + f64 (Laplacian arithmetic)",
-            "data": "synthetic",
-            "config": {"workload": "configs[1]: one %dx%d content/style pair per GPU, %d semantic classes, content+masked-Gram "
-                                   "style+photorealism loss, gradient, Adam+clip; matting_v2 eps=1e-7 r=1; random-init VGG19"
-                                   % (S, S, K),
+            "dtype": DTYPE, "data": "synthetic",
+            "config": {"workload": workload_string(S, K, args.tv_weight),
                        "pairs": world, "parallelism": "independent pairs, one per GPU, no collective",
                        "l2": "per-step working set (1.2 GB of activations) exceeds the 126 MB L2; per-kernel timings flush L2",
                        "cuda_graph": True},
-            "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": nbytes, "d2h_bytes_per_step": nbytes + 20,
+            "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": nbytes, "d2h_bytes_per_step": nbytes + 4 * loss._out.numel(),
                     "ms_per_step": e2e_ms / args.steps, "wall_ms_per_step": 1e3 * wall_e2e / args.steps},
             "gpu_launches": launches_per_step * args.steps, "gpu_launches_per_step": launches_per_step,
-            "clocks": clocks, "roofline": roofline, "roofline_lx": roofline_lx,
-            "final_total_loss": final_total,
+            "clocks": clocks, "final_total_loss": final_total,
         }
-    if world > 1:
-        dist.barrier()
-        dist.destroy_process_group()
+        out["roofline"] = conv_roofline(ext, x, S, total_ms / args.steps)
+        out["roofline_lx"] = lx_roofline(S, content)
+        if world == 1 and not args.no_parity:
+            out["parity"] = parity_check(ext, loss, content, S, K, args.tv_weight)
+    del step, eager
+    torch.cuda.empty_cache()
+
+    if not args.no_extras:
+        extras = {}
+        if rank == 0:
+            extras["roofline_lx_sweep"] = lx_sweep()
+        torch.cuda.empty_cache()
+        D.barrier()
+        rec = pairs_record(D, {"ext": ext}, 64, 512, 4, args.steps, args.tv_weight)
+        if rank == 0:
+            extras["pairs_64x512"] = rec
+        del loss, opt
+        torch.cuda.empty_cache()
+        D.barrier()
+        rec = tiled_record(D, 2160, 3840, K, max(3, min(args.steps, 10)), 3, args.tv_weight)
+        if rank == 0:
+            extras["tiled_4k"] = rec
+            out.update(extras)
+    D.close()
     if rank == 0:
         if world == 1 and not args.no_cpu_baseline:
-            out["cpu_baseline"] = cpu_baseline(S, K)
+            out["cpu_baseline"] = cpu_baseline(S, K, args.tv_weight)
         print(json.dumps(out))
+        p = out.get("parity")
+        if p is not None and not p["ok"]:
+            sys.stderr.write("PARITY FAILURE: %s\n" % json.dumps(p))
+            sys.exit(3)
+        tp = out.get("tiled_4k", {}).get("parity_vs_single_device")
+        if tp is not None and not tp["ok"]:
+            sys.stderr.write("TILED PARITY FAILURE: %s\n" % json.dumps(tp))
+            sys.exit(4)
 
 
-def cpu_baseline(size, K):
-    """Oracle port on the host cores: bounded sample (about 10-30 s of CPU work)."""
-    import torch
-    st = cpu_port_state(size, K)
-    t0 = time.perf_counter(); st.train_step(); first = time.perf_counter() - t0
-    n = max(1, min(3, int(20.0 / max(first, 1e-3))))
-    t0 = time.perf_counter()
-    for _ in range(n):
-        st.train_step()
-    dt = time.perf_counter() - t0
-    return {"value": n / dt, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port", "host_cpus": os.cpu_count(),
-            "sample": "%d iterations at %dx%d, K=%d after 1 warm-up (torch-CPU float32 VGG/Gram + float64 matting_v2 port "
-                      "of the reference step; TensorFlow itself is not installable here)" % (n, size, size, K)}
+# ----------------------------------------------------------------------------------------------------------------
+# single-config modes
+# ----------------------------------------------------------------------------------------------------------------
+def run_pairs(args):
+    D = Dist()
+    rec = pairs_record(D, {}, args.pairs, args.pair_size, args.pair_classes, max(args.steps, 2), args.tv_weight)
+    if D.rank == 0:
+        rec.update({"metric": "adam_iters_per_sec_%d_pairs_%dx%d" % (args.pairs, args.pair_size, args.pair_size),
+                    "steps": args.steps, "warmup": 1, "higher_is_better": True, "vs_baseline": None, "dtype": DTYPE, "data": "synthetic"})
+        print(json.dumps(rec))
+    D.close()
 
 
 def run_tiled(args):
-    """BASELINE configs[3]: ONE 3840x2160 image, column strips over N GPUs (tiled.py): overlapped halos instead of
-    per-layer exchange, NCCL all-reduce of the Gram partials, NCCL all-gather of the updated strips.  Strong scaling."""
+    D = Dist()
+    rec = tiled_record(D, args.tiled_h, args.tiled_w, args.classes, args.steps, args.warmup, args.tv_weight)
+    if D.rank == 0:
+        rec.update({"metric": "adam_iters_per_sec_%dx%d_spatially_tiled" % (args.tiled_w, args.tiled_h), "warmup": max(args.warmup, 3),
+                    "higher_is_better": True, "vs_baseline": None, "dtype": DTYPE, "data": "synthetic"})
+        print(json.dumps(rec))
+    D.close()
+
+
+def run_lx_sweep(args):
+    D = Dist()
+    if D.rank == 0:
+        print(json.dumps(lx_sweep()))
+    D.close()
+
+
+def run_config0(args):
+    """BASELINE configs[0]: 512x512, K = 4, matting_v2 (eps 1e-7, r 1), 100 Adam iterations; GPU vs the CPU port, PSNR."""
+    import numpy as np
     import torch
-    import torch.distributed as dist
-    world = int(os.environ.get("WORLD_SIZE", "1")); rank = int(os.environ.get("RANK", "0")); local = int(os.environ.get("LOCAL_RANK", "0"))
-    torch.cuda.set_device(local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    synth = importlib.import_module(PKG + ".synth"); tiled = importlib.import_module(PKG + ".tiled")
-    sem = importlib.import_module(PKG + ".components.semantic_merge")
-    H, W, K = args.tiled_h, args.tiled_w, args.classes
-    hp = hyper(None)
-    content, style = synth.image(H, W, 0), synth.image(H, W, 1)
-    cm = sem.mask_for_tf(sem.extract_segmentation_masks(synth.label_image(H, W, K, 9, cell=64)))
-    sm = sem.mask_for_tf(sem.extract_segmentation_masks(synth.label_image(H, W, K, 10, cell=64)))
-    if world > 1:
-        job = tiled.TiledStyleTransfer(content, style, hp, cm, sm, synth.vgg_weights(), rank, world)
-    else:
-        job = tiled.TiledStyleTransfer(content, style, hp, cm, sm, synth.vgg_weights(), 0, 1, reduce_sum=lambda t: None,
-                                       gather=lambda s: [s])
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-    for _ in range(max(args.warmup, 3)):
-        d = job.step()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier(); e0.record()
-    for _ in range(args.steps):
-        d = job.step()
-    e1.record(); barrier()
-    ms = torch.tensor([e0.elapsed_time(e1)], device="cuda")
-    if world > 1:
-        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-    if rank == 0:
-        t = job.tile
-        print(json.dumps({"metric": "adam_iters_per_sec_%dx%d_spatially_tiled" % (W, H), "value": args.steps / (float(ms) * 1e-3),
-                          "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
-                          "ms_per_step": float(ms) / args.steps, "higher_is_better": True, "scaling": "strong",
-                          "vs_baseline": None, "dtype": "f32 (float32-accurate 3xFP16 tensor-core products) + f64 (Laplacian arithmetic)", "data": "synthetic",
-                          "config": {"workload": "configs[3]: one %dx%d image, %d classes, column strips of %d px + %d px halo per "
-                                                 "interior side (local width %d), Gram all-reduce + strip all-gather per step"
-                                                 % (W, H, K, W // world, tiled.HALO, t.local_w)},
-                          "final_total_loss": float(d["Total loss"])}))
-    if world > 1:
-        dist.barrier(); dist.destroy_process_group()
+    D = Dist()
+    if D.rank == 0:
+        st, vggm, synth = mod("style_transfer"), mod("components.VGG19.model"), mod("synth")
+        S, K, iters = 512, 4, 100
+        hp = hyper(0.0)
+        ext = vggm.StyleContentModel(st.CONTENT_LAYERS, st.STYLE_LAYERS, shape=(None, None, 3), weights=synth.vgg_weights())
+        loss, opt, content, _ = build_pair(ext, S, K, hp, (0, 1, 9, 10))
+        step = st.make_train_step(ext, loss, opt, use_cuda_graph=True)
+        x = content.clone()
+        step(x); torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(iters - 1):
+            d = step(x)
+        e1.record(); torch.cuda.synchronize()
+        gpu_ms = e0.elapsed_time(e1) / (iters - 1)
+        cores = host_threads()
+        ora = cpu_port_state(S, K, 0.0)
+        t0 = time.perf_counter()
+        for _ in range(iters):
+            do = ora.train_step()
+        cpu_s = (time.perf_counter() - t0) / iters
+        mse = float(((x.cpu().double() - ora.image.double()) ** 2).mean())
+        print(json.dumps({"metric": "configs[0]: 512x512 pair, 4 classes, matting_v2 eps=1e-7 r=1, 100 Adam iterations",
+                          "gpu_ms_per_iteration": gpu_ms, "gpu_iters_per_sec": 1e3 / gpu_ms,
+                          "cpu_port_s_per_iteration": cpu_s, "cpu_port_iters_per_sec": 1.0 / cpu_s, "cpu_cores": cores,
+                          "speedup": cpu_s * 1e3 / gpu_ms, "psnr_db_after_100_iterations": 10 * np.log10(1.0 / max(mse, 1e-30)),
+                          "last_total_loss": {"gpu": float(d["Total loss"]), "cpu_port": do["Total loss"]},
+                          "cpu_kind": "port (torch-CPU float32 VGG/Gram + float64 matting_v2; TF not installable)"}))
+    D.close()
 
 
 def main():
@@ -459,15 +795,31 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--size", type=int, default=1024)
     ap.add_argument("--classes", type=int, default=8)
+    ap.add_argument("--tv-weight", dest="tv_weight", type=float, default=1.0,
+                    help="weight of the TV term (extension named by the north star / configs[1]); 0 = the reference's loss")
     ap.add_argument("--no-cpu-baseline", dest="no_cpu_baseline", action="store_true")
-    ap.add_argument("--tiled", action="store_true", help="configs[3]: one large image tiled spatially over the GPUs")
+    ap.add_argument("--no-parity", dest="no_parity", action="store_true")
+    ap.add_argument("--no-extras", dest="no_extras", action="store_true",
+                    help="skip the configs[2], [3], [4] records (roofline_lx_sweep, pairs_64x512, tiled_4k)")
+    ap.add_argument("--pairs", type=int, default=0, help="configs[2] only: this many independent pairs over the ranks")
+    ap.add_argument("--pair-size", dest="pair_size", type=int, default=512)
+    ap.add_argument("--pair-classes", dest="pair_classes", type=int, default=4)
+    ap.add_argument("--tiled", action="store_true", help="configs[3] only: one large image tiled spatially over the GPUs")
     ap.add_argument("--tiled-h", dest="tiled_h", type=int, default=2160)
     ap.add_argument("--tiled-w", dest="tiled_w", type=int, default=3840)
+    ap.add_argument("--lx-sweep", dest="lx_sweep", action="store_true", help="configs[4] only")
+    ap.add_argument("--config", type=int, default=None, help="--config 0: configs[0] (512x512, 100 iterations, PSNR vs CPU port)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
+    elif args.config == 0:
+        run_config0(args)
+    elif args.pairs > 0:
+        run_pairs(args)
     elif args.tiled:
         run_tiled(args)
+    elif args.lx_sweep:
+        run_lx_sweep(args)
     else:
         run_ours(args)
 

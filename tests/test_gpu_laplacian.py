@@ -189,3 +189,13 @@ def test_v2_matches_reference_code_golden(tag):
     if r == 1:
         np.testing.assert_allclose(op.means.cpu().numpy().reshape(g["means"].shape), g["means"], rtol=0, atol=1e-12)
         np.testing.assert_allclose(op.delta_inv.cpu().numpy().reshape(g["delta_inv"].shape), g["delta_inv"], rtol=1e-7)
+
+
+def test_benchmark_mirror_runs():
+    """benchmark.py of the reference (:11-30): v2 (linear operator) vs v3 (explicit matrix) preprocessing sweep."""
+    bm = importlib.import_module(PKG_NAME + ".benchmark")
+    assert (bm.eps, bm.r, bm.n_iters, bm.repeats) == (1e-5, 1, 10, 5)
+    out = bm.run(sizes=[(20, 20), (33, 50)], repeat=2, verbose=False)
+    assert out["sizes"] == ["20x20", "33x50"]
+    for key in ("linear_operator_v2", "matrix_v3"):
+        assert len(out[key]["mean_s"]) == 2 and all(t > 0 for t in out[key]["mean_s"])

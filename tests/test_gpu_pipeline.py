@@ -334,3 +334,50 @@ def test_nima_weight_is_refused(weights, synth):
     t = {"block4_conv2": torch.zeros(1, 2, 2, 512, device="cuda")}
     with pytest.raises(NotImplementedError):
         lossm.Loss(t, {}, _args(nima_weight=1e5))
+
+
+def test_script_main_with_segmentation_files(tmp_path, synth, monkeypatch, capsys):
+    """python style_transfer.py end to end (reference :207-384): *_seg.png mask files -> extract_segmentation_masks ->
+    mask_for_tf, meta.json, loss printing, per-iteration scalars, intermediate and best image; and the same run through
+    the classes directly gives the same losses."""
+    import json
+    import cv2
+    st = _m("style_transfer")
+    sem = _m("components.semantic_merge")
+    H, W, K = 48, 64, 3
+    monkeypatch.chdir(tmp_path)
+    content, style = synth.smooth_image(H, W, 11), synth.smooth_image(H, W, 12)
+    cv2.imwrite("content.png", (content[0] * 255).round().astype(np.uint8)[:, :, ::-1])
+    cv2.imwrite("style.png", (style[0] * 255).round().astype(np.uint8)[:, :, ::-1])
+    (tmp_path / "raw_seg").mkdir()
+    segc, segs = synth.label_image(H, W, K, 9, cell=16), synth.label_image(H, W, K, 10, cell=16)
+    cv2.imwrite("raw_seg/content_seg.png", segc)
+    cv2.imwrite("raw_seg/style_seg.png", segs)
+    w = synth.vgg_weights(seed=5)
+    np.savez("vgg.npz", **{n + "/kernel": k for n, (k, b) in w.items()}, **{n + "/bias": b for n, (k, b) in w.items()})
+    argv = ["-c", "content.png", "-s", "style.png", "-o", "out.png", "--iter", "6", "--matting_window_radius", "1",
+            "--matting_epsilon", "1e-7", "--vgg_weights", "vgg.npz", "--experiment_name", "t", "--use_masks",
+            "--print_loss_interval", "2", "--intermediate_result_interval", "3"]
+    best, hist = st.main(argv)
+    out = capsys.readouterr().out
+    assert "Load segmentation from files." in out and out.count("[Iter ") == 3 and "Average time per epoch" in out
+    exp = tmp_path / "experiments" / "t"
+    meta = json.loads((exp / "meta.json").read_text())
+    assert meta["load_segmentation"] is True and meta["iter"] == 6 and meta["content"] == "content.png"
+    assert sorted(p.name for p in (exp / "iter").iterdir()) == ["iter_3.png", "iter_6.png"]
+    lines = [json.loads(l) for l in (tmp_path / "logs" / "t" / "scalars.jsonl").read_text().splitlines()]
+    assert [l["step"] for l in lines] == list(range(1, 7)) and "Photorealism regualarization" in lines[0]
+    assert len(hist) == 6 and tuple(best.shape) == (1, H, W, 3)
+    saved = cv2.imread(str(exp / "out.png"))[:, :, ::-1]
+    assert np.array_equal(saved, st.tensor_to_image(best).cpu().numpy())
+    # the *_seg.png files are rewritten from the extracted masks (reference :261-264) without changing them
+    assert np.array_equal(cv2.imread("raw_seg/content_seg.png"), segc)
+    # same run through the classes, masks straight from the label images: identical first-iteration losses
+    a = st.build_parser().parse_args(argv)
+    cm = sem.mask_for_tf(sem.extract_segmentation_masks(segc)); sm = sem.mask_for_tf(sem.extract_segmentation_masks(segs))
+    _, hist2 = st.style_transfer(st.load_image("content.png"), st.load_image("style.png"), a, cm, sm, vgg_weights="vgg.npz")
+    for name, v in hist[0].items():
+        assert abs(v - hist2[0][name]) <= 1e-6 * abs(v) + 1e-12, name
+    # without --use_masks the script behaves like the reference as shipped (masks commented out, :308-309): K = 1
+    _, hist3 = st.main([x for x in argv if x != "--use_masks"])
+    assert abs(hist3[0]["Style loss"] - hist[0]["Style loss"]) > 1e-6 * abs(hist[0]["Style loss"])

@@ -40,12 +40,54 @@ def test_synthetic_inputs_are_deterministic(synth):
 
 
 def test_flag_defaults_follow_the_reference():
+    from pathlib import Path
     st = importlib.import_module(PKG_NAME + ".style_transfer")
-    a = st.build_parser().parse_args([])
-    # style_transfer.py:143-183 of the reference
-    assert (a.iter, a.adam_lr, a.matting_window_radius, a.matting_epsilon) == (1000, 0.1, 3, 1e-5)
-    assert (a.content_weight, a.style_weight, a.regularization_weight) == (1, 100, 10 ** 4)
+    a = vars(st.build_parser().parse_args([]))
+    # every flag of style_transfer.py:126-205 of the reference with its default; nima_weight is the one
+    # deliberate deviation (reference 1e5; the NIMA term is not built, so 0)
+    ref = dict(content_image="blanc.jpg", style_image="bear.jpeg", output_image="result.jpg", dtype="float32", init="content",
+               iter=1000, similarity_metric="li", content_weight=1, style_weight=1e2, regularization_weight=1e4,
+               adam_lr=1e-1, adam_beta1=0.9, adam_beta2=0.999, adam_epsilon=1e-08, matting_epsilon=1e-5,
+               matting_window_radius=3, semantic_thresh=0.5, logs_dir=Path("logs"), results_dir=Path("experiments"),
+               seg_dir=Path("raw_seg"), gpu="0", experiment_name=None, intermediate_result_interval=20, print_loss_interval=10)
+    for k, v in ref.items():
+        assert a[k] == v, k
+    assert a["nima_weight"] == 0
+    assert set(a) - set(ref) == {"nima_weight", "vgg_weights", "matting", "use_masks", "tv_weight"}     # the extensions
     assert st.CONTENT_LAYERS == ["block4_conv2"] and st.STYLE_LAYERS == ["block%d_conv1" % i for i in range(1, 6)]
+    with pytest.raises(SystemExit):
+        st.main(["--nima_weight", "1e5"])
+
+
+def test_script_helpers_follow_the_reference(tmp_path):
+    """tensor_to_image truncation (style_transfer.py:78), change_filename (:82-94), meta.json keys and order (:97-120),
+    load_image = decode + convert_image_dtype (:50-59)."""
+    import json
+    import cv2
+    import torch
+    st = importlib.import_module(PKG_NAME + ".style_transfer")
+    t = torch.tensor([[[[0.0, 0.999 / 255, 1.0 / 255], [0.5, 254.999 / 255, 1.0]]]], dtype=torch.float32)
+    u8 = st.tensor_to_image(t)
+    assert u8.dtype == torch.uint8 and tuple(u8.shape) == (1, 2, 3)
+    assert u8.flatten().tolist() == [0, 0, 1, 127, 254, 255]                 # truncation, not rounding
+    assert st.change_filename('.', 'image.png', '_seg') == './image_seg.png'
+    assert st.change_filename('raw_seg', 'blanc.jpg', '_seg', '.png') == 'raw_seg/blanc_seg.png'
+    args = st.build_parser().parse_args(["--iter", "7", "-c", "a.png", "-s", "b.png"])
+    meta = st.write_metadata(args, True, tmp_path)
+    on_disk = json.loads((tmp_path / "meta.json").read_text())
+    assert on_disk == meta
+    assert list(meta) == ["init", "iter", "content", "style", "content_weight", "style_weight", "regularization_weight",
+                          "nima_weight", "semantic_thresh", "similarity_metric", "load_segmentation", "adam"]
+    assert list(meta["adam"]) == ["learning_rate", "beta1", "beta2", "epsilon"] and meta["iter"] == 7
+    rgb = np.random.default_rng(0).integers(0, 256, (5, 7, 3), dtype=np.uint8)
+    cv2.imwrite(str(tmp_path / "x.png"), rgb[:, :, ::-1])
+    img = st.load_image(tmp_path / "x.png", "float32")
+    assert img.shape == (1, 5, 7, 3) and img.dtype == np.float32
+    assert np.array_equal(img[0], rgb.astype(np.float32) * np.float32(1.0 / 255.0))
+    st.save_image(torch.as_tensor(rgb), tmp_path / "y.png")
+    assert np.array_equal(cv2.imread(str(tmp_path / "y.png"))[:, :, ::-1], rgb)
+    with pytest.raises(FileNotFoundError):
+        st.load_image(tmp_path / "missing.png")
 
 
 _WORKER = r"""
@@ -105,3 +147,67 @@ def test_tile_geometry():
         owned[tr.own_lo:tr.own_hi] += 1
         assert tr.own_lo - tr.ext_lo in (0, tiled.HALO) and tr.ext_hi - tr.own_hi in (0, tiled.HALO)
     assert (owned == 1).all() and tiled.HALO >= 2 * 78 and tiled.HALO % 16 == 0
+
+
+_TILED_WORKER = r"""
+import os, sys, json, importlib
+sys.path.insert(0, %r)
+import torch, torch.distributed as dist
+dist.init_process_group("gloo", rank=int(os.environ["RANK"]), world_size=int(os.environ["WORLD_SIZE"]))
+rank, world = dist.get_rank(), dist.get_world_size()
+tiled = importlib.import_module(%r + ".tiled")
+H, W = 6, 16 * 12 * world                     # strips of 192 px >= HALO
+glob = torch.arange(H * W * 3, dtype=torch.float32).reshape(1, H, W, 3)
+# the rank-local object without its GPU members: exchange_borders / refresh_halo / own_strip only touch these attributes
+job = object.__new__(tiled.TiledStyleTransfer)
+job.rank, job.world = rank, world
+job.tile = tiled.Tile(W, rank, world)
+job._bytes = {"allreduce": 0, "halo": 0}
+t = job.tile
+job.image = glob[:, :, t.ext_lo:t.ext_hi].clone()
+lo, hi = t.own_lo - t.ext_lo, t.own_hi - t.ext_lo
+job.image[0, :, :lo] = -1.0                   # stale halos
+job.image[0, :, hi:] = -1.0
+job.image[0, :, lo:hi] += 1000.0 * (rank + 1)  # "updated" own columns
+job.exchange_borders()
+expect = glob[:, :, t.ext_lo:t.ext_hi].clone()
+for r in range(world):
+    a, b = max(r * W // world, t.ext_lo), min((r + 1) * W // world, t.ext_hi)
+    if a < b:
+        expect[0, :, a - t.ext_lo:b - t.ext_lo] += 1000.0 * (r + 1)
+ok_halo = bool(torch.equal(job.image, expect))
+# the Gram partials: ONE flat float32 buffer + the float64 accumulator, summed over the ranks
+flat = torch.full((1000,), float(rank + 1)); acc = torch.tensor([1.0, 0.0, 2.0 * rank, 0.5], dtype=torch.float64)
+tiled._gloo_reduce_sum([flat, acc])
+ok_sum = bool((flat == world * (world + 1) / 2).all()) and float(acc[0]) == world and float(acc[2]) == world * (world - 1)
+# configs[2] sharding of bench.py: pair p goes to rank p %% world
+mine = list(range(rank, 64, world))
+allp = [None] * world
+dist.all_gather_object(allp, mine)
+res = [None] * world
+dist.all_gather_object(res, (ok_halo, ok_sum, job._bytes["halo"]))
+if rank == 0:
+    print(json.dumps({"results": res, "pairs": sorted(sum(allp, [])), "halo": tiled.HALO, "H": H}))
+dist.destroy_process_group()
+"""
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_tiled_exchange_protocol_gloo(world, tmp_path):
+    """TiledStyleTransfer's own exchange code over a gloo group (CPU tensors): the point-to-point border exchange fills every
+    halo with the neighbours' updated own columns (middle ranks talk to both sides), the flattened Gram partials and the
+    float64 accumulator are summed, and the configs[2] round-robin covers all 64 pairs exactly once."""
+    import json
+    script = tmp_path / "tiled_worker.py"
+    script.write_text(_TILED_WORKER % (ROOT, PKG_NAME))
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT=str(29540 + world), WORLD_SIZE=str(world))
+    procs = [subprocess.Popen([sys.executable, str(script)], env=dict(env, RANK=str(r)), stdout=subprocess.PIPE,
+                              stderr=subprocess.PIPE, text=True) for r in range(world)]
+    outs = [p.communicate(timeout=180) for p in procs]
+    assert all(p.returncode == 0 for p in procs), outs
+    d = json.loads(outs[0][0].strip().splitlines()[-1])
+    assert d["pairs"] == list(range(64))
+    for r, (ok_halo, ok_sum, sent) in enumerate(d["results"]):
+        assert ok_halo and ok_sum, r
+        sides = (r > 0) + (r < world - 1)
+        assert sent == sides * d["H"] * d["halo"] * 3 * 4
