@@ -9,6 +9,7 @@ LIB_PATH = os.path.join(_HERE, "libadpst.so")
 OK, ERR_INVALID, ERR_CUDA, ERR_UNSUPPORTED = 0, 1, 2, 3
 F32, F64 = 0, 1
 LAP_V2, LAP_V3 = 2, 3
+LAP_KERNEL_AUTO, LAP_KERNEL_DIA, LAP_KERNEL_MATRIX_FREE, LAP_KERNEL_TILE = 0, 1, 2, 3
 VGG_NUM_CONV, VGG_NUM_POOL = 13, 4
 
 
@@ -31,6 +32,8 @@ SIGNATURES = {
     "adpst_laplacian_destroy": (None, [_vp]),
     "adpst_laplacian_matvec": (_i, [_vp, _vp, _vp, _d, _vp, _vp]),
     "adpst_laplacian_set_quadratic_window": (_i, [_vp, _i, _i]),
+    "adpst_laplacian_set_kernel": (_i, [_vp, _i, _vp]),
+    "adpst_laplacian_kernel": (_i, [_vp]),
     "adpst_laplacian_coefficients": (_i, [_vp, _vp, _vp, _vp]),
     "adpst_laplacian_nnz": (_c.c_int64, [_vp]),
     "adpst_laplacian_export_coo": (_i, [_vp, _vp, _vp, _vp, _vp]),

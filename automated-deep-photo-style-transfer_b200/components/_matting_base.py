@@ -20,7 +20,10 @@ class LaplacianHandle:
     """Owns one adpst_laplacian*.  `storage_dtype` is the dtype of image / x / y in HBM, `compute_dtype` the
     arithmetic type of the stencil."""
 
-    def __init__(self, mode, image, epsilon, window_radius, storage_dtype=None, compute_dtype=None):
+    KERNELS = {"auto": _lib.LAP_KERNEL_AUTO, "dia": _lib.LAP_KERNEL_DIA, "matrix_free": _lib.LAP_KERNEL_MATRIX_FREE,
+               "tile": _lib.LAP_KERNEL_TILE}
+
+    def __init__(self, mode, image, epsilon, window_radius, storage_dtype=None, compute_dtype=None, kernel=None):
         _lib.require_cuda()
         img = as_cuda_tensor(image)
         if img.dim() != 3 or img.shape[2] != 3:
@@ -41,6 +44,20 @@ class LaplacianHandle:
                 _lib.dtype_code(self.compute_dtype), _lib.stream_ptr(), ctypes.byref(h)))
         self._h = h
         self._xlx = torch.zeros(1, dtype=torch.float64, device=self.device)
+        if kernel is not None:
+            self.set_kernel(kernel)
+
+    def set_kernel(self, kernel):
+        """'auto' (default: 'dia' for radius 1 with float32 storage, else 'matrix_free'), 'dia' (precomputed 5x5 stencil
+        coefficients, float32 evaluation of L I + L (x - I): the hot path), 'matrix_free' (window statistics recomputed in
+        compute_dtype every call: 1e-9 in float64), 'tile' (shared-memory variant of matrix_free; validation)."""
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.lib().adpst_laplacian_set_kernel(self._h, self.KERNELS[kernel], _lib.stream_ptr()))
+
+    @property
+    def kernel(self):
+        k = int(_lib.lib().adpst_laplacian_kernel(self._h))
+        return {v: n for n, v in self.KERNELS.items()}[k]
 
     def __del__(self):
         h, self._h = getattr(self, "_h", None), None

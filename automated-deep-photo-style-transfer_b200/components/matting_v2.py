@@ -14,11 +14,11 @@ class MattingLaplacian:
     r"""Matting Laplacian of "Fast matting using large kernel matting Laplacian matrices" (He et al.),
     symmetric padding, one window per pixel.  reference: matting_v2.py:11-52 (build), :147-176 (matmul)."""
 
-    def __init__(self, image, epsilon=1e-5, window_radius=1, *, storage_dtype=None, compute_dtype=None):
+    def __init__(self, image, epsilon=1e-5, window_radius=1, *, storage_dtype=None, compute_dtype=None, kernel=None):
         """image: (H,W,3) float64 (script, style_transfer.py:315) or float32 (benchmark.py:25).
         The operator dtype is image.dtype, as in the reference (:24-25).  `storage_dtype` / `compute_dtype`
         are extensions: float32 HBM traffic with float64 arithmetic is what Loss uses on the hot path."""
-        self._op = LaplacianHandle(_lib.LAP_V2, image, epsilon, window_radius, storage_dtype, compute_dtype)
+        self._op = LaplacianHandle(_lib.LAP_V2, image, epsilon, window_radius, storage_dtype, compute_dtype, kernel)
         self.radius = int(window_radius)                                   # :33
         self.size = (self._op.H, self._op.W, 3)                            # :35
         self.window_area = (2 * self.radius + 1) ** 2                      # :44

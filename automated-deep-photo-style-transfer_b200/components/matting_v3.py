@@ -19,11 +19,11 @@ class MattingLaplacian:
     r"""Matting Laplacian of "A closed-form solution to natural image matting" (Levin et al.).
     reference: matting_v3.py:27-39 (constructor), :50-51 (matmul), :61-102 (compute_laplacian)."""
 
-    def __init__(self, image, epsilon=1e-5, window_radius=1, fname=None, *, storage_dtype=None, compute_dtype=None):
+    def __init__(self, image, epsilon=1e-5, window_radius=1, fname=None, *, storage_dtype=None, compute_dtype=None, kernel=None):
         # the reference evaluates compute_laplacian in float64 numpy whatever the image dtype (image.numpy() of a
         # float32 tensor is promoted by np.linalg / einsum only partly); float64 arithmetic is the faithful choice.
         self._op = LaplacianHandle(_lib.LAP_V3, image, epsilon, window_radius, storage_dtype,
-                                   compute_dtype or torch.float64)
+                                   compute_dtype or torch.float64, kernel)
         self.size = (self._op.H, self._op.W, 3)                            # :35
         self.dtype = self._op.operator_dtype
         self._coo = None

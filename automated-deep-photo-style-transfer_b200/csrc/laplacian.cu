@@ -18,6 +18,7 @@
 #include <type_traits>
 
 #include "common.cuh"
+#include "laplacian.cuh"
 
 namespace adpst {
 
@@ -811,16 +812,6 @@ lap_export_coo_kernel(const TIO* __restrict__ img, int64_t* __restrict__ rows, i
 // ---------------------------------------------------------------------------------------------
 // C-ABI
 // ---------------------------------------------------------------------------------------------
-struct adpst_laplacian {
-    int mode, H, W, R, io_dtype, compute_dtype;
-    double eps;
-    void* image = nullptr;       // (H,W,3) io_dtype, owned
-    double* partials = nullptr;  // one per CTA, owned; followed by the "last CTA" ticket counter of the march3 kernel
-    int npartials = 0;
-    bool force_tile_kernel = false;   // validation: use the shared-memory tile kernel for r = 1 as well
-    int q_col_lo = 0, q_col_hi = 0;   // x^T L x restricted to these columns (spatially tiled runs); (0,0) = all
-};
-
 namespace adpst {
 
 // rows per marching warp: enough warps for ~2 waves of 8 warps per SM, at most 64 rows (halo overhead (RW+2)/RW)
@@ -871,7 +862,7 @@ static int launch_march(adpst_laplacian* h, const void* x, void* y, double y_sca
 template <typename TIO, typename TC, int R>
 static int launch_matvec(adpst_laplacian* h, const void* x, void* y, double y_scale, double* xLx, cudaStream_t st) {
     if constexpr (R == 1 && std::is_same<TIO, float>::value) {
-        if (!h->force_tile_kernel) return launch_march<TC>(h, x, y, y_scale, xLx, st);
+        if (h->kernel != ADPST_LAP_KERNEL_TILE) return launch_march<TC>(h, x, y, y_scale, xLx, st);
     }
     using T = LapTile<R>;
     const int qlo = h->q_col_hi > h->q_col_lo ? h->q_col_lo : 0, qhi = h->q_col_hi > h->q_col_lo ? h->q_col_hi : h->W;
@@ -937,7 +928,13 @@ static int launch_export(adpst_laplacian* h, int64_t* rows, int64_t* cols, void*
     } while (0)
 
 static int dispatch_matvec(adpst_laplacian* h, const void* x, void* y, double ys, double* xLx, cudaStream_t st) {
+    if (h->kernel == ADPST_LAP_KERNEL_DIA || (h->kernel == ADPST_LAP_KERNEL_AUTO && h->dia_ready))
+        return dia_matvec(h, static_cast<const float*>(x), static_cast<float*>(y), ys, xLx, st);
     ADPST_LAP_DISPATCH(launch_matvec, h, x, y, ys, xLx, st);
+}
+
+int lap_matrix_free_f64(adpst_laplacian* h, const float* x, float* y, double y_scale, double* xLx, cudaStream_t st) {
+    return launch_march<double>(h, x, y, y_scale, xLx, st);
 }
 static int dispatch_coeffs(adpst_laplacian* h, void* means, void* dinv, cudaStream_t st) {
     ADPST_LAP_DISPATCH(launch_coeffs, h, means, dinv, st);
@@ -980,14 +977,44 @@ int adpst_laplacian_create(int mode, int H, int W, int radius, double epsilon, c
         adpst_laplacian_destroy(h);
         return fail(ADPST_ERR_CUDA, "laplacian_create: %s", cudaGetErrorString(e));
     }
+    if (dia_eligible(h)) {               // r = 1, float32 storage: precompute the 5x5 stencil coefficients (the hot path)
+        const int rc = dia_build(h, as_stream(stream));
+        if (rc != ADPST_OK) {
+            adpst_laplacian_destroy(h);
+            return rc;
+        }
+    }
     *out = h;
     return ADPST_OK;
+}
+
+int adpst_laplacian_set_kernel(adpst_laplacian* h, int kind, adpst_stream_t stream) {
+    using namespace adpst;
+    ADPST_REQUIRE(h != nullptr, "laplacian_set_kernel: NULL handle");
+    ADPST_REQUIRE(kind >= ADPST_LAP_KERNEL_AUTO && kind <= ADPST_LAP_KERNEL_TILE, "laplacian_set_kernel: unknown kernel %d", kind);
+    if (kind == ADPST_LAP_KERNEL_DIA) {
+        if (!dia_eligible(h))
+            return fail(ADPST_ERR_UNSUPPORTED, "laplacian_set_kernel: the diagonal-format kernel needs radius 1 and float32 storage");
+        if (!h->dia_ready) {
+            const int rc = dia_build(h, as_stream(stream));
+            if (rc != ADPST_OK) return rc;
+        }
+    }
+    h->kernel = kind;
+    return ADPST_OK;
+}
+
+int adpst_laplacian_kernel(const adpst_laplacian* h) {
+    if (!h) return -1;
+    if (h->kernel != ADPST_LAP_KERNEL_AUTO) return h->kernel;
+    return h->dia_ready ? ADPST_LAP_KERNEL_DIA : ADPST_LAP_KERNEL_MATRIX_FREE;
 }
 
 void adpst_laplacian_destroy(adpst_laplacian* h) {
     if (!h) return;
     if (h->image) cudaFree(h->image);
     if (h->partials) cudaFree(h->partials);
+    adpst::dia_free(h);
     delete h;
 }
 
@@ -1012,6 +1039,7 @@ int adpst_laplacian_set_quadratic_window(adpst_laplacian* h, int col_lo, int col
     ADPST_REQUIRE(h != nullptr && col_lo >= 0 && col_hi <= h->W && col_lo <= col_hi, "laplacian_set_quadratic_window: bad window");
     h->q_col_lo = col_lo;
     h->q_col_hi = col_hi;
+    h->dia_q_dirty = true;          // the constant I^T L I of the diagonal-format kernel is per window
     return ADPST_OK;
 }
 

@@ -32,6 +32,8 @@ typedef void* adpst_stream_t;
 enum { ADPST_OK = 0, ADPST_ERR_INVALID = 1, ADPST_ERR_CUDA = 2, ADPST_ERR_UNSUPPORTED = 3 };
 enum { ADPST_F32 = 0, ADPST_F64 = 1 };
 enum { ADPST_LAP_V2 = 2, ADPST_LAP_V3 = 3 };
+/* mat-vec kernel of a Laplacian handle: AUTO = DIA when the handle has radius 1 and float32 storage, else MATRIX_FREE */
+enum { ADPST_LAP_KERNEL_AUTO = 0, ADPST_LAP_KERNEL_DIA = 1, ADPST_LAP_KERNEL_MATRIX_FREE = 2, ADPST_LAP_KERNEL_TILE = 3 };
 enum { ADPST_VGG_NUM_CONV = 13, ADPST_VGG_NUM_POOL = 4 };
 
 int adpst_version(void);
@@ -57,6 +59,17 @@ void adpst_laplacian_destroy(adpst_laplacian* h);
  * xLx_dev (may be NULL): device double, receives x^T L x accumulated in float64. */
 int adpst_laplacian_matvec(adpst_laplacian* h, const void* x_dev, void* y_dev, double y_scale,
                            double* xLx_dev, adpst_stream_t stream);
+
+/* Which kernel evaluates L x (all of them are the same operator):
+ *   DIA          (radius 1, float32 storage; the default there): the operator's 5x5 stencil coefficients -- the explicit matrix
+ *                of matting_v3.py:61-102 in diagonal format, 12 float32 planes using symmetry and zero row sums -- and L I are
+ *                precomputed ONCE in float64 when the handle is created; each call evaluates y = L I + L (x - I) in float32
+ *                (2e-7 of max|y| measured; exact at x = I), HBM-bound at 96 B/px;
+ *   MATRIX_FREE  window statistics recomputed from I in every call, arithmetic in compute_dtype (float64: 1e-9);
+ *   TILE         the shared-memory tile variant of MATRIX_FREE (any radius; validation).
+ * adpst_laplacian_kernel returns the kind that will run. */
+int adpst_laplacian_set_kernel(adpst_laplacian* h, int kind, adpst_stream_t stream);
+int adpst_laplacian_kernel(const adpst_laplacian* h);
 
 /* Spatially tiled runs (one image split into column strips with halos): restrict the scalar x^T L x to columns
  * [col_lo, col_hi) of the local strip; y is still produced for every column.  (0,0) restores the full sum. */

@@ -2,8 +2,10 @@
 against the numpy float64 oracle and the reference-generated golden vectors.
 
 Tolerances (north star: 1e-5 relative for Laplacian values and Lx; sparsity pattern bit-exact):
-  float64 arithmetic: 1e-9 of max|y| (generic x), 1e-6 of max|y| when x = I (|y| itself is ~1e-6 of generic)
-  float32 arithmetic (optional fast path, not used by Loss): 1e-4 of max|y| on uniform synthetic images, random x
+  matrix-free kernels, float64 arithmetic: 1e-9 of max|y| (generic x), 1e-6 of max|y| when x = I (|y| itself is ~1e-6 of generic)
+  diagonal-format kernel (radius 1, float32 storage: what Loss runs; coefficients and L I precomputed in float64, evaluation of
+    L I + L (x - I) in float32): 1e-6 of max|y| (measured 2e-7), and as accurate as the float64 kernel at x = I
+  matrix-free float32 arithmetic (validation only): 1e-4 of max|y| on uniform synthetic images, random x
 """
 import importlib
 
@@ -67,15 +69,18 @@ def test_v2_coefficient_fields(synth):
     assert _rel(op.delta_inv.cpu().numpy(), ref.delta_inv) < 1e-8
 
 
-def test_v2_float32_storage_float64_arithmetic_hot_path(synth):
-    """What Loss uses: image/x/y are float32 in HBM, the stencil runs in float64."""
+@pytest.mark.parametrize("kernel", ["dia", "matrix_free"])
+def test_v2_float32_storage_float64_arithmetic_hot_path(kernel, synth):
+    """What Loss uses: image/x/y are float32 in HBM, everything that is ill-conditioned runs in float64: either
+    once per image (diagonal-format kernel, the default) or in every call (matrix-free kernel)."""
     H, W = 48, 80
     for make in (synth.image, synth.smooth_image):
         img32 = make(H, W, 11)[0]
         x32 = synth.image(H, W, 12)[0].reshape(-1, 3)
         ref = matting.V2Operator(img32.astype(np.float64), 1e-7, 1)
         op = _v2().MattingLaplacian(torch.as_tensor(img32).cuda(), epsilon=1e-7, window_radius=1,
-                                    storage_dtype=torch.float32, compute_dtype=torch.float64)
+                                    storage_dtype=torch.float32, compute_dtype=torch.float64, kernel=kernel)
+        assert op._op.kernel == kernel
         for xx in (x32, img32.reshape(-1, 3)):
             want = ref.matmul(xx.astype(np.float64))
             q, y = None, None
@@ -95,10 +100,14 @@ def test_v2_float32_arithmetic_fast_path(synth):
     img32 = synth.image(H, W, 13)[0]
     x32 = synth.image(H, W, 14)[0].reshape(-1, 3)
     ref = matting.V2Operator(img32.astype(np.float64), 1e-7, 1)
-    op = _v2().MattingLaplacian(torch.as_tensor(img32).cuda(), epsilon=1e-7, window_radius=1)   # float32 operator
+    op = _v2().MattingLaplacian(torch.as_tensor(img32).cuda(), epsilon=1e-7, window_radius=1, kernel="matrix_free")   # float32 operator
     y = op.matmul(torch.as_tensor(x32).cuda())
     assert y.dtype == torch.float32
     assert _rel(y.cpu().numpy(), ref.matmul(x32.astype(np.float64))) < 1e-4
+    # a float32 operator as benchmark.py builds it (benchmark.py:25-28) runs the diagonal-format kernel by default
+    op = _v2().MattingLaplacian(torch.as_tensor(img32).cuda(), epsilon=1e-7, window_radius=1)
+    assert op._op.kernel == "dia"
+    assert _rel(op.matmul(torch.as_tensor(x32).cuda()).cpu().numpy(), ref.matmul(x32.astype(np.float64))) < 1e-6
 
 
 def test_matmul_other_column_counts(synth):
@@ -177,11 +186,15 @@ def test_v2_matches_reference_code_golden(tag):
     img, eps, r = g["image"], float(g["eps"]), int(g["r"])
     H, W, _ = img.shape
     scale = np.abs(g["Lx"]).max()
-    for kw in ({}, {"storage_dtype": torch.float32, "compute_dtype": torch.float64}):
+    for kw in ({}, {"storage_dtype": torch.float32, "compute_dtype": torch.float64, "kernel": "matrix_free"},
+               {"storage_dtype": torch.float32, "compute_dtype": torch.float64}):
+        dia = r == 1 and "storage_dtype" in kw and "kernel" not in kw
         op = _v2().MattingLaplacian(torch.as_tensor(img).cuda(), epsilon=eps, window_radius=r, **kw)
+        assert (op._op.kernel == "dia") == dia
         assert tuple(op.shape) == tuple(g["shape"]) and op.radius == r and op.window_area == (2 * r + 1) ** 2
         dt = op._op.operator_dtype if hasattr(op, "_op") else torch.float64
-        for x, ref, tol in ((g["x"], g["Lx"], 1e-9 if not kw else 2e-7), (img.reshape(H * W, 3), g["LI"], 1e-6 if not kw else 2e-6)):
+        for x, ref, tol in ((g["x"], g["Lx"], 1e-9 if not kw else (1e-6 if dia else 2e-7)),
+                            (img.reshape(H * W, 3), g["LI"], 1e-6 if not kw else 2e-6)):
             y = op.matmul(torch.as_tensor(x).to(dt).cuda()).cpu().double().numpy()
             # float32 storage rounds the OUTPUT to float32 (relative 6e-8 of each value); the arithmetic is float64
             assert np.abs(y - ref).max() <= tol * max(np.abs(ref).max(), 1e-30) + (6e-8 * scale if kw else 0.0), (kw, np.abs(y - ref).max())
@@ -189,6 +202,61 @@ def test_v2_matches_reference_code_golden(tag):
     if r == 1:
         np.testing.assert_allclose(op.means.cpu().numpy().reshape(g["means"].shape), g["means"], rtol=0, atol=1e-12)
         np.testing.assert_allclose(op.delta_inv.cpu().numpy().reshape(g["delta_inv"].shape), g["delta_inv"], rtol=1e-7)
+
+
+def _dense(op, H, W):
+    return np.asarray(op.matmul(np.eye(H * W)))
+
+
+@pytest.mark.parametrize("mode", ["v2", "v3"])
+@pytest.mark.parametrize("H,W", [(1, 1), (2, 3), (3, 3), (4, 9), (5, 7), (16, 32), (33, 70), (50, 40)])
+@pytest.mark.parametrize("kind", ["uniform", "smooth", "grey"])
+def test_diagonal_format_kernel_matches_oracle(mode, H, W, kind, synth):
+    """The precomputed 5x5 stencil (what Loss runs): y = L I + L (x - I) against the float64 oracle for generic x, for the
+    first Adam iterate (x = I +- 0.1), for x = I, on uniform / smooth / grey (rank-1 covariance) guide images, including
+    images smaller than the footprint; and x^T L x, whole image and restricted to a column window."""
+    if kind == "uniform":
+        img32 = synth.image(H, W, 40 + H)[0]
+    else:
+        img32 = synth.smooth_image(max(H, 8), max(W, 8), 41 + W)[0][:H, :W]
+        if kind == "grey":
+            img32 = np.repeat(img32[..., :1], 3, -1)
+    img32 = np.ascontiguousarray(img32)
+    eps = 1e-7
+    ref = matting.V2Operator(img32.astype(np.float64), eps, 1) if mode == "v2" else \
+        (matting.V3Operator(img32.astype(np.float64), eps, 1) if H >= 3 and W >= 3 else None)
+    cls = _v2() if mode == "v2" else _v3()
+    op = cls.MattingLaplacian(torch.as_tensor(img32).cuda(), epsilon=eps, window_radius=1, storage_dtype=torch.float32,
+                              compute_dtype=torch.float64)
+    assert op._op.kernel == "dia"
+    rng = np.random.default_rng(H * 100 + W)
+    I = img32.reshape(-1, 3)
+    cases = {"random": rng.random((H * W, 3)).astype(np.float32),
+             "first_adam_step": np.clip(I + 0.1 * np.sign(rng.random((H * W, 3)) - 0.5), 0, 1).astype(np.float32),
+             "identity": I.copy()}
+    for name, xx in cases.items():
+        want = ref.matmul(xx.astype(np.float64)) if ref is not None else np.zeros((H * W, 3))
+        y, q = op.quadratic_form(torch.as_tensor(xx).cuda(), want_y=True, y_scale=3.0)
+        got = y.cpu().numpy().astype(np.float64) / 3.0
+        scale = np.abs(want).max()
+        if name == "identity":
+            # |L I| is ~1e-7: as accurate as the float64 kernel (the reference's own cumsum arithmetic is the limit)
+            assert np.abs(got - want).max() <= 2e-6 * scale + 1e-13, (name, np.abs(got - want).max(), scale)
+        else:
+            assert np.abs(got - want).max() <= 1e-6 * scale + 1e-12, (name, np.abs(got - want).max(), scale)
+        quad = float(np.sum(xx.astype(np.float64) * want))
+        assert abs(float(q) - quad) <= 1e-6 * abs(quad) + 1e-12, (name, float(q), quad)
+    if W >= 8:                                   # the scalar restricted to a column window (spatially tiled runs)
+        xx = cases["first_adam_step"]
+        want = ref.matmul(xx.astype(np.float64)) if ref is not None else np.zeros((H * W, 3))
+        lo, hi = W // 4, W - W // 4
+        op._op.set_quadratic_window(lo, hi)
+        _, q = op.quadratic_form(torch.as_tensor(xx).cuda(), want_y=False)
+        part = float(np.sum((xx.astype(np.float64) * want).reshape(H, W, 3)[:, lo:hi]))
+        assert abs(float(q) - part) <= 1e-6 * abs(part) + 1e-12
+        op._op.set_quadratic_window(0, 0)
+        _, q = op.quadratic_form(torch.as_tensor(xx).cuda(), want_y=False)
+        assert abs(float(q) - float(np.sum(xx.astype(np.float64) * want))) <= 1e-6 * abs(float(np.sum(xx.astype(np.float64) * want))) + 1e-12
 
 
 def test_benchmark_mirror_runs():

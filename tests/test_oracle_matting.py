@@ -77,3 +77,17 @@ def test_v2_restatement_matches_reference_code(tag):
     np.testing.assert_allclose(op.delta_inv, g["delta_inv"], rtol=1e-10, atol=0)
     for x, y in ((g["x"], g["Lx"]), (g["image"].reshape(-1, 3), g["LI"])):
         np.testing.assert_allclose(op.matmul(x), y, rtol=0, atol=1e-9 * max(np.abs(g["Lx"]).max(), 1e-30))
+
+
+def test_operator_is_a_symmetric_5x5_stencil_with_zero_row_sums(synth):
+    """The facts the diagonal-format kernel rests on, checked on the ORACLE (dense matrix of the float64 restatement):
+    L = L^T, footprint 5x5, L 1 = 0 -- for v2 (symmetric padding folds back inside) and v3."""
+    H, W = 9, 11
+    img = synth.smooth_image(16, 16, 3)[0][:H, :W].astype(np.float64)
+    idx = np.arange(H * W)
+    yy, xx = idx // W, idx % W
+    far = (np.abs(yy[:, None] - yy[None, :]) > 2) | (np.abs(xx[:, None] - xx[None, :]) > 2)
+    for op in (matting.V2Operator(img, 1e-7, 1), matting.V3Operator(img, 1e-7, 1)):
+        A = np.asarray(op.matmul(np.eye(H * W)))
+        s = np.abs(A).max()
+        assert np.abs(A - A.T).max() < 1e-9 * s and np.abs(A[far]).max() < 1e-9 * s and np.abs(A.sum(1)).max() < 1e-9 * s
