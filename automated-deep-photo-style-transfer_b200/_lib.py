@@ -50,6 +50,7 @@ SIGNATURES = {
     "adpst_vgg_conv_dgrad": (_i, [_vp, _i, _vp, _i, _i, _vp, _vp, _vp]),
     "adpst_vgg_backward": (_i, [_vp, _i, _i, _pp, _pp, _pp, _i, _vp, _vp, _vp, _vp]),
     "adpst_resize_bilinear": (_i, [_vp, _i, _i, _vp, _i, _i, _vp]),
+    "adpst_resize_bilinear_batch": (_i, [_vp, _i, _i, _i, _vp, _i, _i, _vp]),
     "adpst_gram_workspace_bytes": (_sz, [_i, _i, _i]),
     "adpst_gram_masked": (_i, [_vp, _i, _i, _i, _vp, _i, _vp, _vp, _vp, _i, _vp, _vp, _vp, _vp]),
     "adpst_style_layer_backward": (_i, [_vp, _i, _i, _i, _vp, _i, _vp, _vp, _d, _d, _vp, _vp, _i, _i, _d, _vp, _vp, _vp, _vp]),

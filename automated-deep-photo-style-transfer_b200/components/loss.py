@@ -108,10 +108,11 @@ class Loss:
         exist = self.content_masks is not None and self.style_masks is not None     # loss.py:110
         if exist:
             K = len(self.content_masks)
-            cm = torch.stack([kernels.resize_bilinear(_plane(m, self.device), (h, w)).reshape(-1)
-                              for m in self.content_masks]).contiguous()             # loss.py:112-117
-            sm = torch.stack([kernels.resize_bilinear(_plane(m, self.device), (hs, ws_)).reshape(-1)
-                              for m in self.style_masks]).contiguous()
+            if self._mask_planes is None:       # the full-resolution masks go to the device once, as two (K,H,W) stacks
+                self._mask_planes = (torch.stack([_plane(m, self.device) for m in self.content_masks]).contiguous(),
+                                     torch.stack([_plane(m, self.device) for m in self.style_masks]).contiguous())
+            cm = kernels.resize_bilinear_batch(self._mask_planes[0], (h, w)).reshape(K, h * w)        # loss.py:112-117
+            sm = kernels.resize_bilinear_batch(self._mask_planes[1], (hs, ws_)).reshape(K, hs * ws_)
         else:
             K, cm, sm = 1, None, None                                                # loss.py:119-120
         # spatial tiling: the Gram partial of this rank counts only its own columns (mask x column indicator; exact,
@@ -270,6 +271,7 @@ class Loss:
 
     _photo_grad_buf = None
     _tv_grad_buf = None
+    _mask_planes = None
     _nima_note_shown = False
 
     @staticmethod

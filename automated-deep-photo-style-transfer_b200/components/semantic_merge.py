@@ -23,11 +23,14 @@ def extract_segmentation_masks(segmentation, colors=None):
     """BGR label image (cv2.imread order) -> {RGB tuple: bool mask (H,W)}; empty masks are dropped."""
     if colors is None:
         colors = [color[::-1] for color in get_unique_colors_from_image(segmentation)]
-    seg = segmentation.astype(np.int32)
+    seg = segmentation.astype(np.int64)
+    packed = (seg[:, :, 0] << 16) | (seg[:, :, 1] << 8) | seg[:, :, 2]      # one comparison per colour instead of three
     out = {}
     for color in colors:
-        bgr = np.array(color[::-1], dtype=np.int32)
-        mask = (seg == bgr).all(axis=-1)
+        b, g, r = (int(c) for c in color[::-1])
+        if min(b, g, r) < 0 or max(b, g, r) > 255:
+            continue                                   # cannot occur in a uint8 image
+        mask = packed == ((b << 16) | (g << 8) | r)
         if mask.any():
             out[color] = mask
     return out

@@ -88,6 +88,8 @@ __global__ void resize_bilinear_kernel(const float* __restrict__ src, int Hs, in
                                        int Wd) {
     const int j = blockIdx.x * blockDim.x + threadIdx.x, i = blockIdx.y * blockDim.y + threadIdx.y;
     if (i >= Hd || j >= Wd) return;
+    src += size_t(blockIdx.z) * Hs * Ws;                 // plane of a batch
+    dst += size_t(blockIdx.z) * Hd * Wd;
     const double sy = fmax((i + 0.5) * (double(Hs) / Hd) - 0.5, 0.0);
     const double sx = fmax((j + 0.5) * (double(Ws) / Wd) - 0.5, 0.0);
     const int y0 = min(int(sy), Hs - 1), x0 = min(int(sx), Ws - 1);
@@ -183,13 +185,18 @@ int adpst_content_layer(const float* target_dev, const float* output_dev, size_t
     return ADPST_OK;
 }
 
-int adpst_resize_bilinear(const float* src_dev, int Hs, int Ws, float* dst_dev, int Hd, int Wd, adpst_stream_t stream) {
+int adpst_resize_bilinear_batch(const float* src_dev, int n, int Hs, int Ws, float* dst_dev, int Hd, int Wd,
+                                adpst_stream_t stream) {
     using namespace adpst;
-    ADPST_REQUIRE(src_dev && dst_dev && Hs > 0 && Ws > 0 && Hd > 0 && Wd > 0, "resize_bilinear: bad argument");
-    dim3 block(32, 8), grid((Wd + 31) / 32, (Hd + 7) / 8);
+    ADPST_REQUIRE(src_dev && dst_dev && n > 0 && n <= 65535 && Hs > 0 && Ws > 0 && Hd > 0 && Wd > 0, "resize_bilinear: bad argument");
+    dim3 block(32, 8), grid((Wd + 31) / 32, (Hd + 7) / 8, n);
     resize_bilinear_kernel<<<grid, block, 0, as_stream(stream)>>>(src_dev, Hs, Ws, dst_dev, Hd, Wd);
     ADPST_LAUNCH_CHECK();
     return ADPST_OK;
+}
+
+int adpst_resize_bilinear(const float* src_dev, int Hs, int Ws, float* dst_dev, int Hd, int Wd, adpst_stream_t stream) {
+    return adpst_resize_bilinear_batch(src_dev, 1, Hs, Ws, dst_dev, Hd, Wd, stream);
 }
 
 int adpst_tv_loss(const float* x_dev, int H, int W, double loss_scale, double grad_scale, double* loss_dev, float* dX_dev,

@@ -25,19 +25,35 @@ namespace adpst {
 // ---------------------------------------------------------------------------------------------
 // per-window algebra
 // ---------------------------------------------------------------------------------------------
-// Inverse of the symmetric 3x3  [m0 m1 m2; m1 m3 m4; m2 m4 m5]  (same packing for the result).
+// Inverse of the symmetric positive definite 3x3  [m0 m1 m2; m1 m3 m4; m2 m4 m5]  (same packing for the result), through its
+// Cholesky factor: M = G G^T, M^-1 = G^-T G^-1.
+// The cofactor / determinant formula is NOT usable here.  Where the window's colours lie on a line (grey images, two-colour
+// edges) M has eigenvalues (s, eps, eps) with s/eps up to 1e6; the determinant and the cofactors then lose that many digits
+// each, independently, and the result is not the inverse of any nearby matrix (measured: 1e-3 errors of L x on a grey
+// image).  The Cholesky route is backward stable: the computed inverse is the exact inverse of a matrix within rounding of
+// M, which is all the products M^-1 R of this file need -- like the LU behind np.linalg.inv in the reference
+// (matting_v2.py:52, matting_v3.py:92).
 template <typename T>
 __device__ __forceinline__ void sym3_inverse(const T m[6], T inv[6]) {
-    const T c00 = m[3] * m[5] - m[4] * m[4];
-    const T c01 = m[2] * m[4] - m[1] * m[5];
-    const T c02 = m[1] * m[4] - m[2] * m[3];
-    const T c11 = m[0] * m[5] - m[2] * m[2];
-    const T c12 = m[1] * m[2] - m[0] * m[4];
-    const T c22 = m[0] * m[3] - m[1] * m[1];
-    const T det = m[0] * c00 + m[1] * c01 + m[2] * c02;
-    const T id = T(1) / det;
-    inv[0] = c00 * id; inv[1] = c01 * id; inv[2] = c02 * id;
-    inv[3] = c11 * id; inv[4] = c12 * id; inv[5] = c22 * id;
+    const T g00 = sqrt(m[0]);
+    const T i00 = T(1) / g00;
+    const T g10 = m[1] * i00, g20 = m[2] * i00;
+    const T g11 = sqrt(m[3] - g10 * g10);
+    const T i11 = T(1) / g11;
+    const T g21 = (m[4] - g20 * g10) * i11;
+    const T g22 = sqrt(m[5] - g20 * g20 - g21 * g21);
+    const T i22 = T(1) / g22;
+    // K = G^-1 (lower triangular): k00 = i00, k11 = i11, k22 = i22
+    const T k10 = -g10 * i00 * i11;
+    const T k21 = -g21 * i11 * i22;
+    const T k20 = -(g20 * i00 + g21 * k10) * i22;
+    // M^-1 = K^T K
+    inv[0] = i00 * i00 + k10 * k10 + k20 * k20;
+    inv[1] = k10 * i11 + k20 * k21;
+    inv[2] = k20 * i22;
+    inv[3] = i11 * i11 + k21 * k21;
+    inv[4] = k21 * i22;
+    inv[5] = i22 * i22;
 }
 
 // Window moments from a (2R+1)^2 patch in shared memory.  `pI`, `px` point at the patch's top-left pixel,
@@ -966,10 +982,12 @@ int adpst_laplacian_create(int mode, int H, int W, int radius, double epsilon, c
     h->mode = mode; h->H = H; h->W = W; h->R = radius; h->io_dtype = io_dtype; h->compute_dtype = compute_dtype;
     h->eps = epsilon;
     const size_t bytes = size_t(H) * W * 3 * (io_dtype == ADPST_F64 ? 8 : 4);
-    cudaError_t e = cudaMalloc(&h->image, bytes);
+    h->stream = as_stream(stream);
+    cudaError_t e = device_alloc(&h->image, bytes, h->stream) == ADPST_OK ? cudaSuccess : cudaErrorMemoryAllocation;
     if (e == cudaSuccess) {
         h->npartials = ((W + 31) / 32) * ((H + 15) / 16) + 64;
-        e = cudaMalloc(reinterpret_cast<void**>(&h->partials), sizeof(double) * (h->npartials + 1));
+        if (device_alloc(reinterpret_cast<void**>(&h->partials), sizeof(double) * (h->npartials + 1), h->stream) != ADPST_OK)
+            e = cudaErrorMemoryAllocation;
         if (e == cudaSuccess) e = cudaMemsetAsync(h->partials + h->npartials, 0, sizeof(double), as_stream(stream));
     }
     if (e == cudaSuccess) e = cudaMemcpyAsync(h->image, image_dev, bytes, cudaMemcpyDeviceToDevice, as_stream(stream));
@@ -1012,8 +1030,8 @@ int adpst_laplacian_kernel(const adpst_laplacian* h) {
 
 void adpst_laplacian_destroy(adpst_laplacian* h) {
     if (!h) return;
-    if (h->image) cudaFree(h->image);
-    if (h->partials) cudaFree(h->partials);
+    adpst::device_free(h->image, h->stream);
+    adpst::device_free(h->partials, h->stream);
     adpst::dia_free(h);
     delete h;
 }
@@ -1039,7 +1057,6 @@ int adpst_laplacian_set_quadratic_window(adpst_laplacian* h, int col_lo, int col
     ADPST_REQUIRE(h != nullptr && col_lo >= 0 && col_hi <= h->W && col_lo <= col_hi, "laplacian_set_quadratic_window: bad window");
     h->q_col_lo = col_lo;
     h->q_col_hi = col_hi;
-    h->dia_q_dirty = true;          // the constant I^T L I of the diagonal-format kernel is per window
     return ADPST_OK;
 }
 

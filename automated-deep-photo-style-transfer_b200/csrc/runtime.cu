@@ -40,6 +40,37 @@ int num_sms() {
     return n;
 }
 
+int device_alloc(void** p, size_t bytes, cudaStream_t st) {
+    static std::atomic<unsigned long long> tuned{0};
+    const int dev = current_device();
+    const unsigned long long bit = 1ull << (dev & 63);
+    if (!(tuned.load(std::memory_order_acquire) & bit)) {
+        cudaMemPool_t pool;
+        if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+            unsigned long long keep = ~0ull;                 // never trim at synchronisation points
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+        }
+        cudaGetLastError();
+        tuned.fetch_or(bit, std::memory_order_release);
+    }
+    *p = nullptr;
+    cudaError_t e = cudaMallocAsync(p, bytes ? bytes : 1, st);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        e = cudaMalloc(p, bytes ? bytes : 1);                // (stream capture in progress, exhausted pool, ...)
+    }
+    if (e != cudaSuccess) return fail(ADPST_ERR_CUDA, "device allocation of %zu bytes failed: %s", bytes, cudaGetErrorString(e));
+    return ADPST_OK;
+}
+
+void device_free(void* p, cudaStream_t st) {
+    if (!p) return;
+    if (cudaFreeAsync(p, st) != cudaSuccess) {               // e.g. the creating stream no longer exists
+        cudaGetLastError();
+        cudaFree(p);
+    }
+}
+
 }  // namespace adpst
 
 extern "C" {

@@ -65,6 +65,17 @@ def resize_bilinear(mask_hw, size):
 
 
 @_on_tensor_device
+def resize_bilinear_batch(planes, size):
+    """tf.image.resize for a stack of planes (n,H,W) -> (n,h,w): all class masks of a layer in one launch (loss.py:112-117)."""
+    _f32(planes, "planes")
+    n, Hs, Ws = planes.shape
+    Hd, Wd = int(size[0]), int(size[1])
+    out = torch.empty(n, Hd, Wd, dtype=torch.float32, device=planes.device)
+    _lib.check(_lib.lib().adpst_resize_bilinear_batch(_lib.ptr(planes), n, Hs, Ws, _lib.ptr(out), Hd, Wd, _lib.stream_ptr()))
+    return out
+
+
+@_on_tensor_device
 def content_layer(target, output, loss_scale, grad_scale, loss_acc, d_out=None, accumulate=False, n_norm=0.0, own_cols=None):
     """loss_acc (float64[1]) += loss_scale*mean((t-o)^2); d_out (=|+=) grad_scale*2(o-t)/n  (loss.py:90-92).
     Spatially tiled runs: n_norm = element count of the whole layer, own_cols = (lo, hi) columns of this (1,h,w,C) tile

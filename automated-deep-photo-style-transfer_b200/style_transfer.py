@@ -46,6 +46,24 @@ class Adam:
         return 0 if self._slots is None else self._slots.step
 
 
+_GRAPH_POOLS, _SIDE_STREAMS = {}, {}
+
+
+def _graph_pool(device):
+    """One private CUDA-graph memory pool per device, shared by every captured train step."""
+    key = torch.device(device).index if torch.device(device).index is not None else torch.cuda.current_device()
+    if key not in _GRAPH_POOLS:
+        _GRAPH_POOLS[key] = torch.cuda.graph_pool_handle()
+    return _GRAPH_POOLS[key]
+
+
+def _side_stream(device):
+    key = torch.device(device).index if torch.device(device).index is not None else torch.cuda.current_device()
+    if key not in _SIDE_STREAMS:
+        _SIDE_STREAMS[key] = torch.cuda.Stream(device=device)
+    return _SIDE_STREAMS[key]
+
+
 def make_train_step(features_extractor, compute_loss, optimizer, use_cuda_graph=False):
     """Returns train_step(image) -> loss_dict, the closure of style_transfer.py:331-344.
     `image` is a (1,H,W,3) float32 CUDA tensor updated in place (the tf.Variable of :329).
@@ -73,7 +91,7 @@ def make_train_step(features_extractor, compute_loss, optimizer, use_cuda_graph=
             snap = image.clone()
             slots = optimizer._slots
             saved = None if slots is None else (slots.m.clone(), slots.v.clone(), slots.state.clone())
-            s = torch.cuda.Stream()
+            s = _side_stream(image.device)
             s.wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(s):
                 eager_step(image)
@@ -84,9 +102,19 @@ def make_train_step(features_extractor, compute_loss, optimizer, use_cuda_graph=
                 optimizer._slots.m.zero_(); optimizer._slots.v.zero_(); optimizer._slots.state.zero_()
             else:
                 slots.m.copy_(saved[0]); slots.v.copy_(saved[1]); slots.state.copy_(saved[2])
+            # Capture with the raw CUDAGraph API: the torch.cuda.graph() context manager runs gc.collect() and
+            # torch.cuda.empty_cache() on entry, which hands every cached block back to the driver -- measured 0.3 s per
+            # capture plus a cudaMalloc for every buffer of the next pair.  The step allocates nothing while it is captured
+            # (every buffer was created by the warm-up), so one shared private pool per device is enough.
             g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g):
-                out = eager_step(image)
+            s.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(s):
+                g.capture_begin(pool=_graph_pool(image.device))
+                try:
+                    out = eager_step(image)
+                finally:
+                    g.capture_end()
+            torch.cuda.current_stream().wait_stream(s)
             state.update(graph=g, image=image, out=out)
         state["graph"].replay()
         return state["out"]

@@ -149,6 +149,9 @@ int adpst_vgg_backward(adpst_vgg* h, int H, int W, const float* const* acts_dev,
 /* tf.image.resize bilinear, half-pixel centres, no antialias (loss.py:112-113); single channel. */
 int adpst_resize_bilinear(const float* src_dev, int Hs, int Ws, float* dst_dev, int Hd, int Wd,
                           adpst_stream_t stream);
+/* the same for n planes at once: src (n,Hs,Ws) -> dst (n,Hd,Wd) (all K class masks of a layer in one launch) */
+int adpst_resize_bilinear_batch(const float* src_dev, int n, int Hs, int Ws, float* dst_dev, int Hd, int Wd,
+                                adpst_stream_t stream);
 
 /* loss.py:96-102 for K masks at once: G[k] = (F*m_k)^T (F*m_k).  F: (h,w,C) feature map; masks: (K,h*w) or NULL
  * (K==1, all ones); G: (K,C,C).  workspace_dev: at least adpst_gram_workspace_bytes(h*w,C,K) bytes.
