@@ -112,8 +112,12 @@ template <int BN> struct TcCfg {
     static constexpr int OFF_B = A_STAGES * TC_A_BYTES;
     static constexpr int OFF_BARS = OFF_B + B_STAGES * B_STAGE_BYTES;
     static constexpr int SMEM_BYTES = OFF_BARS + 1024 /*alignment slack*/ + 256 /*barriers*/;
-    // tensor memory columns: big0 | big1 | small | A operand slots (2 x (hi: 32 columns of packed fp16 pairs, lo: 32))
+    // tensor memory columns: big0 | big1 | small | A operand slots (each: hi = 32 columns of packed fp16 pairs, lo = 32).
+    // BN = 128 fills the 512 columns with two slots; BN = 64 has room for four, which it needs: its MMAs of one stage take
+    // 384 clk, less than the round trip  tcgen05.st -> MMA -> commit -> a_free -> next tcgen05.st  of a two-slot ring.
+    static constexpr int A_SLOTS = BN == 128 ? 2 : 4;
     static constexpr uint32_t COL_SMALL = 2 * BN, COL_A = 3 * BN, TMEM_COLS = 512;
+    static_assert(COL_A + A_SLOTS * 64 <= TMEM_COLS, "tensor memory columns");
 };
 
 // position of the n-th (0-based) set bit of m
@@ -140,6 +144,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                   const uint32_t* __restrict__ w_absmax, uint32_t* __restrict__ y_absmax, float* __restrict__ pool_out) {
     using Cfg = TcCfg<BN>;
     constexpr int AST = Cfg::A_STAGES, BST = Cfg::B_STAGES;
+    constexpr int NSLOT = Cfg::A_SLOTS;         // A operand slots in tensor memory (ring between the transform warps and the MMAs)
     static_assert(BN == 64 || BN == 128, "tile width");
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -152,8 +157,8 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     uint64_t* chunk_empty = chunk_full + 2;     // [2]       the drain warps have consumed TMEM buffer b
     uint64_t* small_full = chunk_empty + 2;     // [1]       every MMA of the work item has retired
     uint64_t* small_empty = small_full + 1;     // [1]       the drain warps have read the small-term accumulator
-    uint64_t* a_free = small_empty + 1;         // [2]       the MMAs that read TMEM A slot j have retired
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(a_free + 2);
+    uint64_t* a_free = small_empty + 1;         // [NSLOT]   the MMAs that read TMEM A slot j have retired
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(a_free + 4);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int kchunks = Cin / TC_BK;
@@ -183,8 +188,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         }
         tc::mbar_init(small_full, 1);
         tc::mbar_init(small_empty, 128);
-        tc::mbar_init(&a_free[0], 2);
-        tc::mbar_init(&a_free[1], 2);
+        for (int j = 0; j < NSLOT; ++j) tc::mbar_init(&a_free[j], 2);
         tc::fence_barrier_init();
         tc::tma_prefetch_desc(&tmA);
         tc::tma_prefetch_desc(&tmBhi);
@@ -255,7 +259,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             for (int it = 0; it < iters; ++it, ++git) {
                 const int cpos = it % chunk_iters;
                 const uint32_t tmem_big = tmem_base + uint32_t(gc & 1) * BN;
-                const uint32_t a_hi = tmem_a + uint32_t(git & 1) * 64;
+                const uint32_t a_hi = tmem_a + uint32_t(git % NSLOT) * 64;
                 if (cpos == 0) tc::mbar_wait(&chunk_empty[gc & 1], ((gc >> 1) & 1) ^ 1);   // TMEM buffer drained
                 // ONE wait per stage: ready[s] completes when the B tiles have landed (transaction bytes) and the 128
                 // transform threads have stored A hi/lo into tensor memory.
@@ -268,7 +272,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                     for (int k = 0; k < TC_BK / 16; ++k)              // UMMA K = 16: 8 TMEM columns of A, 32 bytes of each B row
                         tc::umma_f16_ts(tmem_big, a_hi + k * 8, d_bhi + soff + uint64_t(k * 2), idesc, (cpos | k) != 0);
                     tc::umma_commit(&empty[s]);
-                    tc::umma_commit(&a_free[git & 1]);
+                    tc::umma_commit(&a_free[git % NSLOT]);
                     if (close) tc::umma_commit(&chunk_full[gc & 1]);
                 }
                 __syncwarp();
@@ -292,7 +296,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                 tc::tcgen05_fence_after();
             }
             for (int it = 0; it < iters; ++it, ++git) {
-                const uint32_t a_hi = tmem_a + uint32_t(git & 1) * 64, a_lo = a_hi + 32;
+                const uint32_t a_hi = tmem_a + uint32_t(git % NSLOT) * 64, a_lo = a_hi + 32;
                 tc::mbar_wait(&ready[s], round & 1);
                 tc::tcgen05_fence_after();
                 const uint64_t soff = uint64_t(uint32_t(s) * uint32_t(Cfg::B_STAGE_BYTES >> 4));
@@ -304,7 +308,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                         tc::umma_f16_ts(tmem_small, a_hi + k * 8, d_blo + koff, idesc, 1);
                     }
                     tc::umma_commit(&empty[s]);
-                    tc::umma_commit(&a_free[git & 1]);
+                    tc::umma_commit(&a_free[git % NSLOT]);
                     if (it == iters - 1) tc::umma_commit(small_full);
                 }
                 __syncwarp();
@@ -324,6 +328,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         // One stage of this loop (16 loads, ~350 arithmetic instructions, tcgen05.st + wait) takes longer than the 768 clk
         // its MMAs need, so warpgroup g handles the stages with (global stage index & 1) == g and owns TMEM A slot g.
         asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(TC_REGS_XFORM));
+        constexpr bool PRESPLIT = (MODE != MODE_STYLE);
         const int grp = (warp - 4) >> 2;
         const int q = warp & 3;
         const int m = q * 32 + lane;
@@ -340,8 +345,74 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             const int gy = (tile / tiles_w) * TC_TH + ty, gx = (tile % tiles_w) * TC_TW + tx;
             for (int kc = 0; kc < kchunks; ++kc) {
                 tc::mbar_wait(&full[sa], ra & 1);
+                if (PRESPLIT) {
+                    // Convolution modes: every pixel of the halo tile is used by up to nine taps with the SAME scale, so it is
+                    // split into FP16 hi / lo ONCE, in place: row r of box 0 (channels 0..31 as float32, 128 bytes) becomes the
+                    // hi halves of all 64 channels, row r of box 1 the lo halves (same 16-byte-chunk swizzle).  A thread reads
+                    // both rows completely before it writes, and touches no other row, so the only synchronisation needed is
+                    // one named barrier of the 256 transform threads before the taps start reading shifted rows.  The per-tap
+                    // work shrinks to a 256-byte copy shared memory -> tensor memory (it was 64 multiplies, 64 conversion
+                    // pairs and the packing per tap: the Cout = 64 layers were bound by the issue slots of these warps).
+                    const int r = int(threadIdx.x) - 128;                   // transform threads are 128..383
+                    if (r < TC_HW * TC_HH) {
+                        const uint32_t row0 = smem_base + uint32_t(sa * TC_A_BYTES + r * 128);
+                        const uint32_t row1 = row0 + TC_A_BOX_BYTES;
+                        float4 v[16];
+#pragma unroll
+                        for (int c = 0; c < 8; ++c) {
+                            v[c] = tc::lds128(row0 + uint32_t((c ^ (r & 7)) << 4));
+                            v[8 + c] = tc::lds128(row1 + uint32_t((c ^ (r & 7)) << 4));
+                        }
+                        uint32_t hi[32], lo[32];
+#pragma unroll
+                        for (int c = 0; c < 16; ++c) {
+                            const float t0 = v[c].x * scale_a, t1 = v[c].y * scale_a, t2 = v[c].z * scale_a, t3 = v[c].w * scale_a;
+                            const __half2 h01 = __floats2half2_rn(t0, t1), h23 = __floats2half2_rn(t2, t3);
+                            const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
+                            const __half2 l01 = __floats2half2_rn((t0 - f01.x) * 2048.0f, (t1 - f01.y) * 2048.0f);
+                            const __half2 l23 = __floats2half2_rn((t2 - f23.x) * 2048.0f, (t3 - f23.y) * 2048.0f);
+                            hi[c * 2] = h2_bits(h01); hi[c * 2 + 1] = h2_bits(h23);
+                            lo[c * 2] = h2_bits(l01); lo[c * 2 + 1] = h2_bits(l23);
+                        }
+#pragma unroll
+                        for (int c = 0; c < 8; ++c) {
+                            tc::sts128(row0 + uint32_t((c ^ (r & 7)) << 4), hi[c * 4], hi[c * 4 + 1], hi[c * 4 + 2], hi[c * 4 + 3]);
+                            tc::sts128(row1 + uint32_t((c ^ (r & 7)) << 4), lo[c * 4], lo[c * 4 + 1], lo[c * 4 + 2], lo[c * 4 + 3]);
+                        }
+                    }
+                    asm volatile("bar.sync 1, 256;" ::: "memory");
+                }
                 for (int slot = 0; slot < ntaps; ++slot, ++git) {
                     if ((git & 1) != grp) {                                 // the other warpgroup's stage
+                        if (++s == BST) s = 0;
+                        continue;
+                    }
+                    if (PRESPLIT) {
+                        const uint32_t dst = tmem_a + uint32_t(git % NSLOT) * 64 + lane_base;
+                        const int kh = slot / 3, kw = slot - kh * 3;
+                        const int r = (ty + kh) * TC_HW + tx + kw;             // this thread's pixel, shifted by the tap, in the halo tile
+                        const uint32_t row0 = smem_base + uint32_t(sa * TC_A_BYTES + r * 128);
+                        const uint32_t row1 = row0 + TC_A_BOX_BYTES;
+                        uint32_t hi[2][16], lo[2][16];
+#pragma unroll
+                        for (int c = 0; c < 8; ++c) {
+                            const float4 h = tc::lds128(row0 + uint32_t((c ^ (r & 7)) << 4));
+                            const float4 l = tc::lds128(row1 + uint32_t((c ^ (r & 7)) << 4));
+                            hi[c >> 2][(c & 3) * 4] = __float_as_uint(h.x); hi[c >> 2][(c & 3) * 4 + 1] = __float_as_uint(h.y);
+                            hi[c >> 2][(c & 3) * 4 + 2] = __float_as_uint(h.z); hi[c >> 2][(c & 3) * 4 + 3] = __float_as_uint(h.w);
+                            lo[c >> 2][(c & 3) * 4] = __float_as_uint(l.x); lo[c >> 2][(c & 3) * 4 + 1] = __float_as_uint(l.y);
+                            lo[c >> 2][(c & 3) * 4 + 2] = __float_as_uint(l.z); lo[c >> 2][(c & 3) * 4 + 3] = __float_as_uint(l.w);
+                        }
+                        // the MMAs that read this TMEM slot two iterations ago must have retired
+                        tc::mbar_wait(&a_free[git % NSLOT], (((git / NSLOT) & 1) ^ 1));
+                        tc::tcgen05_fence_after();
+                        tc::tmem_st_32x16(dst, hi[0]);
+                        tc::tmem_st_32x16(dst + 16, hi[1]);
+                        tc::tmem_st_32x16(dst + 32, lo[0]);
+                        tc::tmem_st_32x16(dst + 48, lo[1]);
+                        tc::tmem_st_wait();
+                        tc::tcgen05_fence_before();
+                        tc::mbar_arrive(&ready[s]);
                         if (++s == BST) s = 0;
                         continue;
                     }
@@ -358,7 +429,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                         kh = slot / 3; kw = slot - kh * 3;
                     }
                     const int r = (ty + kh) * TC_HW + tx + kw;             // this thread's pixel, shifted by the tap, in the halo tile
-                    const uint32_t dst = tmem_a + uint32_t(git & 1) * 64 + lane_base;
+                    const uint32_t dst = tmem_a + uint32_t(git % NSLOT) * 64 + lane_base;
                     uint32_t hi[2][16], lo[2][16];
 #pragma unroll
                     for (int half = 0; half < 2; ++half) {
@@ -376,7 +447,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                         }
                     }
                     // the MMAs that read this TMEM slot two iterations ago must have retired
-                    tc::mbar_wait(&a_free[git & 1], (((git >> 1) & 1) ^ 1));
+                    tc::mbar_wait(&a_free[git % NSLOT], (((git / NSLOT) & 1) ^ 1));
                     tc::tcgen05_fence_after();
                     tc::tmem_st_32x16(dst, hi[0]);
                     tc::tmem_st_32x16(dst + 16, hi[1]);
@@ -388,6 +459,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                     if (++s == BST) s = 0;
                 }
                 // every tap has consumed the halo tile (the tcgen05.st above needed the loaded values): release its slot
+                if (PRESPLIT) tc::fence_proxy_async_smem();                // generic-proxy writes before TMA overwrites the slot
                 tc::mbar_arrive(&a_empty[sa]);
                 if (++sa == AST) { sa = 0; ++ra; }
             }
@@ -559,8 +631,8 @@ __global__ void __launch_bounds__(256) absmax_kernel(const float* __restrict__ x
     if ((threadIdx.x & 31) == 0 && wm != 0u) atomicMax(slot, wm);
 }
 
-int launch_absmax(const float* x, size_t n, uint32_t* slot, cudaStream_t st) {
-    ADPST_CUDA_CHECK(cudaMemsetAsync(slot, 0, sizeof(uint32_t), st));
+int launch_absmax(const float* x, size_t n, uint32_t* slot, cudaStream_t st, bool reset) {
+    if (reset) ADPST_CUDA_CHECK(cudaMemsetAsync(slot, 0, sizeof(uint32_t), st));
     const size_t want = (n / 4 + 255) / 256, cap = size_t(num_sms()) * 8;
     absmax_kernel<<<unsigned(want < cap ? (want ? want : 1) : cap), 256, 0, st>>>(x, n, slot);
     ADPST_LAUNCH_CHECK();

@@ -12,8 +12,8 @@ struct adpst_laplacian {
     int kernel = ADPST_LAP_KERNEL_AUTO;   // which mat-vec runs (adpst_laplacian_set_kernel)
     int q_col_lo = 0, q_col_hi = 0;   // x^T L x restricted to these columns (spatially tiled runs); (0,0) = all
     // diagonal-format operator (laplacian_dia.cu): r = 1, float32 storage
-    float* dia_coef = nullptr;   // [H W][12]: L[i, i+delta] for the 12 "forward" offsets of the 5x5 neighbourhood (48-byte records)
-    float* dia_LI = nullptr;     // (H,W,3): L I, evaluated once in float64 and rounded
+    float* dia_coef = nullptr;   // [12][H][W] planes: L[i, i+delta] for the 12 "forward" offsets of the 5x5 neighbourhood
+    float* dia_LI = nullptr;     // [3][H][W] planes: L I, evaluated once in float64 and rounded
     double* dia_qI = nullptr;    // [W]: per-column sums of I . (L I), float64 (the constant part of x^T L x for any column window)
     bool dia_ready = false;
     cudaStream_t stream = nullptr;   // the stream the handle was created on: its buffers are released in that stream's order

@@ -121,7 +121,7 @@ __device__ __forceinline__ void dia_row(const float* __restrict__ img, int H, in
     }
 }
 
-// coef: [(y W + x)][12] (one 48-byte record per pixel), LI: (H,W,3), colq[x]: sum over the column of I . (L I) (pre-zeroed)
+// coef: [12][H][W] planes, LI: [3][H][W] planes, colq[x]: sum over the column of I . (L I) (pre-zeroed)
 template <bool V2>
 __global__ void __launch_bounds__(128)
 lap_dia_build_kernel(const float* __restrict__ img, float* __restrict__ coef, float* __restrict__ LI, double* __restrict__ colq,
@@ -144,21 +144,16 @@ lap_dia_build_kernel(const float* __restrict__ img, float* __restrict__ coef, fl
         } else {
             dia_row<V2, false>(img, H, W, y, x, eps, acc, li);
         }
-        const size_t o = size_t(y) * W + x;
-        float r[DIA_P];
+        const size_t HW = size_t(H) * W, o = size_t(y) * W + x;
 #pragma unroll
         for (int p = 0; p < DIA_P; ++p) {
             const int ty = y + dia_dy(p), tx = x + dia_dx(p);
-            r[p] = (ty < H && tx >= 0 && tx < W) ? float(acc[p]) : 0.0f;
+            coef[p * HW + o] = (ty < H && tx >= 0 && tx < W) ? float(acc[p]) : 0.0f;
         }
-        float4* rec = reinterpret_cast<float4*>(coef + o * DIA_P);
-        rec[0] = make_float4(r[0], r[1], r[2], r[3]);
-        rec[1] = make_float4(r[4], r[5], r[6], r[7]);
-        rec[2] = make_float4(r[8], r[9], r[10], r[11]);
         const float* pi = img + o * 3;
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
-            LI[o * 3 + c] = float(li[c]);
+            LI[c * HW + o] = float(li[c]);
             q = fma(double(pi[c]), li[c], q);
         }
     }
@@ -168,121 +163,154 @@ lap_dia_build_kernel(const float* __restrict__ img, float* __restrict__ coef, fl
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// mat-vec.  CTA = 32 x 16 output pixels, 256 threads, warp w owns tile rows w and w + 8.  d = x - I of the tile plus a
-// 2-pixel halo is staged in shared memory as float4 (coalesced 4-byte loads of the interleaved RGB rows, no integer
-// division in the loop).  Every pixel then reads its own 48-byte coefficient record (3 x LDG.128) and one coefficient from
-// the record of each of its 12 backward neighbours (L1 hits: those records are the forward loads of the neighbouring
-// threads), one LDS.128 per neighbour, 6 float32 operations per neighbour and channel.
-// x^T L x: per pixel  x_i . (L d)_i + d_i . (L I)_i  (float32 dot of six terms, exact to 1e-7 of its largest term), summed
-// over pixels in float64; the constant I^T L I comes from the per-column float64 sums of the build.
+// mat-vec.  The kernel is bound by the L1 / shared-memory data pipe (one 128-byte wavefront per clock and SM) unless the
+// per-pixel wavefront count is kept near the ~130 that 96 B/px of HBM traffic allow, so:
+//   * CTA = 32 x 16 output pixels, 256 threads; a thread owns TWO vertically adjacent pixels, whose 5x5 neighbourhoods
+//     share 4 of 6 rows: 30 LDS.128 for two pixels instead of 50;
+//   * coefficients and L I are stored as planes ([12][H][W], [3][H][W]): a warp's load of one coefficient of 32 neighbouring
+//     pixels is one 128-byte line, for the own ("forward") coefficients as well as for the ones read from the backward
+//     neighbours' planes (L_ij = L_ji; those are L1 / L2 hits: the same lines are the forward loads of neighbouring warps);
+//   * d = x - I of the tile plus a 2-pixel halo is staged in shared memory as float4 (coalesced 4-byte loads of the
+//     interleaved RGB rows, no integer division in the loop);
+//   * everything that does not depend on shared memory (the staged x / I elements, both pixels' forward coefficients, L I)
+//     is requested before the first use, so every thread has ~50 independent loads in flight.
+// x^T L x: per pixel  x_i . (L d)_i + d_i . (L I)_i  (float32 dot of six terms), summed over pixels in float64; the constant
+// I^T L I comes from the per-column float64 sums of the build (lap_dia_sum_kernel).
 // ---------------------------------------------------------------------------------------------------------------
 constexpr int DT_W = 32, DT_H = 16, DT_THREADS = 256, DT_PW = DT_W + 4, DT_PH = DT_H + 4;
 
-__global__ void __launch_bounds__(DT_THREADS)
+__global__ void __launch_bounds__(DT_THREADS, 3)
 lap_dia_kernel(const float* __restrict__ x, const float* __restrict__ img, const float* __restrict__ LI,
                const float* __restrict__ coef, float* __restrict__ y, double* __restrict__ partial, int H, int W, float y_scale,
-               int qlo, int qhi, unsigned int* __restrict__ ticket, double* __restrict__ xLx_out, const double* __restrict__ colq) {
+               int qlo, int qhi) {
     __shared__ float4 sd[DT_PH][DT_PW];
     __shared__ double sRed[32];
-    __shared__ bool sLast;
     const int x0 = blockIdx.x * DT_W, y0 = blockIdx.y * DT_H;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int row_elems = W * 3;
-    // ---- stage d = x - I (zero outside the image: the coefficients that point there are zero as well)
-    {
-        int soff[4], ge[4];
+    const int gx = x0 + lane;
+    const size_t HW = size_t(H) * W;
+    const bool want_q = partial != nullptr;
+    // ---- (1) requests for the staged rows (3 tile rows x 4 elements per thread)
+    int soff[4], ge[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int e = lane + 32 * k;                               // element of the 108-float tile row
+        soff[k] = (e / 3) * 4 + (e % 3);
+        ge[k] = (x0 - 2) * 3 + e;
+        if (e >= DT_PW * 3 || ge[k] < 0 || ge[k] >= row_elems) ge[k] = -1;
+    }
+    float sx[3][4], si[3][4];
+#pragma unroll
+    for (int it = 0; it < 3; ++it) {
+        const int r = warp + it * (DT_THREADS / 32);
+        const int gyr = y0 - 2 + r;
+        const bool row_ok = r < DT_PH && gyr >= 0 && gyr < H;
+        const size_t g = size_t(row_ok ? gyr : 0) * row_elems;
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
-            const int e = lane + 32 * k;                           // element of the 108-float tile row
-            soff[k] = (e / 3) * 4 + (e % 3);
-            ge[k] = (x0 - 2) * 3 + e;
-            if (e >= DT_PW * 3 || ge[k] < 0 || ge[k] >= row_elems) ge[k] = -1;
+            const bool ok = row_ok && ge[k] >= 0;
+            sx[it][k] = ok ? __ldg(x + g + ge[k]) : 0.f;
+            si[it][k] = ok ? __ldg(img + g + ge[k]) : 0.f;
         }
-        float* sflat = reinterpret_cast<float*>(&sd[0][0]);
-        for (int r = warp; r < DT_PH; r += DT_THREADS / 32) {
-            const int gy = y0 - 2 + r;
-            const bool row_ok = gy >= 0 && gy < H;
-            const size_t g = size_t(row_ok ? gy : 0) * row_elems;
+    }
+    // ---- (2) requests for this thread's two pixels (rows ty, ty + 1): forward coefficients and L I
+    const int ty = 2 * warp, gy = y0 + ty;
+    bool live[2];
+    float cf[2][DIA_P], lv[2][3];
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                if (lane + 32 * k < DT_PW * 3) {
-                    float v = 0.f;
-                    if (row_ok && ge[k] >= 0) v = __ldg(x + g + ge[k]) - __ldg(img + g + ge[k]);
-                    sflat[r * (DT_PW * 4) + soff[k]] = v;
-                }
+    for (int k = 0; k < 2; ++k) {
+        live[k] = gx < W && gy + k < H;
+        const size_t o = live[k] ? size_t(gy + k) * W + gx : 0;
+#pragma unroll
+        for (int p = 0; p < DIA_P; ++p) cf[k][p] = live[k] ? __ldg(coef + p * HW + o) : 0.f;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) lv[k][c] = live[k] ? __ldg(LI + c * HW + o) : 0.f;
+    }
+    // ---- (3) d = x - I into shared memory (zero outside the image: the coefficients that point there are zero as well)
+    {
+        float* sflat = reinterpret_cast<float*>(&sd[0][0]);
+#pragma unroll
+        for (int it = 0; it < 3; ++it) {
+            const int r = warp + it * (DT_THREADS / 32);
+            if (r < DT_PH) {
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                    if (lane + 32 * k < DT_PW * 3) sflat[r * (DT_PW * 4) + soff[k]] = sx[it][k] - si[it][k];
             }
         }
     }
     __syncthreads();
-    const int gx = x0 + lane;
-    // which backward neighbours exist (their records hold the coefficient that points at this pixel)
-    bool okx[5];
-#pragma unroll
-    for (int dx = -2; dx <= 2; ++dx) okx[dx + 2] = gx - dx >= 0 && gx - dx < W;
-    const size_t W12 = size_t(W) * DIA_P;
     double qacc = 0.0;
+    if (live[0]) {                                                  // (live[1] implies live[0])
+        // which backward neighbours exist (their planes hold the coefficient that points at this pixel)
+        bool okx[5];
 #pragma unroll
-    for (int half = 0; half < 2; ++half) {
-        const int ty = warp + half * 8, gy = y0 + ty;
-        if (gx < W && gy < H) {
-            const size_t o = size_t(gy) * W + gx;
-            const float* cb = coef + o * DIA_P;
-            const float4 c0 = __ldg(reinterpret_cast<const float4*>(cb));
-            const float4 c1 = __ldg(reinterpret_cast<const float4*>(cb) + 1);
-            const float4 c2 = __ldg(reinterpret_cast<const float4*>(cb) + 2);
-            const float cf[DIA_P] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w, c2.x, c2.y, c2.z, c2.w};
-            const float* cbr[3] = {cb, cb - W12, cb - 2 * W12};            // records of rows gy, gy - 1, gy - 2
-            const bool oky[3] = {true, gy >= 1, gy >= 2};
-            const float4 di = sd[ty + 2][lane + 2];
-            float a0 = 0.f, a1 = 0.f, a2 = 0.f;
+        for (int dx = -2; dx <= 2; ++dx) okx[dx + 2] = gx + dx >= 0 && gx + dx < W;
+        const float* cbase = coef + size_t(gy) * W + gx;             // plane 0 at pixel 0 of this thread
+        const float4 dc0 = sd[ty + 2][lane + 2], dc1 = sd[ty + 3][lane + 2];
+        float a[2][3] = {{0.f, 0.f, 0.f}, {0.f, 0.f, 0.f}};
 #pragma unroll
-            for (int p = 0; p < DIA_P; ++p) {
-                const int dy = dia_dy(p), dx = dia_dx(p);
-                {   // forward neighbour i + delta: own coefficient (stored as zero when the neighbour is outside the image)
-                    const float4 dj = sd[ty + 2 + dy][lane + 2 + dx];
-                    a0 = fmaf(cf[p], dj.x - di.x, a0); a1 = fmaf(cf[p], dj.y - di.y, a1); a2 = fmaf(cf[p], dj.z - di.z, a2);
-                }
-                if (oky[dy] && okx[dx + 2]) {   // backward neighbour i - delta: its coefficient for +delta (L_ij = L_ji)
-                    const float cbk = __ldg(cbr[dy] - dx * DIA_P + p);
-                    const float4 dj = sd[ty + 2 - dy][lane + 2 - dx];
-                    a0 = fmaf(cbk, dj.x - di.x, a0); a1 = fmaf(cbk, dj.y - di.y, a1); a2 = fmaf(cbk, dj.z - di.z, a2);
+        for (int rr = 0; rr < 6; ++rr) {                             // tile rows ty + rr = image rows gy - 2 + rr
+            float4 dr[5];
+#pragma unroll
+            for (int dx = -2; dx <= 2; ++dx) dr[dx + 2] = sd[ty + rr][lane + 2 + dx];
+#pragma unroll
+            for (int k = 0; k < 2; ++k) {
+                const int dy = rr - 2 - k;                           // offset of this row from pixel k
+                if (dy < -2 || dy > 2) continue;
+                const float4 dc = k == 0 ? dc0 : dc1;
+#pragma unroll
+                for (int dx = -2; dx <= 2; ++dx) {
+                    if (dy == 0 && dx == 0) continue;
+                    float c;
+                    if (dia_forward(dy, dx)) {
+                        c = cf[k][dia_index(dy, dx)];                // own coefficient (stored as zero if the neighbour is outside)
+                    } else {
+                        // backward neighbour j = i + (dy, dx): its coefficient for the offset (-dy, -dx) that points back at i
+                        const bool ok = okx[dx + 2] && gy + k + dy >= 0 && (k == 0 || live[1]);
+                        c = ok ? __ldg(cbase + dia_index(-dy, -dx) * HW + (ptrdiff_t(k + dy) * W + dx)) : 0.f;
+                    }
+                    const float4 dj = dr[dx + 2];
+                    a[k][0] = fmaf(c, dj.x - dc.x, a[k][0]); a[k][1] = fmaf(c, dj.y - dc.y, a[k][1]); a[k][2] = fmaf(c, dj.z - dc.z, a[k][2]);
                 }
             }
-            const float l0 = __ldg(LI + o * 3), l1 = __ldg(LI + o * 3 + 1), l2 = __ldg(LI + o * 3 + 2);
-            if (partial != nullptr && gx >= qlo && gx < qhi) {
-                const float x0v = __ldg(x + o * 3), x1v = __ldg(x + o * 3 + 1), x2v = __ldg(x + o * 3 + 2);
-                float t = x0v * a0;
-                t = fmaf(x1v, a1, t); t = fmaf(x2v, a2, t);
-                t = fmaf(di.x, l0, t); t = fmaf(di.y, l1, t); t = fmaf(di.z, l2, t);
+        }
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+            if (!live[k]) continue;
+            const size_t o = size_t(gy + k) * W + gx;
+            const float4 dc = k == 0 ? dc0 : dc1;
+            if (want_q && gx >= qlo && gx < qhi) {
+                // x_i: an L1 hit (this CTA staged the row a moment ago)
+                float t = __ldg(x + o * 3) * a[k][0];
+                t = fmaf(__ldg(x + o * 3 + 1), a[k][1], t); t = fmaf(__ldg(x + o * 3 + 2), a[k][2], t);
+                t = fmaf(dc.x, lv[k][0], t); t = fmaf(dc.y, lv[k][1], t); t = fmaf(dc.z, lv[k][2], t);
                 qacc += double(t);
             }
             if (y != nullptr) {
-                y[o * 3] = y_scale * (l0 + a0);
-                y[o * 3 + 1] = y_scale * (l1 + a1);
-                y[o * 3 + 2] = y_scale * (l2 + a2);
+                y[o * 3] = y_scale * (lv[k][0] + a[k][0]);
+                y[o * 3 + 1] = y_scale * (lv[k][1] + a[k][1]);
+                y[o * 3 + 2] = y_scale * (lv[k][2] + a[k][2]);
             }
         }
     }
-    if (partial != nullptr) {
-        // per-CTA partials summed in a fixed order by whichever CTA finishes last (deterministic, one launch, graph-replayable),
-        // plus the constant I^T L I of the window from the per-column sums
-        const int nblk = gridDim.x * gridDim.y, blk = blockIdx.y * gridDim.x + blockIdx.x;
+    if (want_q) {       // per-CTA partial; lap_dia_sum_kernel adds them up in a fixed order (deterministic, no atomics, no fence)
         const double tot = block_sum<double>(qacc, sRed);
-        if (threadIdx.x == 0) {
-            partial[blk] = tot;
-            __threadfence();
-            sLast = (atomicAdd(ticket, 1u) == unsigned(nblk - 1));
-        }
-        __syncthreads();
-        if (sLast) {
-            __threadfence();
-            double a = 0.0;
-            for (int i = threadIdx.x; i < nblk; i += blockDim.x) a += partial[i];
-            for (int i = qlo + threadIdx.x; i < qhi; i += blockDim.x) a += colq[i];
-            a = block_sum<double>(a, sRed);
-            if (threadIdx.x == 0) { *xLx_out = a; *ticket = 0u; }
-        }
+        if (threadIdx.x == 0) partial[blockIdx.y * gridDim.x + blockIdx.x] = tot;
     }
+}
+
+// x^T L x = sum of the per-CTA partials + the constant I^T L I of the column window (per-column float64 sums of the build)
+__global__ void __launch_bounds__(256)
+lap_dia_sum_kernel(const double* __restrict__ partial, int n, const double* __restrict__ colq, int qlo, int qhi,
+                   double* __restrict__ out) {
+    __shared__ double red[32];
+    double a = 0.0;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) a += partial[i];
+    for (int i = qlo + threadIdx.x; i < qhi; i += blockDim.x) a += colq[i];
+    a = block_sum<double>(a, red);
+    if (threadIdx.x == 0) *out = a;
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -318,11 +346,13 @@ int dia_matvec(adpst_laplacian* h, const float* x, float* y, double y_scale, dou
     dim3 grid((h->W + DT_W - 1) / DT_W, (h->H + DT_H - 1) / DT_H);
     if (int(grid.x * grid.y) > h->npartials)
         return fail(ADPST_ERR_INVALID, "laplacian: partial buffer too small (%d > %d)", int(grid.x * grid.y), h->npartials);
-    unsigned int* ticket = reinterpret_cast<unsigned int*>(h->partials + h->npartials);
     lap_dia_kernel<<<grid, DT_THREADS, 0, st>>>(x, static_cast<const float*>(h->image), h->dia_LI, h->dia_coef, y,
-                                                xLx ? h->partials : nullptr, h->H, h->W, float(y_scale), qlo, qhi, ticket, xLx,
-                                                h->dia_qI);
+                                                xLx ? h->partials : nullptr, h->H, h->W, float(y_scale), qlo, qhi);
     ADPST_LAUNCH_CHECK();
+    if (xLx) {
+        lap_dia_sum_kernel<<<1, 256, 0, st>>>(h->partials, int(grid.x * grid.y), h->dia_qI, qlo, qhi, xLx);
+        ADPST_LAUNCH_CHECK();
+    }
     return ADPST_OK;
 }
 

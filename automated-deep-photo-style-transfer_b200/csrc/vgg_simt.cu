@@ -506,6 +506,46 @@ void adpst_vgg_destroy(adpst_vgg* h) {
     delete h;
 }
 
+// convolutions first..last of the network; the input of conv `first` is the image (first == 0), the pooled tensor before
+// it, or the previous convolution's output
+static int vgg_forward_range(adpst_vgg* h, const float* image_dev, int H, int W, float* const* acts_dev, float* const* pools_dev,
+                             int first, int last, cudaStream_t st) {
+    using namespace adpst;
+    const float* x = image_dev;
+    if (first > 0) {
+        x = acts_dev[first - 1];
+        for (int j = 0; j < ADPST_VGG_NUM_POOL; ++j)
+            if (kPoolAfter[j] == first - 1) x = pools_dev[j];
+        ADPST_REQUIRE(x != nullptr, "vgg_forward: the input of conv %d is NULL", first);
+    }
+    ADPST_CUDA_CHECK(cudaMemsetAsync(h->amax + AMAX_ACT + first, 0, (last - first + 1) * sizeof(uint32_t), st));
+    for (int i = first; i <= last; ++i) {
+        int lh, lw;
+        layer_hw(i, H, W, &lh, &lw);
+        ADPST_REQUIRE(acts_dev[i] != nullptr, "vgg_forward: acts[%d] is NULL", i);
+        // a max-pool keeps the maximum of a post-ReLU map, so the pooled tensor shares the slot of the conv before it
+        float* pool_out = nullptr;                 // the tensor-core kernel pools in its epilogue
+        for (int j = 0; j < ADPST_VGG_NUM_POOL; ++j)
+            if (kPoolAfter[j] == i && pools_dev[j] != nullptr) pool_out = pools_dev[j];
+        bool pooled = false;
+        int rc = launch_conv(h, i, MODE_FWD, x, acts_dev[i], nullptr, nullptr, lh, lw, i > 0 ? h->amax + AMAX_ACT + i - 1 : nullptr,
+                             h->amax + AMAX_ACT + i, st, pool_out, &pooled);
+        if (rc != ADPST_OK) return rc;
+        x = acts_dev[i];
+        if (pool_out != nullptr) {
+            if (!pooled) {
+                const size_t items = size_t(lh / 2) * (lw / 2) * (conv_cout(i) / 4);
+                if (items > 0) {
+                    maxpool2_kernel<<<stream_grid(items), 256, 0, st>>>(acts_dev[i], pool_out, lh, lw, conv_cout(i));
+                    ADPST_LAUNCH_CHECK();
+                }
+            }
+            x = pool_out;
+        }
+    }
+    return ADPST_OK;
+}
+
 int adpst_vgg_forward(adpst_vgg* h, const float* image_dev, int H, int W, float* const* acts_dev,
                       float* const* pools_dev, int last, adpst_stream_t stream) {
     using namespace adpst;
@@ -514,39 +554,30 @@ int adpst_vgg_forward(adpst_vgg* h, const float* image_dev, int H, int W, float*
     ADPST_REQUIRE(H >= 1 && W >= 1, "vgg_forward: empty image");
     ADPST_REQUIRE((H >> pools_before(last)) >= 1 && (W >> pools_before(last)) >= 1,
                   "vgg_forward: %dx%d image is too small for conv %d", H, W, last);
-    cudaStream_t st = as_stream(stream);
-    const float* x = image_dev;
-    ADPST_CUDA_CHECK(cudaMemsetAsync(h->amax + AMAX_ACT, 0, kNumConv * sizeof(uint32_t), st));
-    for (int i = 0; i <= last; ++i) {
-        int lh, lw;
-        layer_hw(i, H, W, &lh, &lw);
-        ADPST_REQUIRE(acts_dev[i] != nullptr, "vgg_forward: acts[%d] is NULL", i);
-        // a max-pool keeps the maximum of a post-ReLU map, so the pooled tensor shares the slot of the conv before it
-        float* pool_out = nullptr;                 // the tensor-core kernel pools in its epilogue
-        for (int j = 0; j < ADPST_VGG_NUM_POOL; ++j)
-            if (kPoolAfter[j] == i && i < last) {
-                ADPST_REQUIRE(pools_dev[j] != nullptr, "vgg_forward: pools[%d] is NULL", j);
-                pool_out = pools_dev[j];
-            }
-        bool pooled = false;
-        int rc = launch_conv(h, i, MODE_FWD, x, acts_dev[i], nullptr, nullptr, lh, lw, i > 0 ? h->amax + AMAX_ACT + i - 1 : nullptr,
-                             h->amax + AMAX_ACT + i, st, pool_out, &pooled);
-        if (rc != ADPST_OK) return rc;
-        x = acts_dev[i];
-        for (int j = 0; j < ADPST_VGG_NUM_POOL; ++j) {
-            if (kPoolAfter[j] == i && i < last) {
-                if (!pooled) {
-                    const size_t items = size_t(lh / 2) * (lw / 2) * (conv_cout(i) / 4);
-                    if (items > 0) {
-                        maxpool2_kernel<<<stream_grid(items), 256, 0, st>>>(acts_dev[i], pools_dev[j], lh, lw, conv_cout(i));
-                        ADPST_LAUNCH_CHECK();
-                    }
-                }
-                x = pools_dev[j];
-            }
-        }
+    // the pool after conv `last` is not part of the extractor
+    float* pools[ADPST_VGG_NUM_POOL];
+    for (int j = 0; j < ADPST_VGG_NUM_POOL; ++j) {
+        pools[j] = kPoolAfter[j] < last ? pools_dev[j] : nullptr;
+        ADPST_REQUIRE(kPoolAfter[j] >= last || pools[j] != nullptr, "vgg_forward: pools[%d] is NULL", j);
     }
-    return ADPST_OK;
+    return vgg_forward_range(h, image_dev, H, W, acts_dev, pools, 0, last, as_stream(stream));
+}
+
+int adpst_vgg_forward_range(adpst_vgg* h, const float* image_dev, int H, int W, float* const* acts_dev,
+                            float* const* pools_dev, int first, int last, adpst_stream_t stream) {
+    using namespace adpst;
+    ADPST_REQUIRE(h && acts_dev && pools_dev, "vgg_forward_range: NULL argument");
+    ADPST_REQUIRE(first >= 0 && first <= last && last < kNumConv, "vgg_forward_range: bad range %d..%d", first, last);
+    ADPST_REQUIRE(first > 0 || image_dev != nullptr, "vgg_forward_range: the image is NULL");
+    ADPST_REQUIRE(H >= 1 && W >= 1 && (H >> pools_before(last)) >= 1 && (W >> pools_before(last)) >= 1,
+                  "vgg_forward_range: %dx%d image is too small for conv %d", H, W, last);
+    return vgg_forward_range(h, image_dev, H, W, acts_dev, pools_dev, first, last, as_stream(stream));
+}
+
+int adpst_absmax_update(const float* x_dev, size_t n, uint32_t* slot_dev, adpst_stream_t stream) {
+    using namespace adpst;
+    ADPST_REQUIRE(x_dev && slot_dev, "absmax_update: NULL argument");
+    return launch_absmax(x_dev, n, slot_dev, as_stream(stream), false);
 }
 
 int adpst_vgg_set_conv_path(adpst_vgg* h, int path) {
@@ -581,35 +612,44 @@ int adpst_vgg_conv_dgrad(adpst_vgg* h, int i, const float* dpre_dev, int lh, int
     return launch_conv(h, i, MODE_BWD, dpre_dev, dx_dev, nullptr, nullptr, lh, lw, dpre_absmax_dev, nullptr, as_stream(stream));
 }
 
-int adpst_vgg_backward(adpst_vgg* h, int H, int W, const float* const* acts_dev, const float* const* pools_dev,
-                       const float* const* seeds_dev, int last, float* scratch0_dev, float* scratch1_dev,
-                       float* dimage_dev, adpst_stream_t stream) {
+// Backward through convs last..first.  The chain enters either at the top (dpool_in == NULL: the seed of conv `last` goes
+// through its ReLU mask) or below a pool (dpool_in = dLoss/d(pooled output of conv `last`), routed through the un-pool, the
+// ReLU mask and the seed of conv `last`).  It leaves either at the image (first == 0: out = dLoss/d(image)) or above a pool
+// (first > 0 must be the first convolution of a block: out = dLoss/d(pooled input of conv `first`)).
+static int vgg_backward_range(adpst_vgg* h, int H, int W, const float* const* acts_dev, const float* const* seeds_dev, int first,
+                              int last, const float* dpool_in, float* scratch0_dev, float* scratch1_dev, float* out_dev,
+                              cudaStream_t st) {
     using namespace adpst;
-    (void)pools_dev;
-    ADPST_REQUIRE(h && acts_dev && seeds_dev && scratch0_dev && scratch1_dev && dimage_dev, "vgg_backward: NULL argument");
-    ADPST_REQUIRE(last >= 0 && last < kNumConv, "vgg_backward: last=%d out of range", last);
-    ADPST_REQUIRE(seeds_dev[last] != nullptr, "vgg_backward: the seed of the last layer (%d) is required", last);
-    cudaStream_t st = as_stream(stream);
     float* cur = scratch0_dev;   // holds dLoss/d(pre-activation of conv i)
     float* nxt = scratch1_dev;
     int lh, lw;
     layer_hw(last, H, W, &lh, &lw);
     uint32_t* gmax = h->amax + AMAX_GRAD;          // gmax[i]: max|dLoss/d(pre-activation of conv i)|
-    ADPST_CUDA_CHECK(cudaMemsetAsync(gmax, 0, kNumConv * sizeof(uint32_t), st));
-    {
+    ADPST_CUDA_CHECK(cudaMemsetAsync(gmax + first, 0, (last - first + 1) * sizeof(uint32_t), st));
+    if (dpool_in == nullptr) {
+        ADPST_REQUIRE(seeds_dev[last] != nullptr, "vgg_backward: the seed of the last layer (%d) is required", last);
         const size_t n4 = size_t(lh) * lw * conv_cout(last) / 4;
         relu_mask_kernel<<<stream_grid(n4), 256, 0, st>>>(acts_dev[last], seeds_dev[last], cur, n4, gmax + last);
         ADPST_LAUNCH_CHECK();
+    } else {
+        const size_t items = size_t((lh + 1) / 2) * ((lw + 1) / 2) * (conv_cout(last) / 4);
+        unpool_relu_kernel<<<stream_grid(items), 256, 0, st>>>(acts_dev[last], dpool_in, seeds_dev[last], cur, lh, lw,
+                                                               conv_cout(last), gmax + last);
+        ADPST_LAUNCH_CHECK();
     }
-    for (int i = last; i >= 1; --i) {
+    for (int i = last; i >= (first > 0 ? first : 1); --i) {
         layer_hw(i, H, W, &lh, &lw);
         bool pooled_input = false;
         for (int j = 0; j < ADPST_VGG_NUM_POOL; ++j) pooled_input |= (kPoolAfter[j] == i - 1);
         if (!pooled_input) {
             // input of conv i is the post-ReLU output of conv i-1 at the same resolution
+            ADPST_REQUIRE(i > first, "vgg_backward: conv %d is not the first convolution of a block", first);
             int rc = launch_conv(h, i, MODE_BWD, cur, nxt, seeds_dev[i - 1], acts_dev[i - 1], lh, lw, gmax + i, gmax + i - 1, st);
             if (rc != ADPST_OK) return rc;
             float* t = cur; cur = nxt; nxt = t;
+        } else if (i == first) {
+            // leave above the pool: gradient w.r.t. the pooled tensor straight into the caller's buffer
+            return launch_conv(h, i, MODE_BWD, cur, out_dev, nullptr, nullptr, lh, lw, gmax + i, nullptr, st);
         } else {
             // gradient w.r.t. the pooled tensor, then route through the pool + ReLU of conv i-1
             int rc = launch_conv(h, i, MODE_BWD, cur, nxt, nullptr, nullptr, lh, lw, gmax + i, nullptr, st);
@@ -624,9 +664,37 @@ int adpst_vgg_backward(adpst_vgg* h, int H, int W, const float* const* acts_dev,
     }
     ADPST_ONCE_PER_DEVICE(ADPST_CUDA_CHECK(cudaFuncSetAttribute(conv1_dgrad_image_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, IG_SMEM)));
     dim3 grid((W + IG_TW - 1) / IG_TW, (H + IG_TH - 1) / IG_TH);
-    conv1_dgrad_image_kernel<<<grid, IG_THREADS, IG_SMEM, st>>>(cur, h->wg0, dimage_dev, H, W);
+    conv1_dgrad_image_kernel<<<grid, IG_THREADS, IG_SMEM, st>>>(cur, h->wg0, out_dev, H, W);
     ADPST_LAUNCH_CHECK();
     return ADPST_OK;
+}
+
+int adpst_vgg_backward(adpst_vgg* h, int H, int W, const float* const* acts_dev, const float* const* pools_dev,
+                       const float* const* seeds_dev, int last, float* scratch0_dev, float* scratch1_dev,
+                       float* dimage_dev, adpst_stream_t stream) {
+    using namespace adpst;
+    (void)pools_dev;
+    ADPST_REQUIRE(h && acts_dev && seeds_dev && scratch0_dev && scratch1_dev && dimage_dev, "vgg_backward: NULL argument");
+    ADPST_REQUIRE(last >= 0 && last < kNumConv, "vgg_backward: last=%d out of range", last);
+    return vgg_backward_range(h, H, W, acts_dev, seeds_dev, 0, last, nullptr, scratch0_dev, scratch1_dev, dimage_dev,
+                              as_stream(stream));
+}
+
+int adpst_vgg_backward_range(adpst_vgg* h, int H, int W, const float* const* acts_dev, const float* const* seeds_dev, int first,
+                             int last, const float* dpool_in_dev, float* scratch0_dev, float* scratch1_dev, float* out_dev,
+                             adpst_stream_t stream) {
+    using namespace adpst;
+    ADPST_REQUIRE(h && acts_dev && seeds_dev && scratch0_dev && scratch1_dev && out_dev, "vgg_backward_range: NULL argument");
+    ADPST_REQUIRE(first >= 0 && first <= last && last < kNumConv, "vgg_backward_range: bad range %d..%d", first, last);
+    bool block_start = first == 0, pooled_top = false;
+    for (int j = 0; j < ADPST_VGG_NUM_POOL; ++j) {
+        block_start |= (kPoolAfter[j] == first - 1);
+        pooled_top |= (kPoolAfter[j] == last);
+    }
+    ADPST_REQUIRE(block_start, "vgg_backward_range: conv %d does not follow a pool", first);
+    ADPST_REQUIRE(dpool_in_dev == nullptr || pooled_top, "vgg_backward_range: conv %d is not followed by a pool", last);
+    return vgg_backward_range(h, H, W, acts_dev, seeds_dev, first, last, dpool_in_dev, scratch0_dev, scratch1_dev, out_dev,
+                              as_stream(stream));
 }
 
 }  // extern "C"

@@ -46,15 +46,7 @@ class Adam:
         return 0 if self._slots is None else self._slots.step
 
 
-_GRAPH_POOLS, _SIDE_STREAMS = {}, {}
-
-
-def _graph_pool(device):
-    """One private CUDA-graph memory pool per device, shared by every captured train step."""
-    key = torch.device(device).index if torch.device(device).index is not None else torch.cuda.current_device()
-    if key not in _GRAPH_POOLS:
-        _GRAPH_POOLS[key] = torch.cuda.graph_pool_handle()
-    return _GRAPH_POOLS[key]
+_SIDE_STREAMS = {}
 
 
 def _side_stream(device):
@@ -105,11 +97,11 @@ def make_train_step(features_extractor, compute_loss, optimizer, use_cuda_graph=
             # Capture with the raw CUDAGraph API: the torch.cuda.graph() context manager runs gc.collect() and
             # torch.cuda.empty_cache() on entry, which hands every cached block back to the driver -- measured 0.3 s per
             # capture plus a cudaMalloc for every buffer of the next pair.  The step allocates nothing while it is captured
-            # (every buffer was created by the warm-up), so one shared private pool per device is enough.
+            # (every buffer was created by the warm-up), so the graph's private pool stays empty.
             g = torch.cuda.CUDAGraph()
             s.wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(s):
-                g.capture_begin(pool=_graph_pool(image.device))
+                g.capture_begin()
                 try:
                     out = eager_step(image)
                 finally:

@@ -114,6 +114,12 @@ int adpst_vgg_pool_shape(int j, int H, int W, int* h, int* w, int* c);
 int adpst_vgg_forward(adpst_vgg* h, const float* image_dev, int H, int W, float* const* acts_dev,
                       float* const* pools_dev, int last, adpst_stream_t stream);
 
+/* The same for convolutions first..last only (spatially tiled runs exchange halo columns between blocks): the input of conv
+ * `first` is image_dev (first == 0), pools_dev[j] if a pool precedes it, else acts_dev[first-1].  pools_dev[j] may be NULL for
+ * pools that are not wanted. */
+int adpst_vgg_forward_range(adpst_vgg* h, const float* image_dev, int H, int W, float* const* acts_dev,
+                            float* const* pools_dev, int first, int last, adpst_stream_t stream);
+
 /* Convolution kernel family used by this handle: 0 = tcgen05 3xFP16 implicit GEMM, float32-accurate (default;
  * block1_conv1 and the gradient to the image always use the CUDA-core kernels), 1 = exact-float32 CUDA-core kernels
  * everywhere (validation). */
@@ -124,6 +130,9 @@ int adpst_vgg_set_conv_path(adpst_vgg* h, int path);
  * consumer; tensors that enter from outside either come with a device slot holding the float32 bit pattern of
  * max|x| (adpst_absmax) or the entry point measures it with one extra pass (slot argument NULL). */
 int adpst_absmax(const float* x_dev, size_t n, uint32_t* slot_dev, adpst_stream_t stream);
+/* *slot_dev = max(*slot_dev, max|x|): for tensors that were patched after their producer recorded the slot (halo columns
+ * received from a neighbouring rank). */
+int adpst_absmax_update(const float* x_dev, size_t n, uint32_t* slot_dev, adpst_stream_t stream);
 /* slot of conv i's output as left by the most recent adpst_vgg_forward on this handle (device pointer). */
 const uint32_t* adpst_vgg_act_absmax(const adpst_vgg* h, int i);
 
@@ -142,6 +151,14 @@ int adpst_vgg_conv_dgrad(adpst_vgg* h, int i, const float* dpre_dev, int lh, int
 int adpst_vgg_backward(adpst_vgg* h, int H, int W, const float* const* acts_dev, const float* const* pools_dev,
                        const float* const* seeds_dev, int last, float* scratch0_dev, float* scratch1_dev,
                        float* dimage_dev, adpst_stream_t stream);
+
+/* Backward through convs last..first only.  dpool_in_dev: NULL (the chain starts at conv `last` with its seed) or
+ * dLoss/d(pooled output of conv `last`) (conv `last` must be followed by a pool).  first must be 0 (out_dev = dLoss/d(image))
+ * or the first convolution after a pool (out_dev = dLoss/d(that pooled tensor)).  Spatially tiled runs exchange the halo
+ * columns of these pooled-tensor gradients between the calls. */
+int adpst_vgg_backward_range(adpst_vgg* h, int H, int W, const float* const* acts_dev, const float* const* seeds_dev, int first,
+                             int last, const float* dpool_in_dev, float* scratch0_dev, float* scratch1_dev, float* out_dev,
+                             adpst_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Loss terms: components/loss.py

@@ -10,6 +10,12 @@ What can be executed from the reference without TensorFlow (SURVEY §8c, App. B3
   * components/matting_v2.py and components/loss.py: their own code over oracle/tf_shim.py, a numpy stand-in for the
     few TensorFlow primitives they call (the shim's header says which two of those rest on documented TF behaviour)
 The VGG19 arithmetic (Keras) and the optimiser (tf.optimizers.Adam) cannot be executed and stay "parity unpinned".
+
+SECURITY NOTE: this script exec()s third-party Python from /root/reference (untrusted public content) inside the calling
+process, with the caller's privileges.  Run it ONLY in a throw-away sandbox without network access or credentials (the
+authoring container is one).  Nothing under tests/ or the product package ever imports the reference; the committed .npz
+files are plain arrays.  `python oracle/make_golden.py --provenance` (re)writes tests/golden/PROVENANCE.json with the sha256
+of every reference file that was executed, so the origin of the vectors can be audited against a given checkout.
 """
 import importlib.util
 import os
@@ -49,6 +55,24 @@ def _load(path, name):
     mod = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(mod)
     return mod
+
+
+EXECUTED_REFERENCE_FILES = ["components/matting_v3.py", "components/semantic_merge.py", "components/matting_v2.py",
+                            "components/loss.py"]
+
+
+def write_provenance():
+    """sha256 of the reference files this script executes -> tests/golden/PROVENANCE.json."""
+    import hashlib
+    import json
+    rec = {"reference_root": REF, "generator": "oracle/make_golden.py", "executed_files": {}}
+    for rel in EXECUTED_REFERENCE_FILES:
+        with open(os.path.join(REF, rel), "rb") as f:
+            rec["executed_files"][rel] = hashlib.sha256(f.read()).hexdigest()
+    rec["golden_files"] = sorted(f for f in os.listdir(OUT) if f.endswith(".npz"))
+    with open(os.path.join(OUT, "PROVENANCE.json"), "w") as f:
+        json.dump(rec, f, indent=1, sort_keys=True)
+    return rec
 
 
 def main():
@@ -162,5 +186,9 @@ def main_tf_shim():
 
 
 if __name__ == "__main__":
-    main()
-    main_tf_shim()
+    if "--provenance" in sys.argv:
+        print(write_provenance())
+    else:
+        main()
+        main_tf_shim()
+        write_provenance()

@@ -127,6 +127,50 @@ def v2_direct(image, x, epsilon, r):
     return y.reshape(H * W, Cx)
 
 
+def _chol3_solve_ld(M, R):
+    """Solve M A = R for symmetric positive definite 3x3 M in np.longdouble by Cholesky (np.linalg has no longdouble)."""
+    l00 = np.sqrt(M[0, 0]); l10 = M[0, 1] / l00; l20 = M[0, 2] / l00
+    l11 = np.sqrt(M[1, 1] - l10 * l10); l21 = (M[1, 2] - l20 * l10) / l11
+    l22 = np.sqrt(M[2, 2] - l20 * l20 - l21 * l21)
+    z0 = R[0] / l00; z1 = (R[1] - l10 * z0) / l11; z2 = (R[2] - l20 * z0 - l21 * z1) / l22
+    a2 = z2 / l22; a1 = (z1 - l21 * a2) / l11; a0 = (z0 - l10 * a1 - l20 * a2) / l00
+    return np.stack([a0, a1, a2])
+
+
+def v2_extended_precision(image, x, epsilon, r=1):
+    """The v2 operator (same definition as v2_direct / matting_v2.py) evaluated in np.longdouble (64-bit mantissa on x86) with
+    centred window moments and Cholesky solves.  It exists because the reference's own float64 arithmetic is NOT accurate
+    where the result is a tiny remainder: at x = I (iteration 0) |L I| ~ 1e-7 and integral images plus explicit 3x3 inverses
+    leave ~1e-11 of absolute noise (4.7e-5 relative on I^T L I for a grey 2x3 image), more than the GPU kernel's error, so
+    that case is judged against this restatement.  O(HW (2r+1)^2) Python loops: small inputs only."""
+    LD = np.longdouble
+    image = np.asarray(image, LD)
+    H, W, C = image.shape
+    x = np.asarray(x, LD).reshape(H, W, -1)
+    Cx = x.shape[-1]
+    d = 2 * r + 1
+    n = d * d
+    It = np.pad(image, [(r, r), (r, r), (0, 0)], mode="symmetric")
+    xt = np.pad(x, [(r, r), (r, r), (0, 0)], mode="symmetric")
+    a = np.zeros((H, W, C, Cx), LD)
+    b = np.zeros((H, W, Cx), LD)
+    for i in range(H):
+        for j in range(W):
+            wi = It[i:i + d, j:j + d].reshape(n, C)
+            wx = xt[i:i + d, j:j + d].reshape(n, Cx)
+            mu, pb = wi.mean(0), wx.mean(0)
+            ci, cx = wi - mu, wx - pb
+            a[i, j] = _chol3_solve_ld(ci.T @ ci + LD(epsilon) * np.eye(C, dtype=LD), ci.T @ cx)
+            b[i, j] = pb - a[i, j].T @ mu
+    at = np.pad(a, [(r, r), (r, r), (0, 0), (0, 0)], mode="symmetric")
+    bt = np.pad(b, [(r, r), (r, r), (0, 0)], mode="symmetric")
+    y = np.zeros((H, W, Cx), LD)
+    for i in range(H):
+        for j in range(W):
+            y[i, j] = n * x[i, j] - (at[i:i + d, j:j + d].sum((0, 1)).T @ image[i, j] + bt[i:i + d, j:j + d].sum((0, 1)))
+    return y.reshape(H * W, Cx)
+
+
 # --------------------------------------------------------------------------------------
 # v3: explicit COO Laplacian, interior windows only (matting_v3.py:61-100)
 # --------------------------------------------------------------------------------------

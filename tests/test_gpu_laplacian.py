@@ -236,16 +236,22 @@ def test_diagonal_format_kernel_matches_oracle(mode, H, W, kind, synth):
              "identity": I.copy()}
     for name, xx in cases.items():
         want = ref.matmul(xx.astype(np.float64)) if ref is not None else np.zeros((H * W, 3))
+        floor, qtol = 1e-12, 1e-6
+        if name == "identity":
+            # |L I| is ~1e-7..1e-6, a remainder of O(1) terms.  The reference's own float64 arithmetic (integral images over
+            # the whole picture, explicit 3x3 inverses) leaves ~1e-11..1e-10 of ABSOLUTE noise there (4.7e-5 relative on
+            # I^T L I of the grey 2x3 case), more than the kernel's error; so small v2 cases are judged against the
+            # extended-precision restatement, the others carry that absolute floor.
+            if mode == "v2" and H * W <= 600:
+                want = np.asarray(matting.v2_extended_precision(img32, xx, eps), np.float64)
+            else:
+                floor, qtol = 1e-9, 1e-4
         y, q = op.quadratic_form(torch.as_tensor(xx).cuda(), want_y=True, y_scale=3.0)
         got = y.cpu().numpy().astype(np.float64) / 3.0
         scale = np.abs(want).max()
-        if name == "identity":
-            # |L I| is ~1e-7: as accurate as the float64 kernel (the reference's own cumsum arithmetic is the limit)
-            assert np.abs(got - want).max() <= 2e-6 * scale + 1e-13, (name, np.abs(got - want).max(), scale)
-        else:
-            assert np.abs(got - want).max() <= 1e-6 * scale + 1e-12, (name, np.abs(got - want).max(), scale)
+        assert np.abs(got - want).max() <= 1e-6 * scale + floor, (name, np.abs(got - want).max(), scale)
         quad = float(np.sum(xx.astype(np.float64) * want))
-        assert abs(float(q) - quad) <= 1e-6 * abs(quad) + 1e-12, (name, float(q), quad)
+        assert abs(float(q) - quad) <= qtol * abs(quad) + floor, (name, float(q), quad)
     if W >= 8:                                   # the scalar restricted to a column window (spatially tiled runs)
         xx = cases["first_adam_step"]
         want = ref.matmul(xx.astype(np.float64)) if ref is not None else np.zeros((H * W, 3))

@@ -91,3 +91,41 @@ def test_operator_is_a_symmetric_5x5_stencil_with_zero_row_sums(synth):
         A = np.asarray(op.matmul(np.eye(H * W)))
         s = np.abs(A).max()
         assert np.abs(A - A.T).max() < 1e-9 * s and np.abs(A[far]).max() < 1e-9 * s and np.abs(A.sum(1)).max() < 1e-9 * s
+
+
+def test_golden_provenance_is_recorded():
+    """tests/golden/PROVENANCE.json names the reference files whose own code produced the vectors (sha256); where the
+    reference checkout is present (the authoring container) the hashes must still match."""
+    import hashlib
+    import json
+    import os
+    from conftest import GOLDEN
+    rec = json.load(open(os.path.join(GOLDEN, "PROVENANCE.json")))
+    assert set(rec["executed_files"]) == {"components/matting_v3.py", "components/semantic_merge.py",
+                                          "components/matting_v2.py", "components/loss.py"}
+    assert set(rec["golden_files"]) == {f for f in os.listdir(GOLDEN) if f.endswith(".npz")}
+    if os.path.isdir(rec["reference_root"]):
+        for rel, digest in rec["executed_files"].items():
+            with open(os.path.join(rec["reference_root"], rel), "rb") as f:
+                assert hashlib.sha256(f.read()).hexdigest() == digest, rel
+
+
+def test_extended_precision_restatement_agrees_with_the_oracle(synth=None):
+    """oracle.matting.v2_extended_precision (np.longdouble, centred moments, Cholesky) against the float64 restatements:
+    identical to ~1e-14 for generic x; at x = I on a grey (rank-1 covariance) image the float64 oracle itself is only good
+    to ~1e-5 relative on I^T L I, which is why the GPU tests judge that case against the extended-precision version."""
+    import importlib
+    from conftest import PKG_NAME
+    synth = importlib.import_module(PKG_NAME + ".synth")
+    img = synth.image(7, 9, 3)[0]
+    x = np.random.default_rng(0).random((63, 3))
+    a = np.asarray(matting.v2_extended_precision(img, x, 1e-7), np.float64)
+    b = matting.V2Operator(img.astype(np.float64), 1e-7, 1).matmul(x)
+    assert np.abs(a - b).max() < 1e-11 * np.abs(b).max()
+    g = np.ascontiguousarray(np.repeat(synth.smooth_image(8, 8, 44)[0][:2, :3, :1], 3, -1))
+    I = g.reshape(-1, 3)
+    t = matting.v2_extended_precision(g, I, 1e-7)
+    o = matting.V2Operator(g.astype(np.float64), 1e-7, 1).matmul(I.astype(np.float64))
+    qt, qo = float((np.asarray(I, np.longdouble) * t).sum()), float((I.astype(np.float64) * o).sum())
+    assert qt > 0 and abs(qo - qt) < 1e-3 * qt          # same quantity ...
+    print("I^T L I: extended %.12e, float64 oracle %.12e (relative difference %.1e)" % (qt, qo, abs(qo - qt) / qt))
