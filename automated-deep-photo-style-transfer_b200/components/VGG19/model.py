@@ -16,6 +16,7 @@ from ...synth import CONV_LAYERS
 
 LAYER_INDEX = {name: i for i, (name, _, _) in enumerate(CONV_LAYERS)}
 POOL_AFTER = (1, 3, 7, 11)
+BLOCKS = ((0, 1), (2, 3), (4, 7), (8, 11), (12, 12))      # conv index ranges of block1 .. block5
 
 
 def _load_weights(weights):
@@ -70,6 +71,13 @@ class VGG19Handle:
     def act_absmax_ptr(self, i):
         """Device address of the slot holding max|conv i output| of the latest forward pass."""
         return _lib.lib().adpst_vgg_act_absmax(self._h, i)
+
+    def absmax_update(self, t, i):
+        """Raise the slot of conv i's output to max|t| if that is larger (t: data patched into the tensor after its producer
+        ran, e.g. halo columns received from a neighbouring rank)."""
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.lib().adpst_absmax_update(_lib.ptr(t), t.numel(), ctypes.c_void_p(self.act_absmax_ptr(i)),
+                                                      _lib.stream_ptr()))
 
     def __del__(self):
         h, self._h = getattr(self, "_h", None), None
@@ -168,6 +176,81 @@ class StyleContentModel:
         content = {n: o for n, o in zip(names[:self.limit], outs[:self.limit])}
         style = {n: o for n, o in zip(names[self.limit:], outs[self.limit:])}
         return {"content": content, "style": style}
+
+    # ---- spatially tiled runs (tiled.py): block by block, with a halo exchange on every tensor that crosses a pool --------
+    def forward_blocks(self, inputs, exchange, reuse=True):
+        """Like call(), but the network runs one block at a time and `exchange(level, tensor)` is called on every pooled
+        tensor (level 1..4: the input of block level+1) before the next block reads it.  `exchange` overwrites the halo
+        columns in place with the neighbours' data and returns the received slabs (contiguous tensors) or an empty list."""
+        if inputs.dim() != 4 or inputs.shape[0] != 1 or inputs.shape[3] != 3 or inputs.dtype != torch.float32 or not inputs.is_cuda:
+            raise TypeError("expected a float32 CUDA image of shape (1, H, W, 3)")
+        x = inputs.contiguous()
+        H, W = int(x.shape[1]), int(x.shape[2])
+        if reuse:
+            if self._loop is None or (self._loop.H, self._loop.W) != (H, W):
+                self._loop = Activations(H, W, self.last_index, self.device)
+            A = self._loop
+        else:
+            A = Activations(H, W, self.last_index, self.device)
+        L = _lib.lib()
+        for b, (first, last) in enumerate(BLOCKS):
+            if first > self.last_index:
+                break
+            last = min(last, self.last_index)
+            with torch.cuda.device(self.device):
+                _lib.check(L.adpst_vgg_forward_range(self.vgg._h, _lib.ptr(x), H, W, _lib.ptr_array(A.acts),
+                                                     _lib.ptr_array(A.pools), first, last, _lib.stream_ptr()))
+            if b < len(POOL_AFTER) and A.pools[b] is not None and last == POOL_AFTER[b]:
+                for slab in exchange(b + 1, A.pools[b]):
+                    self.vgg.absmax_update(slab, last)          # a pooled tensor shares the scale slot of the conv before it
+        self.last = A
+        self.vgg.generation += 1
+        names = self.content_layers + self.style_layers
+        outs = [A.acts[i] for i in self.indices]
+        for i, o in zip(self.indices, outs):
+            o._adpst_absmax = (weakref.ref(self.vgg), self.vgg.generation, i)
+        content = {n: o for n, o in zip(names[:self.limit], outs[:self.limit])}
+        style = {n: o for n, o in zip(names[self.limit:], outs[self.limit:])}
+        return {"content": content, "style": style}
+
+    def backward_blocks(self, seeds, exchange, out=None):
+        """Like backward(), block by block from the top: the gradient w.r.t. every pooled tensor is handed to
+        `exchange(level, tensor)` (halo columns replaced by the owners' complete values) before the block below uses it."""
+        A = self.last
+        if A is None:
+            raise RuntimeError("backward_blocks() needs a preceding forward call")
+        arr = [None] * _lib.VGG_NUM_CONV
+        for n, t in seeds.items():
+            i = LAYER_INDEX[n]
+            if t.shape != A.acts[i].shape or t.dtype != torch.float32 or not t.is_contiguous():
+                raise ValueError("seed for %s must be a contiguous float32 tensor of shape %s" % (n, tuple(A.acts[i].shape)))
+            arr[i] = t
+        top = max(i for i, t in enumerate(arr) if t is not None)
+        if self._scratch is None or self._scratch[0].numel() < A.acts[0].numel():
+            self._scratch = (torch.empty(A.acts[0].numel(), dtype=torch.float32, device=self.device),
+                             torch.empty(A.acts[0].numel(), dtype=torch.float32, device=self.device))
+        if out is None:
+            out = torch.empty(1, A.H, A.W, 3, dtype=torch.float32, device=self.device)
+        if self._dpool is None or self._dpool[0].shape != A.pools[0].shape:
+            self._dpool = [torch.empty_like(p) if p is not None else None for p in A.pools]
+        L = _lib.lib()
+        dpool = None
+        for b in reversed(range(len(BLOCKS))):
+            first, last = BLOCKS[b]
+            if first > top:
+                continue
+            last = min(last, top)
+            target = out if first == 0 else self._dpool[b - 1]
+            with torch.cuda.device(self.device):
+                _lib.check(L.adpst_vgg_backward_range(self.vgg._h, A.H, A.W, _lib.ptr_array(A.acts), _lib.ptr_array(arr), first,
+                                                      last, _lib.ptr(dpool), _lib.ptr(self._scratch[0]),
+                                                      _lib.ptr(self._scratch[1]), _lib.ptr(target), _lib.stream_ptr()))
+            if first > 0:
+                exchange(b, target)
+                dpool = target
+        return out
+
+    _dpool = None
 
     def backward(self, seeds, out=None):
         """seeds: dict layer name -> dLoss/d(layer output) (1,h,w,C) float32.  Returns dLoss/d(image) (1,H,W,3)."""

@@ -221,12 +221,13 @@ class Loss:
         loss_dict['Total loss'] = self._out[4]                                # loss.py:76
         return loss_dict
 
-    def gradient(self, extractor, out=None):
+    def gradient(self, extractor, out=None, backward=None):
         """d(Total loss)/d(image) for the latest compute_loss call: the role of tape.gradient in
-        style_transfer.py:341.  `extractor` is the StyleContentModel whose outputs were passed in."""
+        style_transfer.py:341.  `extractor` is the StyleContentModel whose outputs were passed in.
+        backward (extension, tiled.py): callable (seeds, out) -> gradient that replaces extractor.backward."""
         if self._seeds is None:
             raise RuntimeError("gradient() needs a preceding compute_loss() call")
-        g = extractor.backward(self._seeds, out=out)
+        g = extractor.backward(self._seeds, out=out) if backward is None else backward(self._seeds, out)
         if self._photo_grad is not None:
             kernels.axpby(g, g, 1.0, self._photo_grad.reshape(g.shape), 1.0)
         return g

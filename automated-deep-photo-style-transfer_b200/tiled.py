@@ -1,20 +1,27 @@
 """One large image optimised on several GPUs (BASELINE configs[3]).
 
-The image is cut into column strips, one per rank.  Each rank works on its strip extended by a halo of HALO = 160
-pixels on every interior side: twice the receptive-field radius (78 px) of block5_conv1, rounded up to the 16-pixel
-pooling alignment.  With that halo
-  * every VGG feature that influences the gradient of an OWN pixel is computed from true image data, so no per-layer
-    halo exchange is needed (redundant convolution work in the halo instead of 25 exchanges per iteration);
-  * the matting Laplacian rows of the own pixels (5x5 footprint) are exact as well.
-What does cross the NVLink fabric, per iteration:
-  * the per-class Gram partials of the five style layers (each rank sums over its OWN pixels only): ONE NCCL all-reduce of
-    one flat float32 buffer (the per-layer Gram tensors are views of it; 19.5 MB at K = 8), plus the 4-entry float64 loss
-    accumulator;
-  * the updated border columns: every rank sends the HALO columns next to each of its interior boundaries to that neighbour
-    and receives the neighbour's (NCCL point-to-point, batched; H x 160 x 3 floats per side) -- not whole strips.
-Strip boundaries must be multiples of 16 px so that pooling grids and the bilinear mask resizing of every layer align
-with the global image (then restricting a resized mask to the own columns is exact).
+The image is cut into column strips, one per rank; a rank stores its strip plus a halo of HALO = 64 image pixels on every
+interior side (halo of a level-l feature map: 64 / 2^l columns: 64, 32, 16, 8, 4 for blocks 1..5).  What a rank needs from
+its neighbours is exchanged, point to point over NVLink, where the data crosses a pooling layer:
+
+  forward    after every pool, the pooled tensor's halo columns are overwritten with the owner's values, so each block starts
+             from exact inputs on own + halo.  Inside a block of n convolutions the valid region shrinks by one column per
+             convolution (the local edge is zero padded), which leaves every activation exact on the own columns plus the
+             n halo columns that the backward pass needs (ReLU masks, arg-max routing): 64 / 2^l >= 2 n holds for every block.
+  backward   the gradient w.r.t. every pooled tensor (the quantity that flows from block b+1 into block b) is exact on the
+             own columns only; its halo columns are overwritten with the owners' complete values before block b continues.
+  image      after the Adam update the HALO columns next to each interior boundary are refreshed from the owner.
+
+Nine exchanges per iteration (4 forward, 4 backward, 1 image, with both neighbours each), 0.1-3 MB per slab at 3840x2160; the
+redundant convolution work is (own + 2 x 64) / own instead of (own + 2 x 160) / own of the previous overlapped-strip design.
+The only collective is ONE NCCL all-reduce of the flattened per-class Gram partials of the five style layers (each rank sums
+over its OWN pixels; 19.5 MB at K = 8) plus the 4-entry float64 loss accumulator.
+
+Strip boundaries must be multiples of 16 px so that the pooling grids and the bilinear mask resizing of every layer align
+with the global image (restricting a resized mask to the own columns is then exact).
 """
+import threading
+
 import torch
 
 from . import kernels
@@ -22,7 +29,7 @@ from .components.VGG19.model import StyleContentModel
 from .components.loss import Loss
 from .style_transfer import Adam, CONTENT_LAYERS, STYLE_LAYERS
 
-HALO = 160
+HALO = 64
 
 
 class Tile:
@@ -31,7 +38,9 @@ class Tile:
     def __init__(self, W, rank, world, halo=HALO):
         if W % (16 * world) != 0:
             raise ValueError("image width %d must be a multiple of 16 x %d ranks" % (W, world))
-        self.W, self.rank, self.world = W, rank, world
+        if world > 1 and W // world < halo:
+            raise ValueError("strips of %d px are narrower than the %d-px halo" % (W // world, halo))
+        self.W, self.rank, self.world, self.halo = W, rank, world, halo
         self.own_lo, self.own_hi = rank * W // world, (rank + 1) * W // world
         self.ext_lo, self.ext_hi = max(0, self.own_lo - halo), min(W, self.own_hi + halo)
         self.local_w = self.ext_hi - self.ext_lo
@@ -50,6 +59,9 @@ class Tile:
     def global_cols(self, w_layer):
         return self.W // self._factor(w_layer)
 
+    def halo_cols(self, w_layer):
+        return self.halo // self._factor(w_layer)
+
     def own_masks(self, masks, K, h, w, device):
         """masks (K, h*w) or None  ->  masks restricted to the own columns (K, h*w)."""
         lo, hi = self.own_cols(w)
@@ -63,27 +75,163 @@ class Tile:
         return full_nhwc[:, :, self.ext_lo:self.ext_hi].contiguous()
 
 
-class TiledStyleTransfer:
-    """Rank-local state of a spatially tiled optimisation.  `reduce_sum(list_of_tensors)` sums each tensor over all ranks
-    in place; `gather(strip)` returns the list of every rank's own strip.  Defaults use torch.distributed (NCCL)."""
+# ----------------------------------------------------------------------------------------------------------------
+# communication back ends: NCCL (one process per GPU) and an in-process stand-in (threads, one per emulated rank)
+# ----------------------------------------------------------------------------------------------------------------
+class NcclComm:
+    """torch.distributed (NCCL): batched point-to-point for the halos, all-reduce for the Gram partials."""
 
-    def __init__(self, content, style, args, content_masks, style_masks, vgg_weights, rank, world, reduce_sum=None,
-                 gather=None, matting="v2", device=None):
+    def __init__(self, rank, world):
+        self.rank, self.world = rank, world
+        self.bytes = {"allreduce": 0, "halo": 0, "exchanges": 0}
+
+    def begin_step(self):
+        self.bytes = {"allreduce": 0, "halo": 0, "exchanges": 0}
+
+    def reduce_sum(self, tensors):
+        import torch.distributed as dist
+        for t in tensors:
+            if self.world > 1:
+                dist.all_reduce(t, op=dist.ReduceOp.SUM)
+            self.bytes["allreduce"] += t.numel() * t.element_size()
+
+    def exchange(self, tensor, lo, hi, hl):
+        """tensor (1,h,w,C) or (h,w,C)-like with columns on dim -2: send the hl own columns next to each interior boundary to
+        that neighbour, overwrite the hl halo columns with what the neighbour sends.  Returns the received slabs."""
+        import torch.distributed as dist
+        t = tensor if tensor.dim() == 4 else tensor.unsqueeze(0)
+        ops, recv = [], []
+        if self.rank > 0 and lo > 0:                                   # left neighbour
+            snd = t[:, :, lo:lo + hl].contiguous()
+            rcv = torch.empty_like(snd)
+            ops += [dist.P2POp(dist.isend, snd, self.rank - 1), dist.P2POp(dist.irecv, rcv, self.rank - 1)]
+            recv.append((rcv, lo - hl, lo))
+            self.bytes["halo"] += snd.numel() * 4
+        if self.rank < self.world - 1 and hi < t.shape[2]:             # right neighbour
+            snd = t[:, :, hi - hl:hi].contiguous()
+            rcv = torch.empty_like(snd)
+            ops += [dist.P2POp(dist.isend, snd, self.rank + 1), dist.P2POp(dist.irecv, rcv, self.rank + 1)]
+            recv.append((rcv, hi, hi + hl))
+            self.bytes["halo"] += snd.numel() * 4
+        if ops:
+            for req in dist.batch_isend_irecv(ops):
+                req.wait()
+            self.bytes["exchanges"] += 1
+        for rcv, a, b in recv:
+            t[:, :, a:b] = rcv
+        return [r for r, _, _ in recv]
+
+
+class GlooComm(NcclComm):
+    """The same protocol over a gloo group with host copies: CPU tests of the exchange code (tests/test_host_logic.py)."""
+
+    def reduce_sum(self, tensors):
+        import torch.distributed as dist
+        for t in tensors:
+            c = t.detach().cpu()
+            dist.all_reduce(c, op=dist.ReduceOp.SUM)
+            t.copy_(c)
+            self.bytes["allreduce"] += t.numel() * t.element_size()
+
+    def exchange(self, tensor, lo, hi, hl):
+        import torch.distributed as dist
+        t = tensor if tensor.dim() == 4 else tensor.unsqueeze(0)
+        recv = []
+        # gloo has no batched isend/irecv on every build: order the blocking calls by parity instead
+        def swap(peer, snd_cols, rcv_cols):
+            snd = t[:, :, snd_cols[0]:snd_cols[1]].detach().cpu().contiguous()
+            rcv = torch.empty_like(snd)
+            if self.rank < peer:
+                dist.send(snd, peer); dist.recv(rcv, peer)
+            else:
+                dist.recv(rcv, peer); dist.send(snd, peer)
+            t[:, :, rcv_cols[0]:rcv_cols[1]] = rcv.to(t.device)
+            recv.append(rcv.to(t.device))
+            self.bytes["halo"] += snd.numel() * 4
+        # even ranks talk to the right first, odd ranks to the left first (no deadlock on a chain)
+        order = ("right", "left") if self.rank % 2 == 0 else ("left", "right")
+        for side in order:
+            if side == "left" and self.rank > 0 and lo > 0:
+                swap(self.rank - 1, (lo, lo + hl), (lo - hl, lo))
+            if side == "right" and self.rank < self.world - 1 and hi < t.shape[2]:
+                swap(self.rank + 1, (hi - hl, hi), (hi, hi + hl))
+        self.bytes["exchanges"] += 1
+        return recv
+
+
+class ThreadComm:
+    """Several ranks inside ONE process (single-GPU emulation, tests): every rank runs in its own thread on the same CUDA
+    stream; an exchange is a mailbox plus two barriers.  Host-side barriers order the enqueueing, the shared stream orders
+    the device work."""
+
+    class Shared:
+        def __init__(self, world):
+            self.world = world
+            self.barrier = threading.Barrier(world)
+            self.box = {}
+
+    def __init__(self, shared, rank):
+        self.s, self.rank, self.world = shared, rank, shared.world
+        self.bytes = {"allreduce": 0, "halo": 0, "exchanges": 0}
+
+    def begin_step(self):
+        self.bytes = {"allreduce": 0, "halo": 0, "exchanges": 0}
+
+    def reduce_sum(self, tensors):
+        self.s.box[("red", self.rank)] = tensors
+        self.s.barrier.wait()
+        if self.rank == 0:
+            for group in zip(*[self.s.box[("red", r)] for r in range(self.world)]):
+                tot = torch.stack([g.to(torch.float64) for g in group]).sum(0)
+                for g in group:
+                    g.copy_(tot.to(g.dtype))
+        self.s.barrier.wait()
+        self.bytes["allreduce"] += sum(t.numel() * t.element_size() for t in tensors)
+
+    def exchange(self, tensor, lo, hi, hl):
+        t = tensor if tensor.dim() == 4 else tensor.unsqueeze(0)
+        has_left, has_right = self.rank > 0 and lo > 0, self.rank < self.world - 1 and hi < t.shape[2]
+        if has_left:
+            self.s.box[("to", self.rank - 1, "from_right")] = t[:, :, lo:lo + hl].clone()
+        if has_right:
+            self.s.box[("to", self.rank + 1, "from_left")] = t[:, :, hi - hl:hi].clone()
+        self.s.barrier.wait()
+        recv = []
+        if has_left:
+            r = self.s.box[("to", self.rank, "from_left")]
+            t[:, :, lo - hl:lo] = r
+            recv.append(r)
+        if has_right:
+            r = self.s.box[("to", self.rank, "from_right")]
+            t[:, :, hi:hi + hl] = r
+            recv.append(r)
+        self.s.barrier.wait()
+        self.bytes["halo"] += sum(r.numel() * 4 for r in recv)
+        self.bytes["exchanges"] += 1
+        return recv
+
+
+class TiledStyleTransfer:
+    """Rank-local state of a spatially tiled optimisation.  `comm` provides exchange(tensor, lo, hi, hl) and
+    reduce_sum(list of tensors); the default is NCCL through torch.distributed."""
+
+    def __init__(self, content, style, args, content_masks, style_masks, vgg_weights, rank, world, comm=None, matting="v2",
+                 device=None):
         dev = torch.device(device if device is not None else "cuda")
         self.rank, self.world = rank, world
+        self.comm = comm if comm is not None else NcclComm(rank, world)
         content = torch.as_tensor(content, dtype=torch.float32)
         style = torch.as_tensor(style, dtype=torch.float32)
         self.tile = Tile(int(content.shape[2]), rank, world)
         self.style_tile = Tile(int(style.shape[2]), rank, world)
-        self.reduce_sum = reduce_sum or _nccl_reduce_sum
-        self.gather = gather                            # None: point-to-point border exchange over NCCL (the default)
         c_loc = self.tile.crop(content).to(dev)
         s_loc = self.style_tile.crop(style).to(dev)
         cm = None if content_masks is None else [self.tile.crop(torch.as_tensor(m)) for m in content_masks]
         sm = None if style_masks is None else [self.style_tile.crop(torch.as_tensor(m)) for m in style_masks]
         self.extractor = StyleContentModel(CONTENT_LAYERS, STYLE_LAYERS, shape=(None, None, 3), weights=vgg_weights, device=dev)
-        content_target = self.extractor(c_loc)['content']
-        style_target = self.extractor(s_loc)['style']
+        # the targets are features of strips as well: same block-wise forward pass with halo exchange
+        content_target = self.extractor.forward_blocks(c_loc, self._exchanger(self.tile), reuse=False)['content']
+        style_target = self.extractor.forward_blocks(s_loc, self._exchanger(self.style_tile), reuse=False)['style']
         self.loss = Loss(content_target, style_target, args, cm, sm, matting=matting, tile=self.tile, style_tile=self.style_tile)
         if args.regularization_weight > 0:
             self.loss.initialize_matting_laplacian(c_loc[0].to(torch.float64))
@@ -92,7 +240,14 @@ class TiledStyleTransfer:
         self._grad = torch.empty_like(self.image)
         self._targets_reduced = False
         self._flat = None                               # flat float32 buffer behind the per-layer Gram partials
-        self._bytes = {"allreduce": 0, "halo": 0}
+
+    def _exchanger(self, tile):
+        """exchange(level, tensor) for feature maps / gradients of this strip: level l tensors have local width local_w / 2^l."""
+        def ex(level, tensor):
+            w_l = int(tensor.shape[-2])
+            lo, hi = tile.own_cols(w_l)
+            return self.comm.exchange(tensor, lo, hi, tile.halo_cols(w_l))
+        return ex
 
     def _flatten_partials(self):
         """Make the per-layer transfer Grams views of ONE buffer, so that a single all-reduce sums them all."""
@@ -108,133 +263,85 @@ class TiledStyleTransfer:
     def describe_exchange(self):
         if self.world == 1:
             return "no exchange (single strip)"
-        return ("one NCCL all-reduce of the flattened Gram partials (%.1f MB) + float64[4] loss accumulator, point-to-point "
-                "exchange of the %d-px border columns with both neighbours" % (4e-6 * (self._flat.numel() if self._flat is not None else 0), HALO))
+        return ("point-to-point halo exchange of every pooled tensor (forward) and of its gradient (backward) plus the image "
+                "border after the update (%d px halo), one NCCL all-reduce of the flattened Gram partials (%.1f MB) + float64[4] "
+                "loss accumulator" % (HALO, 4e-6 * (self._flat.numel() if self._flat is not None else 0)))
 
     def exchange_bytes(self):
-        """Bytes this rank hands to NCCL per step: all-reduce payload and halo columns sent."""
-        return dict(self._bytes)
-
-    # -- the three phases of one iteration; a multi-rank driver interleaves the reductions between them ------------
-    def phase_partials(self):
-        outputs = self.extractor(self.image, reuse=True)
-        if self._flat is None:
-            self.loss.prepare(outputs)                  # per-layer state (idempotent), then one buffer behind all Gram partials
-            self._flatten_partials()
-        parts = self.loss.forward_partials(self.image, outputs)
-        return [self._flat, parts[-1]]                  # every Gram partial lives in the flat buffer; + the float64 accumulator
-
-    def phase_finish(self):
-        loss_dict = self.loss.finish()
-        grad = self.loss.gradient(self.extractor, out=self._grad)
-        self.optimizer.apply_gradients_and_clip(grad, self.image)      # only the own columns of the result are meaningful
-        return loss_dict
+        """Bytes this rank handed to the communication layer in the latest step."""
+        return dict(self.comm.bytes)
 
     def own_strip(self):
         lo, hi = self.tile.own_cols(self.tile.local_w)
         return self.image[0, :, lo:hi].contiguous()
 
-    def refresh_halo(self, strips):
-        """strips[r]: own strip (H, W/world, 3) of rank r after the update."""
-        t = self.tile
-        for r, s in enumerate(strips):
-            lo, hi = r * t.W // t.world, (r + 1) * t.W // t.world
-            a, b = max(lo, t.ext_lo), min(hi, t.ext_hi)
-            if r != self.rank and a < b:
-                self.image[0, :, a - t.ext_lo:b - t.ext_lo] = s[:, a - lo:b - lo]
-
-    def exchange_borders(self):
-        """Halo refresh over NCCL point-to-point: send the HALO own columns next to each interior boundary to that neighbour,
-        receive the neighbour's into the halo columns.  Strips narrower than the halo would need data from farther ranks;
-        that case falls back to gathering whole strips."""
-        import torch.distributed as dist
-        t = self.tile
-        own_w = t.own_hi - t.own_lo
-        if own_w < HALO:
-            out = [torch.empty_like(self.own_strip()) for _ in range(self.world)]
-            dist.all_gather(out, self.own_strip())
-            self._bytes["halo"] = out[0].numel() * 4
-            self.refresh_halo(out)
-            return
-        lo, hi = t.own_lo - t.ext_lo, t.own_hi - t.ext_lo               # own columns in local coordinates
-        ops, recv = [], []
-        sent = 0
-        if self.rank > 0:                                               # left neighbour
-            snd = self.image[0, :, lo:lo + HALO].contiguous()
-            rcv = torch.empty_like(self.image[0, :, 0:lo])
-            ops += [dist.P2POp(dist.isend, snd, self.rank - 1), dist.P2POp(dist.irecv, rcv, self.rank - 1)]
-            recv.append((rcv, 0, lo)); sent += snd.numel() * 4
-        if self.rank < self.world - 1:                                  # right neighbour
-            snd = self.image[0, :, hi - HALO:hi].contiguous()
-            rcv = torch.empty_like(self.image[0, :, hi:t.local_w])
-            ops += [dist.P2POp(dist.isend, snd, self.rank + 1), dist.P2POp(dist.irecv, rcv, self.rank + 1)]
-            recv.append((rcv, hi, t.local_w)); sent += snd.numel() * 4
-        for req in dist.batch_isend_irecv(ops):
-            req.wait()
-        for rcv, a, b in recv:
-            self.image[0, :, a:b] = rcv
-        self._bytes["halo"] = sent
-
     def step(self):
-        """One iteration with real collectives (one process per GPU)."""
-        if not self._targets_reduced:
-            outputs = self.extractor(self.image, reuse=True)
-            self.loss.prepare(outputs)
-            self.reduce_sum(self.loss.style_targets_partial())
+        """One iteration (every rank calls it; the calls to `comm` are collective)."""
+        self.comm.begin_step()
+        ex = self._exchanger(self.tile)
+        outputs = self.extractor.forward_blocks(self.image, ex, reuse=True)
+        if self._flat is None:
+            self.loss.prepare(outputs)                  # per-layer state (idempotent), then one buffer behind all Gram partials
+            self._flatten_partials()
+        if not self._targets_reduced:                   # the style Grams computed at set-up are per-rank partials: sum once
+            self.comm.reduce_sum(self.loss.style_targets_partial())
             self._targets_reduced = True
-        parts = self.phase_partials()
-        self._bytes["allreduce"] = sum(p.numel() * p.element_size() for p in parts)
-        self.reduce_sum(parts)
-        loss_dict = self.phase_finish()
-        if self.gather is not None:
-            self.refresh_halo(self.gather(self.own_strip()))
-        elif self.world > 1:
-            self.exchange_borders()
+        parts = self.loss.forward_partials(self.image, outputs)
+        self.comm.reduce_sum([self._flat, parts[-1]])   # every Gram partial lives in the flat buffer; + the float64 accumulator
+        loss_dict = self.loss.finish()
+        grad = self.loss.gradient(self.extractor, out=self._grad,
+                                  backward=lambda seeds, out: self.extractor.backward_blocks(seeds, ex, out=out))
+        self.optimizer.apply_gradients_and_clip(grad, self.image)      # only the own columns of the result are meaningful
+        ex(0, self.image)                                              # refresh the image halo from the owners
         return loss_dict
 
 
-def _nccl_reduce_sum(tensors):
-    import torch.distributed as dist
-    for t in tensors:
-        dist.all_reduce(t, op=dist.ReduceOp.SUM)
-
-
-def _nccl_gather(strip):
-    import torch.distributed as dist
-    out = [torch.empty_like(strip) for _ in range(dist.get_world_size())]
-    dist.all_gather(out, strip)
-    return out
-
-
-def _gloo_reduce_sum(tensors):
-    """Host-side stand-in used by the CPU protocol tests: the same call sequence over a gloo group."""
-    import torch.distributed as dist
-    for t in tensors:
-        c = t.detach().cpu()
-        dist.all_reduce(c, op=dist.ReduceOp.SUM)
-        t.copy_(c)
-
-
 def run_emulated(ranks, iters):
-    """Drive several TiledStyleTransfer objects that live in ONE process (tests, single-GPU emulation): the reductions are
-    plain sums over the objects.  Returns the list of loss dicts (identical on every rank)."""
-    def reduce_lists(lists):
-        for group in zip(*lists):
-            tot = torch.stack([g.to(torch.float64) for g in group]).sum(0)
-            for g in group:
-                g.copy_(tot.to(g.dtype))
-    history = []
-    if not ranks[0]._targets_reduced:
-        for r in ranks:
-            r.loss.prepare(r.extractor(r.image, reuse=True))
-        reduce_lists([r.loss.style_targets_partial() for r in ranks])
-        for r in ranks:
-            r._targets_reduced = True
-    for _ in range(iters):
-        reduce_lists([r.phase_partials() for r in ranks])
-        dicts = [r.phase_finish() for r in ranks]
-        strips = [r.own_strip() for r in ranks]
-        for r in ranks:
-            r.refresh_halo(strips)
-        history.append({k: float(v) for k, v in dicts[0].items()})
-    return history
+    """Drive several TiledStyleTransfer objects that live in ONE process (their `comm` must be ThreadComm objects sharing one
+    ThreadComm.Shared): one thread per rank.  Returns the list of loss dicts of rank 0 (identical on every rank)."""
+    history = [[] for _ in ranks]
+    errors = []
+
+    def work(i, r):
+        try:
+            for _ in range(iters):
+                d = r.step()
+                history[i].append({k: float(v) for k, v in d.items()})
+        except BaseException as e:           # make a failing rank visible instead of dead-locking the barrier
+            errors.append(e)
+            try:
+                r.comm.s.barrier.abort()
+            except Exception:
+                pass
+
+    threads = [threading.Thread(target=work, args=(i, r)) for i, r in enumerate(ranks)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    if errors:
+        raise errors[0]
+    return history[0]
+
+
+def make_emulated(content, style, args, content_masks, style_masks, vgg_weights, world, matting="v2", device=None):
+    """`world` rank objects in this process.  Construction itself exchanges halos (the targets), so it runs in threads too."""
+    shared = ThreadComm.Shared(world)
+    ranks, errors = [None] * world, []
+
+    def build(r):
+        try:
+            ranks[r] = TiledStyleTransfer(content, style, args, content_masks, style_masks, vgg_weights, r, world,
+                                          comm=ThreadComm(shared, r), matting=matting, device=device)
+        except BaseException as e:
+            errors.append(e)
+            shared.barrier.abort()
+
+    threads = [threading.Thread(target=build, args=(r,)) for r in range(world)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    if errors:
+        raise errors[0]
+    return ranks

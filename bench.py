@@ -580,11 +580,7 @@ def tiled_record(D, H, W, K, steps, warmup, tv_weight, check_parity=True):
     cm = sem.mask_for_tf(sem.extract_segmentation_masks(synth.label_image(H, W, K, 9, cell=64)))
     sm = sem.mask_for_tf(sem.extract_segmentation_masks(synth.label_image(H, W, K, 10, cell=64)))
     weights = synth.vgg_weights()
-    if D.world > 1:
-        job = tiled.TiledStyleTransfer(content, style, hp, cm, sm, weights, D.rank, D.world)
-    else:
-        job = tiled.TiledStyleTransfer(content, style, hp, cm, sm, weights, 0, 1, reduce_sum=lambda t: None,
-                                       gather=lambda s: [s])
+    job = tiled.TiledStyleTransfer(content, style, hp, cm, sm, weights, D.rank, D.world)
     first = {k: float(v) for k, v in job.step().items()}           # iteration 0: evaluated at x = content on every rank
     for _ in range(max(warmup, 3) - 1):
         d = job.step()
@@ -605,8 +601,7 @@ def tiled_record(D, H, W, K, steps, warmup, tv_weight, check_parity=True):
         # the N-rank loss dictionary of iteration 0 against the single-device evaluation of the whole image (rank 0)
         ok, worst = True, 0.0
         if D.rank == 0:
-            single = tiled.TiledStyleTransfer(content, style, hp, cm, sm, weights, 0, 1, reduce_sum=lambda t: None,
-                                              gather=lambda s: [s])
+            single = tiled.TiledStyleTransfer(content, style, hp, cm, sm, weights, 0, 1)
             ref = {k: float(v) for k, v in single.step().items()}
             worst = max(abs(first[k] - ref[k]) / max(abs(ref[k]), 1e-300) for k in ref if k != "NIMA loss")
             ok = worst <= 2e-5

@@ -381,3 +381,32 @@ def test_script_main_with_segmentation_files(tmp_path, synth, monkeypatch, capsy
     # without --use_masks the script behaves like the reference as shipped (masks commented out, :308-309): K = 1
     _, hist3 = st.main([x for x in argv if x != "--use_masks"])
     assert abs(hist3[0]["Style loss"] - hist[0]["Style loss"]) > 1e-6 * abs(hist[0]["Style loss"])
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs in one process")
+def test_second_device_in_the_same_process(weights, synth):
+    """Per-device kernel set-up (cudaFuncSetAttribute, SM count) and launch-device guards: one train step on cuda:0, then the
+    same pair on cuda:1 in the same process while cuda:0 stays the current device; identical losses."""
+    st = _m("style_transfer")
+    vgg, lossm, sem = _m("components.VGG19.model"), _m("components.loss"), _m("components.semantic_merge")
+    args = _args()
+    H, W, K = 64, 96, 3
+    content, style = synth.image(H, W, 0), synth.image(H, W, 1)
+    cm = sem.mask_for_tf(sem.extract_segmentation_masks(synth.label_image(H, W, K, 9, cell=16)))
+    sm = sem.mask_for_tf(sem.extract_segmentation_masks(synth.label_image(H, W, K, 10, cell=16)))
+    results = []
+    for dev in ("cuda:0", "cuda:1"):
+        ext = vgg.StyleContentModel(model.CONTENT_LAYERS, model.STYLE_LAYERS, weights=weights, device=dev)
+        c_dev, s_dev = torch.as_tensor(content).to(dev), torch.as_tensor(style).to(dev)
+        loss = lossm.Loss(ext(c_dev)["content"], ext(s_dev)["style"], args, cm, sm)
+        loss.initialize_matting_laplacian(c_dev[0].double())
+        step = st.make_train_step(ext, loss, st.Adam(args.adam_lr, args.adam_beta1, args.adam_beta2, args.adam_epsilon))
+        x = c_dev.clone()
+        for _ in range(2):
+            d = {k: float(v) for k, v in step(x).items()}
+        torch.cuda.synchronize(dev)
+        results.append((d, x.cpu()))
+    assert torch.cuda.current_device() == 0
+    for name, v in results[0][0].items():
+        assert abs(v - results[1][0][name]) <= 1e-6 * abs(v) + 1e-12, name
+    assert float((results[0][1] - results[1][1]).abs().max()) < 1e-5

@@ -1,6 +1,7 @@
 """GPU: one image split into column strips (spatial tiling, BASELINE configs[3]) must reproduce the single-device
-optimisation: same loss values, same updated image.  The ranks are emulated inside one process (reductions = plain sums);
-the NCCL path uses the same phases and is exercised by bench.py --tiled on >= 2 GPUs."""
+optimisation: same loss values, same updated image.  The ranks are emulated inside one process (one thread per rank, the
+halo exchanges and the Gram reduction go through tiled.ThreadComm); the NCCL back end runs the same step() and is checked
+against the single-device run inside bench.py (tiled_4k.parity_vs_single_device) on >= 2 GPUs."""
 import argparse
 import importlib
 
@@ -44,9 +45,9 @@ def test_tiled_matches_single_device(world, W, K, synth):
     x = c_dev.clone()
     ref = [{k: float(v) for k, v in step(x).items()} for _ in range(3)]
     # tiled run, ranks emulated in this process
-    ranks = [tiled.TiledStyleTransfer(content, style, args, cm, sm, weights, r, world, reduce_sum=lambda t: None,
-                                      gather=lambda s: None) for r in range(world)]
+    ranks = tiled.make_emulated(content, style, args, cm, sm, weights, world)
     got = tiled.run_emulated(ranks, 3)
+    assert ranks[0].exchange_bytes()["exchanges"] == 9 and all(r.tile.halo == tiled.HALO == 64 for r in ranks)
     # Iteration 0 evaluates identical images: 2e-5.  Afterwards the images themselves may differ in a few pixels: Adam's first
     # steps are +-lr * sign(g), so a last-bit difference in a gradient that is ~0 moves that pixel by 2 lr (the image check
     # below counts such flips); the loss values of later iterations are therefore only comparable to ~1e-4.

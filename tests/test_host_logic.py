@@ -134,19 +134,23 @@ def test_tile_geometry():
     """Spatial tiling (BASELINE configs[3]): strip / halo arithmetic, CPU only."""
     tiled = importlib.import_module(PKG_NAME + ".tiled")
     t = tiled.Tile(3840, 3, 8)
-    assert (t.own_lo, t.own_hi, t.ext_lo, t.ext_hi, t.local_w) == (1440, 1920, 1280, 2080, 800)
-    assert t.own_cols(800) == (160, 640) and t.own_cols(50) == (10, 40) and t.global_cols(50) == 240
+    assert (t.own_lo, t.own_hi, t.ext_lo, t.ext_hi, t.local_w) == (1440, 1920, 1376, 1984, 608)
+    assert t.own_cols(608) == (64, 544) and t.own_cols(38) == (4, 34) and t.global_cols(38) == 240 and t.halo_cols(38) == 4
     t0 = tiled.Tile(3840, 0, 8)
-    assert (t0.ext_lo, t0.ext_hi) == (0, 640) and t0.own_cols(640) == (0, 480)
+    assert (t0.ext_lo, t0.ext_hi) == (0, 544) and t0.own_cols(544) == (0, 480)
     with pytest.raises(ValueError):
         tiled.Tile(1000, 0, 8)
-    # every pixel is owned by exactly one rank and every halo is twice the block5_conv1 receptive-field radius
+    # every pixel is owned by exactly one rank; the halo of a level-l tensor (HALO / 2^l columns) must cover twice the number
+    # of convolutions of the block that reads it (forward validity shrinks by one column per convolution, the backward pass
+    # needs the ReLU masks that many columns out): blocks 1..5 have 2, 2, 4, 4, 1 convolutions
     owned = np.zeros(3840, int)
     for r in range(8):
         tr = tiled.Tile(3840, r, 8)
         owned[tr.own_lo:tr.own_hi] += 1
         assert tr.own_lo - tr.ext_lo in (0, tiled.HALO) and tr.ext_hi - tr.own_hi in (0, tiled.HALO)
-    assert (owned == 1).all() and tiled.HALO >= 2 * 78 and tiled.HALO % 16 == 0
+    assert (owned == 1).all() and tiled.HALO % 16 == 0
+    for level, nconv in enumerate((2, 2, 4, 4, 1)):
+        assert tiled.HALO >> level >= 2 * nconv
 
 
 _TILED_WORKER = r"""
@@ -156,47 +160,49 @@ import torch, torch.distributed as dist
 dist.init_process_group("gloo", rank=int(os.environ["RANK"]), world_size=int(os.environ["WORLD_SIZE"]))
 rank, world = dist.get_rank(), dist.get_world_size()
 tiled = importlib.import_module(%r + ".tiled")
-H, W = 6, 16 * 12 * world                     # strips of 192 px >= HALO
-glob = torch.arange(H * W * 3, dtype=torch.float32).reshape(1, H, W, 3)
-# the rank-local object without its GPU members: exchange_borders / refresh_halo / own_strip only touch these attributes
-job = object.__new__(tiled.TiledStyleTransfer)
-job.rank, job.world = rank, world
-job.tile = tiled.Tile(W, rank, world)
-job._bytes = {"allreduce": 0, "halo": 0}
-t = job.tile
-job.image = glob[:, :, t.ext_lo:t.ext_hi].clone()
-lo, hi = t.own_lo - t.ext_lo, t.own_hi - t.ext_lo
-job.image[0, :, :lo] = -1.0                   # stale halos
-job.image[0, :, hi:] = -1.0
-job.image[0, :, lo:hi] += 1000.0 * (rank + 1)  # "updated" own columns
-job.exchange_borders()
-expect = glob[:, :, t.ext_lo:t.ext_hi].clone()
-for r in range(world):
-    a, b = max(r * W // world, t.ext_lo), min((r + 1) * W // world, t.ext_hi)
-    if a < b:
-        expect[0, :, a - t.ext_lo:b - t.ext_lo] += 1000.0 * (r + 1)
-ok_halo = bool(torch.equal(job.image, expect))
+H, W = 6, 16 * 8 * world                       # strips of 128 px >= HALO
+comm = tiled.GlooComm(rank, world)
+t = tiled.Tile(W, rank, world)
+ok = True
+for level, C in ((0, 3), (2, 5), (4, 2)):      # the image, a block-3 input, a block-5 input
+    f = 1 << level
+    w_l, gw = t.local_w // f, W // f
+    glob = torch.arange(H * gw * C, dtype=torch.float32).reshape(1, H, gw, C)
+    loc = glob[:, :, t.ext_lo // f:t.ext_hi // f].clone()
+    lo, hi = t.own_cols(w_l)
+    hl = t.halo_cols(w_l)
+    loc[0, :, :lo] = -1.0                      # stale halos
+    loc[0, :, hi:] = -1.0
+    loc[0, :, lo:hi] += 1000.0 * (rank + 1)    # "updated" own columns
+    recv = comm.exchange(loc, lo, hi, hl)
+    expect = glob[:, :, t.ext_lo // f:t.ext_hi // f].clone()
+    for r in range(world):
+        a, b = max(r * gw // world, t.ext_lo // f), min((r + 1) * gw // world, t.ext_hi // f)
+        if a < b:
+            expect[0, :, a - t.ext_lo // f:b - t.ext_lo // f] += 1000.0 * (r + 1)
+    ok = ok and bool(torch.equal(loc, expect)) and len(recv) == (rank > 0) + (rank < world - 1)
+    ok = ok and hl == tiled.HALO // f and (hi - lo) == W // world // f
 # the Gram partials: ONE flat float32 buffer + the float64 accumulator, summed over the ranks
 flat = torch.full((1000,), float(rank + 1)); acc = torch.tensor([1.0, 0.0, 2.0 * rank, 0.5], dtype=torch.float64)
-tiled._gloo_reduce_sum([flat, acc])
+comm.reduce_sum([flat, acc])
 ok_sum = bool((flat == world * (world + 1) / 2).all()) and float(acc[0]) == world and float(acc[2]) == world * (world - 1)
 # configs[2] sharding of bench.py: pair p goes to rank p %% world
 mine = list(range(rank, 64, world))
 allp = [None] * world
 dist.all_gather_object(allp, mine)
 res = [None] * world
-dist.all_gather_object(res, (ok_halo, ok_sum, job._bytes["halo"]))
+dist.all_gather_object(res, (ok, ok_sum, comm.bytes["exchanges"]))
 if rank == 0:
-    print(json.dumps({"results": res, "pairs": sorted(sum(allp, [])), "halo": tiled.HALO, "H": H}))
+    print(json.dumps({"results": res, "pairs": sorted(sum(allp, []))}))
 dist.destroy_process_group()
 """
 
 
 @pytest.mark.parametrize("world", [2, 3])
 def test_tiled_exchange_protocol_gloo(world, tmp_path):
-    """TiledStyleTransfer's own exchange code over a gloo group (CPU tensors): the point-to-point border exchange fills every
-    halo with the neighbours' updated own columns (middle ranks talk to both sides), the flattened Gram partials and the
-    float64 accumulator are summed, and the configs[2] round-robin covers all 64 pairs exactly once."""
+    """The exchange code of tiled.py over a gloo group (CPU tensors): after an exchange every halo column of the image, of a
+    block-3 input and of a block-5 input holds the owner's updated value (middle ranks talk to both sides), the flattened
+    Gram partials and the float64 accumulator are summed, and the configs[2] round-robin covers all 64 pairs exactly once."""
     import json
     script = tmp_path / "tiled_worker.py"
     script.write_text(_TILED_WORKER % (ROOT, PKG_NAME))
@@ -207,7 +213,5 @@ def test_tiled_exchange_protocol_gloo(world, tmp_path):
     assert all(p.returncode == 0 for p in procs), outs
     d = json.loads(outs[0][0].strip().splitlines()[-1])
     assert d["pairs"] == list(range(64))
-    for r, (ok_halo, ok_sum, sent) in enumerate(d["results"]):
-        assert ok_halo and ok_sum, r
-        sides = (r > 0) + (r < world - 1)
-        assert sent == sides * d["H"] * d["halo"] * 3 * 4
+    for r, (ok, ok_sum, n) in enumerate(d["results"]):
+        assert ok and ok_sum and n == 3, r
