@@ -271,6 +271,41 @@ class TiledStyleTransfer:
         """Bytes this rank handed to the communication layer in the latest step."""
         return dict(self.comm.bytes)
 
+    def time_breakdown(self, steps=5):
+        """Device time of `steps` iterations split into communication (halo exchanges incl. packing / unpacking, the Gram
+        all-reduce) and everything else, measured with CUDA events around every call into `comm` (the events serialise
+        nothing: communication is already stream-ordered with the compute).  Returns ms per step."""
+        events = []
+        comm = self.comm
+        raw_exchange, raw_reduce = comm.exchange, comm.reduce_sum
+
+        def timed(fn):
+            def wrapper(*a, **k):
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                out = fn(*a, **k)
+                e1.record()
+                events.append((e0, e1))
+                return out
+            return wrapper
+
+        comm.exchange, comm.reduce_sum = timed(raw_exchange), timed(raw_reduce)
+        try:
+            t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            torch.cuda.synchronize()
+            t0.record()
+            for _ in range(steps):
+                self.step()
+            t1.record()
+            torch.cuda.synchronize()
+        finally:
+            comm.exchange, comm.reduce_sum = raw_exchange, raw_reduce
+        total = t0.elapsed_time(t1) / steps
+        comm_ms = sum(a.elapsed_time(b) for a, b in events) / steps
+        own = self.tile.own_hi - self.tile.own_lo
+        return {"ms_per_step": total, "communication_ms": comm_ms, "compute_ms": total - comm_ms,
+                "redundant_column_factor": self.tile.local_w / own}
+
     def own_strip(self):
         lo, hi = self.tile.own_cols(self.tile.local_w)
         return self.image[0, :, lo:hi].contiguous()

@@ -591,11 +591,16 @@ def tiled_record(D, H, W, K, steps, warmup, tv_weight, check_parity=True):
     e1.record(); D.barrier()
     ms = D.max_ms(e0.elapsed_time(e1))
     t = job.tile
+    breakdown = job.time_breakdown(3)                                # collective: every rank runs the same three steps
+    breakdown = {k: D.max_ms(v) for k, v in breakdown.items()}
     rec = {"config": "configs[3]: one %dx%d image, %d classes, column strips of %d px + %d px halo per interior side (local width "
                      "%d) over %d GPU(s); per step: %s" % (W, H, K, W // D.world, tiled.HALO if D.world > 1 else 0, t.local_w,
                                                            D.world, job.describe_exchange()),
            "scaling": "strong", "n_gpus": D.world, "value": steps / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms / steps,
            "steps": steps, "bytes_exchanged_per_step": job.exchange_bytes(), "final_total_loss": float(d["Total loss"]),
+           "breakdown_max_over_ranks": dict(breakdown, what="device ms per step: halo exchanges (packing, NCCL point-to-point, "
+                                                               "unpacking) + Gram all-reduce vs everything else; "
+                                                               "redundant_column_factor = (own + halo columns) / own columns"),
            "first_iteration_losses": first}
     if check_parity and D.world > 1:
         # the N-rank loss dictionary of iteration 0 against the single-device evaluation of the whole image (rank 0)

@@ -10,7 +10,7 @@ ap = argparse.ArgumentParser(); ap.add_argument("--size", type=int, default=1024
 ap.add_argument("--steps", type=int, default=2); a = ap.parse_args()
 S, K = a.size, a.K
 args = argparse.Namespace(content_weight=1.0, style_weight=100.0, nima_weight=0.0, regularization_weight=1e4, matting_epsilon=1e-7,
-                          matting_window_radius=1, adam_lr=0.1, adam_beta1=0.9, adam_beta2=0.999, adam_epsilon=1e-8)
+                          matting_window_radius=1, adam_lr=0.1, adam_beta1=0.9, adam_beta2=0.999, adam_epsilon=1e-8, tv_weight=1.0)
 c = torch.as_tensor(synth.image(S, S, 0)).cuda(); s = torch.as_tensor(synth.image(S, S, 1)).cuda()
 cm = sem.mask_for_tf(sem.extract_segmentation_masks(synth.label_image(S, S, K, 9)))
 sm = sem.mask_for_tf(sem.extract_segmentation_masks(synth.label_image(S, S, K, 10)))
