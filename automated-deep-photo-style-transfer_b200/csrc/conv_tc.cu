@@ -96,6 +96,7 @@ constexpr int TC_A_BOX_BYTES = 23 * 1024;                        // one landed b
 constexpr int TC_A_TX_BYTES = 2 * TC_HW * TC_HH * 32 * 4;        // bytes TMA actually delivers per A stage
 constexpr int TC_A_BYTES = 2 * TC_A_BOX_BYTES;                   // 46 KB: channels [0,32) and [32,64) of the K chunk
 constexpr int TC_CHUNK_ITERS = 2;                                // stages per promoted chunk (8 big MMAs)
+constexpr int TC_STYLE_PRELOAD = 4;                              // style mode: class weights preloaded per work item
 constexpr int TC_MAX_CLASSES = 32;                               // style mode: classes per launch (active set is a bit mask)
 
 // Shared-memory bandwidth (128 B/clk/SM) is what bounds this kernel, not the tensor pipe: per K chunk of 64 and BN = 128
@@ -343,6 +344,18 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             if (ntaps == 0) continue;
             const int ty = m / TC_TW, tx = m % TC_TW;
             const int gy = (tile / tiles_w) * TC_TH + ty, gx = (tile % tiles_w) * TC_TW + tx;
+            // style mode: this pixel's weight m_k^2 for the first classes of the tile, requested once per work item (they do
+            // not depend on the K chunk) instead of one exposed global load per stage
+            float wq[TC_STYLE_PRELOAD];
+            if (MODE == MODE_STYLE) {
+#pragma unroll
+                for (int j = 0; j < TC_STYLE_PRELOAD; ++j) {
+                    float wk = 0.f;
+                    if (j < ntaps && gy < H && gx < W)
+                        wk = cls_masks ? __ldg(cls_masks + size_t(nth_set_bit(active, j)) * H * W + size_t(gy) * W + gx) : 1.0f;
+                    wq[j] = wk * wk;
+                }
+            }
             for (int kc = 0; kc < kchunks; ++kc) {
                 tc::mbar_wait(&full[sa], ra & 1);
                 if (PRESPLIT) {
@@ -420,7 +433,9 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                     int kh = 1, kw = 1;
                     if (MODE == MODE_STYLE) {
                         float wk = 0.f;
-                        if (gy < H && gx < W) {
+                        if (slot < TC_STYLE_PRELOAD) {
+                            wk = slot == 0 ? wq[0] : slot == 1 ? wq[1] : slot == 2 ? wq[2] : wq[3];
+                        } else if (gy < H && gx < W) {
                             wk = cls_masks ? __ldg(cls_masks + size_t(nth_set_bit(active, slot)) * H * W + size_t(gy) * W + gx) : 1.0f;
                             wk *= wk;
                         }

@@ -31,6 +31,7 @@ constexpr int GM_THREADS = 512;                                  // 4 warpgroups
 constexpr int GM_REGS_CTRL = 40, GM_REGS_XFORM = 112, GM_REGS_DRAIN = 224;      // setmaxnreg budget, as in conv_tc.cu
 constexpr int GM_CHUNK_ITERS = 4;                                // stages per promoted chunk (8 big MMAs)
 constexpr int GM_RAW_STAGES_MAX = 8;                             // landed float32 tiles in flight: 4 (BN = 128) or 8 (BN = 64)
+constexpr int GM_MASK_AHEAD = 3;                                 // mask values requested this many stages (per warpgroup) early
 constexpr int GM_OP_STAGES = 2;                                  // FP16 operand tiles: slot g belongs to transform warpgroup g
 constexpr int GM_GROUP_BYTES = (GM_PX / 8) * 1024;               // one 64-channel group of an operand tile: 4 KB
 
@@ -213,12 +214,19 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap tmF, const float* __restrict_
             return 0.f;
         };
         static_assert(Cfg::RAW_STAGES % 2 == 0 && Cfg::RAW_STAGES <= GM_RAW_STAGES_MAX && GM_OP_STAGES == 2, "every ring slot must always belong to the same warpgroup");
-        float m_next = mask_of(grp);
+        // The mask value of a stage costs two DEPENDENT global loads (patch id, then the mask at that pixel): ~2 x 700 clk of
+        // latency against ~700 clk of work per stage.  A queue of GM_MASK_AHEAD values per thread keeps that many of this
+        // warpgroup's stages in flight (ncu before: long-scoreboard stalls 8.8 per issued instruction, tensor pipe 20 % busy).
+        float mq[GM_MASK_AHEAD];
+#pragma unroll
+        for (int j = 0; j < GM_MASK_AHEAD; ++j) mq[j] = mask_of(grp + 2 * j);
         for (int it = grp; it < iters; it += 2) {
             // this warpgroup's stages: every second raw slot, operand slot grp
             const int rs = it % Cfg::RAW_STAGES, rround = it / Cfg::RAW_STAGES, os = grp, oround = it >> 1;
-            const float sm = m_next * scale;
-            m_next = mask_of(it + 2);                                   // the dependent global loads of the next stage, early
+            const float sm = mq[0] * scale;
+#pragma unroll
+            for (int j = 0; j + 1 < GM_MASK_AHEAD; ++j) mq[j] = mq[j + 1];
+            mq[GM_MASK_AHEAD - 1] = mask_of(it + 2 * GM_MASK_AHEAD);     // requested now, used GM_MASK_AHEAD stages of this group later
             tc::mbar_wait(&full[rs], rround & 1);                       // the raw tile has landed
             tc::mbar_wait(&empty[os], (oround & 1) ^ 1);                // the MMAs of stage it - 2 no longer read the operand slot
             const uint8_t* st = smem + rs * Cfg::RAW_BYTES;             // raw tile

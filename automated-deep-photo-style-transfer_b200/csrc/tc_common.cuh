@@ -44,13 +44,15 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t by
                  : "memory");
 }
 // Wait on an mbarrier phase.  The first poll is outside the loop: on the MMA-issuing thread every cycle spent here is a
-// cycle the tensor pipe may idle.  After that the thread spins on try_wait (which itself suspends for a
-// hardware-bounded time) and, every 4096 polls, looks at the wall clock (%globaltimer, nanoseconds -- independent of SM
-// clock throttling, preemption and time-slicing): a wait that has made no progress for ADPST_MBAR_TIMEOUT_NS of REAL time
-// (default 30 s; a healthy stage takes microseconds) is a protocol bug and traps, which surfaces as a launch failure
-// instead of a hung GPU.  Build with -DADPST_MBAR_TIMEOUT_NS=0 to spin without any bound.
-#ifndef ADPST_MBAR_TIMEOUT_NS
-#define ADPST_MBAR_TIMEOUT_NS 30000000000ULL
+// cycle the tensor pipe may idle.  After that the thread spins on try_wait (which itself suspends for a hardware-bounded
+// time) and watches the WALL clock: %globaltimer_hi counts units of 2^32 ns (4.3 s) and is independent of SM clock
+// throttling, preemption and time-slicing.  A wait that has made no progress for ADPST_MBAR_TIMEOUT_UNITS of them (default
+// 7: 26-30 s of real time; a healthy stage takes microseconds) is a protocol bug and traps, which surfaces as a launch
+// failure instead of a hung GPU.  One 32-bit register of state: the control warps of the tcgen05 kernels run with 40
+// registers (setmaxnreg), and a 64-bit time stamp plus a poll counter in here made ptxas spill in their loops.
+// Build with -DADPST_MBAR_TIMEOUT_UNITS=0 to spin without any bound.
+#ifndef ADPST_MBAR_TIMEOUT_UNITS
+#define ADPST_MBAR_TIMEOUT_UNITS 7
 #endif
 __device__ __forceinline__ bool mbar_try_wait(uint32_t addr, uint32_t parity) {
     uint32_t done;
@@ -61,23 +63,18 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t addr, uint32_t parity) {
         : "memory");
     return done != 0;
 }
-__device__ __forceinline__ unsigned long long global_timer_ns() {
-    unsigned long long t;
-    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+__device__ __forceinline__ uint32_t global_timer_hi() {
+    uint32_t t;
+    asm volatile("mov.u32 %0, %%globaltimer_hi;" : "=r"(t));
     return t;
 }
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     const uint32_t addr = smem_u32(bar);
     if (mbar_try_wait(addr, parity)) return;
-#if ADPST_MBAR_TIMEOUT_NS > 0
-    unsigned long long t0 = 0;
-    for (uint32_t polls = 1;; ++polls) {
-        if (mbar_try_wait(addr, parity)) return;
-        if ((polls & 4095u) == 0) {
-            const unsigned long long now = global_timer_ns();
-            if (t0 == 0) t0 = now;
-            else if (now - t0 > ADPST_MBAR_TIMEOUT_NS) __trap();
-        }
+#if ADPST_MBAR_TIMEOUT_UNITS > 0
+    const uint32_t t0 = global_timer_hi();
+    while (!mbar_try_wait(addr, parity)) {
+        if (global_timer_hi() - t0 > uint32_t(ADPST_MBAR_TIMEOUT_UNITS)) __trap();
     }
 #else
     while (!mbar_try_wait(addr, parity)) {}
