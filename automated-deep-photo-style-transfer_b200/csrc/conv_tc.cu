@@ -105,7 +105,10 @@ constexpr int TC_MAX_CLASSES = 32;                               // style mode: 
 // tile per K chunk serves all nine taps (the transform warps read their row at the tap's offset), which cuts the A bytes
 // written to shared memory -- and fetched from L2 -- from 9 x 32 KB to 45 KB per chunk.
 // Two rings: the A halo tile lives for nine stages, the B tiles until the MMAs that use them retire.
-template <int BN> struct TcCfg {
+template <int BN, int MODE> struct TcCfg {
+    // Ring depths.  Measured alternatives that did NOT pay (round 2, 1024^2 step): three halo-tile slots with a 4-deep B ring
+    // for BN = 64 (block1_conv2 269/279 TFLOP/s instead of 280/285), two B slots + three halo-tile slots for the style
+    // gradient (330 us instead of 312 us over the four BN = 128 launches), a second small-term accumulator for BN = 64.
     static constexpr int A_STAGES = 2;
     static constexpr int B_STAGES = BN == 128 ? 4 : 6;
     static constexpr int B_BYTES = BN * TC_BK * 2;                          // BN rows x 64 fp16
@@ -117,7 +120,8 @@ template <int BN> struct TcCfg {
     // BN = 128 fills the 512 columns with two slots; BN = 64 has room for four, which it needs: its MMAs of one stage take
     // 384 clk, less than the round trip  tcgen05.st -> MMA -> commit -> a_free -> next tcgen05.st  of a two-slot ring.
     static constexpr int A_SLOTS = BN == 128 ? 2 : 4;
-    static constexpr uint32_t COL_SMALL = 2 * BN, COL_A = 3 * BN, TMEM_COLS = 512;
+    static constexpr int SMALL_BUFS = 1;                                    // small-term accumulators (2 fit for BN = 64: no gain)
+    static constexpr uint32_t COL_SMALL = 2 * BN, COL_A = (2 + SMALL_BUFS) * BN, TMEM_COLS = 512;
     static_assert(COL_A + A_SLOTS * 64 <= TMEM_COLS, "tensor memory columns");
 };
 
@@ -143,8 +147,9 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                   int tiles_w, int num_tiles, const float* __restrict__ cls_masks, const uint32_t* __restrict__ tile_active,
                   const uint32_t* __restrict__ a_absmax, const uint32_t* __restrict__ b_absmax,
                   const uint32_t* __restrict__ w_absmax, uint32_t* __restrict__ y_absmax, float* __restrict__ pool_out) {
-    using Cfg = TcCfg<BN>;
+    using Cfg = TcCfg<BN, MODE>;
     constexpr int AST = Cfg::A_STAGES, BST = Cfg::B_STAGES;
+    constexpr int SB = Cfg::SMALL_BUFS;         // small-term accumulators in tensor memory
     constexpr int NSLOT = Cfg::A_SLOTS;         // A operand slots in tensor memory (ring between the transform warps and the MMAs)
     static_assert(BN == 64 || BN == 128, "tile width");
     extern __shared__ uint8_t smem_raw[];
@@ -156,9 +161,9 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     uint64_t* empty = bars + 12;                // [BST]  MMAs that read the B tiles have retired
     uint64_t* chunk_full = bars + 18;           // [2]    a big-term chunk is complete in TMEM buffer b
     uint64_t* chunk_empty = chunk_full + 2;     // [2]       the drain warps have consumed TMEM buffer b
-    uint64_t* small_full = chunk_empty + 2;     // [1]       every MMA of the work item has retired
-    uint64_t* small_empty = small_full + 1;     // [1]       the drain warps have read the small-term accumulator
-    uint64_t* a_free = small_empty + 1;         // [NSLOT]   the MMAs that read TMEM A slot j have retired
+    uint64_t* small_full = chunk_empty + 2;     // [SB]      every MMA of the work item has retired
+    uint64_t* small_empty = small_full + 2;     // [SB]      the drain warps have read the small-term accumulator
+    uint64_t* a_free = small_empty + 2;         // [NSLOT]   the MMAs that read TMEM A slot j have retired
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(a_free + 4);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -187,8 +192,10 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             tc::mbar_init(&chunk_full[b], 1);
             tc::mbar_init(&chunk_empty[b], 128);
         }
-        tc::mbar_init(small_full, 1);
-        tc::mbar_init(small_empty, 128);
+        for (int j = 0; j < SB; ++j) {
+            tc::mbar_init(&small_full[j], 1);
+            tc::mbar_init(&small_empty[j], 128);
+        }
         for (int j = 0; j < NSLOT; ++j) tc::mbar_init(&a_free[j], 2);
         tc::fence_barrier_init();
         tc::tma_prefetch_desc(&tmA);
@@ -200,7 +207,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     __syncthreads();
     tc::tcgen05_fence_after();
     const uint32_t tmem_base = *tmem_slot;
-    const uint32_t tmem_small = tmem_base + Cfg::COL_SMALL;
+    const uint32_t tmem_small0 = tmem_base + Cfg::COL_SMALL;
     const uint32_t tmem_a = tmem_base + Cfg::COL_A;
 
     // "taps" of an item's K loop: the 9 filter taps (convolution) or the classes whose mask is non-zero somewhere in the
@@ -215,20 +222,35 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(TC_REGS_CTRL));
         if (lane == 0) {
             int sa = 0, ra = 0, s = 0, round = 0;                      // A ring slot / phase, B ring slot / phase
+            // The halo tile of a K chunk comes from HBM (1-2 us), its nine B tiles from L2.  The tile of chunk c + AST - 1 is
+            // therefore requested while the B tiles of chunk c are still being issued -- after the first BST of them, by which
+            // time the MMAs of chunk c - 1 have retired and its slot is free without waiting -- instead of after the last one.
+            // With one K chunk per work item (Cin = 64) the previous order (request after the last B tile, two slots) exposed
+            // most of the load latency once per item (ncu: tensor pipe 40 % busy on block1_conv2).
+            int wa = blockIdx.x, kca = 0;                              // cursor of the next halo tile to request
+            auto skip_empty = [&]() { while (wa < total && __popc(item_active(wa / nblk)) == 0) wa += gridDim.x; };
+            auto issue_a = [&]() {
+                if (wa >= total) return;
+                const int tile = wa / nblk;
+                const int y0 = (tile / tiles_w) * TC_TH, x0 = (tile % tiles_w) * TC_TW;
+                // 10 x 18 pixels x 64 channels, zero-filled outside the image (= SAME padding)
+                tc::mbar_wait(&a_empty[sa], (ra & 1) ^ 1);
+                uint8_t* sta = smem + sa * TC_A_BYTES;
+                tc::mbar_arrive_expect_tx(&full[sa], TC_A_TX_BYTES);
+                tc::tma_load_4d(sta, &tmA, &full[sa], kca * TC_BK, x0 - 1, y0 - 1, 0);
+                tc::tma_load_4d(sta + TC_A_BOX_BYTES, &tmA, &full[sa], kca * TC_BK + 32, x0 - 1, y0 - 1, 0);
+                if (++sa == AST) { sa = 0; ++ra; }
+                if (++kca == kchunks) { kca = 0; wa += gridDim.x; skip_empty(); }
+            };
+            skip_empty();
+            for (int j = 0; j < AST - 1; ++j) issue_a();              // run AST - 1 halo tiles ahead of the B tiles
             for (int w = blockIdx.x; w < total; w += gridDim.x) {
                 const int tile = w / nblk, n0 = (w - tile * nblk) * BN;
-                const int y0 = (tile / tiles_w) * TC_TH, x0 = (tile % tiles_w) * TC_TW;
                 const uint32_t active = item_active(tile);
                 const int ntaps = __popc(active);
                 if (ntaps == 0) continue;
+                const int a_at = (ntaps < BST ? ntaps : BST) - 1;      // request the next halo tile after this many B tiles
                 for (int kc = 0; kc < kchunks; ++kc) {
-                    // the halo tile of this K chunk: 10 x 18 pixels x 64 channels, zero-filled outside the image (= SAME padding)
-                    tc::mbar_wait(&a_empty[sa], (ra & 1) ^ 1);
-                    uint8_t* sta = smem + sa * TC_A_BYTES;
-                    tc::mbar_arrive_expect_tx(&full[sa], TC_A_TX_BYTES);
-                    tc::tma_load_4d(sta, &tmA, &full[sa], kc * TC_BK, x0 - 1, y0 - 1, 0);
-                    tc::tma_load_4d(sta + TC_A_BOX_BYTES, &tmA, &full[sa], kc * TC_BK + 32, x0 - 1, y0 - 1, 0);
-                    if (++sa == AST) { sa = 0; ++ra; }
                     for (int slot = 0; slot < ntaps; ++slot) {
                         const int tap = (MODE == MODE_STYLE) ? nth_set_bit(active, slot) : slot;
                         tc::mbar_wait(&empty[s], (round & 1) ^ 1);
@@ -237,6 +259,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                         tc::tma_load_2d(stb, &tmBhi, &ready[s], kc * TC_BK, tap * Cout + n0);
                         tc::tma_load_2d(stb + Cfg::B_BYTES, &tmBlo, &ready[s], kc * TC_BK, tap * Cout + n0);
                         if (++s == BST) { s = 0; ++round; }
+                        if (slot == a_at) issue_a();
                     }
                 }
             }
@@ -292,10 +315,10 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         for (int w = blockIdx.x; w < total; w += gridDim.x) {
             const int iters = __popc(item_active(w / nblk)) * kchunks;
             if (iters == 0) continue;
-            if (sj > 0) {                                              // the previous item's small terms must have been read
-                tc::mbar_wait(small_empty, (sj - 1) & 1);
-                tc::tcgen05_fence_after();
-            }
+            // the accumulator this item uses must have been read by the drain warps (SB items ago; free the first SB times)
+            tc::mbar_wait(&small_empty[sj % SB], ((sj / SB) & 1) ^ 1);
+            tc::tcgen05_fence_after();
+            const uint32_t tmem_small = tmem_small0 + uint32_t(sj % SB) * BN;
             for (int it = 0; it < iters; ++it, ++git) {
                 const uint32_t a_hi = tmem_a + uint32_t(git % NSLOT) * 64, a_lo = a_hi + 32;
                 tc::mbar_wait(&ready[s], round & 1);
@@ -310,7 +333,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                     }
                     tc::umma_commit(&empty[s]);
                     tc::umma_commit(&a_free[git % NSLOT]);
-                    if (it == iters - 1) tc::umma_commit(small_full);
+                    if (it == iters - 1) tc::umma_commit(&small_full[sj % SB]);
                 }
                 __syncwarp();
                 if (++s == BST) { s = 0; ++round; }
@@ -512,7 +535,8 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             }
             if (iters > 0) {
                 // fold in the small terms and hand their accumulator back at once: the next item's MMAs are already running
-                tc::mbar_wait(small_full, sj & 1);
+                const uint32_t tmem_small = tmem_small0 + uint32_t(sj % SB) * BN;
+                tc::mbar_wait(&small_full[sj % SB], (sj / SB) & 1);
                 tc::tcgen05_fence_after();
 #pragma unroll
                 for (int c0 = 0; c0 < BN; c0 += 32) {
@@ -523,7 +547,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                     for (int j = 0; j < 32; ++j) acc[c0 + j] = fmaf(__uint_as_float(v[j]), inv_small, acc[c0 + j] * inv_big);
                 }
                 tc::tcgen05_fence_before();
-                tc::mbar_arrive(small_empty);
+                tc::mbar_arrive(&small_empty[sj % SB]);
                 ++sj;
             }
             const int gy = (tile / tiles_w) * TC_TH + m / TC_TW, gx = (tile % tiles_w) * TC_TW + m % TC_TW;
@@ -716,7 +740,7 @@ static int launch_tc(const CUtensorMap& tmA, const CUtensorMap& tmBhi, const CUt
                      const float* seed, const float* mask, int H, int W, int Cin, int Cout, const uint32_t* a_absmax,
                      const uint32_t* b_absmax, uint32_t* y_absmax, cudaStream_t st, const float* cls_masks = nullptr,
                      const uint32_t* tile_active = nullptr, const uint32_t* w_absmax = nullptr, float* pool_out = nullptr) {
-    using Cfg = TcCfg<BN>;
+    using Cfg = TcCfg<BN, MODE>;
     auto kern = conv3x3_tc_kernel<BN, MODE>;
     ADPST_ONCE_PER_DEVICE(ADPST_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES)));
     const int tw = (W + TC_TW - 1) / TC_TW, th = (H + TC_TH - 1) / TC_TH;
