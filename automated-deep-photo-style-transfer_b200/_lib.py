@@ -46,6 +46,7 @@ SIGNATURES = {
     "adpst_vgg_forward_range": (_i, [_vp, _vp, _i, _i, _pp, _pp, _i, _i, _vp]),
     "adpst_vgg_backward_range": (_i, [_vp, _i, _i, _pp, _pp, _i, _i, _vp, _vp, _vp, _vp, _vp]),
     "adpst_absmax_update": (_i, [_vp, _sz, _vp, _vp]),
+    "adpst_vgg_grad_absmax": (_vp, [_vp, _i]),
     "adpst_vgg_set_conv_path": (_i, [_vp, _i]),
     "adpst_absmax": (_i, [_vp, _sz, _vp, _vp]),
     "adpst_vgg_act_absmax": (_vp, [_vp, _i]),

@@ -17,6 +17,9 @@ from ...synth import CONV_LAYERS
 LAYER_INDEX = {name: i for i, (name, _, _) in enumerate(CONV_LAYERS)}
 POOL_AFTER = (1, 3, 7, 11)
 BLOCKS = ((0, 1), (2, 3), (4, 7), (8, 11), (12, 12))      # conv index ranges of block1 .. block5
+# Segments of a spatially tiled pass (tiled.py): the blocks, with block4 cut in two so that no segment has more than two
+# convolutions at 1/8 resolution -- a halo of h columns supports n <= h / 2 convolutions between two exchanges.
+SEGMENTS = ((0, 1), (2, 3), (4, 7), (8, 9), (10, 11), (12, 12))
 
 
 def _load_weights(weights):
@@ -72,12 +75,12 @@ class VGG19Handle:
         """Device address of the slot holding max|conv i output| of the latest forward pass."""
         return _lib.lib().adpst_vgg_act_absmax(self._h, i)
 
-    def absmax_update(self, t, i):
-        """Raise the slot of conv i's output to max|t| if that is larger (t: data patched into the tensor after its producer
-        ran, e.g. halo columns received from a neighbouring rank)."""
+    def absmax_update(self, t, i, grad=False):
+        """Raise the slot of conv i's output (grad: of the gradient w.r.t. its pre-activation) to max|t| if that is larger
+        (t: data patched into the tensor after its producer ran, e.g. halo columns received from a neighbouring rank)."""
+        slot = _lib.lib().adpst_vgg_grad_absmax(self._h, i) if grad else self.act_absmax_ptr(i)
         with torch.cuda.device(self.device):
-            _lib.check(_lib.lib().adpst_absmax_update(_lib.ptr(t), t.numel(), ctypes.c_void_p(self.act_absmax_ptr(i)),
-                                                      _lib.stream_ptr()))
+            _lib.check(_lib.lib().adpst_absmax_update(_lib.ptr(t), t.numel(), ctypes.c_void_p(slot), _lib.stream_ptr()))
 
     def __del__(self):
         h, self._h = getattr(self, "_h", None), None
@@ -179,9 +182,10 @@ class StyleContentModel:
 
     # ---- spatially tiled runs (tiled.py): block by block, with a halo exchange on every tensor that crosses a pool --------
     def forward_blocks(self, inputs, exchange, reuse=True):
-        """Like call(), but the network runs one block at a time and `exchange(level, tensor)` is called on every pooled
-        tensor (level 1..4: the input of block level+1) before the next block reads it.  `exchange` overwrites the halo
-        columns in place with the neighbours' data and returns the received slabs (contiguous tensors) or an empty list."""
+        """Like call(), but the network runs one segment (SEGMENTS) at a time and `exchange(tensor)` is called on the tensor
+        that leaves a segment -- the pooled tensor, or conv 9's output between the two halves of block4 -- before the next
+        segment reads it.  `exchange` overwrites the halo columns in place with the neighbours' data and returns the received
+        slabs (contiguous tensors) or an empty list."""
         if inputs.dim() != 4 or inputs.shape[0] != 1 or inputs.shape[3] != 3 or inputs.dtype != torch.float32 or not inputs.is_cuda:
             raise TypeError("expected a float32 CUDA image of shape (1, H, W, 3)")
         x = inputs.contiguous()
@@ -193,16 +197,18 @@ class StyleContentModel:
         else:
             A = Activations(H, W, self.last_index, self.device)
         L = _lib.lib()
-        for b, (first, last) in enumerate(BLOCKS):
+        for first, last in SEGMENTS:
             if first > self.last_index:
                 break
             last = min(last, self.last_index)
             with torch.cuda.device(self.device):
                 _lib.check(L.adpst_vgg_forward_range(self.vgg._h, _lib.ptr(x), H, W, _lib.ptr_array(A.acts),
                                                      _lib.ptr_array(A.pools), first, last, _lib.stream_ptr()))
-            if b < len(POOL_AFTER) and A.pools[b] is not None and last == POOL_AFTER[b]:
-                for slab in exchange(b + 1, A.pools[b]):
-                    self.vgg.absmax_update(slab, last)          # a pooled tensor shares the scale slot of the conv before it
+            if last == self.last_index:
+                break
+            out = A.pools[POOL_AFTER.index(last)] if last in POOL_AFTER else A.acts[last]
+            for slab in exchange(out):
+                self.vgg.absmax_update(slab, last)              # a pooled tensor shares the scale slot of the conv before it
         self.last = A
         self.vgg.generation += 1
         names = self.content_layers + self.style_layers
@@ -214,8 +220,9 @@ class StyleContentModel:
         return {"content": content, "style": style}
 
     def backward_blocks(self, seeds, exchange, out=None):
-        """Like backward(), block by block from the top: the gradient w.r.t. every pooled tensor is handed to
-        `exchange(level, tensor)` (halo columns replaced by the owners' complete values) before the block below uses it."""
+        """Like backward(), segment by segment from the top: the gradient that leaves a segment -- w.r.t. the pooled tensor
+        below it, or w.r.t. conv 9's pre-activation between the two halves of block4 -- is handed to `exchange(tensor)` (halo
+        columns replaced by the owners' complete values) before the segment below uses it."""
         A = self.last
         if A is None:
             raise RuntimeError("backward_blocks() needs a preceding forward call")
@@ -231,26 +238,35 @@ class StyleContentModel:
                              torch.empty(A.acts[0].numel(), dtype=torch.float32, device=self.device))
         if out is None:
             out = torch.empty(1, A.H, A.W, 3, dtype=torch.float32, device=self.device)
-        if self._dpool is None or self._dpool[0].shape != A.pools[0].shape:
-            self._dpool = [torch.empty_like(p) if p is not None else None for p in A.pools]
+        if self._dseg is None or self._dseg_shape != (A.H, A.W):
+            # the gradient that leaves segment s (entering at conv `first`): shaped like that segment's input
+            self._dseg = {}
+            for first, _ in SEGMENTS[1:]:
+                src = A.pools[POOL_AFTER.index(first - 1)] if (first - 1) in POOL_AFTER else A.acts[first - 1]
+                if src is not None:
+                    self._dseg[first] = torch.empty_like(src)
+            self._dseg_shape = (A.H, A.W)
         L = _lib.lib()
-        dpool = None
-        for b in reversed(range(len(BLOCKS))):
-            first, last = BLOCKS[b]
+        grad_in = None
+        for first, last in reversed(SEGMENTS):
             if first > top:
                 continue
             last = min(last, top)
-            target = out if first == 0 else self._dpool[b - 1]
+            target = out if first == 0 else self._dseg[first]
             with torch.cuda.device(self.device):
                 _lib.check(L.adpst_vgg_backward_range(self.vgg._h, A.H, A.W, _lib.ptr_array(A.acts), _lib.ptr_array(arr), first,
-                                                      last, _lib.ptr(dpool), _lib.ptr(self._scratch[0]),
+                                                      last, _lib.ptr(grad_in), _lib.ptr(self._scratch[0]),
                                                       _lib.ptr(self._scratch[1]), _lib.ptr(target), _lib.stream_ptr()))
             if first > 0:
-                exchange(b, target)
-                dpool = target
+                slabs = exchange(target)
+                if (first - 1) not in POOL_AFTER:               # mid-block: the consumer reads the slot of conv first-1's gradient
+                    for slab in slabs:
+                        self.vgg.absmax_update(slab, first - 1, grad=True)
+                grad_in = target
         return out
 
-    _dpool = None
+    _dseg = None
+    _dseg_shape = None
 
     def backward(self, seeds, out=None):
         """seeds: dict layer name -> dLoss/d(layer output) (1,h,w,C) float32.  Returns dLoss/d(image) (1,H,W,3)."""

@@ -612,12 +612,15 @@ int adpst_vgg_conv_dgrad(adpst_vgg* h, int i, const float* dpre_dev, int lh, int
     return launch_conv(h, i, MODE_BWD, dpre_dev, dx_dev, nullptr, nullptr, lh, lw, dpre_absmax_dev, nullptr, as_stream(stream));
 }
 
-// Backward through convs last..first.  The chain enters either at the top (dpool_in == NULL: the seed of conv `last` goes
-// through its ReLU mask) or below a pool (dpool_in = dLoss/d(pooled output of conv `last`), routed through the un-pool, the
-// ReLU mask and the seed of conv `last`).  It leaves either at the image (first == 0: out = dLoss/d(image)) or above a pool
-// (first > 0 must be the first convolution of a block: out = dLoss/d(pooled input of conv `first`)).
+// Backward through convs last..first.
+// Entry: at the top (grad_in == NULL: the seed of conv `last` goes through its ReLU mask); below a pool (conv `last` is followed
+// by a pool: grad_in = dLoss/d(pooled output of conv last), routed through the un-pool, the ReLU mask and the seed of conv last);
+// or in the middle of a block (no pool after conv `last`: grad_in = dLoss/d(pre-activation of conv last), already masked).
+// Exit: at the image (first == 0: out = dLoss/d(image)); above a pool (conv `first` follows a pool: out = dLoss/d(pooled input
+// of conv first)); or in the middle of a block (out = dLoss/d(pre-activation of conv first - 1), i.e. with the seed and the
+// ReLU mask of conv first - 1 applied -- exactly what the next call takes as grad_in).
 static int vgg_backward_range(adpst_vgg* h, int H, int W, const float* const* acts_dev, const float* const* seeds_dev, int first,
-                              int last, const float* dpool_in, float* scratch0_dev, float* scratch1_dev, float* out_dev,
+                              int last, const float* grad_in, float* scratch0_dev, float* scratch1_dev, float* out_dev,
                               cudaStream_t st) {
     using namespace adpst;
     float* cur = scratch0_dev;   // holds dLoss/d(pre-activation of conv i)
@@ -625,17 +628,28 @@ static int vgg_backward_range(adpst_vgg* h, int H, int W, const float* const* ac
     int lh, lw;
     layer_hw(last, H, W, &lh, &lw);
     uint32_t* gmax = h->amax + AMAX_GRAD;          // gmax[i]: max|dLoss/d(pre-activation of conv i)|
-    ADPST_CUDA_CHECK(cudaMemsetAsync(gmax + first, 0, (last - first + 1) * sizeof(uint32_t), st));
-    if (dpool_in == nullptr) {
+    bool pooled_top = false;
+    for (int j = 0; j < ADPST_VGG_NUM_POOL; ++j) pooled_top |= (kPoolAfter[j] == last);
+    const bool mid_entry = grad_in != nullptr && !pooled_top;
+    bool mid_exit = first > 0;
+    for (int j = 0; j < ADPST_VGG_NUM_POOL; ++j)
+        if (kPoolAfter[j] == first - 1) mid_exit = false;
+    // slots written in this call: a mid-block entry arrives with gmax[last] already set by the producer of grad_in; a
+    // mid-block exit also writes gmax[first - 1]
+    const int zlo = first - (mid_exit ? 1 : 0), zhi = last - (mid_entry ? 1 : 0);
+    if (zhi >= zlo) ADPST_CUDA_CHECK(cudaMemsetAsync(gmax + zlo, 0, (zhi - zlo + 1) * sizeof(uint32_t), st));
+    if (grad_in == nullptr) {
         ADPST_REQUIRE(seeds_dev[last] != nullptr, "vgg_backward: the seed of the last layer (%d) is required", last);
         const size_t n4 = size_t(lh) * lw * conv_cout(last) / 4;
         relu_mask_kernel<<<stream_grid(n4), 256, 0, st>>>(acts_dev[last], seeds_dev[last], cur, n4, gmax + last);
         ADPST_LAUNCH_CHECK();
-    } else {
+    } else if (pooled_top) {
         const size_t items = size_t((lh + 1) / 2) * ((lw + 1) / 2) * (conv_cout(last) / 4);
-        unpool_relu_kernel<<<stream_grid(items), 256, 0, st>>>(acts_dev[last], dpool_in, seeds_dev[last], cur, lh, lw,
+        unpool_relu_kernel<<<stream_grid(items), 256, 0, st>>>(acts_dev[last], grad_in, seeds_dev[last], cur, lh, lw,
                                                                conv_cout(last), gmax + last);
         ADPST_LAUNCH_CHECK();
+    } else {
+        ADPST_CUDA_CHECK(cudaMemcpyAsync(cur, grad_in, size_t(lh) * lw * conv_cout(last) * sizeof(float), cudaMemcpyDeviceToDevice, st));
     }
     for (int i = last; i >= (first > 0 ? first : 1); --i) {
         layer_hw(i, H, W, &lh, &lw);
@@ -643,9 +657,10 @@ static int vgg_backward_range(adpst_vgg* h, int H, int W, const float* const* ac
         for (int j = 0; j < ADPST_VGG_NUM_POOL; ++j) pooled_input |= (kPoolAfter[j] == i - 1);
         if (!pooled_input) {
             // input of conv i is the post-ReLU output of conv i-1 at the same resolution
-            ADPST_REQUIRE(i > first, "vgg_backward: conv %d is not the first convolution of a block", first);
-            int rc = launch_conv(h, i, MODE_BWD, cur, nxt, seeds_dev[i - 1], acts_dev[i - 1], lh, lw, gmax + i, gmax + i - 1, st);
+            float* dst = (i == first) ? out_dev : nxt;              // (first > 0 here: leave in the middle of a block)
+            int rc = launch_conv(h, i, MODE_BWD, cur, dst, seeds_dev[i - 1], acts_dev[i - 1], lh, lw, gmax + i, gmax + i - 1, st);
             if (rc != ADPST_OK) return rc;
+            if (i == first) return ADPST_OK;
             float* t = cur; cur = nxt; nxt = t;
         } else if (i == first) {
             // leave above the pool: gradient w.r.t. the pooled tensor straight into the caller's buffer
@@ -681,20 +696,18 @@ int adpst_vgg_backward(adpst_vgg* h, int H, int W, const float* const* acts_dev,
 }
 
 int adpst_vgg_backward_range(adpst_vgg* h, int H, int W, const float* const* acts_dev, const float* const* seeds_dev, int first,
-                             int last, const float* dpool_in_dev, float* scratch0_dev, float* scratch1_dev, float* out_dev,
+                             int last, const float* grad_in_dev, float* scratch0_dev, float* scratch1_dev, float* out_dev,
                              adpst_stream_t stream) {
     using namespace adpst;
     ADPST_REQUIRE(h && acts_dev && seeds_dev && scratch0_dev && scratch1_dev && out_dev, "vgg_backward_range: NULL argument");
     ADPST_REQUIRE(first >= 0 && first <= last && last < kNumConv, "vgg_backward_range: bad range %d..%d", first, last);
-    bool block_start = first == 0, pooled_top = false;
-    for (int j = 0; j < ADPST_VGG_NUM_POOL; ++j) {
-        block_start |= (kPoolAfter[j] == first - 1);
-        pooled_top |= (kPoolAfter[j] == last);
-    }
-    ADPST_REQUIRE(block_start, "vgg_backward_range: conv %d does not follow a pool", first);
-    ADPST_REQUIRE(dpool_in_dev == nullptr || pooled_top, "vgg_backward_range: conv %d is not followed by a pool", last);
-    return vgg_backward_range(h, H, W, acts_dev, seeds_dev, first, last, dpool_in_dev, scratch0_dev, scratch1_dev, out_dev,
+    return vgg_backward_range(h, H, W, acts_dev, seeds_dev, first, last, grad_in_dev, scratch0_dev, scratch1_dev, out_dev,
                               as_stream(stream));
+}
+
+const uint32_t* adpst_vgg_grad_absmax(const adpst_vgg* h, int i) {
+    if (!h || i < 0 || i >= adpst::kNumConv || !h->amax) return nullptr;
+    return h->amax + adpst::AMAX_GRAD + i;
 }
 
 }  // extern "C"

@@ -1,19 +1,21 @@
 """One large image optimised on several GPUs (BASELINE configs[3]).
 
-The image is cut into column strips, one per rank; a rank stores its strip plus a halo of HALO = 64 image pixels on every
-interior side (halo of a level-l feature map: 64 / 2^l columns: 64, 32, 16, 8, 4 for blocks 1..5).  What a rank needs from
-its neighbours is exchanged, point to point over NVLink, where the data crosses a pooling layer:
+The image is cut into column strips, one per rank; a rank stores its strip plus a halo of HALO = 32 image pixels on every
+interior side (halo of a level-l feature map: 32 / 2^l columns: 32, 16, 8, 4, 2 for blocks 1..5).  What a rank needs from
+its neighbours is exchanged, point to point over NVLink, between the SEGMENTS of the network (the five blocks, block4 cut in
+two):
 
-  forward    after every pool, the pooled tensor's halo columns are overwritten with the owner's values, so each block starts
-             from exact inputs on own + halo.  Inside a block of n convolutions the valid region shrinks by one column per
-             convolution (the local edge is zero padded), which leaves every activation exact on the own columns plus the
-             n halo columns that the backward pass needs (ReLU masks, arg-max routing): 64 / 2^l >= 2 n holds for every block.
-  backward   the gradient w.r.t. every pooled tensor (the quantity that flows from block b+1 into block b) is exact on the
-             own columns only; its halo columns are overwritten with the owners' complete values before block b continues.
+  forward    the tensor that leaves a segment (the pooled tensor; conv 9's output inside block4) gets its halo columns
+             overwritten with the owner's values, so each segment starts from exact inputs on own + halo.  Inside a segment of
+             n convolutions the valid region shrinks by one column per convolution (the local edge is zero padded); the
+             backward pass needs the activations' ReLU masks / arg-max routing exact on n halo columns, so a segment may
+             hold n <= halo / 2 convolutions: (2, 2, 4, 2, 2, 1) against halos of (32, 16, 8, 4, 4, 2) columns.
+  backward   the gradient that flows from a segment into the one below is exact on the own columns only; its halo columns
+             are overwritten with the owners' complete values before the lower segment continues.
   image      after the Adam update the HALO columns next to each interior boundary are refreshed from the owner.
 
-Nine exchanges per iteration (4 forward, 4 backward, 1 image, with both neighbours each), 0.1-3 MB per slab at 3840x2160; the
-redundant convolution work is (own + 2 x 64) / own instead of (own + 2 x 160) / own of the previous overlapped-strip design.
+Eleven exchanges per iteration (5 forward, 5 backward, 1 image, with both neighbours each), 0.1-2 MB per slab at 3840x2160; the
+redundant convolution work is (own + 2 x 32) / own -- it was (own + 2 x 160) / own with round 1's overlapped strips.
 The only collective is ONE NCCL all-reduce of the flattened per-class Gram partials of the five style layers (each rank sums
 over its OWN pixels; 19.5 MB at K = 8) plus the 4-entry float64 loss accumulator.
 
@@ -29,7 +31,7 @@ from .components.VGG19.model import StyleContentModel
 from .components.loss import Loss
 from .style_transfer import Adam, CONTENT_LAYERS, STYLE_LAYERS
 
-HALO = 64
+HALO = 32
 
 
 class Tile:
@@ -242,8 +244,8 @@ class TiledStyleTransfer:
         self._flat = None                               # flat float32 buffer behind the per-layer Gram partials
 
     def _exchanger(self, tile):
-        """exchange(level, tensor) for feature maps / gradients of this strip: level l tensors have local width local_w / 2^l."""
-        def ex(level, tensor):
+        """exchange(tensor) for the image, feature maps and gradients of this strip (the level follows from the width)."""
+        def ex(tensor):
             w_l = int(tensor.shape[-2])
             lo, hi = tile.own_cols(w_l)
             return self.comm.exchange(tensor, lo, hi, tile.halo_cols(w_l))
@@ -263,8 +265,8 @@ class TiledStyleTransfer:
     def describe_exchange(self):
         if self.world == 1:
             return "no exchange (single strip)"
-        return ("point-to-point halo exchange of every pooled tensor (forward) and of its gradient (backward) plus the image "
-                "border after the update (%d px halo), one NCCL all-reduce of the flattened Gram partials (%.1f MB) + float64[4] "
+        return ("point-to-point halo exchange between the six network segments (forward activations, backward gradients) and of "
+                "the image border after the update (%d px halo), one NCCL all-reduce of the flattened Gram partials (%.1f MB) + float64[4] "
                 "loss accumulator" % (HALO, 4e-6 * (self._flat.numel() if self._flat is not None else 0)))
 
     def exchange_bytes(self):
@@ -327,7 +329,7 @@ class TiledStyleTransfer:
         grad = self.loss.gradient(self.extractor, out=self._grad,
                                   backward=lambda seeds, out: self.extractor.backward_blocks(seeds, ex, out=out))
         self.optimizer.apply_gradients_and_clip(grad, self.image)      # only the own columns of the result are meaningful
-        ex(0, self.image)                                              # refresh the image halo from the owners
+        ex(self.image)                                                 # refresh the image halo from the owners
         return loss_dict
 
 

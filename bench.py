@@ -83,34 +83,46 @@ def conv_flops(size):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+    """nvidia-smi clocks / throttle reasons sampled every 100 ms.  start() launches nvidia-smi (before the warm-up, so that its
+    start-up cost of up to a second on a fresh box is not inside the timed region) and waits for its first line; mark() is called
+    when the timed region begins and stop() when the last timed loop (device-timed steps, then the end-to-end steps: the same
+    load) has ended; only the samples in between are reported."""
     Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown," \
         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown," \
         "clocks_event_reasons.sw_power_cap"
 
     def __init__(self, index):
-        self.index, self.proc, self.lines = index, None, []
+        self.index, self.proc, self.lines, self.t_mark = index, None, [], None
 
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._pump, daemon=True).start()
+            t0 = time.perf_counter()
+            while not self.lines and time.perf_counter() - t0 < 10.0 and self.proc.poll() is None:
+                time.sleep(0.02)
         except Exception:
             self.proc = None
 
     def _pump(self):
         for line in self.proc.stdout:
-            self.lines.append(line.strip())
+            self.lines.append((time.perf_counter(), line.strip()))
+
+    def mark(self):
+        self.t_mark = time.perf_counter()
 
     def stop(self):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.25)
+        t_end = time.perf_counter()
+        time.sleep(0.15)
         self.proc.terminate()
         sm, mx, reasons = [], [], set()
-        for ln in self.lines:
+        for t, ln in list(self.lines):
+            if self.t_mark is not None and not (self.t_mark <= t <= t_end + 0.1):
+                continue
             f = [x.strip() for x in ln.split(",")]
             if len(f) < 8:
                 continue
@@ -641,12 +653,13 @@ def run_ours(args):
     x.copy_(content); opt._slots.m.zero_(); opt._slots.v.zero_(); opt._slots.state.zero_()
     step = st.make_train_step(ext, loss, opt, use_cuda_graph=True)
 
-    for _ in range(max(args.warmup, 3)):
-        step(x)
     sampler = ClockSampler(local)
-    D.barrier()
     if rank == 0:
         sampler.start()
+    for _ in range(max(args.warmup, 3)):
+        step(x)
+    D.barrier()
+    sampler.mark()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     D.barrier()
     e0.record()
@@ -655,7 +668,6 @@ def run_ours(args):
     e1.record()
     D.barrier()
     total_ms = D.max_ms(e0.elapsed_time(e1))
-    clocks = sampler.stop() if rank == 0 else None
     final_total = float(d["Total loss"])
 
     # e2e: image starts and ends in pinned host memory every step; losses read back every step
@@ -676,6 +688,9 @@ def run_ours(args):
     e1.record(); D.barrier()
     e2e_ms = D.max_ms(e0.elapsed_time(e1))
     wall_e2e = time.perf_counter() - t0
+    clocks = sampler.stop() if rank == 0 else None
+    if clocks is not None:
+        clocks["window"] = "the device-timed steps and the end-to-end steps that follow them, sampled every 100 ms"
 
     out = None
     if rank == 0:

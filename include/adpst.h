@@ -152,13 +152,18 @@ int adpst_vgg_backward(adpst_vgg* h, int H, int W, const float* const* acts_dev,
                        const float* const* seeds_dev, int last, float* scratch0_dev, float* scratch1_dev,
                        float* dimage_dev, adpst_stream_t stream);
 
-/* Backward through convs last..first only.  dpool_in_dev: NULL (the chain starts at conv `last` with its seed) or
- * dLoss/d(pooled output of conv `last`) (conv `last` must be followed by a pool).  first must be 0 (out_dev = dLoss/d(image))
- * or the first convolution after a pool (out_dev = dLoss/d(that pooled tensor)).  Spatially tiled runs exchange the halo
- * columns of these pooled-tensor gradients between the calls. */
+/* Backward through convs last..first only (spatially tiled runs exchange halo columns between the calls).
+ * Entry  grad_in_dev == NULL: the chain starts at conv `last` with its seed;
+ *        conv `last` is followed by a pool: grad_in_dev = dLoss/d(pooled output of conv last);
+ *        otherwise: grad_in_dev = dLoss/d(pre-activation of conv last) (already ReLU-masked), with its max|.| in the slot
+ *        adpst_vgg_grad_absmax(h, last) (left there by the call that produced it; adpst_absmax_update after patching it).
+ * Exit   first == 0: out_dev = dLoss/d(image);  conv `first` follows a pool: out_dev = dLoss/d(that pooled tensor);
+ *        otherwise: out_dev = dLoss/d(pre-activation of conv first-1) (seed and ReLU mask of conv first-1 applied). */
 int adpst_vgg_backward_range(adpst_vgg* h, int H, int W, const float* const* acts_dev, const float* const* seeds_dev, int first,
-                             int last, const float* dpool_in_dev, float* scratch0_dev, float* scratch1_dev, float* out_dev,
+                             int last, const float* grad_in_dev, float* scratch0_dev, float* scratch1_dev, float* out_dev,
                              adpst_stream_t stream);
+/* slot holding max|dLoss/d(pre-activation of conv i)| of the latest backward pass (device pointer). */
+const uint32_t* adpst_vgg_grad_absmax(const adpst_vgg* h, int i);
 
 /* ------------------------------------------------------------------------------------------------
  * Loss terms: components/loss.py

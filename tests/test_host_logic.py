@@ -134,23 +134,25 @@ def test_tile_geometry():
     """Spatial tiling (BASELINE configs[3]): strip / halo arithmetic, CPU only."""
     tiled = importlib.import_module(PKG_NAME + ".tiled")
     t = tiled.Tile(3840, 3, 8)
-    assert (t.own_lo, t.own_hi, t.ext_lo, t.ext_hi, t.local_w) == (1440, 1920, 1376, 1984, 608)
-    assert t.own_cols(608) == (64, 544) and t.own_cols(38) == (4, 34) and t.global_cols(38) == 240 and t.halo_cols(38) == 4
+    assert (t.own_lo, t.own_hi, t.ext_lo, t.ext_hi, t.local_w) == (1440, 1920, 1408, 1952, 544)
+    assert t.own_cols(544) == (32, 512) and t.own_cols(34) == (2, 32) and t.global_cols(34) == 240 and t.halo_cols(34) == 2
     t0 = tiled.Tile(3840, 0, 8)
-    assert (t0.ext_lo, t0.ext_hi) == (0, 544) and t0.own_cols(544) == (0, 480)
+    assert (t0.ext_lo, t0.ext_hi) == (0, 512) and t0.own_cols(512) == (0, 480)
     with pytest.raises(ValueError):
         tiled.Tile(1000, 0, 8)
     # every pixel is owned by exactly one rank; the halo of a level-l tensor (HALO / 2^l columns) must cover twice the number
-    # of convolutions of the block that reads it (forward validity shrinks by one column per convolution, the backward pass
-    # needs the ReLU masks that many columns out): blocks 1..5 have 2, 2, 4, 4, 1 convolutions
+    # of convolutions of the segment that reads it (forward validity shrinks by one column per convolution, the backward pass
+    # needs the ReLU masks that many columns out)
     owned = np.zeros(3840, int)
     for r in range(8):
         tr = tiled.Tile(3840, r, 8)
         owned[tr.own_lo:tr.own_hi] += 1
         assert tr.own_lo - tr.ext_lo in (0, tiled.HALO) and tr.ext_hi - tr.own_hi in (0, tiled.HALO)
     assert (owned == 1).all() and tiled.HALO % 16 == 0
-    for level, nconv in enumerate((2, 2, 4, 4, 1)):
-        assert tiled.HALO >> level >= 2 * nconv
+    vgg = importlib.import_module(PKG_NAME + ".components.VGG19.model")
+    for first, last in vgg.SEGMENTS:
+        level = sum(1 for p in vgg.POOL_AFTER if p < first)
+        assert tiled.HALO >> level >= 2 * (last - first + 1), (first, last)
 
 
 _TILED_WORKER = r"""
