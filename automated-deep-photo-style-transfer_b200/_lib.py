@@ -47,6 +47,14 @@ SIGNATURES = {
     "adpst_vgg_backward_range": (_i, [_vp, _i, _i, _pp, _pp, _i, _i, _vp, _vp, _vp, _vp, _vp]),
     "adpst_absmax_update": (_i, [_vp, _sz, _vp, _vp]),
     "adpst_vgg_grad_absmax": (_vp, [_vp, _i]),
+    "adpst_halo_create": (_i, [_sz, _pp]),
+    "adpst_halo_destroy": (None, [_vp]),
+    "adpst_halo_ipc_handle_bytes": (_i, []),
+    "adpst_halo_export": (_i, [_vp, _vp]),
+    "adpst_halo_connect_ipc": (_i, [_vp, _i, _vp, _sz]),
+    "adpst_halo_connect_local": (_i, [_vp, _i, _vp]),
+    "adpst_halo_push": (_i, [_vp, _i, _sz, _vp, _i, _i, _i, _i, _i, _i, _vp]),
+    "adpst_halo_pull": (_i, [_vp, _i, _sz, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp]),
     "adpst_vgg_set_conv_path": (_i, [_vp, _i]),
     "adpst_absmax": (_i, [_vp, _sz, _vp, _vp]),
     "adpst_vgg_act_absmax": (_vp, [_vp, _i]),

@@ -75,10 +75,13 @@ class VGG19Handle:
         """Device address of the slot holding max|conv i output| of the latest forward pass."""
         return _lib.lib().adpst_vgg_act_absmax(self._h, i)
 
-    def absmax_update(self, t, i, grad=False):
-        """Raise the slot of conv i's output (grad: of the gradient w.r.t. its pre-activation) to max|t| if that is larger
-        (t: data patched into the tensor after its producer ran, e.g. halo columns received from a neighbouring rank)."""
-        slot = _lib.lib().adpst_vgg_grad_absmax(self._h, i) if grad else self.act_absmax_ptr(i)
+    def grad_absmax_ptr(self, i):
+        """Device address of the max|dLoss/d(pre-activation of conv i)| word of the latest backward pass."""
+        return _lib.lib().adpst_vgg_grad_absmax(self._h, i)
+
+    def absmax_update(self, t, slot):
+        """Raise the scale word at device address `slot` (act_absmax_ptr / grad_absmax_ptr) to max|t| if that is larger (t: data
+        patched into the tensor after its producer ran, e.g. halo columns received from a neighbouring rank)."""
         with torch.cuda.device(self.device):
             _lib.check(_lib.lib().adpst_absmax_update(_lib.ptr(t), t.numel(), ctypes.c_void_p(slot), _lib.stream_ptr()))
 
@@ -181,11 +184,13 @@ class StyleContentModel:
         return {"content": content, "style": style}
 
     # ---- spatially tiled runs (tiled.py): block by block, with a halo exchange on every tensor that crosses a pool --------
-    def forward_blocks(self, inputs, exchange, reuse=True):
-        """Like call(), but the network runs one segment (SEGMENTS) at a time and `exchange(tensor)` is called on the tensor
-        that leaves a segment -- the pooled tensor, or conv 9's output between the two halves of block4 -- before the next
-        segment reads it.  `exchange` overwrites the halo columns in place with the neighbours' data and returns the received
-        slabs (contiguous tensors) or an empty list."""
+    def forward_blocks(self, inputs, exchange, reuse=True, overlap=None):
+        """Like call(), but the network runs one segment (SEGMENTS) at a time and `exchange(tensor, slot)` is called on the
+        tensor that leaves a segment -- the pooled tensor, or conv 9's output between the two halves of block4 -- before the
+        next segment reads it.  `exchange` overwrites the halo columns in place with the neighbours' data and raises the scale
+        slot `slot` (device address of the tensor's max|.| word, see VGG19Handle.absmax_update) to the maximum of what arrived.
+        overlap(last, outputs): optional; work that only needs the layers up to conv `last`, handed to exchange() as a third
+        argument (a callable without arguments) to be enqueued while the halo columns are in flight."""
         if inputs.dim() != 4 or inputs.shape[0] != 1 or inputs.shape[3] != 3 or inputs.dtype != torch.float32 or not inputs.is_cuda:
             raise TypeError("expected a float32 CUDA image of shape (1, H, W, 3)")
         x = inputs.contiguous()
@@ -197,6 +202,15 @@ class StyleContentModel:
         else:
             A = Activations(H, W, self.last_index, self.device)
         L = _lib.lib()
+        self.last = A
+        self.vgg.generation += 1
+        names = self.content_layers + self.style_layers
+        outs = [A.acts[i] for i in self.indices]
+        for i, o in zip(self.indices, outs):
+            o._adpst_absmax = (weakref.ref(self.vgg), self.vgg.generation, i)
+        content = {n: o for n, o in zip(names[:self.limit], outs[:self.limit])}
+        style = {n: o for n, o in zip(names[self.limit:], outs[self.limit:])}
+        outputs = {"content": content, "style": style}
         for first, last in SEGMENTS:
             if first > self.last_index:
                 break
@@ -207,22 +221,19 @@ class StyleContentModel:
             if last == self.last_index:
                 break
             out = A.pools[POOL_AFTER.index(last)] if last in POOL_AFTER else A.acts[last]
-            for slab in exchange(out):
-                self.vgg.absmax_update(slab, last)              # a pooled tensor shares the scale slot of the conv before it
-        self.last = A
-        self.vgg.generation += 1
-        names = self.content_layers + self.style_layers
-        outs = [A.acts[i] for i in self.indices]
-        for i, o in zip(self.indices, outs):
-            o._adpst_absmax = (weakref.ref(self.vgg), self.vgg.generation, i)
-        content = {n: o for n, o in zip(names[:self.limit], outs[:self.limit])}
-        style = {n: o for n, o in zip(names[self.limit:], outs[self.limit:])}
-        return {"content": content, "style": style}
+            # a pooled tensor shares the scale slot of the conv before it
+            exchange(out, self.vgg.act_absmax_ptr(last), None if overlap is None else (lambda l=last: overlap(l, outputs)))
+        return outputs
 
-    def backward_blocks(self, seeds, exchange, out=None):
+    def backward_blocks(self, seeds, exchange, out=None, overlap=None):
         """Like backward(), segment by segment from the top: the gradient that leaves a segment -- w.r.t. the pooled tensor
-        below it, or w.r.t. conv 9's pre-activation between the two halves of block4 -- is handed to `exchange(tensor)` (halo
-        columns replaced by the owners' complete values) before the segment below uses it."""
+        below it, or w.r.t. conv 9's pre-activation between the two halves of block4 -- is handed to `exchange(tensor, slot)`
+        (halo columns replaced by the owners' complete values; slot: None, or the scale word the consumer reads for that
+        gradient) before the segment below uses it.
+        overlap(first): optional.  The seed tensors may be filled lazily: overlap(first) is called (a) directly, with the first
+        conv index of the segment that is about to run, and must make sure that the seeds of every layer >= first hold their
+        values, and (b) through exchange()'s third argument with first = -1 while halo columns are in flight, where it may
+        produce any seed that is still missing."""
         A = self.last
         if A is None:
             raise RuntimeError("backward_blocks() needs a preceding forward call")
@@ -253,15 +264,17 @@ class StyleContentModel:
                 continue
             last = min(last, top)
             target = out if first == 0 else self._dseg[first]
+            if overlap is not None:
+                overlap(first)
             with torch.cuda.device(self.device):
                 _lib.check(L.adpst_vgg_backward_range(self.vgg._h, A.H, A.W, _lib.ptr_array(A.acts), _lib.ptr_array(arr), first,
                                                       last, _lib.ptr(grad_in), _lib.ptr(self._scratch[0]),
                                                       _lib.ptr(self._scratch[1]), _lib.ptr(target), _lib.stream_ptr()))
             if first > 0:
-                slabs = exchange(target)
-                if (first - 1) not in POOL_AFTER:               # mid-block: the consumer reads the slot of conv first-1's gradient
-                    for slab in slabs:
-                        self.vgg.absmax_update(slab, first - 1, grad=True)
+                # mid-block: the consumer reads the scale slot of conv first-1's gradient; below a pool the un-pooling kernel
+                # measures its own output
+                exchange(target, None if (first - 1) in POOL_AFTER else self.vgg.grad_absmax_ptr(first - 1),
+                         None if overlap is None else (lambda: overlap(-1)))
                 grad_in = target
         return out
 

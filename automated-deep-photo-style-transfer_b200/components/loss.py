@@ -78,6 +78,8 @@ class Loss:
         self._content_seeds = {}
         self._photo_grad = None
         self._seeds = None
+        self._seed_jobs = []
+        self._part = None
 
     def initialize_matting_laplacian(self, image):                            # loss.py:45-46
         """image: (H,W,3) float64 (as in style_transfer.py:315) or float32.  If every value is exactly representable
@@ -149,13 +151,26 @@ class Loss:
         """First half of compute_loss: everything that is local to this image (or image strip).  Returns the tensors that
         must be summed over the ranks of a spatially tiled run before finish(): the per-layer Gram partials and the
         float64 accumulator {content, (unused), photo}.  A single-device run just calls finish() afterwards."""
-        content_output, style_output = outputs['content'], outputs['style']
-        wts = self.loss_weights
+        self.begin_partials(image)
+        return self.end_partials(outputs)
+
+    # The pieces of forward_partials, so that a tiled run can enqueue each one as soon as its inputs exist (while halo columns
+    # of the next network segment are in flight): begin_partials, then partial_layers(outputs, upto) / partial_image() in any
+    # order, then end_partials (which runs whatever is still missing).
+    def begin_partials(self, image):
         self._acc.zero_()
-        seeds = {}
+        self._photo_grad = None
+        self._part = {"image": image, "seeds": {}, "G": {}, "image_done": False}
+
+    def partial_layers(self, outputs, upto):
+        """Content terms and Gram partials of every layer whose conv index is <= upto and that has not been evaluated yet."""
+        from .VGG19.model import LAYER_INDEX
+        P, wts = self._part, self.loss_weights
         n_args = 2.0                                                          # len(args) in iter_on_layers, loss.py:85
         for name, target in self.content_target.items():                     # loss.py:59, :90-92
-            out = content_output[name]
+            if name in P["seeds"] or LAYER_INDEX.get(name, 0) > upto:     # names outside VGG19: no ordering
+                continue
+            out = outputs['content'][name]
             seed = self._content_seeds.get(name)
             if seed is None or seed.shape != out.shape:
                 seed = self._content_seeds[name] = torch.empty_like(out)
@@ -165,16 +180,24 @@ class Loss:
                 _, h, w, C = out.shape
                 kernels.content_layer(target, out, 1.0 / n_args, wts['content'] / n_args, self._acc[0:1], seed,
                                       n_norm=float(h) * self.tile.global_cols(w) * C, own_cols=self.tile.own_cols(w))
-            seeds[name] = seed
-        partials = []
+            P["seeds"][name] = seed
         for name, target in self.style_target.items():                       # loss.py:62, :96-102
-            out = style_output[name]
+            if name in P["G"] or LAYER_INDEX.get(name, 0) > upto:
+                continue
+            out = outputs['style'][name]
             st = self._style_layer_state(name, target, out)
             _, h, w, C = out.shape
-            partials.append(kernels.gram_masked(out.reshape(h, w, C), st["own_masks"], st["K"], st["ws"],
-                                                patches=st["patches"], out=st["G"], f_absmax=kernels.act_absmax_slot(out),
-                                                masks_absmax=st["own_masks_absmax"]))
-        self._photo_grad = None
+            P["G"][name] = kernels.gram_masked(out.reshape(h, w, C), st["own_masks"], st["K"], st["ws"], patches=st["patches"],
+                                               out=st["G"], f_absmax=kernels.act_absmax_slot(out),
+                                               masks_absmax=st["own_masks_absmax"])
+
+    def partial_image(self):
+        """The terms that read the image only: photorealism regulariser and (extension) total variation."""
+        P, wts = self._part, self.loss_weights
+        if P["image_done"]:
+            return
+        P["image_done"] = True
+        image = P["image"]
         if wts['photo'] > 0:                                                  # loss.py:67-69, :157-161
             if self.matting_laplacian is None:
                 raise RuntimeError("regularization_weight > 0 but initialize_matting_laplacian() was not called")
@@ -189,29 +212,55 @@ class Loss:
             else:
                 kernels.tv_loss(image, 1.0, self.tv_weight, self._acc[3:4], self._photo_grad.reshape(image.shape),
                                 accumulate=True, own_cols=own)
-        self._pending = (outputs, seeds)
-        return partials + [self._acc]
 
-    def finish(self):
-        """Second half of compute_loss: style loss and its gradient seeds from the (global) Grams, weighted total."""
+    def end_partials(self, outputs):
+        self.partial_layers(outputs, 1 << 30)
+        self.partial_image()
+        P = self._part
+        self._pending = (outputs, P["seeds"])
+        return [P["G"][name] for name in self.style_target] + [self._acc]
+
+    def finish(self, lazy=False):
+        """Second half of compute_loss: style loss and its gradient seeds from the (global) Grams, weighted total.
+        lazy (tiled.py): nothing is evaluated here; every seed tensor is handed out and filled by seed_layers(), the loss
+        dictionary comes from finalize() once all of them have run."""
+        from .VGG19.model import LAYER_INDEX
         outputs, seeds = self._pending
-        style_output = outputs['style']
-        wts = self.loss_weights
-        n_args = 2.0
         self._acc[1:2].zero_()       # a cross-rank sum of the accumulator must not multiply the (global) style term
-        for name, target in self.style_target.items():                       # loss.py:104-137
-            out = style_output[name]
+        self._seed_jobs = []
+        for name in self.style_target:                                        # loss.py:104-137
+            shared = name in seeds                                            # a layer can be both content and style
+            dF = seeds[name] if shared else self._layer_cache[name]["seed"]
+            self._seed_jobs.append((LAYER_INDEX.get(name, 0), name, dF, shared))
+            seeds[name] = dF
+        self._seed_jobs.sort()                                                # seed_layers() pops the deepest layer first
+        self._seeds = seeds
+        if lazy:
+            return None
+        self.seed_layers(0)
+        return self.finalize()
+
+    def seed_layers(self, down_to, at_most=None):
+        """Evaluate the style term and gradient seed of the pending layers with conv index >= down_to, deepest first (at_most:
+        stop after that many)."""
+        outputs, _ = self._pending
+        wts, n_args, done = self.loss_weights, 2.0, 0
+        while self._seed_jobs and self._seed_jobs[-1][0] >= down_to and (at_most is None or done < at_most):
+            _, name, dF, shared = self._seed_jobs.pop()
+            out = outputs['style'][name]
             st = self._layer_cache[name]
             _, h, w, C = out.shape
-            shared = name in seeds                                            # a layer can be both content and style
-            dF = seeds[name] if shared else st["seed"]
             kernels.style_layer_backward(out.reshape(h, w, C), st["masks"], st["K"], st["G"], st["A"], 1.0 / n_args,
                                          wts['style'] / n_args, self._acc[1:2], dF.reshape(h * w, C), accumulate=shared,
                                          workspace=st["ws"], hw_norm=st["hw_norm"], f_absmax=kernels.act_absmax_slot(out),
                                          tiles=st["tiles"])
-            seeds[name] = dF
+            done += 1
+
+    def finalize(self):
+        if self._seed_jobs:
+            raise RuntimeError("finalize() before every style layer was evaluated")
+        wts = self.loss_weights
         kernels.loss_finalize(self._acc, wts['content'], wts['style'], wts['photo'], self._out, w_tv=self.tv_weight)   # loss.py:72
-        self._seeds = seeds
         loss_dict = {self.loss_names['content']: self._out[0], self.loss_names['style']: self._out[1],
                      self.loss_names['nima']: self._out[2]}
         if wts['photo'] > 0:

@@ -22,12 +22,14 @@ over its OWN pixels; 19.5 MB at K = 8) plus the 4-entry float64 loss accumulator
 Strip boundaries must be multiples of 16 px so that the pooling grids and the bilinear mask resizing of every layer align
 with the global image (restricting a resized mask to the own columns is then exact).
 """
+import ctypes
 import threading
+import time
 
 import torch
 
-from . import kernels
-from .components.VGG19.model import StyleContentModel
+from . import _lib, kernels
+from .components.VGG19.model import POOL_AFTER, SEGMENTS, StyleContentModel, VGG19Handle
 from .components.loss import Loss
 from .style_transfer import Adam, CONTENT_LAYERS, STYLE_LAYERS
 
@@ -213,12 +215,116 @@ class ThreadComm:
         return recv
 
 
+def exchange_plan(H, local_w, halo, last_layer):
+    """(rows, halo columns, channels) of the tensors whose halos are exchanged in one step, in order: the tensors that leave
+    the network segments on the way up, the gradients w.r.t. the same tensors on the way down, the image."""
+    up = []
+    for first, last in SEGMENTS:
+        if last >= last_layer:
+            break
+        if last in POOL_AFTER:
+            h, w, c = VGG19Handle.pool_shape(POOL_AFTER.index(last), H, local_w)
+        else:
+            h, w, c = VGG19Handle.conv_shape(last, H, local_w)
+        up.append((h, halo // (local_w // w), c))
+    return up + up[::-1] + [(H, halo, 3)]
+
+
+class PeerHalo:
+    """Halo exchange through mailboxes in peer memory (csrc/halo_peer.cu): the sender's kernel stores its boundary columns
+    straight into the neighbour's mailbox over NVLink and releases a sequence number, the receiver's kernel waits for it and
+    copies the slab into its halo columns (folding max|slab| into the tensor's scale word).  Two launches per exchange, no
+    host involvement, capturable in a CUDA graph."""
+
+    def __init__(self, side_bytes, rank, world, device=None):
+        _lib.require_cuda()
+        self.rank, self.world = rank, world
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        self.side_bytes = (int(side_bytes) + 15) // 16 * 16
+        self.sync = None                     # ranks of one process on one stream: called between the pushes and the pulls
+        self._slot, self._off = 0, 0
+        self.bytes = {"halo": 0, "exchanges": 0}
+        h = ctypes.c_void_p()
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.lib().adpst_halo_create(self.side_bytes, ctypes.byref(h)))
+        self._h = h
+
+    def __del__(self):
+        h, self._h = getattr(self, "_h", None), None
+        if h:
+            try:
+                _lib.lib().adpst_halo_destroy(h)
+            except Exception:
+                pass
+
+    def connect_processes(self):
+        """Collective over the default process group (one process per GPU of one node): map the neighbours' mailboxes
+        through CUDA IPC."""
+        import torch.distributed as dist
+        L = _lib.lib()
+        buf = ctypes.create_string_buffer(L.adpst_halo_ipc_handle_bytes())
+        _lib.check(L.adpst_halo_export(self._h, buf))
+        mine = (self.rank, bytes(buf.raw), self.side_bytes)
+        everyone = [None] * self.world
+        dist.all_gather_object(everyone, mine)
+        table = {r: (hb, sb) for r, hb, sb in everyone}
+        with torch.cuda.device(self.device):
+            for side, peer in ((0, self.rank - 1), (1, self.rank + 1)):
+                if 0 <= peer < self.world:
+                    hb, sb = table[peer]
+                    _lib.check(L.adpst_halo_connect_ipc(self._h, side, ctypes.c_char_p(hb), sb))
+        dist.barrier()
+
+    @staticmethod
+    def connect_local(halos, sync=None):
+        """Ranks that live in one process: neighbours use each other's mailbox pointers directly."""
+        L = _lib.lib()
+        for r, h in enumerate(halos):
+            with torch.cuda.device(h.device):
+                if r > 0:
+                    _lib.check(L.adpst_halo_connect_local(h._h, 0, halos[r - 1]._h))
+                if r + 1 < len(halos):
+                    _lib.check(L.adpst_halo_connect_local(h._h, 1, halos[r + 1]._h))
+            h.sync = sync
+
+    def begin_step(self):
+        self._slot, self._off = 0, 0
+        self.bytes = {"halo": 0, "exchanges": 0}
+
+    def exchange(self, tensor, lo, hi, hl, slot_ptr=None, overlap=None):
+        """tensor (1, rows, width, C) float32, own columns [lo, hi): see the class comment.  slot_ptr: device address of the
+        tensor's scale word or None.  overlap: callable that enqueues independent work between the push and the pull, so that
+        the slabs travel (and a slower neighbour catches up) while this GPU keeps computing."""
+        if tensor.dim() != 4 or tensor.shape[0] != 1 or tensor.dtype != torch.float32 or not tensor.is_contiguous():
+            raise TypeError("expected a contiguous float32 tensor of shape (1, rows, width, C)")
+        rows, width, C = int(tensor.shape[1]), int(tensor.shape[2]), int(tensor.shape[3])
+        L = _lib.lib()
+        with torch.cuda.device(self.device):
+            _lib.check(L.adpst_halo_push(self._h, self._slot, self._off, _lib.ptr(tensor), rows, width, C, hl, lo, hi,
+                                         _lib.stream_ptr()))
+            if self.sync is not None:
+                self.sync()
+            if overlap is not None:
+                overlap()
+            _lib.check(L.adpst_halo_pull(self._h, self._slot, self._off, _lib.ptr(tensor), rows, width, C, hl, lo, hi,
+                                         ctypes.c_void_p(slot_ptr or 0), _lib.stream_ptr()))
+            if self.sync is not None:
+                self.sync()
+        sides = int(self.rank > 0 and lo > 0) + int(self.rank < self.world - 1 and hi < width)
+        self.bytes["halo"] += sides * rows * hl * C * 4
+        self.bytes["exchanges"] += 1
+        self._slot += 1
+        self._off += rows * hl * C * 4
+
+
 class TiledStyleTransfer:
     """Rank-local state of a spatially tiled optimisation.  `comm` provides exchange(tensor, lo, hi, hl) and
-    reduce_sum(list of tensors); the default is NCCL through torch.distributed."""
+    reduce_sum(list of tensors); the default is NCCL through torch.distributed.  halo: None -- the halos travel through
+    `comm` as well; 'peer' -- through a PeerHalo mailbox connected over CUDA IPC (collective); or a connected PeerHalo.  The
+    set-up passes (content / style targets) always use `comm`."""
 
     def __init__(self, content, style, args, content_masks, style_masks, vgg_weights, rank, world, comm=None, matting="v2",
-                 device=None):
+                 device=None, halo=None):
         dev = torch.device(device if device is not None else "cuda")
         self.rank, self.world = rank, world
         self.comm = comm if comm is not None else NcclComm(rank, world)
@@ -242,13 +348,40 @@ class TiledStyleTransfer:
         self._grad = torch.empty_like(self.image)
         self._targets_reduced = False
         self._flat = None                               # flat float32 buffer behind the per-layer Gram partials
+        li = self.extractor.last_index
+        self._last_exchange_layer = max(last for _, last in SEGMENTS if last < li)     # the forward pass's last exchange
+        self.halo = None
+        if halo is not None and world > 1:
+            if isinstance(halo, str):
+                if halo != "peer":
+                    raise ValueError("halo must be None, 'peer' or a PeerHalo")
+                halo = PeerHalo(self.mailbox_bytes(), rank, world, dev)
+                halo.connect_processes()
+            if halo.side_bytes < self.mailbox_bytes():
+                raise ValueError("the mailbox holds %d bytes per side, one step needs %d" % (halo.side_bytes, self.mailbox_bytes()))
+            self.halo = halo
 
-    def _exchanger(self, tile):
-        """exchange(tensor) for the image, feature maps and gradients of this strip (the level follows from the width)."""
-        def ex(tensor):
+    def mailbox_bytes(self):
+        """Bytes per mailbox side that the exchanges of one step occupy."""
+        plan = exchange_plan(int(self.image.shape[1]), self.tile.local_w, self.tile.halo, self.extractor.last_index)
+        return sum(r * h * c * 4 for r, h, c in plan)
+
+    def _exchanger(self, tile, peer=False):
+        """exchange(tensor, slot) for the image, feature maps and gradients of this strip (the level follows from the width):
+        halo columns replaced by the neighbours' own columns, the scale word at device address `slot` raised accordingly."""
+        vgg = self.extractor.vgg
+
+        def ex(tensor, slot=None, overlap=None):
             w_l = int(tensor.shape[-2])
             lo, hi = tile.own_cols(w_l)
-            return self.comm.exchange(tensor, lo, hi, tile.halo_cols(w_l))
+            if peer and self.halo is not None:
+                self.halo.exchange(tensor, lo, hi, tile.halo_cols(w_l), slot, overlap)
+                return
+            if overlap is not None:
+                overlap()
+            for slab in self.comm.exchange(tensor, lo, hi, tile.halo_cols(w_l)):
+                if slot:
+                    vgg.absmax_update(slab, slot)
         return ex
 
     def _flatten_partials(self):
@@ -265,13 +398,19 @@ class TiledStyleTransfer:
     def describe_exchange(self):
         if self.world == 1:
             return "no exchange (single strip)"
-        return ("point-to-point halo exchange between the six network segments (forward activations, backward gradients) and of "
-                "the image border after the update (%d px halo), one NCCL all-reduce of the flattened Gram partials (%.1f MB) + float64[4] "
-                "loss accumulator" % (HALO, 4e-6 * (self._flat.numel() if self._flat is not None else 0)))
+        how = ("two kernels per exchange over peer memory: stores into the neighbour's mailbox through NVLink + release flag, "
+               "then wait + copy into the halo columns" if self.halo is not None else "NCCL batched send/recv")
+        return ("halo exchange between the six network segments (forward activations, backward gradients) and of the image "
+                "border after the update (%d px halo; %s), one NCCL all-reduce of the flattened Gram partials (%.1f MB) + float64[4] "
+                "loss accumulator" % (HALO, how, 4e-6 * (self._flat.numel() if self._flat is not None else 0)))
 
     def exchange_bytes(self):
         """Bytes this rank handed to the communication layer in the latest step."""
-        return dict(self.comm.bytes)
+        b = dict(self.comm.bytes)
+        if self.halo is not None:
+            b["halo"] += self.halo.bytes["halo"]
+            b["exchanges"] += self.halo.bytes["exchanges"]
+        return b
 
     def time_breakdown(self, steps=5):
         """Device time of `steps` iterations split into communication (halo exchanges incl. packing / unpacking, the Gram
@@ -280,6 +419,8 @@ class TiledStyleTransfer:
         events = []
         comm = self.comm
         raw_exchange, raw_reduce = comm.exchange, comm.reduce_sum
+        halo = self.halo
+        raw_peer = None if halo is None else halo.exchange
 
         def timed(fn):
             def wrapper(*a, **k):
@@ -291,46 +432,117 @@ class TiledStyleTransfer:
                 return out
             return wrapper
 
+        hidden = []                                  # (start, end) of the work enqueued inside an exchange window
+
+        def timed_peer(tensor, lo, hi, hl, slot_ptr=None, overlap=None):
+            def inner():
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record()
+                overlap()
+                b.record()
+                hidden.append((a, b))
+            return raw_peer(tensor, lo, hi, hl, slot_ptr, None if overlap is None else inner)
+
         comm.exchange, comm.reduce_sum = timed(raw_exchange), timed(raw_reduce)
+        if halo is not None:
+            halo.exchange = timed(timed_peer)
         try:
             t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             torch.cuda.synchronize()
+            h0 = time.perf_counter()
             t0.record()
             for _ in range(steps):
                 self.step()
             t1.record()
+            host_ms = (time.perf_counter() - h0) * 1e3 / steps
             torch.cuda.synchronize()
         finally:
             comm.exchange, comm.reduce_sum = raw_exchange, raw_reduce
+            if halo is not None:
+                del halo.exchange                   # back to the class's method
         total = t0.elapsed_time(t1) / steps
-        comm_ms = sum(a.elapsed_time(b) for a, b in events) / steps
+        comm_ms = (sum(a.elapsed_time(b) for a, b in events) - sum(a.elapsed_time(b) for a, b in hidden)) / steps
         own = self.tile.own_hi - self.tile.own_lo
         return {"ms_per_step": total, "communication_ms": comm_ms, "compute_ms": total - comm_ms,
-                "redundant_column_factor": self.tile.local_w / own}
+                "host_enqueue_ms": host_ms, "redundant_column_factor": self.tile.local_w / own}
 
     def own_strip(self):
         lo, hi = self.tile.own_cols(self.tile.local_w)
         return self.image[0, :, lo:hi].contiguous()
 
+    def graphed_step(self):
+        """Capture one iteration -- kernels, the NCCL point-to-point exchanges and the all-reduce -- into a CUDA graph and
+        return replay() -> loss dict.  Collective: every rank captures, and every rank replays the same number of times.
+        At least one eager step() must have run (lazy state, NCCL communicators, persistent buffers).  The capture runs in
+        thread-local error mode: NCCL's watchdog thread may query its events while this thread captures."""
+        if self._flat is None or not self._targets_reduced:
+            raise RuntimeError("graphed_step() needs a preceding eager step()")
+        if not isinstance(self.comm, NcclComm) or isinstance(self.comm, GlooComm):
+            raise RuntimeError("graphed_step() needs the NCCL communication layer")
+        s = _capture_stream(self.image.device)
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s):
+            g.capture_begin(capture_error_mode="thread_local")
+            try:
+                out = self.step()
+            finally:
+                g.capture_end()
+        torch.cuda.current_stream().wait_stream(s)
+        self._graph = g                                 # keeps the graph's private pool (send / receive slabs) alive
+
+        def replay():
+            g.replay()
+            return out
+        return replay
+
     def step(self):
         """One iteration (every rank calls it; the calls to `comm` are collective)."""
         self.comm.begin_step()
-        ex = self._exchanger(self.tile)
-        outputs = self.extractor.forward_blocks(self.image, ex, reuse=True)
-        if self._flat is None:
-            self.loss.prepare(outputs)                  # per-layer state (idempotent), then one buffer behind all Gram partials
+        if self.halo is not None:
+            self.halo.begin_step()
+        ex = self._exchanger(self.tile, peer=True)
+        loss = self.loss
+        first_step = self._flat is None
+        # Loss terms are enqueued as soon as their inputs exist, inside the exchange windows of the forward pass (Gram
+        # partials and the content term of the layers below the exchanged tensor; the image-only terms in the last window).
+        # On the first step the per-layer state does not exist yet: everything runs after the forward pass.
+        loss.begin_partials(self.image)
+
+        def fwd_overlap(last, outputs):
+            loss.partial_layers(outputs, last)
+            if last >= self._last_exchange_layer:
+                loss.partial_image()
+        outputs = self.extractor.forward_blocks(self.image, ex, reuse=True, overlap=None if first_step else fwd_overlap)
+        if first_step:
+            loss.prepare(outputs)                       # per-layer state (idempotent), then one buffer behind all Gram partials
             self._flatten_partials()
         if not self._targets_reduced:                   # the style Grams computed at set-up are per-rank partials: sum once
-            self.comm.reduce_sum(self.loss.style_targets_partial())
+            self.comm.reduce_sum(loss.style_targets_partial())
             self._targets_reduced = True
-        parts = self.loss.forward_partials(self.image, outputs)
+        parts = loss.end_partials(outputs)
         self.comm.reduce_sum([self._flat, parts[-1]])   # every Gram partial lives in the flat buffer; + the float64 accumulator
-        loss_dict = self.loss.finish()
-        grad = self.loss.gradient(self.extractor, out=self._grad,
-                                  backward=lambda seeds, out: self.extractor.backward_blocks(seeds, ex, out=out))
+        # Style terms / gradient seeds are evaluated lazily on the way down: the seeds of a segment at the latest right before
+        # it runs, one more layer (the deepest pending one) inside every exchange window.
+        loss.finish(lazy=True)
+
+        def bwd_overlap(first):
+            if first >= 0:
+                loss.seed_layers(first)
+            else:
+                loss.seed_layers(0, at_most=1)
+        grad = loss.gradient(self.extractor, out=self._grad,
+                             backward=lambda seeds, out: self.extractor.backward_blocks(seeds, ex, out=out, overlap=bwd_overlap))
+        loss_dict = loss.finalize()
         self.optimizer.apply_gradients_and_clip(grad, self.image)      # only the own columns of the result are meaningful
         ex(self.image)                                                 # refresh the image halo from the owners
         return loss_dict
+
+
+def _capture_stream(device):
+    from .style_transfer import _side_stream
+    return _side_stream(device)
 
 
 def run_emulated(ranks, iters):
@@ -361,8 +573,10 @@ def run_emulated(ranks, iters):
     return history[0]
 
 
-def make_emulated(content, style, args, content_masks, style_masks, vgg_weights, world, matting="v2", device=None):
-    """`world` rank objects in this process.  Construction itself exchanges halos (the targets), so it runs in threads too."""
+def make_emulated(content, style, args, content_masks, style_masks, vgg_weights, world, matting="v2", device=None, halo=None):
+    """`world` rank objects in this process.  Construction itself exchanges halos (the targets), so it runs in threads too.
+    halo='peer': the steps exchange their halos through PeerHalo mailboxes (the kernels of csrc/halo_peer.cu, with the
+    neighbours' mailboxes addressed directly) instead of the in-process stand-in."""
     shared = ThreadComm.Shared(world)
     ranks, errors = [None] * world, []
 
@@ -381,4 +595,12 @@ def make_emulated(content, style, args, content_masks, style_masks, vgg_weights,
         t.join()
     if errors:
         raise errors[0]
+    if halo == "peer" and world > 1:
+        need = max(r.mailbox_bytes() for r in ranks)
+        boxes = [PeerHalo(need, r, world, ranks[r].image.device) for r in range(world)]
+        PeerHalo.connect_local(boxes, sync=shared.barrier.wait)
+        for r, b in zip(ranks, boxes):
+            r.halo = b
+    elif halo is not None and world > 1:
+        raise ValueError("halo must be None or 'peer'")
     return ranks

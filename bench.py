@@ -584,7 +584,7 @@ def pairs_record(D, ext_cache, n_pairs, size, K, iters, tv_weight):
 # ----------------------------------------------------------------------------------------------------------------
 # BASELINE configs[3]: one large image, column strips over the ranks (tiled.py)
 # ----------------------------------------------------------------------------------------------------------------
-def tiled_record(D, H, W, K, steps, warmup, tv_weight, check_parity=True):
+def tiled_record(D, H, W, K, steps, warmup, tv_weight, check_parity=True, graph=True, halo="peer"):
     import torch
     synth, tiled, sem = mod("synth"), mod("tiled"), mod("components.semantic_merge")
     hp = hyper(tv_weight)
@@ -592,26 +592,33 @@ def tiled_record(D, H, W, K, steps, warmup, tv_weight, check_parity=True):
     cm = sem.mask_for_tf(sem.extract_segmentation_masks(synth.label_image(H, W, K, 9, cell=64)))
     sm = sem.mask_for_tf(sem.extract_segmentation_masks(synth.label_image(H, W, K, 10, cell=64)))
     weights = synth.vgg_weights()
-    job = tiled.TiledStyleTransfer(content, style, hp, cm, sm, weights, D.rank, D.world)
+    job = tiled.TiledStyleTransfer(content, style, hp, cm, sm, weights, D.rank, D.world, halo=None if halo == "nccl" else halo)
     first = {k: float(v) for k, v in job.step().items()}           # iteration 0: evaluated at x = content on every rank
-    for _ in range(max(warmup, 3) - 1):
+    for _ in range(2):
         d = job.step()
+    breakdown = job.time_breakdown(3)                                # collective: every rank runs the same three eager steps
+    breakdown = {k: D.max_ms(v) for k, v in breakdown.items()}
+    # the timed steps replay ONE CUDA graph per rank that holds the kernels, the NCCL send/recv pairs and the all-reduce
+    run = job.graphed_step() if (graph and D.world > 1) else job.step
+    for _ in range(max(warmup, 3)):
+        d = run()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     D.barrier(); e0.record()
     for _ in range(steps):
-        d = job.step()
+        d = run()
     e1.record(); D.barrier()
     ms = D.max_ms(e0.elapsed_time(e1))
     t = job.tile
-    breakdown = job.time_breakdown(3)                                # collective: every rank runs the same three steps
-    breakdown = {k: D.max_ms(v) for k, v in breakdown.items()}
     rec = {"config": "configs[3]: one %dx%d image, %d classes, column strips of %d px + %d px halo per interior side (local width "
                      "%d) over %d GPU(s); per step: %s" % (W, H, K, W // D.world, tiled.HALO if D.world > 1 else 0, t.local_w,
                                                            D.world, job.describe_exchange()),
            "scaling": "strong", "n_gpus": D.world, "value": steps / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms / steps,
-           "steps": steps, "bytes_exchanged_per_step": job.exchange_bytes(), "final_total_loss": float(d["Total loss"]),
-           "breakdown_max_over_ranks": dict(breakdown, what="device ms per step: halo exchanges (packing, NCCL point-to-point, "
-                                                               "unpacking) + Gram all-reduce vs everything else; "
+           "steps": steps, "launch": ("one CUDA graph per rank and step (kernels + NCCL send/recv + all-reduce)"
+                                      if (graph and D.world > 1) else "eager launches"),
+           "bytes_exchanged_per_step": job.exchange_bytes(), "final_total_loss": float(d["Total loss"]),
+           "breakdown_max_over_ranks": dict(breakdown, what="EAGER steps, device ms per step: halo exchanges (packing, NCCL "
+                                                               "point-to-point, unpacking) + Gram all-reduce vs everything else; "
+                                                               "host_enqueue_ms = host time to enqueue one eager step; "
                                                                "redundant_column_factor = (own + halo columns) / own columns"),
            "first_iteration_losses": first}
     if check_parity and D.world > 1:
@@ -729,7 +736,7 @@ def run_ours(args):
         del loss, opt
         torch.cuda.empty_cache()
         D.barrier()
-        rec = tiled_record(D, 2160, 3840, K, max(3, min(args.steps, 10)), 3, args.tv_weight)
+        rec = tiled_record(D, 2160, 3840, K, max(3, min(args.steps, 10)), 3, args.tv_weight, graph=not args.no_tiled_graph, halo=args.halo)
         if rank == 0:
             extras["tiled_4k"] = rec
             out.update(extras)
@@ -763,7 +770,8 @@ def run_pairs(args):
 
 def run_tiled(args):
     D = Dist()
-    rec = tiled_record(D, args.tiled_h, args.tiled_w, args.classes, args.steps, args.warmup, args.tv_weight)
+    rec = tiled_record(D, args.tiled_h, args.tiled_w, args.classes, args.steps, args.warmup, args.tv_weight,
+                       graph=not args.no_tiled_graph, halo=args.halo)
     if D.rank == 0:
         rec.update({"metric": "adam_iters_per_sec_%dx%d_spatially_tiled" % (args.tiled_w, args.tiled_h), "warmup": max(args.warmup, 3),
                     "higher_is_better": True, "vs_baseline": None, "dtype": DTYPE, "data": "synthetic"})
@@ -832,6 +840,10 @@ def main():
     ap.add_argument("--pair-size", dest="pair_size", type=int, default=512)
     ap.add_argument("--pair-classes", dest="pair_classes", type=int, default=4)
     ap.add_argument("--tiled", action="store_true", help="configs[3] only: one large image tiled spatially over the GPUs")
+    ap.add_argument("--no-tiled-graph", dest="no_tiled_graph", action="store_true",
+                    help="time eager tiled steps instead of one captured CUDA graph per rank")
+    ap.add_argument("--halo", choices=("peer", "nccl"), default="peer",
+                    help="tiled runs: halo columns through peer-memory mailboxes (our kernels) or NCCL send/recv")
     ap.add_argument("--tiled-h", dest="tiled_h", type=int, default=2160)
     ap.add_argument("--tiled-w", dest="tiled_w", type=int, default=3840)
     ap.add_argument("--lx-sweep", dest="lx_sweep", action="store_true", help="configs[4] only")

@@ -166,6 +166,29 @@ int adpst_vgg_backward_range(adpst_vgg* h, int H, int W, const float* const* act
 const uint32_t* adpst_vgg_grad_absmax(const adpst_vgg* h, int i);
 
 /* ------------------------------------------------------------------------------------------------
+ * Halo exchange of column strips over peer memory (spatially tiled runs; the reference is single-device, SURVEY.md 8e:
+ * this is the exchange the strip decomposition of style_transfer.py:331-344 needs between two network segments).
+ * Every rank owns a mailbox with room for `side_bytes` of slabs from each of its two neighbours; neighbours store into it
+ * over NVLink (CUDA IPC mapping between processes, direct pointers between ranks of one process).
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct adpst_halo adpst_halo;
+int adpst_halo_create(size_t side_bytes, adpst_halo** out);        /* on the current device; side_bytes % 16 == 0 */
+void adpst_halo_destroy(adpst_halo* h);
+int adpst_halo_ipc_handle_bytes(void);                              /* size of the opaque handle adpst_halo_export writes */
+int adpst_halo_export(const adpst_halo* h, void* handle_out);
+/* side 0 = left neighbour, 1 = right neighbour */
+int adpst_halo_connect_ipc(adpst_halo* h, int side, const void* handle, size_t peer_side_bytes);
+int adpst_halo_connect_local(adpst_halo* h, int side, adpst_halo* neighbour);
+/* x_dev: (rows, width, C) float32; own columns [own_lo, own_hi).  push: the hl own columns next to each interior boundary go
+ * into the neighbours' mailboxes at `offset` and are published under `slot`.  pull: waits for both neighbours' slabs of `slot`,
+ * writes them into the hl halo columns on either side and raises *absmax_slot_dev (float bits, may be NULL) to max|slab|.
+ * Every rank must issue the same sequence of (slot, offset) pairs, at least two exchanges per step. */
+int adpst_halo_push(adpst_halo* h, int slot, size_t offset, const float* x_dev, int rows, int width, int C, int hl,
+                    int own_lo, int own_hi, adpst_stream_t stream);
+int adpst_halo_pull(adpst_halo* h, int slot, size_t offset, float* x_dev, int rows, int width, int C, int hl, int own_lo,
+                    int own_hi, uint32_t* absmax_slot_dev, adpst_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
  * Loss terms: components/loss.py
  * ---------------------------------------------------------------------------------------------- */
 /* tf.image.resize bilinear, half-pixel centres, no antialias (loss.py:112-113); single channel. */
