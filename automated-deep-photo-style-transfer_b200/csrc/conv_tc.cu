@@ -146,8 +146,12 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                   const float* __restrict__ seed, const float* __restrict__ mask_src, int H, int W, int Cin, int Cout,
                   int tiles_w, int num_tiles, const float* __restrict__ cls_masks, const uint32_t* __restrict__ tile_active,
                   const uint32_t* __restrict__ a_absmax, const uint32_t* __restrict__ b_absmax,
-                  const uint32_t* __restrict__ w_absmax, uint32_t* __restrict__ y_absmax, float* __restrict__ pool_out) {
+                  const uint32_t* __restrict__ w_absmax, uint32_t* __restrict__ y_absmax, float* __restrict__ pool_out,
+                  int tw_log2_arg) {
     using Cfg = TcCfg<BN, MODE>;
+    // pixel tile: 8 rows x 16 columns (tw_log2 = 4) or 16 rows x 8 columns (tw_log2 = 3, narrow maps: the column strips of a
+    // spatially tiled run are 68 or 34 pixels wide at 1/8 and 1/16 resolution); 128 pixels and a 180-pixel halo tile either way
+    const int tw_log2 = (MODE == MODE_STYLE) ? 4 : tw_log2_arg;             // (the per-tile class sets are made for 8 x 16)
     constexpr int AST = Cfg::A_STAGES, BST = Cfg::B_STAGES;
     constexpr int SB = Cfg::SMALL_BUFS;         // small-term accumulators in tensor memory
     constexpr int NSLOT = Cfg::A_SLOTS;         // A operand slots in tensor memory (ring between the transform warps and the MMAs)
@@ -232,7 +236,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             auto issue_a = [&]() {
                 if (wa >= total) return;
                 const int tile = wa / nblk;
-                const int y0 = (tile / tiles_w) * TC_TH, x0 = (tile % tiles_w) * TC_TW;
+                const int y0 = (tile / tiles_w) << (7 - tw_log2), x0 = (tile % tiles_w) << tw_log2;
                 // 10 x 18 pixels x 64 channels, zero-filled outside the image (= SAME padding)
                 tc::mbar_wait(&a_empty[sa], (ra & 1) ^ 1);
                 uint8_t* sta = smem + sa * TC_A_BYTES;
@@ -365,8 +369,9 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             const uint32_t active = item_active(tile);
             const int ntaps = __popc(active);
             if (ntaps == 0) continue;
-            const int ty = m / TC_TW, tx = m % TC_TW;
-            const int gy = (tile / tiles_w) * TC_TH + ty, gx = (tile % tiles_w) * TC_TW + tx;
+            const int halo_w = (1 << tw_log2) + 2;
+            const int ty = m >> tw_log2, tx = m & ((1 << tw_log2) - 1);
+            const int gy = ((tile / tiles_w) << (7 - tw_log2)) + ty, gx = ((tile % tiles_w) << tw_log2) + tx;
             // style mode: this pixel's weight m_k^2 for the first classes of the tile, requested once per work item (they do
             // not depend on the K chunk) instead of one exposed global load per stage
             float wq[TC_STYLE_PRELOAD];
@@ -426,7 +431,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                     if (PRESPLIT) {
                         const uint32_t dst = tmem_a + uint32_t(git % NSLOT) * 64 + lane_base;
                         const int kh = slot / 3, kw = slot - kh * 3;
-                        const int r = (ty + kh) * TC_HW + tx + kw;             // this thread's pixel, shifted by the tap, in the halo tile
+                        const int r = (ty + kh) * halo_w + tx + kw;             // this thread's pixel, shifted by the tap, in the halo tile
                         const uint32_t row0 = smem_base + uint32_t(sa * TC_A_BYTES + r * 128);
                         const uint32_t row1 = row0 + TC_A_BOX_BYTES;
                         uint32_t hi[2][16], lo[2][16];
@@ -466,7 +471,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                     } else {
                         kh = slot / 3; kw = slot - kh * 3;
                     }
-                    const int r = (ty + kh) * TC_HW + tx + kw;             // this thread's pixel, shifted by the tap, in the halo tile
+                    const int r = (ty + kh) * halo_w + tx + kw;             // this thread's pixel, shifted by the tap, in the halo tile
                     const uint32_t dst = tmem_a + uint32_t(git % NSLOT) * 64 + lane_base;
                     uint32_t hi[2][16], lo[2][16];
 #pragma unroll
@@ -550,7 +555,8 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                 tc::mbar_arrive(&small_empty[sj % SB]);
                 ++sj;
             }
-            const int gy = (tile / tiles_w) * TC_TH + m / TC_TW, gx = (tile % tiles_w) * TC_TW + m % TC_TW;
+            const int tile_w = 1 << tw_log2;
+            const int gy = ((tile / tiles_w) << (7 - tw_log2)) + (m >> tw_log2), gx = ((tile % tiles_w) << tw_log2) + (m & (tile_w - 1));
             const bool inb = gy < H && gx < W;
             if (inb || (MODE == MODE_FWD && pool_out != nullptr)) {        // (pooling shuffles need the whole warp)
                 const size_t rowoff = (size_t(gy) * W + gx) * size_t(Cout) + n0;
@@ -576,9 +582,10 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                         }
                         if (pool_out != nullptr) {
                             // fused 2x2/2 VALID max-pool (model.py / Keras MaxPooling2D): the window partners of pixel
-                            // (ty, tx) are lanes ^1 (tx + 1) and ^16 (ty + 1) of this warp -- a warp holds tile rows 2q, 2q+1.
-                            // Windows that exist lie completely inside the image, so out-of-image lanes never contribute.
-                            const bool writer = (lane & 17) == 0 && gy + 1 < H && gx + 1 < W;
+                            // (ty, tx) are lanes ^1 (tx + 1) and ^tile_w (ty + 1) of this warp -- a warp holds tile rows 2q, 2q+1
+                            // (4q .. 4q+3 of a 16 x 8 tile).  Windows that exist lie completely inside the image, so
+                            // out-of-image lanes never contribute.
+                            const bool writer = (lane & (tile_w | 1)) == 0 && gy + 1 < H && gx + 1 < W;
                             float* prow = pool_out + (size_t(gy >> 1) * (W >> 1) + (gx >> 1)) * size_t(Cout) + n0 + c0;
 #pragma unroll
                             for (int j = 0; j < 32; j += 4) {
@@ -586,7 +593,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 #pragma unroll
                                 for (int e = 0; e < 4; ++e) {
                                     float v = fmaxf(r[j + e], __shfl_xor_sync(0xffffffffu, r[j + e], 1));
-                                    pv[e] = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, 16));
+                                    pv[e] = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, tile_w));
                                 }
                                 if (writer) *reinterpret_cast<float4*>(prow + j) = make_float4(pv[0], pv[1], pv[2], pv[3]);
                             }
@@ -739,23 +746,32 @@ template <int BN, int MODE>
 static int launch_tc(const CUtensorMap& tmA, const CUtensorMap& tmBhi, const CUtensorMap& tmBlo, const float* bias, float* Y,
                      const float* seed, const float* mask, int H, int W, int Cin, int Cout, const uint32_t* a_absmax,
                      const uint32_t* b_absmax, uint32_t* y_absmax, cudaStream_t st, const float* cls_masks = nullptr,
-                     const uint32_t* tile_active = nullptr, const uint32_t* w_absmax = nullptr, float* pool_out = nullptr) {
+                     const uint32_t* tile_active = nullptr, const uint32_t* w_absmax = nullptr, float* pool_out = nullptr,
+                     int tw_log2 = 4) {
     using Cfg = TcCfg<BN, MODE>;
     auto kern = conv3x3_tc_kernel<BN, MODE>;
     ADPST_ONCE_PER_DEVICE(ADPST_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES)));
-    const int tw = (W + TC_TW - 1) / TC_TW, th = (H + TC_TH - 1) / TC_TH;
+    const int tile_w = 1 << tw_log2, tile_h = TC_BM >> tw_log2;
+    const int tw = (W + tile_w - 1) / tile_w, th = (H + tile_h - 1) / tile_h;
     const int total = tw * th * (Cout / BN);
     const int grid = total < num_sms() ? total : num_sms();
     kern<<<grid, TC_THREADS, Cfg::SMEM_BYTES, st>>>(tmA, tmBhi, tmBlo, bias, Y, seed, mask, H, W, Cin, Cout, tw, tw * th,
-                                                    cls_masks, tile_active, a_absmax, b_absmax, w_absmax, y_absmax, pool_out);
+                                                    cls_masks, tile_active, a_absmax, b_absmax, w_absmax, y_absmax, pool_out,
+                                                    tw_log2);
     ADPST_LAUNCH_CHECK();
     return ADPST_OK;
 }
 
-static int make_act_map(CUtensorMap* tm, const float* X, int H, int W, int C) {
+// 8 x 16 pixel tiles, or 16 x 8 where that covers the map with fewer of them (narrow maps)
+static int pick_tile_shape(int H, int W) {
+    const long wide = long((W + 15) / 16) * ((H + 7) / 8), tall = long((W + 7) / 8) * ((H + 15) / 16);
+    return tall < wide ? 3 : 4;
+}
+
+static int make_act_map(CUtensorMap* tm, const float* X, int H, int W, int C, int tw_log2 = 4) {
     const uint64_t dims[4] = {uint64_t(C), uint64_t(W), uint64_t(H), 1};
     const uint64_t strides[3] = {uint64_t(C) * 4, uint64_t(W) * C * 4, uint64_t(H) * W * C * 4};
-    const uint32_t box[4] = {32u, uint32_t(TC_HW), uint32_t(TC_HH), 1};      // the pixel tile plus its 1-pixel halo
+    const uint32_t box[4] = {32u, uint32_t((1 << tw_log2) + 2), uint32_t((TC_BM >> tw_log2) + 2), 1};   // pixel tile + 1-pixel halo
     return tc::make_tensor_map_f32(tm, X, 4, dims, strides, box);
 }
 
@@ -766,7 +782,8 @@ static int make_act_map(CUtensorMap* tm, const float* X, int H, int W, int C) {
 int launch_conv_tc(adpst_vgg* h, int i, int gradient, const float* X, float* Y, const float* seed, const float* mask, int H,
                    int W, int Cin, int Cout, const uint32_t* x_absmax, uint32_t* y_absmax, float* pool_out, cudaStream_t st) {
     CUtensorMap tmA;
-    int rc = make_act_map(&tmA, X, H, W, Cin);
+    const int shape = pick_tile_shape(H, W);
+    int rc = make_act_map(&tmA, X, H, W, Cin, shape);
     if (rc != ADPST_OK) return rc;
     const CUtensorMap& bh = h->tm_hi[gradient][i];
     const CUtensorMap& bl = h->tm_lo[gradient][i];
@@ -776,13 +793,15 @@ int launch_conv_tc(adpst_vgg* h, int i, int gradient, const float* X, float* Y, 
     if (!gradient) {
         if (BN == 128)
             return launch_tc<128, MODE_FWD>(tmA, bh, bl, bias, Y, seed, mask, H, W, Cin, Cout, x_absmax, wslot, y_absmax, st,
-                                            nullptr, nullptr, nullptr, pool_out);
+                                            nullptr, nullptr, nullptr, pool_out, shape);
         return launch_tc<64, MODE_FWD>(tmA, bh, bl, bias, Y, seed, mask, H, W, Cin, Cout, x_absmax, wslot, y_absmax, st, nullptr,
-                                       nullptr, nullptr, pool_out);
+                                       nullptr, nullptr, pool_out, shape);
     }
     if (BN == 128)
-        return launch_tc<128, MODE_BWD>(tmA, bh, bl, bias, Y, seed, mask, H, W, Cin, Cout, x_absmax, wslot, y_absmax, st);
-    return launch_tc<64, MODE_BWD>(tmA, bh, bl, bias, Y, seed, mask, H, W, Cin, Cout, x_absmax, wslot, y_absmax, st);
+        return launch_tc<128, MODE_BWD>(tmA, bh, bl, bias, Y, seed, mask, H, W, Cin, Cout, x_absmax, wslot, y_absmax, st, nullptr,
+                                        nullptr, nullptr, nullptr, shape);
+    return launch_tc<64, MODE_BWD>(tmA, bh, bl, bias, Y, seed, mask, H, W, Cin, Cout, x_absmax, wslot, y_absmax, st, nullptr,
+                                   nullptr, nullptr, nullptr, shape);
 }
 
 // ---------------------------------------------------------------------------------------------------------------

@@ -30,7 +30,7 @@ def _run(ext, fn_name, i, x, h, w, cout, path):
 
 
 @pytest.mark.parametrize("i", [1, 2, 3, 4, 5, 8, 9, 12])
-@pytest.mark.parametrize("h,w", [(32, 32), (19, 45), (8, 16), (5, 3)])
+@pytest.mark.parametrize("h,w", [(32, 32), (19, 45), (8, 16), (5, 3), (45, 19), (135, 34)])    # the last two: 16x8 pixel tiles
 def test_forward_matches_fp32_kernel(i, h, w, ext, synth):
     cin, cout = synth.CONV_LAYERS[i][1], synth.CONV_LAYERS[i][2]
     g = torch.Generator(device="cuda").manual_seed(100 * i + h)
@@ -43,7 +43,7 @@ def test_forward_matches_fp32_kernel(i, h, w, ext, synth):
 
 
 @pytest.mark.parametrize("i", [1, 2, 4, 8, 12])
-@pytest.mark.parametrize("h,w", [(32, 32), (19, 45)])
+@pytest.mark.parametrize("h,w", [(32, 32), (19, 45), (45, 19), (135, 34)])
 def test_dgrad_matches_fp32_kernel(i, h, w, ext, synth):
     cin, cout = synth.CONV_LAYERS[i][1], synth.CONV_LAYERS[i][2]
     g = torch.Generator(device="cuda").manual_seed(7 * i + w)

@@ -58,7 +58,7 @@ def weights(synth):
     return synth.vgg_weights(seed=5)
 
 
-@pytest.mark.parametrize("H,W", [(64, 64), (37, 50), (16, 16), (96, 138)])
+@pytest.mark.parametrize("H,W", [(64, 64), (37, 50), (16, 16), (96, 138), (144, 72)])     # 144x72: 16x8 pixel tiles (narrow maps)
 def test_vgg_forward_all_taps(H, W, weights, synth):
     vgg = _m("components.VGG19.model")
     names = [n for n, _, _ in synth.CONV_LAYERS]
@@ -72,7 +72,7 @@ def test_vgg_forward_all_taps(H, W, weights, synth):
         assert _rel(got[n].cpu().numpy(), ref[n].numpy()) < TOL, n
 
 
-@pytest.mark.parametrize("H,W", [(32, 32), (37, 50)])
+@pytest.mark.parametrize("H,W", [(32, 32), (37, 50), (90, 40)])
 def test_vgg_backward_matches_autograd(H, W, weights, synth):
     """d(sum_i <seed_i, layer_i>)/d(image) with random seeds on the six tapped layers."""
     vgg = _m("components.VGG19.model")

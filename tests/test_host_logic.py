@@ -153,6 +153,13 @@ def test_tile_geometry():
     for first, last in vgg.SEGMENTS:
         level = sum(1 for p in vgg.POOL_AFTER if p < first)
         assert tiled.HALO >> level >= 2 * (last - first + 1), (first, last)
+    # the tensors exchanged in one step of a 3840x2160 run (interior strip): five on the way up, their gradients on the way
+    # down, the image; the mailbox of tiled.PeerHalo is sized from this list
+    plan = tiled.exchange_plan(2160, 544, tiled.HALO, 12)
+    up = [(1080, 16, 64), (540, 8, 128), (270, 4, 256), (270, 4, 512), (135, 2, 512)]
+    assert plan == up + up[::-1] + [(2160, 32, 3)]
+    assert all((hl * c) % 4 == 0 for _, hl, c in plan)                         # float4 rows in the push / pull kernels
+    assert sum(r * hl * c * 4 for r, hl, c in plan) < 32 << 20
 
 
 _TILED_WORKER = r"""
