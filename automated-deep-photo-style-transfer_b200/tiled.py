@@ -259,21 +259,35 @@ class PeerHalo:
 
     def connect_processes(self):
         """Collective over the default process group (one process per GPU of one node): map the neighbours' mailboxes
-        through CUDA IPC."""
+        through CUDA IPC.  Every rank raises RuntimeError if any rank could not connect (the ranks agree on the outcome, so
+        the caller can fall back to another transport collectively)."""
         import torch.distributed as dist
         L = _lib.lib()
         buf = ctypes.create_string_buffer(L.adpst_halo_ipc_handle_bytes())
-        _lib.check(L.adpst_halo_export(self._h, buf))
-        mine = (self.rank, bytes(buf.raw), self.side_bytes)
+        error = None
+        try:
+            _lib.check(L.adpst_halo_export(self._h, buf))
+        except _lib.AdpstError as e:
+            error = str(e)
+        mine = (self.rank, bytes(buf.raw), self.side_bytes, error)
         everyone = [None] * self.world
         dist.all_gather_object(everyone, mine)
-        table = {r: (hb, sb) for r, hb, sb in everyone}
-        with torch.cuda.device(self.device):
-            for side, peer in ((0, self.rank - 1), (1, self.rank + 1)):
-                if 0 <= peer < self.world:
-                    hb, sb = table[peer]
-                    _lib.check(L.adpst_halo_connect_ipc(self._h, side, ctypes.c_char_p(hb), sb))
-        dist.barrier()
+        table = {r: (hb, sb) for r, hb, sb, _ in everyone}
+        error = next((e for _, _, _, e in everyone if e), None)
+        if error is None:
+            try:
+                with torch.cuda.device(self.device):
+                    for side, peer in ((0, self.rank - 1), (1, self.rank + 1)):
+                        if 0 <= peer < self.world:
+                            hb, sb = table[peer]
+                            _lib.check(L.adpst_halo_connect_ipc(self._h, side, ctypes.c_char_p(hb), sb))
+            except _lib.AdpstError as e:
+                error = str(e)
+        outcomes = [None] * self.world
+        dist.all_gather_object(outcomes, error)
+        failed = [(r, e) for r, e in enumerate(outcomes) if e]
+        if failed:
+            raise RuntimeError("peer-memory mailboxes could not be connected (rank %d: %s)" % failed[0])
 
     @staticmethod
     def connect_local(halos, sync=None):

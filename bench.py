@@ -592,7 +592,14 @@ def tiled_record(D, H, W, K, steps, warmup, tv_weight, check_parity=True, graph=
     cm = sem.mask_for_tf(sem.extract_segmentation_masks(synth.label_image(H, W, K, 9, cell=64)))
     sm = sem.mask_for_tf(sem.extract_segmentation_masks(synth.label_image(H, W, K, 10, cell=64)))
     weights = synth.vgg_weights()
-    job = tiled.TiledStyleTransfer(content, style, hp, cm, sm, weights, D.rank, D.world, halo=None if halo == "nccl" else halo)
+    transport = halo
+    try:
+        job = tiled.TiledStyleTransfer(content, style, hp, cm, sm, weights, D.rank, D.world, halo=None if halo == "nccl" else halo)
+    except RuntimeError as e:                           # raised on every rank alike (PeerHalo.connect_processes)
+        if "mailboxes could not be connected" not in str(e):
+            raise
+        transport = "nccl (fallback: %s)" % e
+        job = tiled.TiledStyleTransfer(content, style, hp, cm, sm, weights, D.rank, D.world, halo=None)
     first = {k: float(v) for k, v in job.step().items()}           # iteration 0: evaluated at x = content on every rank
     for _ in range(2):
         d = job.step()
@@ -613,7 +620,7 @@ def tiled_record(D, H, W, K, steps, warmup, tv_weight, check_parity=True, graph=
                      "%d) over %d GPU(s); per step: %s" % (W, H, K, W // D.world, tiled.HALO if D.world > 1 else 0, t.local_w,
                                                            D.world, job.describe_exchange()),
            "scaling": "strong", "n_gpus": D.world, "value": steps / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms / steps,
-           "steps": steps, "launch": ("one CUDA graph per rank and step (kernels + NCCL send/recv + all-reduce)"
+           "steps": steps, "halo_transport": transport if D.world > 1 else "none", "launch": ("one CUDA graph per rank and step (kernels + NCCL send/recv + all-reduce)"
                                       if (graph and D.world > 1) else "eager launches"),
            "bytes_exchanged_per_step": job.exchange_bytes(), "final_total_loss": float(d["Total loss"]),
            "breakdown_max_over_ranks": dict(breakdown, what="EAGER steps, device ms per step: halo exchanges (packing, NCCL "
