@@ -99,6 +99,15 @@ class NcclComm:
                 dist.all_reduce(t, op=dist.ReduceOp.SUM)
             self.bytes["allreduce"] += t.numel() * t.element_size()
 
+    def reduce_start(self, t):
+        """Start summing t over the ranks on NCCL's own stream (it waits for the work queued on the current stream so far) and
+        return a callable that makes the current stream wait for the result.  Kernels enqueued in between overlap with it."""
+        import torch.distributed as dist
+        self.bytes["allreduce"] += t.numel() * t.element_size()
+        if self.world == 1:
+            return lambda: None
+        return dist.all_reduce(t, op=dist.ReduceOp.SUM, async_op=True).wait
+
     def exchange(self, tensor, lo, hi, hl):
         """tensor (1,h,w,C) or (h,w,C)-like with columns on dim -2: send the hl own columns next to each interior boundary to
         that neighbour, overwrite the hl halo columns with what the neighbour sends.  Returns the received slabs."""
@@ -136,6 +145,10 @@ class GlooComm(NcclComm):
             dist.all_reduce(c, op=dist.ReduceOp.SUM)
             t.copy_(c)
             self.bytes["allreduce"] += t.numel() * t.element_size()
+
+    def reduce_start(self, t):
+        self.reduce_sum([t])
+        return lambda: None
 
     def exchange(self, tensor, lo, hi, hl):
         import torch.distributed as dist
@@ -191,6 +204,10 @@ class ThreadComm:
                     g.copy_(tot.to(g.dtype))
         self.s.barrier.wait()
         self.bytes["allreduce"] += sum(t.numel() * t.element_size() for t in tensors)
+
+    def reduce_start(self, t):
+        self.reduce_sum([t])
+        return lambda: None
 
     def exchange(self, tensor, lo, hi, hl):
         t = tensor if tensor.dim() == 4 else tensor.unsqueeze(0)
@@ -338,7 +355,7 @@ class TiledStyleTransfer:
     set-up passes (content / style targets) always use `comm`."""
 
     def __init__(self, content, style, args, content_masks, style_masks, vgg_weights, rank, world, comm=None, matting="v2",
-                 device=None, halo=None):
+                 device=None, halo=None, overlap_reduce=True):
         dev = torch.device(device if device is not None else "cuda")
         self.rank, self.world = rank, world
         self.comm = comm if comm is not None else NcclComm(rank, world)
@@ -364,6 +381,7 @@ class TiledStyleTransfer:
         self._flat = None                               # flat float32 buffer behind the per-layer Gram partials
         li = self.extractor.last_index
         self._last_exchange_layer = max(last for _, last in SEGMENTS if last < li)     # the forward pass's last exchange
+        self.overlap_reduce = overlap_reduce            # sum finished Gram partials while the forward pass continues
         self.halo = None
         if halo is not None and world > 1:
             if isinstance(halo, str):
@@ -436,13 +454,17 @@ class TiledStyleTransfer:
         halo = self.halo
         raw_peer = None if halo is None else halo.exchange
 
-        def timed(fn):
+        reduces = []
+
+        def timed(fn, into=None):
+            into = events if into is None else into
+
             def wrapper(*a, **k):
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 e0.record()
                 out = fn(*a, **k)
                 e1.record()
-                events.append((e0, e1))
+                into.append((e0, e1))
                 return out
             return wrapper
 
@@ -457,7 +479,7 @@ class TiledStyleTransfer:
                 hidden.append((a, b))
             return raw_peer(tensor, lo, hi, hl, slot_ptr, None if overlap is None else inner)
 
-        comm.exchange, comm.reduce_sum = timed(raw_exchange), timed(raw_reduce)
+        comm.exchange, comm.reduce_sum = timed(raw_exchange), timed(raw_reduce, reduces)
         if halo is not None:
             halo.exchange = timed(timed_peer)
         try:
@@ -475,9 +497,10 @@ class TiledStyleTransfer:
             if halo is not None:
                 del halo.exchange                   # back to the class's method
         total = t0.elapsed_time(t1) / steps
-        comm_ms = (sum(a.elapsed_time(b) for a, b in events) - sum(a.elapsed_time(b) for a, b in hidden)) / steps
+        reduce_ms = sum(a.elapsed_time(b) for a, b in reduces) / steps
+        comm_ms = (sum(a.elapsed_time(b) for a, b in events) - sum(a.elapsed_time(b) for a, b in hidden)) / steps + reduce_ms
         own = self.tile.own_hi - self.tile.own_lo
-        return {"ms_per_step": total, "communication_ms": comm_ms, "compute_ms": total - comm_ms,
+        return {"ms_per_step": total, "communication_ms": comm_ms, "allreduce_ms": reduce_ms, "compute_ms": total - comm_ms,
                 "host_enqueue_ms": host_ms, "redundant_column_factor": self.tile.local_w / own}
 
     def own_strip(self):
@@ -524,8 +547,17 @@ class TiledStyleTransfer:
         # On the first step the per-layer state does not exist yet: everything runs after the forward pass.
         loss.begin_partials(self.image)
 
+        # A Gram partial that is complete is summed over the ranks at once, on NCCL's stream, while this rank computes the
+        # deeper segments; only the last layer's partial and the float64 accumulator are reduced after the forward pass.
+        waits, reduced = [], set()
+
         def fwd_overlap(last, outputs):
             loss.partial_layers(outputs, last)
+            if self.overlap_reduce:
+                for name, G in loss._part["G"].items():
+                    if name not in reduced:
+                        reduced.add(name)
+                        waits.append(self.comm.reduce_start(G))
             if last >= self._last_exchange_layer:
                 loss.partial_image()
         outputs = self.extractor.forward_blocks(self.image, ex, reuse=True, overlap=None if first_step else fwd_overlap)
@@ -536,7 +568,12 @@ class TiledStyleTransfer:
             self.comm.reduce_sum(loss.style_targets_partial())
             self._targets_reduced = True
         parts = loss.end_partials(outputs)
-        self.comm.reduce_sum([self._flat, parts[-1]])   # every Gram partial lives in the flat buffer; + the float64 accumulator
+        if reduced:                                     # the partials still local (views of the flat buffer) + the accumulator
+            self.comm.reduce_sum([G for name, G in loss._part["G"].items() if name not in reduced] + [parts[-1]])
+            for wait in waits:
+                wait()
+        else:
+            self.comm.reduce_sum([self._flat, parts[-1]])   # every Gram partial lives in the flat buffer
         # Style terms / gradient seeds are evaluated lazily on the way down: the seeds of a segment at the latest right before
         # it runs, one more layer (the deepest pending one) inside every exchange window.
         loss.finish(lazy=True)
