@@ -111,8 +111,8 @@ w("* `sass_opcodes.txt`: per-kernel counts of UTCHMMA / UTMALDG / LDTM / STTM / 
   "  (`scripts/sass_opcodes.py`).\n")
 
 w("\n## 4. Multi-GPU (plain runs of the default `bench.py` line under torch.distributed.run)\n\n"
-  "| GPUs | headline iter/s (one 1024^2 pair per GPU) | e2e | pairs_64x512 iter/s | set-up ms/pair | tiled_4k iter/s | ms/step | comm ms | redundant columns | parity vs 1 GPU |\n"
-  "|---:|---:|---:|---:|---:|---:|---:|---:|---:|---:|\n")
+  "| GPUs | headline iter/s (one 1024^2 pair per GPU) | e2e | pairs_64x512 iter/s | set-up ms/pair | tiled_4k iter/s | ms/step | halo transport | comm ms (of which all-reduce) | redundant columns | parity vs 1 GPU |\n"
+  "|---:|---:|---:|---:|---:|---:|---:|---|---:|---:|---:|\n")
 for n, name in ((1, "r2_bench_1gpu.json"), (2, "r2_bench_2gpu.json"), (4, "r2_bench_4gpu.json"), (8, "r2_bench_8gpu.json")):
     d = jline(name)
     if not d:
@@ -120,13 +120,18 @@ for n, name in ((1, "r2_bench_1gpu.json"), (2, "r2_bench_2gpu.json"), (4, "r2_be
     pr, t4 = d.get("pairs_64x512", {}), d.get("tiled_4k", {})
     bd = t4.get("breakdown_max_over_ranks", {})
     par = t4.get("parity_vs_single_device", {})
-    w("| %d | %.1f | %.1f | %.0f | %.1f | %.1f | %.2f | %s | %s | %s |\n"
+    w("| %d | %.1f | %.1f | %.0f | %.1f | %.1f | %.2f | %s | %s | %s | %s |\n"
       % (n, d["value"], d["e2e"]["value"], pr.get("value", 0), pr.get("setup_ms_per_pair", 0), t4.get("value", 0), t4.get("ms_per_step", 0),
-         ("%.2f" % bd["communication_ms"]) if bd else "-", ("%.2f" % bd["redundant_column_factor"]) if bd else "-",
+         t4.get("halo_transport", "-"),
+         ("%.2f (%.2f)" % (bd["communication_ms"], bd.get("allreduce_ms", float("nan")))) if bd else "-",
+         ("%.2f" % bd["redundant_column_factor"]) if bd else "-",
          ("%.1e" % par["max_rel_loss_diff"]) if par else "-"))
-w("\n`tiled_4k`: one 3840x2160 image in column strips with a 64-px halo; per step nine point-to-point halo exchanges (pooled tensors\n"
-  "forward, their gradients backward, the image border) and one all-reduce of the flattened Gram partials.  `comm ms` = device time\n"
-  "inside the exchange / all-reduce calls (packing, NCCL, unpacking), max over ranks; `redundant columns` = (own + halo) / own.\n")
+w("\n`tiled_4k`: one 3840x2160 image in column strips with a 32-px halo; per step eleven halo exchanges between the six network\n"
+  "segments (activations up, gradients down, the image border) by our push/pull kernels over NVLink peer memory, and NCCL\n"
+  "all-reduces of the Gram partials (started as each partial is complete).  The timed steps replay one CUDA graph per rank.\n"
+  "`comm ms` comes from a short EAGER run with CUDA events around every exchange / all-reduce call (work enqueued inside an\n"
+  "exchange window subtracted), max over ranks: it contains the time a rank waits for a slower neighbour; `redundant columns` =\n"
+  "(own + halo) / own.\n")
 
 old = open(os.path.join(P, "README.md")).read()
 marker = "# Round 1 profiles"
