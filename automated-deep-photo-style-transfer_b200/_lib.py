@@ -22,6 +22,7 @@ class AdpstError(RuntimeError):
 _c = ctypes
 _vp, _i, _d, _f, _sz = _c.c_void_p, _c.c_int, _c.c_double, _c.c_float, _c.c_size_t
 _pp = _c.POINTER(_c.c_void_p)
+_ip = _c.POINTER(_c.c_int)
 
 # name -> (restype, argtypes).  Must list every symbol declared in include/adpst.h (tests/test_abi.py checks).
 SIGNATURES = {
@@ -43,8 +44,8 @@ SIGNATURES = {
     "adpst_vgg_conv_shape": (_i, [_i, _i, _i, _c.POINTER(_i), _c.POINTER(_i), _c.POINTER(_i)]),
     "adpst_vgg_pool_shape": (_i, [_i, _i, _i, _c.POINTER(_i), _c.POINTER(_i), _c.POINTER(_i)]),
     "adpst_vgg_forward": (_i, [_vp, _vp, _i, _i, _pp, _pp, _i, _vp]),
-    "adpst_vgg_forward_range": (_i, [_vp, _vp, _i, _i, _pp, _pp, _i, _i, _vp]),
-    "adpst_vgg_backward_range": (_i, [_vp, _i, _i, _pp, _pp, _i, _i, _vp, _vp, _vp, _vp, _vp]),
+    "adpst_vgg_forward_range": (_i, [_vp, _vp, _i, _i, _pp, _pp, _i, _i, _ip, _ip, _vp]),
+    "adpst_vgg_backward_range": (_i, [_vp, _i, _i, _pp, _pp, _i, _i, _vp, _vp, _vp, _vp, _ip, _ip, _vp]),
     "adpst_absmax_update": (_i, [_vp, _sz, _vp, _vp]),
     "adpst_vgg_grad_absmax": (_vp, [_vp, _i]),
     "adpst_halo_create": (_i, [_sz, _pp]),

@@ -109,19 +109,28 @@ class VGG19Handle:
 class Activations:
     """Caller-owned activation set of one forward pass (conv outputs post-ReLU and pool outputs)."""
 
-    def __init__(self, H, W, last, device):
-        self.H, self.W, self.last = H, W, last
+    def __init__(self, H, W, last, device, geom=None):
+        """geom (strips of a tiled run, see adpst_vgg_forward_range): (widths of the five resolution levels, column offsets of
+        the four pooled tensors); such tensors are zero-filled once, because the columns next to a pooled tensor are only
+        ever written by the halo exchange."""
+        self.H, self.W, self.last, self.geom = H, W, last, geom
         self.acts = [None] * _lib.VGG_NUM_CONV
         self.pools = [None] * _lib.VGG_NUM_POOL
+        make = torch.empty if geom is None else torch.zeros
         for i in range(last + 1):
             h, w, c = VGG19Handle.conv_shape(i, H, W)
+            if geom is not None:
+                w = geom[0][sum(1 for p in POOL_AFTER if p < i)]
             if h < 1 or w < 1:
                 raise ValueError("a %dx%d image is too small for VGG19 layer %s" % (H, W, CONV_LAYERS[i][0]))
-            self.acts[i] = torch.empty(1, h, w, c, dtype=torch.float32, device=device)
+            self.acts[i] = make(1, h, w, c, dtype=torch.float32, device=device)
         for j, after in enumerate(POOL_AFTER):
             if after < last:
                 h, w, c = VGG19Handle.pool_shape(j, H, W)
-                self.pools[j] = torch.empty(1, h, w, c, dtype=torch.float32, device=device)
+                if geom is not None:
+                    w = geom[0][j + 1]
+                self.pools[j] = make(1, h, w, c, dtype=torch.float32, device=device)
+        self.c_geom = (None, None) if geom is None else ((ctypes.c_int * 5)(*geom[0]), (ctypes.c_int * 4)(*geom[1]))
 
 
 def vgg_layers(layer_names, shape=None, weights=None, device=None):
@@ -165,7 +174,7 @@ class StyleContentModel:
         if reuse:
             # a private buffer set that only reuse=True calls ever write: results handed out by reuse=False calls
             # (the content / style targets) are never overwritten
-            if self._loop is None or (self._loop.H, self._loop.W) != (H, W):
+            if self._loop is None or (self._loop.H, self._loop.W, self._loop.geom) != (H, W, None):
                 self._loop = Activations(H, W, self.last_index, self.device)
             A = self._loop
         else:
@@ -184,23 +193,26 @@ class StyleContentModel:
         return {"content": content, "style": style}
 
     # ---- spatially tiled runs (tiled.py): block by block, with a halo exchange on every tensor that crosses a pool --------
-    def forward_blocks(self, inputs, exchange, reuse=True, overlap=None):
+    def forward_blocks(self, inputs, exchange, reuse=True, overlap=None, geom=None):
         """Like call(), but the network runs one segment (SEGMENTS) at a time and `exchange(tensor, slot)` is called on the
         tensor that leaves a segment -- the pooled tensor, or conv 9's output between the two halves of block4 -- before the
         next segment reads it.  `exchange` overwrites the halo columns in place with the neighbours' data and raises the scale
         slot `slot` (device address of the tensor's max|.| word, see VGG19Handle.absmax_update) to the maximum of what arrived.
         overlap(last, outputs): optional; work that only needs the layers up to conv `last`, handed to exchange() as a third
-        argument (a callable without arguments) to be enqueued while the halo columns are in flight."""
+        argument (a callable without arguments) to be enqueued while the halo columns are in flight.
+        geom: (level widths, pool column offsets) of a strip with per-level halos (Activations)."""
         if inputs.dim() != 4 or inputs.shape[0] != 1 or inputs.shape[3] != 3 or inputs.dtype != torch.float32 or not inputs.is_cuda:
             raise TypeError("expected a float32 CUDA image of shape (1, H, W, 3)")
         x = inputs.contiguous()
         H, W = int(x.shape[1]), int(x.shape[2])
+        if geom is not None:
+            geom = (tuple(int(v) for v in geom[0]), tuple(int(v) for v in geom[1]))
         if reuse:
-            if self._loop is None or (self._loop.H, self._loop.W) != (H, W):
-                self._loop = Activations(H, W, self.last_index, self.device)
+            if self._loop is None or (self._loop.H, self._loop.W, self._loop.geom) != (H, W, geom):
+                self._loop = Activations(H, W, self.last_index, self.device, geom)
             A = self._loop
         else:
-            A = Activations(H, W, self.last_index, self.device)
+            A = Activations(H, W, self.last_index, self.device, geom)
         L = _lib.lib()
         self.last = A
         self.vgg.generation += 1
@@ -217,7 +229,8 @@ class StyleContentModel:
             last = min(last, self.last_index)
             with torch.cuda.device(self.device):
                 _lib.check(L.adpst_vgg_forward_range(self.vgg._h, _lib.ptr(x), H, W, _lib.ptr_array(A.acts),
-                                                     _lib.ptr_array(A.pools), first, last, _lib.stream_ptr()))
+                                                     _lib.ptr_array(A.pools), first, last, A.c_geom[0], A.c_geom[1],
+                                                     _lib.stream_ptr()))
             if last == self.last_index:
                 break
             out = A.pools[POOL_AFTER.index(last)] if last in POOL_AFTER else A.acts[last]
@@ -249,14 +262,14 @@ class StyleContentModel:
                              torch.empty(A.acts[0].numel(), dtype=torch.float32, device=self.device))
         if out is None:
             out = torch.empty(1, A.H, A.W, 3, dtype=torch.float32, device=self.device)
-        if self._dseg is None or self._dseg_shape != (A.H, A.W):
+        if self._dseg is None or self._dseg_shape != (A.H, A.W, A.geom):
             # the gradient that leaves segment s (entering at conv `first`): shaped like that segment's input
             self._dseg = {}
             for first, _ in SEGMENTS[1:]:
                 src = A.pools[POOL_AFTER.index(first - 1)] if (first - 1) in POOL_AFTER else A.acts[first - 1]
                 if src is not None:
                     self._dseg[first] = torch.empty_like(src)
-            self._dseg_shape = (A.H, A.W)
+            self._dseg_shape = (A.H, A.W, A.geom)
         L = _lib.lib()
         grad_in = None
         for first, last in reversed(SEGMENTS):
@@ -269,7 +282,8 @@ class StyleContentModel:
             with torch.cuda.device(self.device):
                 _lib.check(L.adpst_vgg_backward_range(self.vgg._h, A.H, A.W, _lib.ptr_array(A.acts), _lib.ptr_array(arr), first,
                                                       last, _lib.ptr(grad_in), _lib.ptr(self._scratch[0]),
-                                                      _lib.ptr(self._scratch[1]), _lib.ptr(target), _lib.stream_ptr()))
+                                                      _lib.ptr(self._scratch[1]), _lib.ptr(target), A.c_geom[0], A.c_geom[1],
+                                                      _lib.stream_ptr()))
             if first > 0:
                 # mid-block: the consumer reads the scale slot of conv first-1's gradient; below a pool the un-pooling kernel
                 # measures its own output

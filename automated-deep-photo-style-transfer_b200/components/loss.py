@@ -113,8 +113,15 @@ class Loss:
             if self._mask_planes is None:       # the full-resolution masks go to the device once, as two (K,H,W) stacks
                 self._mask_planes = (torch.stack([_plane(m, self.device) for m in self.content_masks]).contiguous(),
                                      torch.stack([_plane(m, self.device) for m in self.style_masks]).contiguous())
-            cm = kernels.resize_bilinear_batch(self._mask_planes[0], (h, w)).reshape(K, h * w)        # loss.py:112-117
-            sm = kernels.resize_bilinear_batch(self._mask_planes[1], (hs, ws_)).reshape(K, hs * ws_)
+            cplanes, splanes = self._mask_planes
+            if self.tile is not None:            # a strip keeps a different number of halo columns on every resolution level
+                a, b = self.tile.mask_cols(w)
+                cplanes = cplanes[:, :, a:b].contiguous()
+            if self.style_tile is not None:
+                a, b = self.style_tile.mask_cols(ws_)
+                splanes = splanes[:, :, a:b].contiguous()
+            cm = kernels.resize_bilinear_batch(cplanes, (h, w)).reshape(K, h * w)                      # loss.py:112-117
+            sm = kernels.resize_bilinear_batch(splanes, (hs, ws_)).reshape(K, hs * ws_)
         else:
             K, cm, sm = 1, None, None                                                # loss.py:119-120
         # spatial tiling: the Gram partial of this rank counts only its own columns (mask x column indicator; exact,

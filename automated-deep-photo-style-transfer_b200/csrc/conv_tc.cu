@@ -147,7 +147,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                   int tiles_w, int num_tiles, const float* __restrict__ cls_masks, const uint32_t* __restrict__ tile_active,
                   const uint32_t* __restrict__ a_absmax, const uint32_t* __restrict__ b_absmax,
                   const uint32_t* __restrict__ w_absmax, uint32_t* __restrict__ y_absmax, float* __restrict__ pool_out,
-                  int tw_log2_arg) {
+                  int tw_log2_arg, int pool_pitch, int pool_xoff) {
     using Cfg = TcCfg<BN, MODE>;
     // pixel tile: 8 rows x 16 columns (tw_log2 = 4) or 16 rows x 8 columns (tw_log2 = 3, narrow maps: the column strips of a
     // spatially tiled run are 68 or 34 pixels wide at 1/8 and 1/16 resolution); 128 pixels and a 180-pixel halo tile either way
@@ -586,7 +586,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                             // (4q .. 4q+3 of a 16 x 8 tile).  Windows that exist lie completely inside the image, so
                             // out-of-image lanes never contribute.
                             const bool writer = (lane & (tile_w | 1)) == 0 && gy + 1 < H && gx + 1 < W;
-                            float* prow = pool_out + (size_t(gy >> 1) * (W >> 1) + (gx >> 1)) * size_t(Cout) + n0 + c0;
+                            float* prow = pool_out + (size_t(gy >> 1) * pool_pitch + (gx >> 1) + pool_xoff) * size_t(Cout) + n0 + c0;
 #pragma unroll
                             for (int j = 0; j < 32; j += 4) {
                                 float pv[4];
@@ -747,7 +747,7 @@ static int launch_tc(const CUtensorMap& tmA, const CUtensorMap& tmBhi, const CUt
                      const float* seed, const float* mask, int H, int W, int Cin, int Cout, const uint32_t* a_absmax,
                      const uint32_t* b_absmax, uint32_t* y_absmax, cudaStream_t st, const float* cls_masks = nullptr,
                      const uint32_t* tile_active = nullptr, const uint32_t* w_absmax = nullptr, float* pool_out = nullptr,
-                     int tw_log2 = 4) {
+                     int tw_log2 = 4, int pool_pitch = 0, int pool_xoff = 0) {
     using Cfg = TcCfg<BN, MODE>;
     auto kern = conv3x3_tc_kernel<BN, MODE>;
     ADPST_ONCE_PER_DEVICE(ADPST_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES)));
@@ -757,7 +757,7 @@ static int launch_tc(const CUtensorMap& tmA, const CUtensorMap& tmBhi, const CUt
     const int grid = total < num_sms() ? total : num_sms();
     kern<<<grid, TC_THREADS, Cfg::SMEM_BYTES, st>>>(tmA, tmBhi, tmBlo, bias, Y, seed, mask, H, W, Cin, Cout, tw, tw * th,
                                                     cls_masks, tile_active, a_absmax, b_absmax, w_absmax, y_absmax, pool_out,
-                                                    tw_log2);
+                                                    tw_log2, pool_pitch, pool_xoff);
     ADPST_LAUNCH_CHECK();
     return ADPST_OK;
 }
@@ -778,9 +778,11 @@ static int make_act_map(CUtensorMap* tm, const float* X, int H, int W, int C, in
 // X: (H,W,Cin) activation; gradient = 0: conv i forward (bias + ReLU), 1: data gradient of conv i (Cin/Cout are the GEMM's
 // K and N, i.e. already swapped for the gradient).  x_absmax: device slot holding max|X| (float bits); y_absmax (may be
 // NULL): slot that receives max|Y| (atomicMax; the caller zeroes it).
-// pool_out (forward only, may be NULL): receives the 2x2/2 max-pool of Y, (H/2, W/2, Cout).
+// pool_out (forward only, may be NULL): receives the 2x2/2 max-pool of Y, (H/2, W/2, Cout), stored with pool_pitch columns per
+// row starting at column pool_xoff (W/2 and 0 for a plain tensor).
 int launch_conv_tc(adpst_vgg* h, int i, int gradient, const float* X, float* Y, const float* seed, const float* mask, int H,
-                   int W, int Cin, int Cout, const uint32_t* x_absmax, uint32_t* y_absmax, float* pool_out, cudaStream_t st) {
+                   int W, int Cin, int Cout, const uint32_t* x_absmax, uint32_t* y_absmax, float* pool_out, cudaStream_t st,
+                   int pool_pitch, int pool_xoff) {
     CUtensorMap tmA;
     const int shape = pick_tile_shape(H, W);
     int rc = make_act_map(&tmA, X, H, W, Cin, shape);
@@ -793,9 +795,9 @@ int launch_conv_tc(adpst_vgg* h, int i, int gradient, const float* X, float* Y, 
     if (!gradient) {
         if (BN == 128)
             return launch_tc<128, MODE_FWD>(tmA, bh, bl, bias, Y, seed, mask, H, W, Cin, Cout, x_absmax, wslot, y_absmax, st,
-                                            nullptr, nullptr, nullptr, pool_out, shape);
+                                            nullptr, nullptr, nullptr, pool_out, shape, pool_pitch, pool_xoff);
         return launch_tc<64, MODE_FWD>(tmA, bh, bl, bias, Y, seed, mask, H, W, Cin, Cout, x_absmax, wslot, y_absmax, st, nullptr,
-                                       nullptr, nullptr, pool_out, shape);
+                                       nullptr, nullptr, pool_out, shape, pool_pitch, pool_xoff);
     }
     if (BN == 128)
         return launch_tc<128, MODE_BWD>(tmA, bh, bl, bias, Y, seed, mask, H, W, Cin, Cout, x_absmax, wslot, y_absmax, st, nullptr,

@@ -39,7 +39,8 @@ namespace adpst {
 bool conv_tc_eligible(int Cin, int Cout);
 int prepare_tc_weights(adpst_vgg* h, int i, cudaStream_t st);
 int launch_conv_tc(adpst_vgg* h, int i, int gradient, const float* X, float* Y, const float* seed, const float* mask, int H,
-                   int W, int Cin, int Cout, const uint32_t* x_absmax, uint32_t* y_absmax, float* pool_out, cudaStream_t st);
+                   int W, int Cin, int Cout, const uint32_t* x_absmax, uint32_t* y_absmax, float* pool_out, cudaStream_t st,
+                   int pool_pitch, int pool_xoff);
 // *slot = float bits of max|x| (reset: zeroes the slot first; otherwise the slot keeps the larger of its value and max|x|)
 int launch_absmax(const float* x, size_t n, uint32_t* slot, cudaStream_t st, bool reset = true);
 // style gradient on the tensor cores: dF[px,:] (=|+=) sum_k m_k[px]^2 F[px,:] D_k, D given as FP16 hi/lo planes (K,C,C)

@@ -251,7 +251,7 @@ __device__ __forceinline__ void record_absmax(float amax, uint32_t* __restrict__
 // 2x2/2 VALID max-pool, forward and (fused with the ReLU mask and an optional loss seed) backward
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
-maxpool2_kernel(const float* __restrict__ X, float* __restrict__ P, int H, int W, int C) {
+maxpool2_kernel(const float* __restrict__ X, float* __restrict__ P, int H, int W, int C, int p_pitch, int p_xoff) {
     const int Hp = H / 2, Wp = W / 2, C4 = C / 4;
     const size_t total = size_t(Hp) * Wp * C4;
     for (size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += size_t(gridDim.x) * blockDim.x) {
@@ -266,7 +266,7 @@ maxpool2_kernel(const float* __restrict__ X, float* __restrict__ P, int H, int W
         m.y = fmaxf(fmaxf(v00.y, v01.y), fmaxf(v10.y, v11.y));
         m.z = fmaxf(fmaxf(v00.z, v01.z), fmaxf(v10.z, v11.z));
         m.w = fmaxf(fmaxf(v00.w, v01.w), fmaxf(v10.w, v11.w));
-        reinterpret_cast<float4*>(P)[i] = m;
+        reinterpret_cast<float4*>(P)[(size_t(py) * p_pitch + px + p_xoff) * C4 + c4] = m;     // (p_pitch = Wp, p_xoff = 0: P[i])
     }
 }
 
@@ -275,7 +275,9 @@ maxpool2_kernel(const float* __restrict__ X, float* __restrict__ P, int H, int W
 // are not pooling windows (VALID pooling); their pixels only see the seed.
 __global__ void __launch_bounds__(256)
 unpool_relu_kernel(const float* __restrict__ Y, const float* __restrict__ dP, const float* __restrict__ seed,
-                   float* __restrict__ dPre, int H, int W, int C, uint32_t* __restrict__ out_absmax) {
+                   float* __restrict__ dPre, int H, int W, int C, uint32_t* __restrict__ out_absmax, int dp_pitch, int dp_xoff) {
+    // dP is stored with dp_pitch columns per row and the window of cell cx at column cx + dp_xoff (a strip of a tiled run keeps
+    // a wider halo on the pooled side; dp_pitch = W / 2, dp_xoff = 0 otherwise)
     const int Hp = H / 2, Wp = W / 2, Hc = (H + 1) / 2, Wc = (W + 1) / 2, C4 = C / 4;
     const size_t total = size_t(Hc) * Wc * C4;
     float amax = 0.f;
@@ -295,7 +297,7 @@ unpool_relu_kernel(const float* __restrict__ Y, const float* __restrict__ dP, co
             if (ok[j]) v[j] = __ldg(reinterpret_cast<const float4*>(Y + (size_t(y) * W + x) * C) + c4);
         }
         if (window) {
-            const float4 d = __ldg(reinterpret_cast<const float4*>(dP + (size_t(cy) * Wp + cx) * C) + c4);
+            const float4 d = __ldg(reinterpret_cast<const float4*>(dP + (size_t(cy) * dp_pitch + cx + dp_xoff) * C) + c4);
             const float* vf = reinterpret_cast<const float*>(v);
             float* gf = reinterpret_cast<float*>(g);
             const float df[4] = {d.x, d.y, d.z, d.w};
@@ -381,6 +383,19 @@ static void layer_hw(int conv, int H, int W, int* h, int* w) {
     *w = W >> p;
 }
 
+// Column geometry of a strip of a spatially tiled run (tiled.py): the tensors of resolution level l are widths[l] columns wide
+// (own columns + that level's halo), and the 2x2 max-pool of a level-l tensor (widths[l] / 2 columns) lands at column
+// pool_xoff[l] of the level-(l+1) tensor, whose outer columns only ever hold what the neighbour sends.  NULL: one image,
+// widths[l] = W >> l, no offsets.
+struct StripGeom {
+    const int* widths;
+    const int* pool_xoff;
+};
+static void layer_hw(int conv, int H, int W, const StripGeom& g, int* h, int* w) {
+    layer_hw(conv, H, W, h, w);
+    if (g.widths != nullptr) *w = g.widths[pools_before(conv)];
+}
+
 static int launch_conv_simt(int mode, bool pre, const float* X, const float* Wt, const float* bias, float* Y, const float* seed,
                        const float* mask, int H, int W, int Cin, int Cout, uint32_t* y_absmax, cudaStream_t st) {
     ADPST_REQUIRE(Cout % CT_N == 0, "conv3x3: Cout=%d must be a multiple of %d", Cout, CT_N);
@@ -404,7 +419,7 @@ static int launch_conv_simt(int mode, bool pre, const float* X, const float* Wt,
 // pool_out (forward, may be NULL): where the following 2x2 max-pool goes; *pooled is set when the kernel wrote it.
 static int launch_conv(adpst_vgg* h, int i, int mode, const float* X, float* Y, const float* seed, const float* mask,
                        int lh, int lw, const uint32_t* x_absmax, uint32_t* y_absmax, cudaStream_t st,
-                       float* pool_out = nullptr, bool* pooled = nullptr) {
+                       float* pool_out = nullptr, bool* pooled = nullptr, int pool_pitch = 0, int pool_xoff = 0) {
     const bool grad = (mode == MODE_BWD);
     const int K = grad ? conv_cout(i) : conv_cin(i), N = grad ? conv_cin(i) : conv_cout(i);
     if (h->conv_path == CONV_PATH_TENSOR && h->tc_ready && i > 0 && conv_tc_eligible(K, N)) {
@@ -415,7 +430,8 @@ static int launch_conv(adpst_vgg* h, int i, int mode, const float* X, float* Y, 
             x_absmax = scratch;
         }
         if (pooled) *pooled = (pool_out != nullptr && !grad);
-        return launch_conv_tc(h, i, grad ? 1 : 0, X, Y, seed, mask, lh, lw, K, N, x_absmax, y_absmax, grad ? nullptr : pool_out, st);
+        return launch_conv_tc(h, i, grad ? 1 : 0, X, Y, seed, mask, lh, lw, K, N, x_absmax, y_absmax, grad ? nullptr : pool_out, st,
+                              pool_pitch > 0 ? pool_pitch : lw / 2, pool_xoff);
     }
     return launch_conv_simt(mode, i == 0 && !grad, X, grad ? h->wb[i] : h->wf[i], grad ? nullptr : h->bias[i], Y, seed, mask,
                             lh, lw, K, N, y_absmax, st);
@@ -509,7 +525,7 @@ void adpst_vgg_destroy(adpst_vgg* h) {
 // convolutions first..last of the network; the input of conv `first` is the image (first == 0), the pooled tensor before
 // it, or the previous convolution's output
 static int vgg_forward_range(adpst_vgg* h, const float* image_dev, int H, int W, float* const* acts_dev, float* const* pools_dev,
-                             int first, int last, cudaStream_t st) {
+                             int first, int last, cudaStream_t st, adpst::StripGeom geom = {nullptr, nullptr}) {
     using namespace adpst;
     const float* x = image_dev;
     if (first > 0) {
@@ -521,22 +537,31 @@ static int vgg_forward_range(adpst_vgg* h, const float* image_dev, int H, int W,
     ADPST_CUDA_CHECK(cudaMemsetAsync(h->amax + AMAX_ACT + first, 0, (last - first + 1) * sizeof(uint32_t), st));
     for (int i = first; i <= last; ++i) {
         int lh, lw;
-        layer_hw(i, H, W, &lh, &lw);
+        layer_hw(i, H, W, geom, &lh, &lw);
         ADPST_REQUIRE(acts_dev[i] != nullptr, "vgg_forward: acts[%d] is NULL", i);
         // a max-pool keeps the maximum of a post-ReLU map, so the pooled tensor shares the slot of the conv before it
         float* pool_out = nullptr;                 // the tensor-core kernel pools in its epilogue
+        int pool_pitch = lw / 2, pool_xoff = 0;
         for (int j = 0; j < ADPST_VGG_NUM_POOL; ++j)
-            if (kPoolAfter[j] == i && pools_dev[j] != nullptr) pool_out = pools_dev[j];
+            if (kPoolAfter[j] == i && pools_dev[j] != nullptr) {
+                pool_out = pools_dev[j];
+                if (geom.widths != nullptr) {
+                    pool_pitch = geom.widths[j + 1];
+                    pool_xoff = geom.pool_xoff[j];
+                    ADPST_REQUIRE(pool_xoff >= 0 && pool_xoff + lw / 2 <= pool_pitch, "vgg_forward: pool %d does not fit its strip", j);
+                }
+            }
         bool pooled = false;
         int rc = launch_conv(h, i, MODE_FWD, x, acts_dev[i], nullptr, nullptr, lh, lw, i > 0 ? h->amax + AMAX_ACT + i - 1 : nullptr,
-                             h->amax + AMAX_ACT + i, st, pool_out, &pooled);
+                             h->amax + AMAX_ACT + i, st, pool_out, &pooled, pool_pitch, pool_xoff);
         if (rc != ADPST_OK) return rc;
         x = acts_dev[i];
         if (pool_out != nullptr) {
             if (!pooled) {
                 const size_t items = size_t(lh / 2) * (lw / 2) * (conv_cout(i) / 4);
                 if (items > 0) {
-                    maxpool2_kernel<<<stream_grid(items), 256, 0, st>>>(acts_dev[i], pool_out, lh, lw, conv_cout(i));
+                    maxpool2_kernel<<<stream_grid(items), 256, 0, st>>>(acts_dev[i], pool_out, lh, lw, conv_cout(i), pool_pitch,
+                                                                        pool_xoff);
                     ADPST_LAUNCH_CHECK();
                 }
             }
@@ -563,15 +588,32 @@ int adpst_vgg_forward(adpst_vgg* h, const float* image_dev, int H, int W, float*
     return vgg_forward_range(h, image_dev, H, W, acts_dev, pools, 0, last, as_stream(stream));
 }
 
+static int check_strip_geom(const int* level_widths, const int* pool_col_offset, int W, int last, const char* who) {
+    using namespace adpst;
+    ADPST_REQUIRE((level_widths == nullptr) == (pool_col_offset == nullptr), "%s: level_widths and pool_col_offset go together", who);
+    if (level_widths == nullptr) return ADPST_OK;
+    ADPST_REQUIRE(level_widths[0] == W, "%s: level_widths[0]=%d is not the image width %d", who, level_widths[0], W);
+    for (int l = 0; l <= pools_before(last); ++l) ADPST_REQUIRE(level_widths[l] >= 1, "%s: level %d is empty", who, l);
+    for (int l = 0; l < pools_before(last); ++l)
+        ADPST_REQUIRE(pool_col_offset[l] >= 0 && pool_col_offset[l] + level_widths[l] / 2 <= level_widths[l + 1],
+                      "%s: the pool of level %d (%d columns at offset %d) does not fit level %d (%d columns)", who, l,
+                      level_widths[l] / 2, pool_col_offset[l], l + 1, level_widths[l + 1]);
+    return ADPST_OK;
+}
+
 int adpst_vgg_forward_range(adpst_vgg* h, const float* image_dev, int H, int W, float* const* acts_dev,
-                            float* const* pools_dev, int first, int last, adpst_stream_t stream) {
+                            float* const* pools_dev, int first, int last, const int* level_widths, const int* pool_col_offset,
+                            adpst_stream_t stream) {
     using namespace adpst;
     ADPST_REQUIRE(h && acts_dev && pools_dev, "vgg_forward_range: NULL argument");
     ADPST_REQUIRE(first >= 0 && first <= last && last < kNumConv, "vgg_forward_range: bad range %d..%d", first, last);
     ADPST_REQUIRE(first > 0 || image_dev != nullptr, "vgg_forward_range: the image is NULL");
     ADPST_REQUIRE(H >= 1 && W >= 1 && (H >> pools_before(last)) >= 1 && (W >> pools_before(last)) >= 1,
                   "vgg_forward_range: %dx%d image is too small for conv %d", H, W, last);
-    return vgg_forward_range(h, image_dev, H, W, acts_dev, pools_dev, first, last, as_stream(stream));
+    int rc = check_strip_geom(level_widths, pool_col_offset, W, last, "vgg_forward_range");
+    if (rc != ADPST_OK) return rc;
+    return vgg_forward_range(h, image_dev, H, W, acts_dev, pools_dev, first, last, as_stream(stream),
+                             StripGeom{level_widths, pool_col_offset});
 }
 
 int adpst_absmax_update(const float* x_dev, size_t n, uint32_t* slot_dev, adpst_stream_t stream) {
@@ -621,12 +663,22 @@ int adpst_vgg_conv_dgrad(adpst_vgg* h, int i, const float* dpre_dev, int lh, int
 // ReLU mask of conv first - 1 applied -- exactly what the next call takes as grad_in).
 static int vgg_backward_range(adpst_vgg* h, int H, int W, const float* const* acts_dev, const float* const* seeds_dev, int first,
                               int last, const float* grad_in, float* scratch0_dev, float* scratch1_dev, float* out_dev,
-                              cudaStream_t st) {
+                              cudaStream_t st, adpst::StripGeom geom = {nullptr, nullptr}) {
     using namespace adpst;
     float* cur = scratch0_dev;   // holds dLoss/d(pre-activation of conv i)
     float* nxt = scratch1_dev;
     int lh, lw;
-    layer_hw(last, H, W, &lh, &lw);
+    layer_hw(last, H, W, geom, &lh, &lw);
+    // where the gradient w.r.t. the pooled output of conv i lives: pitch and column offset (see StripGeom)
+    auto pooled_geom = [&](int i, int w_i, int* pitch, int* xoff) {
+        *pitch = w_i / 2;
+        *xoff = 0;
+        if (geom.widths != nullptr) {
+            const int l = pools_before(i);
+            *pitch = geom.widths[l + 1];
+            *xoff = geom.pool_xoff[l];
+        }
+    };
     uint32_t* gmax = h->amax + AMAX_GRAD;          // gmax[i]: max|dLoss/d(pre-activation of conv i)|
     bool pooled_top = false;
     for (int j = 0; j < ADPST_VGG_NUM_POOL; ++j) pooled_top |= (kPoolAfter[j] == last);
@@ -645,14 +697,16 @@ static int vgg_backward_range(adpst_vgg* h, int H, int W, const float* const* ac
         ADPST_LAUNCH_CHECK();
     } else if (pooled_top) {
         const size_t items = size_t((lh + 1) / 2) * ((lw + 1) / 2) * (conv_cout(last) / 4);
+        int dpp, dpx;
+        pooled_geom(last, lw, &dpp, &dpx);
         unpool_relu_kernel<<<stream_grid(items), 256, 0, st>>>(acts_dev[last], grad_in, seeds_dev[last], cur, lh, lw,
-                                                               conv_cout(last), gmax + last);
+                                                               conv_cout(last), gmax + last, dpp, dpx);
         ADPST_LAUNCH_CHECK();
     } else {
         ADPST_CUDA_CHECK(cudaMemcpyAsync(cur, grad_in, size_t(lh) * lw * conv_cout(last) * sizeof(float), cudaMemcpyDeviceToDevice, st));
     }
     for (int i = last; i >= (first > 0 ? first : 1); --i) {
-        layer_hw(i, H, W, &lh, &lw);
+        layer_hw(i, H, W, geom, &lh, &lw);
         bool pooled_input = false;
         for (int j = 0; j < ADPST_VGG_NUM_POOL; ++j) pooled_input |= (kPoolAfter[j] == i - 1);
         if (!pooled_input) {
@@ -670,10 +724,12 @@ static int vgg_backward_range(adpst_vgg* h, int H, int W, const float* const* ac
             int rc = launch_conv(h, i, MODE_BWD, cur, nxt, nullptr, nullptr, lh, lw, gmax + i, nullptr, st);
             if (rc != ADPST_OK) return rc;
             int ph, pw;
-            layer_hw(i - 1, H, W, &ph, &pw);
+            layer_hw(i - 1, H, W, geom, &ph, &pw);
             const size_t items = size_t((ph + 1) / 2) * ((pw + 1) / 2) * (conv_cout(i - 1) / 4);
+            int dpp, dpx;
+            pooled_geom(i - 1, pw, &dpp, &dpx);
             unpool_relu_kernel<<<stream_grid(items), 256, 0, st>>>(acts_dev[i - 1], nxt, seeds_dev[i - 1], cur, ph, pw,
-                                                                   conv_cout(i - 1), gmax + i - 1);
+                                                                   conv_cout(i - 1), gmax + i - 1, dpp, dpx);
             ADPST_LAUNCH_CHECK();
         }
     }
@@ -697,12 +753,15 @@ int adpst_vgg_backward(adpst_vgg* h, int H, int W, const float* const* acts_dev,
 
 int adpst_vgg_backward_range(adpst_vgg* h, int H, int W, const float* const* acts_dev, const float* const* seeds_dev, int first,
                              int last, const float* grad_in_dev, float* scratch0_dev, float* scratch1_dev, float* out_dev,
-                             adpst_stream_t stream) {
+                             const int* level_widths, const int* pool_col_offset, adpst_stream_t stream) {
     using namespace adpst;
     ADPST_REQUIRE(h && acts_dev && seeds_dev && scratch0_dev && scratch1_dev && out_dev, "vgg_backward_range: NULL argument");
     ADPST_REQUIRE(first >= 0 && first <= last && last < kNumConv, "vgg_backward_range: bad range %d..%d", first, last);
+    // (the gradient w.r.t. the pooled output of conv `last` lives one level up)
+    int rc = check_strip_geom(level_widths, pool_col_offset, W, last + 1 < kNumConv ? last + 1 : last, "vgg_backward_range");
+    if (rc != ADPST_OK) return rc;
     return vgg_backward_range(h, H, W, acts_dev, seeds_dev, first, last, grad_in_dev, scratch0_dev, scratch1_dev, out_dev,
-                              as_stream(stream));
+                              as_stream(stream), StripGeom{level_widths, pool_col_offset});
 }
 
 const uint32_t* adpst_vgg_grad_absmax(const adpst_vgg* h, int i) {

@@ -1,23 +1,28 @@
 """One large image optimised on several GPUs (BASELINE configs[3]).
 
-The image is cut into column strips, one per rank; a rank stores its strip plus a halo of HALO = 32 image pixels on every
-interior side (halo of a level-l feature map: 32 / 2^l columns: 32, 16, 8, 4, 2 for blocks 1..5).  What a rank needs from
-its neighbours is exchanged, point to point over NVLink, between the SEGMENTS of the network (the five blocks, block4 cut in
-two):
+The image is cut into column strips, one per rank; on every resolution level l (image and block1: 0, block2: 1, ... block5: 4)
+a rank stores its own columns plus LEVEL_HALO[l] = (4, 4, 8, 4, 2) halo columns on every interior side.  What a rank needs
+from its neighbours is exchanged, point to point over NVLink, between the SEGMENTS of the network (the five blocks, block4
+cut in two):
 
   forward    the tensor that leaves a segment (the pooled tensor; conv 9's output inside block4) gets its halo columns
              overwritten with the owner's values, so each segment starts from exact inputs on own + halo.  Inside a segment of
              n convolutions the valid region shrinks by one column per convolution (the local edge is zero padded); the
              backward pass needs the activations' ReLU masks / arg-max routing exact on n halo columns, so a segment may
-             hold n <= halo / 2 convolutions: (2, 2, 4, 2, 2, 1) against halos of (32, 16, 8, 4, 4, 2) columns.
+             hold n <= halo / 2 convolutions: (2, 2, 4, 2, 2, 1) against halos of (4, 4, 8, 4, 4, 2) columns.
   backward   the gradient that flows from a segment into the one below is exact on the own columns only; its halo columns
              are overwritten with the owners' complete values before the lower segment continues.
-  image      after the Adam update the HALO columns next to each interior boundary are refreshed from the owner.
+  image      after the Adam update the halo columns of the image are refreshed from the owner.
 
-Eleven exchanges per iteration (5 forward, 5 backward, 1 image, with both neighbours each), 0.1-2 MB per slab at 3840x2160; the
-redundant convolution work is (own + 2 x 32) / own -- it was (own + 2 x 160) / own with round 1's overlapped strips.
-The only collective is ONE NCCL all-reduce of the flattened per-class Gram partials of the five style layers (each rank sums
-over its OWN pixels; 19.5 MB at K = 8) plus the 4-entry float64 loss accumulator.
+Because the halo of a pooled tensor is overwritten by the neighbour anyway, the halos of two levels are independent: the pool
+of a level-l tensor (own/2 + h_l/2 columns per side) is written INTO the wider level-(l+1) tensor at a column offset
+(adpst_vgg_forward_range's level_widths / pool_col_offset), and levels 0 and 1 -- where most of the work is -- carry 4 columns
+instead of the 32 / 16 that a uniform 2^-l geometry needs for block5's two.  Redundant work at 8 GPUs and 3840 px: 1.7 % on
+block1, 3.3 % on block2, 13 % on blocks 3-5 (round 1's overlapped strips: 67 % everywhere).
+
+Eleven exchanges per iteration (5 forward, 5 backward, 1 image, with both neighbours each), 0.1-2 MB per slab at 3840x2160.
+The only collective is the NCCL all-reduce of the per-class Gram partials of the five style layers (each rank sums over its
+OWN pixels; 19.5 MB at K = 8) plus the 4-entry float64 loss accumulator.
 
 Strip boundaries must be multiples of 16 px so that the pooling grids and the bilinear mask resizing of every layer align
 with the global image (restricting a resized mask to the own columns is then exact).
@@ -33,38 +38,80 @@ from .components.VGG19.model import POOL_AFTER, SEGMENTS, StyleContentModel, VGG
 from .components.loss import Loss
 from .style_transfer import Adam, CONTENT_LAYERS, STYLE_LAYERS
 
-HALO = 32
+LEVEL_HALO = (4, 4, 8, 4, 2)            # halo columns per interior side on resolution level 0..4
+HALO = LEVEL_HALO[0]                    # ... of the image
+
+
+def _level_convs():
+    """For every resolution level: the sizes of the network segments on it (number of convolutions between two exchanges)."""
+    out = [[] for _ in range(5)]
+    for first, last in SEGMENTS:
+        out[sum(1 for p in POOL_AFTER if p < first)].append(last - first + 1)
+    return out
 
 
 class Tile:
-    """Column strip of a W-pixel-wide image: own = [own_lo, own_hi), stored = [ext_lo, ext_hi) (own + halo)."""
+    """Column strip of a W-pixel-wide image on every resolution level: own columns [own_lo, own_hi) of the image, and per level
+    l the local tensor layout  [left halo | own >> l | right halo]  with halos[l] columns on interior sides, none at the
+    image border."""
 
-    def __init__(self, W, rank, world, halo=HALO):
+    def __init__(self, W, rank, world, halos=LEVEL_HALO):
         if W % (16 * world) != 0:
             raise ValueError("image width %d must be a multiple of 16 x %d ranks" % (W, world))
-        if world > 1 and W // world < halo:
-            raise ValueError("strips of %d px are narrower than the %d-px halo" % (W // world, halo))
-        self.W, self.rank, self.world, self.halo = W, rank, world, halo
+        halos = tuple(int(h) for h in halos)
+        self.W, self.rank, self.world, self.halos = W, rank, world, halos
         self.own_lo, self.own_hi = rank * W // world, (rank + 1) * W // world
-        self.ext_lo, self.ext_hi = max(0, self.own_lo - halo), min(W, self.own_hi + halo)
-        self.local_w = self.ext_hi - self.ext_lo
+        own = self.own_hi - self.own_lo
+        convs = _level_convs()
+        for l in range(5):
+            if world > 1 and (own >> l) < halos[l]:
+                raise ValueError("strips of %d px are too narrow for a %d-column halo on level %d" % (own, halos[l], l))
+            if any(halos[l] < 2 * n for n in convs[l]):
+                raise ValueError("level %d: %d halo columns cannot carry segments of %s convolutions" % (l, halos[l], convs[l]))
+            if l < 4 and (halos[l] % 2 or 2 * halos[l + 1] < convs[l][-1]):
+                raise ValueError("level %d: halos %s do not line up with the pooling grid" % (l, halos))
+        self.has_left, self.has_right = rank > 0, rank < world - 1
+        self.left = tuple(h if self.has_left else 0 for h in halos)
+        self.right = tuple(h if self.has_right else 0 for h in halos)
+        self.widths = tuple(self.left[l] + (own >> l) + self.right[l] for l in range(5))
+        if len(set(self.widths)) != 5:
+            raise ValueError("strip geometry %s: two levels have the same width" % (self.widths,))
+        # column where the 2x2 pool of a level-l tensor starts inside the level-(l+1) tensor
+        self.pool_xoff = tuple(self.left[l + 1] - self.left[l] // 2 for l in range(4))
+        self.halo = halos[0]
+        self.ext_lo, self.ext_hi = self.own_lo - self.left[0], self.own_hi + self.right[0]
+        self.local_w = self.widths[0]
+        # the segmentation masks are kept at full resolution for the widest footprint of any level
+        reach = max(h << l for l, h in enumerate(halos))
+        self.mask_lo = self.own_lo - (reach if self.has_left else 0)
+        self.mask_hi = self.own_hi + (reach if self.has_right else 0)
 
-    def _factor(self, w_layer):
-        f = self.local_w // w_layer
-        if f * w_layer != self.local_w or f & (f - 1):
-            raise ValueError("layer width %d does not divide the strip width %d by a power of two" % (w_layer, self.local_w))
-        return f
+    def geom(self):
+        """(level widths, pool column offsets) for adpst_vgg_forward_range / _backward_range; None for a single strip."""
+        return None if self.world == 1 else (self.widths, self.pool_xoff)
+
+    def level(self, w_layer):
+        try:
+            return self.widths.index(int(w_layer))
+        except ValueError:
+            raise ValueError("no level of this strip is %d columns wide (%s)" % (w_layer, self.widths))
 
     def own_cols(self, w_layer):
-        """Own column range in the coordinates of a layer whose local width is w_layer."""
-        f = self._factor(w_layer)
-        return (self.own_lo - self.ext_lo) // f, (self.own_hi - self.ext_lo) // f
+        """Own column range in the coordinates of a tensor that is w_layer columns wide."""
+        l = self.level(w_layer)
+        return self.left[l], self.left[l] + ((self.own_hi - self.own_lo) >> l)
 
     def global_cols(self, w_layer):
-        return self.W // self._factor(w_layer)
+        return self.W >> self.level(w_layer)
 
     def halo_cols(self, w_layer):
-        return self.halo // self._factor(w_layer)
+        return self.halos[self.level(w_layer)]
+
+    def mask_cols(self, w_layer):
+        """Columns of the cropped full-resolution masks (crop_masks) that a tensor of w_layer columns covers."""
+        l = self.level(w_layer)
+        a = (self.own_lo - (self.left[l] << l)) - self.mask_lo
+        return a, a + (self.widths[l] << l)
 
     def own_masks(self, masks, K, h, w, device):
         """masks (K, h*w) or None  ->  masks restricted to the own columns (K, h*w)."""
@@ -77,6 +124,12 @@ class Tile:
 
     def crop(self, full_nhwc):
         return full_nhwc[:, :, self.ext_lo:self.ext_hi].contiguous()
+
+    def crop_masks(self, mask):
+        """mask (H, W) or (1, H, W, 1) (mask_for_tf): the columns kept at full resolution, same rank."""
+        if mask.dim() == 4:
+            return mask[:, :, self.mask_lo:self.mask_hi].contiguous()
+        return mask[:, self.mask_lo:self.mask_hi].contiguous()
 
 
 # ----------------------------------------------------------------------------------------------------------------
@@ -232,19 +285,17 @@ class ThreadComm:
         return recv
 
 
-def exchange_plan(H, local_w, halo, last_layer):
+def exchange_plan(H, tile, last_layer):
     """(rows, halo columns, channels) of the tensors whose halos are exchanged in one step, in order: the tensors that leave
     the network segments on the way up, the gradients w.r.t. the same tensors on the way down, the image."""
     up = []
     for first, last in SEGMENTS:
         if last >= last_layer:
             break
-        if last in POOL_AFTER:
-            h, w, c = VGG19Handle.pool_shape(POOL_AFTER.index(last), H, local_w)
-        else:
-            h, w, c = VGG19Handle.conv_shape(last, H, local_w)
-        up.append((h, halo // (local_w // w), c))
-    return up + up[::-1] + [(H, halo, 3)]
+        level = sum(1 for p in POOL_AFTER if p <= last)
+        c = VGG19Handle.conv_shape(last, H, tile.local_w)[2]
+        up.append((H >> level, tile.halos[level], c))
+    return up + up[::-1] + [(H, tile.halos[0], 3)]
 
 
 class PeerHalo:
@@ -365,12 +416,14 @@ class TiledStyleTransfer:
         self.style_tile = Tile(int(style.shape[2]), rank, world)
         c_loc = self.tile.crop(content).to(dev)
         s_loc = self.style_tile.crop(style).to(dev)
-        cm = None if content_masks is None else [self.tile.crop(torch.as_tensor(m)) for m in content_masks]
-        sm = None if style_masks is None else [self.style_tile.crop(torch.as_tensor(m)) for m in style_masks]
+        cm = None if content_masks is None else [self.tile.crop_masks(torch.as_tensor(m)) for m in content_masks]
+        sm = None if style_masks is None else [self.style_tile.crop_masks(torch.as_tensor(m)) for m in style_masks]
         self.extractor = StyleContentModel(CONTENT_LAYERS, STYLE_LAYERS, shape=(None, None, 3), weights=vgg_weights, device=dev)
         # the targets are features of strips as well: same block-wise forward pass with halo exchange
-        content_target = self.extractor.forward_blocks(c_loc, self._exchanger(self.tile), reuse=False)['content']
-        style_target = self.extractor.forward_blocks(s_loc, self._exchanger(self.style_tile), reuse=False)['style']
+        content_target = self.extractor.forward_blocks(c_loc, self._exchanger(self.tile), reuse=False,
+                                                       geom=self.tile.geom())['content']
+        style_target = self.extractor.forward_blocks(s_loc, self._exchanger(self.style_tile), reuse=False,
+                                                     geom=self.style_tile.geom())['style']
         self.loss = Loss(content_target, style_target, args, cm, sm, matting=matting, tile=self.tile, style_tile=self.style_tile)
         if args.regularization_weight > 0:
             self.loss.initialize_matting_laplacian(c_loc[0].to(torch.float64))
@@ -395,7 +448,7 @@ class TiledStyleTransfer:
 
     def mailbox_bytes(self):
         """Bytes per mailbox side that the exchanges of one step occupy."""
-        plan = exchange_plan(int(self.image.shape[1]), self.tile.local_w, self.tile.halo, self.extractor.last_index)
+        plan = exchange_plan(int(self.image.shape[1]), self.tile, self.extractor.last_index)
         return sum(r * h * c * 4 for r, h, c in plan)
 
     def _exchanger(self, tile, peer=False):
@@ -433,8 +486,9 @@ class TiledStyleTransfer:
         how = ("two kernels per exchange over peer memory: stores into the neighbour's mailbox through NVLink + release flag, "
                "then wait + copy into the halo columns" if self.halo is not None else "NCCL batched send/recv")
         return ("halo exchange between the six network segments (forward activations, backward gradients) and of the image "
-                "border after the update (%d px halo; %s), one NCCL all-reduce of the flattened Gram partials (%.1f MB) + float64[4] "
-                "loss accumulator" % (HALO, how, 4e-6 * (self._flat.numel() if self._flat is not None else 0)))
+                "border after the update (halo columns per resolution level %s; %s), NCCL all-reduce of the Gram partials (%.1f MB, "
+                "started as each layer's partial is complete) + float64[4] loss accumulator"
+                % (list(self.tile.halos), how, 4e-6 * (self._flat.numel() if self._flat is not None else 0)))
 
     def exchange_bytes(self):
         """Bytes this rank handed to the communication layer in the latest step."""
@@ -501,7 +555,8 @@ class TiledStyleTransfer:
         comm_ms = (sum(a.elapsed_time(b) for a, b in events) - sum(a.elapsed_time(b) for a, b in hidden)) / steps + reduce_ms
         own = self.tile.own_hi - self.tile.own_lo
         return {"ms_per_step": total, "communication_ms": comm_ms, "allreduce_ms": reduce_ms, "compute_ms": total - comm_ms,
-                "host_enqueue_ms": host_ms, "redundant_column_factor": self.tile.local_w / own}
+                "host_enqueue_ms": host_ms, "redundant_column_factor": self.tile.local_w / own,
+                "redundant_column_factor_blocks345": self.tile.widths[2] / (own >> 2)}
 
     def own_strip(self):
         lo, hi = self.tile.own_cols(self.tile.local_w)
@@ -560,7 +615,8 @@ class TiledStyleTransfer:
                         waits.append(self.comm.reduce_start(G))
             if last >= self._last_exchange_layer:
                 loss.partial_image()
-        outputs = self.extractor.forward_blocks(self.image, ex, reuse=True, overlap=None if first_step else fwd_overlap)
+        outputs = self.extractor.forward_blocks(self.image, ex, reuse=True, overlap=None if first_step else fwd_overlap,
+                                                geom=self.tile.geom())
         if first_step:
             loss.prepare(outputs)                       # per-layer state (idempotent), then one buffer behind all Gram partials
             self._flatten_partials()

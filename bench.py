@@ -616,9 +616,9 @@ def tiled_record(D, H, W, K, steps, warmup, tv_weight, check_parity=True, graph=
     e1.record(); D.barrier()
     ms = D.max_ms(e0.elapsed_time(e1))
     t = job.tile
-    rec = {"config": "configs[3]: one %dx%d image, %d classes, column strips of %d px + %d px halo per interior side (local width "
-                     "%d) over %d GPU(s); per step: %s" % (W, H, K, W // D.world, tiled.HALO if D.world > 1 else 0, t.local_w,
-                                                           D.world, job.describe_exchange()),
+    rec = {"config": "configs[3]: one %dx%d image, %d classes, column strips of %d px + %s halo columns per interior side on the five "
+                     "resolution levels (local widths %s) over %d GPU(s); per step: %s"
+                     % (W, H, K, W // D.world, list(t.halos) if D.world > 1 else 0, list(t.widths), D.world, job.describe_exchange()),
            "scaling": "strong", "n_gpus": D.world, "value": steps / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms / steps,
            "steps": steps, "halo_transport": transport if D.world > 1 else "none", "launch": ("one CUDA graph per rank and step (kernels + NCCL send/recv + all-reduce)"
                                       if (graph and D.world > 1) else "eager launches"),
@@ -643,6 +643,27 @@ def tiled_record(D, H, W, K, steps, warmup, tv_weight, check_parity=True, graph=
     del job
     torch.cuda.empty_cache()
     return rec
+
+
+class _Deadline:
+    """Give up on a multi-GPU section that hangs: after `seconds` rank 0 (the rank that got `line`) prints the line it has,
+    with the reason, and every rank leaves the process."""
+
+    def __init__(self, seconds, line):
+        self.timer = threading.Timer(seconds, self._fire, args=(seconds, line))
+        self.timer.daemon = True
+        self.timer.start()
+
+    @staticmethod
+    def _fire(seconds, line):
+        if line is not None:
+            line["tiled_4k"] = {"error": "not finished after %d s; the other records of this line are complete" % seconds}
+            print(json.dumps(line))
+            sys.stdout.flush()
+        os._exit(0 if line is not None else 5)
+
+    def cancel(self):
+        self.timer.cancel()
 
 
 # ----------------------------------------------------------------------------------------------------------------
@@ -743,10 +764,25 @@ def run_ours(args):
         del loss, opt
         torch.cuda.empty_cache()
         D.barrier()
-        rec = tiled_record(D, 2160, 3840, K, max(3, min(args.steps, 10)), 3, args.tv_weight, graph=not args.no_tiled_graph, halo=args.halo)
         if rank == 0:
-            extras["tiled_4k"] = rec
             out.update(extras)
+        # The tiled record is the last thing measured and the only part of the line whose kernels wait for OTHER GPUs (a pull
+        # waits for the neighbour's push): if it does not finish within its budget every rank gives up, and rank 0 still
+        # prints the line it has (with the reason) instead of losing the run.
+        guard = _Deadline(args.tiled_budget_s, out if rank == 0 else None)
+        try:
+            rec = tiled_record(D, 2160, 3840, K, max(3, min(args.steps, 10)), 3, args.tv_weight, graph=not args.no_tiled_graph,
+                               halo=args.halo)
+        except Exception as e:                          # (a CUDA error is sticky: nothing below touches the device)
+            guard.cancel()
+            if rank == 0:
+                out["tiled_4k"] = {"error": "%s: %s" % (type(e).__name__, str(e)[:300])}
+                print(json.dumps(out))
+                sys.stdout.flush()
+            os._exit(0 if rank == 0 else 5)
+        guard.cancel()
+        if rank == 0:
+            out["tiled_4k"] = rec
     D.close()
     if rank == 0:
         if world == 1 and not args.no_cpu_baseline:
@@ -849,6 +885,8 @@ def main():
     ap.add_argument("--tiled", action="store_true", help="configs[3] only: one large image tiled spatially over the GPUs")
     ap.add_argument("--no-tiled-graph", dest="no_tiled_graph", action="store_true",
                     help="time eager tiled steps instead of one captured CUDA graph per rank")
+    ap.add_argument("--tiled-budget-s", dest="tiled_budget_s", type=float, default=240.0,
+                    help="default line: seconds after which the tiled_4k record is abandoned (see _Deadline)")
     ap.add_argument("--halo", choices=("peer", "nccl"), default="peer",
                     help="tiled runs: halo columns through peer-memory mailboxes (our kernels) or NCCL send/recv")
     ap.add_argument("--tiled-h", dest="tiled_h", type=int, default=2160)

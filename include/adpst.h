@@ -116,9 +116,14 @@ int adpst_vgg_forward(adpst_vgg* h, const float* image_dev, int H, int W, float*
 
 /* The same for convolutions first..last only (spatially tiled runs exchange halo columns between blocks): the input of conv
  * `first` is image_dev (first == 0), pools_dev[j] if a pool precedes it, else acts_dev[first-1].  pools_dev[j] may be NULL for
- * pools that are not wanted. */
+ * pools that are not wanted.
+ * level_widths / pool_col_offset (host arrays of 5 and 4 ints, or both NULL): column geometry of a strip whose halo is not the
+ * same multiple of 2^-l on every resolution level l.  Tensors of level l are level_widths[l] columns wide (level_widths[0] ==
+ * W); the 2x2 max-pool of a level-l tensor has level_widths[l] / 2 columns and is stored from column pool_col_offset[l] of the
+ * level-(l+1) tensor on (the columns around it are the caller's: they hold what the neighbouring strip sent). */
 int adpst_vgg_forward_range(adpst_vgg* h, const float* image_dev, int H, int W, float* const* acts_dev,
-                            float* const* pools_dev, int first, int last, adpst_stream_t stream);
+                            float* const* pools_dev, int first, int last, const int* level_widths, const int* pool_col_offset,
+                            adpst_stream_t stream);
 
 /* Convolution kernel family used by this handle: 0 = tcgen05 3xFP16 implicit GEMM, float32-accurate (default;
  * block1_conv1 and the gradient to the image always use the CUDA-core kernels), 1 = exact-float32 CUDA-core kernels
@@ -158,10 +163,11 @@ int adpst_vgg_backward(adpst_vgg* h, int H, int W, const float* const* acts_dev,
  *        otherwise: grad_in_dev = dLoss/d(pre-activation of conv last) (already ReLU-masked), with its max|.| in the slot
  *        adpst_vgg_grad_absmax(h, last) (left there by the call that produced it; adpst_absmax_update after patching it).
  * Exit   first == 0: out_dev = dLoss/d(image);  conv `first` follows a pool: out_dev = dLoss/d(that pooled tensor);
- *        otherwise: out_dev = dLoss/d(pre-activation of conv first-1) (seed and ReLU mask of conv first-1 applied). */
+ *        otherwise: out_dev = dLoss/d(pre-activation of conv first-1) (seed and ReLU mask of conv first-1 applied).
+ * level_widths / pool_col_offset: as for adpst_vgg_forward_range (a gradient w.r.t. a pooled tensor has that tensor's layout). */
 int adpst_vgg_backward_range(adpst_vgg* h, int H, int W, const float* const* acts_dev, const float* const* seeds_dev, int first,
                              int last, const float* grad_in_dev, float* scratch0_dev, float* scratch1_dev, float* out_dev,
-                             adpst_stream_t stream);
+                             const int* level_widths, const int* pool_col_offset, adpst_stream_t stream);
 /* slot holding max|dLoss/d(pre-activation of conv i)| of the latest backward pass (device pointer). */
 const uint32_t* adpst_vgg_grad_absmax(const adpst_vgg* h, int i);
 

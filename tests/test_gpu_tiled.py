@@ -48,7 +48,7 @@ def test_tiled_matches_single_device(world, W, K, halo, synth):
     ranks = tiled.make_emulated(content, style, args, cm, sm, weights, world, halo=halo)
     assert all((r.halo is not None) == (halo == "peer") for r in ranks)
     got = tiled.run_emulated(ranks, 3)
-    assert ranks[0].exchange_bytes()["exchanges"] == 11 and all(r.tile.halo == tiled.HALO == 32 for r in ranks)
+    assert ranks[0].exchange_bytes()["exchanges"] == 11 and all(r.tile.halos == tiled.LEVEL_HALO == (4, 4, 8, 4, 2) for r in ranks)
     # Iteration 0 evaluates identical images: 2e-5.  Afterwards the images themselves may differ in a few pixels: Adam's first
     # steps are +-lr * sign(g), so a last-bit difference in a gradient that is ~0 moves that pixel by 2 lr (the image check
     # below counts such flips); the loss values of later iterations are therefore only comparable to ~1e-4.

@@ -133,31 +133,50 @@ def test_reference_arm_non_zero_ranks_exit_quietly():
 def test_tile_geometry():
     """Spatial tiling (BASELINE configs[3]): strip / halo arithmetic, CPU only."""
     tiled = importlib.import_module(PKG_NAME + ".tiled")
-    t = tiled.Tile(3840, 3, 8)
-    assert (t.own_lo, t.own_hi, t.ext_lo, t.ext_hi, t.local_w) == (1440, 1920, 1408, 1952, 544)
-    assert t.own_cols(544) == (32, 512) and t.own_cols(34) == (2, 32) and t.global_cols(34) == 240 and t.halo_cols(34) == 2
-    t0 = tiled.Tile(3840, 0, 8)
-    assert (t0.ext_lo, t0.ext_hi) == (0, 512) and t0.own_cols(512) == (0, 480)
+    vgg = importlib.import_module(PKG_NAME + ".components.VGG19.model")
+    assert tiled.LEVEL_HALO == (4, 4, 8, 4, 2)
+    t = tiled.Tile(3840, 3, 8)                                                  # an interior strip of a 3840-px image
+    assert (t.own_lo, t.own_hi, t.ext_lo, t.ext_hi, t.local_w) == (1440, 1920, 1436, 1924, 488)
+    assert t.widths == (488, 248, 136, 68, 34) and t.pool_xoff == (2, 6, 0, 0)
+    assert t.own_cols(488) == (4, 484) and t.own_cols(136) == (8, 128) and t.own_cols(34) == (2, 32)
+    assert t.global_cols(34) == 240 and t.halo_cols(34) == 2 and t.halo_cols(248) == 4
+    assert (t.mask_lo, t.mask_hi) == (1408, 1952)                               # widest footprint: 8 << 2 = 4 << 3 = 2 << 4 = 32 px
+    assert t.mask_cols(488) == (28, 516) and t.mask_cols(136) == (0, 544) and t.mask_cols(248) == (24, 520)
+    t0 = tiled.Tile(3840, 0, 8)                                                 # the left edge: no halo on the left
+    assert (t0.ext_lo, t0.ext_hi, t0.widths, t0.pool_xoff) == (0, 484, (484, 244, 128, 64, 32), (0, 0, 0, 0))
+    assert t0.own_cols(484) == (0, 480) and t0.mask_cols(244) == (0, 488)
+    t1 = tiled.Tile(3840, 0, 1)                                                 # a single strip: the plain geometry
+    assert t1.geom() is None and t1.widths == (3840, 1920, 960, 480, 240) and t1.own_cols(960) == (0, 960)
     with pytest.raises(ValueError):
         tiled.Tile(1000, 0, 8)
-    # every pixel is owned by exactly one rank; the halo of a level-l tensor (HALO / 2^l columns) must cover twice the number
-    # of convolutions of the segment that reads it (forward validity shrinks by one column per convolution, the backward pass
-    # needs the ReLU masks that many columns out)
+    with pytest.raises(ValueError):
+        tiled.Tile(3840, 3, 8, halos=(4, 4, 6, 4, 2))                           # block3 has four convolutions: needs 8
+    with pytest.raises(ValueError):
+        t.own_cols(100)
+    # every pixel is owned by exactly one rank; on every level the halo covers twice the number of convolutions of each segment
+    # (forward validity shrinks by one column per convolution, the backward pass needs the ReLU masks that many columns out),
+    # and the un-pooled gradient (2 x the pooled level's halo) reaches as far as the segment below needs it
     owned = np.zeros(3840, int)
     for r in range(8):
         tr = tiled.Tile(3840, r, 8)
         owned[tr.own_lo:tr.own_hi] += 1
-        assert tr.own_lo - tr.ext_lo in (0, tiled.HALO) and tr.ext_hi - tr.own_hi in (0, tiled.HALO)
-    assert (owned == 1).all() and tiled.HALO % 16 == 0
-    vgg = importlib.import_module(PKG_NAME + ".components.VGG19.model")
+        for l in range(4):                                                      # the pool of level l fits inside level l + 1
+            assert tr.pool_xoff[l] >= 0 and tr.pool_xoff[l] + tr.widths[l] // 2 <= tr.widths[l + 1]
+            assert (tr.own_lo >> l) % 2 == 0 and tr.left[l] % 2 == 0           # 2x2 windows line up with the global grid
+            lo_next, _ = tr.own_cols(tr.widths[l + 1])
+            assert tr.pool_xoff[l] + tr.own_cols(tr.widths[l])[0] // 2 == lo_next
+    assert (owned == 1).all()
     for first, last in vgg.SEGMENTS:
         level = sum(1 for p in vgg.POOL_AFTER if p < first)
-        assert tiled.HALO >> level >= 2 * (last - first + 1), (first, last)
+        n = last - first + 1
+        assert tiled.LEVEL_HALO[level] >= 2 * n, (first, last)
+        if last in vgg.POOL_AFTER:
+            assert 2 * tiled.LEVEL_HALO[level + 1] >= n, (first, last)
     # the tensors exchanged in one step of a 3840x2160 run (interior strip): five on the way up, their gradients on the way
     # down, the image; the mailbox of tiled.PeerHalo is sized from this list
-    plan = tiled.exchange_plan(2160, 544, tiled.HALO, 12)
-    up = [(1080, 16, 64), (540, 8, 128), (270, 4, 256), (270, 4, 512), (135, 2, 512)]
-    assert plan == up + up[::-1] + [(2160, 32, 3)]
+    plan = tiled.exchange_plan(2160, t, 12)
+    up = [(1080, 4, 64), (540, 8, 128), (270, 4, 256), (270, 4, 512), (135, 2, 512)]
+    assert plan == up + up[::-1] + [(2160, 4, 3)]
     assert all((hl * c) % 4 == 0 for _, hl, c in plan)                         # float4 rows in the push / pull kernels
     assert sum(r * hl * c * 4 for r, hl, c in plan) < 32 << 20
 
@@ -169,28 +188,29 @@ import torch, torch.distributed as dist
 dist.init_process_group("gloo", rank=int(os.environ["RANK"]), world_size=int(os.environ["WORLD_SIZE"]))
 rank, world = dist.get_rank(), dist.get_world_size()
 tiled = importlib.import_module(%r + ".tiled")
-H, W = 6, 16 * 8 * world                       # strips of 128 px >= HALO
+H, W = 6, 16 * 8 * world                       # strips of 128 px
 comm = tiled.GlooComm(rank, world)
 t = tiled.Tile(W, rank, world)
 ok = True
 for level, C in ((0, 3), (2, 5), (4, 2)):      # the image, a block-3 input, a block-5 input
     f = 1 << level
-    w_l, gw = t.local_w // f, W // f
+    w_l, gw = t.widths[level], W // f
+    e_lo, e_hi = t.own_lo // f - t.left[level], t.own_hi // f + t.right[level]      # this level's columns, global coordinates
     glob = torch.arange(H * gw * C, dtype=torch.float32).reshape(1, H, gw, C)
-    loc = glob[:, :, t.ext_lo // f:t.ext_hi // f].clone()
+    loc = glob[:, :, e_lo:e_hi].clone()
     lo, hi = t.own_cols(w_l)
     hl = t.halo_cols(w_l)
     loc[0, :, :lo] = -1.0                      # stale halos
     loc[0, :, hi:] = -1.0
     loc[0, :, lo:hi] += 1000.0 * (rank + 1)    # "updated" own columns
     recv = comm.exchange(loc, lo, hi, hl)
-    expect = glob[:, :, t.ext_lo // f:t.ext_hi // f].clone()
+    expect = glob[:, :, e_lo:e_hi].clone()
     for r in range(world):
-        a, b = max(r * gw // world, t.ext_lo // f), min((r + 1) * gw // world, t.ext_hi // f)
+        a, b = max(r * gw // world, e_lo), min((r + 1) * gw // world, e_hi)
         if a < b:
-            expect[0, :, a - t.ext_lo // f:b - t.ext_lo // f] += 1000.0 * (r + 1)
+            expect[0, :, a - e_lo:b - e_lo] += 1000.0 * (r + 1)
     ok = ok and bool(torch.equal(loc, expect)) and len(recv) == (rank > 0) + (rank < world - 1)
-    ok = ok and hl == tiled.HALO // f and (hi - lo) == W // world // f
+    ok = ok and hl == tiled.LEVEL_HALO[level] and (hi - lo) == W // world // f and loc.shape[2] == w_l
 # the Gram partials: ONE flat float32 buffer + the float64 accumulator, summed over the ranks
 flat = torch.full((1000,), float(rank + 1)); acc = torch.tensor([1.0, 0.0, 2.0 * rank, 0.5], dtype=torch.float64)
 comm.reduce_sum([flat, acc])
