@@ -111,7 +111,7 @@ w("* `sass_opcodes.txt`: per-kernel counts of UTCHMMA / UTMALDG / LDTM / STTM / 
   "  (`scripts/sass_opcodes.py`).\n")
 
 w("\n## 4. Multi-GPU (plain runs of the default `bench.py` line under torch.distributed.run)\n\n"
-  "| GPUs | headline iter/s (one 1024^2 pair per GPU) | e2e | pairs_64x512 iter/s | set-up ms/pair | tiled_4k iter/s | ms/step | halo transport | comm ms (of which all-reduce) | redundant columns | parity vs 1 GPU |\n"
+  "| GPUs | headline iter/s (one 1024^2 pair per GPU) | e2e | pairs_64x512 iter/s | set-up ms/pair | tiled_4k iter/s | ms/step | halo transport | comm ms (of which all-reduce) | redundant columns, blocks 1 / 3-5 | parity vs 1 GPU |\n"
   "|---:|---:|---:|---:|---:|---:|---:|---|---:|---:|---:|\n")
 for n, name in ((1, "r2_bench_1gpu.json"), (2, "r2_bench_2gpu.json"), (4, "r2_bench_4gpu.json"), (8, "r2_bench_8gpu.json")):
     d = jline(name)
@@ -124,9 +124,9 @@ for n, name in ((1, "r2_bench_1gpu.json"), (2, "r2_bench_2gpu.json"), (4, "r2_be
       % (n, d["value"], d["e2e"]["value"], pr.get("value", 0), pr.get("setup_ms_per_pair", 0), t4.get("value", 0), t4.get("ms_per_step", 0),
          t4.get("halo_transport", "-"),
          ("%.2f (%.2f)" % (bd["communication_ms"], bd.get("allreduce_ms", float("nan")))) if bd else "-",
-         ("%.2f" % bd["redundant_column_factor"]) if bd else "-",
+         ("%.3f / %.3f" % (bd["redundant_column_factor"], bd.get("redundant_column_factor_blocks345", bd["redundant_column_factor"]))) if bd else "-",
          ("%.1e" % par["max_rel_loss_diff"]) if par else "-"))
-w("\n`tiled_4k`: one 3840x2160 image in column strips with a 32-px halo; per step eleven halo exchanges between the six network\n"
+w("\n`tiled_4k`: one 3840x2160 image in column strips with 4, 4, 8, 4, 2 halo columns on the five resolution levels; per step eleven halo exchanges between the six network\n"
   "segments (activations up, gradients down, the image border) by our push/pull kernels over NVLink peer memory, and NCCL\n"
   "all-reduces of the Gram partials (started as each partial is complete).  The timed steps replay one CUDA graph per rank.\n"
   "`comm ms` comes from a short EAGER run with CUDA events around every exchange / all-reduce call (work enqueued inside an\n"
