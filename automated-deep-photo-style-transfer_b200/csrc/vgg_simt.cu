@@ -271,6 +271,9 @@ maxpool2_kernel(const float* __restrict__ X, float* __restrict__ P, int H, int W
 }
 
 // dPre[pos] = Y[pos] > 0 ? ((pos is the first max of its window ? dP[window] : 0) + seed[pos]) : 0
+// (Tried in round 2: arg-max nibbles written by the forward pass's fused-pool epilogue, so that this kernel reads dP and the
+// codes only.  It took 159 us instead of 244 us over the four pools at 1024^2, but the two extra shuffles per element in the
+// convolution epilogue cost more than that (block1_conv2 forward 333 -> 417 us): not kept.)
 // One thread per (2x2 cell, 4 channels): every Y / seed / dPre element is touched exactly once.  Cells cut by an odd H or W
 // are not pooling windows (VALID pooling); their pixels only see the seed.
 __global__ void __launch_bounds__(256)

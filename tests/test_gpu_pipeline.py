@@ -91,6 +91,26 @@ def test_vgg_backward_matches_autograd(H, W, weights, synth):
     assert _rel(g.cpu().numpy(), gr.numpy()) < TOL
 
 
+@pytest.mark.parametrize("H,W", [(32, 32), (37, 51)])
+def test_vgg_backward_with_seeds_on_every_layer(H, W, weights, synth):
+    """Seeds on all 13 convolutions: the layers in front of a max-pool then carry a seed as well (the un-pooling kernel adds it
+    before the ReLU mask; the six tapped layers of the real objective leave those layers without one)."""
+    vgg = _m("components.VGG19.model")
+    names = [n for n, _, _ in synth.CONV_LAYERS]
+    ext = vgg.StyleContentModel(names[:1], names[1:], weights=weights)
+    img = synth.image(H, W, 5)
+    out = ext(torch.as_tensor(img).cuda())
+    rng = np.random.default_rng(6)
+    flat = dict(out["content"]); flat.update(out["style"])
+    seeds = {n: rng.standard_normal(tuple(t.shape)).astype(np.float32) for n, t in flat.items()}
+    g = ext.backward({n: torch.as_tensor(s).cuda() for n, s in seeds.items()})
+    x = torch.as_tensor(img, dtype=torch.float64).requires_grad_(True)
+    ref = model.vgg_forward(x, weights)
+    tot = sum((ref[n] * torch.as_tensor(s, dtype=torch.float64)).sum() for n, s in seeds.items())
+    (gr,) = torch.autograd.grad(tot, x)
+    assert _rel(g.cpu().numpy(), gr.numpy()) < TOL
+
+
 @pytest.mark.parametrize("path", ["tensor", "simt"])
 @pytest.mark.parametrize("hw,C,K", [((64, 64), 64, 3), ((25, 40), 128, 1), ((21, 37), 256, 4), ((16, 16), 512, 2),
                                     ((40, 48), 128, 8)])
