@@ -623,10 +623,13 @@ def tiled_record(D, H, W, K, steps, warmup, tv_weight, check_parity=True, graph=
            "steps": steps, "halo_transport": transport if D.world > 1 else "none", "launch": ("one CUDA graph per rank and step (kernels + NCCL send/recv + all-reduce)"
                                       if (graph and D.world > 1) else "eager launches"),
            "bytes_exchanged_per_step": job.exchange_bytes(), "final_total_loss": float(d["Total loss"]),
-           "breakdown_max_over_ranks": dict(breakdown, what="EAGER steps, device ms per step: halo exchanges (packing, NCCL "
-                                                               "point-to-point, unpacking) + Gram all-reduce vs everything else; "
-                                                               "host_enqueue_ms = host time to enqueue one eager step; "
-                                                               "redundant_column_factor = (own + halo columns) / own columns"),
+           "breakdown_max_over_ranks": dict(breakdown, what="three EAGER steps, device ms per step, each entry the max over the ranks: "
+                                                               "communication_ms = halo exchanges (push + wait + pull kernels, or NCCL "
+                                                               "send/recv with packing; work enqueued inside an exchange window subtracted) "
+                                                               "+ allreduce_ms (the all-reduce that is not overlapped with the forward "
+                                                               "pass); compute_ms = the rest; host_enqueue_ms = host time to enqueue one "
+                                                               "eager step; redundant_column_factor = (own + halo columns) / own columns "
+                                                               "on the image level and on blocks 3-5"),
            "first_iteration_losses": first}
     if check_parity and D.world > 1:
         # the N-rank loss dictionary of iteration 0 against the single-device evaluation of the whole image (rank 0)
