@@ -115,7 +115,13 @@ template <int BN, int MODE> struct TcCfg {
     static constexpr int B_STAGE_BYTES = 2 * B_BYTES;                       // B_hi, B_lo
     static constexpr int OFF_B = A_STAGES * TC_A_BYTES;
     static constexpr int OFF_BARS = OFF_B + B_STAGES * B_STAGE_BYTES;
-    static constexpr int SMEM_BYTES = OFF_BARS + 1024 /*alignment slack*/ + 256 /*barriers*/;
+    // BN = 64 has shared memory to spare: the drain warps transpose their 32 pixel x 32 channel pieces through it so that a
+    // store instruction writes four complete 128-byte lines instead of 32 half sectors 256 bytes apart (the L1 data pipe, which
+    // also carries the transform warps' shared-memory loads, is what these layers wait for)
+    static constexpr bool STAGE_OUT = (BN == 64);
+    static constexpr int OFF_STAGE = OFF_BARS + 256;
+    static constexpr int STAGE_BYTES = STAGE_OUT ? 4 * 32 * 33 * 4 : 0;
+    static constexpr int SMEM_BYTES = OFF_BARS + 1024 /*alignment slack*/ + 256 /*barriers*/ + STAGE_BYTES;
     // tensor memory columns: big0 | big1 | small | A operand slots (each: hi = 32 columns of packed fp16 pairs, lo = 32).
     // BN = 128 fills the 512 columns with two slots; BN = 64 has room for four, which it needs: its MMAs of one stage take
     // 384 clk, less than the round trip  tcgen05.st -> MMA -> commit -> a_free -> next tcgen05.st  of a two-slot ring.
@@ -558,15 +564,43 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             const int tile_w = 1 << tw_log2;
             const int gy = ((tile / tiles_w) << (7 - tw_log2)) + (m >> tw_log2), gx = ((tile % tiles_w) << tw_log2) + (m & (tile_w - 1));
             const bool inb = gy < H && gx < W;
-            if (inb || (MODE == MODE_FWD && pool_out != nullptr)) {        // (pooling shuffles need the whole warp)
+            if (Cfg::STAGE_OUT || inb || (MODE == MODE_FWD && pool_out != nullptr)) {   // (pooling shuffles / the staged store need the whole warp)
                 const size_t rowoff = (size_t(gy) * W + gx) * size_t(Cout) + n0;
+                // STAGE_OUT: the 32 pixel x 32 channel piece of a global tensor laid out like Y, read with coalesced loads (four
+                // pixels x 128 contiguous bytes per instruction) and handed to the pixels' threads through the staging tile
+                [[maybe_unused]] auto gather = [&](const float* T, int c0, float (&v)[32], bool read_only) {
+                    float* stg = reinterpret_cast<float*>(smem + Cfg::OFF_STAGE) + q * (32 * 33);
+                    const int sub = lane >> 3, piece = (lane & 7) * 4;
+                    const int ty0 = (tile / tiles_w) << (7 - tw_log2), tx0 = (tile % tiles_w) << tw_log2;
+                    __syncwarp();
+#pragma unroll
+                    for (int s8 = 0; s8 < 8; ++s8) {
+                        const int pl = 4 * s8 + sub, pm = q * 32 + pl;
+                        const int py = ty0 + (pm >> tw_log2), px = tx0 + (pm & (tile_w - 1));
+                        float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (py < H && px < W) {
+                            const float4* g = reinterpret_cast<const float4*>(T + (size_t(py) * W + px) * size_t(Cout) + n0 + c0 + piece);
+                            t = read_only ? __ldg(g) : *g;
+                        }
+                        float* d = stg + pl * 33 + piece;
+                        d[0] = t.x; d[1] = t.y; d[2] = t.z; d[3] = t.w;
+                    }
+                    __syncwarp();
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) v[j] = stg[lane * 33 + j];
+                };
 #pragma unroll
                 for (int c0 = 0; c0 < BN; c0 += 32) {
                     float r[32];
 #pragma unroll
                     for (int j = 0; j < 32; ++j) r[j] = acc[c0 + j];
                     if (MODE == MODE_STYLE) {
-                        if (seed != nullptr) {                             // accumulate into an existing gradient seed
+                        if (Cfg::STAGE_OUT && seed != nullptr) {           // accumulate into an existing gradient seed (= Y)
+                            float sv[32];
+                            gather(seed, c0, sv, false);
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) r[j] += sv[j];
+                        } else if (seed != nullptr && inb) {
 #pragma unroll
                             for (int j = 0; j < 32; j += 4) {
                                 const float4 sd = *reinterpret_cast<const float4*>(seed + rowoff + c0 + j);
@@ -599,14 +633,24 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                             }
                         }
                     } else {
-                        if (seed != nullptr) {
+                        if (Cfg::STAGE_OUT && seed != nullptr) {
+                            float sv[32];
+                            gather(seed, c0, sv, true);
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) r[j] += sv[j];
+                        } else if (seed != nullptr && inb) {
 #pragma unroll
                             for (int j = 0; j < 32; j += 4) {
                                 const float4 sd = __ldg(reinterpret_cast<const float4*>(seed + rowoff + c0 + j));
                                 r[j] += sd.x; r[j + 1] += sd.y; r[j + 2] += sd.z; r[j + 3] += sd.w;
                             }
                         }
-                        if (mask_src != nullptr) {
+                        if (Cfg::STAGE_OUT && mask_src != nullptr) {
+                            float mv[32];
+                            gather(mask_src, c0, mv, true);
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) r[j] = mv[j] > 0.f ? r[j] : 0.f;
+                        } else if (mask_src != nullptr && inb) {
 #pragma unroll
                             for (int j = 0; j < 32; j += 4) {
                                 const float4 mk = __ldg(reinterpret_cast<const float4*>(mask_src + rowoff + c0 + j));
@@ -618,6 +662,29 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                     if (inb) {
 #pragma unroll
                         for (int j = 0; j < 32; ++j) amax = fmaxf(amax, fabsf(r[j]));
+                    }
+                    if constexpr (Cfg::STAGE_OUT) {
+                        // pixel-major registers -> shared memory (row = pixel, 33-float pitch: conflict-free both ways) -> every
+                        // store instruction writes 4 pixels x 128 contiguous bytes
+                        float* stg = reinterpret_cast<float*>(smem + Cfg::OFF_STAGE) + q * (32 * 33);
+                        __syncwarp();
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) stg[lane * 33 + j] = r[j];
+                        __syncwarp();
+                        const int sub = lane >> 3, piece = (lane & 7) * 4;
+                        const int ty0 = (tile / tiles_w) << (7 - tw_log2), tx0 = (tile % tiles_w) << tw_log2;
+#pragma unroll
+                        for (int s8 = 0; s8 < 8; ++s8) {
+                            const int pl = 4 * s8 + sub;                    // pixel of this warp's 32
+                            const int pm = q * 32 + pl;
+                            const int py = ty0 + (pm >> tw_log2), px = tx0 + (pm & (tile_w - 1));
+                            if (py < H && px < W) {
+                                const float* src = stg + pl * 33 + piece;
+                                *reinterpret_cast<float4*>(Y + (size_t(py) * W + px) * size_t(Cout) + n0 + c0 + piece) =
+                                    make_float4(src[0], src[1], src[2], src[3]);
+                            }
+                        }
+                    } else if (inb) {
 #pragma unroll
                         for (int j = 0; j < 32; j += 4)
                             *reinterpret_cast<float4*>(Y + rowoff + c0 + j) = make_float4(r[j], r[j + 1], r[j + 2], r[j + 3]);
