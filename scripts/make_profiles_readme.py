@@ -111,6 +111,8 @@ w("* `sass_opcodes.txt`: per-kernel counts of UTCHMMA / UTMALDG / LDTM / STTM / 
   "  (`scripts/sass_opcodes.py`).\n")
 
 w("\n## 4. Multi-GPU (plain runs of the default `bench.py` line under torch.distributed.run)\n\n"
+  "The 2-, 4- and 8-GPU lines were taken one commit before the last change to the epilogue of the 64-channel convolutions (a few\n"
+  "percent on two layers); everything multi-GPU is identical.  Different boxes of the pool differ by about +-2.5 % per kernel.\n\n"
   "| GPUs | headline iter/s (one 1024^2 pair per GPU) | e2e | pairs_64x512 iter/s | set-up ms/pair | tiled_4k iter/s | ms/step | halo transport | comm ms (of which all-reduce) | redundant columns, blocks 1 / 3-5 | parity vs 1 GPU |\n"
   "|---:|---:|---:|---:|---:|---:|---:|---|---:|---:|---:|\n")
 for n, name in ((1, "r2_bench_1gpu.json"), (2, "r2_bench_2gpu.json"), (4, "r2_bench_4gpu.json"), (8, "r2_bench_8gpu.json")):
