@@ -110,15 +110,20 @@ template <int BN, int MODE> struct TcCfg {
     // for BN = 64 (block1_conv2 269/279 TFLOP/s instead of 280/285), two B slots + three halo-tile slots for the style
     // gradient (330 us instead of 312 us over the four BN = 128 launches), a second small-term accumulator for BN = 64.
     static constexpr int A_STAGES = 2;
-    static constexpr int B_STAGES = BN == 128 ? 4 : 6;
+    static constexpr int B_STAGES = BN == 128 ? (MODE == MODE_BWD ? 4 : 3) : 6;
     static constexpr int B_BYTES = BN * TC_BK * 2;                          // BN rows x 64 fp16
     static constexpr int B_STAGE_BYTES = 2 * B_BYTES;                       // B_hi, B_lo
     static constexpr int OFF_B = A_STAGES * TC_A_BYTES;
     static constexpr int OFF_BARS = OFF_B + B_STAGES * B_STAGE_BYTES;
-    // BN = 64 has shared memory to spare: the drain warps transpose their 32 pixel x 32 channel pieces through it so that a
-    // store instruction writes four complete 128-byte lines instead of 32 half sectors 256 bytes apart (the L1 data pipe, which
-    // also carries the transform warps' shared-memory loads, is what these layers wait for)
-    static constexpr bool STAGE_OUT = (BN == 64);
+    // The drain warps transpose their 32 pixel x 32 channel pieces through shared memory so that a store instruction writes four
+    // complete 128-byte lines instead of 32 half sectors a pixel apart (the L1 data pipe, which also carries the transform
+    // warps' shared-memory loads, is what the layers with few K chunks wait for).  BN = 128 pays for the staging tile with one B
+    // stage (3 instead of 4).  Forward and style-gradient kernels only (one train step at 1024^2, ncu: forward launches
+    // 1708 + 333 -> 1669 + 313 us, style gradient 318 + 154 -> 306 + 134 us).  The data-gradient kernels keep the direct stores:
+    // their epilogue also loads the ReLU mask and the seed, the __syncwarp()s of the staging tile stop the compiler from issuing
+    // those loads ahead of the chunk loop, and the exposed latency cost more than the stores saved (1764 + 584 -> 1868 + 620 us;
+    // routing the loads through the tile as well: 2031 + 659 us).
+    static constexpr bool STAGE_OUT = (MODE != MODE_BWD);
     static constexpr int OFF_STAGE = OFF_BARS + 256;
     static constexpr int STAGE_BYTES = STAGE_OUT ? 4 * 32 * 33 * 4 : 0;
     static constexpr int SMEM_BYTES = OFF_BARS + 1024 /*alignment slack*/ + 256 /*barriers*/ + STAGE_BYTES;
@@ -566,41 +571,13 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             const bool inb = gy < H && gx < W;
             if (Cfg::STAGE_OUT || inb || (MODE == MODE_FWD && pool_out != nullptr)) {   // (pooling shuffles / the staged store need the whole warp)
                 const size_t rowoff = (size_t(gy) * W + gx) * size_t(Cout) + n0;
-                // STAGE_OUT: the 32 pixel x 32 channel piece of a global tensor laid out like Y, read with coalesced loads (four
-                // pixels x 128 contiguous bytes per instruction) and handed to the pixels' threads through the staging tile
-                [[maybe_unused]] auto gather = [&](const float* T, int c0, float (&v)[32], bool read_only) {
-                    float* stg = reinterpret_cast<float*>(smem + Cfg::OFF_STAGE) + q * (32 * 33);
-                    const int sub = lane >> 3, piece = (lane & 7) * 4;
-                    const int ty0 = (tile / tiles_w) << (7 - tw_log2), tx0 = (tile % tiles_w) << tw_log2;
-                    __syncwarp();
-#pragma unroll
-                    for (int s8 = 0; s8 < 8; ++s8) {
-                        const int pl = 4 * s8 + sub, pm = q * 32 + pl;
-                        const int py = ty0 + (pm >> tw_log2), px = tx0 + (pm & (tile_w - 1));
-                        float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
-                        if (py < H && px < W) {
-                            const float4* g = reinterpret_cast<const float4*>(T + (size_t(py) * W + px) * size_t(Cout) + n0 + c0 + piece);
-                            t = read_only ? __ldg(g) : *g;
-                        }
-                        float* d = stg + pl * 33 + piece;
-                        d[0] = t.x; d[1] = t.y; d[2] = t.z; d[3] = t.w;
-                    }
-                    __syncwarp();
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) v[j] = stg[lane * 33 + j];
-                };
 #pragma unroll
                 for (int c0 = 0; c0 < BN; c0 += 32) {
                     float r[32];
 #pragma unroll
                     for (int j = 0; j < 32; ++j) r[j] = acc[c0 + j];
                     if (MODE == MODE_STYLE) {
-                        if (Cfg::STAGE_OUT && seed != nullptr) {           // accumulate into an existing gradient seed (= Y)
-                            float sv[32];
-                            gather(seed, c0, sv, false);
-#pragma unroll
-                            for (int j = 0; j < 32; ++j) r[j] += sv[j];
-                        } else if (seed != nullptr && inb) {
+                        if (seed != nullptr && inb) {                      // accumulate into an existing gradient seed (= Y)
 #pragma unroll
                             for (int j = 0; j < 32; j += 4) {
                                 const float4 sd = *reinterpret_cast<const float4*>(seed + rowoff + c0 + j);
@@ -633,24 +610,14 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                             }
                         }
                     } else {
-                        if (Cfg::STAGE_OUT && seed != nullptr) {
-                            float sv[32];
-                            gather(seed, c0, sv, true);
-#pragma unroll
-                            for (int j = 0; j < 32; ++j) r[j] += sv[j];
-                        } else if (seed != nullptr && inb) {
+                        if (seed != nullptr && inb) {
 #pragma unroll
                             for (int j = 0; j < 32; j += 4) {
                                 const float4 sd = __ldg(reinterpret_cast<const float4*>(seed + rowoff + c0 + j));
                                 r[j] += sd.x; r[j + 1] += sd.y; r[j + 2] += sd.z; r[j + 3] += sd.w;
                             }
                         }
-                        if (Cfg::STAGE_OUT && mask_src != nullptr) {
-                            float mv[32];
-                            gather(mask_src, c0, mv, true);
-#pragma unroll
-                            for (int j = 0; j < 32; ++j) r[j] = mv[j] > 0.f ? r[j] : 0.f;
-                        } else if (mask_src != nullptr && inb) {
+                        if (mask_src != nullptr && inb) {
 #pragma unroll
                             for (int j = 0; j < 32; j += 4) {
                                 const float4 mk = __ldg(reinterpret_cast<const float4*>(mask_src + rowoff + c0 + j));

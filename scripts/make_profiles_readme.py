@@ -76,6 +76,14 @@ if b:
     t4 = b.get("tiled_4k")
     if t4:
         w("\n`tiled_4k` (configs[3] on one GPU, the whole 3840x2160 image): %.1f iter/s (%.1f ms/step).\n" % (t4["value"], t4["ms_per_step"]))
+q = jline("r2_bench_1gpu_quick_final.json")
+if q:
+    w("\n`r2_bench_1gpu_quick_final.json` (`python bench.py --no-extras --no-parity --no-cpu-baseline`, the LAST build of the round:\n"
+      "staged epilogue stores in the forward and style-gradient convolutions only, section 2's launch list is from the same run):\n"
+      "**%.1f iter/s** (%.3f ms/step), %.1f end to end, convolutions %.1f TFLOP/s.  The full line above and `r2_conv_layers_1024.txt`\n"
+      "were taken one build earlier (the data-gradient kernels of the 64-channel layers staged their stores as well, which this\n"
+      "build undoes because it costs time when the ReLU mask is loaded in the same epilogue, as it is in a train step);\n"
+      "boxes of the pool differ by +-2.5 %%.\n" % (q["value"], q["ms_per_step"], q["e2e"]["value"], q["roofline"]["achieved"]))
 ref = jline("r2_bench_reference_arm.json")
 if ref:
     w("\n`r2_bench_reference_arm.json` (`bench.py --impl reference`): %.3f iter/s on %d threads, kind \"%s\" (%s).\n"
