@@ -244,3 +244,27 @@ def test_tiled_exchange_protocol_gloo(world, tmp_path):
     assert d["pairs"] == list(range(64))
     for r, (ok, ok_sum, n) in enumerate(d["results"]):
         assert ok and ok_sum and n == 3, r
+
+
+def test_bench_deadline_prints_the_line_it_has(tmp_path):
+    """bench.py's guard around the multi-GPU tiled record: when the deadline passes, the rank that owns the line prints it
+    with an error entry in place of tiled_4k and the process ends with status 0 (the other ranks: status 5, no output)."""
+    import json
+    code = ("import sys, time; sys.path.insert(0, %r); import bench\n"
+            "line = {'metric': 'adam_iters_per_sec_1024x1024', 'value': 1.0} if sys.argv[1] == '0' else None\n"
+            "g = bench._Deadline(0.3, line)\n"
+            "time.sleep(30)\n") % ROOT
+    script = tmp_path / "deadline.py"
+    script.write_text(code)
+    r0 = subprocess.run([sys.executable, str(script), "0"], capture_output=True, text=True, timeout=120)
+    assert r0.returncode == 0, r0.stderr
+    d = json.loads(r0.stdout.strip().splitlines()[-1])
+    assert d["value"] == 1.0 and "not finished" in d["tiled_4k"]["error"]
+    r1 = subprocess.run([sys.executable, str(script), "1"], capture_output=True, text=True, timeout=120)
+    assert r1.returncode == 5 and r1.stdout.strip() == ""
+    # a cancelled guard does nothing
+    code2 = ("import sys, time; sys.path.insert(0, %r); import bench\n"
+             "g = bench._Deadline(0.2, {'metric': 'x'}); g.cancel(); time.sleep(0.6); print('alive')\n") % ROOT
+    script.write_text(code2)
+    r2 = subprocess.run([sys.executable, str(script)], capture_output=True, text=True, timeout=120)
+    assert r2.returncode == 0 and r2.stdout.strip() == "alive"

@@ -133,6 +133,23 @@ def test_strips_reproduce_the_whole_image(world):
     assert float((grad_strips - grad).abs().max()) <= 1e-12 * float(grad.abs().max())
 
 
+def test_ragged_height_and_four_strips():
+    """H not a multiple of 16 (VALID pooling drops the odd rows), four strips: two interior ranks with halos on both sides."""
+    img, ws, seeds = _setup(4, H=44, seed=3)
+    acts, grad = _whole(img, ws, seeds)
+    per_rank, grad_strips = _strips(img, ws, seeds, 4, tiled.LEVEL_HALO)
+    for a_loc, t in per_rank:
+        lo, hi = t.own_cols(a_loc[12].shape[3])
+        assert torch.equal(a_loc[12][..., lo:hi], acts[12][..., t.own_lo >> 4:t.own_hi >> 4])
+    assert float((grad_strips - grad).abs().max()) <= 1e-12 * float(grad.abs().max())
+
+
+def test_every_rank_plans_the_same_exchanges():
+    """The mailbox offsets of tiled.PeerHalo are running sums over exchange_plan: it must not depend on the rank."""
+    plans = [tiled.exchange_plan(2160, tiled.Tile(3840, r, 8), 12) for r in range(8)]
+    assert all(p == plans[0] for p in plans) and len(plans[0]) == 11
+
+
 def test_uniform_halos_are_a_special_case():
     """halo 32 / 2^l on level l (what a geometry without per-level offsets needs for block5's two columns)."""
     img, ws, seeds = _setup(2)
